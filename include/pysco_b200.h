@@ -1,0 +1,157 @@
+/*
+ * pysco_b200.h -- C ABI of libpysco_b200.so: the B200 (sm_100a) particle-mesh gravity step for PySCo.
+ *
+ * The reference (mianbreton/pysco 1.0.9) has no FFI layer: its hot path is a set of Numba-jitted
+ * module-level Python functions.  Each entry point below replaces one (or a fused group) of those
+ * functions; the reference file:line it stands in for is cited next to it.  INTEGRATION.md shows
+ * the ctypes binding a PySCo maintainer would add.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _host; no ownership is transferred
+ *     and nothing is allocated behind the caller's back except cuFFT plans (psc_fft_plan_*).
+ *   - scalar grids [N,N,N] float32 C-order (k fastest); vector grids AoS [N,N,N,3]; particles AoS
+ *     [Np,3]; rfft half-spectrum [N,N,N/2+1] complex64 interleaved (same as numpy.fft.rfftn).
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).
+ *   - return value: 0 on success, negative psc_status otherwise; psc_last_error() gives the text.
+ *   - no entry point synchronises the stream unless documented (results that are scalars are
+ *     written to device memory so that callers choose when to read them).
+ */
+#ifndef PYSCO_B200_H
+#define PYSCO_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+  PSC_OK = 0,
+  PSC_ERR_INVALID = -1, /* bad argument (maps to ValueError / NotImplementedError in the Python shim) */
+  PSC_ERR_CUDA = -2,    /* CUDA runtime error */
+  PSC_ERR_CUFFT = -3,   /* cuFFT error */
+  PSC_ERR_WORKSPACE = -4 /* caller-provided scratch too small */
+} psc_status;
+
+/* mass-assignment schemes (param["mass_scheme"], MAS_index = scheme + 1 for CIC/TSC) */
+enum { PSC_NGP = 0, PSC_CIC = 1, PSC_TSC = 2 };
+/* Green's functions: fourier.inverse_laplacian / _compensated / _7pt */
+enum { PSC_GREEN_PLAIN = 0, PSC_GREEN_COMPENSATED = 1, PSC_GREEN_7PT = 2 };
+/* smoother / operator families: laplacian.py, cubic.py (f(R) n=1), quartic.py (f(R) n=2) */
+enum { PSC_OP_LAPLACIAN = 0, PSC_OP_CUBIC = 1, PSC_OP_QUARTIC = 2 };
+/* QUMOND interpolating functions: mond.py:16-162 */
+enum { PSC_MOND_SIMPLE = 0, PSC_MOND_N = 1, PSC_MOND_BETA = 2, PSC_MOND_GAMMA = 3, PSC_MOND_DELTA = 4 };
+
+const char *psc_last_error(void);
+int psc_version(void);
+/* number of kernel launches issued by this library since load (bench.py's gpu_launches claim) */
+int64_t psc_launch_count(void);
+
+/* ---------------------------------------------------------------- particles ---------------- */
+/* morton.positions_to_keys (morton.py:42-137): 21 bits per axis, key = X<<2 | Y<<1 | Z */
+int psc_morton_keys(const float *pos, int64_t np, int64_t *keys, void *stream);
+/* stable argsort of int64 keys, as utils.reorder_particles with nthreads == 1 (utils.py:1019-1075,
+ * np.argsort).  idx_out[i] = source row of sorted row i.  scratch from psc_argsort_workspace_bytes. */
+size_t psc_argsort_workspace_bytes(int64_t np);
+int psc_argsort_keys(const int64_t *keys, int64_t np, int64_t *idx_out, void *scratch,
+                     size_t scratch_bytes, void *stream);
+/* utils.injection_with_indices (utils.py:894-924) on [Np,3] rows: dst[i] = src[idx[i]] */
+int psc_gather3(const int64_t *idx, const float *src, float *dst, int64_t np, void *stream);
+/* utils.add_vector_scalar_inplace (utils.py:264-297): y += a*x.  a_is_f64 selects the float64-scalar
+ * typing of the reference (drift with a snapshot-clamped dt, integration.py:84-85, 252) */
+int psc_axpy(float *y, const float *x, double a, int a_is_f64, int64_t n, void *stream);
+/* utils.periodic_wrap (utils.py:1120-1149) */
+int psc_periodic_wrap(float *x, int64_t n, void *stream);
+/* utils.max_abs (utils.py:220-240): *out = max(*out, max|x|); caller zeroes *out (device float) */
+int psc_max_abs(const float *x, int64_t n, float *out, void *stream);
+/* fused first half of integration.leapfrog (integration.py:250-258): v -= half_dt*a; x += dt*v;
+ * periodic_wrap(x) */
+int psc_kick_drift_wrap(float *pos, float *vel, const float *acc, int64_t np, float half_dt,
+                        double dt, int dt_is_f64, void *stream);
+
+/* ---------------------------------------------------------------- mesh <-> particles ------- */
+/* mesh.NGP/CIC/TSC/TSC_seq (mesh.py:2240-2595) followed by solver.pm's density rescale and
+ * rhs_poisson's affine map (solver.py:114-116, 444-449): rho = f1*(scale*deposit) + f2.
+ * Pass scale = 1, f1 = 1, f2 = 0 for the bare mass assignment.  rho is overwritten. */
+int psc_deposit(const float *pos, int64_t np, int N, int scheme, float scale, float f1, float f2,
+                float *rho, void *stream);
+/* mesh.invNGP/invCIC/invTSC and their _vec forms (mesh.py:2600-3088); ncomp = 1 or 3 */
+int psc_interp(const float *grid, const float *pos, int64_t np, int N, int ncomp, int scheme,
+               float *out, void *stream);
+/* mesh.inv{CIC,TSC}_vec fused with the second half-kick and the two reductions the next
+ * integration.integrate needs (solver.py:205-213; integration.py:262, 293-295, 324-326):
+ * acc = interp(force, pos); vel -= half_dt*acc; maxout[0] = max|acc|, maxout[1] = max|vel|
+ * (maxout is max-combined: caller zeroes it).  half_dt = 0 and vel = NULL gives plain interp+max. */
+int psc_interp_kick(const float *force, const float *pos, float *vel, float *acc, int64_t np, int N,
+                    int scheme, float half_dt, float *maxout, void *stream);
+
+/* ---------------------------------------------------------------- grid algebra ------------- */
+/* utils.linear_operator[_inplace] (utils.py:644-717): out = f1*x + f2 (out may alias x) */
+int psc_linear_operator(const float *x, float f1, float f2, float *out, int64_t n, void *stream);
+/* utils.linear_operator_vectors_inplace (utils.py:721-755): x = f1*x + f2*y */
+int psc_lincomb(float *x, float f1, const float *y, float f2, int64_t n, void *stream);
+/* mesh.derivative / derivative_fR / add_derivative_fR (mesh.py:639-2237).  order in {2,3,5,7};
+ * fr_n = 0 (plain), 1 (a + f*b^2), 2 (a + f*b^3); add != 0: force += f * grad(b^(fr_n+1)) */
+int psc_gradient(const float *a, const float *b, float f, int fr_n, int order, int add, int N,
+                 float *force, void *stream);
+
+/* ---------------------------------------------------------------- Fourier ------------------ */
+/* fourier.fft_3D_real / ifft_3D_real (fourier.py:104-147, 251-294): cuFFT R2C / C2R plans for an
+ * N^3 grid.  C2R overwrites its input (cuFFT semantics) and is UNNORMALISED: fold 1/N^3 into the
+ * `scale` of psc_green / psc_grad_green, or call psc_linear_operator afterwards. */
+int psc_fft_plan_create(int N, void **plan_out);
+int psc_fft_plan_destroy(void *plan);
+size_t psc_fft_plan_workspace_bytes(void *plan);
+int psc_fft_r2c(void *plan, const float *in, float *spec_out, void *stream);
+int psc_fft_c2r(void *plan, float *spec_in, float *out, void *stream);
+/* fourier.ifft_3D_real_grad (fourier.py:372-410): three C2R transforms of an interleaved
+ * [N,N,N/2+1,3] spectrum into an AoS [N,N,N,3] grid */
+int psc_fft_c2r_vec3(void *plan, float *spec3_in, float *out3, void *stream);
+/* fourier.inverse_laplacian / _compensated / _7pt (fourier.py:460-595), in place, DC zeroed;
+ * every mode is additionally multiplied by `scale` */
+int psc_green(float *spec, int N, int kind, int p, float scale, void *stream);
+/* fourier.gradient_inverse_laplacian[_compensated] (fourier.py:606-719): out3[...,d] =
+ * -i k_d/(2 pi k^2) W^-2p spec * scale; p = 0 means uncompensated */
+int psc_grad_green(const float *spec, int N, int p, float scale, float *out3, void *stream);
+/* fourier.fourier_grid_to_Pk (fourier.py:22-100): bins[3][N] (device, double) receive per nearest-
+ * integer |k| bin: sum |k|, sum |delta_k W^-p|^2, mode count; also zeroes spec[0,0,0] like the
+ * reference.  The host shim divides and slices bins 1..int(2*(N/2)/3)-1. bins is overwritten. */
+int psc_pk(float *spec, int N, int p, double *bins, void *stream);
+
+/* ---------------------------------------------------------------- multigrid ---------------- */
+/* laplacian.operator (laplacian.py:12-54) / cubic.operator (cubic.py:23-81) / quartic.operator
+ * (quartic.py:20-77).  kind = PSC_OP_*; b and q ignored for the Laplacian. */
+int psc_operator(const float *x, const float *b, float q, int N, int kind, float *out, void *stream);
+/* laplacian.residual (laplacian.py:63-117): b - Lx;  cubic/quartic.residual_with_rhs
+ * (cubic.py:90-154, quartic.py:86-149): rhs - L(x; b, q) */
+int psc_residual(const float *x, const float *b, float q, const float *rhs, int N, int kind,
+                 float *out, void *stream);
+/* laplacian.restrict_residual (laplacian.py:125-226): coarse = R(b - Lx), fused */
+int psc_restrict_residual(const float *x, const float *b, int N, float *coarse, void *stream);
+/* laplacian.residual_error (laplacian.py:327-381), cubic/quartic.residual_error (cubic.py:844-901,
+ * quartic.py:844-901): *sumsq_out (device double) += sum of squared residuals; caller zeroes it and
+ * takes the square root. */
+int psc_residual_sumsq(const float *x, const float *b, float q, int N, int kind, double *sumsq_out,
+                       void *stream);
+/* sum (fa*a - b)^2 into *sumsq_out: the reductions of laplacian.truncation_error
+ * (laplacian.py:502-533, fa = 1) and cubic/quartic.truncation_error (cubic.py:1021-1061, fa = 4) */
+int psc_diff_sumsq(const float *a, float fa, const float *b, int64_t n, double *sumsq_out, void *stream);
+/* laplacian.initialise_potential (laplacian.py:765-796) kind 0; cubic/quartic.initialise_potential
+ * (cubic.py:217-259, quartic.py:214-260) kinds 1, 2 */
+int psc_initialise_potential(const float *b, float q, int N, int kind, float *out, void *stream);
+/* one red-black SOR sweep: laplacian.gauss_seidel (laplacian.py:844-1022), cubic.gauss_seidel[_with_rhs]
+ * (cubic.py:269-627), quartic.gauss_seidel[_with_rhs] (quartic.py:270-628).  rhs may be NULL. */
+int psc_gauss_seidel(float *x, const float *b, float q, const float *rhs, int N, int kind,
+                     float f_relax, void *stream);
+/* mesh.restriction / minus_restriction (mesh.py:14-108): coarse = sign/8 * sum of 8 children */
+int psc_restriction(const float *x, int N, float sign, float *coarse, void *stream);
+/* mesh.prolongation / add_prolongation (mesh.py:180-453): fine (2Nc) (+)= P(coarse Nc) */
+int psc_prolongation(float *fine, const float *coarse, int Nc, int add, void *stream);
+/* mond.rhs_simple/n/beta/gamma/delta (mond.py:171-932) */
+int psc_mond_rhs(const float *phi, float *out, int N, float g0, int fn, float alpha, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PYSCO_B200_H */

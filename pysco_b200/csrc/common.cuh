@@ -1,0 +1,93 @@
+// common.cuh -- shared helpers for libpysco_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/pysco_b200.h"
+
+namespace psc {
+
+void set_error(const char *fmt, ...);
+void count_launch(int n = 1);
+
+// B200: 148 SMs.  Streaming kernels are launched as grid-stride loops over a multiple of the SM count.
+constexpr int kNumSMs = 148;
+
+#define PSC_CHECK_ARG(cond, msg)                                  \
+  do {                                                            \
+    if (!(cond)) {                                                \
+      psc::set_error("%s: invalid argument: %s", __func__, msg);  \
+      return PSC_ERR_INVALID;                                     \
+    }                                                             \
+  } while (0)
+
+#define PSC_CHECK_LAUNCH()                                                          \
+  do {                                                                              \
+    cudaError_t e__ = cudaGetLastError();                                           \
+    if (e__ != cudaSuccess) {                                                       \
+      psc::set_error("%s: CUDA error: %s", __func__, cudaGetErrorString(e__));      \
+      return PSC_ERR_CUDA;                                                          \
+    }                                                                               \
+  } while (0)
+
+#define PSC_CUDA(call)                                                              \
+  do {                                                                              \
+    cudaError_t e__ = (call);                                                       \
+    if (e__ != cudaSuccess) {                                                       \
+      psc::set_error("%s: %s failed: %s", __func__, #call, cudaGetErrorString(e__)); \
+      return PSC_ERR_CUDA;                                                          \
+    }                                                                               \
+  } while (0)
+
+static inline cudaStream_t as_stream(void *s) { return reinterpret_cast<cudaStream_t>(s); }
+
+// grid size for a grid-stride loop over n items with `block` threads, capped at `waves` CTAs per SM
+static inline int grid_for(int64_t n, int block, int ctas_per_sm = 8) {
+  int64_t need = (n + block - 1) / block;
+  int64_t cap = (int64_t)kNumSMs * ctas_per_sm;
+  if (need < 1) need = 1;
+  return (int)(need < cap ? need : cap);
+}
+
+// periodic index wrap for |offset| < N (the reference relies on numpy negative indexing)
+__device__ __forceinline__ int wrap(int i, int N) {
+  i = i < 0 ? i + N : i;
+  return i >= N ? i - N : i;
+}
+
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+// non-negative floats order like their bit patterns
+__device__ __forceinline__ void atomic_max_nonneg(float *addr, float v) {
+  atomicMax(reinterpret_cast<unsigned int *>(addr), __float_as_uint(v));
+}
+
+// TSC cell + the three 1-D weights of one axis (mesh.py:2502-2522): xp = x*N (float32)
+__device__ __forceinline__ void tsc_axis(float xp, int &c, float &wm, float &w0, float &wp) {
+  c = (int)xp;  // trunc == floor for xp >= 0 (reference: np.int16(xp))
+  float d = xp - 0.5f - (float)c;
+  w0 = 0.75f - d * d;
+  float m = 0.5f - d, p = 0.5f + d;
+  wm = 0.5f * (m * m);
+  wp = 0.5f * (p * p);
+}
+// CIC: second cell offset (sign of d, 0 when d == 0) and weights (mesh.py:2318-2345)
+__device__ __forceinline__ void cic_axis(float xp, int N, int &c, int &c2, float &w, float &w2) {
+  c = (int)xp;
+  float d = xp - 0.5f - (float)c;
+  int s = (d > 0.0f) - (d < 0.0f);
+  w2 = fabsf(d);
+  w = 1.0f - w2;
+  c2 = wrap(c + s, N);
+}
+
+}  // namespace psc

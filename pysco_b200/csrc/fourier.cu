@@ -1,0 +1,267 @@
+// fourier.cu -- FFT Poisson solve: cuFFT for the transforms only; hand-written kernels for the
+// Green's-function multiply (+ deconvolution + normalisation), the spectral gradient and P(k).
+//   fourier.fft_3D_real / ifft_3D_real / ifft_3D_real_grad   fourier.py:104-147, 251-294, 372-410
+//   fourier.inverse_laplacian[_compensated|_7pt]             fourier.py:460-595
+//   fourier.gradient_inverse_laplacian[_compensated]         fourier.py:606-719
+//   fourier.fourier_grid_to_Pk                               fourier.py:22-100
+#include <cufft.h>
+
+#include "common.cuh"
+
+namespace psc {
+
+struct FftPlan {
+  int N;
+  cufftHandle r2c, c2r, c2r_vec3;
+  bool has_vec3;
+  size_t work_bytes;
+};
+
+static const char *cufft_str(cufftResult r) {
+  switch (r) {
+    case CUFFT_SUCCESS: return "CUFFT_SUCCESS";
+    case CUFFT_INVALID_PLAN: return "CUFFT_INVALID_PLAN";
+    case CUFFT_ALLOC_FAILED: return "CUFFT_ALLOC_FAILED";
+    case CUFFT_INVALID_VALUE: return "CUFFT_INVALID_VALUE";
+    case CUFFT_INTERNAL_ERROR: return "CUFFT_INTERNAL_ERROR";
+    case CUFFT_EXEC_FAILED: return "CUFFT_EXEC_FAILED";
+    case CUFFT_SETUP_FAILED: return "CUFFT_SETUP_FAILED";
+    case CUFFT_INVALID_SIZE: return "CUFFT_INVALID_SIZE";
+    default: return "CUFFT_ERROR";
+  }
+}
+#define PSC_CUFFT(call)                                                     \
+  do {                                                                      \
+    cufftResult r__ = (call);                                               \
+    if (r__ != CUFFT_SUCCESS) {                                             \
+      psc::set_error("%s: %s failed: %s", __func__, #call, cufft_str(r__)); \
+      return PSC_ERR_CUFFT;                                                 \
+    }                                                                       \
+  } while (0)
+
+__device__ __forceinline__ float sinc_pi(float x) {
+  // np.sinc(x) = sin(pi x) / (pi x)
+  return x == 0.0f ? 1.0f : sinpif(x) / (3.14159265358979323846f * x);
+}
+__device__ __forceinline__ float inv_pow_int(float w, int e) {
+  // w^(-e), e >= 0 small integer (e = 2p in {0,4,6})
+  float r = 1.0f, iw = 1.0f / w;
+  for (int n = 0; n < e; n++) r *= iw;
+  return r;
+}
+__device__ __forceinline__ float kfreq(int i, int N) { return (float)(i >= (N >> 1) ? i - N : i); }
+
+// One thread per complex mode; rows of N/2+1 modes are contiguous.  8 B read + 8 B write per mode.
+template <int KIND>
+__global__ void __launch_bounds__(256) green_kernel(float2 *__restrict__ spec, int N, int p, float scale) {
+  const int nz = N / 2 + 1;
+  const int64_t total = (int64_t)N * N * nz;
+  const float h = 1.0f / (float)N;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+       t += (int64_t)gridDim.x * blockDim.x) {
+    int k = (int)(t % nz);
+    int64_t r = t / nz;
+    int j = (int)(r % N), i = (int)(r / N);
+    float g;
+    if (KIND == PSC_GREEN_7PT) {
+      // -(h^2/4) / (sin^2(pi h kx) + sin^2(pi h ky) + sin^2(pi h kz))
+      float sx = sinpif(h * kfreq(i, N)), sy = sinpif(h * kfreq(j, N)), sz = sinpif(h * (float)k);
+      g = -(0.25f * h * h) / (sx * sx + sy * sy + sz * sz);
+    } else {
+      float kx = KIND == PSC_GREEN_PLAIN ? (float)(i > (N >> 1) ? N - i : i) : kfreq(i, N);
+      float ky = KIND == PSC_GREEN_PLAIN ? (float)(j > (N >> 1) ? N - j : j) : kfreq(j, N);
+      float kz = (float)k;
+      g = -0.0253302959105844f / (kx * kx + ky * ky + kz * kz);  // -1/(4 pi^2)
+      if (KIND == PSC_GREEN_COMPENSATED) {
+        float w = sinc_pi(kx * h) * sinc_pi(ky * h) * sinc_pi(kz * h);
+        g *= inv_pow_int(w, 2 * p);
+      }
+    }
+    g = (t == 0) ? 0.0f : g * scale;  // DC mode -> 0 (reference: x[0,0,0] = 0 after the division)
+    float2 v = spec[t];
+    v.x *= g;
+    v.y *= g;
+    spec[t] = v;
+  }
+}
+
+// out3[t][d] = -i * k_d / (2 pi k^2) * W^-2p * spec[t] * scale       (8 B read, 24 B write)
+__global__ void __launch_bounds__(256) grad_green_kernel(const float2 *__restrict__ spec, int N, int p,
+                                                         float scale, float2 *__restrict__ out3) {
+  const int nz = N / 2 + 1;
+  const int64_t total = (int64_t)N * N * nz;
+  const float h = 1.0f / (float)N;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+       t += (int64_t)gridDim.x * blockDim.x) {
+    int k = (int)(t % nz);
+    int64_t r = t / nz;
+    int j = (int)(r % N), i = (int)(r / N);
+    float kx = kfreq(i, N), ky = kfreq(j, N), kz = (float)k;
+    float g = 0.159154943091895f / (kx * kx + ky * ky + kz * kz);  // 1/(2 pi)
+    if (p) g *= inv_pow_int(sinc_pi(kx * h) * sinc_pi(ky * h) * sinc_pi(kz * h), 2 * p);
+    g = (t == 0) ? 0.0f : g * scale;
+    float2 v = __ldg(&spec[t]);
+    // -i * (re + i im) = im - i re
+    float tr = g * v.y, ti = -g * v.x;
+    out3[3 * t + 0] = make_float2(tr * kx, ti * kx);
+    out3[3 * t + 1] = make_float2(tr * ky, ti * ky);
+    out3[3 * t + 2] = make_float2(tr * kz, ti * kz);
+  }
+}
+
+// P(k): nearest-integer |k| bins, each stored half-spectrum mode counted once (no Hermitian weight).
+// Per-CTA shared-memory bins (double), flushed with native global double atomics.
+__global__ void __launch_bounds__(256) pk_kernel(float2 *__restrict__ spec, int N, int p,
+                                                 double *__restrict__ bins) {
+  extern __shared__ double sb[];  // [3][N]
+  for (int t = threadIdx.x; t < 3 * N; t += blockDim.x) sb[t] = 0.0;
+  __syncthreads();
+  const int nz = N / 2 + 1;
+  const int64_t total = (int64_t)N * N * nz;
+  const float h = 1.0f / (float)N;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+       t += (int64_t)gridDim.x * blockDim.x) {
+    if (t == 0) {
+      spec[0] = make_float2(0.f, 0.f);  // side effect of the reference kept (fourier.py:61)
+      continue;
+    }
+    int k = (int)(t % nz);
+    int64_t r = t / nz;
+    int j = (int)(r % N), i = (int)(r / N);
+    float kx = kfreq(i, N), ky = kfreq(j, N), kz = (float)k;
+    float w = sinc_pi(kx * h) * sinc_pi(ky * h) * sinc_pi(kz * h);
+    float iw = inv_pow_int(w, p);
+    float2 v = spec[t];
+    double re = (double)v.x * (double)iw, im = (double)v.y * (double)iw;
+    float knorm = sqrtf(kx * kx + ky * ky + kz * kz);
+    int bin = (int)(knorm + 0.5f);
+    if (bin < N) {
+      atomicAdd(&sb[bin], (double)knorm);
+      atomicAdd(&sb[N + bin], re * re + im * im);
+      atomicAdd(&sb[2 * N + bin], 1.0);
+    }
+  }
+  __syncthreads();
+  for (int t = threadIdx.x; t < 3 * N; t += blockDim.x)
+    if (sb[t] != 0.0) atomicAdd(&bins[t], sb[t]);
+}
+
+}  // namespace psc
+
+using namespace psc;
+
+extern "C" {
+
+int psc_fft_plan_create(int N, void **plan_out) {
+  PSC_CHECK_ARG(plan_out, "null plan_out");
+  PSC_CHECK_ARG(N >= 2 && N <= 4096, "N out of range");
+  FftPlan *pl = new FftPlan();
+  pl->N = N;
+  pl->has_vec3 = false;
+  size_t w1 = 0, w2 = 0;
+  PSC_CUFFT(cufftCreate(&pl->r2c));
+  PSC_CUFFT(cufftMakePlan3d(pl->r2c, N, N, N, CUFFT_R2C, &w1));
+  PSC_CUFFT(cufftCreate(&pl->c2r));
+  PSC_CUFFT(cufftMakePlan3d(pl->c2r, N, N, N, CUFFT_C2R, &w2));
+  pl->work_bytes = w1 > w2 ? w1 : w2;
+  *plan_out = pl;
+  return PSC_OK;
+}
+
+int psc_fft_plan_destroy(void *plan) {
+  if (!plan) return PSC_OK;
+  FftPlan *pl = reinterpret_cast<FftPlan *>(plan);
+  cufftDestroy(pl->r2c);
+  cufftDestroy(pl->c2r);
+  if (pl->has_vec3) cufftDestroy(pl->c2r_vec3);
+  delete pl;
+  return PSC_OK;
+}
+
+size_t psc_fft_plan_workspace_bytes(void *plan) {
+  return plan ? reinterpret_cast<FftPlan *>(plan)->work_bytes : 0;
+}
+
+int psc_fft_r2c(void *plan, const float *in, float *spec_out, void *stream) {
+  PSC_CHECK_ARG(plan && in && spec_out, "null pointer");
+  FftPlan *pl = reinterpret_cast<FftPlan *>(plan);
+  PSC_CUFFT(cufftSetStream(pl->r2c, as_stream(stream)));
+  PSC_CUFFT(cufftExecR2C(pl->r2c, const_cast<float *>(in), reinterpret_cast<cufftComplex *>(spec_out)));
+  count_launch(3);
+  return PSC_OK;
+}
+
+int psc_fft_c2r(void *plan, float *spec_in, float *out, void *stream) {
+  PSC_CHECK_ARG(plan && spec_in && out, "null pointer");
+  FftPlan *pl = reinterpret_cast<FftPlan *>(plan);
+  PSC_CUFFT(cufftSetStream(pl->c2r, as_stream(stream)));
+  PSC_CUFFT(cufftExecC2R(pl->c2r, reinterpret_cast<cufftComplex *>(spec_in), out));
+  count_launch(3);
+  return PSC_OK;
+}
+
+int psc_fft_c2r_vec3(void *plan, float *spec3_in, float *out3, void *stream) {
+  PSC_CHECK_ARG(plan && spec3_in && out3, "null pointer");
+  FftPlan *pl = reinterpret_cast<FftPlan *>(plan);
+  if (!pl->has_vec3) {
+    int N = pl->N;
+    int n[3] = {N, N, N};
+    int inembed[3] = {N, N, N / 2 + 1};
+    int onembed[3] = {N, N, N};
+    size_t w = 0;
+    PSC_CUFFT(cufftCreate(&pl->c2r_vec3));
+    PSC_CUFFT(cufftMakePlanMany(pl->c2r_vec3, 3, n, inembed, 3, 1, onembed, 3, 1, CUFFT_C2R, 3, &w));
+    pl->has_vec3 = true;
+  }
+  PSC_CUFFT(cufftSetStream(pl->c2r_vec3, as_stream(stream)));
+  PSC_CUFFT(cufftExecC2R(pl->c2r_vec3, reinterpret_cast<cufftComplex *>(spec3_in), out3));
+  count_launch(9);
+  return PSC_OK;
+}
+
+int psc_green(float *spec, int N, int kind, int p, float scale, void *stream) {
+  PSC_CHECK_ARG(spec, "null pointer");
+  PSC_CHECK_ARG(N >= 2, "N out of range");
+  PSC_CHECK_ARG(kind >= PSC_GREEN_PLAIN && kind <= PSC_GREEN_7PT, "unknown Green's function");
+  PSC_CHECK_ARG(p >= 0 && p <= 8, "MAS index out of range");
+  int64_t total = (int64_t)N * N * (N / 2 + 1);
+  int g = grid_for(total, 256);
+  float2 *s = reinterpret_cast<float2 *>(spec);
+  cudaStream_t st = as_stream(stream);
+  if (kind == PSC_GREEN_PLAIN) green_kernel<PSC_GREEN_PLAIN><<<g, 256, 0, st>>>(s, N, p, scale);
+  else if (kind == PSC_GREEN_COMPENSATED) green_kernel<PSC_GREEN_COMPENSATED><<<g, 256, 0, st>>>(s, N, p, scale);
+  else green_kernel<PSC_GREEN_7PT><<<g, 256, 0, st>>>(s, N, p, scale);
+  count_launch();
+  PSC_CHECK_LAUNCH();
+  return PSC_OK;
+}
+
+int psc_grad_green(const float *spec, int N, int p, float scale, float *out3, void *stream) {
+  PSC_CHECK_ARG(spec && out3, "null pointer");
+  PSC_CHECK_ARG(N >= 2, "N out of range");
+  PSC_CHECK_ARG(p >= 0 && p <= 8, "MAS index out of range");
+  int64_t total = (int64_t)N * N * (N / 2 + 1);
+  grad_green_kernel<<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(
+      reinterpret_cast<const float2 *>(spec), N, p, scale, reinterpret_cast<float2 *>(out3));
+  count_launch();
+  PSC_CHECK_LAUNCH();
+  return PSC_OK;
+}
+
+int psc_pk(float *spec, int N, int p, double *bins, void *stream) {
+  PSC_CHECK_ARG(spec && bins, "null pointer");
+  PSC_CHECK_ARG(N >= 2 && N <= 2048, "N out of range");
+  PSC_CHECK_ARG(p >= 0 && p <= 8, "MAS index out of range");
+  cudaStream_t st = as_stream(stream);
+  PSC_CUDA(cudaMemsetAsync(bins, 0, sizeof(double) * 3 * N, st));
+  int64_t total = (int64_t)N * N * (N / 2 + 1);
+  size_t smem = sizeof(double) * 3 * N;
+  if (smem > 48 * 1024)
+    PSC_CUDA(cudaFuncSetAttribute(pk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  pk_kernel<<<grid_for(total, 256, 2), 256, smem, st>>>(reinterpret_cast<float2 *>(spec), N, p, bins);
+  count_launch();
+  PSC_CHECK_LAUNCH();
+  return PSC_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,542 @@
+// multigrid.cu -- 7-point-stencil kernels of the multigrid solvers.
+//   laplacian.py: operator :12, residual :63, restrict_residual :125, residual_error :327,
+//                 initialise_potential :765, gauss_seidel :844
+//   cubic.py / quartic.py: operator, residual_with_rhs, initialise_potential, gauss_seidel[_with_rhs],
+//                 residual_error, solution_cubic_equation (cubic.py:162-207, float64),
+//                 solution_quartic_equation (quartic.py:157-204, float64)
+//   mesh.py: restriction :14, minus_restriction :62, prolongation :180, add_prolongation :334
+//   mond.py: rhs_simple/n/beta/gamma/delta :171-932
+//
+// Thread mapping: threadIdx.x walks k (fastest axis, coalesced 128-byte rows), blockIdx.y/z carry
+// (j, i) tiles; neighbour rows come through L1/L2 (each row is re-read by its 4 lateral neighbours
+// of the same CTA).  Reductions: warp shuffle -> one double atomic per CTA.
+#include "common.cuh"
+
+namespace psc {
+
+constexpr int TJ = 4;  // rows (j) per CTA
+constexpr int TKX = 64;  // k-threads per CTA
+
+__device__ __forceinline__ float npow(float v, int kind) {
+  return kind == PSC_OP_CUBIC ? v * v : v * v * v;
+}
+
+struct Cell {
+  int i, j, k;
+  size_t t;
+  bool ok;
+};
+
+__device__ __forceinline__ Cell this_cell(int N) {
+  Cell c;
+  c.k = blockIdx.x * TKX + threadIdx.x;
+  c.j = blockIdx.y * TJ + threadIdx.y;
+  c.i = blockIdx.z;
+  c.ok = c.k < N && c.j < N;
+  c.t = ((size_t)c.i * N + c.j) * N + c.k;
+  return c;
+}
+
+// sum of the six neighbours (optionally of their squares / cubes)
+template <int KIND>
+__device__ __forceinline__ float nb6(const float *__restrict__ x, int i, int j, int k, int N) {
+  const size_t N2 = (size_t)N * N;
+  const size_t ri = (size_t)i * N2, rj = (size_t)j * N;
+  float a = x[(size_t)wrap(i - 1, N) * N2 + rj + k];
+  float b = x[ri + (size_t)wrap(j - 1, N) * N + k];
+  float c = x[ri + rj + wrap(k - 1, N)];
+  float d = x[ri + rj + wrap(k + 1, N)];
+  float e = x[ri + (size_t)wrap(j + 1, N) * N + k];
+  float f = x[(size_t)wrap(i + 1, N) * N2 + rj + k];
+  if (KIND == PSC_OP_LAPLACIAN) return a + b + c + d + e + f;
+  return npow(a, KIND) + npow(b, KIND) + npow(c, KIND) + npow(d, KIND) + npow(e, KIND) + npow(f, KIND);
+}
+
+// L(x) at one cell.  Laplacian: (sum6 - 6x) N^2.  f(R): x^(n+2) + p x + q h^2, p = h^2 b - sum6(x^(n+1))/6
+template <int KIND>
+__device__ __forceinline__ float op_at(const float *__restrict__ x, const float *__restrict__ b, float q,
+                                       int i, int j, int k, size_t t, int N) {
+  if (KIND == PSC_OP_LAPLACIAN) {
+    const float invh2 = (float)N * (float)N;
+    return (nb6<KIND>(x, i, j, k, N) - 6.0f * x[t]) * invh2;
+  } else {
+    const float h2 = 1.0f / ((float)N * (float)N);
+    const float invsix = 1.0f / 6.0f;
+    float p = h2 * b[t] - invsix * nb6<KIND>(x, i, j, k, N);
+    float xt = x[t];
+    float lead = KIND == PSC_OP_CUBIC ? xt * xt * xt : (xt * xt) * (xt * xt);
+    return lead + p * xt + q * h2;
+  }
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(TKX *TJ) operator_kernel(const float *__restrict__ x,
+                                                           const float *__restrict__ b, float q, int N,
+                                                           float *__restrict__ out) {
+  Cell c = this_cell(N);
+  if (c.ok) out[c.t] = op_at<KIND>(x, b, q, c.i, c.j, c.k, c.t, N);
+}
+
+// Laplacian: out = b - Lx.   f(R): out = rhs - L(x)
+template <int KIND>
+__global__ void __launch_bounds__(TKX *TJ) residual_kernel(const float *__restrict__ x,
+                                                           const float *__restrict__ b, float q,
+                                                           const float *__restrict__ rhs, int N,
+                                                           float *__restrict__ out) {
+  Cell c = this_cell(N);
+  if (!c.ok) return;
+  float L = op_at<KIND>(x, b, q, c.i, c.j, c.k, c.t, N);
+  out[c.t] = (KIND == PSC_OP_LAPLACIAN) ? (-L + b[c.t]) : (-L + rhs[c.t]);
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(TKX *TJ) residual_sumsq_kernel(const float *__restrict__ x,
+                                                                 const float *__restrict__ b, float q, int N,
+                                                                 double *__restrict__ out) {
+  Cell c = this_cell(N);
+  double s = 0.0;
+  if (c.ok) {
+    float L = op_at<KIND>(x, b, q, c.i, c.j, c.k, c.t, N);
+    float r = (KIND == PSC_OP_LAPLACIAN) ? (-L + b[c.t]) : L;
+    s = (double)r * (double)r;
+  }
+  s = warp_sum(s);
+  __shared__ double sm[TKX * TJ / 32];
+  int tid = threadIdx.y * TKX + threadIdx.x;
+  if ((tid & 31) == 0) sm[tid >> 5] = s;
+  __syncthreads();
+  if (tid == 0) {
+    double tot = 0.0;
+#pragma unroll
+    for (int w = 0; w < TKX * TJ / 32; w++) tot += sm[w];
+    atomicAdd(out, tot);
+  }
+}
+
+__global__ void __launch_bounds__(256) diff_sumsq_kernel(const float *__restrict__ a, float fa,
+                                                         const float *__restrict__ b, int64_t n,
+                                                         double *__restrict__ out) {
+  double s = 0.0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    float d = fa * a[i] - b[i];
+    s += (double)d * (double)d;
+  }
+  s = warp_sum(s);
+  __shared__ double sm[8];
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double tot = 0.0;
+#pragma unroll
+    for (int w = 0; w < 8; w++) tot += sm[w];
+    atomicAdd(out, tot);
+  }
+}
+
+// coarse[i,j,k] = 1/8 sum_{2^3 children} (b - Lx): thread per coarse cell, children evaluated in place
+__global__ void __launch_bounds__(TKX *TJ) restrict_residual_kernel(const float *__restrict__ x,
+                                                                    const float *__restrict__ b, int N,
+                                                                    float *__restrict__ coarse) {
+  const int Nc = N >> 1;
+  Cell c = this_cell(Nc);
+  if (!c.ok) return;
+  const float invh2 = (float)N * (float)N;
+  const size_t N2 = (size_t)N * N;
+  float outer = 0.0f, inner = 0.0f, bs = 0.0f;
+#pragma unroll
+  for (int a = 0; a < 2; a++)
+#pragma unroll
+    for (int e = 0; e < 2; e++)
+#pragma unroll
+      for (int g = 0; g < 2; g++) {
+        int ii = 2 * c.i + a, jj = 2 * c.j + e, kk = 2 * c.k + g;
+        size_t t = (size_t)ii * N2 + (size_t)jj * N + kk;
+        outer += x[(size_t)wrap(ii + (a ? 1 : -1), N) * N2 + (size_t)jj * N + kk] +
+                 x[(size_t)ii * N2 + (size_t)wrap(jj + (e ? 1 : -1), N) * N + kk] +
+                 x[(size_t)ii * N2 + (size_t)jj * N + wrap(kk + (g ? 1 : -1), N)];
+        inner += x[t];
+        bs += b[t];
+      }
+  coarse[c.t] = 0.125f * (-(outer - 3.0f * inner) * invh2 + bs);
+}
+
+__global__ void __launch_bounds__(TKX *TJ) restriction_kernel(const float *__restrict__ x, int N, float f,
+                                                              float *__restrict__ coarse) {
+  const int Nc = N >> 1;
+  Cell c = this_cell(Nc);
+  if (!c.ok) return;
+  const size_t N2 = (size_t)N * N;
+  const float *p = x + (size_t)(2 * c.i) * N2 + (size_t)(2 * c.j) * N + 2 * c.k;
+  float2 r00 = *reinterpret_cast<const float2 *>(p);
+  float2 r01 = *reinterpret_cast<const float2 *>(p + N);
+  float2 r10 = *reinterpret_cast<const float2 *>(p + N2);
+  float2 r11 = *reinterpret_cast<const float2 *>(p + N2 + N);
+  coarse[c.t] = f * (r00.x + r00.y + r01.x + r01.y + r10.x + r10.y + r11.x + r11.y);
+}
+
+// thread per COARSE cell: reads its 27-neighbourhood once, writes (or adds to) its 8 children
+template <bool ADD>
+__global__ void __launch_bounds__(TKX *TJ) prolongation_kernel(float *__restrict__ fine,
+                                                               const float *__restrict__ coarse, int Nc) {
+  Cell c = this_cell(Nc);
+  if (!c.ok) return;
+  const int N = 2 * Nc;
+  const size_t Nc2 = (size_t)Nc * Nc, N2 = (size_t)N * N;
+  const float f0 = 27.0f / 64, f1 = 9.0f / 64, f2 = 3.0f / 64, f3 = 1.0f / 64;
+  float v[3][3][3];
+#pragma unroll
+  for (int a = 0; a < 3; a++)
+#pragma unroll
+    for (int e = 0; e < 3; e++)
+#pragma unroll
+      for (int g = 0; g < 3; g++)
+        v[a][e][g] = coarse[(size_t)wrap(c.i + a - 1, Nc) * Nc2 + (size_t)wrap(c.j + e - 1, Nc) * Nc +
+                            wrap(c.k + g - 1, Nc)];
+  const float t0 = f0 * v[1][1][1];
+#pragma unroll
+  for (int a = 0; a < 2; a++)
+#pragma unroll
+    for (int e = 0; e < 2; e++) {
+      float r[2];
+#pragma unroll
+      for (int g = 0; g < 2; g++) {
+        int A = 2 * a, E = 2 * e, G = 2 * g;
+        r[g] = t0 + f1 * (v[A][1][1] + v[1][E][1] + v[1][1][G]) +
+               f2 * (v[A][E][1] + v[1][E][G] + v[A][1][G]) + f3 * v[A][E][G];
+      }
+      float2 *dst = reinterpret_cast<float2 *>(fine + (size_t)(2 * c.i + a) * N2 +
+                                               (size_t)(2 * c.j + e) * N + 2 * c.k);
+      if (ADD) {
+        float2 old = *dst;
+        *dst = make_float2(old.x + r[0], old.y + r[1]);
+      } else {
+        *dst = make_float2(r[0], r[1]);
+      }
+    }
+}
+
+// ------------------------------------------------------------------------- f(R) root solvers
+__device__ __forceinline__ float solve_cubic(float pf, float d1f) {
+  // cubic.py:162-207 (float64 inside, float32 in/out)
+  const double inv3 = 1.0 / 3;
+  double d1 = (double)d1f, p = (double)pf;
+  double d = d1 * d1 + 108.0 * (p * p * p);
+  if (d > 0.0) {
+    d = d1 + sqrt(d);
+    if (d == 0.0) return (float)(-inv3 * pow(d1, inv3));
+    double C = pow(0.5 * d, inv3);
+    return (float)(-inv3 * (C - 3.0 * p / C));
+  } else if (d < 0.0) {
+    double d0 = -3.0 * p;
+    double s0 = sqrt(d0);
+    d = d1 / (2.0 * (d0 * s0));
+    if (fabs(d) < 1.0) {
+      double theta = acos(d);
+      return (float)(-2.0 * inv3 * s0 * cos(inv3 * (theta + 2.0 * 3.14159265358979323846)));
+    }
+    return (float)(-inv3 * pow(d1, inv3));
+  }
+  return (float)(-inv3 * pow(d1, inv3));
+}
+__device__ __forceinline__ float solve_quartic(float pf, float qf) {
+  // quartic.py:157-204
+  double pp = (double)pf, qq = (double)qf;
+  if (pp == 0.0) return (float)pow(-qq, 0.25);
+  const double inv3 = 1.0 / 3.0;
+  double d0 = 12.0 * qq;
+  double d1 = 27.0 * (pp * pp);
+  double r = d0 / d1;
+  double sqrt_term = 1.0 - 4.0 * d0 * (r * r);
+  if (sqrt_term < 0.0) return (float)pow(-qq, 0.25);
+  double Q = pow(0.5 * d1 * (1.0 + sqrt(sqrt_term)), inv3);
+  double Qd = Q + d0 / Q;
+  if (Qd > 0.0) {
+    double S = 0.5 * sqrt(Qd * inv3);
+    if (pp > 0.0) return (float)(-S + 0.5 * sqrt(-4.0 * (S * S) + pp / S));
+    return (float)(S + 0.5 * sqrt(-4.0 * (S * S) - pp / S));
+  }
+  return (float)pow(-qq, 0.25);
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(256) init_potential_kernel(const float *__restrict__ b, float q, int N,
+                                                             float *__restrict__ out, int64_t n) {
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n;
+       t += (int64_t)gridDim.x * blockDim.x) {
+    if (KIND == PSC_OP_LAPLACIAN) {
+      const float h = 1.0f / (float)N;
+      const float c = (float)(-(double)h * (double)h / 6.0);
+      out[t] = c * b[t];
+    } else if (KIND == PSC_OP_CUBIC) {
+      // cubic.py:247-258
+      const float h2 = 1.0f / ((float)N * (float)N);
+      const float threeh2 = 3.0f * h2;
+      const double d1 = 27.0 * (double)h2 * (double)q;
+      float d0 = -threeh2 * b[t];
+      double d03 = (double)d0 * (double)d0 * (double)d0;
+      double C = cbrt(0.5 * (d1 + sqrt(d1 * d1 - 4.0 * d03)));
+      out[t] = (float)(-(1.0 / 3) * (C + (double)d0 / C));
+    } else {
+      // quartic.py:241-259
+      const double h2 = 1.0 / ((double)N * (double)N);
+      const double inv3 = 1.0 / 3;
+      const double d0 = 12.0 * h2 * (double)q;
+      double p = h2 * (double)b[t];
+      double d1 = 27.0 * (p * p);
+      double Q = pow(0.5 * (d1 + sqrt(d1 * d1 - 4.0 * (d0 * d0 * d0))), inv3);
+      double S = 0.5 * sqrt((Q + d0 / Q) * inv3);
+      out[t] = (float)(-S + 0.5 * sqrt(-4.0 * (S * S) + p / S));
+    }
+  }
+}
+
+// One colour of a red-black SOR sweep.  colour = 1: odd i+j+k ("red" in the reference, first),
+// colour = 0: even ("black").  Thread per updated cell: threadIdx.x walks k in steps of 2.
+template <int KIND>
+__global__ void __launch_bounds__(TKX *TJ) gs_colour_kernel(float *__restrict__ x,
+                                                            const float *__restrict__ b, float q,
+                                                            const float *__restrict__ rhs, int N,
+                                                            float f_relax, int colour) {
+  const int kh = blockIdx.x * TKX + threadIdx.x;
+  const int j = blockIdx.y * TJ + threadIdx.y;
+  const int i = blockIdx.z;
+  const int k = 2 * kh + ((i + j + colour) & 1);
+  if (k >= N || j >= N) return;
+  const size_t t = ((size_t)i * N + j) * N + k;
+  const float h2 = 1.0f / ((float)N * (float)N);
+  const float invsix = 1.0f / 6.0f;
+  float xt = x[t];
+  float s = nb6<KIND>(x, i, j, k, N);
+  float target;
+  if (KIND == PSC_OP_LAPLACIAN) {
+    target = (s - h2 * b[t]) * invsix;
+  } else {
+    float p = h2 * b[t] - invsix * s;
+    if (KIND == PSC_OP_CUBIC) {
+      float d1 = 27.0f * h2 * q;
+      if (rhs) d1 -= 27.0f * rhs[t];
+      target = solve_cubic(p, d1);
+    } else {
+      float qq = q * h2;
+      if (rhs) qq -= rhs[t];
+      target = solve_quartic(p, qq);
+    }
+  }
+  x[t] = xt + f_relax * (target - xt);
+}
+
+// ----------------------------------------------------------------------------------- MOND
+template <int FN>
+__device__ __forceinline__ float mond_nu(float y, float alpha) {
+  if (FN == PSC_MOND_SIMPLE) return 0.5f + sqrtf(0.25f + 1.0f / y);
+  if (FN == PSC_MOND_N) {
+    int n = (int)alpha;
+    return powf(0.5f + sqrtf(0.25f + powf(y, (float)(-n))), 1.0f / (float)n);
+  }
+  if (FN == PSC_MOND_BETA) {
+    float e = expf(-y);
+    float nu = alpha * e;
+    float om = 1.0f - e;
+    if (om > 0.0f) nu += rsqrtf(om);
+    return nu;
+  }
+  if (FN == PSC_MOND_GAMMA) {
+    float e = expf(-powf(y, 0.5f * alpha));
+    return powf(1.0f - e, -1.0f / alpha) + (1.0f - 1.0f / alpha) * e;
+  }
+  return powf(1.0f - expf(-powf(y, 0.5f * alpha)), -1.0f / alpha);
+}
+
+template <int FN>
+__global__ void __launch_bounds__(TKX *TJ) mond_rhs_kernel(const float *__restrict__ phi,
+                                                           float *__restrict__ out, int N, float g0,
+                                                           float alpha) {
+  Cell c = this_cell(N);
+  if (!c.ok) return;
+  const size_t N2 = (size_t)N * N;
+  const float inv_g0 = 1.0f / g0;
+  const float invh = (float)N, inv4h = 0.25f * (float)N;
+  const int i = c.i, j = c.j, k = c.k;
+  const size_t ri[3] = {(size_t)wrap(i - 1, N) * N2, (size_t)i * N2, (size_t)wrap(i + 1, N) * N2};
+  const size_t rj[3] = {(size_t)wrap(j - 1, N) * N, (size_t)j * N, (size_t)wrap(j + 1, N) * N};
+  const int rk[3] = {wrap(k - 1, N), k, wrap(k + 1, N)};
+#define P(a, e, g) phi[ri[(a) + 1] + rj[(e) + 1] + rk[(g) + 1]]
+  float p0 = P(0, 0, 0);
+  // Point A at -h/2, point B at +h/2 along each axis (mond.py:209-300)
+  float Axx = invh * (p0 - P(-1, 0, 0));
+  float Axy = inv4h * (P(0, 1, 0) - P(0, -1, 0) + P(-1, 1, 0) - P(-1, -1, 0));
+  float Axz = inv4h * (P(0, 0, 1) - P(0, 0, -1) + P(-1, 0, 1) - P(-1, 0, -1));
+  float fAx = sqrtf(Axx * Axx + Axy * Axy + Axz * Axz);
+  float Bxx = invh * (-p0 + P(1, 0, 0));
+  float Bxy = inv4h * (P(1, 1, 0) - P(1, -1, 0) + P(0, 1, 0) - P(0, -1, 0));
+  float Bxz = inv4h * (P(1, 0, 1) - P(1, 0, -1) + P(0, 0, 1) - P(0, 0, -1));
+  float fBx = sqrtf(Bxx * Bxx + Bxy * Bxy + Bxz * Bxz);
+  float Ayy = invh * (p0 - P(0, -1, 0));
+  float Ayx = inv4h * (P(1, 0, 0) - P(-1, 0, 0) + P(1, -1, 0) - P(-1, -1, 0));
+  float Ayz = inv4h * (P(0, 0, 1) - P(0, 0, -1) + P(0, -1, 1) - P(0, -1, -1));
+  float fAy = sqrtf(Ayx * Ayx + Ayy * Ayy + Ayz * Ayz);
+  float Byy = invh * (-p0 + P(0, 1, 0));
+  float Byx = inv4h * (P(1, 1, 0) - P(-1, 1, 0) + P(1, 0, 0) - P(-1, 0, 0));
+  float Byz = inv4h * (P(0, 1, 1) - P(0, 1, -1) + P(0, 0, 1) - P(0, 0, -1));
+  float fBy = sqrtf(Byx * Byx + Byy * Byy + Byz * Byz);
+  float Azz = invh * (p0 - P(0, 0, -1));
+  float Azx = inv4h * (P(1, 0, 0) - P(-1, 0, 0) + P(1, 0, -1) - P(-1, 0, -1));
+  float Azy = inv4h * (P(0, 1, 0) - P(0, -1, 0) + P(0, 1, -1) - P(0, -1, -1));
+  float fAz = sqrtf(Azx * Azx + Azy * Azy + Azz * Azz);
+  float Bzz = invh * (-p0 + P(0, 0, 1));
+  float Bzx = inv4h * (P(1, 0, 1) - P(-1, 0, 1) + P(1, 0, 0) - P(-1, 0, 0));
+  float Bzy = inv4h * (P(0, 1, 1) - P(0, -1, 1) + P(0, 1, 0) - P(0, -1, 0));
+  float fBz = sqrtf(Bzx * Bzx + Bzy * Bzy + Bzz * Bzz);
+#undef P
+  float r = mond_nu<FN>(fBx * inv_g0, alpha) * Bxx - mond_nu<FN>(fAx * inv_g0, alpha) * Axx +
+            mond_nu<FN>(fBy * inv_g0, alpha) * Byy - mond_nu<FN>(fAy * inv_g0, alpha) * Ayy +
+            mond_nu<FN>(fBz * inv_g0, alpha) * Bzz - mond_nu<FN>(fAz * inv_g0, alpha) * Azz;
+  out[c.t] = invh * r;
+}
+
+static inline dim3 cell_grid(int N) { return dim3((N + TKX - 1) / TKX, (N + TJ - 1) / TJ, N); }
+static inline dim3 cell_block() { return dim3(TKX, TJ, 1); }
+
+}  // namespace psc
+
+using namespace psc;
+
+#define PSC_KIND_SWITCH(kind, CALL)                     \
+  if ((kind) == PSC_OP_LAPLACIAN) { CALL(PSC_OP_LAPLACIAN); } \
+  else if ((kind) == PSC_OP_CUBIC) { CALL(PSC_OP_CUBIC); }    \
+  else { CALL(PSC_OP_QUARTIC); }
+
+#define PSC_CHECK_GRID(N) PSC_CHECK_ARG((N) >= 2 && (N) <= 32767 && ((N) % 2) == 0, "N must be even, 2..32766")
+#define PSC_CHECK_KIND(kind) \
+  PSC_CHECK_ARG((kind) >= PSC_OP_LAPLACIAN && (kind) <= PSC_OP_QUARTIC, "unknown operator kind")
+
+extern "C" {
+
+int psc_operator(const float *x, const float *b, float q, int N, int kind, float *out, void *stream) {
+  PSC_CHECK_GRID(N);
+  PSC_CHECK_KIND(kind);
+  PSC_CHECK_ARG(x && out && (b || kind == PSC_OP_LAPLACIAN), "null pointer");
+#define CALL(K) operator_kernel<K><<<cell_grid(N), cell_block(), 0, as_stream(stream)>>>(x, b, q, N, out)
+  PSC_KIND_SWITCH(kind, CALL)
+#undef CALL
+  count_launch();
+  PSC_CHECK_LAUNCH();
+  return PSC_OK;
+}
+
+int psc_residual(const float *x, const float *b, float q, const float *rhs, int N, int kind, float *out,
+                 void *stream) {
+  PSC_CHECK_GRID(N);
+  PSC_CHECK_KIND(kind);
+  PSC_CHECK_ARG(x && b && out && (rhs || kind == PSC_OP_LAPLACIAN), "null pointer");
+#define CALL(K) residual_kernel<K><<<cell_grid(N), cell_block(), 0, as_stream(stream)>>>(x, b, q, rhs, N, out)
+  PSC_KIND_SWITCH(kind, CALL)
+#undef CALL
+  count_launch();
+  PSC_CHECK_LAUNCH();
+  return PSC_OK;
+}
+
+int psc_restrict_residual(const float *x, const float *b, int N, float *coarse, void *stream) {
+  PSC_CHECK_GRID(N);
+  PSC_CHECK_ARG(x && b && coarse, "null pointer");
+  restrict_residual_kernel<<<cell_grid(N / 2), cell_block(), 0, as_stream(stream)>>>(x, b, N, coarse);
+  count_launch();
+  PSC_CHECK_LAUNCH();
+  return PSC_OK;
+}
+
+int psc_residual_sumsq(const float *x, const float *b, float q, int N, int kind, double *sumsq_out,
+                       void *stream) {
+  PSC_CHECK_GRID(N);
+  PSC_CHECK_KIND(kind);
+  PSC_CHECK_ARG(x && b && sumsq_out, "null pointer");
+#define CALL(K) residual_sumsq_kernel<K><<<cell_grid(N), cell_block(), 0, as_stream(stream)>>>(x, b, q, N, sumsq_out)
+  PSC_KIND_SWITCH(kind, CALL)
+#undef CALL
+  count_launch();
+  PSC_CHECK_LAUNCH();
+  return PSC_OK;
+}
+
+int psc_diff_sumsq(const float *a, float fa, const float *b, int64_t n, double *sumsq_out, void *stream) {
+  PSC_CHECK_ARG(n >= 0, "n < 0");
+  PSC_CHECK_ARG(a && b && sumsq_out, "null pointer");
+  if (n == 0) return PSC_OK;
+  diff_sumsq_kernel<<<grid_for(n, 256, 4), 256, 0, as_stream(stream)>>>(a, fa, b, n, sumsq_out);
+  count_launch();
+  PSC_CHECK_LAUNCH();
+  return PSC_OK;
+}
+
+int psc_initialise_potential(const float *b, float q, int N, int kind, float *out, void *stream) {
+  PSC_CHECK_ARG(N >= 1 && N <= 32767, "N out of range");
+  PSC_CHECK_KIND(kind);
+  PSC_CHECK_ARG(b && out, "null pointer");
+  int64_t n = (int64_t)N * N * N;
+#define CALL(K) init_potential_kernel<K><<<grid_for(n, 256), 256, 0, as_stream(stream)>>>(b, q, N, out, n)
+  PSC_KIND_SWITCH(kind, CALL)
+#undef CALL
+  count_launch();
+  PSC_CHECK_LAUNCH();
+  return PSC_OK;
+}
+
+int psc_gauss_seidel(float *x, const float *b, float q, const float *rhs, int N, int kind, float f_relax,
+                     void *stream) {
+  PSC_CHECK_GRID(N);
+  PSC_CHECK_KIND(kind);
+  PSC_CHECK_ARG(x && b, "null pointer");
+  dim3 grid((N / 2 + TKX - 1) / TKX, (N + TJ - 1) / TJ, N);
+  for (int colour = 1; colour >= 0; colour--) {
+#define CALL(K) gs_colour_kernel<K><<<grid, cell_block(), 0, as_stream(stream)>>>(x, b, q, rhs, N, f_relax, colour)
+    PSC_KIND_SWITCH(kind, CALL)
+#undef CALL
+    count_launch();
+  }
+  PSC_CHECK_LAUNCH();
+  return PSC_OK;
+}
+
+int psc_restriction(const float *x, int N, float sign, float *coarse, void *stream) {
+  PSC_CHECK_GRID(N);
+  PSC_CHECK_ARG(x && coarse, "null pointer");
+  restriction_kernel<<<cell_grid(N / 2), cell_block(), 0, as_stream(stream)>>>(x, N, sign * 0.125f, coarse);
+  count_launch();
+  PSC_CHECK_LAUNCH();
+  return PSC_OK;
+}
+
+int psc_prolongation(float *fine, const float *coarse, int Nc, int add, void *stream) {
+  PSC_CHECK_ARG(Nc >= 1 && Nc <= 16383, "Nc out of range");
+  PSC_CHECK_ARG(fine && coarse, "null pointer");
+  if (add)
+    prolongation_kernel<true><<<cell_grid(Nc), cell_block(), 0, as_stream(stream)>>>(fine, coarse, Nc);
+  else
+    prolongation_kernel<false><<<cell_grid(Nc), cell_block(), 0, as_stream(stream)>>>(fine, coarse, Nc);
+  count_launch();
+  PSC_CHECK_LAUNCH();
+  return PSC_OK;
+}
+
+int psc_mond_rhs(const float *phi, float *out, int N, float g0, int fn, float alpha, void *stream) {
+  PSC_CHECK_ARG(N >= 2 && N <= 32767, "N out of range");
+  PSC_CHECK_ARG(phi && out && phi != out, "null or aliased pointer");
+  PSC_CHECK_ARG(fn >= PSC_MOND_SIMPLE && fn <= PSC_MOND_DELTA, "unknown MOND interpolating function");
+  cudaStream_t st = as_stream(stream);
+#define CALL(F) mond_rhs_kernel<F><<<cell_grid(N), cell_block(), 0, st>>>(phi, out, N, g0, alpha)
+  switch (fn) {
+    case PSC_MOND_SIMPLE: CALL(PSC_MOND_SIMPLE); break;
+    case PSC_MOND_N: CALL(PSC_MOND_N); break;
+    case PSC_MOND_BETA: CALL(PSC_MOND_BETA); break;
+    case PSC_MOND_GAMMA: CALL(PSC_MOND_GAMMA); break;
+    default: CALL(PSC_MOND_DELTA); break;
+  }
+#undef CALL
+  count_launch();
+  PSC_CHECK_LAUNCH();
+  return PSC_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,286 @@
+// particles.cu -- particle-array kernels: Morton keys, reorder, leapfrog vector ops.
+// HBM-bound streaming kernels: 128-bit loads/stores, grid-stride over a multiple of 148 SMs.
+#include <cub/device/device_radix_sort.cuh>
+
+#include "common.cuh"
+
+namespace psc {
+
+// ---------------------------------------------------------------------------- Morton keys
+// morton.py:42-77: 21-bit magic-mask spread
+__device__ __forceinline__ unsigned long long spread21(unsigned long long x) {
+  x &= 0x1FFFFFull;
+  x = (x | x << 32) & 0x1F00000000FFFFull;
+  x = (x | x << 16) & 0x1F0000FF0000FFull;
+  x = (x | x << 8) & 0x100F00F00F00F00Full;
+  x = (x | x << 4) & 0x10C30C30C30C30C3ull;
+  x = (x | x << 2) & 0x1249249249249249ull;
+  return x;
+}
+
+__global__ void __launch_bounds__(256) morton_keys_kernel(const float *__restrict__ pos, int64_t np,
+                                                          int64_t *__restrict__ keys) {
+  for (int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; n < np;
+       n += (int64_t)gridDim.x * blockDim.x) {
+    // x * 2^21 is exact in float32; floor then & 0x1FFFFF (two's complement for negatives, as
+    // numpy int64 & does)
+    long long xi = (long long)floorf(pos[3 * n + 0] * 2097152.0f);
+    long long yi = (long long)floorf(pos[3 * n + 1] * 2097152.0f);
+    long long zi = (long long)floorf(pos[3 * n + 2] * 2097152.0f);
+    unsigned long long k = spread21((unsigned long long)xi) << 2 |
+                           spread21((unsigned long long)yi) << 1 | spread21((unsigned long long)zi);
+    keys[n] = (int64_t)k;
+  }
+}
+
+__global__ void __launch_bounds__(256) iota_kernel(int64_t *idx, int64_t np) {
+  for (int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; n < np;
+       n += (int64_t)gridDim.x * blockDim.x)
+    idx[n] = n;
+}
+
+__global__ void __launch_bounds__(256) gather3_kernel(const int64_t *__restrict__ idx,
+                                                      const float *__restrict__ src,
+                                                      float *__restrict__ dst, int64_t np) {
+  // one thread per output float: consecutive threads write consecutive floats (coalesced stores);
+  // the gathered reads are 12-byte rows, consecutive in a Morton-sorted permutation's runs.
+  int64_t total = 3 * np;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+       t += (int64_t)gridDim.x * blockDim.x) {
+    int64_t row = t / 3;
+    int c = (int)(t - 3 * row);
+    dst[t] = __ldg(&src[3 * idx[row] + c]);
+  }
+}
+
+// ---------------------------------------------------------------------------- vector ops
+__device__ __forceinline__ float wrap01(float t) {
+  // utils.py:1131-1149: tiny negatives snap to 0 (t + 1 would round to 1.0), else shift by one box
+  const double eps = -2.98023223876953125e-08 * (1.0 + 1e-6);  // -(2^-25) * (1 + 1e-6)
+  if (t < 0.0f) return ((double)t > eps) ? 0.0f : t + 1.0f;
+  if (t >= 1.0f) return t - 1.0f;
+  return t;
+}
+
+template <bool F64>
+__global__ void __launch_bounds__(256) axpy_kernel(float *__restrict__ y, const float *__restrict__ x,
+                                                   double a, int64_t n) {
+  const float af = (float)a;
+  int64_t n4 = n >> 2;
+  float4 *y4 = reinterpret_cast<float4 *>(y);
+  const float4 *x4 = reinterpret_cast<const float4 *>(x);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    float4 yv = y4[i], xv = x4[i];
+    if (F64) {
+      yv.x = (float)((double)yv.x + a * (double)xv.x);
+      yv.y = (float)((double)yv.y + a * (double)xv.y);
+      yv.z = (float)((double)yv.z + a * (double)xv.z);
+      yv.w = (float)((double)yv.w + a * (double)xv.w);
+    } else {
+      yv.x += af * xv.x; yv.y += af * xv.y; yv.z += af * xv.z; yv.w += af * xv.w;
+    }
+    y4[i] = yv;
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
+    int64_t i = (n4 << 2) + threadIdx.x;
+    y[i] = F64 ? (float)((double)y[i] + a * (double)x[i]) : y[i] + af * x[i];
+  }
+}
+
+__global__ void __launch_bounds__(256) wrap_kernel(float *__restrict__ x, int64_t n) {
+  int64_t n4 = n >> 2;
+  float4 *x4 = reinterpret_cast<float4 *>(x);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    float4 v = x4[i];
+    v.x = wrap01(v.x); v.y = wrap01(v.y); v.z = wrap01(v.z); v.w = wrap01(v.w);
+    x4[i] = v;
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
+    int64_t i = (n4 << 2) + threadIdx.x;
+    x[i] = wrap01(x[i]);
+  }
+}
+
+__global__ void __launch_bounds__(256) max_abs_kernel(const float *__restrict__ x, int64_t n,
+                                                      float *__restrict__ out) {
+  float m = 0.0f;
+  int64_t n4 = n >> 2;
+  const float4 *x4 = reinterpret_cast<const float4 *>(x);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    float4 v = __ldg(&x4[i]);
+    m = fmaxf(fmaxf(fmaxf(m, fabsf(v.x)), fmaxf(fabsf(v.y), fabsf(v.z))), fabsf(v.w));
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (n & 3)) m = fmaxf(m, fabsf(x[(n4 << 2) + threadIdx.x]));
+  m = warp_max(m);
+  __shared__ float sm[8];
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x < 8) {
+    m = sm[threadIdx.x];
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffu, m, o));
+    if (threadIdx.x == 0) atomic_max_nonneg(out, m);
+  }
+}
+
+// v -= half_dt*a ; x += dt*v ; wrap(x)   -- integration.py:250-258 in one pass (60 B/particle)
+template <bool F64>
+__global__ void __launch_bounds__(256) kick_drift_wrap_kernel(float *__restrict__ pos,
+                                                              float *__restrict__ vel,
+                                                              const float *__restrict__ acc, int64_t n,
+                                                              float half_dt, double dt) {
+  const float dtf = (float)dt;
+  const float mh = -half_dt;
+  int64_t n4 = n >> 2;
+  float4 *p4 = reinterpret_cast<float4 *>(pos);
+  float4 *v4 = reinterpret_cast<float4 *>(vel);
+  const float4 *a4 = reinterpret_cast<const float4 *>(acc);
+#define PSC_KDW(pc, vc, ac)                                       \
+  vc += mh * ac;                                                  \
+  pc = F64 ? (float)((double)pc + dt * (double)vc) : pc + dtf * vc; \
+  pc = wrap01(pc);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    float4 p = p4[i], v = v4[i], a = __ldg(&a4[i]);
+    PSC_KDW(p.x, v.x, a.x) PSC_KDW(p.y, v.y, a.y) PSC_KDW(p.z, v.z, a.z) PSC_KDW(p.w, v.w, a.w)
+    p4[i] = p;
+    v4[i] = v;
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
+    int64_t i = (n4 << 2) + threadIdx.x;
+    float p = pos[i], v = vel[i], a = acc[i];
+    PSC_KDW(p, v, a)
+    pos[i] = p;
+    vel[i] = v;
+  }
+#undef PSC_KDW
+}
+
+}  // namespace psc
+
+using namespace psc;
+
+extern "C" {
+
+int psc_morton_keys(const float *pos, int64_t np, int64_t *keys, void *stream) {
+  PSC_CHECK_ARG(np >= 0, "np < 0");
+  if (np == 0) return PSC_OK;
+  PSC_CHECK_ARG(pos && keys, "null pointer");
+  morton_keys_kernel<<<grid_for(np, 256), 256, 0, as_stream(stream)>>>(pos, np, keys);
+  count_launch();
+  PSC_CHECK_LAUNCH();
+  return PSC_OK;
+}
+
+static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+size_t psc_argsort_workspace_bytes(int64_t np) {
+  if (np <= 0) return 256;
+  size_t cub_bytes = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, (const uint64_t *)nullptr, (uint64_t *)nullptr,
+                                  (const int64_t *)nullptr, (int64_t *)nullptr, np, 0, 63);
+  // keys_out + iota + cub temp
+  return align256(sizeof(int64_t) * np) * 2 + align256(cub_bytes) + 256;
+}
+
+int psc_argsort_keys(const int64_t *keys, int64_t np, int64_t *idx_out, void *scratch,
+                     size_t scratch_bytes, void *stream) {
+  PSC_CHECK_ARG(np >= 0, "np < 0");
+  if (np == 0) return PSC_OK;
+  PSC_CHECK_ARG(keys && idx_out && scratch, "null pointer");
+  if (scratch_bytes < psc_argsort_workspace_bytes(np)) {
+    set_error("psc_argsort_keys: scratch too small");
+    return PSC_ERR_WORKSPACE;
+  }
+  char *base = reinterpret_cast<char *>(scratch);
+  uint64_t *keys_sorted = reinterpret_cast<uint64_t *>(base);
+  int64_t *iota = reinterpret_cast<int64_t *>(base + align256(sizeof(int64_t) * np));
+  void *cub_tmp = base + 2 * align256(sizeof(int64_t) * np);
+  size_t cub_bytes = scratch_bytes - 2 * align256(sizeof(int64_t) * np);
+  cudaStream_t st = as_stream(stream);
+  iota_kernel<<<grid_for(np, 256), 256, 0, st>>>(iota, np);
+  count_launch();
+  // Morton keys are non-negative 63-bit integers: an unsigned LSD radix sort over bits [0,63) is a
+  // stable sort of the signed keys.
+  cudaError_t e = cub::DeviceRadixSort::SortPairs(cub_tmp, cub_bytes,
+                                                  reinterpret_cast<const uint64_t *>(keys), keys_sorted,
+                                                  iota, idx_out, np, 0, 63, st);
+  count_launch(8);
+  if (e != cudaSuccess) {
+    set_error("psc_argsort_keys: cub radix sort failed: %s", cudaGetErrorString(e));
+    return PSC_ERR_CUDA;
+  }
+  PSC_CHECK_LAUNCH();
+  return PSC_OK;
+}
+
+int psc_gather3(const int64_t *idx, const float *src, float *dst, int64_t np, void *stream) {
+  PSC_CHECK_ARG(np >= 0, "np < 0");
+  if (np == 0) return PSC_OK;
+  PSC_CHECK_ARG(idx && src && dst, "null pointer");
+  PSC_CHECK_ARG(src != dst, "gather must be out of place");
+  gather3_kernel<<<grid_for(3 * np, 256), 256, 0, as_stream(stream)>>>(idx, src, dst, np);
+  count_launch();
+  PSC_CHECK_LAUNCH();
+  return PSC_OK;
+}
+
+int psc_axpy(float *y, const float *x, double a, int a_is_f64, int64_t n, void *stream) {
+  PSC_CHECK_ARG(n >= 0, "n < 0");
+  if (n == 0) return PSC_OK;
+  PSC_CHECK_ARG(y && x, "null pointer");
+  PSC_CHECK_ARG(((uintptr_t)y & 15) == 0 && ((uintptr_t)x & 15) == 0, "pointers must be 16-byte aligned");
+  int g = grid_for((n + 3) / 4, 256);
+  if (a_is_f64)
+    axpy_kernel<true><<<g, 256, 0, as_stream(stream)>>>(y, x, a, n);
+  else
+    axpy_kernel<false><<<g, 256, 0, as_stream(stream)>>>(y, x, a, n);
+  count_launch();
+  PSC_CHECK_LAUNCH();
+  return PSC_OK;
+}
+
+int psc_periodic_wrap(float *x, int64_t n, void *stream) {
+  PSC_CHECK_ARG(n >= 0, "n < 0");
+  if (n == 0) return PSC_OK;
+  PSC_CHECK_ARG(x, "null pointer");
+  PSC_CHECK_ARG(((uintptr_t)x & 15) == 0, "pointer must be 16-byte aligned");
+  wrap_kernel<<<grid_for((n + 3) / 4, 256), 256, 0, as_stream(stream)>>>(x, n);
+  count_launch();
+  PSC_CHECK_LAUNCH();
+  return PSC_OK;
+}
+
+int psc_max_abs(const float *x, int64_t n, float *out, void *stream) {
+  PSC_CHECK_ARG(n >= 0, "n < 0");
+  if (n == 0) return PSC_OK;
+  PSC_CHECK_ARG(x && out, "null pointer");
+  PSC_CHECK_ARG(((uintptr_t)x & 15) == 0, "pointer must be 16-byte aligned");
+  max_abs_kernel<<<grid_for((n + 3) / 4, 256, 4), 256, 0, as_stream(stream)>>>(x, n, out);
+  count_launch();
+  PSC_CHECK_LAUNCH();
+  return PSC_OK;
+}
+
+int psc_kick_drift_wrap(float *pos, float *vel, const float *acc, int64_t np, float half_dt, double dt,
+                        int dt_is_f64, void *stream) {
+  PSC_CHECK_ARG(np >= 0, "np < 0");
+  if (np == 0) return PSC_OK;
+  PSC_CHECK_ARG(pos && vel && acc, "null pointer");
+  PSC_CHECK_ARG((((uintptr_t)pos | (uintptr_t)vel | (uintptr_t)acc) & 15) == 0,
+                "pointers must be 16-byte aligned");
+  int64_t n = 3 * np;
+  int g = grid_for((n + 3) / 4, 256);
+  if (dt_is_f64)
+    kick_drift_wrap_kernel<true><<<g, 256, 0, as_stream(stream)>>>(pos, vel, acc, n, half_dt, dt);
+  else
+    kick_drift_wrap_kernel<false><<<g, 256, 0, as_stream(stream)>>>(pos, vel, acc, n, half_dt, dt);
+  count_launch();
+  PSC_CHECK_LAUNCH();
+  return PSC_OK;
+}
+
+}  // extern "C"
