@@ -1,0 +1,362 @@
+#!/usr/bin/env python
+"""bench.py -- particle-updates/s of one full Newtonian FFT particle-mesh step (BASELINE.json metric).
+
+    python bench.py --gpus 1 --steps 20 --warmup 3            # B200 arm (this repo's CUDA path)
+    python bench.py --impl reference --steps 3 --warmup 1     # CPU arm: the oracle port on host cores
+    torchrun --nproc-per-node N bench.py --gpus N ...         # one rank per GPU
+
+Workload: N^3 particles on an N^3 mesh (default N = 512), synthetic ICs = cell-centre
+lattice + Gaussian displacement 0.3 cells (seed 42), Morton-ordered as after a reorder, TSC deposit,
+compensated-Green FFT solve, 5-point gradient, TSC interpolation, leapfrog KDK through the public API
+`pysco_b200.integration.integrate` with analytic background tables; `utils.reorder_particles` every
+n_reorder = 50 steps (its cost is measured in the same run and amortised as t_reorder/50 when no
+reorder falls inside the K timed steps).
+
+One JSON line on stdout (rank 0).  `value` = device-resident throughput; `e2e` = the same call with
+HOST (pinned) buffers, i.e. every step uploads position/velocity/acceleration and downloads the results.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+
+METRIC = "particle_updates_per_sec_full_pm_step"
+UNIT = "particle-updates/s"
+N_REORDER = 50
+
+# algorithmic bytes per particle (= per cell, Np = N^3) of each C-ABI call of the Newtonian FFT step
+# (SURVEY 8d): the figure `roofline.achieved` is computed from.
+ALGO_BYTES = {
+    "psc_kick_drift_wrap": 60.0,   # read x,v,a (36) + write x,v (24)
+    "psc_deposit": 16.0,           # read x (12) + write rho (4); rescale + RHS affine fused (0)
+    "psc_fft_r2c": 8.0,            # read 4 + write 4 (half-spectrum ~ 4 B per real cell)
+    "psc_green": 8.0,
+    "psc_fft_c2r": 8.0,
+    "psc_gradient": 16.0,          # read phi (4) + write force (12)
+    "psc_interp_kick": 60.0,       # read x,v (24) + force once per cell (12) + write v,a (24)
+}
+
+
+def make_tables():
+    """Analytic background (EdS-like supercomoving time, D1 = a); same layout as cosmotable.generate."""
+    from scipy.interpolate import interp1d
+    lna = np.linspace(np.log(1.0 / 201), 0.0, 20001)
+    a = np.exp(lna)
+    t = -2.0 * (a ** -0.5 - 1.0)
+    tabs = [interp1d(t, lna, fill_value="extrapolate"), interp1d(lna, t, fill_value="extrapolate"),
+            interp1d(lna, 72.0 * a ** -1.5, fill_value="extrapolate"), interp1d(lna, a, fill_value="extrapolate")]
+    return tabs + [interp1d(lna, np.ones_like(a), fill_value="extrapolate")] * 9
+
+
+def make_param(ncoarse, nthreads):
+    import pandas as pd
+    N = 2 ** ncoarse
+    return pd.Series({
+        "nthreads": nthreads, "theory": "newton", "H0": 72, "Om_m": 0.25733, "boxlen": 100, "ncoarse": ncoarse,
+        "npart": N ** 3, "integrator": "leapfrog", "mass_scheme": "TSC", "n_reorder": N_REORDER,
+        "Courant_factor": 1.0, "max_aexp_stepping": 10, "linear_newton_solver": "fft",
+        "gradient_stencil_order": 5, "save_power_spectrum": "no", "aexp": 0.02, "aexp_old": 0.02, "nsteps": 0,
+        "write_snapshot": False, "w0": -1.0, "wa": 0.0, "Om_r": 8.0763e-05, "Om_lambda": 1 - 0.25733 - 8.0763e-05,
+        "parametrized_mu0": 0.0, "epsrel": 1e-2, "Npre": 2, "Npost": 1,
+    })
+
+
+def synthetic_ics_numpy(N, seed=42):
+    import cases
+    pos = cases.lattice_particles(N, 0.3, seed=seed)
+    vel = cases.velocities(N ** 3, seed=seed + 1, scale=1e-3)
+    return pos, vel
+
+
+def synthetic_ics_device(N, seed=42):
+    """Same distribution as synthetic_ics_numpy, generated on the device (512^3 on the host is slow)."""
+    import torch
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    ax = (torch.arange(N, device="cuda", dtype=torch.float32) + 0.5) / N
+    pos = torch.stack(torch.meshgrid(ax, ax, ax, indexing="ij"), dim=-1).reshape(-1, 3)
+    pos = pos + torch.randn(pos.shape, generator=g, device="cuda", dtype=torch.float32) * (0.3 / N)
+    pos = pos - torch.floor(pos)
+    pos[pos >= 1.0] = 0.0
+    vel = torch.randn(pos.shape, generator=g, device="cuda", dtype=torch.float32) * 1e-3
+    return pos.contiguous(), vel.contiguous()
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.gpu), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i].lower() == "active"})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def measured_peak_gbs():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------ CPU (oracle) arm
+def cpu_step_rate(ncoarse, steps, warmup, threads):
+    """Times the oracle port (C/OpenMP + numpy FFT, the reference's algorithm) for full leapfrog steps
+    at 2^ncoarse cells per side on the host cores.  Returns (particle-updates/s, ms/step)."""
+    import oracle
+    from oracle import host
+    oracle.set_num_threads(threads)
+    N = 2 ** ncoarse
+    tables = make_tables()
+    param = make_param(ncoarse, threads)
+    param["t"] = float(tables[1](np.log(param["aexp"])))
+    host.set_units(param)
+    pos, vel = synthetic_ics_numpy(N)
+    pos, vel = oracle.utils.reorder_particles(pos, vel)
+    acc, pot, add = host.pm(pos, param)
+    times = []
+    for s in range(warmup + steps):
+        t0 = time.perf_counter()
+        param["nsteps"] += 1
+        pos, vel, acc, pot, add = host.integrate(pos, vel, acc, pot, add, tables, param, 1e30)
+        times.append(time.perf_counter() - t0)
+    dt = float(np.mean(times[warmup:]))
+    return N ** 3 / dt, dt * 1e3
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    nc = args.cpu_ncoarse
+    value, ms = cpu_step_rate(nc, args.steps, args.warmup, threads)
+    N = 2 ** nc
+    sample = f"{N}^3 particles / {N}^3 mesh full leapfrog step (1/{(2 ** args.ncoarse // N) ** 3} of the {2 ** args.ncoarse}^3 workload)"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args.ncoarse),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
+                         "fft": "numpy-pocketfft (single thread), as the reference without pyfftw"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(ncoarse):
+    N = 2 ** ncoarse
+    return {"workload": f"Newtonian FFT-PM leapfrog step, {N}^3 particles on {N}^3 mesh, TSC, compensated Green, "
+                        f"5-pt gradient, n_reorder={N_REORDER} (BASELINE configs[0] shape at the metric's {N}^3 size)",
+            "ncells_1d": N, "npart": N ** 3, "ics": "lattice + N(0, 0.3 cell) displacement, seed 42, Morton-ordered",
+            "l2_policy": "inputs larger than L2 (particle arrays 3 x %.1f GB, grids %.2f GB vs 126 MB L2)" % (
+                12 * N ** 3 / 1e9, 4 * N ** 3 / 1e9)}
+
+
+# ---------------------------------------------------------------------------------- B200 arm
+def run_gpu_arm(args):
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    import pysco_b200
+    from pysco_b200 import _lib, integration, solver, utils
+    _lib.load()
+
+    nc = args.ncoarse
+    N = 2 ** nc
+    tables = make_tables()
+    param = make_param(nc, 1)
+    param["t"] = float(tables[1](np.log(param["aexp"])))
+    utils.set_units(param)
+
+    # Multi-GPU (this round): independent replicas of the single-GPU workload, no data-path collective
+    # (weak scaling: each rank advances its own N^3 box).  The slab-decomposed single box
+    # is the next row.
+    pos, vel = synthetic_ics_device(N, seed=42 + rank)
+    pos, vel = utils.reorder_particles(pos, vel)
+    acc, pot, add = solver.pm(pos, param)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    state = [pos, vel, acc, pot, add]
+
+    def step():
+        param["nsteps"] += 1
+        state[:] = integration.integrate(*state, tables, param, 1e30)
+        if param["nsteps"] % N_REORDER == 0:
+            state[0], state[1], state[2] = utils.reorder_particles(state[0], state[1], state[2])
+            return True
+        return False
+
+    for _ in range(args.warmup):
+        step()
+    # reorder cost (amortised below if no reorder lands in the timed steps)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    rp, rv, ra = utils.reorder_particles(state[0], state[1], state[2])
+    e1.record()
+    torch.cuda.synchronize()
+    t_reorder_ms = e0.elapsed_time(e1)
+    state[0], state[1], state[2] = rp, rv, ra
+    del rp, rv, ra
+
+    sampler = ClockSampler(local_rank)
+    _lib.enable_timing(True)
+    launches0 = _lib.launch_count()
+    barrier()
+    if rank == 0:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    n_reorders = 0
+    for _ in range(args.steps):
+        n_reorders += bool(step())
+    ev1.record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    launches = _lib.launch_count() - launches0
+    records = _lib.timing_records()
+    _lib.enable_timing(False)
+    t_ms = ev0.elapsed_time(ev1)
+    # amortised reorder: K/50 reorders belong to K steps
+    t_ms_total = t_ms + (args.steps / N_REORDER - n_reorders) * t_reorder_ms
+    tt = torch.tensor([t_ms_total], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    t_ms_total = tt.item()
+    ms_per_step = t_ms_total / args.steps
+    value = world * N ** 3 / (ms_per_step * 1e-3)
+
+    # per-kernel device times from the CUDA-event pairs recorded around every C-ABI call
+    per = {}
+    for name, a, b in records:
+        per.setdefault(name, []).append(a.elapsed_time(b))
+    kern = {k: {"calls_per_step": len(v) / args.steps, "ms_per_call": float(np.mean(v)),
+                "ms_per_step": float(np.sum(v)) / args.steps} for k, v in per.items()}
+    peak, peak_src = measured_peak_gbs()
+    for k, d in kern.items():
+        if k in ALGO_BYTES:
+            d["algo_bytes"] = ALGO_BYTES[k] * N ** 3
+            d["achieved_gbs"] = d["algo_bytes"] / (d["ms_per_call"] * 1e-3) / 1e9
+            d["frac_of_peak"] = d["achieved_gbs"] / peak
+    step_algo_bytes = sum(ALGO_BYTES.values()) * N ** 3
+    dom = max((k for k in kern if k in ALGO_BYTES), key=lambda k: kern[k]["ms_per_step"])
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": kern[dom]["achieved_gbs"], "peak": peak,
+                "unit": "GB/s", "frac": kern[dom]["achieved_gbs"] / peak, "traffic": None,
+                "peak_source": peak_src, "algo_bytes_per_launch": kern[dom]["algo_bytes"],
+                "ms_per_launch": kern[dom]["ms_per_call"],
+                "whole_step": {"algo_bytes": step_algo_bytes,
+                               "achieved": step_algo_bytes / (ms_per_step * 1e-3) / 1e9,
+                               "frac": step_algo_bytes / (ms_per_step * 1e-3) / 1e9 / peak}}
+
+    # ---- e2e: same public call with HOST (pinned) buffers, H2D + D2H inside the timed region
+    e2e = None
+    if not args.no_e2e:
+        host = [torch.empty(t.shape, dtype=t.dtype, pin_memory=True).copy_(t) for t in state[:4]]
+        host.append(state[4])
+        del state[:]
+        torch.cuda.empty_cache()
+        e2e_steps = max(1, min(args.e2e_steps, args.steps))
+        h2d = sum(t.numel() * 4 for t in host[:4])
+        d2h = h2d
+        for i in range(1 + e2e_steps):
+            if i == 1:
+                barrier()
+                t0 = time.perf_counter()
+            param["nsteps"] += 1
+            host[:] = integration.integrate(*host, tables, param, 1e30)
+        torch.cuda.synchronize()
+        dt = (time.perf_counter() - t0) / e2e_steps
+        tt = torch.tensor([dt], device="cuda", dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e = {"value": world * N ** 3 / tt.item(), "unit": UNIT, "h2d_bytes_per_step": h2d,
+               "d2h_bytes_per_step": d2h, "steps": e2e_steps, "ms_per_step": tt.item() * 1e3,
+               "api": "pysco_b200.integration.integrate(pinned host tensors)"}
+
+    if rank == 0:
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            threads = os.cpu_count() or 1
+            v, ms = cpu_step_rate(args.cpu_ncoarse, 1, 1, threads)
+            Nc = 2 ** args.cpu_ncoarse
+            cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
+                   "sample": f"{Nc}^3 particles / {Nc}^3 mesh full leapfrog step of the same workload shape "
+                             f"(1 warm-up + 1 timed, {ms:.0f} ms); numpy-pocketfft FFT"}
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(nc),
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
+            "clocks": clocks, "kernels": kern,
+            "reorder": {"ms": t_reorder_ms, "in_timed_steps": n_reorders, "amortised_over": N_REORDER},
+            "multi_gpu": "independent replicas (no collective)" if world > 1 else None,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--ncoarse", type=int, default=9, help="log2 cells per side of the workload (9 -> 512^3)")
+    ap.add_argument("--cpu-ncoarse", type=int, default=8, help="log2 cells per side of the CPU sample (8 -> 256^3)")
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_gpu_arm(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -270,7 +270,7 @@ def get_additional_field(additional_field, density, param, tables):
 
 
 def pm(position, param, potential=_EMPTY, additional_field=_EMPTY, tables=(), pk_sink=None):
-    """solver.py:30-215.  Canonical oracle configuration: nthreads = 1 semantics (TSC_seq)."""
+    """solver.py:30-215.  Canonical (bit-reproducible) oracle configuration: param["nthreads"] = 1."""
     N = 2 ** param["ncoarse"]
     scheme = param["mass_scheme"].casefold()
     theory = param["theory"].casefold()
@@ -279,7 +279,8 @@ def pm(position, param, potential=_EMPTY, additional_field=_EMPTY, tables=(), pk
         density = mesh.CIC(position, N)
     elif scheme == "tsc":
         param["MAS_index"] = 3
-        density = mesh.TSC_seq(position, N)
+        # solver.py:86-89: atomic (parallel) TSC from 4 threads up, sequential below
+        density = mesh.TSC(position, N) if param["nthreads"] >= 4 else mesh.TSC_seq(position, N)
     else:
         raise NotImplementedError(f"{param['mass_scheme']=}")
     if theory == "parametrized":

@@ -1,0 +1,84 @@
+"""Host-side I/O of the run loop (reference pysco/iostream.py): parameter file
+reader, parquet/HDF5 particle snapshots and the P(k) ascii writer, with the reference's file names
+and on-disk layout.  Device tensors are copied to the host here."""
+import ast
+import logging
+import os
+
+import numpy as np
+import pandas as pd
+
+
+def _host(a):
+    return a.detach().cpu().numpy() if hasattr(a, "detach") else np.asarray(a)
+
+
+def read_param_file(name: str) -> pd.Series:
+    """iostream.py:13-69: ``key = value  # comment`` lines; values evaluated when they are Python
+    literals / arithmetic (e.g. ``128**3``), lists kept as strings, true/false case-folded."""
+    out = {}
+    with open(name) as f:
+        for line in f:
+            line = line.split("#", 1)[0].strip()
+            if not line or "=" not in line:
+                continue
+            key, val = (s.strip() for s in line.split("=", 1))
+            if val == "":
+                val = "False"
+            if val.casefold() in ("true", "false"):
+                val = val.capitalize()
+            try:
+                v = eval(val, {"__builtins__": {}}, {})  # same contract as the reference (eval per value)
+                out[key] = val if isinstance(v, list) else v
+            except Exception:
+                out[key] = val
+    return pd.Series(out)
+
+
+def write_power_spectrum_to_ascii_file(k, Pk, Nmodes, param) -> None:
+    """iostream.py:268-304"""
+    output_pk = f"{param['base']}/power/pk_{param['extra']}_{param['nsteps']:05d}.dat"
+    os.makedirs(os.path.dirname(output_pk), exist_ok=True)
+    logging.warning(f"Write P(k) in {output_pk}")
+    np.savetxt(
+        output_pk, np.c_[k, Pk, Nmodes],
+        header=f"aexp = {param['aexp']}\nboxlen = {param['boxlen']} Mpc/h \nnpart = {param['npart']} \n"
+               f"k [h/Mpc] P(k) [Mpc/h]^3 Nmodes")
+
+
+def write_snapshot_particles(position, velocity, param) -> None:
+    """iostream.py:136-182"""
+    fmt = param["output_snapshot_format"].casefold()
+    position, velocity = _host(position), _host(velocity)
+    d = f"{param['base']}/output_{param['i_snap']:05d}"
+    os.makedirs(d, exist_ok=True)
+    if fmt == "parquet":
+        import pyarrow as pa
+        import pyarrow.parquet as pq
+        filename = f"{d}/particles_{param['extra']}.parquet"
+        pq.write_table(pa.table({"x": position[:, 0], "y": position[:, 1], "z": position[:, 2],
+                                 "vx": velocity[:, 0], "vy": velocity[:, 1], "vz": velocity[:, 2]}), filename)
+        param.to_csv(f"{d}/param_{param['extra']}_{param['i_snap']:05d}.txt", sep="=", header=False)
+    elif fmt == "hdf5":
+        import h5py  # optional dependency, as in the reference
+        filename = f"{d}/particles_{param['extra']}.h5"
+        with h5py.File(filename, "w") as h5f:
+            h5f.create_dataset("position", data=position)
+            h5f.create_dataset("velocity", data=velocity)
+            for key, item in param.items():
+                h5f.attrs[key] = item
+    else:
+        raise NotImplementedError(f"{param['output_snapshot_format']=}, should be 'parquet' or 'hdf5'")
+    logging.warning(f"Snapshot written at ...{filename=} {param['aexp']=}")
+
+
+def read_snapshot_particles_parquet(filename: str):
+    """iostream.py:111-133"""
+    import pyarrow.parquet as pq
+    position = np.ascontiguousarray(np.array(pq.read_table(filename, columns=["x", "y", "z"])).T)
+    velocity = np.ascontiguousarray(np.array(pq.read_table(filename, columns=["vx", "vy", "vz"])).T)
+    return position, velocity
+
+
+def parse_z_out(param):
+    return ast.literal_eval(param["z_out"]) if isinstance(param["z_out"], str) else list(param["z_out"])

@@ -1,0 +1,91 @@
+"""Mirror of pysco/laplacian.py (7-point Laplacian multigrid kernels)."""
+import numpy as np
+import torch
+
+from . import _lib
+
+K = _lib.OP_LAPLACIAN
+
+
+def _sumsq(fn_call):
+    out = _lib.zeros((1,), torch.float64)
+    fn_call(out)
+    return np.float32(np.sqrt(out.item()))
+
+
+def operator(x, _kind=K, b=None, q=0.0):
+    """laplacian.py:12-54"""
+    c = _lib.Ctx()
+    tx, tb = c.dev(x), c.dev(b)
+    out = torch.empty_like(tx)
+    _lib.check(_lib.load().psc_operator(_lib.ptr(tx), _lib.ptr(tb), float(np.float32(q)), tx.shape[0], _kind,
+                                        _lib.ptr(out), _lib.stream()))
+    return c.ret(out)
+
+
+def residual(x, b):
+    """laplacian.py:63-117: b - Lx"""
+    c = _lib.Ctx()
+    tx, tb = c.dev(x), c.dev(b)
+    out = torch.empty_like(tx)
+    _lib.check(_lib.load().psc_residual(_lib.ptr(tx), _lib.ptr(tb), 0.0, None, tx.shape[0], K, _lib.ptr(out),
+                                        _lib.stream()))
+    return c.ret(out)
+
+
+def restrict_residual(x, b):
+    """laplacian.py:125-226: R(b - Lx), fused"""
+    c = _lib.Ctx()
+    tx, tb = c.dev(x), c.dev(b)
+    N = tx.shape[0]
+    out = _lib.empty((N // 2,) * 3)
+    _lib.check(_lib.load().psc_restrict_residual(_lib.ptr(tx), _lib.ptr(tb), N, _lib.ptr(out), _lib.stream()))
+    return c.ret(out)
+
+
+def residual_error(x, b, _kind=K, q=0.0):
+    """laplacian.py:327-381: sqrt(sum (b - Lx)^2) (synchronises)"""
+    c = _lib.Ctx()
+    tx, tb = c.dev(x), c.dev(b)
+    return _sumsq(lambda out: _lib.check(_lib.load().psc_residual_sumsq(
+        _lib.ptr(tx), _lib.ptr(tb), float(np.float32(q)), tx.shape[0], _kind, _lib.ptr(out), _lib.stream())))
+
+
+def truncation_error(x):
+    """laplacian.py:502-533: || R(Lx) - L(Rx) ||"""
+    c = _lib.Ctx()
+    tx = c.dev(x)
+    from . import mesh
+    RLx = mesh.restriction(operator(tx))
+    LRx = operator(mesh.restriction(tx))
+    return _sumsq(lambda out: _lib.check(_lib.load().psc_diff_sumsq(
+        _lib.ptr(RLx), 1.0, _lib.ptr(LRx), RLx.numel(), _lib.ptr(out), _lib.stream())))
+
+
+def initialise_potential(b, _kind=K, q=0.0):
+    """laplacian.py:765-796: -h^2/6 * b"""
+    c = _lib.Ctx()
+    tb = c.dev(b)
+    out = torch.empty_like(tb)
+    _lib.check(_lib.load().psc_initialise_potential(_lib.ptr(tb), float(np.float32(q)), tb.shape[0], _kind,
+                                                    _lib.ptr(out), _lib.stream()))
+    return c.ret(out)
+
+
+def gauss_seidel(x, b, f_relax, _kind=K, q=0.0, rhs=None) -> None:
+    """laplacian.py:844-1022: one red-black SOR sweep, in place"""
+    c = _lib.Ctx()
+    tx, tb, tr = c.dev(x, inplace=True), c.dev(b), c.dev(rhs)
+    _lib.check(_lib.load().psc_gauss_seidel(_lib.ptr(tx), _lib.ptr(tb), float(np.float32(q)), _lib.ptr(tr),
+                                            tx.shape[0], _kind, float(f_relax), _lib.stream()))
+    c.finish()
+
+
+def smoothing(x, b, n_smoothing) -> None:
+    """laplacian.py:1026-1055"""
+    f_relax = np.float32(1.25)
+    c = _lib.Ctx()
+    tx, tb = c.dev(x, inplace=True), c.dev(b)
+    for _ in range(int(n_smoothing)):
+        gauss_seidel(tx, tb, f_relax)
+    c.finish()

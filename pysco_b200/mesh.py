@@ -1,0 +1,153 @@
+"""Mirror of pysco/mesh.py: mass assignment, inverse interpolation, finite-difference gradients,
+restriction / prolongation.  Same names and argument meaning as the reference."""
+import numpy as np
+import torch
+
+from . import _lib
+
+
+def _deposit(position, ncells_1d, scheme, scale=1.0, f1=1.0, f2=0.0):
+    c = _lib.Ctx()
+    pos = c.dev(position)
+    N = int(ncells_1d)
+    rho = _lib.empty((N, N, N))
+    _lib.check(_lib.load().psc_deposit(_lib.ptr(pos), pos.shape[0], N, scheme, float(scale), float(f1),
+                                       float(f2), _lib.ptr(rho), _lib.stream()))
+    return c.ret(rho)
+
+
+def NGP(position, ncells_1d):
+    """mesh.py:2240-2278"""
+    return _deposit(position, ncells_1d, _lib.NGP)
+
+
+def CIC(position, ncells_1d):
+    """mesh.py:2284-2358"""
+    return _deposit(position, ncells_1d, _lib.CIC)
+
+
+def TSC(position, ncells_1d):
+    """mesh.py:2468-2595"""
+    return _deposit(position, ncells_1d, _lib.TSC)
+
+
+TSC_seq = TSC  # mesh.py:2363-2462: same result, the reference's sequential variant
+
+
+def deposit_rhs(position, ncells_1d, scheme, scale, f1, f2):
+    """Fused mass assignment + density rescale + Poisson right-hand side (solver.py:80-116, 444-449):
+    f1 * (scale * deposit) + f2 in one pass over the grid."""
+    return _deposit(position, ncells_1d, scheme, scale, f1, f2)
+
+
+def _interp(grid, position, scheme):
+    c = _lib.Ctx()
+    g, pos = c.dev(grid), c.dev(position)
+    N = g.shape[0]
+    ncomp = 3 if g.dim() == 4 else 1
+    n = pos.shape[0]
+    out = _lib.empty((n, 3) if ncomp == 3 else (n,))
+    _lib.check(_lib.load().psc_interp(_lib.ptr(g), _lib.ptr(pos), n, N, ncomp, scheme, _lib.ptr(out),
+                                      _lib.stream()))
+    return c.ret(out)
+
+
+def invNGP(grid, position):
+    return _interp(grid, position, _lib.NGP)
+
+
+def invCIC(grid, position):
+    return _interp(grid, position, _lib.CIC)
+
+
+def invTSC(grid, position):
+    return _interp(grid, position, _lib.TSC)
+
+
+invNGP_vec, invCIC_vec, invTSC_vec = invNGP, invCIC, invTSC  # mesh.py:2627-3088 (AoS [N,N,N,3] grid)
+
+
+def interp_kick(force, position, velocity, scheme, half_dt):
+    """inv{CIC,TSC}_vec fused with v -= half_dt*a and the max|a|, max|v| reductions.
+    Returns (acceleration, maxima[2] device tensor).  velocity may be None (plain interpolation)."""
+    c = _lib.Ctx()
+    g, pos = c.dev(force), c.dev(position)
+    vel = c.dev(velocity, inplace=True)
+    n = pos.shape[0]
+    acc = _lib.empty((n, 3))
+    mx = _lib.zeros((2,))
+    _lib.check(_lib.load().psc_interp_kick(_lib.ptr(g), _lib.ptr(pos), _lib.ptr(vel), _lib.ptr(acc), n,
+                                           g.shape[0], scheme, float(half_dt), _lib.ptr(mx), _lib.stream()))
+    c.finish()
+    return c.ret(acc), mx
+
+
+def _gradient(a, b, f, fr_n, order, add, force=None):
+    if fr_n not in (0, 1, 2):
+        raise NotImplementedError(f"Unsupported: fR_n={fr_n}")
+    if order not in (2, 3, 5, 7):
+        raise NotImplementedError(f"Unsupported: gradient_order={order}")
+    c = _lib.Ctx()
+    ta, tb = c.dev(a), c.dev(b)
+    N = (ta if ta is not None else tb).shape[0]
+    out = c.dev(force, inplace=True) if add else _lib.empty((N, N, N, 3))
+    _lib.check(_lib.load().psc_gradient(_lib.ptr(ta), _lib.ptr(tb), float(np.float32(f)), fr_n, order,
+                                        1 if add else 0, N, _lib.ptr(out), _lib.stream()))
+    c.finish()
+    return None if add else c.ret(out)
+
+
+def derivative(a, gradient_order):
+    """mesh.py:2072-2109"""
+    return _gradient(a, None, 0.0, 0, gradient_order, False)
+
+
+def derivative_fR(a, b, f, fR_n, gradient_order):
+    """mesh.py:2112-2174"""
+    if fR_n not in (1, 2):
+        raise NotImplementedError(f"Unsupported: {fR_n=}")
+    return _gradient(a, b, f, fR_n, gradient_order, False)
+
+
+def add_derivative_fR(force, b, f, fR_n, gradient_order) -> None:
+    """mesh.py:2177-2237 (in place on force)"""
+    if fR_n not in (1, 2):
+        raise NotImplementedError(f"Unsupported: {fR_n=}")
+    _gradient(None, b, f, fR_n, gradient_order, True, force)
+
+
+def _restriction(x, sign):
+    c = _lib.Ctx()
+    tx = c.dev(x)
+    N = tx.shape[0]
+    out = _lib.empty((N // 2,) * 3)
+    _lib.check(_lib.load().psc_restriction(_lib.ptr(tx), N, sign, _lib.ptr(out), _lib.stream()))
+    return c.ret(out)
+
+
+def restriction(x):
+    """mesh.py:14-60"""
+    return _restriction(x, 1.0)
+
+
+def minus_restriction(x):
+    """mesh.py:62-108"""
+    return _restriction(x, -1.0)
+
+
+def prolongation(x):
+    """mesh.py:180-330"""
+    c = _lib.Ctx()
+    tx = c.dev(x)
+    Nc = tx.shape[0]
+    out = _lib.empty((2 * Nc,) * 3)
+    _lib.check(_lib.load().psc_prolongation(_lib.ptr(out), _lib.ptr(tx), Nc, 0, _lib.stream()))
+    return c.ret(out)
+
+
+def add_prolongation(y, x) -> None:
+    """mesh.py:334-453: y += P(x), in place"""
+    c = _lib.Ctx()
+    ty, tx = c.dev(y, inplace=True), c.dev(x)
+    _lib.check(_lib.load().psc_prolongation(_lib.ptr(ty), _lib.ptr(tx), tx.shape[0], 1, _lib.stream()))
+    c.finish()

@@ -1,0 +1,131 @@
+"""Mirror of the hot-path part of pysco/utils.py."""
+import numpy as np
+import torch
+
+from . import _lib
+
+# astropy.constants values the reference reads (utils.py:11): CODATA-2018 / IAU-2015
+_PC = 3.0856775814913673e16
+_G = 6.6743e-11
+
+
+def set_units(param) -> None:
+    """utils.py:167-196 (host scalars)."""
+    mpc_to_km = 1e3 * _PC
+    g = _G * 1e-9
+    H0 = param["H0"] / mpc_to_km
+    rhoc = 3.0 * H0 ** 2 / (8.0 * np.pi * g)
+    param["unit_l"] = param["aexp"] * param["boxlen"] * 100.0 / H0
+    param["unit_t"] = param["aexp"] ** 2 / H0
+    param["unit_d"] = param["Om_m"] * rhoc / param["aexp"] ** 3
+    param["mpart"] = param["unit_d"] * param["unit_l"] ** 3 / param["npart"]
+
+
+def max_abs(x):
+    """utils.py:220-240 -> np.float32 (synchronises)."""
+    c = _lib.Ctx()
+    t = c.dev(x)
+    out = _lib.zeros((1,))
+    _lib.check(_lib.load().psc_max_abs(_lib.ptr(t), t.numel(), _lib.ptr(out), _lib.stream()))
+    return np.float32(out.item())
+
+
+def add_vector_scalar_inplace(y, x, a) -> None:
+    """utils.py:264-297: y += a*x.  The arithmetic type follows the scalar's type as in Numba:
+    np.float32 -> float32 FMA; Python float / np.float64 -> float64 intermediate."""
+    c = _lib.Ctx()
+    ty, tx = c.dev(y, inplace=True), c.dev(x)
+    is64 = 0 if isinstance(a, np.float32) else 1
+    _lib.check(_lib.load().psc_axpy(_lib.ptr(ty), _lib.ptr(tx), float(a), is64, ty.numel(), _lib.stream()))
+    c.finish()
+
+
+def prod_vector_scalar_inplace(y, a) -> None:
+    """utils.py:410-430: y *= a"""
+    c = _lib.Ctx()
+    ty = c.dev(y, inplace=True)
+    _lib.check(_lib.load().psc_linear_operator(_lib.ptr(ty), float(np.float32(a)), 0.0, _lib.ptr(ty),
+                                               ty.numel(), _lib.stream()))
+    c.finish()
+
+
+def linear_operator(x, f1, f2):
+    """utils.py:644-680: f1*x + f2 (new array)"""
+    c = _lib.Ctx()
+    tx = c.dev(x)
+    out = torch.empty_like(tx)
+    _lib.check(_lib.load().psc_linear_operator(_lib.ptr(tx), float(np.float32(f1)), float(np.float32(f2)),
+                                               _lib.ptr(out), tx.numel(), _lib.stream()))
+    return c.ret(out)
+
+
+def linear_operator_inplace(x, f1, f2) -> None:
+    """utils.py:684-717"""
+    c = _lib.Ctx()
+    tx = c.dev(x, inplace=True)
+    _lib.check(_lib.load().psc_linear_operator(_lib.ptr(tx), float(np.float32(f1)), float(np.float32(f2)),
+                                               _lib.ptr(tx), tx.numel(), _lib.stream()))
+    c.finish()
+
+
+def linear_operator_vectors_inplace(x, f1, y, f2) -> None:
+    """utils.py:721-755: x = f1*x + f2*y"""
+    c = _lib.Ctx()
+    tx, ty = c.dev(x, inplace=True), c.dev(y)
+    _lib.check(_lib.load().psc_lincomb(_lib.ptr(tx), float(np.float32(f1)), _lib.ptr(ty),
+                                       float(np.float32(f2)), tx.numel(), _lib.stream()))
+    c.finish()
+
+
+def periodic_wrap(position) -> None:
+    """utils.py:1120-1149"""
+    c = _lib.Ctx()
+    t = c.dev(position, inplace=True)
+    _lib.check(_lib.load().psc_periodic_wrap(_lib.ptr(t), t.numel(), _lib.stream()))
+    c.finish()
+
+
+def injection_with_indices(idx, a):
+    """utils.py:894-924: out[i] = a[idx[i]] (rows of [Np,3])"""
+    c = _lib.Ctx()
+    ti, ta = c.dev(idx, torch.int64), c.dev(a)
+    out = torch.empty_like(ta)
+    _lib.check(_lib.load().psc_gather3(_lib.ptr(ti), _lib.ptr(ta), _lib.ptr(out), ta.shape[0], _lib.stream()))
+    return c.ret(out)
+
+
+def argsort_keys(keys):
+    """Stable argsort of Morton keys on the device (= np.argsort(keys, kind='stable'))."""
+    lib = _lib.load()
+    n = keys.shape[0]
+    idx = _lib.empty((n,), torch.int64)
+    nbytes = int(lib.psc_argsort_workspace_bytes(n))
+    scratch = _lib.empty((nbytes,), torch.uint8)
+    _lib.check(lib.psc_argsort_keys(_lib.ptr(keys), n, _lib.ptr(idx), _lib.ptr(scratch), nbytes, _lib.stream()))
+    return idx
+
+
+def reorder_particles(position, velocity=None, acceleration=None):
+    """utils.py:1019-1075: Morton keys -> (global, stable) argsort -> gathers; returns NEW arrays.
+    Matches the reference's nthreads == 1 path (np.argsort); rows of equal key keep their order."""
+    c = _lib.Ctx()
+    pos = c.dev(position)
+    vel = c.dev(velocity)
+    acc = c.dev(acceleration)
+    lib = _lib.load()
+    n = pos.shape[0]
+    keys = _lib.empty((n,), torch.int64)
+    _lib.check(lib.psc_morton_keys(_lib.ptr(pos), n, _lib.ptr(keys), _lib.stream()))
+    idx = argsort_keys(keys)
+    del keys
+
+    def g(a):
+        out = torch.empty_like(a)
+        _lib.check(lib.psc_gather3(_lib.ptr(idx), _lib.ptr(a), _lib.ptr(out), n, _lib.stream()))
+        return out
+
+    if acc is not None:
+        return c.ret(g(pos)), c.ret(g(vel)), c.ret(g(acc))
+    if vel is not None:
+        return c.ret(g(pos)), c.ret(g(vel))
+    return c.ret(g(pos))
