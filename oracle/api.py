@@ -221,7 +221,17 @@ def _add_prolongation(y, x):
     lib().orc_prolongation(_p(_chk(y)), _p(_chk(x)), C.c_int(x.shape[0]), C.c_int(1))
 
 
+def _deposit_f64(position, ncells_1d, scheme):
+    """float64-accumulated deposit (exact-sum yardstick for tests; scheme 1 = CIC, 2 = TSC)."""
+    pos = _chk(position)
+    N = int(ncells_1d)
+    rho = np.empty((N, N, N), dtype=np.float64)
+    lib().orc_deposit_f64(_p(pos), C.c_int64(pos.shape[0]), C.c_int(N), C.c_int(scheme), _p(rho))
+    return rho
+
+
 mesh = SimpleNamespace(
+    deposit_f64=_deposit_f64,
     NGP=lambda position, n: _deposit("orc_ngp", position, n, 0),
     CIC=lambda position, n: _deposit("orc_cic", position, n, 0),
     TSC=lambda position, n: _deposit("orc_tsc", position, n, 1),
