@@ -42,7 +42,7 @@ ALGO_BYTES = {
     "psc_green": 8.0,
     "psc_fft_c2r": 8.0,
     "psc_gradient": 16.0,          # read phi (4) + write force (12)
-    "psc_interp_kick": 60.0,       # read x,v (24) + force once per cell (12) + write v,a (24)
+    "psc_interp_kick4": 60.0,      # read x,v (24) + force once per cell (12) + write v,a (24)
 }
 
 
@@ -77,8 +77,29 @@ def synthetic_ics_numpy(N, seed=42):
     return pos, vel
 
 
+def smooth_velocity_field(N, seed, rms=1e-3, corr_cells=16.0):
+    """Gaussian random velocity field with N(0, rms) marginals and a correlation length of corr_cells
+    cells, sampled at the lattice sites: like the large-scale flows of real N-body initial conditions
+    (uncorrelated per-particle velocities would scramble the Morton order within ~10 steps, which no
+    cosmological run does)."""
+    import torch
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    k1 = torch.fft.fftfreq(N, device="cuda") * N
+    kz = torch.fft.rfftfreq(N, device="cuda") * N
+    k2 = k1[:, None, None] ** 2 + k1[None, :, None] ** 2 + kz[None, None, :] ** 2
+    filt = torch.exp(-0.5 * k2 * (2 * np.pi * corr_cells / N) ** 2 / (2 * np.pi) ** 2 * 4.0)
+    comps = []
+    for _ in range(3):
+        w = torch.randn((N, N, N), generator=g, device="cuda", dtype=torch.float32)
+        f = torch.fft.irfftn(torch.fft.rfftn(w) * filt, s=(N, N, N))
+        comps.append((f * (rms / f.std())).reshape(-1))
+        del w, f
+    return torch.stack(comps, dim=1).contiguous()
+
+
 def synthetic_ics_device(N, seed=42):
-    """Same distribution as synthetic_ics_numpy, generated on the device (512^3 on the host is slow)."""
+    """Positions as synthetic_ics_numpy (lattice + N(0, 0.3 cell) jitter), generated on the device;
+    velocities: smooth Gaussian field with N(0, 1e-3) marginals (see smooth_velocity_field)."""
     import torch
     g = torch.Generator(device="cuda").manual_seed(seed)
     ax = (torch.arange(N, device="cuda", dtype=torch.float32) + 0.5) / N
@@ -86,8 +107,8 @@ def synthetic_ics_device(N, seed=42):
     pos = pos + torch.randn(pos.shape, generator=g, device="cuda", dtype=torch.float32) * (0.3 / N)
     pos = pos - torch.floor(pos)
     pos[pos >= 1.0] = 0.0
-    vel = torch.randn(pos.shape, generator=g, device="cuda", dtype=torch.float32) * 1e-3
-    return pos.contiguous(), vel.contiguous()
+    vel = smooth_velocity_field(N, seed + 1)
+    return pos.contiguous(), vel
 
 
 class ClockSampler:
@@ -180,7 +201,7 @@ def workload_config(ncoarse):
     N = 2 ** ncoarse
     return {"workload": f"Newtonian FFT-PM leapfrog step, {N}^3 particles on {N}^3 mesh, TSC, compensated Green, "
                         f"5-pt gradient, n_reorder={N_REORDER} (BASELINE configs[0] shape at the metric's {N}^3 size)",
-            "ncells_1d": N, "npart": N ** 3, "ics": "lattice + N(0, 0.3 cell) displacement, seed 42, Morton-ordered",
+            "ncells_1d": N, "npart": N ** 3, "ics": "lattice + N(0, 0.3 cell) displacement, seed 42, Morton-ordered; velocities: Gaussian field, rms 1e-3, 16-cell correlation length (coherent flows)",
             "l2_policy": "inputs larger than L2 (particle arrays 3 x %.1f GB, grids %.2f GB vs 126 MB L2)" % (
                 12 * N ** 3 / 1e9, 4 * N ** 3 / 1e9)}
 
@@ -232,7 +253,8 @@ def run_gpu_arm(args):
 
     for _ in range(args.warmup):
         step()
-    # reorder cost (amortised below if no reorder lands in the timed steps)
+    # reorder cost (amortised below if no reorder lands in the timed steps); first call warms the allocator
+    state[0], state[1], state[2] = utils.reorder_particles(state[0], state[1], state[2])
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -275,7 +297,8 @@ def run_gpu_arm(args):
     for name, a, b in records:
         per.setdefault(name, []).append(a.elapsed_time(b))
     kern = {k: {"calls_per_step": len(v) / args.steps, "ms_per_call": float(np.mean(v)),
-                "ms_per_step": float(np.sum(v)) / args.steps} for k, v in per.items()}
+                "ms_per_step": float(np.sum(v)) / args.steps,
+                "ms_first_last": [float(np.mean(v[:3])), float(np.mean(v[-3:]))]} for k, v in per.items()}
     peak, peak_src = measured_peak_gbs()
     for k, d in kern.items():
         if k in ALGO_BYTES:
@@ -343,7 +366,7 @@ def run_gpu_arm(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50, help="default = one full n_reorder cycle")
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--ncoarse", type=int, default=9, help="log2 cells per side of the workload (9 -> 512^3)")

@@ -86,15 +86,21 @@ int psc_interp(const float *grid, const float *pos, int64_t np, int N, int ncomp
 int psc_interp_kick(const float *force, const float *pos, float *vel, float *acc, int64_t np, int N,
                     int scheme, float half_dt, float *maxout, void *stream);
 
+/* same on a float4-padded force grid [N,N,N,4] produced by psc_gradient(out_stride = 4); CIC or TSC */
+int psc_interp_kick4(const float *force4, const float *pos, float *vel, float *acc, int64_t np, int N,
+                     int scheme, float half_dt, float *maxout, void *stream);
+
 /* ---------------------------------------------------------------- grid algebra ------------- */
 /* utils.linear_operator[_inplace] (utils.py:644-717): out = f1*x + f2 (out may alias x) */
 int psc_linear_operator(const float *x, float f1, float f2, float *out, int64_t n, void *stream);
 /* utils.linear_operator_vectors_inplace (utils.py:721-755): x = f1*x + f2*y */
 int psc_lincomb(float *x, float f1, const float *y, float f2, int64_t n, void *stream);
 /* mesh.derivative / derivative_fR / add_derivative_fR (mesh.py:639-2237).  order in {2,3,5,7};
- * fr_n = 0 (plain), 1 (a + f*b^2), 2 (a + f*b^3); add != 0: force += f * grad(b^(fr_n+1)) */
+ * fr_n = 0 (plain), 1 (a + f*b^2), 2 (a + f*b^3); add != 0: force += f * grad(b^(fr_n+1)).
+ * out_stride = 3: the reference's AoS [N,N,N,3]; out_stride = 4: float4-padded [N,N,N,4] (fx,fy,fz,0),
+ * the internal layout consumed by psc_interp_kick4 (one 16-byte load per stencil point) */
 int psc_gradient(const float *a, const float *b, float f, int fr_n, int order, int add, int N,
-                 float *force, void *stream);
+                 float *force, int out_stride, void *stream);
 
 /* ---------------------------------------------------------------- Fourier ------------------ */
 /* fourier.fft_3D_real / ifft_3D_real (fourier.py:104-147, 251-294): cuFFT R2C / C2R plans for an

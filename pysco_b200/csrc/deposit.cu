@@ -57,6 +57,7 @@ __global__ void __launch_bounds__(256) deposit_atomic_kernel(const float *__rest
 }
 
 // rho = f1 * (scale * rho) + f2  (evaluated in the reference's order: scale first, then affine)
+__global__ void rho_affine_kernel(float *rho, int64_t n, float scale, float f1, float f2, int do_scale);
 __global__ void __launch_bounds__(256) rho_affine_kernel(float *__restrict__ rho, int64_t n, float scale,
                                                          float f1, float f2, int do_scale) {
   int64_t n4 = n >> 2;

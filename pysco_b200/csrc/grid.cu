@@ -54,7 +54,7 @@ __device__ __forceinline__ float fr_val(const float *__restrict__ a, const float
   return add ? f * pb : __ldg(&a[t]) + f * pb;
 }
 
-template <int ORDER, int FRN>
+template <int ORDER, int FRN, int STRIDE>
 __global__ void __launch_bounds__(128) gradient_kernel(const float *__restrict__ a,
                                                        const float *__restrict__ b, float f, int add,
                                                        int N, float *__restrict__ force) {
@@ -89,6 +89,19 @@ __global__ void __launch_bounds__(128) gradient_kernel(const float *__restrict__
       g[2] = pref * (45.0f * (-V(0, 0, -1) + V(0, 0, 1)) + 9.0f * (V(0, 0, -2) - V(0, 0, 2)) - V(0, 0, -3) + V(0, 0, 3));
     }
 #undef V
+  }
+  if (STRIDE == 4) {
+    // float4-padded layout (fx, fy, fz, 0): one 16-byte store per cell, 512 contiguous bytes per warp
+    if (k < N) {
+      float4 *dst4 = reinterpret_cast<float4 *>(force) + ((size_t)i * N2 + (size_t)j * N + k);
+      if (addb) {
+        float4 o = *dst4;
+        *dst4 = make_float4(o.x + g[0], o.y + g[1], o.z + g[2], 0.0f);
+      } else {
+        *dst4 = make_float4(g[0], g[1], g[2], 0.0f);
+      }
+    }
+    return;
   }
   stage[3 * threadIdx.x + 0] = g[0];
   stage[3 * threadIdx.x + 1] = g[1];
@@ -133,16 +146,22 @@ int psc_lincomb(float *x, float f1, const float *y, float f2, int64_t n, void *s
 }
 
 int psc_gradient(const float *a, const float *b, float f, int fr_n, int order, int add, int N,
-                 float *force, void *stream) {
+                 float *force, int out_stride, void *stream) {
   PSC_CHECK_ARG(N >= 4 && N <= 32767, "N out of range");
   PSC_CHECK_ARG(order == 2 || order == 3 || order == 5 || order == 7, "gradient order must be 2, 3, 5 or 7");
   PSC_CHECK_ARG(fr_n >= 0 && fr_n <= 2, "fR_n must be 1 or 2");
   PSC_CHECK_ARG(force && (a || add) && (b || fr_n == 0), "null pointer");
   PSC_CHECK_ARG(!(add && fr_n == 0), "add requires fr_n in {1,2}");
   PSC_CHECK_ARG(N <= 65535, "N too large for grid.y/z");
+  PSC_CHECK_ARG(out_stride == 3 || out_stride == 4, "out_stride must be 3 (AoS xyz) or 4 (float4-padded)");
+  PSC_CHECK_ARG(out_stride == 3 || ((uintptr_t)force & 15) == 0, "float4 output must be 16-byte aligned");
   dim3 grid((N + 127) / 128, N, N);
   cudaStream_t st = as_stream(stream);
-#define PSC_G(O, F) gradient_kernel<O, F><<<grid, 128, 0, st>>>(a, b, f, add, N, force)
+#define PSC_G(O, F)                                                              \
+  do {                                                                           \
+    if (out_stride == 4) gradient_kernel<O, F, 4><<<grid, 128, 0, st>>>(a, b, f, add, N, force); \
+    else gradient_kernel<O, F, 3><<<grid, 128, 0, st>>>(a, b, f, add, N, force); \
+  } while (0)
 #define PSC_GO(O)            \
   if (fr_n == 0) PSC_G(O, 0); \
   else if (fr_n == 1) PSC_G(O, 1); \

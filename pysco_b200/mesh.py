@@ -69,20 +69,22 @@ invNGP_vec, invCIC_vec, invTSC_vec = invNGP, invCIC, invTSC  # mesh.py:2627-3088
 
 def interp_kick(force, position, velocity, scheme, half_dt):
     """inv{CIC,TSC}_vec fused with v -= half_dt*a and the max|a|, max|v| reductions.
-    Returns (acceleration, maxima[2] device tensor).  velocity may be None (plain interpolation)."""
+    Returns (acceleration, maxima[2] device tensor).  velocity may be None (plain interpolation).
+    force is AoS [N,N,N,3] (reference layout) or float4-padded [N,N,N,4] (derivative(..., padded=True))."""
     c = _lib.Ctx()
     g, pos = c.dev(force), c.dev(position)
     vel = c.dev(velocity, inplace=True)
     n = pos.shape[0]
     acc = _lib.empty((n, 3))
     mx = _lib.zeros((2,))
-    _lib.check(_lib.load().psc_interp_kick(_lib.ptr(g), _lib.ptr(pos), _lib.ptr(vel), _lib.ptr(acc), n,
-                                           g.shape[0], scheme, float(half_dt), _lib.ptr(mx), _lib.stream()))
+    fn = _lib.load().psc_interp_kick4 if g.shape[-1] == 4 else _lib.load().psc_interp_kick
+    _lib.check(fn(_lib.ptr(g), _lib.ptr(pos), _lib.ptr(vel), _lib.ptr(acc), n,
+                  g.shape[0], scheme, float(half_dt), _lib.ptr(mx), _lib.stream()))
     c.finish()
     return c.ret(acc), mx
 
 
-def _gradient(a, b, f, fr_n, order, add, force=None):
+def _gradient(a, b, f, fr_n, order, add, force=None, padded=False):
     if fr_n not in (0, 1, 2):
         raise NotImplementedError(f"Unsupported: fR_n={fr_n}")
     if order not in (2, 3, 5, 7):
@@ -90,23 +92,23 @@ def _gradient(a, b, f, fr_n, order, add, force=None):
     c = _lib.Ctx()
     ta, tb = c.dev(a), c.dev(b)
     N = (ta if ta is not None else tb).shape[0]
-    out = c.dev(force, inplace=True) if add else _lib.empty((N, N, N, 3))
+    out = c.dev(force, inplace=True) if add else _lib.empty((N, N, N, 4 if padded else 3))
     _lib.check(_lib.load().psc_gradient(_lib.ptr(ta), _lib.ptr(tb), float(np.float32(f)), fr_n, order,
-                                        1 if add else 0, N, _lib.ptr(out), _lib.stream()))
+                                        1 if add else 0, N, _lib.ptr(out), out.shape[-1], _lib.stream()))
     c.finish()
     return None if add else c.ret(out)
 
 
-def derivative(a, gradient_order):
-    """mesh.py:2072-2109"""
-    return _gradient(a, None, 0.0, 0, gradient_order, False)
+def derivative(a, gradient_order, padded=False):
+    """mesh.py:2072-2109.  padded=True returns the float4-padded [N,N,N,4] layout used inside solver.pm."""
+    return _gradient(a, None, 0.0, 0, gradient_order, False, padded=padded)
 
 
-def derivative_fR(a, b, f, fR_n, gradient_order):
+def derivative_fR(a, b, f, fR_n, gradient_order, padded=False):
     """mesh.py:2112-2174"""
     if fR_n not in (1, 2):
         raise NotImplementedError(f"Unsupported: {fR_n=}")
-    return _gradient(a, b, f, fR_n, gradient_order, False)
+    return _gradient(a, b, f, fR_n, gradient_order, False, padded=padded)
 
 
 def add_derivative_fR(force, b, f, fR_n, gradient_order) -> None:

@@ -236,12 +236,12 @@ def _pm_device(position, param, potential, additional_field, tables, kick=None):
             force = fft_force(rhs, param)
             mesh.add_derivative_fR(force, additional_field, half_c2, param["fR_n"], order)
         else:
-            force = mesh.derivative_fR(potential, additional_field, half_c2, param["fR_n"], order)
+            force = mesh.derivative_fR(potential, additional_field, half_c2, param["fR_n"], order, padded=True)
     else:
         if LINEAR_NEWTON_SOLVER == "full_fft":
             force = fft_force(rhs, param)
         else:
-            force = mesh.derivative(potential, order)
+            force = mesh.derivative(potential, order, padded=True)
     del rhs
 
     velocity, half_dt = kick if kick is not None else (None, 0.0)

@@ -37,7 +37,7 @@ def test_header_symbols_exported(lib):
 def test_argument_validation_without_gpu(lib):
     L = lib.load()
     # invalid arguments are rejected before any CUDA call
-    assert L.psc_gradient(None, None, 0.0, 0, 4, 0, 16, None, None) == -1
+    assert L.psc_gradient(None, None, 0.0, 0, 4, 0, 16, None, 3, None) == -1
     assert b"order" in L.psc_last_error()
     assert L.psc_deposit(None, 10, 16, 7, 1.0, 1.0, 0.0, None, None) == -1
     assert L.psc_green(None, 16, 0, 0, 1.0, None) == -1
