@@ -12,7 +12,7 @@ import weakref
 import numpy as np
 import torch
 
-from . import _lib, solver, utils
+from . import _lib, distributed, solver, utils
 
 # maxima produced by the fused interpolation kernel, valid for exactly the (acceleration, velocity)
 # tensors returned by the last leapfrog step
@@ -23,7 +23,11 @@ def _cached_max(x, which):
     ref = _maxima_cache[which]
     if ref is not None and isinstance(x, torch.Tensor) and ref() is x and _maxima_cache["max"] is not None:
         return np.float32(_maxima_cache["max"][0 if which == "acc" else 1])
-    return utils.max_abs(x)
+    m = utils.max_abs(x)
+    if distributed.is_active():  # particle-parallel: the time step is global
+        t = torch.tensor([float(m)], dtype=torch.float32, device=_lib.device())
+        m = np.float32(distributed.allreduce_max_(t).item())
+    return m
 
 
 def dt_CFL_maxacc(acceleration, param):
@@ -78,6 +82,7 @@ def leapfrog(position, velocity, acceleration, potential, additional_field, dt, 
                                                float(half_dt), float(dt), dt_is_f64, _lib.stream()))
     _advance_clock(dt, tables, param)
     acc, pot, add, maxima = solver._pm_device(pos, param, pot, add, tables, kick=(vel, half_dt))
+    distributed.allreduce_max_(maxima)
     mx = maxima.cpu().numpy()  # one 8-byte read: max|a|, max|v| for the next integrate()
     _maxima_cache.update(acc=weakref.ref(acc), vel=weakref.ref(vel), max=mx)
     return _from_device(c, position, velocity, pos, vel, acc, pot, add)

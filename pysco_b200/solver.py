@@ -18,7 +18,7 @@ import logging
 import numpy as np
 import torch
 
-from . import _lib, cubic, fourier, iostream, laplacian, mesh, mond, multigrid, quartic, utils
+from . import _lib, cubic, distributed, fourier, iostream, laplacian, mesh, mond, multigrid, quartic, utils
 
 _C_LIGHT = 299792458.0  # astropy.constants.c (solver.py:14)
 _EMPTY = np.empty(0, dtype=np.float32)
@@ -200,7 +200,19 @@ def _pm_device(position, param, potential, additional_field, tables, kick=None):
     conversion = np.float32(ncells_1d ** 3 / param["npart"]) if ncells_1d ** 3 != param["npart"] else np.float32(1)
     pk_from_density = param["save_pk"] and "multigrid" == LINEAR_NEWTON_SOLVER
     fuse_rhs = THEORY in ("newton", "parametrized") and not pk_from_density
-    if fuse_rhs:
+    if distributed.is_active():
+        # particle-parallel / mesh-replicated: local counts -> all-reduce(sum) -> the affine maps
+        density = mesh.deposit_rhs(position, ncells_1d, scheme, 1.0, 1.0, 0.0)
+        distributed.allreduce_sum_(density)
+        if conversion != 1:
+            utils.prod_vector_scalar_inplace(density, conversion)
+        if fuse_rhs:
+            f1 = np.float32(1.5 * param["aexp"] * param["Om_m"] * param["parametrized_mu_z"])
+            utils.linear_operator_inplace(density, f1, -f1)
+            rhs = density
+            param["compute_additional_field"] = False
+            additional_field = _EMPTY
+    elif fuse_rhs:
         # deposit + rescale + 1.5 a Om mu (rho - 1) in one kernel
         f1 = np.float32(1.5 * param["aexp"] * param["Om_m"] * param["parametrized_mu_z"])
         rhs = mesh.deposit_rhs(position, ncells_1d, scheme, conversion, f1, -f1)
@@ -208,6 +220,7 @@ def _pm_device(position, param, potential, additional_field, tables, kick=None):
         additional_field = _EMPTY
     else:
         density = mesh.deposit_rhs(position, ncells_1d, scheme, conversion, 1.0, 0.0)
+    if not fuse_rhs:
         if pk_from_density:
             density_fourier = fourier.fft_3D_real(density, param["nthreads"])
             k, Pk, Nmodes = fourier.fourier_grid_to_Pk(density_fourier, param["MAS_index"])
