@@ -51,37 +51,70 @@ __device__ __forceinline__ float inv_pow_int(float w, int e) {
 }
 __device__ __forceinline__ float kfreq(int i, int N) { return (float)(i >= (N >> 1) ? i - N : i); }
 
-// One thread per complex mode; rows of N/2+1 modes are contiguous.  8 B read + 8 B write per mode.
+// Per-axis factors of the Green's functions, tabulated once per CTA in shared memory so that the
+// per-mode work is one LDS, one add and one reciprocal (the kernel then runs at memory speed: 8 B read +
+// 8 B write per mode).  tab[n] = {k_n^2 (or sin^2(pi k_n / N)), sinc(k_n / N)^(-2p)} for index n in [0, N).
+template <int KIND>
+__device__ __forceinline__ float2 green_axis_entry(int n, int N, int p) {
+  const float h = 1.0f / (float)N;
+  if (KIND == PSC_GREEN_7PT) {
+    float s = sinpif(h * kfreq(n, N));
+    return make_float2(s * s, 1.0f);
+  }
+  // plain: |k| folded as N - n above N/2 (fourier.py:475-483); compensated: signed k with n >= N/2 -> n - N
+  float k = KIND == PSC_GREEN_PLAIN ? (float)(n > (N >> 1) ? N - n : n) : kfreq(n, N);
+  float w = KIND == PSC_GREEN_COMPENSATED ? inv_pow_int(sinc_pi(k * h), 2 * p) : 1.0f;
+  return make_float2(k * k, w);
+}
+
+// Persistent CTAs walk rows (i, j) of N/2+1 contiguous modes, four rows per iteration (four independent
+// 8-byte loads in flight per thread).  The N/2 "even" modes of a row map cleanly onto the threads; the
+// Nyquist mode k = N/2 of the four rows is handled by threads 0..3 afterwards.
 template <int KIND>
 __global__ void __launch_bounds__(256) green_kernel(float2 *__restrict__ spec, int N, int p, float scale) {
-  const int nz = N / 2 + 1;
-  const int64_t total = (int64_t)N * N * nz;
+  extern __shared__ float2 gtab[];  // [N]
+  for (int n = threadIdx.x; n < N; n += blockDim.x) gtab[n] = green_axis_entry<KIND>(n, N, p);
+  __syncthreads();
+  const int nh = N / 2, nz = nh + 1;
+  const int64_t nrows = (int64_t)N * N;
   const float h = 1.0f / (float)N;
-  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total;
-       t += (int64_t)gridDim.x * blockDim.x) {
-    int k = (int)(t % nz);
-    int64_t r = t / nz;
-    int j = (int)(r % N), i = (int)(r / N);
-    float g;
-    if (KIND == PSC_GREEN_7PT) {
-      // -(h^2/4) / (sin^2(pi h kx) + sin^2(pi h ky) + sin^2(pi h kz))
-      float sx = sinpif(h * kfreq(i, N)), sy = sinpif(h * kfreq(j, N)), sz = sinpif(h * (float)k);
-      g = -(0.25f * h * h) / (sx * sx + sy * sy + sz * sz);
-    } else {
-      float kx = KIND == PSC_GREEN_PLAIN ? (float)(i > (N >> 1) ? N - i : i) : kfreq(i, N);
-      float ky = KIND == PSC_GREEN_PLAIN ? (float)(j > (N >> 1) ? N - j : j) : kfreq(j, N);
-      float kz = (float)k;
-      g = -0.0253302959105844f / (kx * kx + ky * ky + kz * kz);  // -1/(4 pi^2)
-      if (KIND == PSC_GREEN_COMPENSATED) {
-        float w = sinc_pi(kx * h) * sinc_pi(ky * h) * sinc_pi(kz * h);
-        g *= inv_pow_int(w, 2 * p);
+  // -1/(4 pi^2) for the continuous Green's functions, -(h^2/4) for the 7-point one
+  const float c = (KIND == PSC_GREEN_7PT ? -(0.25f * h * h) : -0.0253302959105844f) * scale;
+  for (int64_t r0 = (int64_t)blockIdx.x * 4; r0 < nrows; r0 += (int64_t)gridDim.x * 4) {
+    float kxy[4], wxy[4];
+    float2 *row[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const int64_t r = min(r0 + u, nrows - 1);
+      const int j = (int)(r % N), i = (int)(r / N);
+      const float2 tx = gtab[i], ty = gtab[j];
+      kxy[u] = tx.x + ty.x;
+      wxy[u] = tx.y * ty.y;
+      row[u] = spec + r * nz;
+    }
+    for (int k = threadIdx.x; k < nh; k += blockDim.x) {
+      const float2 tz = gtab[k];
+      float2 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; u++) v[u] = row[u][k];
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        float g = c * (wxy[u] * tz.y) / (kxy[u] + tz.x);
+        if (r0 + u == 0 && k == 0) g = 0.0f;  // DC mode -> 0 (reference: x[0,0,0] = 0 after the division)
+        v[u].x *= g;
+        v[u].y *= g;
+        if (r0 + u < nrows) row[u][k] = v[u];
       }
     }
-    g = (t == 0) ? 0.0f : g * scale;  // DC mode -> 0 (reference: x[0,0,0] = 0 after the division)
-    float2 v = spec[t];
-    v.x *= g;
-    v.y *= g;
-    spec[t] = v;
+    if (threadIdx.x < 4 && r0 + threadIdx.x < nrows) {
+      const int u = threadIdx.x;
+      const float2 tz = gtab[nh];
+      const float g = c * (wxy[u] * tz.y) / (kxy[u] + tz.x);
+      float2 v = row[u][nh];
+      v.x *= g;
+      v.y *= g;
+      row[u][nh] = v;
+    }
   }
 }
 
@@ -224,13 +257,15 @@ int psc_green(float *spec, int N, int kind, int p, float scale, void *stream) {
   PSC_CHECK_ARG(N >= 2, "N out of range");
   PSC_CHECK_ARG(kind >= PSC_GREEN_PLAIN && kind <= PSC_GREEN_7PT, "unknown Green's function");
   PSC_CHECK_ARG(p >= 0 && p <= 8, "MAS index out of range");
-  int64_t total = (int64_t)N * N * (N / 2 + 1);
-  int g = grid_for(total, 256);
+  PSC_CHECK_ARG(N <= 4096, "N out of range");
+  int64_t nrows = (int64_t)N * N;
+  int g = (int)((nrows + 3) / 4 < (int64_t)kNumSMs * 8 ? (nrows + 3) / 4 : (int64_t)kNumSMs * 8);
   float2 *s = reinterpret_cast<float2 *>(spec);
   cudaStream_t st = as_stream(stream);
-  if (kind == PSC_GREEN_PLAIN) green_kernel<PSC_GREEN_PLAIN><<<g, 256, 0, st>>>(s, N, p, scale);
-  else if (kind == PSC_GREEN_COMPENSATED) green_kernel<PSC_GREEN_COMPENSATED><<<g, 256, 0, st>>>(s, N, p, scale);
-  else green_kernel<PSC_GREEN_7PT><<<g, 256, 0, st>>>(s, N, p, scale);
+  const size_t smem = sizeof(float2) * N;
+  if (kind == PSC_GREEN_PLAIN) green_kernel<PSC_GREEN_PLAIN><<<g, 256, smem, st>>>(s, N, p, scale);
+  else if (kind == PSC_GREEN_COMPENSATED) green_kernel<PSC_GREEN_COMPENSATED><<<g, 256, smem, st>>>(s, N, p, scale);
+  else green_kernel<PSC_GREEN_7PT><<<g, 256, smem, st>>>(s, N, p, scale);
   count_launch();
   PSC_CHECK_LAUNCH();
   return PSC_OK;

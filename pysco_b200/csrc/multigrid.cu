@@ -89,16 +89,25 @@ __global__ void __launch_bounds__(TKX *TJ) residual_kernel(const float *__restri
   out[c.t] = (KIND == PSC_OP_LAPLACIAN) ? (-L + b[c.t]) : (-L + rhs[c.t]);
 }
 
+// sum of squared residuals: persistent CTAs loop over (i, j-tile, k-tile) tiles, one double atomic per CTA
 template <int KIND>
 __global__ void __launch_bounds__(TKX *TJ) residual_sumsq_kernel(const float *__restrict__ x,
                                                                  const float *__restrict__ b, float q, int N,
                                                                  double *__restrict__ out) {
-  Cell c = this_cell(N);
+  const int nkt = (N + TKX - 1) / TKX, njt = (N + TJ - 1) / TJ;
+  const int64_t ntiles = (int64_t)nkt * njt * N;
   double s = 0.0;
-  if (c.ok) {
-    float L = op_at<KIND>(x, b, q, c.i, c.j, c.k, c.t, N);
-    float r = (KIND == PSC_OP_LAPLACIAN) ? (-L + b[c.t]) : L;
-    s = (double)r * (double)r;
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int kt = (int)(tile % nkt);
+    const int64_t r = tile / nkt;
+    const int jt = (int)(r % njt), i = (int)(r / njt);
+    const int k = kt * TKX + threadIdx.x, j = jt * TJ + threadIdx.y;
+    if (k < N && j < N) {
+      const size_t t = ((size_t)i * N + j) * N + k;
+      float L = op_at<KIND>(x, b, q, i, j, k, t, N);
+      float res = (KIND == PSC_OP_LAPLACIAN) ? (-L + b[t]) : L;
+      s += (double)res * (double)res;
+    }
   }
   s = warp_sum(s);
   __shared__ double sm[TKX * TJ / 32];
@@ -452,7 +461,9 @@ int psc_residual_sumsq(const float *x, const float *b, float q, int N, int kind,
   PSC_CHECK_GRID(N);
   PSC_CHECK_KIND(kind);
   PSC_CHECK_ARG(x && b && sumsq_out, "null pointer");
-#define CALL(K) residual_sumsq_kernel<K><<<cell_grid(N), cell_block(), 0, as_stream(stream)>>>(x, b, q, N, sumsq_out)
+  const int64_t ntiles = (int64_t)((N + TKX - 1) / TKX) * ((N + TJ - 1) / TJ) * N;
+  const int nblk = (int)(ntiles < (int64_t)kNumSMs * 8 ? ntiles : (int64_t)kNumSMs * 8);
+#define CALL(K) residual_sumsq_kernel<K><<<nblk, cell_block(), 0, as_stream(stream)>>>(x, b, q, N, sumsq_out)
   PSC_KIND_SWITCH(kind, CALL)
 #undef CALL
   count_launch();

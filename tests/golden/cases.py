@@ -167,3 +167,21 @@ def fr_cycle_case(kind, set_units):
     f1, f2, q = fr_coeffs(param)
     param["fR_q"] = q
     return f1, f2, q, param
+
+
+def run_param(base, solver_name, ncoarse=5):
+    """param of a whole pysco.run at (2^ncoarse)^3: examples/param.ini with the size / solver overrides
+    (BASELINE config 1 shape)."""
+    N = 2 ** ncoarse
+    return {
+        "nthreads": 1, "theory": "newton", "fR_logfR0": 5, "fR_n": 1, "mond_function": "simple", "mond_g0": 1.2,
+        "mond_scale_factor_exponent": 0, "mond_alpha": 1, "parametrized_mu0": -0.1, "H0": 72, "Om_m": 0.25733,
+        "T_cmb": 2.726, "N_eff": 3.044, "w0": -1.0, "wa": 0.0, "boxlen": 100, "ncoarse": ncoarse, "npart": N ** 3,
+        "z_start": 49, "seed": 42, "position_ICS": "center", "fixed_ICS": False, "paired_ICS": False,
+        "dealiased_ICS": False, "power_spectrum_file": "/root/reference/examples/pk_lcdmw7v2.dat",
+        "initial_conditions": "2LPT", "base": base, "output_snapshot_format": "parquet",
+        "z_out": "[10, 5, 2, 1, 0.5, 0]", "save_power_spectrum": "z_out", "integrator": "leapfrog",
+        "mass_scheme": "TSC", "n_reorder": 50, "Courant_factor": 1.0, "max_aexp_stepping": 10,
+        "linear_newton_solver": solver_name, "gradient_stencil_order": 5, "Npre": 2, "Npost": 1, "epsrel": 1e-2,
+        "verbose": 0,
+    }

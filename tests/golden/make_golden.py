@@ -282,6 +282,52 @@ def g_steps():
 GROUPS = {"particles": g_particles, "grids": g_grids, "multigrid": g_multigrid, "fr": g_fr,
           "mond": g_mond, "pm": g_pm, "steps": g_steps}
 
+
+
+def g_run():
+    """Whole-run golden (BASELINE config 1 shape at 32^3): pysco.run, z = 49 -> 0, FFT and multigrid
+    solvers, leapfrog, TSC, n_reorder = 50, P(k) at the last snapshot.  The initial conditions the
+    reference generated (2LPT, seed 42) are stored so that the build starts from identical particles."""
+    import shutil
+    import pandas as pd
+    sys.path.insert(0, REF)
+    import pysco
+    import initial_conditions, cosmotable  # noqa: E401
+    out = {}
+    for solver_name in ("fft", "multigrid"):
+        base = f"/tmp/pysco_golden_run_{solver_name}/"
+        shutil.rmtree(base, ignore_errors=True)
+        param = cases.run_param(base, solver_name)
+        # capture the ICs by generating them exactly as main.run does (main.py:105-112)
+        p0 = pd.Series(dict(param))
+        p0["write_snapshot"] = False
+        p0["extra"] = "ics"
+        os.makedirs(base + "/output_00000", exist_ok=True)
+        p0["i_snap"] = 0
+        tables = cosmotable.generate(p0)
+        p0["aexp"] = 1.0 / (1 + p0["z_start"])
+        utils.set_units(p0)
+        p0["nsteps"] = 0
+        pos0, vel0 = initial_conditions.generate(p0, tables)
+        if solver_name == "fft":
+            out["ic_pos"], out["ic_vel"] = pos0.copy(), vel0.copy()
+        else:
+            assert np.array_equal(out["ic_pos"], pos0)
+        pysco.run(dict(param))
+        import pyarrow.parquet as pq
+        extra = f"newton_{solver_name}_ncoarse5"
+        snap = f"{base}/output_00006/particles_{extra}.parquet"
+        t = pq.read_table(snap)
+        out[f"{solver_name}_pos"] = np.stack([np.asarray(t[c]) for c in ("x", "y", "z")], axis=1).astype(np.float32)
+        out[f"{solver_name}_vel"] = np.stack([np.asarray(t[c]) for c in ("vx", "vy", "vz")], axis=1).astype(np.float32)
+        pks = sorted(f for f in os.listdir(f"{base}/power") if f.endswith(".dat"))
+        out[f"{solver_name}_pk_last"] = np.loadtxt(f"{base}/power/{pks[-1]}")
+        out[f"{solver_name}_nsteps"] = np.array([int(pks[-1].split("_")[-1].split(".")[0])])
+    save("run", **out)
+
+
+GROUPS["run"] = g_run
+
 if __name__ == "__main__":
     todo = sys.argv[1:] or list(GROUPS)
     for g in todo:
