@@ -90,6 +90,19 @@ int psc_interp_kick(const float *force, const float *pos, float *vel, float *acc
 int psc_interp_kick4(const float *force4, const float *pos, float *vel, float *acc, int64_t np, int N,
                      int scheme, float half_dt, float *maxout, void *stream);
 
+/* Order-independent variants on a per-step binning of the particles into 8^3-cell bins (the particle
+ * arrays themselves keep the reference's order).  psc_bin_particles fills `scratch` (size from
+ * psc_bin_workspace_bytes, 256-byte aligned) with bin offsets, the binned copy of the positions and the
+ * source row of every binned particle; the two kernels below consume it.  N must be a multiple of 8.
+ * psc_deposit_binned == psc_deposit, psc_interp_kick4_binned == psc_interp_kick4 (results are written to the
+ * particles' original rows). */
+size_t psc_bin_workspace_bytes(int64_t np, int N);
+int psc_bin_particles(const float *pos, int64_t np, int N, void *scratch, size_t scratch_bytes, void *stream);
+int psc_deposit_binned(const void *scratch, size_t scratch_bytes, int64_t np, int N, int scheme, float scale,
+                       float f1, float f2, float *rho, void *stream);
+int psc_interp_kick4_binned(const float *force4, const void *scratch, size_t scratch_bytes, float *vel, float *acc,
+                            int64_t np, int N, int scheme, float half_dt, float *maxout, void *stream);
+
 /* ---------------------------------------------------------------- grid algebra ------------- */
 /* utils.linear_operator[_inplace] (utils.py:644-717): out = f1*x + f2 (out may alias x) */
 int psc_linear_operator(const float *x, float f1, float f2, float *out, int64_t n, void *stream);

@@ -1,0 +1,375 @@
+// binned.cu -- order-independent particle <-> mesh kernels on a per-step "shadow" binning of the particles.
+//
+// Motivation (measured): the walking-window deposit and the direct gather depend on how
+// well the reference-ordered particle array is still sorted (deposit 5.0 ms right after a Morton reorder,
+// 2x that before the next one, 69 ms for a random order).  The reference order itself must not change
+// (bit-exact ordering parity), so every step the positions are COPIED into bins of 8^3 cells:
+//
+//   psc_bin_particles   count (warp-aggregated int atomics) -> exclusive scan (CUB) -> scatter of
+//                       (x,y,z) and the source row into bin order.  ~32 B / particle of traffic.
+//   psc_deposit_binned  one CTA per bin: every particle of the bin lies inside the CTA's 10^3-cell tile
+//                       (8^3 + one halo cell), so there is no bounding-box logic, no re-anchoring and no
+//                       fallback.  Each warp accumulates chunks of 32 particles into its private tile with
+//                       the conflict-free phase scheme of deposit_window.cuh (merge equal cells, 27 plain
+//                       LDS/FADD/STS phases); the four tiles are summed, the 6^3 cells no other bin can
+//                       touch are stored plainly and only the shell (784 cells per bin, ~1.5 per particle)
+//                       goes to L2 as float REDs.
+//   psc_interp_kick4_binned  one CTA per bin: the 10^3 float4 force tile is staged once in shared memory
+//                       (16 KB), every particle gathers its 27 points with LDS.128, the result is written to
+//                       the particle's ORIGINAL row (acceleration, velocity kick) through the source index.
+#include <cub/device/device_scan.cuh>
+
+#include "deposit_window.cuh"
+
+namespace psc {
+
+constexpr int BB = 8;           // bin edge in cells
+constexpr int BT = BB + 2;      // tile edge (one halo cell per side)
+constexpr int BD_WARPS = 4;     // warps per CTA in the binned deposit
+constexpr int BD_P1 = 11;       // row pitch of the per-warp tile (skews the banks), plane pitch BT * BD_P1
+constexpr int BD_P0 = BT * BD_P1;
+constexpr int BD_TILE = BT * BD_P0;  // 1100 floats per warp
+
+struct BinLayout {
+  int NB;            // bins per dimension
+  int64_t nbins;     // NB^3
+  int *counts;       // [nbins + 1]
+  int *offsets;      // [nbins + 1]  exclusive prefix sum, offsets[nbins] = np
+  int *src;          // [np] source row of the binned particle
+  float *pos;        // [np, 3] binned positions
+  void *cub_tmp;
+  size_t cub_bytes;
+};
+
+static size_t a256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+static size_t scan_tmp_bytes(int64_t n) {
+  size_t b = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, b, (const int *)nullptr, (int *)nullptr, (int)n);
+  return b;
+}
+
+static bool bin_layout(void *scratch, size_t bytes, int64_t np, int N, BinLayout &L) {
+  L.NB = N / BB;
+  L.nbins = (int64_t)L.NB * L.NB * L.NB;
+  char *p = reinterpret_cast<char *>(scratch);
+  size_t off = 0;
+  L.counts = reinterpret_cast<int *>(p + off); off += a256(sizeof(int) * (L.nbins + 1));
+  L.offsets = reinterpret_cast<int *>(p + off); off += a256(sizeof(int) * (L.nbins + 1));
+  L.src = reinterpret_cast<int *>(p + off); off += a256(sizeof(int) * (size_t)np);
+  L.pos = reinterpret_cast<float *>(p + off); off += a256(sizeof(float) * 3 * (size_t)np);
+  L.cub_tmp = p + off;
+  L.cub_bytes = scan_tmp_bytes(L.nbins + 1);
+  off += a256(L.cub_bytes);
+  return off <= bytes;
+}
+
+__device__ __forceinline__ int bin_of(float x, float y, float z, float Nf, int NB) {
+  const int i = (int)(x * Nf), j = (int)(y * Nf), k = (int)(z * Nf);
+  return ((i >> 3) * NB + (j >> 3)) * NB + (k >> 3);
+}
+
+// pass 1: counts[bin] += 1, one atomic per distinct bin per warp
+__global__ void __launch_bounds__(256) bin_count_kernel(const float *__restrict__ pos, int64_t np, int N, int NB,
+                                                        int *__restrict__ counts) {
+  const float Nf = (float)N;
+  const int lane = threadIdx.x & 31;
+  const int64_t nwarp_iters = (np + 31) >> 5;
+  const int64_t wstride = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < nwarp_iters; w += wstride) {
+    const int64_t n = w * 32 + lane;
+    int b = -1 - lane;
+    if (n < np) b = bin_of(__ldg(&pos[3 * n]), __ldg(&pos[3 * n + 1]), __ldg(&pos[3 * n + 2]), Nf, NB);
+    const unsigned peers = __match_any_sync(0xffffffffu, b);
+    if (b >= 0 && (__ffs(peers) - 1) == lane) atomicAdd(&counts[b], __popc(peers));
+  }
+}
+
+// pass 2: slot = offsets[bin] + (claimed range in the bin); counts[] is consumed (counted down to zero)
+__global__ void __launch_bounds__(256) bin_scatter_kernel(const float *__restrict__ pos, int64_t np, int N, int NB,
+                                                          int *__restrict__ counts, const int *__restrict__ offsets,
+                                                          float *__restrict__ bpos, int *__restrict__ bsrc) {
+  const float Nf = (float)N;
+  const int lane = threadIdx.x & 31;
+  const int64_t nwarp_iters = (np + 31) >> 5;
+  const int64_t wstride = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < nwarp_iters; w += wstride) {
+    const int64_t n = w * 32 + lane;
+    float x = 0.f, y = 0.f, z = 0.f;
+    int b = -1 - lane;
+    if (n < np) {
+      x = __ldg(&pos[3 * n]); y = __ldg(&pos[3 * n + 1]); z = __ldg(&pos[3 * n + 2]);
+      b = bin_of(x, y, z, Nf, NB);
+    }
+    const unsigned peers = __match_any_sync(0xffffffffu, b);
+    const int leader = __ffs(peers) - 1;
+    int base = 0;
+    if (b >= 0 && leader == lane) {
+      const int cnt = __popc(peers);
+      base = atomicSub(&counts[b], cnt) - cnt;
+    }
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (b >= 0) {
+      const int slot = offsets[b] + base + __popc(peers & ((1u << lane) - 1u));
+      bpos[3 * (size_t)slot + 0] = x;
+      bpos[3 * (size_t)slot + 1] = y;
+      bpos[3 * (size_t)slot + 2] = z;
+      bsrc[slot] = (int)n;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------- deposit
+template <int SCHEME>
+__global__ void __launch_bounds__(BD_WARPS * 32) deposit_binned_kernel(const float *__restrict__ bpos,
+                                                                       const int *__restrict__ offsets, int N, int NB,
+                                                                       float *__restrict__ rho) {
+  __shared__ float tiles[BD_WARPS][BD_TILE];
+  const int b = blockIdx.x;
+  const int beg = offsets[b], end = offsets[b + 1];
+  if (beg == end) return;  // rho was zeroed by the caller
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int bk = b % NB, bj = (b / NB) % NB, bi = b / (NB * NB);
+  const int oi = bi * BB - 1, oj = bj * BB - 1, ok = bk * BB - 1;  // absolute cell of tile cell (0,0,0)
+  const float Nf = (float)N;
+  float *tile = tiles[warp];
+  for (int t = lane; t < BD_TILE; t += 32) tile[t] = 0.0f;
+  __syncwarp();
+  for (int c = beg + warp * 32; c < end; c += BD_WARPS * 32) {
+    const int n = c + lane;
+    const bool valid = n < end;
+    float px = 0.f, py = 0.f, pz = 0.f;
+    if (valid) { px = __ldg(&bpos[3 * (size_t)n]); py = __ldg(&bpos[3 * (size_t)n + 1]); pz = __ldg(&bpos[3 * (size_t)n + 2]); }
+    int i, j, k;
+    float wx[3], wy[3], wz[3];
+    axis_weights<SCHEME>(px * Nf, N, i, wx[0], wx[1], wx[2]);
+    axis_weights<SCHEME>(py * Nf, N, j, wy[0], wy[1], wy[2]);
+    axis_weights<SCHEME>(pz * Nf, N, k, wz[0], wz[1], wz[2]);
+    const int t0 = i - oi, t1 = j - oj, t2 = k - ok;  // in [1, 8] for every particle of this bin
+    float wgt[27];
+#pragma unroll
+    for (int a = 0; a < 3; a++)
+#pragma unroll
+      for (int e = 0; e < 3; e++) {
+        const float wxy = wx[a] * wy[e];
+#pragma unroll
+        for (int g = 0; g < 3; g++) wgt[(a * 3 + e) * 3 + g] = wxy * wz[g];
+      }
+    // merge lanes of equal cell into the lowest lane of the group
+    const int cellkey = valid ? t0 * BD_P0 + t1 * BD_P1 + t2 : -1 - lane;
+    const unsigned peers = __match_any_sync(0xffffffffu, cellkey);
+    const bool is_leader = valid && (__ffs(peers) - 1) == lane;
+    unsigned rest = is_leader ? (peers & ~(1u << lane)) : 0u;
+    while (__any_sync(0xffffffffu, rest != 0u)) {
+      const int src = rest ? (__ffs(rest) - 1) : lane;
+#pragma unroll
+      for (int q = 0; q < 27; q++) {
+        const float v = __shfl_sync(0xffffffffu, wgt[q], src);
+        if (rest) wgt[q] += v;
+      }
+      rest &= rest - 1;
+    }
+    // 27 conflict-free phases: distinct cells + identical offset => distinct addresses
+    float *cell0 = tile + (t0 - 1) * BD_P0 + (t1 - 1) * BD_P1 + (t2 - 1);
+#pragma unroll
+    for (int a = 0; a < 3; a++)
+#pragma unroll
+      for (int e = 0; e < 3; e++)
+#pragma unroll
+        for (int g = 0; g < 3; g++) {
+          if (SCHEME == PSC_NGP && !(a == 1 && e == 1 && g == 1)) continue;
+          if (is_leader) {
+            float *p = cell0 + a * BD_P0 + e * BD_P1 + g;
+            *p += wgt[(a * 3 + e) * 3 + g];
+          }
+          __syncwarp();
+        }
+  }
+  __syncthreads();
+  // sum the per-warp tiles; cells no other bin can reach (2 <= t <= 7 in every dimension) are stored,
+  // the shell is added to L2
+  const size_t N2 = (size_t)N * N;
+  for (int t = threadIdx.x; t < BT * BT * BT; t += BD_WARPS * 32) {
+    const int g = t % BT, r = t / BT;
+    const int e = r % BT, a = r / BT;
+    const int s = a * BD_P0 + e * BD_P1 + g;
+    float v = tiles[0][s];
+#pragma unroll
+    for (int w = 1; w < BD_WARPS; w++) v += tiles[w][s];
+    const int gi = wrap(oi + a, N), gj = wrap(oj + e, N), gk = wrap(ok + g, N);
+    float *dst = rho + (size_t)gi * N2 + (size_t)gj * N + gk;
+    const bool mine = a >= 2 && a <= BT - 3 && e >= 2 && e <= BT - 3 && g >= 2 && g <= BT - 3;
+    if (mine) *dst = v;
+    else if (v != 0.0f) atomicAdd(dst, v);
+  }
+}
+
+// ------------------------------------------------------------------------------- interpolation
+constexpr int BI_THREADS = 128;
+
+template <int SCHEME>
+__global__ void __launch_bounds__(BI_THREADS) interp_kick4_binned_kernel(
+    const float4 *__restrict__ force4, const float *__restrict__ bpos, const int *__restrict__ bsrc,
+    const int *__restrict__ offsets, float *__restrict__ vel, float *__restrict__ accel, int N, int NB,
+    float half_dt, float *__restrict__ maxout) {
+  __shared__ float4 tile[BT * BT * BT];  // 16,000 B
+  __shared__ float s_max[BI_THREADS / 32][2];
+  const int b = blockIdx.x;
+  const int beg = offsets[b], end = offsets[b + 1];
+  if (beg == end) return;
+  const int bk = b % NB, bj = (b / NB) % NB, bi = b / (NB * NB);
+  const int oi = bi * BB - 1, oj = bj * BB - 1, ok = bk * BB - 1;
+  const size_t N2 = (size_t)N * N;
+  for (int t = threadIdx.x; t < BT * BT * BT; t += BI_THREADS) {
+    const int g = t % BT, r = t / BT;
+    const int e = r % BT, a = r / BT;
+    tile[t] = __ldg(&force4[(size_t)wrap(oi + a, N) * N2 + (size_t)wrap(oj + e, N) * N + wrap(ok + g, N)]);
+  }
+  __syncthreads();
+  const float Nf = (float)N;
+  const float mh = -half_dt;
+  float ma = 0.0f, mv = 0.0f;
+  for (int n = beg + threadIdx.x; n < end; n += BI_THREADS) {
+    const float px = __ldg(&bpos[3 * (size_t)n]), py = __ldg(&bpos[3 * (size_t)n + 1]), pz = __ldg(&bpos[3 * (size_t)n + 2]);
+    const int row = __ldg(&bsrc[n]);
+    int i, j, k;
+    float wx[3], wy[3], wz[3];
+    axis_weights<SCHEME>(px * Nf, N, i, wx[0], wx[1], wx[2]);
+    axis_weights<SCHEME>(py * Nf, N, j, wy[0], wy[1], wy[2]);
+    axis_weights<SCHEME>(pz * Nf, N, k, wz[0], wz[1], wz[2]);
+    const float4 *c0 = tile + ((i - oi - 1) * BT + (j - oj - 1)) * BT + (k - ok - 1);
+    float ax = 0.0f, ay = 0.0f, az = 0.0f;
+#pragma unroll
+    for (int a = 0; a < 3; a++)
+#pragma unroll
+      for (int e = 0; e < 3; e++) {
+        const float wxy = wx[a] * wy[e];
+#pragma unroll
+        for (int g = 0; g < 3; g++) {
+          const float w = wxy * wz[g];
+          const float4 f = c0[(a * BT + e) * BT + g];
+          ax += w * f.x; ay += w * f.y; az += w * f.z;
+        }
+      }
+    float *ap = accel + 3 * (size_t)row;
+    ap[0] = ax; ap[1] = ay; ap[2] = az;
+    ma = fmaxf(ma, fmaxf(fabsf(ax), fmaxf(fabsf(ay), fabsf(az))));
+    if (vel) {
+      float *vp = vel + 3 * (size_t)row;
+      const float v0 = vp[0] + mh * ax, v1 = vp[1] + mh * ay, v2 = vp[2] + mh * az;
+      vp[0] = v0; vp[1] = v1; vp[2] = v2;
+      mv = fmaxf(mv, fmaxf(fabsf(v0), fmaxf(fabsf(v1), fabsf(v2))));
+    }
+  }
+  ma = warp_max(ma);
+  mv = warp_max(mv);
+  if ((threadIdx.x & 31) == 0) { s_max[threadIdx.x >> 5][0] = ma; s_max[threadIdx.x >> 5][1] = mv; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int w = 1; w < BI_THREADS / 32; w++) { ma = fmaxf(ma, s_max[w][0]); mv = fmaxf(mv, s_max[w][1]); }
+    atomic_max_nonneg(&maxout[0], ma);
+    atomic_max_nonneg(&maxout[1], mv);
+  }
+}
+
+// rho = f1 * (scale * rho) + f2, defined in deposit.cu
+__global__ void rho_affine_kernel(float *rho, int64_t n, float scale, float f1, float f2, int do_scale);
+
+}  // namespace psc
+
+using namespace psc;
+
+extern "C" {
+
+size_t psc_bin_workspace_bytes(int64_t np, int N) {
+  if (np < 0 || N < BB || (N % BB) != 0) return 0;
+  const int64_t nbins = (int64_t)(N / BB) * (N / BB) * (N / BB);
+  return 2 * a256(sizeof(int) * (nbins + 1)) + a256(sizeof(int) * (size_t)np) + a256(sizeof(float) * 3 * (size_t)np) +
+         a256(scan_tmp_bytes(nbins + 1)) + 256;
+}
+
+int psc_bin_particles(const float *pos, int64_t np, int N, void *scratch, size_t scratch_bytes, void *stream) {
+  PSC_CHECK_ARG(np >= 0 && np < ((int64_t)1 << 31), "np out of range");
+  PSC_CHECK_ARG(N >= BB && (N % BB) == 0 && N <= 32767, "N must be a multiple of 8");
+  PSC_CHECK_ARG(scratch && (pos || np == 0), "null pointer");
+  PSC_CHECK_ARG(((uintptr_t)scratch & 255) == 0, "scratch must be 256-byte aligned");
+  BinLayout L;
+  if (!bin_layout(scratch, scratch_bytes, np, N, L)) {
+    set_error("psc_bin_particles: scratch too small");
+    return PSC_ERR_WORKSPACE;
+  }
+  cudaStream_t st = as_stream(stream);
+  PSC_CUDA(cudaMemsetAsync(L.counts, 0, sizeof(int) * (L.nbins + 1), st));
+  if (np > 0) {
+    bin_count_kernel<<<grid_for(np, 256, 8), 256, 0, st>>>(pos, np, N, L.NB, L.counts);
+    count_launch();
+  }
+  cudaError_t e = cub::DeviceScan::ExclusiveSum(L.cub_tmp, L.cub_bytes, L.counts, L.offsets, (int)(L.nbins + 1), st);
+  count_launch(2);
+  if (e != cudaSuccess) {
+    set_error("psc_bin_particles: cub scan failed: %s", cudaGetErrorString(e));
+    return PSC_ERR_CUDA;
+  }
+  if (np > 0) {
+    bin_scatter_kernel<<<grid_for(np, 256, 8), 256, 0, st>>>(pos, np, N, L.NB, L.counts, L.offsets, L.pos, L.src);
+    count_launch();
+  }
+  PSC_CHECK_LAUNCH();
+  return PSC_OK;
+}
+
+int psc_deposit_binned(const void *scratch, size_t scratch_bytes, int64_t np, int N, int scheme, float scale, float f1,
+                       float f2, float *rho, void *stream) {
+  PSC_CHECK_ARG(scheme == PSC_NGP || scheme == PSC_CIC || scheme == PSC_TSC, "unknown mass scheme");
+  PSC_CHECK_ARG(N >= BB && (N % BB) == 0, "N must be a multiple of 8");
+  PSC_CHECK_ARG(scratch && rho, "null pointer");
+  BinLayout L;
+  if (!bin_layout(const_cast<void *>(scratch), scratch_bytes, np, N, L)) {
+    set_error("psc_deposit_binned: scratch too small");
+    return PSC_ERR_WORKSPACE;
+  }
+  cudaStream_t st = as_stream(stream);
+  const int64_t n3 = (int64_t)N * N * N;
+  PSC_CUDA(cudaMemsetAsync(rho, 0, sizeof(float) * n3, st));
+  if (np > 0) {
+    const int grid = (int)L.nbins;
+    if (scheme == PSC_TSC) deposit_binned_kernel<PSC_TSC><<<grid, BD_WARPS * 32, 0, st>>>(L.pos, L.offsets, N, L.NB, rho);
+    else if (scheme == PSC_CIC) deposit_binned_kernel<PSC_CIC><<<grid, BD_WARPS * 32, 0, st>>>(L.pos, L.offsets, N, L.NB, rho);
+    else deposit_binned_kernel<PSC_NGP><<<grid, BD_WARPS * 32, 0, st>>>(L.pos, L.offsets, N, L.NB, rho);
+    count_launch();
+    PSC_CHECK_LAUNCH();
+  }
+  if (scale != 1.0f || f1 != 1.0f || f2 != 0.0f) {
+    rho_affine_kernel<<<grid_for((n3 + 3) / 4, 256), 256, 0, st>>>(rho, n3, scale, f1, f2, scale != 1.0f);
+    count_launch();
+    PSC_CHECK_LAUNCH();
+  }
+  return PSC_OK;
+}
+
+int psc_interp_kick4_binned(const float *force4, const void *scratch, size_t scratch_bytes, float *vel, float *acc,
+                            int64_t np, int N, int scheme, float half_dt, float *maxout, void *stream) {
+  PSC_CHECK_ARG(scheme == PSC_CIC || scheme == PSC_TSC, "mass scheme must be CIC or TSC");
+  PSC_CHECK_ARG(N >= BB && (N % BB) == 0, "N must be a multiple of 8");
+  PSC_CHECK_ARG(force4 && scratch && acc && maxout, "null pointer");
+  PSC_CHECK_ARG(((uintptr_t)force4 & 15) == 0, "force4 must be 16-byte aligned");
+  if (np == 0) return PSC_OK;
+  BinLayout L;
+  if (!bin_layout(const_cast<void *>(scratch), scratch_bytes, np, N, L)) {
+    set_error("psc_interp_kick4_binned: scratch too small");
+    return PSC_ERR_WORKSPACE;
+  }
+  cudaStream_t st = as_stream(stream);
+  const float4 *f4 = reinterpret_cast<const float4 *>(force4);
+  const int grid = (int)L.nbins;
+  if (scheme == PSC_TSC)
+    interp_kick4_binned_kernel<PSC_TSC><<<grid, BI_THREADS, 0, st>>>(f4, L.pos, L.src, L.offsets, vel, acc, N, L.NB, half_dt, maxout);
+  else
+    interp_kick4_binned_kernel<PSC_CIC><<<grid, BI_THREADS, 0, st>>>(f4, L.pos, L.src, L.offsets, vel, acc, N, L.NB, half_dt, maxout);
+  count_launch();
+  PSC_CHECK_LAUNCH();
+  return PSC_OK;
+}
+
+}  // extern "C"

@@ -6,13 +6,43 @@ import torch
 from . import _lib
 
 
-def _deposit(position, ncells_1d, scheme, scale=1.0, f1=1.0, f2=0.0):
+class Binned:
+    """Per-step shadow binning of the particles into 8^3-cell bins (csrc/binned.cu): bin offsets, a binned
+    copy of the positions and the source row of every binned particle, in one device scratch buffer."""
+
+    def __init__(self, scratch, np_, N):
+        self.scratch, self.np, self.N = scratch, np_, N
+
+
+def can_bin(N, np_):
+    return N >= 8 and N % 8 == 0 and 0 < np_ < 2 ** 31
+
+
+def bin_particles(position, ncells_1d):
+    """Bin a device position array; returns a Binned handle for deposit_rhs / interp_kick."""
+    pos = _lib.Ctx().dev(position)
+    N, n = int(ncells_1d), pos.shape[0]
+    lib = _lib.load()
+    nbytes = int(lib.psc_bin_workspace_bytes(n, N))
+    scratch = _lib.empty((nbytes,), torch.uint8)
+    _lib.check(lib.psc_bin_particles(_lib.ptr(pos), n, N, _lib.ptr(scratch), nbytes, _lib.stream()))
+    return Binned(scratch, n, N)
+
+
+def _deposit(position, ncells_1d, scheme, scale=1.0, f1=1.0, f2=0.0, binned=None):
     c = _lib.Ctx()
     pos = c.dev(position)
     N = int(ncells_1d)
     rho = _lib.empty((N, N, N))
-    _lib.check(_lib.load().psc_deposit(_lib.ptr(pos), pos.shape[0], N, scheme, float(scale), float(f1),
-                                       float(f2), _lib.ptr(rho), _lib.stream()))
+    lib = _lib.load()
+    if binned is None and can_bin(N, pos.shape[0]):
+        binned = bin_particles(pos, N)
+    if binned is not None:
+        _lib.check(lib.psc_deposit_binned(_lib.ptr(binned.scratch), binned.scratch.numel(), binned.np, N, scheme,
+                                          float(scale), float(f1), float(f2), _lib.ptr(rho), _lib.stream()))
+    else:
+        _lib.check(lib.psc_deposit(_lib.ptr(pos), pos.shape[0], N, scheme, float(scale), float(f1),
+                                   float(f2), _lib.ptr(rho), _lib.stream()))
     return c.ret(rho)
 
 
@@ -34,10 +64,10 @@ def TSC(position, ncells_1d):
 TSC_seq = TSC  # mesh.py:2363-2462: same result, the reference's sequential variant
 
 
-def deposit_rhs(position, ncells_1d, scheme, scale, f1, f2):
+def deposit_rhs(position, ncells_1d, scheme, scale, f1, f2, binned=None):
     """Fused mass assignment + density rescale + Poisson right-hand side (solver.py:80-116, 444-449):
-    f1 * (scale * deposit) + f2 in one pass over the grid."""
-    return _deposit(position, ncells_1d, scheme, scale, f1, f2)
+    f1 * (scale * deposit) + f2.  binned: a Binned handle of the same positions (shared with interp_kick)."""
+    return _deposit(position, ncells_1d, scheme, scale, f1, f2, binned)
 
 
 def _interp(grid, position, scheme):
@@ -67,7 +97,7 @@ def invTSC(grid, position):
 invNGP_vec, invCIC_vec, invTSC_vec = invNGP, invCIC, invTSC  # mesh.py:2627-3088 (AoS [N,N,N,3] grid)
 
 
-def interp_kick(force, position, velocity, scheme, half_dt):
+def interp_kick(force, position, velocity, scheme, half_dt, binned=None):
     """inv{CIC,TSC}_vec fused with v -= half_dt*a and the max|a|, max|v| reductions.
     Returns (acceleration, maxima[2] device tensor).  velocity may be None (plain interpolation).
     force is AoS [N,N,N,3] (reference layout) or float4-padded [N,N,N,4] (derivative(..., padded=True))."""
@@ -77,9 +107,14 @@ def interp_kick(force, position, velocity, scheme, half_dt):
     n = pos.shape[0]
     acc = _lib.empty((n, 3))
     mx = _lib.zeros((2,))
-    fn = _lib.load().psc_interp_kick4 if g.shape[-1] == 4 else _lib.load().psc_interp_kick
-    _lib.check(fn(_lib.ptr(g), _lib.ptr(pos), _lib.ptr(vel), _lib.ptr(acc), n,
-                  g.shape[0], scheme, float(half_dt), _lib.ptr(mx), _lib.stream()))
+    if binned is not None and g.shape[-1] == 4 and scheme != _lib.NGP:
+        _lib.check(_lib.load().psc_interp_kick4_binned(
+            _lib.ptr(g), _lib.ptr(binned.scratch), binned.scratch.numel(), _lib.ptr(vel), _lib.ptr(acc), n,
+            g.shape[0], scheme, float(half_dt), _lib.ptr(mx), _lib.stream()))
+    else:
+        fn = _lib.load().psc_interp_kick4 if g.shape[-1] == 4 else _lib.load().psc_interp_kick
+        _lib.check(fn(_lib.ptr(g), _lib.ptr(pos), _lib.ptr(vel), _lib.ptr(acc), n,
+                      g.shape[0], scheme, float(half_dt), _lib.ptr(mx), _lib.stream()))
     c.finish()
     return c.ret(acc), mx
 

@@ -198,11 +198,13 @@ def _pm_device(position, param, potential, additional_field, tables, kick=None):
             f"{param['linear_newton_solver']=}, should be multigrid, fft, fft_7pt or full_fft")
 
     conversion = np.float32(ncells_1d ** 3 / param["npart"]) if ncells_1d ** 3 != param["npart"] else np.float32(1)
+    # one shadow binning of the particles per step, shared by the deposit and the interpolation
+    binned = mesh.bin_particles(position, ncells_1d) if mesh.can_bin(ncells_1d, position.shape[0]) else None
     pk_from_density = param["save_pk"] and "multigrid" == LINEAR_NEWTON_SOLVER
     fuse_rhs = THEORY in ("newton", "parametrized") and not pk_from_density
     if distributed.is_active():
         # particle-parallel / mesh-replicated: local counts -> all-reduce(sum) -> the affine maps
-        density = mesh.deposit_rhs(position, ncells_1d, scheme, 1.0, 1.0, 0.0)
+        density = mesh.deposit_rhs(position, ncells_1d, scheme, 1.0, 1.0, 0.0, binned)
         distributed.allreduce_sum_(density)
         if conversion != 1:
             utils.prod_vector_scalar_inplace(density, conversion)
@@ -215,11 +217,11 @@ def _pm_device(position, param, potential, additional_field, tables, kick=None):
     elif fuse_rhs:
         # deposit + rescale + 1.5 a Om mu (rho - 1) in one kernel
         f1 = np.float32(1.5 * param["aexp"] * param["Om_m"] * param["parametrized_mu_z"])
-        rhs = mesh.deposit_rhs(position, ncells_1d, scheme, conversion, f1, -f1)
+        rhs = mesh.deposit_rhs(position, ncells_1d, scheme, conversion, f1, -f1, binned)
         param["compute_additional_field"] = False
         additional_field = _EMPTY
     else:
-        density = mesh.deposit_rhs(position, ncells_1d, scheme, conversion, 1.0, 0.0)
+        density = mesh.deposit_rhs(position, ncells_1d, scheme, conversion, 1.0, 0.0, binned)
     if not fuse_rhs:
         if pk_from_density:
             density_fourier = fourier.fft_3D_real(density, param["nthreads"])
@@ -258,7 +260,8 @@ def _pm_device(position, param, potential, additional_field, tables, kick=None):
     del rhs
 
     velocity, half_dt = kick if kick is not None else (None, 0.0)
-    acceleration, maxima = mesh.interp_kick(force, position, velocity, scheme, half_dt)
+    acceleration, maxima = mesh.interp_kick(force, position, velocity, scheme, half_dt, binned)
+    del binned
     del force
     return acceleration, potential, additional_field, (maxima if kick is not None else None)
 

@@ -75,6 +75,18 @@ for name, p in cases.items():
     os.environ.pop("PSC_INTERP_MODE", None)
     t_ww = timeit(lambda: raw.psc_interp_kick4(force4.data_ptr(), p.data_ptr(), vel2.data_ptr(), acc4.data_ptr(), np_, N, 2, 0.0, mxo.data_ptr(), None))
     errw = (a_ref - acc4).abs().max().item()
+    from pysco_b200 import mesh as _m
+    t_bin = timeit(lambda: _m.bin_particles(p, N))
+    bn = _m.bin_particles(p, N)
+    t_dep_b = timeit(lambda: _m.deposit_rhs(p, N, 2, 1.0, 1.0, 0.0, bn))
+    rho_b = _m.deposit_rhs(p, N, 2, 1.0, 1.0, 0.0, bn)
+    err_b = (rho_b - ref).abs().max().item()
+    vel3 = vel.clone()
+    t_int_b = timeit(lambda: _m.interp_kick(force4, p, vel3, 2, 0.0, bn))
+    a_b, _ = _m.interp_kick(force4, p, None, 2, 0.0, bn)
+    err_ib = (a_b - a_ref).abs().max().item()
+    print(f"N={N} {name:18s} BINNED: bin {t_bin:6.3f} ms  deposit {t_dep_b:6.3f} ms (maxdiff {err_b:.1e})  "
+          f"interp_kick {t_int_b:6.3f} ms (maxdiff {err_ib:.1e})", flush=True)
     print(f"N={N} {name:18s} deposit(total) {t_win:7.3f} ms  fallback {100.0 * st[0] / np_:6.2f}%  "
           f"floats RED'ed/particle {4.0 * st[1] / np_:5.2f}  reanchors/1k {1000.0 * st[2] / np_:6.2f}  "
           f"rerun maxdiff {err:.1e} mass {mass:.7f} | interp_kick {t_int:7.3f} ms | direct float4 {t_int4:7.3f} ms (maxdiff {err4:.1e}) | warp-window float4 {t_ww:7.3f} ms (maxdiff {errw:.1e})", flush=True)
