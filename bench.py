@@ -44,6 +44,7 @@ ALGO_BYTES = {
     "psc_gradient": 16.0,          # read phi (4) + write force (12)
     "psc_interp_kick4": 60.0,      # read x,v (24) + force once per cell (12) + write v,a (24)
     "psc_interp_kick4_binned": 60.0,
+    "psc_interp_kick_phi_binned": 76.0,   # gradient (16) + interpolation/kick (60) in one kernel
     "psc_deposit_binned": 16.0,
     "psc_bin_particles": 0.0,      # pure overhead of the order-independent scheme (not in the 176 B budget)
 }
@@ -314,6 +315,8 @@ def run_gpu_arm(args):
         if ALGO_BYTES.get(k, 0) > 0:
             # particle kernels see N^3 / world particles per rank, grid kernels the full (replicated) mesh
             units = N ** 3 / world if k in ("psc_kick_drift_wrap", "psc_interp_kick4", "psc_interp_kick4_binned") else N ** 3
+            if k == "psc_interp_kick_phi_binned":
+                units = N ** 3 * (60.0 / world + 16.0) / 76.0
             if k in ("psc_deposit", "psc_deposit_binned"):
                 units = N ** 3 * (12.0 / world + 4.0) / 16.0
             d["algo_bytes"] = ALGO_BYTES[k] * units

@@ -103,6 +103,13 @@ int psc_deposit_binned(const void *scratch, size_t scratch_bytes, int64_t np, in
 int psc_interp_kick4_binned(const float *force4, const void *scratch, size_t scratch_bytes, float *vel, float *acc,
                             int64_t np, int N, int scheme, float half_dt, float *maxout, void *stream);
 
+/* mesh.derivative / derivative_fR (mesh.py:639-2174) fused into the binned interpolation + kick: every bin's CTA
+ * derives its force tile from the potential phi (and, for f(R), the scalaron u: phi + f * u^(fr_n+1)) in shared
+ * memory, so neither the gradient kernel nor the force grid exist in the step.  fr_n = 0: plain. */
+int psc_interp_kick_phi_binned(const float *phi, const float *u, float f, int fr_n, int order, const void *scratch,
+                               size_t scratch_bytes, float *vel, float *acc, int64_t np, int N, int scheme,
+                               float half_dt, float *maxout, void *stream);
+
 /* ---------------------------------------------------------------- grid algebra ------------- */
 /* utils.linear_operator[_inplace] (utils.py:644-717): out = f1*x + f2 (out may alias x) */
 int psc_linear_operator(const float *x, float f1, float f2, float *out, int64_t n, void *stream);

@@ -273,6 +273,110 @@ __global__ void __launch_bounds__(BI_THREADS) interp_kick4_binned_kernel(
   }
 }
 
+// ------------------------------------------------------- gradient fused into the interpolation
+// Same as interp_kick4_binned_kernel, but the CTA derives its 10^3 force tile itself from the potential:
+// it stages the (10 + 2H)^3 potential tile (H = stencil reach: 1, 1, 2, 3 for orders 2, 3, 5, 7), applies
+// the finite-difference stencil of mesh.derivative{2,3,5,7} (mesh.py:639-850) in shared memory and gathers
+// from the result.  For f(R) the tile holds phi + f * u^(n+1) (mesh.derivative*_fR_n{1,2}).  This removes
+// the gradient kernel and the force grid (16 B/cell written + re-read) from the step.
+template <int ORDER> struct Reach { static constexpr int H = ORDER == 7 ? 3 : ORDER == 5 ? 2 : 1; };
+
+template <int SCHEME, int ORDER>
+__global__ void __launch_bounds__(BI_THREADS) interp_kick_phi_binned_kernel(
+    const float *__restrict__ phi, const float *__restrict__ u, float f, int fr_n,
+    const float *__restrict__ bpos, const int *__restrict__ bsrc, const int *__restrict__ offsets,
+    float *__restrict__ vel, float *__restrict__ accel, int N, int NB, float half_dt, float *__restrict__ maxout) {
+  constexpr int H = Reach<ORDER>::H;
+  constexpr int PT = BT + 2 * H;  // potential tile edge
+  __shared__ float ptile[PT * PT * PT];
+  __shared__ float4 tile[BT * BT * BT];
+  __shared__ float s_max[BI_THREADS / 32][2];
+  const int b = blockIdx.x;
+  const int beg = offsets[b], end = offsets[b + 1];
+  if (beg == end) return;
+  const int bk = b % NB, bj = (b / NB) % NB, bi = b / (NB * NB);
+  const int oi = bi * BB - 1, oj = bj * BB - 1, ok = bk * BB - 1;
+  const size_t N2 = (size_t)N * N;
+  for (int t = threadIdx.x; t < PT * PT * PT; t += BI_THREADS) {
+    const int g = t % PT, r = t / PT;
+    const int e = r % PT, a = r / PT;
+    int gi = oi - H + a, gj = oj - H + e, gk = ok - H + g;
+    gi += gi < 0 ? N : 0; gi -= gi >= N ? N : 0;
+    gj += gj < 0 ? N : 0; gj -= gj >= N ? N : 0;
+    gk += gk < 0 ? N : 0; gk -= gk >= N ? N : 0;
+    const size_t c = (size_t)gi * N2 + (size_t)gj * N + gk;
+    float v = __ldg(&phi[c]);
+    if (fr_n) {
+      const float w = __ldg(&u[c]);
+      v += f * (fr_n == 1 ? w * w : w * w * w);
+    }
+    ptile[t] = v;
+  }
+  __syncthreads();
+  const float pref = ORDER == 2 ? (float)N : ORDER == 3 ? (float)(0.5 * N) : ORDER == 5 ? (float)(N / 12.0) : (float)(N / 60.0);
+  for (int t = threadIdx.x; t < BT * BT * BT; t += BI_THREADS) {
+    const int g = t % BT, r = t / BT;
+    const int e = r % BT, a = r / BT;
+    const float *c = ptile + ((a + H) * PT + (e + H)) * PT + (g + H);
+    float gr[3];
+#pragma unroll
+    for (int d = 0; d < 3; d++) {
+      const int s = d == 0 ? PT * PT : d == 1 ? PT : 1;
+      if (ORDER == 2) gr[d] = pref * (-c[0] + c[s]);
+      else if (ORDER == 3) gr[d] = pref * (-c[-s] + c[s]);
+      else if (ORDER == 5) gr[d] = pref * (8.0f * (-c[-s] + c[s]) + c[-2 * s] - c[2 * s]);
+      else gr[d] = pref * (45.0f * (-c[-s] + c[s]) + 9.0f * (c[-2 * s] - c[2 * s]) - c[-3 * s] + c[3 * s]);
+    }
+    tile[t] = make_float4(gr[0], gr[1], gr[2], 0.0f);
+  }
+  __syncthreads();
+  const float Nf = (float)N;
+  const float mh = -half_dt;
+  float ma = 0.0f, mv = 0.0f;
+  for (int n = beg + threadIdx.x; n < end; n += BI_THREADS) {
+    const float px = __ldg(&bpos[3 * (size_t)n]), py = __ldg(&bpos[3 * (size_t)n + 1]), pz = __ldg(&bpos[3 * (size_t)n + 2]);
+    const int row = __ldg(&bsrc[n]);
+    int i, j, k;
+    float wx[3], wy[3], wz[3];
+    axis_weights<SCHEME>(px * Nf, N, i, wx[0], wx[1], wx[2]);
+    axis_weights<SCHEME>(py * Nf, N, j, wy[0], wy[1], wy[2]);
+    axis_weights<SCHEME>(pz * Nf, N, k, wz[0], wz[1], wz[2]);
+    const float4 *c0 = tile + ((i - oi - 1) * BT + (j - oj - 1)) * BT + (k - ok - 1);
+    float ax = 0.0f, ay = 0.0f, az = 0.0f;
+#pragma unroll
+    for (int a = 0; a < 3; a++)
+#pragma unroll
+      for (int e = 0; e < 3; e++) {
+        const float wxy = wx[a] * wy[e];
+#pragma unroll
+        for (int g = 0; g < 3; g++) {
+          const float w = wxy * wz[g];
+          const float4 ff = c0[(a * BT + e) * BT + g];
+          ax += w * ff.x; ay += w * ff.y; az += w * ff.z;
+        }
+      }
+    float *ap = accel + 3 * (size_t)row;
+    ap[0] = ax; ap[1] = ay; ap[2] = az;
+    ma = fmaxf(ma, fmaxf(fabsf(ax), fmaxf(fabsf(ay), fabsf(az))));
+    if (vel) {
+      float *vp = vel + 3 * (size_t)row;
+      const float v0 = vp[0] + mh * ax, v1 = vp[1] + mh * ay, v2 = vp[2] + mh * az;
+      vp[0] = v0; vp[1] = v1; vp[2] = v2;
+      mv = fmaxf(mv, fmaxf(fabsf(v0), fmaxf(fabsf(v1), fabsf(v2))));
+    }
+  }
+  ma = warp_max(ma);
+  mv = warp_max(mv);
+  if ((threadIdx.x & 31) == 0) { s_max[threadIdx.x >> 5][0] = ma; s_max[threadIdx.x >> 5][1] = mv; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int w = 1; w < BI_THREADS / 32; w++) { ma = fmaxf(ma, s_max[w][0]); mv = fmaxf(mv, s_max[w][1]); }
+    atomic_max_nonneg(&maxout[0], ma);
+    atomic_max_nonneg(&maxout[1], mv);
+  }
+}
+
 // rho = f1 * (scale * rho) + f2, defined in deposit.cu
 __global__ void rho_affine_kernel(float *rho, int64_t n, float scale, float f1, float f2, int do_scale);
 
@@ -367,6 +471,37 @@ int psc_interp_kick4_binned(const float *force4, const void *scratch, size_t scr
     interp_kick4_binned_kernel<PSC_TSC><<<grid, BI_THREADS, 0, st>>>(f4, L.pos, L.src, L.offsets, vel, acc, N, L.NB, half_dt, maxout);
   else
     interp_kick4_binned_kernel<PSC_CIC><<<grid, BI_THREADS, 0, st>>>(f4, L.pos, L.src, L.offsets, vel, acc, N, L.NB, half_dt, maxout);
+  count_launch();
+  PSC_CHECK_LAUNCH();
+  return PSC_OK;
+}
+
+int psc_interp_kick_phi_binned(const float *phi, const float *u, float f, int fr_n, int order, const void *scratch,
+                               size_t scratch_bytes, float *vel, float *acc, int64_t np, int N, int scheme,
+                               float half_dt, float *maxout, void *stream) {
+  PSC_CHECK_ARG(scheme == PSC_CIC || scheme == PSC_TSC, "mass scheme must be CIC or TSC");
+  PSC_CHECK_ARG(order == 2 || order == 3 || order == 5 || order == 7, "gradient order must be 2, 3, 5 or 7");
+  PSC_CHECK_ARG(fr_n >= 0 && fr_n <= 2, "fR_n must be 1 or 2");
+  PSC_CHECK_ARG(N >= 2 * BB && (N % BB) == 0, "N must be a multiple of 8 and >= 16");
+  PSC_CHECK_ARG(phi && scratch && acc && maxout && (u || fr_n == 0), "null pointer");
+  if (np == 0) return PSC_OK;
+  BinLayout L;
+  if (!bin_layout(const_cast<void *>(scratch), scratch_bytes, np, N, L)) {
+    set_error("psc_interp_kick_phi_binned: scratch too small");
+    return PSC_ERR_WORKSPACE;
+  }
+  cudaStream_t st = as_stream(stream);
+  const int grid = (int)L.nbins;
+#define PSC_IKP(S, O) \
+  interp_kick_phi_binned_kernel<S, O><<<grid, BI_THREADS, 0, st>>>(phi, u, f, fr_n, L.pos, L.src, L.offsets, vel, acc, N, L.NB, half_dt, maxout)
+#define PSC_IKP_O(S)               \
+  if (order == 2) PSC_IKP(S, 2);    \
+  else if (order == 3) PSC_IKP(S, 3); \
+  else if (order == 5) PSC_IKP(S, 5); \
+  else PSC_IKP(S, 7);
+  if (scheme == PSC_TSC) { PSC_IKP_O(PSC_TSC) } else { PSC_IKP_O(PSC_CIC) }
+#undef PSC_IKP_O
+#undef PSC_IKP
   count_launch();
   PSC_CHECK_LAUNCH();
   return PSC_OK;

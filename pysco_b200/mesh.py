@@ -119,6 +119,28 @@ def interp_kick(force, position, velocity, scheme, half_dt, binned=None):
     return c.ret(acc), mx
 
 
+def interp_kick_phi(potential, u, f, fr_n, order, position, velocity, scheme, half_dt, binned):
+    """derivative[_fR](potential[, u]) + inv{CIC,TSC}_vec + half-kick + max reductions in one kernel per bin:
+    the force tile of every 8^3 bin is formed in shared memory from the potential (no force grid in HBM).
+    Returns (acceleration, maxima[2] device tensor)."""
+    if fr_n not in (0, 1, 2):
+        raise NotImplementedError(f"Unsupported: fR_n={fr_n}")
+    if order not in (2, 3, 5, 7):
+        raise NotImplementedError(f"Unsupported: gradient_order={order}")
+    c = _lib.Ctx()
+    phi, tu, pos = c.dev(potential), c.dev(u), c.dev(position)
+    vel = c.dev(velocity, inplace=True)
+    n = pos.shape[0]
+    acc = _lib.empty((n, 3))
+    mx = _lib.zeros((2,))
+    _lib.check(_lib.load().psc_interp_kick_phi_binned(
+        _lib.ptr(phi), _lib.ptr(tu), float(np.float32(f)), fr_n, order, _lib.ptr(binned.scratch),
+        binned.scratch.numel(), _lib.ptr(vel), _lib.ptr(acc), n, phi.shape[0], scheme, float(half_dt), _lib.ptr(mx),
+        _lib.stream()))
+    c.finish()
+    return c.ret(acc), mx
+
+
 def _gradient(a, b, f, fr_n, order, add, force=None, padded=False):
     if fr_n not in (0, 1, 2):
         raise NotImplementedError(f"Unsupported: fR_n={fr_n}")

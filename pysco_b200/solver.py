@@ -244,25 +244,39 @@ def _pm_device(position, param, potential, additional_field, tables, kick=None):
         potential = fft(rhs, param)
 
     order = param["gradient_stencil_order"]
+    velocity, half_dt = kick if kick is not None else (None, 0.0)
+    fused = binned is not None and ncells_1d >= 16 and LINEAR_NEWTON_SOLVER != "full_fft"
+    half_c2 = np.float32(0)
     if "fr" == THEORY:
         _, fR_a, c2 = _fr_background(param)
         half_c2 = np.float32(0.5 * (-fR_a) * c2)
-        if LINEAR_NEWTON_SOLVER == "full_fft":
-            force = fft_force(rhs, param)
-            mesh.add_derivative_fR(force, additional_field, half_c2, param["fR_n"], order)
+    if fused:
+        # gradient fused into the binned interpolation: no force grid
+        if order not in (2, 3, 5, 7):
+            raise NotImplementedError(f"Unsupported: gradient_order={order}")
+        if "fr" == THEORY:
+            if param["fR_n"] not in (1, 2):
+                raise NotImplementedError(f"Unsupported: fR_n={param['fR_n']}")
+            acceleration, maxima = mesh.interp_kick_phi(potential, additional_field, half_c2, param["fR_n"], order,
+                                                        position, velocity, scheme, half_dt, binned)
         else:
-            force = mesh.derivative_fR(potential, additional_field, half_c2, param["fR_n"], order, padded=True)
+            acceleration, maxima = mesh.interp_kick_phi(potential, None, 0.0, 0, order, position, velocity, scheme,
+                                                        half_dt, binned)
     else:
-        if LINEAR_NEWTON_SOLVER == "full_fft":
-            force = fft_force(rhs, param)
+        if "fr" == THEORY:
+            if LINEAR_NEWTON_SOLVER == "full_fft":
+                force = fft_force(rhs, param)
+                mesh.add_derivative_fR(force, additional_field, half_c2, param["fR_n"], order)
+            else:
+                force = mesh.derivative_fR(potential, additional_field, half_c2, param["fR_n"], order, padded=True)
         else:
-            force = mesh.derivative(potential, order, padded=True)
-    del rhs
-
-    velocity, half_dt = kick if kick is not None else (None, 0.0)
-    acceleration, maxima = mesh.interp_kick(force, position, velocity, scheme, half_dt, binned)
-    del binned
-    del force
+            if LINEAR_NEWTON_SOLVER == "full_fft":
+                force = fft_force(rhs, param)
+            else:
+                force = mesh.derivative(potential, order, padded=True)
+        acceleration, maxima = mesh.interp_kick(force, position, velocity, scheme, half_dt, binned)
+        del force
+    del rhs, binned
     return acceleration, potential, additional_field, (maxima if kick is not None else None)
 
 
