@@ -110,6 +110,58 @@ int psc_interp_kick_phi_binned(const float *phi, const float *u, float f, int fr
                                size_t scratch_bytes, float *vel, float *acc, int64_t np, int N, int scheme,
                                float half_dt, float *maxout, void *stream);
 
+/* ---------------------------------------------------------------- x-slab decomposition ------ */
+/* The reference is single-process (README.md:49).  These entry points are the per-GPU pieces of the slab
+ * decomposition of its hot path: rank r of P owns the planes [x0, x0 + nxl) = [r N/P, (r+1) N/P)
+ * of every grid and the particles whose cell floor(x N) lies in them.  Collectives (NCCL) are issued by the
+ * host (pysco_b200/slab.py); nothing here communicates.
+ *
+ * Binned particle <-> mesh kernels on a slab: bins cover the owned planes only (nxl % 8 == 0).
+ * psc_deposit_binned_slab writes raw TSC/CIC/NGP sums into rho_ghost[nxl + 2][N][N]; plane 0 and plane
+ * nxl + 1 hold what belongs to the left / right neighbour's last / first owned plane (mesh.py:2468-2595 with
+ * the periodic wrap in x replaced by ghost planes).  psc_interp_kick_phi_binned_slab reads phi_ghost (and
+ * u_ghost) [nxl + 2*ghost][N][N] whose owned planes start at plane `ghost` >= 1 + stencil reach. */
+size_t psc_bin_workspace_bytes_slab(int64_t np, int N, int nxl);
+int psc_bin_particles_slab(const float *pos, int64_t np, int N, int x0, int nxl, void *scratch, size_t scratch_bytes,
+                           void *stream);
+int psc_deposit_binned_slab(const void *scratch, size_t scratch_bytes, int64_t np, int N, int x0, int nxl, int scheme,
+                            float *rho_ghost, void *stream);
+int psc_interp_kick_phi_binned_slab(const float *phi_ghost, const float *u_ghost, float f, int fr_n, int order,
+                                    int x0, int nxl, int ghost, const void *scratch, size_t scratch_bytes, float *vel,
+                                    float *acc, int64_t np, int N, int scheme, float half_dt, float *maxout,
+                                    void *stream);
+/* Particle migration after the drift (integration.py:252-258; utils.periodic_wrap utils.py:1120).
+ * psc_slab_count: counts[d] (device int64[P], overwritten) = particles whose owner floor(x N) / nxl is rank d.
+ * psc_slab_pack_leavers: every particle not owned by `me` is packed as a 32-byte record (x y z vx vy vz id)
+ *   at sendbuf[8 * (offsets[owner] + slot)], its row stored in holes[same index]; offsets = exclusive prefix
+ *   of the send counts by destination (device int64[P]); cursor = device int64[P] scratch.
+ * psc_slab_unpack_rows: record t of recvbuf -> row rows[t] of pos / vel / ids.
+ * psc_slab_move_rows: row src[t] -> row dst[t] (fills the holes that the arrivals did not fill). */
+int psc_slab_count(const float *pos, int64_t np, int N, int nxl, int P, int64_t *counts, void *stream);
+int psc_slab_pack_leavers(const float *pos, const float *vel, const int64_t *ids, int64_t np, int N, int nxl, int P,
+                          int me, const int64_t *offsets, int64_t *cursor, float *sendbuf, int64_t *holes,
+                          void *stream);
+int psc_slab_unpack_rows(const float *recvbuf, const int64_t *rows, int64_t n, float *pos, float *vel, int64_t *ids,
+                         void *stream);
+int psc_slab_move_rows(const int64_t *src, const int64_t *dst, int64_t n, float *pos, float *vel, int64_t *ids,
+                       void *stream);
+/* Transposed FFT of fourier.fft_3D_real / ifft_3D_real (fourier.py:104-147, 251-294) for one slab:
+ *   forward: psc_slab_fft_r2c_planes ([nxl][N][N] -> [nxl][N][N/2+1]) -> psc_slab_yblocks(to_blocks = 1)
+ *            ([P][nxl][nyl][N/2+1]) -> all-to-all (host) = [N][nyl][N/2+1] -> psc_slab_fft_x(inverse = 0)
+ *   psc_green_slab on the transposed layout, then the mirror image back.  All transforms are unnormalised.
+ * The three cuFFT plans share ONE caller-provided work area (psc_slab_fft_workspace_bytes /
+ * psc_slab_fft_set_workspace). */
+int psc_slab_fft_plan_create(int N, int nxl, int nyl, void **plan_out);
+int psc_slab_fft_plan_destroy(void *plan);
+size_t psc_slab_fft_workspace_bytes(void *plan);
+int psc_slab_fft_set_workspace(void *plan, void *work);
+int psc_slab_fft_r2c_planes(void *plan, const float *planes, float *spec2d, void *stream);
+int psc_slab_fft_c2r_planes(void *plan, float *spec2d, float *planes, void *stream);
+int psc_slab_fft_x(void *plan, float *spec_t, int inverse, void *stream);
+int psc_slab_yblocks(const float *in, float *out, int N, int nxl, int nyl, int to_blocks, void *stream);
+/* psc_green on a y-block of the transposed spectrum [N (kx)][nyl (ky = y0 + .)][N/2+1] */
+int psc_green_slab(float *spec_t, int N, int nyl, int y0, int kind, int p, float scale, void *stream);
+
 /* ---------------------------------------------------------------- grid algebra ------------- */
 /* utils.linear_operator[_inplace] (utils.py:644-717): out = f1*x + f2 (out may alias x) */
 int psc_linear_operator(const float *x, float f1, float f2, float *out, int64_t n, void *stream);

@@ -36,6 +36,24 @@ SIGNATURES = {
     "psc_deposit_binned": [_vp, _sz, _i64, _i, _i, _f, _f, _f, _vp, _vp],
     "psc_interp_kick4_binned": [_vp, _vp, _sz, _vp, _vp, _i64, _i, _i, _f, _vp, _vp],
     "psc_interp_kick_phi_binned": [_vp, _vp, _f, _i, _i, _vp, _sz, _vp, _vp, _i64, _i, _i, _f, _vp, _vp],
+    "psc_bin_workspace_bytes_slab": [_i64, _i, _i],
+    "psc_bin_particles_slab": [_vp, _i64, _i, _i, _i, _vp, _sz, _vp],
+    "psc_deposit_binned_slab": [_vp, _sz, _i64, _i, _i, _i, _i, _vp, _vp],
+    "psc_interp_kick_phi_binned_slab": [_vp, _vp, _f, _i, _i, _i, _i, _i, _vp, _sz, _vp, _vp, _i64, _i, _i, _f, _vp,
+                                        _vp],
+    "psc_slab_count": [_vp, _i64, _i, _i, _i, _vp, _vp],
+    "psc_slab_pack_leavers": [_vp, _vp, _vp, _i64, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp],
+    "psc_slab_unpack_rows": [_vp, _vp, _i64, _vp, _vp, _vp, _vp],
+    "psc_slab_move_rows": [_vp, _vp, _i64, _vp, _vp, _vp, _vp],
+    "psc_slab_fft_plan_create": [_i, _i, _i, C.POINTER(_vp)],
+    "psc_slab_fft_plan_destroy": [_vp],
+    "psc_slab_fft_workspace_bytes": [_vp],
+    "psc_slab_fft_set_workspace": [_vp, _vp],
+    "psc_slab_fft_r2c_planes": [_vp, _vp, _vp, _vp],
+    "psc_slab_fft_c2r_planes": [_vp, _vp, _vp, _vp],
+    "psc_slab_fft_x": [_vp, _vp, _i, _vp],
+    "psc_slab_yblocks": [_vp, _vp, _i, _i, _i, _i, _vp],
+    "psc_green_slab": [_vp, _i, _i, _i, _i, _i, _f, _vp],
     "psc_linear_operator": [_vp, _f, _f, _vp, _i64, _vp],
     "psc_lincomb": [_vp, _f, _vp, _f, _i64, _vp],
     "psc_gradient": [_vp, _vp, _f, _i, _i, _i, _i, _vp, _i, _vp],
@@ -61,7 +79,8 @@ SIGNATURES = {
     "psc_mond_rhs": [_vp, _vp, _i, _f, _i, _f, _vp],
 }
 _RESTYPES = {"psc_last_error": C.c_char_p, "psc_launch_count": _i64, "psc_argsort_workspace_bytes": _sz,
-             "psc_bin_workspace_bytes": _sz,
+             "psc_bin_workspace_bytes": _sz, "psc_bin_workspace_bytes_slab": _sz,
+             "psc_slab_fft_workspace_bytes": _sz,
              "psc_fft_plan_workspace_bytes": _sz}
 
 NGP, CIC, TSC = 0, 1, 2
@@ -106,7 +125,10 @@ _TIMED = ("psc_morton_keys", "psc_argsort_keys", "psc_gather3", "psc_axpy", "psc
           "psc_lincomb", "psc_gradient", "psc_fft_r2c", "psc_fft_c2r", "psc_fft_c2r_vec3", "psc_green",
           "psc_grad_green", "psc_pk", "psc_operator", "psc_residual", "psc_restrict_residual",
           "psc_residual_sumsq", "psc_diff_sumsq", "psc_initialise_potential", "psc_gauss_seidel",
-          "psc_restriction", "psc_prolongation", "psc_mond_rhs")
+          "psc_restriction", "psc_prolongation", "psc_mond_rhs",
+          "psc_bin_particles_slab", "psc_deposit_binned_slab", "psc_interp_kick_phi_binned_slab", "psc_slab_count",
+          "psc_slab_pack_leavers", "psc_slab_unpack_rows", "psc_slab_move_rows", "psc_slab_fft_r2c_planes",
+          "psc_slab_fft_c2r_planes", "psc_slab_fft_x", "psc_slab_yblocks", "psc_green_slab")
 
 
 def load():

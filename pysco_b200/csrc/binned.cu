@@ -31,8 +31,10 @@ constexpr int BD_P0 = BT * BD_P1;
 constexpr int BD_TILE = BT * BD_P0;  // 1100 floats per warp
 
 struct BinLayout {
-  int NB;            // bins per dimension
-  int64_t nbins;     // NB^3
+  int NB;            // bins along y and z (N / 8)
+  int NBX;           // bins along x (owned planes / 8; == NB for the periodic single-domain case)
+  int x0;            // first owned x cell (0 unless the mesh is slab-decomposed)
+  int64_t nbins;     // NBX * NB^2
   int *counts;       // [nbins + 1]
   int *offsets;      // [nbins + 1]  exclusive prefix sum, offsets[nbins] = np
   int *src;          // [np] source row of the binned particle
@@ -49,9 +51,11 @@ static size_t scan_tmp_bytes(int64_t n) {
   return b;
 }
 
-static bool bin_layout(void *scratch, size_t bytes, int64_t np, int N, BinLayout &L) {
+static bool bin_layout(void *scratch, size_t bytes, int64_t np, int N, int x0, int nxl, BinLayout &L) {
   L.NB = N / BB;
-  L.nbins = (int64_t)L.NB * L.NB * L.NB;
+  L.NBX = nxl / BB;
+  L.x0 = x0;
+  L.nbins = (int64_t)L.NBX * L.NB * L.NB;
   char *p = reinterpret_cast<char *>(scratch);
   size_t off = 0;
   L.counts = reinterpret_cast<int *>(p + off); off += a256(sizeof(int) * (L.nbins + 1));
@@ -64,14 +68,17 @@ static bool bin_layout(void *scratch, size_t bytes, int64_t np, int N, BinLayout
   return off <= bytes;
 }
 
-__device__ __forceinline__ int bin_of(float x, float y, float z, float Nf, int NB) {
-  const int i = (int)(x * Nf), j = (int)(y * Nf), k = (int)(z * Nf);
-  return ((i >> 3) * NB + (j >> 3)) * NB + (k >> 3);
+// x0 / NBX: the slab of owned planes [x0, x0 + 8 NBX); a particle outside it (the host migrates particles
+// before binning) is clamped into the edge bin so that nothing is ever written out of bounds.
+__device__ __forceinline__ int bin_of(float x, float y, float z, float Nf, int NB, int x0, int NBX) {
+  const int i = (int)(x * Nf) - x0, j = (int)(y * Nf), k = (int)(z * Nf);
+  const int bi = min(max(i >> 3, 0), NBX - 1);
+  return (bi * NB + (j >> 3)) * NB + (k >> 3);
 }
 
 // pass 1: counts[bin] += 1, one atomic per distinct bin per warp
 __global__ void __launch_bounds__(256) bin_count_kernel(const float *__restrict__ pos, int64_t np, int N, int NB,
-                                                        int *__restrict__ counts) {
+                                                        int x0, int NBX, int *__restrict__ counts) {
   const float Nf = (float)N;
   const int lane = threadIdx.x & 31;
   const int64_t nwarp_iters = (np + 31) >> 5;
@@ -79,7 +86,7 @@ __global__ void __launch_bounds__(256) bin_count_kernel(const float *__restrict_
   for (int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < nwarp_iters; w += wstride) {
     const int64_t n = w * 32 + lane;
     int b = -1 - lane;
-    if (n < np) b = bin_of(__ldg(&pos[3 * n]), __ldg(&pos[3 * n + 1]), __ldg(&pos[3 * n + 2]), Nf, NB);
+    if (n < np) b = bin_of(__ldg(&pos[3 * n]), __ldg(&pos[3 * n + 1]), __ldg(&pos[3 * n + 2]), Nf, NB, x0, NBX);
     const unsigned peers = __match_any_sync(0xffffffffu, b);
     if (b >= 0 && (__ffs(peers) - 1) == lane) atomicAdd(&counts[b], __popc(peers));
   }
@@ -87,7 +94,7 @@ __global__ void __launch_bounds__(256) bin_count_kernel(const float *__restrict_
 
 // pass 2: slot = offsets[bin] + (claimed range in the bin); counts[] is consumed (counted down to zero)
 __global__ void __launch_bounds__(256) bin_scatter_kernel(const float *__restrict__ pos, int64_t np, int N, int NB,
-                                                          int *__restrict__ counts, const int *__restrict__ offsets,
+                                                          int x0, int NBX, int *__restrict__ counts, const int *__restrict__ offsets,
                                                           float *__restrict__ bpos, int *__restrict__ bsrc) {
   const float Nf = (float)N;
   const int lane = threadIdx.x & 31;
@@ -99,7 +106,7 @@ __global__ void __launch_bounds__(256) bin_scatter_kernel(const float *__restric
     int b = -1 - lane;
     if (n < np) {
       x = __ldg(&pos[3 * n]); y = __ldg(&pos[3 * n + 1]); z = __ldg(&pos[3 * n + 2]);
-      b = bin_of(x, y, z, Nf, NB);
+      b = bin_of(x, y, z, Nf, NB, x0, NBX);
     }
     const unsigned peers = __match_any_sync(0xffffffffu, b);
     const int leader = __ffs(peers) - 1;
@@ -123,6 +130,7 @@ __global__ void __launch_bounds__(256) bin_scatter_kernel(const float *__restric
 template <int SCHEME>
 __global__ void __launch_bounds__(BD_WARPS * 32) deposit_binned_kernel(const float *__restrict__ bpos,
                                                                        const int *__restrict__ offsets, int N, int NB,
+                                                                       int x0, int xoff, int nxa,
                                                                        float *__restrict__ rho) {
   __shared__ float tiles[BD_WARPS][BD_TILE];
   const int b = blockIdx.x;
@@ -130,7 +138,8 @@ __global__ void __launch_bounds__(BD_WARPS * 32) deposit_binned_kernel(const flo
   if (beg == end) return;  // rho was zeroed by the caller
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int bk = b % NB, bj = (b / NB) % NB, bi = b / (NB * NB);
-  const int oi = bi * BB - 1, oj = bj * BB - 1, ok = bk * BB - 1;  // absolute cell of tile cell (0,0,0)
+  const int oi = x0 + bi * BB - 1, oj = bj * BB - 1, ok = bk * BB - 1;  // global cell of tile cell (0,0,0)
+  const int pl0 = bi * BB - 1 + xoff;  // its plane in rho (nxa planes; periodic only when nxa == N)
   const float Nf = (float)N;
   float *tile = tiles[warp];
   for (int t = lane; t < BD_TILE; t += 32) tile[t] = 0.0f;
@@ -145,7 +154,7 @@ __global__ void __launch_bounds__(BD_WARPS * 32) deposit_binned_kernel(const flo
     axis_weights<SCHEME>(px * Nf, N, i, wx[0], wx[1], wx[2]);
     axis_weights<SCHEME>(py * Nf, N, j, wy[0], wy[1], wy[2]);
     axis_weights<SCHEME>(pz * Nf, N, k, wz[0], wz[1], wz[2]);
-    const int t0 = i - oi, t1 = j - oj, t2 = k - ok;  // in [1, 8] for every particle of this bin
+    const int t0 = min(max(i - oi, 1), BB), t1 = j - oj, t2 = k - ok;  // in [1, 8] for every particle of this bin
     float wgt[27];
 #pragma unroll
     for (int a = 0; a < 3; a++)
@@ -196,7 +205,7 @@ __global__ void __launch_bounds__(BD_WARPS * 32) deposit_binned_kernel(const flo
     float v = tiles[0][s];
 #pragma unroll
     for (int w = 1; w < BD_WARPS; w++) v += tiles[w][s];
-    const int gi = wrap(oi + a, N), gj = wrap(oj + e, N), gk = wrap(ok + g, N);
+    const int gi = wrap(pl0 + a, nxa), gj = wrap(oj + e, N), gk = wrap(ok + g, N);
     float *dst = rho + (size_t)gi * N2 + (size_t)gj * N + gk;
     const bool mine = a >= 2 && a <= BT - 3 && e >= 2 && e <= BT - 3 && g >= 2 && g <= BT - 3;
     if (mine) *dst = v;
@@ -211,19 +220,20 @@ template <int SCHEME>
 __global__ void __launch_bounds__(BI_THREADS) interp_kick4_binned_kernel(
     const float4 *__restrict__ force4, const float *__restrict__ bpos, const int *__restrict__ bsrc,
     const int *__restrict__ offsets, float *__restrict__ vel, float *__restrict__ accel, int N, int NB,
-    float half_dt, float *__restrict__ maxout) {
+    int x0, int xoff, int nxa, float half_dt, float *__restrict__ maxout) {
   __shared__ float4 tile[BT * BT * BT];  // 16,000 B
   __shared__ float s_max[BI_THREADS / 32][2];
   const int b = blockIdx.x;
   const int beg = offsets[b], end = offsets[b + 1];
   if (beg == end) return;
   const int bk = b % NB, bj = (b / NB) % NB, bi = b / (NB * NB);
-  const int oi = bi * BB - 1, oj = bj * BB - 1, ok = bk * BB - 1;
+  const int oi = x0 + bi * BB - 1, oj = bj * BB - 1, ok = bk * BB - 1;
+  const int pl0 = bi * BB - 1 + xoff;
   const size_t N2 = (size_t)N * N;
   for (int t = threadIdx.x; t < BT * BT * BT; t += BI_THREADS) {
     const int g = t % BT, r = t / BT;
     const int e = r % BT, a = r / BT;
-    tile[t] = __ldg(&force4[(size_t)wrap(oi + a, N) * N2 + (size_t)wrap(oj + e, N) * N + wrap(ok + g, N)]);
+    tile[t] = __ldg(&force4[(size_t)wrap(pl0 + a, nxa) * N2 + (size_t)wrap(oj + e, N) * N + wrap(ok + g, N)]);
   }
   __syncthreads();
   const float Nf = (float)N;
@@ -237,7 +247,7 @@ __global__ void __launch_bounds__(BI_THREADS) interp_kick4_binned_kernel(
     axis_weights<SCHEME>(px * Nf, N, i, wx[0], wx[1], wx[2]);
     axis_weights<SCHEME>(py * Nf, N, j, wy[0], wy[1], wy[2]);
     axis_weights<SCHEME>(pz * Nf, N, k, wz[0], wz[1], wz[2]);
-    const float4 *c0 = tile + ((i - oi - 1) * BT + (j - oj - 1)) * BT + (k - ok - 1);
+    const float4 *c0 = tile + ((min(max(i - oi, 1), BB) - 1) * BT + (j - oj - 1)) * BT + (k - ok - 1);
     float ax = 0.0f, ay = 0.0f, az = 0.0f;
 #pragma unroll
     for (int a = 0; a < 3; a++)
@@ -285,7 +295,8 @@ template <int SCHEME, int ORDER>
 __global__ void __launch_bounds__(BI_THREADS) interp_kick_phi_binned_kernel(
     const float *__restrict__ phi, const float *__restrict__ u, float f, int fr_n,
     const float *__restrict__ bpos, const int *__restrict__ bsrc, const int *__restrict__ offsets,
-    float *__restrict__ vel, float *__restrict__ accel, int N, int NB, float half_dt, float *__restrict__ maxout) {
+    float *__restrict__ vel, float *__restrict__ accel, int N, int NB, int x0, int xoff, int nxa, float half_dt,
+    float *__restrict__ maxout) {
   constexpr int H = Reach<ORDER>::H;
   constexpr int PT = BT + 2 * H;  // potential tile edge
   __shared__ float ptile[PT * PT * PT];
@@ -295,13 +306,14 @@ __global__ void __launch_bounds__(BI_THREADS) interp_kick_phi_binned_kernel(
   const int beg = offsets[b], end = offsets[b + 1];
   if (beg == end) return;
   const int bk = b % NB, bj = (b / NB) % NB, bi = b / (NB * NB);
-  const int oi = bi * BB - 1, oj = bj * BB - 1, ok = bk * BB - 1;
+  const int oi = x0 + bi * BB - 1, oj = bj * BB - 1, ok = bk * BB - 1;
+  const int pl0 = bi * BB - 1 + xoff;
   const size_t N2 = (size_t)N * N;
   for (int t = threadIdx.x; t < PT * PT * PT; t += BI_THREADS) {
     const int g = t % PT, r = t / PT;
     const int e = r % PT, a = r / PT;
-    int gi = oi - H + a, gj = oj - H + e, gk = ok - H + g;
-    gi += gi < 0 ? N : 0; gi -= gi >= N ? N : 0;
+    int gi = pl0 - H + a, gj = oj - H + e, gk = ok - H + g;
+    gi += gi < 0 ? nxa : 0; gi -= gi >= nxa ? nxa : 0;
     gj += gj < 0 ? N : 0; gj -= gj >= N ? N : 0;
     gk += gk < 0 ? N : 0; gk -= gk >= N ? N : 0;
     const size_t c = (size_t)gi * N2 + (size_t)gj * N + gk;
@@ -341,7 +353,7 @@ __global__ void __launch_bounds__(BI_THREADS) interp_kick_phi_binned_kernel(
     axis_weights<SCHEME>(px * Nf, N, i, wx[0], wx[1], wx[2]);
     axis_weights<SCHEME>(py * Nf, N, j, wy[0], wy[1], wy[2]);
     axis_weights<SCHEME>(pz * Nf, N, k, wz[0], wz[1], wz[2]);
-    const float4 *c0 = tile + ((i - oi - 1) * BT + (j - oj - 1)) * BT + (k - ok - 1);
+    const float4 *c0 = tile + ((min(max(i - oi, 1), BB) - 1) * BT + (j - oj - 1)) * BT + (k - ok - 1);
     float ax = 0.0f, ay = 0.0f, az = 0.0f;
 #pragma unroll
     for (int a = 0; a < 3; a++)
@@ -386,27 +398,33 @@ using namespace psc;
 
 extern "C" {
 
-size_t psc_bin_workspace_bytes(int64_t np, int N) {
-  if (np < 0 || N < BB || (N % BB) != 0) return 0;
-  const int64_t nbins = (int64_t)(N / BB) * (N / BB) * (N / BB);
+static bool slab_ok(int N, int x0, int nxl) {
+  return N >= BB && (N % BB) == 0 && N <= 32767 && nxl >= BB && (nxl % BB) == 0 && x0 >= 0 && x0 + nxl <= N;
+}
+
+size_t psc_bin_workspace_bytes_slab(int64_t np, int N, int nxl) {
+  if (np < 0 || !slab_ok(N, 0, nxl)) return 0;
+  const int64_t nbins = (int64_t)(nxl / BB) * (N / BB) * (N / BB);
   return 2 * a256(sizeof(int) * (nbins + 1)) + a256(sizeof(int) * (size_t)np) + a256(sizeof(float) * 3 * (size_t)np) +
          a256(scan_tmp_bytes(nbins + 1)) + 256;
 }
+size_t psc_bin_workspace_bytes(int64_t np, int N) { return psc_bin_workspace_bytes_slab(np, N, N); }
 
-int psc_bin_particles(const float *pos, int64_t np, int N, void *scratch, size_t scratch_bytes, void *stream) {
+int psc_bin_particles_slab(const float *pos, int64_t np, int N, int x0, int nxl, void *scratch, size_t scratch_bytes,
+                           void *stream) {
   PSC_CHECK_ARG(np >= 0 && np < ((int64_t)1 << 31), "np out of range");
-  PSC_CHECK_ARG(N >= BB && (N % BB) == 0 && N <= 32767, "N must be a multiple of 8");
+  PSC_CHECK_ARG(slab_ok(N, x0, nxl), "N and the slab thickness must be multiples of 8");
   PSC_CHECK_ARG(scratch && (pos || np == 0), "null pointer");
   PSC_CHECK_ARG(((uintptr_t)scratch & 255) == 0, "scratch must be 256-byte aligned");
   BinLayout L;
-  if (!bin_layout(scratch, scratch_bytes, np, N, L)) {
+  if (!bin_layout(scratch, scratch_bytes, np, N, x0, nxl, L)) {
     set_error("psc_bin_particles: scratch too small");
     return PSC_ERR_WORKSPACE;
   }
   cudaStream_t st = as_stream(stream);
   PSC_CUDA(cudaMemsetAsync(L.counts, 0, sizeof(int) * (L.nbins + 1), st));
   if (np > 0) {
-    bin_count_kernel<<<grid_for(np, 256, 8), 256, 0, st>>>(pos, np, N, L.NB, L.counts);
+    bin_count_kernel<<<grid_for(np, 256, 8), 256, 0, st>>>(pos, np, N, L.NB, x0, L.NBX, L.counts);
     count_launch();
   }
   cudaError_t e = cub::DeviceScan::ExclusiveSum(L.cub_tmp, L.cub_bytes, L.counts, L.offsets, (int)(L.nbins + 1), st);
@@ -416,31 +434,38 @@ int psc_bin_particles(const float *pos, int64_t np, int N, void *scratch, size_t
     return PSC_ERR_CUDA;
   }
   if (np > 0) {
-    bin_scatter_kernel<<<grid_for(np, 256, 8), 256, 0, st>>>(pos, np, N, L.NB, L.counts, L.offsets, L.pos, L.src);
+    bin_scatter_kernel<<<grid_for(np, 256, 8), 256, 0, st>>>(pos, np, N, L.NB, x0, L.NBX, L.counts, L.offsets, L.pos,
+                                                             L.src);
     count_launch();
   }
   PSC_CHECK_LAUNCH();
   return PSC_OK;
 }
+int psc_bin_particles(const float *pos, int64_t np, int N, void *scratch, size_t scratch_bytes, void *stream) {
+  return psc_bin_particles_slab(pos, np, N, 0, N, scratch, scratch_bytes, stream);
+}
 
-int psc_deposit_binned(const void *scratch, size_t scratch_bytes, int64_t np, int N, int scheme, float scale, float f1,
-                       float f2, float *rho, void *stream) {
-  PSC_CHECK_ARG(scheme == PSC_NGP || scheme == PSC_CIC || scheme == PSC_TSC, "unknown mass scheme");
-  PSC_CHECK_ARG(N >= BB && (N % BB) == 0, "N must be a multiple of 8");
-  PSC_CHECK_ARG(scratch && rho, "null pointer");
+// ghost = 0: periodic N^3 grid (x0 = 0, nxl = N); ghost = 1: rho has nxl + 2 planes, plane 0 / nxl + 1 collect the
+// mass that belongs to the neighbouring slabs
+static int deposit_binned_impl(const void *scratch, size_t scratch_bytes, int64_t np, int N, int x0, int nxl,
+                               int ghost, int scheme, float scale, float f1, float f2, float *rho, void *stream) {
   BinLayout L;
-  if (!bin_layout(const_cast<void *>(scratch), scratch_bytes, np, N, L)) {
+  if (!bin_layout(const_cast<void *>(scratch), scratch_bytes, np, N, x0, nxl, L)) {
     set_error("psc_deposit_binned: scratch too small");
     return PSC_ERR_WORKSPACE;
   }
   cudaStream_t st = as_stream(stream);
-  const int64_t n3 = (int64_t)N * N * N;
+  const int nxa = nxl + 2 * ghost;
+  const int64_t n3 = (int64_t)nxa * N * N;
   PSC_CUDA(cudaMemsetAsync(rho, 0, sizeof(float) * n3, st));
   if (np > 0) {
     const int grid = (int)L.nbins;
-    if (scheme == PSC_TSC) deposit_binned_kernel<PSC_TSC><<<grid, BD_WARPS * 32, 0, st>>>(L.pos, L.offsets, N, L.NB, rho);
-    else if (scheme == PSC_CIC) deposit_binned_kernel<PSC_CIC><<<grid, BD_WARPS * 32, 0, st>>>(L.pos, L.offsets, N, L.NB, rho);
-    else deposit_binned_kernel<PSC_NGP><<<grid, BD_WARPS * 32, 0, st>>>(L.pos, L.offsets, N, L.NB, rho);
+    if (scheme == PSC_TSC)
+      deposit_binned_kernel<PSC_TSC><<<grid, BD_WARPS * 32, 0, st>>>(L.pos, L.offsets, N, L.NB, x0, ghost, nxa, rho);
+    else if (scheme == PSC_CIC)
+      deposit_binned_kernel<PSC_CIC><<<grid, BD_WARPS * 32, 0, st>>>(L.pos, L.offsets, N, L.NB, x0, ghost, nxa, rho);
+    else
+      deposit_binned_kernel<PSC_NGP><<<grid, BD_WARPS * 32, 0, st>>>(L.pos, L.offsets, N, L.NB, x0, ghost, nxa, rho);
     count_launch();
     PSC_CHECK_LAUNCH();
   }
@@ -452,15 +477,31 @@ int psc_deposit_binned(const void *scratch, size_t scratch_bytes, int64_t np, in
   return PSC_OK;
 }
 
+int psc_deposit_binned(const void *scratch, size_t scratch_bytes, int64_t np, int N, int scheme, float scale, float f1,
+                       float f2, float *rho, void *stream) {
+  PSC_CHECK_ARG(scheme == PSC_NGP || scheme == PSC_CIC || scheme == PSC_TSC, "unknown mass scheme");
+  PSC_CHECK_ARG(slab_ok(N, 0, N), "N must be a multiple of 8");
+  PSC_CHECK_ARG(scratch && rho, "null pointer");
+  return deposit_binned_impl(scratch, scratch_bytes, np, N, 0, N, 0, scheme, scale, f1, f2, rho, stream);
+}
+
+int psc_deposit_binned_slab(const void *scratch, size_t scratch_bytes, int64_t np, int N, int x0, int nxl, int scheme,
+                            float *rho_ghost, void *stream) {
+  PSC_CHECK_ARG(scheme == PSC_NGP || scheme == PSC_CIC || scheme == PSC_TSC, "unknown mass scheme");
+  PSC_CHECK_ARG(slab_ok(N, x0, nxl), "N and the slab thickness must be multiples of 8");
+  PSC_CHECK_ARG(scratch && rho_ghost, "null pointer");
+  return deposit_binned_impl(scratch, scratch_bytes, np, N, x0, nxl, 1, scheme, 1.0f, 1.0f, 0.0f, rho_ghost, stream);
+}
+
 int psc_interp_kick4_binned(const float *force4, const void *scratch, size_t scratch_bytes, float *vel, float *acc,
                             int64_t np, int N, int scheme, float half_dt, float *maxout, void *stream) {
   PSC_CHECK_ARG(scheme == PSC_CIC || scheme == PSC_TSC, "mass scheme must be CIC or TSC");
-  PSC_CHECK_ARG(N >= BB && (N % BB) == 0, "N must be a multiple of 8");
+  PSC_CHECK_ARG(slab_ok(N, 0, N), "N must be a multiple of 8");
   PSC_CHECK_ARG(force4 && scratch && acc && maxout, "null pointer");
   PSC_CHECK_ARG(((uintptr_t)force4 & 15) == 0, "force4 must be 16-byte aligned");
   if (np == 0) return PSC_OK;
   BinLayout L;
-  if (!bin_layout(const_cast<void *>(scratch), scratch_bytes, np, N, L)) {
+  if (!bin_layout(const_cast<void *>(scratch), scratch_bytes, np, N, 0, N, L)) {
     set_error("psc_interp_kick4_binned: scratch too small");
     return PSC_ERR_WORKSPACE;
   }
@@ -468,9 +509,39 @@ int psc_interp_kick4_binned(const float *force4, const void *scratch, size_t scr
   const float4 *f4 = reinterpret_cast<const float4 *>(force4);
   const int grid = (int)L.nbins;
   if (scheme == PSC_TSC)
-    interp_kick4_binned_kernel<PSC_TSC><<<grid, BI_THREADS, 0, st>>>(f4, L.pos, L.src, L.offsets, vel, acc, N, L.NB, half_dt, maxout);
+    interp_kick4_binned_kernel<PSC_TSC><<<grid, BI_THREADS, 0, st>>>(f4, L.pos, L.src, L.offsets, vel, acc, N, L.NB, 0, 0, N, half_dt, maxout);
   else
-    interp_kick4_binned_kernel<PSC_CIC><<<grid, BI_THREADS, 0, st>>>(f4, L.pos, L.src, L.offsets, vel, acc, N, L.NB, half_dt, maxout);
+    interp_kick4_binned_kernel<PSC_CIC><<<grid, BI_THREADS, 0, st>>>(f4, L.pos, L.src, L.offsets, vel, acc, N, L.NB, 0, 0, N, half_dt, maxout);
+  count_launch();
+  PSC_CHECK_LAUNCH();
+  return PSC_OK;
+}
+
+// ghost = 0: periodic N^3 grids; ghost = G >= 1 + reach(order): phi (and u) have nxl + 2G planes, the owned ones
+// start at plane G
+static int interp_kick_phi_impl(const float *phi, const float *u, float f, int fr_n, int order, int x0, int nxl,
+                                int ghost, const void *scratch, size_t scratch_bytes, float *vel, float *acc,
+                                int64_t np, int N, int scheme, float half_dt, float *maxout, void *stream) {
+  if (np == 0) return PSC_OK;
+  BinLayout L;
+  if (!bin_layout(const_cast<void *>(scratch), scratch_bytes, np, N, x0, nxl, L)) {
+    set_error("psc_interp_kick_phi_binned: scratch too small");
+    return PSC_ERR_WORKSPACE;
+  }
+  cudaStream_t st = as_stream(stream);
+  const int grid = (int)L.nbins;
+  const int nxa = nxl + 2 * ghost;
+#define PSC_IKP(S, O)                                                                                            \
+  interp_kick_phi_binned_kernel<S, O><<<grid, BI_THREADS, 0, st>>>(phi, u, f, fr_n, L.pos, L.src, L.offsets, vel, acc, \
+                                                                   N, L.NB, x0, ghost, nxa, half_dt, maxout)
+#define PSC_IKP_O(S)               \
+  if (order == 2) PSC_IKP(S, 2);    \
+  else if (order == 3) PSC_IKP(S, 3); \
+  else if (order == 5) PSC_IKP(S, 5); \
+  else PSC_IKP(S, 7);
+  if (scheme == PSC_TSC) { PSC_IKP_O(PSC_TSC) } else { PSC_IKP_O(PSC_CIC) }
+#undef PSC_IKP_O
+#undef PSC_IKP
   count_launch();
   PSC_CHECK_LAUNCH();
   return PSC_OK;
@@ -484,27 +555,22 @@ int psc_interp_kick_phi_binned(const float *phi, const float *u, float f, int fr
   PSC_CHECK_ARG(fr_n >= 0 && fr_n <= 2, "fR_n must be 1 or 2");
   PSC_CHECK_ARG(N >= 2 * BB && (N % BB) == 0, "N must be a multiple of 8 and >= 16");
   PSC_CHECK_ARG(phi && scratch && acc && maxout && (u || fr_n == 0), "null pointer");
-  if (np == 0) return PSC_OK;
-  BinLayout L;
-  if (!bin_layout(const_cast<void *>(scratch), scratch_bytes, np, N, L)) {
-    set_error("psc_interp_kick_phi_binned: scratch too small");
-    return PSC_ERR_WORKSPACE;
-  }
-  cudaStream_t st = as_stream(stream);
-  const int grid = (int)L.nbins;
-#define PSC_IKP(S, O) \
-  interp_kick_phi_binned_kernel<S, O><<<grid, BI_THREADS, 0, st>>>(phi, u, f, fr_n, L.pos, L.src, L.offsets, vel, acc, N, L.NB, half_dt, maxout)
-#define PSC_IKP_O(S)               \
-  if (order == 2) PSC_IKP(S, 2);    \
-  else if (order == 3) PSC_IKP(S, 3); \
-  else if (order == 5) PSC_IKP(S, 5); \
-  else PSC_IKP(S, 7);
-  if (scheme == PSC_TSC) { PSC_IKP_O(PSC_TSC) } else { PSC_IKP_O(PSC_CIC) }
-#undef PSC_IKP_O
-#undef PSC_IKP
-  count_launch();
-  PSC_CHECK_LAUNCH();
-  return PSC_OK;
+  return interp_kick_phi_impl(phi, u, f, fr_n, order, 0, N, 0, scratch, scratch_bytes, vel, acc, np, N, scheme,
+                              half_dt, maxout, stream);
+}
+
+int psc_interp_kick_phi_binned_slab(const float *phi_ghost, const float *u_ghost, float f, int fr_n, int order,
+                                    int x0, int nxl, int ghost, const void *scratch, size_t scratch_bytes, float *vel,
+                                    float *acc, int64_t np, int N, int scheme, float half_dt, float *maxout,
+                                    void *stream) {
+  PSC_CHECK_ARG(scheme == PSC_CIC || scheme == PSC_TSC, "mass scheme must be CIC or TSC");
+  PSC_CHECK_ARG(order == 2 || order == 3 || order == 5 || order == 7, "gradient order must be 2, 3, 5 or 7");
+  PSC_CHECK_ARG(fr_n >= 0 && fr_n <= 2, "fR_n must be 1 or 2");
+  PSC_CHECK_ARG(slab_ok(N, x0, nxl) && N >= 2 * BB, "N and the slab thickness must be multiples of 8");
+  PSC_CHECK_ARG(ghost >= 1 + (order == 7 ? 3 : order == 5 ? 2 : 1), "not enough ghost planes for this stencil");
+  PSC_CHECK_ARG(phi_ghost && scratch && acc && maxout && (u_ghost || fr_n == 0), "null pointer");
+  return interp_kick_phi_impl(phi_ghost, u_ghost, f, fr_n, order, x0, nxl, ghost, scratch, scratch_bytes, vel, acc, np,
+                              N, scheme, half_dt, maxout, stream);
 }
 
 }  // extern "C"

@@ -70,23 +70,28 @@ __device__ __forceinline__ float2 green_axis_entry(int n, int N, int p) {
 // Persistent CTAs walk rows (i, j) of N/2+1 contiguous modes, four rows per iteration (four independent
 // 8-byte loads in flight per thread).  The N/2 "even" modes of a row map cleanly onto the threads; the
 // Nyquist mode k = N/2 of the four rows is handled by threads 0..3 afterwards.
+// The spectrum is [N (kx)][nyl (ky = y0 ..)][N/2+1]: nyl = N, y0 = 0 for a whole grid, a y-block for the
+// transposed layout of the slab-decomposed FFT.
 template <int KIND>
-__global__ void __launch_bounds__(256) green_kernel(float2 *__restrict__ spec, int N, int p, float scale) {
+__global__ void __launch_bounds__(256) green_kernel(float2 *__restrict__ spec, int N, int nyl, int y0, int p,
+                                                    float scale) {
   extern __shared__ float2 gtab[];  // [N]
   for (int n = threadIdx.x; n < N; n += blockDim.x) gtab[n] = green_axis_entry<KIND>(n, N, p);
   __syncthreads();
   const int nh = N / 2, nz = nh + 1;
-  const int64_t nrows = (int64_t)N * N;
+  const int64_t nrows = (int64_t)N * nyl;
   const float h = 1.0f / (float)N;
   // -1/(4 pi^2) for the continuous Green's functions, -(h^2/4) for the 7-point one
   const float c = (KIND == PSC_GREEN_7PT ? -(0.25f * h * h) : -0.0253302959105844f) * scale;
   for (int64_t r0 = (int64_t)blockIdx.x * 4; r0 < nrows; r0 += (int64_t)gridDim.x * 4) {
     float kxy[4], wxy[4];
     float2 *row[4];
+    bool dc[4];
 #pragma unroll
     for (int u = 0; u < 4; u++) {
       const int64_t r = min(r0 + u, nrows - 1);
-      const int j = (int)(r % N), i = (int)(r / N);
+      const int j = y0 + (int)(r % nyl), i = (int)(r / nyl);
+      dc[u] = i == 0 && j == 0;
       const float2 tx = gtab[i], ty = gtab[j];
       kxy[u] = tx.x + ty.x;
       wxy[u] = tx.y * ty.y;
@@ -100,7 +105,7 @@ __global__ void __launch_bounds__(256) green_kernel(float2 *__restrict__ spec, i
 #pragma unroll
       for (int u = 0; u < 4; u++) {
         float g = c * (wxy[u] * tz.y) / (kxy[u] + tz.x);
-        if (r0 + u == 0 && k == 0) g = 0.0f;  // DC mode -> 0 (reference: x[0,0,0] = 0 after the division)
+        if (dc[u] && k == 0) g = 0.0f;  // DC mode -> 0 (reference: x[0,0,0] = 0 after the division)
         v[u].x *= g;
         v[u].y *= g;
         if (r0 + u < nrows) row[u][k] = v[u];
@@ -258,14 +263,23 @@ int psc_green(float *spec, int N, int kind, int p, float scale, void *stream) {
   PSC_CHECK_ARG(kind >= PSC_GREEN_PLAIN && kind <= PSC_GREEN_7PT, "unknown Green's function");
   PSC_CHECK_ARG(p >= 0 && p <= 8, "MAS index out of range");
   PSC_CHECK_ARG(N <= 4096, "N out of range");
-  int64_t nrows = (int64_t)N * N;
+  return psc_green_slab(spec, N, N, 0, kind, p, scale, stream);
+}
+
+int psc_green_slab(float *spec_t, int N, int nyl, int y0, int kind, int p, float scale, void *stream) {
+  PSC_CHECK_ARG(spec_t, "null pointer");
+  PSC_CHECK_ARG(N >= 2 && N <= 4096, "N out of range");
+  PSC_CHECK_ARG(nyl >= 1 && y0 >= 0 && y0 + nyl <= N, "bad y block");
+  PSC_CHECK_ARG(kind >= PSC_GREEN_PLAIN && kind <= PSC_GREEN_7PT, "unknown Green's function");
+  PSC_CHECK_ARG(p >= 0 && p <= 8, "MAS index out of range");
+  int64_t nrows = (int64_t)N * nyl;
   int g = (int)((nrows + 3) / 4 < (int64_t)kNumSMs * 8 ? (nrows + 3) / 4 : (int64_t)kNumSMs * 8);
-  float2 *s = reinterpret_cast<float2 *>(spec);
+  float2 *s = reinterpret_cast<float2 *>(spec_t);
   cudaStream_t st = as_stream(stream);
   const size_t smem = sizeof(float2) * N;
-  if (kind == PSC_GREEN_PLAIN) green_kernel<PSC_GREEN_PLAIN><<<g, 256, smem, st>>>(s, N, p, scale);
-  else if (kind == PSC_GREEN_COMPENSATED) green_kernel<PSC_GREEN_COMPENSATED><<<g, 256, smem, st>>>(s, N, p, scale);
-  else green_kernel<PSC_GREEN_7PT><<<g, 256, smem, st>>>(s, N, p, scale);
+  if (kind == PSC_GREEN_PLAIN) green_kernel<PSC_GREEN_PLAIN><<<g, 256, smem, st>>>(s, N, nyl, y0, p, scale);
+  else if (kind == PSC_GREEN_COMPENSATED) green_kernel<PSC_GREEN_COMPENSATED><<<g, 256, smem, st>>>(s, N, nyl, y0, p, scale);
+  else green_kernel<PSC_GREEN_7PT><<<g, 256, smem, st>>>(s, N, nyl, y0, p, scale);
   count_launch();
   PSC_CHECK_LAUNCH();
   return PSC_OK;

@@ -1,0 +1,604 @@
+"""x-slab decomposed particle-mesh step: one slab of N/P mesh planes (and the particles inside it) per GPU.
+
+The reference is single-process (README.md:49); this module is the multi-GPU form of its hot path
+(`integration.integrate` integration.py:17 -> `leapfrog` :192 -> `solver.pm` solver.py:30 with
+`linear_newton_solver = fft`), laid out as SURVEY 8(e) asks:
+
+  rank r of P owns planes [r N/P, (r+1) N/P) of every grid and the particles whose cell floor(x N) is in them
+  kick + drift + wrap          local                                  (psc_kick_drift_wrap)
+  migration                    counts all-to-all + records all-to-all (psc_slab_count / pack / unpack / move)
+  deposit                      local bins -> rho[nxl + 2 ghost planes] (psc_bin_particles_slab, psc_deposit_binned_slab)
+                               ghost planes SENT to the neighbours and ADDED there
+  FFT Poisson solve            2-D R2C per plane -> y-block all-to-all -> 1-D C2C along x -> Green ->
+                               inverse 1-D -> all-to-all -> 2-D C2R      (psc_slab_fft_*, psc_green_slab)
+  gradient + interpolation     potential with G = 1 + stencil-reach ghost planes COPIED from the neighbours
+                               (psc_interp_kick_phi_binned_slab: gradient, TSC gather, half-kick, max|a|, max|v|)
+  time step                    all-reduce(max) of two floats
+
+Collectives go through a small `Comm` interface with three implementations: `SelfComm` (P = 1),
+`TorchComm` (torch.distributed: NCCL over NVLink on GPUs, gloo in the CPU tests) and `ThreadComm` (P virtual
+ranks as threads of one process sharing one GPU: lets the single-GPU test tier exercise the whole slab path).
+The kernels are reached through an `ops` object (`CudaOps` = the C ABI); tests may pass another implementation
+of the same methods (tests/slab_oracle_ops.py: the CPU oracle) to check the host logic without a GPU -- the
+product default is CudaOps and nothing here falls back to it silently.
+"""
+import ctypes as C
+import logging
+import threading
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import _lib
+
+REC = 8  # floats per migration record (x y z vx vy vz id_lo id_hi)
+
+
+# ------------------------------------------------------------------------------------------ comms
+class SelfComm:
+    """P = 1: every exchange is with oneself (periodic wrap)."""
+    rank, size = 0, 1
+
+    def exchange_counts(self, counts):
+        return list(counts)
+
+    def all_to_all_v(self, send, send_counts, recv_counts):
+        return send
+
+    def all_to_all_equal(self, send, out):
+        out.copy_(send)
+        return out
+
+    def exchange_planes(self, to_left, to_right):
+        return to_right, to_left
+
+    def allreduce_max_(self, t):
+        return t
+
+    def allreduce_sum_(self, t):
+        return t
+
+    def barrier(self):
+        pass
+
+
+class TorchComm:
+    """torch.distributed process group (NCCL on GPUs, gloo on CPU).  Everything is expressed as all-to-all /
+    all-reduce so that the same code runs on both backends."""
+
+    def __init__(self, group=None):
+        self.group = group
+        self.rank = dist.get_rank(group)
+        self.size = dist.get_world_size(group)
+
+    def exchange_counts(self, counts):
+        dev = "cuda" if dist.get_backend(self.group) == "nccl" else "cpu"
+        s = torch.tensor(list(counts), dtype=torch.int64, device=dev)
+        r = torch.empty_like(s)
+        dist.all_to_all_single(r, s, group=self.group)
+        return [int(v) for v in r.cpu().tolist()]
+
+    def all_to_all_v(self, send, send_counts, recv_counts):
+        recv = torch.empty((int(sum(recv_counts)),) + tuple(send.shape[1:]), dtype=send.dtype, device=send.device)
+        dist.all_to_all_single(recv, send.contiguous(), list(recv_counts), list(send_counts), group=self.group)
+        return recv
+
+    def all_to_all_equal(self, send, out):
+        dist.all_to_all_single(out, send, group=self.group)
+        return out
+
+    def exchange_planes(self, to_left, to_right):
+        P, r = self.size, self.rank
+        left, right = (r - 1) % P, (r + 1) % P
+        n = to_left.shape[0]
+        assert to_right.shape == to_left.shape
+        counts = [0] * P
+        if P == 2:
+            send = torch.cat([to_left, to_right])
+            counts[left] = 2 * n
+            recv = self.all_to_all_v(send, counts, counts)
+            # the peer is both neighbours: its to_left comes from my right, its to_right from my left
+            return recv[n:], recv[:n]
+        parts = sorted([(left, to_left), (right, to_right)], key=lambda t: t[0])
+        send = torch.cat([p[1] for p in parts])
+        counts[left] = n
+        counts[right] = n
+        recv = self.all_to_all_v(send, counts, counts)
+        first, second = recv[:n], recv[n:]
+        # chunks arrive ordered by source rank; the left neighbour sent its to_right, the right one its to_left
+        return (first, second) if left < right else (second, first)
+
+    def allreduce_max_(self, t):
+        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
+        return t
+
+    def allreduce_sum_(self, t):
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+        return t
+
+    def barrier(self):
+        dist.barrier(group=self.group)
+
+
+class _ThreadWorld:
+    def __init__(self, size):
+        self.size = size
+        self.barrier = threading.Barrier(size)
+        self.slots = [None] * size
+
+
+class ThreadComm:
+    """P virtual ranks = P threads of one process (all on the current CUDA device, same stream).  Used by the
+    single-GPU tests and tools to run the complete slab path without NCCL.  Create with ThreadComm.world(P)."""
+
+    def __init__(self, world, rank):
+        self.w, self.rank, self.size = world, rank, world.size
+
+    @staticmethod
+    def world(size):
+        w = _ThreadWorld(size)
+        return [ThreadComm(w, r) for r in range(size)]
+
+    def _share(self, obj):
+        self.w.slots[self.rank] = obj
+        self.w.barrier.wait()
+        allv = list(self.w.slots)
+        self.w.barrier.wait()
+        return allv
+
+    def barrier(self):
+        self.w.barrier.wait()
+
+    def exchange_counts(self, counts):
+        allc = self._share(list(counts))
+        return [int(allc[s][self.rank]) for s in range(self.size)]
+
+    def all_to_all_v(self, send, send_counts, recv_counts):
+        offs = np.concatenate([[0], np.cumsum(send_counts)]).astype(np.int64)
+        alls = self._share((send, offs))
+        parts = []
+        for s in range(self.size):
+            t, o = alls[s]
+            parts.append(t[int(o[self.rank]):int(o[self.rank + 1])])
+        out = torch.cat(parts)
+        self.w.barrier.wait()  # senders may reuse their buffers only after everybody copied
+        return out
+
+    def all_to_all_equal(self, send, out):
+        n = send.shape[0] // self.size
+        alls = self._share(send)
+        for s in range(self.size):
+            out[s * n:(s + 1) * n] = alls[s][self.rank * n:(self.rank + 1) * n]
+        self.w.barrier.wait()
+        return out
+
+    def exchange_planes(self, to_left, to_right):
+        alls = self._share((to_left, to_right))
+        left, right = (self.rank - 1) % self.size, (self.rank + 1) % self.size
+        out = alls[left][1].clone(), alls[right][0].clone()
+        self.w.barrier.wait()
+        return out
+
+    def _allreduce(self, t, fn):
+        alls = self._share(t.clone())
+        acc = alls[0].clone()
+        for o in alls[1:]:
+            acc = fn(acc, o)
+        t.copy_(acc)
+        return t
+
+    def allreduce_max_(self, t):
+        return self._allreduce(t, torch.maximum)
+
+    def allreduce_sum_(self, t):
+        return self._allreduce(t, torch.add)
+
+
+def default_comm():
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        return TorchComm()
+    return SelfComm()
+
+
+# ------------------------------------------------------------------------------------------ kernels
+class CudaOps:
+    """The slab kernels through the C ABI (include/pysco_b200.h).  One instance per slab."""
+
+    def __init__(self, N, P, rank):
+        self.N, self.P, self.rank = N, P, rank
+        self.nxl = N // P
+        self.x0 = rank * self.nxl
+        self.nyl = N // P
+        self.y0 = rank * self.nyl
+        self.lib = _lib.load()
+        self.dev = _lib.device()
+        self._plan = None
+        self._work = None
+        self._scratch = None
+
+    # -- particles
+    def kick_drift_wrap(self, pos, vel, acc, half_dt, dt, dt_is_f64):
+        _lib.check(self.lib.psc_kick_drift_wrap(_lib.ptr(pos), _lib.ptr(vel), _lib.ptr(acc), pos.shape[0],
+                                                float(half_dt), float(dt), int(dt_is_f64), _lib.stream()))
+
+    def count_owners(self, pos):
+        counts = torch.empty((self.P,), dtype=torch.int64, device=self.dev)
+        _lib.check(self.lib.psc_slab_count(_lib.ptr(pos), pos.shape[0], self.N, self.nxl, self.P, _lib.ptr(counts),
+                                           _lib.stream()))
+        return counts
+
+    def pack_leavers(self, pos, vel, ids, offsets, nout):
+        sendbuf = torch.empty((nout, REC), dtype=torch.float32, device=self.dev)
+        holes = torch.empty((nout,), dtype=torch.int64, device=self.dev)
+        cursor = torch.empty((self.P,), dtype=torch.int64, device=self.dev)
+        _lib.check(self.lib.psc_slab_pack_leavers(_lib.ptr(pos), _lib.ptr(vel), _lib.ptr(ids), pos.shape[0], self.N,
+                                                  self.nxl, self.P, self.rank, _lib.ptr(offsets), _lib.ptr(cursor),
+                                                  _lib.ptr(sendbuf), _lib.ptr(holes), _lib.stream()))
+        return sendbuf, holes
+
+    def unpack_rows(self, recvbuf, rows, pos, vel, ids):
+        _lib.check(self.lib.psc_slab_unpack_rows(_lib.ptr(recvbuf), _lib.ptr(rows), rows.shape[0], _lib.ptr(pos),
+                                                 _lib.ptr(vel), _lib.ptr(ids), _lib.stream()))
+
+    def move_rows(self, src, dst, pos, vel, ids):
+        _lib.check(self.lib.psc_slab_move_rows(_lib.ptr(src), _lib.ptr(dst), src.shape[0], _lib.ptr(pos),
+                                               _lib.ptr(vel), _lib.ptr(ids), _lib.stream()))
+
+    def max_abs(self, x):
+        out = torch.zeros((1,), dtype=torch.float32, device=self.dev)
+        if x.numel():
+            _lib.check(self.lib.psc_max_abs(_lib.ptr(x), x.numel(), _lib.ptr(out), _lib.stream()))
+        return out
+
+    def morton_order(self, pos):
+        """permutation that sorts the local particles by Morton key (morton.py:42-137, utils.py:1019-1075)"""
+        from . import utils
+        n = pos.shape[0]
+        keys = torch.empty((n,), dtype=torch.int64, device=self.dev)
+        _lib.check(self.lib.psc_morton_keys(_lib.ptr(pos), n, _lib.ptr(keys), _lib.stream()))
+        return utils.argsort_keys(keys)
+
+    def gather_rows(self, idx, a):
+        out = torch.empty_like(a)
+        _lib.check(self.lib.psc_gather3(_lib.ptr(idx), _lib.ptr(a), _lib.ptr(out), a.shape[0], _lib.stream()))
+        return out
+
+    # -- particles <-> mesh
+    def bin(self, pos):
+        n = pos.shape[0]
+        nbytes = int(self.lib.psc_bin_workspace_bytes_slab(n, self.N, self.nxl))
+        if self._scratch is None or self._scratch.numel() < nbytes:
+            self._scratch = None
+            self._scratch = torch.empty((int(nbytes * 1.1) + 256,), dtype=torch.uint8, device=self.dev)
+        _lib.check(self.lib.psc_bin_particles_slab(_lib.ptr(pos), n, self.N, self.x0, self.nxl,
+                                                   _lib.ptr(self._scratch), self._scratch.numel(), _lib.stream()))
+        return n
+
+    def deposit(self, binned, scheme):
+        rho = torch.empty((self.nxl + 2, self.N, self.N), dtype=torch.float32, device=self.dev)
+        _lib.check(self.lib.psc_deposit_binned_slab(_lib.ptr(self._scratch), self._scratch.numel(), binned, self.N,
+                                                    self.x0, self.nxl, scheme, _lib.ptr(rho), _lib.stream()))
+        return rho
+
+    def affine(self, x, f1, f2):
+        _lib.check(self.lib.psc_linear_operator(_lib.ptr(x), float(f1), float(f2), _lib.ptr(x), x.numel(),
+                                                _lib.stream()))
+
+    def interp_kick_phi(self, phi_g, ghost, order, binned, vel, acc, scheme, half_dt):
+        mx = torch.zeros((2,), dtype=torch.float32, device=self.dev)
+        _lib.check(self.lib.psc_interp_kick_phi_binned_slab(
+            _lib.ptr(phi_g), None, 0.0, 0, order, self.x0, self.nxl, ghost, _lib.ptr(self._scratch),
+            self._scratch.numel(), _lib.ptr(vel), _lib.ptr(acc), binned, self.N, scheme, float(half_dt), _lib.ptr(mx),
+            _lib.stream()))
+        return mx
+
+    # -- transposed FFT
+    def _fft_plan(self):
+        if self._plan is None:
+            h = C.c_void_p()
+            _lib.check(self.lib.psc_slab_fft_plan_create(self.N, self.nxl, self.nyl, C.byref(h)))
+            nbytes = int(self.lib.psc_slab_fft_workspace_bytes(h))
+            self._work = torch.empty((max(nbytes, 256),), dtype=torch.uint8, device=self.dev)
+            _lib.check(self.lib.psc_slab_fft_set_workspace(h, _lib.ptr(self._work)))
+            self._plan = h
+        return self._plan
+
+    def spectrum_buffer(self):
+        return torch.empty((self.nxl * self.N * (self.N // 2 + 1), 2), dtype=torch.float32, device=self.dev)
+
+    def fft2d_r2c(self, planes, spec2d):
+        _lib.check(self.lib.psc_slab_fft_r2c_planes(self._fft_plan(), _lib.ptr(planes), _lib.ptr(spec2d),
+                                                    _lib.stream()))
+
+    def fft2d_c2r(self, spec2d, planes):
+        _lib.check(self.lib.psc_slab_fft_c2r_planes(self._fft_plan(), _lib.ptr(spec2d), _lib.ptr(planes),
+                                                    _lib.stream()))
+
+    def yblocks(self, src, dst, to_blocks):
+        _lib.check(self.lib.psc_slab_yblocks(_lib.ptr(src), _lib.ptr(dst), self.N, self.nxl, self.nyl,
+                                             int(to_blocks), _lib.stream()))
+
+    def fft_x(self, spec_t, inverse):
+        _lib.check(self.lib.psc_slab_fft_x(self._fft_plan(), _lib.ptr(spec_t), int(inverse), _lib.stream()))
+
+    def green(self, spec_t, kind, p, scale):
+        _lib.check(self.lib.psc_green_slab(_lib.ptr(spec_t), self.N, self.nyl, self.y0, kind, p, float(scale),
+                                           _lib.stream()))
+
+    def close(self):
+        if self._plan is not None:
+            self.lib.psc_slab_fft_plan_destroy(self._plan)
+            self._plan = None
+        self._work = self._scratch = None
+
+
+# ------------------------------------------------------------------------------------------ the slab
+_SCHEMES = {"cic": (_lib.CIC, 2), "tsc": (_lib.TSC, 3)}
+_REACH = {2: 1, 3: 1, 5: 2, 7: 3}
+
+
+class Slab:
+    """State and step of one rank: particle buffers (with spare capacity for arrivals), ids, and the kernels."""
+
+    def __init__(self, ncells_1d, comm=None, ops=None, capacity_factor=1.3):
+        self.comm = comm if comm is not None else default_comm()
+        self.N = int(ncells_1d)
+        self.P, self.rank = self.comm.size, self.comm.rank
+        if self.N % self.P or (self.N // self.P) % 8:
+            raise ValueError(f"slab decomposition needs N / P to be a multiple of 8 (N={self.N}, P={self.P})")
+        self.nxl = self.N // self.P
+        self.x0 = self.rank * self.nxl
+        self.ops = ops if ops is not None else CudaOps(self.N, self.P, self.rank)
+        self.capacity_factor = capacity_factor
+        self.np = 0
+        self.pos = self.vel = self.acc = self.ids = None
+        self.max_acc = self.max_vel = None
+        self.potential = None  # owned planes [nxl, N, N] of the last solve (a view into the ghosted array)
+        self.migrated_last = (0, 0)
+
+    # -- particle storage
+    @property
+    def position(self):
+        return self.pos[:self.np]
+
+    @property
+    def velocity(self):
+        return self.vel[:self.np]
+
+    @property
+    def acceleration(self):
+        return self.acc[:self.np]
+
+    @property
+    def particle_ids(self):
+        return self.ids[:self.np]
+
+    def _ensure_capacity(self, n):
+        cap = 0 if self.pos is None else self.pos.shape[0]
+        if n <= cap:
+            return
+        new_cap = int(n * self.capacity_factor) + 1024
+
+        def grow(a, width, dtype):
+            shape = (new_cap, width) if width else (new_cap,)
+            b = torch.empty(shape, dtype=dtype, device=self._device())
+            if a is not None and self.np:
+                b[:self.np] = a[:self.np]
+            return b
+
+        self.pos = grow(self.pos, 3, torch.float32)
+        self.vel = grow(self.vel, 3, torch.float32)
+        self.acc = grow(self.acc, 3, torch.float32)
+        self.ids = grow(self.ids, 0, torch.int64)
+
+    def _device(self):
+        return getattr(self.ops, "dev", torch.device("cpu"))
+
+    def set_particles(self, position, velocity, ids):
+        """Adopt particles (any of them may lie outside the slab: migrate() is called).  Arrays are [n,3] / [n]
+        tensors on this rank's device; ids are the global rows of the particles (kept through migrations so that
+        results can be put back in the reference's order)."""
+        n = position.shape[0]
+        self.np = 0
+        self.pos = self.vel = self.acc = self.ids = None
+        self._ensure_capacity(n)
+        self.pos[:n] = position
+        self.vel[:n] = velocity
+        self.ids[:n] = ids
+        self.acc[:n] = 0
+        self.np = n
+        self.migrate()
+
+    # -- migration
+    def migrate(self):
+        """Send every particle that left the slab to its owner and take in the arrivals (O(migrants) row moves)."""
+        ops, comm, me = self.ops, self.comm, self.rank
+        n = self.np
+        counts = ops.count_owners(self.pos[:n]).cpu().tolist()
+        send_counts = [int(c) for c in counts]
+        send_counts[me] = 0
+        nout = sum(send_counts)
+        recv_counts = comm.exchange_counts(send_counts)
+        nin = sum(recv_counts)
+        self.migrated_last = (nout, nin)
+        if comm.size == 1:
+            return  # periodic wrap keeps every particle in the only slab
+        dev = self._device()
+        if nout:
+            offsets = torch.tensor(np.concatenate([[0], np.cumsum(send_counts)[:-1]]).astype(np.int64), device=dev)
+            sendbuf, holes = ops.pack_leavers(self.pos[:n], self.vel[:n], self.ids[:n], offsets, nout)
+        else:
+            sendbuf = torch.empty((0, REC), dtype=torch.float32, device=dev)
+            holes = torch.empty((0,), dtype=torch.int64, device=dev)
+        # every rank enters the all-to-all, even with nothing to send or receive
+        recvbuf = comm.all_to_all_v(sendbuf, send_counts, recv_counts)
+        if nout == 0 and nin == 0:
+            return
+        n_new = n - nout + nin
+        self._ensure_capacity(n_new)
+        if nin >= nout:
+            rows = torch.cat([holes, torch.arange(n, n_new, dtype=torch.int64, device=dev)])
+            ops.unpack_rows(recvbuf, rows, self.pos, self.vel, self.ids)
+        else:
+            low = holes[holes < n_new]           # holes that stay inside the shrunken array
+            ops.unpack_rows(recvbuf, low[:nin].contiguous(), self.pos, self.vel, self.ids)
+            dst = low[nin:].contiguous()
+            if dst.numel():
+                # stayers living in the tail [n_new, n) move into the remaining holes
+                tail = torch.ones((n - n_new,), dtype=torch.bool, device=dev)
+                tail[holes[holes >= n_new] - n_new] = False
+                src = torch.nonzero(tail).flatten() + n_new
+                assert src.numel() == dst.numel(), (src.numel(), dst.numel())
+                ops.move_rows(src.contiguous(), dst, self.pos, self.vel, self.ids)
+        self.np = n_new
+
+    # -- Poisson solve on the slab
+    def fft_poisson(self, rhs_planes, out_planes, param):
+        """solver.fft (solver.py:452-523) with the transposed slab FFT.  rhs_planes [nxl,N,N] is consumed;
+        the potential is written to out_planes [nxl,N,N] (may be a view into a ghosted array)."""
+        ops, comm = self.ops, self.comm
+        name = param["linear_newton_solver"].casefold()
+        p = int(param["MAS_index"])
+        if name == "fft":
+            kind, pp = (_lib.GREEN_PLAIN, 0) if p == 0 else (_lib.GREEN_COMPENSATED, p)
+        elif name == "fft_7pt":
+            kind, pp = _lib.GREEN_7PT, 0
+        else:
+            raise NotImplementedError(f"slab path: linear_newton_solver={param['linear_newton_solver']!r}, "
+                                      "should be 'fft' or 'fft_7pt'")
+        a = ops.spectrum_buffer()
+        b = ops.spectrum_buffer()
+        ops.fft2d_r2c(rhs_planes, a)            # [nxl][N][nz]
+        ops.yblocks(a, b, True)                 # [P][nxl][nyl][nz]
+        comm.all_to_all_equal(b.view(self.P, -1), a.view(self.P, -1))   # [N][nyl][nz]
+        ops.fft_x(a, False)
+        ops.green(a, kind, pp, 1.0 / float(self.N) ** 3)
+        ops.fft_x(a, True)
+        comm.all_to_all_equal(a.view(self.P, -1), b.view(self.P, -1))   # [P(y block)][nxl][nyl][nz]
+        ops.yblocks(b, a, False)                # [nxl][N][nz]
+        ops.fft2d_c2r(a, out_planes)
+
+    # -- solver.pm on the slab
+    def pm(self, param, kick=None):
+        """solver.pm (solver.py:30-215), Newtonian / parametrized, FFT solvers.  Fills self.acc[:np]; with
+        kick = half_dt also applies the second half-kick to the velocities.  Returns the device tensor
+        [max|a|, max|v|] already reduced over ranks."""
+        ops, comm, N, nxl = self.ops, self.comm, self.N, self.nxl
+        theory = param["theory"].casefold()
+        if theory not in ("newton", "parametrized"):
+            raise NotImplementedError(f"slab path: theory={param['theory']!r} (newton / parametrized only)")
+        ms = param["mass_scheme"].casefold()
+        if ms not in _SCHEMES:
+            raise NotImplementedError(f"{param['mass_scheme']=}, should be 'CIC' or 'TSC'")
+        scheme, param["MAS_index"] = _SCHEMES[ms]
+        order = param["gradient_stencil_order"]
+        if order not in _REACH:
+            raise NotImplementedError(f"Unsupported: gradient_order={order}")
+        if theory == "parametrized":
+            a = param["aexp"]
+            evo = a ** (-3 * (1 + param["w0"] + param["wa"])) * np.exp(-3 * param["wa"] * (1 - a))
+            olz = (param["Om_lambda"] * evo / (param["Om_m"] * a ** (-3) + param["Om_r"] * a ** (-4)
+                                               + param["Om_lambda"] * evo))
+            param["parametrized_mu_z"] = np.float32(1 + param["parametrized_mu0"] * olz / param["Om_lambda"])
+        else:
+            param["parametrized_mu_z"] = np.float32(1)
+        n = self.np
+        binned = ops.bin(self.pos[:n])
+        rho = ops.deposit(binned, scheme)                      # [nxl + 2, N, N] raw sums
+        from_left, from_right = comm.exchange_planes(rho[0:1], rho[nxl + 1:nxl + 2])
+        rho[1] += from_left[0]         # the left neighbour's plane nxl + 1 is my first owned plane
+        rho[nxl] += from_right[0]      # the right neighbour's plane 0 is my last owned plane
+        rhs = rho[1:nxl + 1]
+        conversion = np.float32(N ** 3 / param["npart"]) if N ** 3 != param["npart"] else np.float32(1)
+        if conversion != 1:
+            ops.affine(rhs, conversion, 0.0)
+        f1 = np.float32(1.5 * param["aexp"] * param["Om_m"] * param["parametrized_mu_z"])
+        ops.affine(rhs, f1, -f1)
+        G = 1 + _REACH[order]
+        if nxl < G:
+            raise ValueError(f"slab of {nxl} planes is thinner than the {G} ghost planes the stencils need")
+        phi_g = torch.empty((nxl + 2 * G, N, N), dtype=torch.float32, device=rho.device)
+        self.fft_poisson(rhs, phi_g[G:G + nxl], param)
+        del rho, rhs
+        from_left, from_right = comm.exchange_planes(phi_g[G:2 * G], phi_g[nxl:nxl + G])
+        phi_g[:G] = from_left          # the left neighbour's last G owned planes
+        phi_g[nxl + G:] = from_right   # the right neighbour's first G owned planes
+        half_dt = 0.0 if kick is None else kick
+        mx = ops.interp_kick_phi(phi_g, G, order, binned, self.vel[:n] if kick is not None else None,
+                                 self.acc[:n], scheme, half_dt)
+        self.potential = phi_g[G:G + nxl]
+        if kick is None:
+            mx[1] = ops.max_abs(self.vel[:n])[0]
+        comm.allreduce_max_(mx)
+        m = mx.cpu().numpy()
+        self.max_acc, self.max_vel = np.float32(m[0]), np.float32(m[1])
+        return mx
+
+    # -- integration.integrate / leapfrog on the slab
+    def leapfrog(self, dt, tables, param):
+        """integration.leapfrog (integration.py:192-264)"""
+        from . import utils
+        n = self.np
+        half_dt = np.float32(0.5 * dt)
+        dt_is_f64 = 0 if isinstance(dt, np.float32) else 1
+        self.ops.kick_drift_wrap(self.pos[:n], self.vel[:n], self.acc[:n], half_dt, dt, dt_is_f64)
+        param["t"] += dt
+        param["aexp_old"] = param["aexp"]
+        param["aexp"] = np.exp(tables[0](param["t"]))
+        logging.info(f"{param['t']=} {param['aexp']=}")
+        utils.set_units(param)
+        self.migrate()
+        self.pm(param, kick=half_dt)
+
+    def integrate(self, tables, param, t_snap_next=np.float32(0)):
+        """integration.integrate (integration.py:17-118), leapfrog only"""
+        if self.max_acc is None:
+            raise RuntimeError("call pm() once before integrate() (the time step needs max|a|, max|v|)")
+        if param["integrator"].casefold() != "leapfrog":
+            raise NotImplementedError("slab path: integrator must be 'leapfrog'")
+        dx = np.float32(0.5 ** param["ncoarse"])
+        cf = np.float32(param["Courant_factor"])
+        dt1 = cf * np.sqrt(dx / self.max_acc)
+        dt2 = cf * dx / self.max_vel
+        aexp_factor = 1.0 + 0.01 * param["max_aexp_stepping"]
+        dt3 = np.float32(tables[1](np.log(aexp_factor * param["aexp"])) - tables[1](np.log(param["aexp"])))
+        dt = np.min([dt1, dt2, dt3])
+        if (param["t"] + dt) > t_snap_next:
+            dt = t_snap_next - param["t"]
+            param["write_snapshot"] = True
+        else:
+            param["write_snapshot"] = False
+        self.leapfrog(dt, tables, param)
+        return dt
+
+    def reorder(self):
+        """utils.reorder_particles (utils.py:1019-1075) on the local particles (the Morton key's leading bits are
+        x, so the local order is a contiguous piece of the global Morton order)."""
+        n = self.np
+        if n == 0:
+            return
+        idx = self.ops.morton_order(self.pos[:n])
+        for name in ("pos", "vel", "acc"):
+            a = getattr(self, name)
+            a[:n] = self.ops.gather_rows(idx, a[:n].contiguous())
+        self.ids[:n] = self.ids[:n][idx]
+
+    # -- gathering results in the reference's order (tests / snapshots)
+    def gather_to_root(self, npart_total):
+        """All particles in global-id order on rank 0 (pos, vel, acc as CPU tensors); None elsewhere."""
+        n = self.np
+        payload = torch.cat([self.pos[:n].double(), self.vel[:n].double(), self.acc[:n].double(),
+                             self.ids[:n].double().view(-1, 1)], dim=1)
+        counts = [0] * self.P
+        counts[0] = n
+        recv_counts = self.comm.exchange_counts(counts)
+        got = self.comm.all_to_all_v(payload, counts, recv_counts)
+        if self.rank != 0:
+            return None
+        got = got.cpu()
+        assert got.shape[0] == npart_total, (got.shape, npart_total)
+        order = torch.argsort(got[:, 9].long())
+        got = got[order]
+        assert torch.equal(got[:, 9].long(), torch.arange(npart_total)), "particle ids lost or duplicated"
+        return got[:, 0:3].float(), got[:, 3:6].float(), got[:, 6:9].float()

@@ -1,0 +1,156 @@
+"""CPU stand-in for pysco_b200.slab.CudaOps, built on the oracle (test infrastructure only).
+
+It lets the world_size-2 gloo test run the slab decomposition's HOST logic (migration bookkeeping, ghost-plane
+exchanges, the y-block all-to-all of the transposed FFT, time-step reduction) without a GPU: every kernel call is
+answered by the C/NumPy oracle working on the full periodic grid and cut down to the slab.
+"""
+import numpy as np
+import torch
+
+import oracle
+from oracle import api as oapi
+
+REC = 8
+
+
+def _np(t):
+    return t.detach().cpu().numpy()
+
+
+class OracleOps:
+    def __init__(self, N, P, rank):
+        self.N, self.P, self.rank = N, P, rank
+        self.nxl = N // P
+        self.x0 = rank * self.nxl
+        self.nyl = N // P
+        self.y0 = rank * self.nyl
+        self.dev = torch.device("cpu")
+        self._binned = None
+
+    # -- particles
+    def kick_drift_wrap(self, pos, vel, acc, half_dt, dt, dt_is_f64):
+        p, v, a = _np(pos), _np(vel), _np(acc)
+        oracle.utils.add_vector_scalar_inplace(v, a, -np.float32(half_dt))
+        oracle.utils.add_vector_scalar_inplace(p, v, dt if dt_is_f64 else np.float32(dt))
+        oracle.utils.periodic_wrap(p)
+
+    def _owner(self, pos):
+        i = (_np(pos)[:, 0] * np.float32(self.N)).astype(np.int64)
+        return np.clip(i // self.nxl, 0, self.P - 1)
+
+    def count_owners(self, pos):
+        return torch.from_numpy(np.bincount(self._owner(pos), minlength=self.P).astype(np.int64))
+
+    def pack_leavers(self, pos, vel, ids, offsets, nout):
+        own = self._owner(pos)
+        rows = np.nonzero(own != self.rank)[0]
+        rows = rows[np.argsort(own[rows], kind="stable")]
+        assert rows.size == nout
+        rec = np.empty((nout, REC), dtype=np.float32)
+        rec[:, 0:3] = _np(pos)[rows]
+        rec[:, 3:6] = _np(vel)[rows]
+        rec[:, 6:8] = _np(ids)[rows].astype(np.int64).view(np.float32).reshape(-1, 2)
+        return torch.from_numpy(rec), torch.from_numpy(rows.astype(np.int64))
+
+    def unpack_rows(self, recvbuf, rows, pos, vel, ids):
+        rec = _np(recvbuf)
+        r = _np(rows)
+        _np(pos)[r] = rec[:, 0:3]
+        _np(vel)[r] = rec[:, 3:6]
+        _np(ids)[r] = np.ascontiguousarray(rec[:, 6:8]).view(np.int64).reshape(-1)
+
+    def move_rows(self, src, dst, pos, vel, ids):
+        s, d = _np(src), _np(dst)
+        for a in (pos, vel, ids):
+            _np(a)[d] = _np(a)[s]
+
+    def max_abs(self, x):
+        return torch.tensor([float(np.abs(_np(x)).max()) if x.numel() else 0.0], dtype=torch.float32)
+
+    def morton_order(self, pos):
+        keys = oracle.morton.positions_to_keys(np.ascontiguousarray(_np(pos)))
+        return torch.from_numpy(np.argsort(keys, kind="stable").astype(np.int64))
+
+    def gather_rows(self, idx, a):
+        return a[idx]
+
+    # -- particles <-> mesh (oracle on the full periodic grid, cut to the slab + ghosts)
+    def bin(self, pos):
+        self._binned = np.ascontiguousarray(_np(pos))
+        own = self._owner(pos)
+        assert (own == self.rank).all(), "binning particles that are not in the slab"
+        return pos.shape[0]
+
+    def _planes(self, ghost):
+        return np.arange(self.x0 - ghost, self.x0 + self.nxl + ghost) % self.N
+
+    def deposit(self, binned, scheme):
+        fn = {1: oracle.mesh.CIC, 2: oracle.mesh.TSC_seq}[scheme]
+        full = fn(self._binned, self.N) if binned else np.zeros((self.N,) * 3, np.float32)
+        if self.P == 1:
+            # ghosts of a periodic slab: what fell on the wrapped planes is counted in the ghosts only
+            out = np.zeros((self.nxl + 2, self.N, self.N), np.float32)
+            out[1:-1] = full
+            return torch.from_numpy(out)
+        # particles of this slab only touch planes x0-1 .. x0+nxl, each exactly once when P >= 2 and nxl >= 2
+        return torch.from_numpy(np.ascontiguousarray(full[self._planes(1)]))
+
+    def affine(self, x, f1, f2):
+        a = _np(x)
+        oracle.utils.linear_operator_inplace(a.reshape(-1), np.float32(f1), np.float32(f2))
+
+    def interp_kick_phi(self, phi_g, ghost, order, binned, vel, acc, scheme, half_dt):
+        full = np.zeros((self.N,) * 3, np.float32)
+        full[self._planes(ghost)] = _np(phi_g)
+        force = oracle.mesh.derivative(full, order)
+        fn = {1: oracle.mesh.invCIC_vec, 2: oracle.mesh.invTSC_vec}[scheme]
+        a = fn(force, self._binned) if binned else np.zeros((0, 3), np.float32)
+        _np(acc)[:] = a
+        mv = 0.0
+        if vel is not None:
+            v = _np(vel)
+            oracle.utils.add_vector_scalar_inplace(v, a, -np.float32(half_dt))
+            mv = float(np.abs(v).max()) if v.size else 0.0
+        return torch.tensor([float(np.abs(a).max()) if a.size else 0.0, mv], dtype=torch.float32)
+
+    # -- transposed FFT
+    def spectrum_buffer(self):
+        return torch.empty((self.nxl * self.N * (self.N // 2 + 1), 2), dtype=torch.float32)
+
+    def _c(self, t, shape):
+        return _np(t).reshape(-1).view(np.complex64).reshape(shape)
+
+    def fft2d_r2c(self, planes, spec2d):
+        self._c(spec2d, (self.nxl, self.N, self.N // 2 + 1))[:] = np.fft.rfftn(_np(planes), axes=(1, 2))
+
+    def fft2d_c2r(self, spec2d, planes):
+        s = self._c(spec2d, (self.nxl, self.N, self.N // 2 + 1))
+        # unnormalised, like cuFFT
+        _np(planes)[:] = np.fft.irfftn(s, s=(self.N, self.N), axes=(1, 2)) * (self.N * self.N)
+
+    def yblocks(self, src, dst, to_blocks):
+        nz = self.N // 2 + 1
+        if to_blocks:
+            a = self._c(src, (self.nxl, self.P, self.nyl, nz))
+            self._c(dst, (self.P, self.nxl, self.nyl, nz))[:] = a.transpose(1, 0, 2, 3)
+        else:
+            a = self._c(src, (self.P, self.nxl, self.nyl, nz))
+            self._c(dst, (self.nxl, self.P, self.nyl, nz))[:] = a.transpose(1, 0, 2, 3)
+
+    def fft_x(self, spec_t, inverse):
+        s = self._c(spec_t, (self.N, self.nyl, self.N // 2 + 1))
+        s[:] = np.fft.ifft(s, axis=0) * self.N if inverse else np.fft.fft(s, axis=0)
+
+    def green(self, spec_t, kind, p, scale):
+        ones = np.ones((self.N, self.N, self.N // 2 + 1), dtype=np.complex64)
+        if kind == 0:
+            oapi.fourier.inverse_laplacian(ones)
+        elif kind == 1:
+            oapi.fourier.inverse_laplacian_compensated(ones, p)
+        else:
+            oapi.fourier.inverse_laplacian_7pt(ones)
+        s = self._c(spec_t, (self.N, self.nyl, self.N // 2 + 1))
+        s *= ones[:, self.y0:self.y0 + self.nyl, :] * np.float32(scale)
+
+    def close(self):
+        pass

@@ -1,0 +1,164 @@
+"""CPU tests of the x-slab decomposition's host logic (pysco_b200/slab.py): migration bookkeeping, ghost-plane
+exchanges, the transposed-FFT all-to-alls and the time-step reduction, with the oracle standing in for the CUDA
+kernels (tests/slab_oracle_ops.py).  Two transports are covered: ThreadComm (P = 1, 2, 4 virtual ranks in one
+process) and TorchComm over gloo with world_size 2 (spawned processes).  The yardstick is the oracle's
+single-process leapfrog (oracle/host.py)."""
+import os
+import socket
+import sys
+import threading
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "tests"), os.path.join(ROOT, "tests", "golden")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import cases  # noqa: E402
+import oracle  # noqa: E402
+from oracle import host  # noqa: E402
+
+NSTEPS = 3
+
+
+def _setup(N):
+    tables = cases.toy_tables()
+    pos = cases.lattice_particles(N, 0.4, seed=11)
+    vel = cases.velocities(N ** 3, seed=12, scale=0.3)  # large enough that particles cross slab boundaries
+    param = cases.base_param(int(np.log2(N)), N ** 3, linear_newton_solver="fft")
+    param["aexp"] = 0.2
+    param["t"] = float(tables[1](np.log(param["aexp"])))
+    host.set_units(param)
+    return tables, pos, vel, param
+
+
+def _reference(N):
+    tables, pos, vel, param = _setup(N)
+    pos, vel = pos.copy(), vel.copy()
+    acc, phi, add = host.pm(pos, param)
+    state = [pos, vel, acc, phi, add]
+    for _ in range(NSTEPS):
+        param["nsteps"] += 1
+        state = list(host.integrate(*state, tables, param, 1e30))
+    return state, float(param["t"])
+
+
+def _run_rank(N, comm, out, reorder_at=None):
+    from pysco_b200 import slab
+    from slab_oracle_ops import OracleOps
+    tables, pos, vel, param = _setup(N)
+    P, r = comm.size, comm.rank
+    # every rank adopts an arbitrary 1/P of the particles: set_particles must route them to their owners
+    ids = np.arange(N ** 3, dtype=np.int64)
+    mine = slice(r, None, P)
+    s = slab.Slab(N, comm=comm, ops=OracleOps(N, P, r))
+    s.set_particles(torch.from_numpy(pos[mine].copy()), torch.from_numpy(vel[mine].copy()),
+                    torch.from_numpy(ids[mine].copy()))
+    own = (s.position[:, 0].numpy() * np.float32(N)).astype(np.int64) // (N // P)
+    assert (own == r).all()
+    s.pm(param)
+    moved = 0
+    for step in range(NSTEPS):
+        param["nsteps"] += 1
+        if reorder_at is not None and step == reorder_at:
+            s.reorder()
+        s.integrate(tables, param, 1e30)
+        moved += s.migrated_last[0]
+    phi_planes = s.potential.clone()
+    res = s.gather_to_root(N ** 3)
+    tot = torch.tensor([float(moved)])
+    comm.allreduce_sum_(tot)
+    # the potential: gather the owned planes on rank 0
+    counts = [0] * P
+    counts[0] = phi_planes.shape[0]
+    phi = comm.all_to_all_v(phi_planes.reshape(phi_planes.shape[0], -1), counts, comm.exchange_counts(counts))
+    if r == 0:
+        out["state"] = [t.numpy() for t in res] + [phi.numpy().reshape(N, N, N)]
+        out["t"] = float(param["t"])
+        out["moved"] = float(tot[0])
+
+
+def _check(out, ref, ref_t, P):
+    pos, vel, acc, phi = out["state"]
+    rpos, rvel, racc, rphi = ref[0], ref[1], ref[2], ref[3]
+    assert abs(out["t"] - ref_t) <= 1e-6 * abs(ref_t)
+    if P > 1:
+        assert out["moved"] > 0, "the test must exercise migration"
+
+    def rel(a, b):
+        return float(np.max(np.abs(a.astype(np.float64) - b)) / max(np.sqrt(np.mean(b.astype(np.float64) ** 2)), 1e-30))
+    d = np.abs(pos - rpos)
+    d = np.minimum(d, 1 - d)  # periodic distance
+    assert d.max() < 2e-6
+    assert rel(vel, rvel) < 5e-5
+    assert rel(acc, racc) < 2e-4
+    assert rel(phi, rphi) < 2e-4
+
+
+@pytest.mark.parametrize("P", [1, 2, 4])
+def test_slab_threads_vs_oracle(P):
+    from pysco_b200 import slab
+    N = 32
+    ref, ref_t = _reference(N)
+    comms = slab.ThreadComm.world(P) if P > 1 else [slab.SelfComm()]
+    out, errs = {}, []
+
+    def work(c):
+        try:
+            _run_rank(N, c, out, reorder_at=1)
+        except BaseException as e:  # noqa: BLE001
+            errs.append(e)
+            if P > 1:
+                c.w.barrier.abort()
+
+    ts = [threading.Thread(target=work, args=(c,)) for c in comms]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    if errs:
+        raise errs[0]
+    _check(out, ref, ref_t, P)
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _gloo_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    for p in (ROOT, os.path.join(ROOT, "tests"), os.path.join(ROOT, "tests", "golden")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    import torch.distributed as dist
+    from pysco_b200 import distributed, slab
+    distributed.init_from_env("gloo")
+    comm = slab.default_comm()
+    assert isinstance(comm, slab.TorchComm) and comm.size == world
+    # ghost-plane exchange semantics: what I get "from the left" is what my left neighbour sent "to the right"
+    a = torch.full((1, 4), float(10 * rank + 1))
+    b = torch.full((1, 4), float(10 * rank + 2))
+    fl, fr = comm.exchange_planes(a, b)
+    left, right = (rank - 1) % world, (rank + 1) % world
+    assert fl[0, 0].item() == 10 * left + 2 and fr[0, 0].item() == 10 * right + 1
+    local = {}
+    _run_rank(32, comm, local)
+    if rank == 0:
+        out.update(local)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_slab_gloo_world2_vs_oracle():
+    import torch.multiprocessing as mp
+    ref, ref_t = _reference(32)
+    port = _free_port()
+    with mp.Manager() as mgr:
+        out = mgr.dict()
+        mp.spawn(_gloo_worker, args=(2, port, out), nprocs=2, join=True)
+        out = dict(out)
+    _check(out, ref, ref_t, 2)
