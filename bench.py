@@ -47,6 +47,17 @@ ALGO_BYTES = {
     "psc_interp_kick_phi_binned": 76.0,   # gradient (16) + interpolation/kick (60) in one kernel
     "psc_deposit_binned": 16.0,
     "psc_bin_particles": 0.0,      # pure overhead of the order-independent scheme (not in the 176 B budget)
+    # x-slab path (every kernel works on N^3 / P particles or cells)
+    "psc_bin_particles_slab": 0.0,
+    "psc_deposit_binned_slab": 16.0,
+    "psc_linear_operator": 8.0,            # RHS affine map (fused into the deposit on the single-domain path)
+    "psc_slab_fft_r2c_planes": 8.0,        # 2-D R2C of the owned planes
+    "psc_slab_yblocks": 0.0,               # pack / unpack around the all-to-all: overhead
+    "psc_slab_fft_x": 8.0,                 # strided 1-D C2C along x on the transposed spectrum
+    "psc_green_slab": 8.0,
+    "psc_slab_fft_c2r_planes": 8.0,
+    "psc_interp_kick_phi_binned_slab": 76.0,
+    "psc_slab_count": 0.0, "psc_slab_pack_leavers": 0.0, "psc_slab_unpack_rows": 0.0, "psc_slab_move_rows": 0.0,
 }
 
 
@@ -118,6 +129,41 @@ def synthetic_ics_device(N, seed=42):
     pos[pos >= 1.0] = 0.0
     vel = smooth_velocity_field(N, seed + 1)
     return pos.contiguous(), vel
+
+
+def analytic_velocity(pos, seed, rms=1e-3, nmodes=8, kmax=4):
+    """Coherent large-scale flow evaluated at the particle positions: sum of `nmodes` long-wavelength plane waves
+    per component (integer wave vectors, |k_i| <= kmax box modes), rms `rms`.  Rank-local (needs no mesh), so the
+    slab-decomposed runs generate it per slab; same role as smooth_velocity_field."""
+    import torch
+    rng = np.random.default_rng(seed)
+    vel = torch.zeros_like(pos)
+    for d in range(3):
+        for _ in range(nmodes):
+            k = rng.integers(-kmax, kmax + 1, size=3)
+            if not k.any():
+                k[d] = 1
+            ph = float(rng.uniform(0, 2 * np.pi))
+            arg = (pos[:, 0] * float(k[0]) + pos[:, 1] * float(k[1]) + pos[:, 2] * float(k[2])) * (2 * np.pi) + ph
+            vel[:, d] += torch.sin(arg)
+            del arg
+    vel *= rms * np.sqrt(2.0 / nmodes)
+    return vel
+
+
+def slab_ics(N, x0, nxl, seed=42, vel_rms=1e-3):
+    """Synthetic ICs of the planes [x0, x0 + nxl): cell-centre lattice + N(0, 0.3 cell) jitter,
+    analytic coherent velocities, ids = lexicographic lattice index (the reference's particle order)."""
+    import torch
+    g = torch.Generator(device="cuda").manual_seed(seed * 4099 + x0)
+    ax = (torch.arange(N, device="cuda", dtype=torch.float32) + 0.5) / N
+    pos = torch.stack(torch.meshgrid(ax[x0:x0 + nxl], ax, ax, indexing="ij"), dim=-1).reshape(-1, 3).contiguous()
+    pos += torch.randn(pos.shape, generator=g, device="cuda", dtype=torch.float32) * (0.3 / N)
+    pos -= torch.floor(pos)
+    pos[pos >= 1.0] = 0.0
+    ids = torch.arange(x0 * N * N, (x0 + nxl) * N * N, device="cuda", dtype=torch.int64)
+    vel = analytic_velocity(pos, seed + 1, vel_rms)
+    return pos, vel, ids
 
 
 class ClockSampler:
@@ -203,7 +249,7 @@ def run_reference_arm(args):
                          "fft": "numpy-pocketfft (single thread), as the reference without pyfftw"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def workload_config(ncoarse):
@@ -377,10 +423,200 @@ def run_gpu_arm(args):
             "multi_gpu": ("particle-parallel, mesh-replicated: all-reduce(sum) of the %d^3 density grid + all-reduce(max) of "
                           "2 floats per step (NCCL)" % N) if world > 1 else None,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------- B200 arm, x-slab decomposition
+def run_slab_arm(args):
+    """N GPUs, one x-slab of the mesh (and its particles) per rank: pysco_b200/slab.py.  STRONG scaling: the
+    same N^3 problem on every GPU count (BASELINE quotes the metric at 512^3 on 1/2/4/8 GPUs and 2048^3 on 8:
+    --ncoarse 11)."""
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    from pysco_b200 import _lib, distributed, slab, utils
+    distributed.init_from_env("nccl")
+    _lib.load()
+    nc = args.ncoarse
+    N = 2 ** nc
+    tables = make_tables()
+    param = make_param(nc, 1)
+    param["t"] = float(tables[1](np.log(param["aexp"])))
+    utils.set_units(param)
+    comm = slab.default_comm()
+    S = slab.Slab(N, comm=comm)
+    pos, vel, ids = slab_ics(N, S.x0, S.nxl, seed=42)
+    S.set_particles(pos, vel, ids)
+    del pos, vel, ids
+    torch.cuda.empty_cache()
+    S.reorder()
+    S.pm(param)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step():
+        param["nsteps"] += 1
+        S.integrate(tables, param, 1e30)
+        if param["nsteps"] % N_REORDER == 0:
+            S.reorder()
+            return True
+        return False
+
+    for _ in range(args.warmup):
+        step()
+    S.reorder()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    S.reorder()
+    e1.record()
+    torch.cuda.synchronize()
+    t_reorder_ms = e0.elapsed_time(e1)
+
+    sampler = ClockSampler(local_rank)
+    _lib.enable_timing(True)
+    launches0 = _lib.launch_count()
+    barrier()
+    if rank == 0:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    n_reorders = 0
+    migrated = 0
+    for _ in range(args.steps):
+        n_reorders += bool(step())
+        migrated += S.migrated_last[0]
+    ev1.record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    launches = _lib.launch_count() - launches0
+    records = _lib.timing_records()
+    _lib.enable_timing(False)
+    t_ms_total = ev0.elapsed_time(ev1) + (args.steps / N_REORDER - n_reorders) * t_reorder_ms
+    tt = torch.tensor([t_ms_total, float(S.np), float(migrated)], device="cuda", dtype=torch.float64)
+    mx = tt.clone()
+    if world > 1:
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tt, op=dist.ReduceOp.SUM)
+    ms_per_step = mx[0].item() / args.steps
+    assert int(round(tt[1].item())) == N ** 3 or world == 1, "particles lost in migration"
+    value = N ** 3 / (ms_per_step * 1e-3)
+
+    per = {}
+    for name, a, b in records:
+        per.setdefault(name, []).append(a.elapsed_time(b))
+    kern = {k: {"calls_per_step": len(v) / args.steps, "ms_per_call": float(np.mean(v)),
+                "ms_per_step": float(np.sum(v)) / args.steps} for k, v in per.items()}
+    peak, peak_src = measured_peak_gbs()
+    for k, d in kern.items():
+        if ALGO_BYTES.get(k, 0) > 0:
+            d["algo_bytes"] = ALGO_BYTES[k] * N ** 3 / world
+            d["achieved_gbs"] = d["algo_bytes"] / (d["ms_per_call"] * 1e-3) / 1e9
+            d["frac_of_peak"] = d["achieved_gbs"] / peak
+    kernel_ms = sum(d["ms_per_step"] for d in kern.values())
+    step_algo_bytes = STEP_ALGO_BYTES * N ** 3
+    dom = max((k for k in kern if ALGO_BYTES.get(k, 0) > 0), key=lambda k: kern[k]["ms_per_step"])
+    agg = step_algo_bytes / (ms_per_step * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": kern[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s",
+                "frac": kern[dom]["achieved_gbs"] / peak, "traffic": None, "peak_source": peak_src,
+                "algo_bytes_per_launch": kern[dom]["algo_bytes"], "ms_per_launch": kern[dom]["ms_per_call"],
+                "whole_step": {"algo_bytes": step_algo_bytes, "achieved": agg, "aggregate_peak": peak * world,
+                               "frac": agg / (peak * world)}}
+
+    # ---- e2e: every step uploads the rank's x, v, a from pinned host memory and downloads them afterwards
+    e2e = None
+    if not args.no_e2e:
+        n = S.np
+        hp, hv, ha = (torch.empty((int(n * 1.2) + 1024, 3), dtype=torch.float32, pin_memory=True) for _ in range(3))
+        hp[:n].copy_(S.position); hv[:n].copy_(S.velocity); ha[:n].copy_(S.acceleration)
+        e2e_steps = max(1, min(args.e2e_steps, args.steps))
+        moved_bytes = 0
+        for i in range(1 + e2e_steps):
+            if i == 1:
+                barrier()
+                t0 = time.perf_counter()
+                moved_bytes = 0
+            n = S.np
+            S.pos[:n].copy_(hp[:n], non_blocking=True)
+            S.vel[:n].copy_(hv[:n], non_blocking=True)
+            S.acc[:n].copy_(ha[:n], non_blocking=True)
+            param["nsteps"] += 1
+            S.integrate(tables, param, 1e30)
+            n2 = S.np
+            hp[:n2].copy_(S.position, non_blocking=True)
+            hv[:n2].copy_(S.velocity, non_blocking=True)
+            ha[:n2].copy_(S.acceleration, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            moved_bytes += 36 * (n + n2)
+        dt = (time.perf_counter() - t0) / e2e_steps
+        t2 = torch.tensor([dt, moved_bytes / e2e_steps / 2], device="cuda", dtype=torch.float64)
+        t2s = t2.clone()
+        if world > 1:
+            dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+            dist.all_reduce(t2s, op=dist.ReduceOp.SUM)
+        e2e = {"value": N ** 3 / t2[0].item(), "unit": UNIT, "h2d_bytes_per_step": int(t2s[1].item()),
+               "d2h_bytes_per_step": int(t2s[1].item()), "steps": e2e_steps, "ms_per_step": t2[0].item() * 1e3,
+               "api": "pysco_b200.slab.Slab.integrate with the rank's x, v, a uploaded from / downloaded to pinned "
+                      "host memory every step (particle ids stay on the device)"}
+
+    if rank == 0:
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            threads = os.cpu_count() or 1
+            v, ms = cpu_step_rate(args.cpu_ncoarse, 1, 1, threads)
+            Nc = 2 ** args.cpu_ncoarse
+            cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
+                   "sample": f"{Nc}^3 particles / {Nc}^3 mesh full leapfrog step of the same workload shape "
+                             f"(1 warm-up + 1 timed, {ms:.0f} ms); numpy-pocketfft FFT"}
+        cfg = workload_config(nc)
+        cfg["ics"] = ("lattice + N(0, 0.3 cell) displacement, generated per slab, Morton-ordered per slab; velocities: "
+                      "8 long-wavelength plane waves per component, rms 1e-3 (coherent flows)")
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg,
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
+            "clocks": clocks, "kernels": kern,
+            "kernel_ms_per_step": kernel_ms, "comm_and_host_ms_per_step": ms_per_step - kernel_ms,
+            "reorder": {"ms": t_reorder_ms, "in_timed_steps": n_reorders, "amortised_over": N_REORDER},
+            "multi_gpu": {"decomposition": f"x-slabs of {S.nxl} planes per GPU",
+                          "collectives_per_step": "migration counts + records all-to-all, 2 ghost-plane exchanges "
+                                                  "(density add, potential copy), 2 all-to-all transposes of the "
+                                                  "half-spectrum, all-reduce(max) of 2 floats (NCCL)",
+                          "particles_migrated_per_step": tt[2].item() / args.steps},
+        }
+        emit(line)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+_REAL_STDOUT = None
+
+
+def quiet_stdout():
+    """Libraries (NCCL's version banner) write to fd 1; the contract is ONE JSON line on stdout.  Point fd 1 at
+    stderr for the run and keep the real stdout for the final line."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line):
+    out = _REAL_STDOUT if _REAL_STDOUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
 
 
 def main():
@@ -394,9 +630,15 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--decomposition", default="auto", choices=["auto", "slab", "replicated"],
+                    help="multi-GPU layout: x-slabs (default for N > 1) or particle-parallel / mesh-replicated")
     args = ap.parse_args()
+    quiet_stdout()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.impl == "reference":
         run_reference_arm(args)
+    elif args.decomposition == "slab" or (args.decomposition == "auto" and world > 1):
+        run_slab_arm(args)
     else:
         run_gpu_arm(args)
 

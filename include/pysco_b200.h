@@ -131,13 +131,14 @@ int psc_interp_kick_phi_binned_slab(const float *phi_ghost, const float *u_ghost
                                     float *acc, int64_t np, int N, int scheme, float half_dt, float *maxout,
                                     void *stream);
 /* Particle migration after the drift (integration.py:252-258; utils.periodic_wrap utils.py:1120).
- * psc_slab_count: counts[d] (device int64[P], overwritten) = particles whose owner floor(x N) / nxl is rank d.
+ * psc_slab_count: counts[d] (device int64[P], overwritten) = particles whose owner floor(x N) / nxl is rank
+ *   d != me; counts[me] is left 0 (the stayers are np minus the others).
  * psc_slab_pack_leavers: every particle not owned by `me` is packed as a 32-byte record (x y z vx vy vz id)
  *   at sendbuf[8 * (offsets[owner] + slot)], its row stored in holes[same index]; offsets = exclusive prefix
  *   of the send counts by destination (device int64[P]); cursor = device int64[P] scratch.
  * psc_slab_unpack_rows: record t of recvbuf -> row rows[t] of pos / vel / ids.
  * psc_slab_move_rows: row src[t] -> row dst[t] (fills the holes that the arrivals did not fill). */
-int psc_slab_count(const float *pos, int64_t np, int N, int nxl, int P, int64_t *counts, void *stream);
+int psc_slab_count(const float *pos, int64_t np, int N, int nxl, int P, int me, int64_t *counts, void *stream);
 int psc_slab_pack_leavers(const float *pos, const float *vel, const int64_t *ids, int64_t np, int N, int nxl, int P,
                           int me, const int64_t *offsets, int64_t *cursor, float *sendbuf, int64_t *holes,
                           void *stream);

@@ -41,7 +41,7 @@ SIGNATURES = {
     "psc_deposit_binned_slab": [_vp, _sz, _i64, _i, _i, _i, _i, _vp, _vp],
     "psc_interp_kick_phi_binned_slab": [_vp, _vp, _f, _i, _i, _i, _i, _i, _vp, _sz, _vp, _vp, _i64, _i, _i, _f, _vp,
                                         _vp],
-    "psc_slab_count": [_vp, _i64, _i, _i, _i, _vp, _vp],
+    "psc_slab_count": [_vp, _i64, _i, _i, _i, _i, _vp, _vp],
     "psc_slab_pack_leavers": [_vp, _vp, _vp, _i64, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp],
     "psc_slab_unpack_rows": [_vp, _vp, _i64, _vp, _vp, _vp, _vp],
     "psc_slab_move_rows": [_vp, _vp, _i64, _vp, _vp, _vp, _vp],

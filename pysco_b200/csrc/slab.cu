@@ -25,19 +25,22 @@ __device__ __forceinline__ int owner_of(float x, float Nf, int nxl, int P) {
   return min(max(i / nxl, 0), P - 1);
 }
 
-// counts[d] = number of particles owned by rank d (one warp-aggregated atomic per distinct owner per warp)
+// counts[d] = number of particles owned by rank d != me (stayers are the vast majority and are not counted with
+// atomics: the host gets counts[me] as np - sum of the others); one aggregated atomic per distinct owner per warp
 __global__ void __launch_bounds__(256) slab_count_kernel(const float *__restrict__ pos, int64_t np, int N, int nxl,
-                                                         int P, unsigned long long *__restrict__ counts) {
+                                                         int P, int me, unsigned long long *__restrict__ counts) {
   const float Nf = (float)N;
   const int lane = threadIdx.x & 31;
   const int64_t nwarp_iters = (np + 31) >> 5;
   const int64_t wstride = ((int64_t)gridDim.x * blockDim.x) >> 5;
   for (int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < nwarp_iters; w += wstride) {
     const int64_t n = w * 32 + lane;
-    int d = -1 - lane;
+    int d = me;
     if (n < np) d = owner_of(__ldg(&pos[3 * n]), Nf, nxl, P);
-    const unsigned peers = __match_any_sync(0xffffffffu, d);
-    if (d >= 0 && (__ffs(peers) - 1) == lane) atomicAdd(&counts[d], (unsigned long long)__popc(peers));
+    if (__any_sync(0xffffffffu, d != me)) {
+      const unsigned peers = __match_any_sync(0xffffffffu, d);
+      if (d != me && (__ffs(peers) - 1) == lane) atomicAdd(&counts[d], (unsigned long long)__popc(peers));
+    }
   }
 }
 
@@ -142,13 +145,13 @@ using namespace psc;
 
 extern "C" {
 
-int psc_slab_count(const float *pos, int64_t np, int N, int nxl, int P, int64_t *counts, void *stream) {
-  PSC_CHECK_ARG(np >= 0 && N >= 1 && nxl >= 1 && P >= 1 && nxl * P == N, "bad slab geometry");
+int psc_slab_count(const float *pos, int64_t np, int N, int nxl, int P, int me, int64_t *counts, void *stream) {
+  PSC_CHECK_ARG(np >= 0 && N >= 1 && nxl >= 1 && P >= 1 && nxl * P == N && me >= 0 && me < P, "bad slab geometry");
   PSC_CHECK_ARG(counts && (pos || np == 0), "null pointer");
   cudaStream_t st = as_stream(stream);
   PSC_CUDA(cudaMemsetAsync(counts, 0, sizeof(int64_t) * P, st));
   if (np > 0) {
-    slab_count_kernel<<<grid_for(np, 256, 8), 256, 0, st>>>(pos, np, N, nxl, P,
+    slab_count_kernel<<<grid_for(np, 256, 8), 256, 0, st>>>(pos, np, N, nxl, P, me,
                                                             reinterpret_cast<unsigned long long *>(counts));
     count_launch();
     PSC_CHECK_LAUNCH();

@@ -224,8 +224,8 @@ class CudaOps:
 
     def count_owners(self, pos):
         counts = torch.empty((self.P,), dtype=torch.int64, device=self.dev)
-        _lib.check(self.lib.psc_slab_count(_lib.ptr(pos), pos.shape[0], self.N, self.nxl, self.P, _lib.ptr(counts),
-                                           _lib.stream()))
+        _lib.check(self.lib.psc_slab_count(_lib.ptr(pos), pos.shape[0], self.N, self.nxl, self.P, self.rank,
+                                           _lib.ptr(counts), _lib.stream()))
         return counts
 
     def pack_leavers(self, pos, vel, ids, offsets, nout):
