@@ -450,7 +450,8 @@ def run_slab_arm(args):
     param["t"] = float(tables[1](np.log(param["aexp"])))
     utils.set_units(param)
     comm = slab.default_comm()
-    S = slab.Slab(N, comm=comm)
+    # spare rows for arrivals: migration moves O(N^2 / P) particles per step, a few per cent is plenty
+    S = slab.Slab(N, comm=comm, capacity_factor=1.3 if N ** 3 / world < 2e8 else 1.1)
     pos, vel, ids = slab_ics(N, S.x0, S.nxl, seed=42)
     S.set_particles(pos, vel, ids)
     del pos, vel, ids
@@ -534,7 +535,9 @@ def run_slab_arm(args):
 
     # ---- e2e: every step uploads the rank's x, v, a from pinned host memory and downloads them afterwards
     e2e = None
-    if not args.no_e2e:
+    if not args.no_e2e and 36 * S.np * 1.2 > 8e9:
+        e2e = {"skipped": "pinned host staging of %.1f GB per rank exceeds the 8 GB guard" % (36 * S.np * 1.2 / 1e9)}
+    elif not args.no_e2e:
         n = S.np
         hp, hv, ha = (torch.empty((int(n * 1.2) + 1024, 3), dtype=torch.float32, pin_memory=True) for _ in range(3))
         hp[:n].copy_(S.position); hv[:n].copy_(S.velocity); ha[:n].copy_(S.acceleration)
