@@ -256,7 +256,7 @@ def workload_config(ncoarse):
     N = 2 ** ncoarse
     return {"workload": f"Newtonian FFT-PM leapfrog step, {N}^3 particles on {N}^3 mesh, TSC, compensated Green, "
                         f"5-pt gradient, n_reorder={N_REORDER} (BASELINE configs[0] shape at the metric's {N}^3 size)",
-            "ncells_1d": N, "npart": N ** 3, "ics": "lattice + N(0, 0.3 cell) displacement, seed 42, Morton-ordered; velocities: Gaussian field, rms 1e-3, 16-cell correlation length (coherent flows)",
+            "ncells_1d": N, "npart": N ** 3, "ics": "lattice + N(0, 0.3 cell) displacement, seed 42, Morton-ordered; velocities: 8 long-wavelength plane waves per component, rms 1e-3 (coherent flows)",
             "l2_policy": "inputs larger than L2 (particle arrays 3 x %.1f GB, grids %.2f GB vs 126 MB L2)" % (
                 12 * N ** 3 / 1e9, 4 * N ** 3 / 1e9)}
 
@@ -285,7 +285,8 @@ def run_gpu_arm(args):
     # Multi-GPU: particle-parallel / mesh-replicated (pysco_b200/distributed.py).  The SAME N^3 problem is
     # split by particle index over the ranks (strong scaling); per step one all-reduce(sum) of the density
     # grid and one all-reduce(max) of two floats.
-    pos, vel = synthetic_ics_device(N, seed=42)
+    # same ICs as the slab arm (lattice + jitter, analytic coherent velocities) so that the per-N values compare
+    pos, vel, _ = slab_ics(N, 0, N, seed=42)
     pos, vel = utils.reorder_particles(pos, vel)
     if world > 1:
         lo, hi = distributed.local_range(pos.shape[0])

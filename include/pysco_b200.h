@@ -138,6 +138,16 @@ int psc_interp_kick_phi_binned_slab(const float *phi_ghost, const float *u_ghost
  *   of the send counts by destination (device int64[P]); cursor = device int64[P] scratch.
  * psc_slab_unpack_rows: record t of recvbuf -> row rows[t] of pos / vel / ids.
  * psc_slab_move_rows: row src[t] -> row dst[t] (fills the holes that the arrivals did not fill). */
+/* psc_kick_drift_wrap on a slab with the leavers detected in the same pass: counts[0..P) (device int64[P + 1],
+ * overwritten) = leavers per destination, counts[P] = number of leavers; their rows are appended to
+ * leaver_rows[capacity] (unordered).  If counts[P] > capacity the list is incomplete: fall back to
+ * psc_slab_pack_leavers.  psc_slab_pack_rows = psc_slab_pack_leavers over such a list. */
+int psc_kick_drift_wrap_slab(float *pos, float *vel, const float *acc, int64_t np, float half_dt, double dt,
+                             int dt_is_f64, int N, int nxl, int P, int me, int64_t *counts, int64_t *leaver_rows,
+                             int64_t capacity, void *stream);
+int psc_slab_pack_rows(const float *pos, const float *vel, const int64_t *ids, const int64_t *rows, int64_t nrows,
+                       int N, int nxl, int P, int me, const int64_t *offsets, int64_t *cursor, float *sendbuf,
+                       int64_t *holes, void *stream);
 int psc_slab_count(const float *pos, int64_t np, int N, int nxl, int P, int me, int64_t *counts, void *stream);
 int psc_slab_pack_leavers(const float *pos, const float *vel, const int64_t *ids, int64_t np, int N, int nxl, int P,
                           int me, const int64_t *offsets, int64_t *cursor, float *sendbuf, int64_t *holes,

@@ -159,6 +159,55 @@ __global__ void __launch_bounds__(256) kick_drift_wrap_kernel(float *__restrict_
 #undef PSC_KDW
 }
 
+// Same pass on a slab (pysco_b200/slab.py): additionally every particle whose new cell floor(x N) belongs to another
+// rank's slab is counted per destination and its row appended to a list, so that the migration that follows touches
+// only the leavers instead of scanning all positions twice (psc_slab_count + psc_slab_pack_leavers).
+template <bool F64>
+__global__ void __launch_bounds__(256) kick_drift_wrap_slab_kernel(float *__restrict__ pos, float *__restrict__ vel,
+                                                                   const float *__restrict__ acc, int64_t n,
+                                                                   float half_dt, double dt, float Nf, int nxl, int P,
+                                                                   int me, unsigned long long *__restrict__ counts,
+                                                                   int64_t *__restrict__ rows, int64_t capacity) {
+  const float dtf = (float)dt;
+  const float mh = -half_dt;
+  int64_t n4 = n >> 2;
+  float4 *p4 = reinterpret_cast<float4 *>(pos);
+  float4 *v4 = reinterpret_cast<float4 *>(vel);
+  const float4 *a4 = reinterpret_cast<const float4 *>(acc);
+#define PSC_KDW(pc, vc, ac)                                       \
+  vc += mh * ac;                                                  \
+  pc = F64 ? (float)((double)pc + dt * (double)vc) : pc + dtf * vc; \
+  pc = wrap01(pc);
+#define PSC_LEAVER(pc, flat)                                                        \
+  if ((flat) % 3 == 0) {                                                            \
+    const int d = min(max((int)(pc * Nf) / nxl, 0), P - 1);                         \
+    if (d != me) {                                                                  \
+      atomicAdd(&counts[d], 1ull);                                                  \
+      const int64_t slot = (int64_t)atomicAdd(&counts[P], 1ull);                    \
+      if (slot < capacity) rows[slot] = (flat) / 3;                                 \
+    }                                                                               \
+  }
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    float4 p = p4[i], v = v4[i], a = __ldg(&a4[i]);
+    PSC_KDW(p.x, v.x, a.x) PSC_KDW(p.y, v.y, a.y) PSC_KDW(p.z, v.z, a.z) PSC_KDW(p.w, v.w, a.w)
+    p4[i] = p;
+    v4[i] = v;
+    const int64_t f = i << 2;
+    PSC_LEAVER(p.x, f) PSC_LEAVER(p.y, f + 1) PSC_LEAVER(p.z, f + 2) PSC_LEAVER(p.w, f + 3)
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
+    int64_t i = (n4 << 2) + threadIdx.x;
+    float p = pos[i], v = vel[i], a = acc[i];
+    PSC_KDW(p, v, a)
+    pos[i] = p;
+    vel[i] = v;
+    PSC_LEAVER(p, i)
+  }
+#undef PSC_LEAVER
+#undef PSC_KDW
+}
+
 }  // namespace psc
 
 using namespace psc;
@@ -278,6 +327,32 @@ int psc_kick_drift_wrap(float *pos, float *vel, const float *acc, int64_t np, fl
     kick_drift_wrap_kernel<true><<<g, 256, 0, as_stream(stream)>>>(pos, vel, acc, n, half_dt, dt);
   else
     kick_drift_wrap_kernel<false><<<g, 256, 0, as_stream(stream)>>>(pos, vel, acc, n, half_dt, dt);
+  count_launch();
+  PSC_CHECK_LAUNCH();
+  return PSC_OK;
+}
+
+int psc_kick_drift_wrap_slab(float *pos, float *vel, const float *acc, int64_t np, float half_dt, double dt,
+                             int dt_is_f64, int N, int nxl, int P, int me, int64_t *counts, int64_t *leaver_rows,
+                             int64_t capacity, void *stream) {
+  PSC_CHECK_ARG(np >= 0, "np < 0");
+  PSC_CHECK_ARG(N >= 1 && nxl >= 1 && P >= 1 && nxl * P == N && me >= 0 && me < P, "bad slab geometry");
+  PSC_CHECK_ARG(counts && (leaver_rows || capacity == 0) && capacity >= 0, "null pointer");
+  cudaStream_t st = as_stream(stream);
+  PSC_CUDA(cudaMemsetAsync(counts, 0, sizeof(int64_t) * (P + 1), st));
+  if (np == 0) return PSC_OK;
+  PSC_CHECK_ARG(pos && vel && acc, "null pointer");
+  PSC_CHECK_ARG((((uintptr_t)pos | (uintptr_t)vel | (uintptr_t)acc) & 15) == 0,
+                "pointers must be 16-byte aligned");
+  int64_t n = 3 * np;
+  int g = grid_for((n + 3) / 4, 256);
+  unsigned long long *c = reinterpret_cast<unsigned long long *>(counts);
+  if (dt_is_f64)
+    kick_drift_wrap_slab_kernel<true><<<g, 256, 0, st>>>(pos, vel, acc, n, half_dt, dt, (float)N, nxl, P, me, c,
+                                                         leaver_rows, capacity);
+  else
+    kick_drift_wrap_slab_kernel<false><<<g, 256, 0, st>>>(pos, vel, acc, n, half_dt, dt, (float)N, nxl, P, me, c,
+                                                          leaver_rows, capacity);
   count_launch();
   PSC_CHECK_LAUNCH();
   return PSC_OK;

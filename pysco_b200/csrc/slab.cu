@@ -65,6 +65,30 @@ __global__ void __launch_bounds__(256) slab_pack_kernel(const float *__restrict_
   }
 }
 
+// same, over a list of candidate rows (written by psc_kick_drift_wrap_slab) instead of all particles
+__global__ void __launch_bounds__(256) slab_pack_rows_kernel(const float *__restrict__ pos, const float *__restrict__ vel,
+                                                             const int64_t *__restrict__ ids,
+                                                             const int64_t *__restrict__ rows, int64_t nrows, int N,
+                                                             int nxl, int P, int me,
+                                                             const int64_t *__restrict__ offsets,
+                                                             unsigned long long *__restrict__ cursor,
+                                                             float *__restrict__ sendbuf, int64_t *__restrict__ holes) {
+  const float Nf = (float)N;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < nrows; t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t n = rows[t];
+    const float x = pos[3 * n];
+    const int d = owner_of(x, Nf, nxl, P);
+    if (d == me) continue;
+    const int64_t slot = offsets[d] + (int64_t)atomicAdd(&cursor[d], 1ull);
+    float4 *rec = reinterpret_cast<float4 *>(sendbuf + REC * slot);
+    const int64_t id = ids[n];
+    rec[0] = make_float4(x, pos[3 * n + 1], pos[3 * n + 2], vel[3 * n]);
+    rec[1] = make_float4(vel[3 * n + 1], vel[3 * n + 2], __int_as_float((int)(id & 0xffffffffll)),
+                         __int_as_float((int)(id >> 32)));
+    holes[slot] = n;
+  }
+}
+
 __global__ void __launch_bounds__(256) slab_unpack_kernel(const float *__restrict__ recvbuf,
                                                           const int64_t *__restrict__ rows, int64_t n,
                                                           float *__restrict__ pos, float *__restrict__ vel,
@@ -171,6 +195,24 @@ int psc_slab_pack_leavers(const float *pos, const float *vel, const int64_t *ids
     slab_pack_kernel<<<grid_for(np, 256, 8), 256, 0, st>>>(pos, vel, ids, np, N, nxl, P, me, offsets,
                                                            reinterpret_cast<unsigned long long *>(cursor), sendbuf,
                                                            holes);
+    count_launch();
+    PSC_CHECK_LAUNCH();
+  }
+  return PSC_OK;
+}
+
+int psc_slab_pack_rows(const float *pos, const float *vel, const int64_t *ids, const int64_t *rows, int64_t nrows,
+                       int N, int nxl, int P, int me, const int64_t *offsets, int64_t *cursor, float *sendbuf,
+                       int64_t *holes, void *stream) {
+  PSC_CHECK_ARG(nrows >= 0 && N >= 1 && nxl >= 1 && P >= 1 && nxl * P == N && me >= 0 && me < P, "bad slab geometry");
+  PSC_CHECK_ARG(offsets && cursor && (nrows == 0 || (pos && vel && ids && rows)), "null pointer");
+  PSC_CHECK_ARG(((uintptr_t)sendbuf & 15) == 0, "sendbuf must be 16-byte aligned");
+  cudaStream_t st = as_stream(stream);
+  PSC_CUDA(cudaMemsetAsync(cursor, 0, sizeof(int64_t) * P, st));
+  if (nrows > 0) {
+    slab_pack_rows_kernel<<<grid_for(nrows, 256, 8), 256, 0, st>>>(pos, vel, ids, rows, nrows, N, nxl, P, me, offsets,
+                                                                   reinterpret_cast<unsigned long long *>(cursor),
+                                                                   sendbuf, holes);
     count_launch();
     PSC_CHECK_LAUNCH();
   }

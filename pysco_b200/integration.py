@@ -72,8 +72,102 @@ def _from_device(c, position, velocity, pos, vel, acc, pot, add):
     return pos, vel, acc, pot, add
 
 
+_copy_streams = {}
+
+
+def _streams():
+    d = torch.cuda.current_device()
+    if d not in _copy_streams:
+        _copy_streams[d] = (torch.cuda.Stream(), torch.cuda.Stream())
+    return _copy_streams[d]
+
+
+def _is_pinned_host(*ts):
+    return all(isinstance(t, torch.Tensor) and not t.is_cuda and t.is_pinned() and t.dtype == torch.float32
+               and t.is_contiguous() for t in ts)
+
+
+def _leapfrog_pinned(position, velocity, acceleration, potential, additional_field, dt, tables, param, nchunk=8):
+    """leapfrog() for PINNED host tensors: the PCIe transfers are pipelined with the kernels instead of being
+    serialised around them.  The particle arrays are uploaded in chunks on a copy stream; each chunk is
+    kicked / drifted / wrapped as soon as it has landed and its final positions start flowing back on a second
+    copy stream while later chunks are still arriving (full-duplex PCIe).  After the solve, velocity (in place),
+    acceleration and potential are downloaded on the copy stream.  Same arithmetic as leapfrog()."""
+    lib = _lib.load()
+    dev = _lib.device()
+    n = position.shape[0]
+    cur = torch.cuda.current_stream()
+    s_in, s_out = _streams()
+    pos, vel, acc = (torch.empty((n, 3), dtype=torch.float32, device=dev) for _ in range(3))
+    for t in (pos, vel, acc):
+        t.record_stream(s_in)
+        t.record_stream(s_out)
+    s_in.wait_stream(cur)
+    s_out.wait_stream(cur)
+    half_dt = np.float32(0.5 * dt)
+    dt_is_f64 = 0 if isinstance(dt, np.float32) else 1
+    solver_name = param["linear_newton_solver"].casefold()
+    pot = potential
+    if len(potential) and solver_name == "multigrid":      # the previous potential is only a multigrid first guess
+        pot = torch.empty(potential.shape, dtype=torch.float32, device=dev)
+        pot.record_stream(s_in)
+        with torch.cuda.stream(s_in):
+            pot.copy_(potential, non_blocking=True)
+    elif len(potential):
+        pot = torch.empty(0, dtype=torch.float32, device=dev)
+    add = additional_field
+    if len(additional_field):
+        add = additional_field.to(dev, non_blocking=True)
+    # rows per chunk: a multiple of 4 keeps every chunk 16-byte aligned
+    step = max(4, ((n + nchunk - 1) // nchunk + 3) // 4 * 4)
+    for a in range(0, n, step):
+        b = min(n, a + step)
+        with torch.cuda.stream(s_in):
+            pos[a:b].copy_(position[a:b], non_blocking=True)
+            vel[a:b].copy_(velocity[a:b], non_blocking=True)
+            acc[a:b].copy_(acceleration[a:b], non_blocking=True)
+            landed = torch.cuda.Event()
+            landed.record(s_in)
+        cur.wait_event(landed)
+        _lib.check(lib.psc_kick_drift_wrap(_lib.ptr(pos[a:b]), _lib.ptr(vel[a:b]), _lib.ptr(acc[a:b]), b - a,
+                                           float(half_dt), float(dt), dt_is_f64, _lib.stream()))
+        drifted = torch.cuda.Event()
+        drifted.record(cur)
+        s_out.wait_event(drifted)
+        with torch.cuda.stream(s_out):
+            position[a:b].copy_(pos[a:b], non_blocking=True)
+    _advance_clock(dt, tables, param)
+    cur.wait_stream(s_in)
+    del acc
+    acc, pot, add, maxima = solver._pm_device(pos, param, pot, add, tables, kick=(vel, half_dt))
+    distributed.allreduce_max_(maxima)
+    acc_h = torch.empty((n, 3), dtype=torch.float32, pin_memory=True)
+    pot_h = torch.empty(pot.shape, dtype=torch.float32, pin_memory=True) if len(pot) else pot
+    add_h = add
+    s_out.wait_stream(cur)
+    for t in (acc, pot, add):
+        if isinstance(t, torch.Tensor) and t.is_cuda:
+            t.record_stream(s_out)
+    with torch.cuda.stream(s_out):
+        velocity.copy_(vel, non_blocking=True)
+        acc_h.copy_(acc, non_blocking=True)
+        if len(pot):
+            pot_h.copy_(pot, non_blocking=True)
+        if len(add):
+            add_h = torch.empty(add.shape, dtype=torch.float32, pin_memory=True)
+            add_h.copy_(add, non_blocking=True)
+    mx = maxima.cpu().numpy()
+    s_out.synchronize()
+    # the cached maxima belong to exactly these host tensors
+    _maxima_cache.update(acc=weakref.ref(acc_h), vel=weakref.ref(velocity), max=mx)
+    return position, velocity, acc_h, pot_h, add_h
+
+
 def leapfrog(position, velocity, acceleration, potential, additional_field, dt, tables, param):
     """integration.py:192-264 (kick-drift-kick)"""
+    if _is_pinned_host(position, velocity, acceleration) and (not len(potential) or _is_pinned_host(potential)) \
+            and (not len(additional_field) or _is_pinned_host(additional_field)) and position.shape[0] >= 4096:
+        return _leapfrog_pinned(position, velocity, acceleration, potential, additional_field, dt, tables, param)
     c = _lib.Ctx()
     pos, vel, acc, pot, add = _to_device(c, position, velocity, acceleration, potential, additional_field)
     half_dt = np.float32(0.5 * dt)

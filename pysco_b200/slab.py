@@ -216,11 +216,35 @@ class CudaOps:
         self._plan = None
         self._work = None
         self._scratch = None
+        self._leavers = None
 
     # -- particles
     def kick_drift_wrap(self, pos, vel, acc, half_dt, dt, dt_is_f64):
         _lib.check(self.lib.psc_kick_drift_wrap(_lib.ptr(pos), _lib.ptr(vel), _lib.ptr(acc), pos.shape[0],
                                                 float(half_dt), float(dt), int(dt_is_f64), _lib.stream()))
+
+    def kick_drift_wrap_detect(self, pos, vel, acc, half_dt, dt, dt_is_f64):
+        """kick + drift + wrap with the leavers found in the same pass: returns (counts[P + 1], rows) device
+        tensors; counts[P] = number of leavers, rows[:min(counts[P], len(rows))] their rows."""
+        n = pos.shape[0]
+        cap = max(4096, n // 8)
+        if self._leavers is None or self._leavers.numel() < cap:
+            self._leavers = torch.empty((cap,), dtype=torch.int64, device=self.dev)
+        counts = torch.empty((self.P + 1,), dtype=torch.int64, device=self.dev)
+        _lib.check(self.lib.psc_kick_drift_wrap_slab(
+            _lib.ptr(pos), _lib.ptr(vel), _lib.ptr(acc), n, float(half_dt), float(dt), int(dt_is_f64), self.N,
+            self.nxl, self.P, self.rank, _lib.ptr(counts), _lib.ptr(self._leavers), self._leavers.numel(),
+            _lib.stream()))
+        return counts, self._leavers
+
+    def pack_rows(self, pos, vel, ids, rows, offsets, nout):
+        sendbuf = torch.empty((nout, REC), dtype=torch.float32, device=self.dev)
+        holes = torch.empty((nout,), dtype=torch.int64, device=self.dev)
+        cursor = torch.empty((self.P,), dtype=torch.int64, device=self.dev)
+        _lib.check(self.lib.psc_slab_pack_rows(_lib.ptr(pos), _lib.ptr(vel), _lib.ptr(ids), _lib.ptr(rows),
+                                               rows.shape[0], self.N, self.nxl, self.P, self.rank, _lib.ptr(offsets),
+                                               _lib.ptr(cursor), _lib.ptr(sendbuf), _lib.ptr(holes), _lib.stream()))
+        return sendbuf, holes
 
     def count_owners(self, pos):
         counts = torch.empty((self.P,), dtype=torch.int64, device=self.dev)
@@ -411,11 +435,19 @@ class Slab:
         self.migrate()
 
     # -- migration
-    def migrate(self):
-        """Send every particle that left the slab to its owner and take in the arrivals (O(migrants) row moves)."""
+    def migrate(self, detected=None):
+        """Send every particle that left the slab to its owner and take in the arrivals (O(migrants) row moves).
+        detected = (counts[P + 1], rows) from ops.kick_drift_wrap_detect skips the two scans over all positions."""
         ops, comm, me = self.ops, self.comm, self.rank
         n = self.np
-        counts = ops.count_owners(self.pos[:n]).cpu().tolist()
+        rows = None
+        if detected is not None:
+            counts = detected[0].cpu().tolist()
+            if counts[self.P] <= detected[1].numel():
+                rows = detected[1][:counts[self.P]]
+            counts = counts[:self.P]
+        else:
+            counts = ops.count_owners(self.pos[:n]).cpu().tolist()
         send_counts = [int(c) for c in counts]
         send_counts[me] = 0
         nout = sum(send_counts)
@@ -427,7 +459,10 @@ class Slab:
         dev = self._device()
         if nout:
             offsets = torch.tensor(np.concatenate([[0], np.cumsum(send_counts)[:-1]]).astype(np.int64), device=dev)
-            sendbuf, holes = ops.pack_leavers(self.pos[:n], self.vel[:n], self.ids[:n], offsets, nout)
+            if rows is not None:
+                sendbuf, holes = ops.pack_rows(self.pos[:n], self.vel[:n], self.ids[:n], rows, offsets, nout)
+            else:
+                sendbuf, holes = ops.pack_leavers(self.pos[:n], self.vel[:n], self.ids[:n], offsets, nout)
         else:
             sendbuf = torch.empty((0, REC), dtype=torch.float32, device=dev)
             holes = torch.empty((0,), dtype=torch.int64, device=dev)
@@ -542,13 +577,18 @@ class Slab:
         n = self.np
         half_dt = np.float32(0.5 * dt)
         dt_is_f64 = 0 if isinstance(dt, np.float32) else 1
-        self.ops.kick_drift_wrap(self.pos[:n], self.vel[:n], self.acc[:n], half_dt, dt, dt_is_f64)
+        detected = None
+        if self.P > 1:
+            detected = self.ops.kick_drift_wrap_detect(self.pos[:n], self.vel[:n], self.acc[:n], half_dt, dt,
+                                                       dt_is_f64)
+        else:
+            self.ops.kick_drift_wrap(self.pos[:n], self.vel[:n], self.acc[:n], half_dt, dt, dt_is_f64)
         param["t"] += dt
         param["aexp_old"] = param["aexp"]
         param["aexp"] = np.exp(tables[0](param["t"]))
         logging.info(f"{param['t']=} {param['aexp']=}")
         utils.set_units(param)
-        self.migrate()
+        self.migrate(detected)
         self.pm(param, kick=half_dt)
 
     def integrate(self, tables, param, t_snap_next=np.float32(0)):

@@ -34,6 +34,29 @@ class OracleOps:
         oracle.utils.add_vector_scalar_inplace(p, v, dt if dt_is_f64 else np.float32(dt))
         oracle.utils.periodic_wrap(p)
 
+    def kick_drift_wrap_detect(self, pos, vel, acc, half_dt, dt, dt_is_f64):
+        self.kick_drift_wrap(pos, vel, acc, half_dt, dt, dt_is_f64)
+        own = self._owner(pos)
+        rows = np.nonzero(own != self.rank)[0].astype(np.int64)
+        counts = np.bincount(own[rows], minlength=self.P).astype(np.int64)
+        # a deliberately small list every third call exercises the overflow fallback (full scan)
+        self._calls = getattr(self, "_calls", 0) + 1
+        cap = max(1, rows.size // 2) if self._calls % 3 == 0 else rows.size + 7
+        lst = np.full(cap, -1, dtype=np.int64)
+        lst[:min(cap, rows.size)] = rows[::-1][:cap]
+        return torch.from_numpy(np.concatenate([counts, [rows.size]])), torch.from_numpy(lst)
+
+    def pack_rows(self, pos, vel, ids, rows, offsets, nout):
+        r = np.sort(_np(rows))
+        own = self._owner(pos)[r]
+        r = r[np.argsort(own, kind="stable")]
+        assert r.size == nout
+        rec = np.empty((nout, REC), dtype=np.float32)
+        rec[:, 0:3] = _np(pos)[r]
+        rec[:, 3:6] = _np(vel)[r]
+        rec[:, 6:8] = _np(ids)[r].astype(np.int64).view(np.float32).reshape(-1, 2)
+        return torch.from_numpy(rec), torch.from_numpy(r.astype(np.int64))
+
     def _owner(self, pos):
         i = (_np(pos)[:, 0] * np.float32(self.N)).astype(np.int64)
         return np.clip(i // self.nxl, 0, self.P - 1)
