@@ -197,19 +197,24 @@ __global__ void __launch_bounds__(BD_WARPS * 32) deposit_binned_kernel(const flo
   __syncthreads();
   // sum the per-warp tiles; cells no other bin can reach (2 <= t <= 7 in every dimension) are stored,
   // the shell is added to L2
-  const size_t N2 = (size_t)N * N;
-  for (int t = threadIdx.x; t < BT * BT * BT; t += BD_WARPS * 32) {
-    const int g = t % BT, r = t / BT;
-    const int e = r % BT, a = r / BT;
-    const int s = a * BD_P0 + e * BD_P1 + g;
-    float v = tiles[0][s];
+  // one half-warp per (i, j) row of the tile: wraps and the 64-bit row address once per row, not per cell (the
+  // cell-wise loop was 36% of the kernel's instructions in ncu)
+  const int hl = threadIdx.x & 15, hw = threadIdx.x >> 4;
+  if (hl < BT) {
+    const int gk = wrap(ok + hl, N);
+    const bool kin = hl >= 2 && hl <= BT - 3;
+    for (int row = hw; row < BT * BT; row += BD_WARPS * 2) {
+      const int a = row / BT, e = row - a * BT;
+      const int s = a * BD_P0 + e * BD_P1 + hl;
+      float v = tiles[0][s];
 #pragma unroll
-    for (int w = 1; w < BD_WARPS; w++) v += tiles[w][s];
-    const int gi = wrap(pl0 + a, nxa), gj = wrap(oj + e, N), gk = wrap(ok + g, N);
-    float *dst = rho + (size_t)gi * N2 + (size_t)gj * N + gk;
-    const bool mine = a >= 2 && a <= BT - 3 && e >= 2 && e <= BT - 3 && g >= 2 && g <= BT - 3;
-    if (mine) *dst = v;
-    else if (v != 0.0f) atomicAdd(dst, v);
+      for (int w = 1; w < BD_WARPS; w++) v += tiles[w][s];
+      const int gi = wrap(pl0 + a, nxa), gj = wrap(oj + e, N);
+      float *dst = rho + ((size_t)gi * N + gj) * N + gk;
+      const bool mine = kin && a >= 2 && a <= BT - 3 && e >= 2 && e <= BT - 3;
+      if (mine) *dst = v;
+      else if (v != 0.0f) atomicAdd(dst, v);
+    }
   }
 }
 
@@ -291,49 +296,77 @@ __global__ void __launch_bounds__(BI_THREADS) interp_kick4_binned_kernel(
 // the gradient kernel and the force grid (16 B/cell written + re-read) from the step.
 template <int ORDER> struct Reach { static constexpr int H = ORDER == 7 ? 3 : ORDER == 5 ? 2 : 1; };
 
+constexpr int BP_THREADS = 256;  // gradient + interpolation kernel
+
 template <int SCHEME, int ORDER>
-__global__ void __launch_bounds__(BI_THREADS) interp_kick_phi_binned_kernel(
+__global__ void __launch_bounds__(BP_THREADS) interp_kick_phi_binned_kernel(
     const float *__restrict__ phi, const float *__restrict__ u, float f, int fr_n,
     const float *__restrict__ bpos, const int *__restrict__ bsrc, const int *__restrict__ offsets,
     float *__restrict__ vel, float *__restrict__ accel, int N, int NB, int x0, int xoff, int nxa, float half_dt,
     float *__restrict__ maxout) {
   constexpr int H = Reach<ORDER>::H;
   constexpr int PT = BT + 2 * H;  // potential tile edge
-  __shared__ float ptile[PT * PT * PT];
+  constexpr int PK = 16;          // k pitch of the potential tile: the aligned 16-float window
+  __shared__ __align__(16) float ptile[PT * PT * PK];
   __shared__ float4 tile[BT * BT * BT];
-  __shared__ float s_max[BI_THREADS / 32][2];
+  __shared__ float s_max[BP_THREADS / 32][2];
   const int b = blockIdx.x;
   const int beg = offsets[b], end = offsets[b + 1];
   if (beg == end) return;
   const int bk = b % NB, bj = (b / NB) % NB, bi = b / (NB * NB);
   const int oi = x0 + bi * BB - 1, oj = bj * BB - 1, ok = bk * BB - 1;
   const int pl0 = bi * BB - 1 + xoff;
-  const size_t N2 = (size_t)N * N;
-  for (int t = threadIdx.x; t < PT * PT * PT; t += BI_THREADS) {
-    const int g = t % PT, r = t / PT;
-    const int e = r % PT, a = r / PT;
-    int gi = pl0 - H + a, gj = oj - H + e, gk = ok - H + g;
-    gi += gi < 0 ? nxa : 0; gi -= gi >= nxa ? nxa : 0;
-    gj += gj < 0 ? N : 0; gj -= gj >= N ? N : 0;
-    gk += gk < 0 ? N : 0; gk -= gk >= N ? N : 0;
-    const size_t c = (size_t)gi * N2 + (size_t)gj * N + gk;
-    float v = __ldg(&phi[c]);
-    if (fr_n) {
-      const float w = __ldg(&u[c]);
-      v += f * (fr_n == 1 ? w * w : w * w * w);
+  {
+    // Every (i, j) row of the potential tile is fetched as the aligned 16-float window [8 bk - 4, 8 bk + 12) that
+    // contains the PT cells the stencils need: four LDG.128 per row (784 per tile instead of 2744 scalar loads,
+    // whose index arithmetic was 59% of this kernel's instructions in ncu), all issued before the first store.  A
+    // window group never straddles the periodic boundary because N % 4 == 0.
+    const float4 *phi4 = reinterpret_cast<const float4 *>(phi);
+    const float4 *u4 = reinterpret_cast<const float4 *>(u);
+    float4 *pt4 = reinterpret_cast<float4 *>(ptile);
+    const int n4 = N >> 2;
+    constexpr int NITEM = PT * PT * 4;
+    constexpr int NIT = (NITEM + BP_THREADS - 1) / BP_THREADS;
+    float4 v[NIT];
+#pragma unroll
+    for (int it = 0; it < NIT; it++) {
+      const int item = threadIdx.x + it * BP_THREADS;
+      const int row = item >> 2, q = item & 3;
+      const int a = row / PT, e = row - a * PT;
+      int gi = pl0 - H + a, gj = oj - H + e, g4 = 2 * bk - 1 + q;
+      gi += gi < 0 ? nxa : 0; gi -= gi >= nxa ? nxa : 0;
+      gj += gj < 0 ? N : 0; gj -= gj >= N ? N : 0;
+      g4 += g4 < 0 ? n4 : 0; g4 -= g4 >= n4 ? n4 : 0;
+      const size_t c = ((size_t)gi * N + gj) * n4 + g4;
+      v[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (item < NITEM) {
+        v[it] = __ldg(&phi4[c]);
+        if (fr_n) {
+          const float4 w = __ldg(&u4[c]);
+          v[it].x += f * (fr_n == 1 ? w.x * w.x : w.x * w.x * w.x);
+          v[it].y += f * (fr_n == 1 ? w.y * w.y : w.y * w.y * w.y);
+          v[it].z += f * (fr_n == 1 ? w.z * w.z : w.z * w.z * w.z);
+          v[it].w += f * (fr_n == 1 ? w.w * w.w : w.w * w.w * w.w);
+        }
+      }
     }
-    ptile[t] = v;
+#pragma unroll
+    for (int it = 0; it < NIT; it++) {
+      const int item = threadIdx.x + it * BP_THREADS;
+      if (item < NITEM) pt4[item] = v[it];
+    }
   }
   __syncthreads();
   const float pref = ORDER == 2 ? (float)N : ORDER == 3 ? (float)(0.5 * N) : ORDER == 5 ? (float)(N / 12.0) : (float)(N / 60.0);
-  for (int t = threadIdx.x; t < BT * BT * BT; t += BI_THREADS) {
+  for (int t = threadIdx.x; t < BT * BT * BT; t += BP_THREADS) {
     const int g = t % BT, r = t / BT;
     const int e = r % BT, a = r / BT;
-    const float *c = ptile + ((a + H) * PT + (e + H)) * PT + (g + H);
+    // tile cell g is global k = 8 bk - 1 + g = window position g + 3
+    const float *c = ptile + ((a + H) * PT + (e + H)) * PK + (g + 3);
     float gr[3];
 #pragma unroll
     for (int d = 0; d < 3; d++) {
-      const int s = d == 0 ? PT * PT : d == 1 ? PT : 1;
+      const int s = d == 0 ? PT * PK : d == 1 ? PK : 1;
       if (ORDER == 2) gr[d] = pref * (-c[0] + c[s]);
       else if (ORDER == 3) gr[d] = pref * (-c[-s] + c[s]);
       else if (ORDER == 5) gr[d] = pref * (8.0f * (-c[-s] + c[s]) + c[-2 * s] - c[2 * s]);
@@ -345,7 +378,7 @@ __global__ void __launch_bounds__(BI_THREADS) interp_kick_phi_binned_kernel(
   const float Nf = (float)N;
   const float mh = -half_dt;
   float ma = 0.0f, mv = 0.0f;
-  for (int n = beg + threadIdx.x; n < end; n += BI_THREADS) {
+  for (int n = beg + threadIdx.x; n < end; n += BP_THREADS) {
     const float px = __ldg(&bpos[3 * (size_t)n]), py = __ldg(&bpos[3 * (size_t)n + 1]), pz = __ldg(&bpos[3 * (size_t)n + 2]);
     const int row = __ldg(&bsrc[n]);
     int i, j, k;
@@ -383,7 +416,7 @@ __global__ void __launch_bounds__(BI_THREADS) interp_kick_phi_binned_kernel(
   __syncthreads();
   if (threadIdx.x == 0) {
 #pragma unroll
-    for (int w = 1; w < BI_THREADS / 32; w++) { ma = fmaxf(ma, s_max[w][0]); mv = fmaxf(mv, s_max[w][1]); }
+    for (int w = 1; w < BP_THREADS / 32; w++) { ma = fmaxf(ma, s_max[w][0]); mv = fmaxf(mv, s_max[w][1]); }
     atomic_max_nonneg(&maxout[0], ma);
     atomic_max_nonneg(&maxout[1], mv);
   }
@@ -523,6 +556,7 @@ static int interp_kick_phi_impl(const float *phi, const float *u, float f, int f
                                 int ghost, const void *scratch, size_t scratch_bytes, float *vel, float *acc,
                                 int64_t np, int N, int scheme, float half_dt, float *maxout, void *stream) {
   if (np == 0) return PSC_OK;
+  PSC_CHECK_ARG((((uintptr_t)phi | (uintptr_t)u) & 15) == 0, "phi and u must be 16-byte aligned");
   BinLayout L;
   if (!bin_layout(const_cast<void *>(scratch), scratch_bytes, np, N, x0, nxl, L)) {
     set_error("psc_interp_kick_phi_binned: scratch too small");
@@ -532,7 +566,7 @@ static int interp_kick_phi_impl(const float *phi, const float *u, float f, int f
   const int grid = (int)L.nbins;
   const int nxa = nxl + 2 * ghost;
 #define PSC_IKP(S, O)                                                                                            \
-  interp_kick_phi_binned_kernel<S, O><<<grid, BI_THREADS, 0, st>>>(phi, u, f, fr_n, L.pos, L.src, L.offsets, vel, acc, \
+  interp_kick_phi_binned_kernel<S, O><<<grid, BP_THREADS, 0, st>>>(phi, u, f, fr_n, L.pos, L.src, L.offsets, vel, acc, \
                                                                    N, L.NB, x0, ghost, nxa, half_dt, maxout)
 #define PSC_IKP_O(S)               \
   if (order == 2) PSC_IKP(S, 2);    \

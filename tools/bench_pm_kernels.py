@@ -1,0 +1,49 @@
+#!/usr/bin/env python
+"""Timing of the binned particle<->mesh kernels alone (bin, deposit, gradient+interpolation+kick) on one GPU, for a
+freshly Morton-sorted order and for an order that has drifted by one cell rms.
+usage: python tools/bench_pm_kernels.py [ncoarse=9]"""
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import bench  # noqa: E402
+from pysco_b200 import _lib, mesh, utils  # noqa: E402
+
+nc = int(sys.argv[1]) if len(sys.argv) > 1 else 9
+N = 2 ** nc
+_lib.load()
+
+
+def timeit(fn, reps=5):
+    fn()
+    torch.cuda.synchronize()
+    best = 1e9
+    for _ in range(reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1))
+    return best
+
+
+pos, vel, _ = bench.slab_ics(N, 0, N)
+pos_mor, vel = utils.reorder_particles(pos, vel)
+g = torch.Generator(device="cuda").manual_seed(1)
+p = pos_mor + torch.randn(pos_mor.shape, generator=g, device="cuda") * (1.0 / N)
+p = p - torch.floor(p)
+p[p >= 1.0] = 0.0
+cases = {"morton": pos_mor, "morton+drift1.0": p.contiguous()}
+phi = torch.randn((N, N, N), device="cuda")
+for name, p in cases.items():
+    t_bin = timeit(lambda: mesh.bin_particles(p, N))
+    bn = mesh.bin_particles(p, N)
+    t_dep = timeit(lambda: mesh.deposit_rhs(p, N, 2, 1.0, 1.0, 0.0, bn))
+    v2 = vel.clone()
+    t_int = timeit(lambda: mesh.interp_kick_phi(phi, None, 0.0, 0, 5, p, v2, 2, 0.0, bn))
+    print(f"N={N} {name:18s} bin {t_bin:6.3f} ms | deposit {t_dep:6.3f} ms | gradient+interp+kick {t_int:6.3f} ms",
+          flush=True)
