@@ -26,8 +26,8 @@ namespace psc {
 constexpr int BB = 8;           // bin edge in cells
 constexpr int BT = BB + 2;      // tile edge (one halo cell per side)
 constexpr int BD_WARPS = 4;     // warps per CTA in the binned deposit
-constexpr int BD_P1 = 11;       // row pitch of the per-warp tile (skews the banks), plane pitch BT * BD_P1
-constexpr int BD_P0 = BT * BD_P1;
+constexpr int BD_P1 = 12;       // row pitch of the per-warp tile; 12 / 144 spreads a Morton chunk (2x4x4 cells) over the banks
+constexpr int BD_P0 = 144;
 constexpr int BD_TILE = BT * BD_P0;  // 1100 floats per warp
 
 struct BinLayout {
@@ -298,7 +298,9 @@ template <int ORDER> struct Reach { static constexpr int H = ORDER == 7 ? 3 : OR
 
 constexpr int BP_THREADS = 256;  // gradient + interpolation kernel
 
-template <int SCHEME, int ORDER>
+// TP1 / TP0: row / plane pitch of the float4 force tile.  Measured at 512^3 (Morton order): 10/100 4.41 ms, 11/110 4.62,
+// 12/120 4.59, 12/144 4.75, 14/140 4.70, 11/112 5.19, 10/104 5.39 -- the dense tile is the best of those.
+template <int SCHEME, int ORDER, int TP1 = BT, int TP0 = BT * BT>
 __global__ void __launch_bounds__(BP_THREADS) interp_kick_phi_binned_kernel(
     const float *__restrict__ phi, const float *__restrict__ u, float f, int fr_n,
     const float *__restrict__ bpos, const int *__restrict__ bsrc, const int *__restrict__ offsets,
@@ -308,7 +310,7 @@ __global__ void __launch_bounds__(BP_THREADS) interp_kick_phi_binned_kernel(
   constexpr int PT = BT + 2 * H;  // potential tile edge
   constexpr int PK = 16;          // k pitch of the potential tile: the aligned 16-float window
   __shared__ __align__(16) float ptile[PT * PT * PK];
-  __shared__ float4 tile[BT * BT * BT];
+  __shared__ float4 tile[BT * TP0];
   __shared__ float s_max[BP_THREADS / 32][2];
   const int b = blockIdx.x;
   const int beg = offsets[b], end = offsets[b + 1];
@@ -372,7 +374,7 @@ __global__ void __launch_bounds__(BP_THREADS) interp_kick_phi_binned_kernel(
       else if (ORDER == 5) gr[d] = pref * (8.0f * (-c[-s] + c[s]) + c[-2 * s] - c[2 * s]);
       else gr[d] = pref * (45.0f * (-c[-s] + c[s]) + 9.0f * (c[-2 * s] - c[2 * s]) - c[-3 * s] + c[3 * s]);
     }
-    tile[t] = make_float4(gr[0], gr[1], gr[2], 0.0f);
+    tile[a * TP0 + e * TP1 + g] = make_float4(gr[0], gr[1], gr[2], 0.0f);
   }
   __syncthreads();
   const float Nf = (float)N;
@@ -386,7 +388,7 @@ __global__ void __launch_bounds__(BP_THREADS) interp_kick_phi_binned_kernel(
     axis_weights<SCHEME>(px * Nf, N, i, wx[0], wx[1], wx[2]);
     axis_weights<SCHEME>(py * Nf, N, j, wy[0], wy[1], wy[2]);
     axis_weights<SCHEME>(pz * Nf, N, k, wz[0], wz[1], wz[2]);
-    const float4 *c0 = tile + ((min(max(i - oi, 1), BB) - 1) * BT + (j - oj - 1)) * BT + (k - ok - 1);
+    const float4 *c0 = tile + (min(max(i - oi, 1), BB) - 1) * TP0 + (j - oj - 1) * TP1 + (k - ok - 1);
     float ax = 0.0f, ay = 0.0f, az = 0.0f;
 #pragma unroll
     for (int a = 0; a < 3; a++)
@@ -396,7 +398,7 @@ __global__ void __launch_bounds__(BP_THREADS) interp_kick_phi_binned_kernel(
 #pragma unroll
         for (int g = 0; g < 3; g++) {
           const float w = wxy * wz[g];
-          const float4 ff = c0[(a * BT + e) * BT + g];
+          const float4 ff = c0[a * TP0 + e * TP1 + g];
           ax += w * ff.x; ay += w * ff.y; az += w * ff.z;
         }
       }
