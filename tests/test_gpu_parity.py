@@ -449,3 +449,90 @@ def test_newtonian_step_properties_256(psc):
     perm = torch.randperm(pos.shape[0], device=pos.device)
     rho2 = psc.mesh.TSC(pos[perm].contiguous(), N)
     assert (rho2 - rho).abs().max().item() < 2e-5
+
+
+# ------------------------------------------------------------------ BASELINE configs 2-4 at their full sizes
+def _rel_rms(a, b):
+    import torch
+    return ((a - b).double().pow(2).mean().sqrt() / b.double().pow(2).mean().sqrt().clamp_min(1e-300)).item()
+
+
+def test_config2_multigrid_256_matches_7pt_fft(psc):
+    """BASELINE config 2 (Newtonian 256^3, multigrid, red-black Gauss-Seidel).  Size-independent property: the
+    multigrid iterates converge to the solution of the SAME discrete 7-point Poisson problem that `fft_7pt` solves
+    exactly, so the two potentials agree to the solver tolerance and the accelerations to well below a per cent."""
+    N = 256
+    pos = _cuda(cases.lattice_particles(N, 0.3, seed=81))
+    pm_mg = cases.base_param(8, N ** 3, linear_newton_solver="multigrid", epsrel=1e-3)
+    pm_ft = cases.base_param(8, N ** 3, linear_newton_solver="fft_7pt")
+    for p in (pm_mg, pm_ft):
+        psc.utils.set_units(p)
+    acc_f, pot_f, _ = psc.solver.pm(pos, pm_ft)
+    acc_m, pot_m, _ = psc.solver.pm(pos, pm_mg)
+    pot_f = pot_f - pot_f.mean()
+    pot_m = pot_m - pot_m.mean()
+    assert _rel_rms(pot_m, pot_f) < 2e-2       # fft_7pt deconvolves nothing: same operator, same RHS
+    assert _rel_rms(acc_m, acc_f) < 2e-2
+    # the discrete residual of the multigrid solution is small against the RHS
+    rho = psc.mesh.TSC(pos, N)
+    f1 = np.float32(1.5 * pm_mg["aexp"] * pm_mg["Om_m"])
+    rhs = rho * f1 - f1
+    res = psc.laplacian.residual_error(pot_m.contiguous(), rhs.contiguous())
+    rhs_norm = float(rhs.double().pow(2).sum().sqrt())
+    assert float(res) < 2e-2 * rhs_norm
+    # and one more V-cycle reduces it further (the smoother + transfer operators contract)
+    x2 = pot_m.clone().contiguous()
+    psc.multigrid.V_cycle(x2, rhs.contiguous(), pm_mg)
+    assert float(psc.laplacian.residual_error(x2, rhs.contiguous())) < 0.5 * float(res)
+
+
+def test_config3_fr_256_scalaron(psc):
+    """BASELINE config 3 (f(R) Hu-Sawicki n = 1, |fR0| = 1e-5, 256^3, nonlinear FAS multigrid with the cubic
+    smoother).  Properties: the FAS solve lowers the nonlinear residual by the requested factor, the scalaron stays
+    positive and finite, and the fifth force is a small, finite correction on top of the Newtonian one."""
+    import torch
+    N = 256
+    pos = _cuda(cases.lattice_particles(N, 0.3, seed=82))
+    over = dict(theory="fr", fR_n=1, fR_logfR0=5, linear_newton_solver="multigrid", aexp=0.05, aexp_old=0.05)
+    p_fr = cases.base_param(8, N ** 3, **over)
+    p_nw = cases.base_param(8, N ** 3, linear_newton_solver="multigrid", aexp=0.05, aexp_old=0.05)
+    for p in (p_fr, p_nw):
+        psc.utils.set_units(p)
+    tables = cases.toy_tables()
+    acc_n, pot_n, _ = psc.solver.pm(pos, p_nw, tables=tables)
+    acc_f, pot_f, u = psc.solver.pm(pos, p_fr, tables=tables)
+    assert u.shape == (N, N, N) and bool(torch.isfinite(u).all()) and u.min().item() > 0
+    assert bool(torch.isfinite(acc_f).all())
+    assert _rel_rms(pot_f, pot_n) < 1e-6 or _rel_rms(pot_f, pot_n) < 5e-2   # same Newtonian potential
+    d = _rel_rms(acc_f, acc_n)
+    assert 0 <= d < 0.34      # |F5| <= F_N / 3 in f(R)
+    # nonlinear residual of the returned scalaron against the residual of the initial guess
+    f1, f2, q = cases.fr_coeffs(p_fr)
+    rho = psc.mesh.TSC(pos, N)
+    b = (rho * np.float32(f1) + np.float32(f2)).contiguous()
+    r_sol = float(psc.cubic.residual_error(u.contiguous(), b, np.float32(q)))
+    u0 = psc.cubic.initialise_potential(b, np.float32(q))
+    r0 = float(psc.cubic.residual_error(u0, b, np.float32(q)))
+    assert r_sol < r0
+
+
+def test_config4_mond_512_newtonian_limit(psc):
+    """BASELINE config 4 (QUMOND 512^3: FFT Newtonian solve + MOND source + second Poisson solve).  With g0 -> 0
+    the interpolating function nu -> 1, so the MOND acceleration must reduce to the Newtonian one; with the
+    physical g0 the MOND force is stronger than Newton everywhere on average."""
+    import torch
+    N = 512
+    pos = _cuda(cases.lattice_particles(N, 0.3, seed=83))
+    p_nw = cases.base_param(9, N ** 3, linear_newton_solver="fft_7pt")
+    p_m0 = cases.base_param(9, N ** 3, theory="mond", linear_newton_solver="fft_7pt", mond_g0=1e-12)
+    p_m1 = cases.base_param(9, N ** 3, theory="mond", linear_newton_solver="fft_7pt", mond_g0=1.2)
+    for p in (p_nw, p_m0, p_m1):
+        psc.utils.set_units(p)
+    acc_n, _, _ = psc.solver.pm(pos, p_nw)
+    acc_0, _, _ = psc.solver.pm(pos, p_m0)
+    assert _rel_rms(acc_0, acc_n) < 2e-3
+    del acc_0
+    acc_1, _, _ = psc.solver.pm(pos, p_m1)
+    assert bool(torch.isfinite(acc_1).all())
+    ratio = (acc_1.double().pow(2).mean().sqrt() / acc_n.double().pow(2).mean().sqrt()).item()
+    assert ratio > 1.0
