@@ -53,6 +53,12 @@ class SelfComm:
     def exchange_planes(self, to_left, to_right):
         return to_right, to_left
 
+    def neighbor_counts(self, n_to_left, n_to_right):
+        return n_to_right, n_to_left
+
+    def neighbor_exchange(self, to_left, to_right, n_from_left, n_from_right):
+        return to_right, to_left
+
     def allreduce_max_(self, t):
         return t
 
@@ -88,26 +94,45 @@ class TorchComm:
         dist.all_to_all_single(out, send, group=self.group)
         return out
 
-    def exchange_planes(self, to_left, to_right):
+    def _p2p(self, to_left, to_right, from_left, from_right):
+        """One batch of point-to-point messages with the two neighbours (4 NCCL p2p ops instead of the P (P - 1)
+        of an all-to-all).  Message order per peer is what pairs sends with receives when P == 2 (the peer is both
+        neighbours): sends go out as [to_left, to_right], receives are posted as [from_right, from_left]."""
         P, r = self.size, self.rank
         left, right = (r - 1) % P, (r + 1) % P
-        n = to_left.shape[0]
+        ops = []
+        if to_left.numel():
+            ops.append(dist.P2POp(dist.isend, to_left.contiguous(), left, self.group))
+        if to_right.numel():
+            ops.append(dist.P2POp(dist.isend, to_right.contiguous(), right, self.group))
+        if from_right.numel():
+            ops.append(dist.P2POp(dist.irecv, from_right, right, self.group))
+        if from_left.numel():
+            ops.append(dist.P2POp(dist.irecv, from_left, left, self.group))
+        if ops:
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
+
+    def exchange_planes(self, to_left, to_right):
         assert to_right.shape == to_left.shape
-        counts = [0] * P
-        if P == 2:
-            send = torch.cat([to_left, to_right])
-            counts[left] = 2 * n
-            recv = self.all_to_all_v(send, counts, counts)
-            # the peer is both neighbours: its to_left comes from my right, its to_right from my left
-            return recv[n:], recv[:n]
-        parts = sorted([(left, to_left), (right, to_right)], key=lambda t: t[0])
-        send = torch.cat([p[1] for p in parts])
-        counts[left] = n
-        counts[right] = n
-        recv = self.all_to_all_v(send, counts, counts)
-        first, second = recv[:n], recv[n:]
-        # chunks arrive ordered by source rank; the left neighbour sent its to_right, the right one its to_left
-        return (first, second) if left < right else (second, first)
+        from_left, from_right = torch.empty_like(to_left), torch.empty_like(to_right)
+        self._p2p(to_left, to_right, from_left, from_right)
+        return from_left, from_right
+
+    def neighbor_counts(self, n_to_left, n_to_right):
+        dev = "cuda" if dist.get_backend(self.group) == "nccl" else "cpu"
+        s = torch.tensor([int(n_to_left), int(n_to_right)], dtype=torch.int64, device=dev)
+        r = torch.empty_like(s)
+        self._p2p(s[0:1], s[1:2], r[0:1], r[1:2])
+        r = r.cpu().tolist()
+        return int(r[0]), int(r[1])
+
+    def neighbor_exchange(self, to_left, to_right, n_from_left, n_from_right):
+        shape = tuple(to_left.shape[1:])
+        from_left = torch.empty((n_from_left,) + shape, dtype=to_left.dtype, device=to_left.device)
+        from_right = torch.empty((n_from_right,) + shape, dtype=to_left.dtype, device=to_left.device)
+        self._p2p(to_left, to_right, from_left, from_right)
+        return from_left, from_right
 
     def allreduce_max_(self, t):
         dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
@@ -178,6 +203,16 @@ class ThreadComm:
         left, right = (self.rank - 1) % self.size, (self.rank + 1) % self.size
         out = alls[left][1].clone(), alls[right][0].clone()
         self.w.barrier.wait()
+        return out
+
+    def neighbor_counts(self, n_to_left, n_to_right):
+        alls = self._share((int(n_to_left), int(n_to_right)))
+        left, right = (self.rank - 1) % self.size, (self.rank + 1) % self.size
+        return alls[left][1], alls[right][0]
+
+    def neighbor_exchange(self, to_left, to_right, n_from_left, n_from_right):
+        out = self.exchange_planes(to_left, to_right)
+        assert out[0].shape[0] == n_from_left and out[1].shape[0] == n_from_right
         return out
 
     def _allreduce(self, t, fn):
@@ -435,9 +470,12 @@ class Slab:
         self.migrate()
 
     # -- migration
-    def migrate(self, detected=None):
+    def migrate(self, detected=None, neighbours_only=False):
         """Send every particle that left the slab to its owner and take in the arrivals (O(migrants) row moves).
-        detected = (counts[P + 1], rows) from ops.kick_drift_wrap_detect skips the two scans over all positions."""
+        detected = (counts[P + 1], rows) from ops.kick_drift_wrap_detect skips the two scans over all positions.
+        neighbours_only: after a leapfrog drift the Courant condition keeps every particle within one cell of where
+        it was (integration.py:324-326), so leavers can only go to the adjacent slabs and the exchange is two
+        point-to-point messages instead of an all-to-all."""
         ops, comm, me = self.ops, self.comm, self.rank
         n = self.np
         rows = None
@@ -451,8 +489,21 @@ class Slab:
         send_counts = [int(c) for c in counts]
         send_counts[me] = 0
         nout = sum(send_counts)
-        recv_counts = comm.exchange_counts(send_counts)
-        nin = sum(recv_counts)
+        left, right = (me - 1) % self.P, (me + 1) % self.P
+        if neighbours_only and self.P > 1:
+            if any(c and d not in (left, right) for d, c in enumerate(send_counts)):
+                raise RuntimeError("a particle crossed more than one slab in a single step: the Courant condition "
+                                   "is violated (Courant_factor > slab thickness in cells?)")
+            if left == right:     # P == 2: one peer; its records are ordered [to_left | to_right] by destination
+                n_l, n_r = send_counts[left], 0
+            else:
+                n_l, n_r = send_counts[left], send_counts[right]
+            from_l, from_r = comm.neighbor_counts(n_l, n_r)
+            recv_counts = None
+            nin = from_l + from_r
+        else:
+            recv_counts = comm.exchange_counts(send_counts)
+            nin = sum(recv_counts)
         self.migrated_last = (nout, nin)
         if comm.size == 1:
             return  # periodic wrap keeps every particle in the only slab
@@ -466,8 +517,18 @@ class Slab:
         else:
             sendbuf = torch.empty((0, REC), dtype=torch.float32, device=dev)
             holes = torch.empty((0,), dtype=torch.int64, device=dev)
-        # every rank enters the all-to-all, even with nothing to send or receive
-        recvbuf = comm.all_to_all_v(sendbuf, send_counts, recv_counts)
+        if recv_counts is None:
+            # records are ordered by destination rank: the part for the lower-numbered neighbour comes first
+            first, second = (left, right) if left < right else (right, left)
+            a, b = sendbuf[:send_counts[first]], sendbuf[send_counts[first]:]
+            to_l, to_r = (a, b) if first == left else (b, a)
+            if left == right:
+                to_l, to_r = sendbuf, sendbuf[:0]
+            got_l, got_r = comm.neighbor_exchange(to_l, to_r, from_l, from_r)
+            recvbuf = torch.cat([got_l, got_r]) if (from_l and from_r) else (got_l if from_l else got_r)
+        else:
+            # every rank enters the all-to-all, even with nothing to send or receive
+            recvbuf = comm.all_to_all_v(sendbuf, send_counts, recv_counts)
         if nout == 0 and nin == 0:
             return
         n_new = n - nout + nin
@@ -588,7 +649,7 @@ class Slab:
         param["aexp"] = np.exp(tables[0](param["t"]))
         logging.info(f"{param['t']=} {param['aexp']=}")
         utils.set_units(param)
-        self.migrate(detected)
+        self.migrate(detected, neighbours_only=True)
         self.pm(param, kick=half_dt)
 
     def integrate(self, tables, param, t_snap_next=np.float32(0)):
