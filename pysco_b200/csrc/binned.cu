@@ -37,8 +37,7 @@ struct BinLayout {
   int64_t nbins;     // NBX * NB^2
   int *counts;       // [nbins + 1]
   int *offsets;      // [nbins + 1]  exclusive prefix sum, offsets[nbins] = np
-  int *src;          // [np] source row of the binned particle
-  float *pos;        // [np, 3] binned positions
+  float4 *rec;       // [np] binned particles: (x, y, z, source row as int bits) -- one 16-byte access per particle
   void *cub_tmp;
   size_t cub_bytes;
 };
@@ -60,8 +59,7 @@ static bool bin_layout(void *scratch, size_t bytes, int64_t np, int N, int x0, i
   size_t off = 0;
   L.counts = reinterpret_cast<int *>(p + off); off += a256(sizeof(int) * (L.nbins + 1));
   L.offsets = reinterpret_cast<int *>(p + off); off += a256(sizeof(int) * (L.nbins + 1));
-  L.src = reinterpret_cast<int *>(p + off); off += a256(sizeof(int) * (size_t)np);
-  L.pos = reinterpret_cast<float *>(p + off); off += a256(sizeof(float) * 3 * (size_t)np);
+  L.rec = reinterpret_cast<float4 *>(p + off); off += a256(sizeof(float4) * (size_t)np);
   L.cub_tmp = p + off;
   L.cub_bytes = scan_tmp_bytes(L.nbins + 1);
   off += a256(L.cub_bytes);
@@ -95,7 +93,7 @@ __global__ void __launch_bounds__(256) bin_count_kernel(const float *__restrict_
 // pass 2: slot = offsets[bin] + (claimed range in the bin); counts[] is consumed (counted down to zero)
 __global__ void __launch_bounds__(256) bin_scatter_kernel(const float *__restrict__ pos, int64_t np, int N, int NB,
                                                           int x0, int NBX, int *__restrict__ counts, const int *__restrict__ offsets,
-                                                          float *__restrict__ bpos, int *__restrict__ bsrc) {
+                                                          float4 *__restrict__ brec) {
   const float Nf = (float)N;
   const int lane = threadIdx.x & 31;
   const int64_t nwarp_iters = (np + 31) >> 5;
@@ -118,17 +116,14 @@ __global__ void __launch_bounds__(256) bin_scatter_kernel(const float *__restric
     base = __shfl_sync(0xffffffffu, base, leader);
     if (b >= 0) {
       const int slot = offsets[b] + base + __popc(peers & ((1u << lane) - 1u));
-      bpos[3 * (size_t)slot + 0] = x;
-      bpos[3 * (size_t)slot + 1] = y;
-      bpos[3 * (size_t)slot + 2] = z;
-      bsrc[slot] = (int)n;
+      brec[slot] = make_float4(x, y, z, __int_as_float((int)n));
     }
   }
 }
 
 // ------------------------------------------------------------------------------------- deposit
 template <int SCHEME>
-__global__ void __launch_bounds__(BD_WARPS * 32) deposit_binned_kernel(const float *__restrict__ bpos,
+__global__ void __launch_bounds__(BD_WARPS * 32) deposit_binned_kernel(const float4 *__restrict__ brec,
                                                                        const int *__restrict__ offsets, int N, int NB,
                                                                        int x0, int xoff, int nxa,
                                                                        float *__restrict__ rho) {
@@ -148,7 +143,7 @@ __global__ void __launch_bounds__(BD_WARPS * 32) deposit_binned_kernel(const flo
     const int n = c + lane;
     const bool valid = n < end;
     float px = 0.f, py = 0.f, pz = 0.f;
-    if (valid) { px = __ldg(&bpos[3 * (size_t)n]); py = __ldg(&bpos[3 * (size_t)n + 1]); pz = __ldg(&bpos[3 * (size_t)n + 2]); }
+    if (valid) { const float4 r = __ldg(&brec[n]); px = r.x; py = r.y; pz = r.z; }
     int i, j, k;
     float wx[3], wy[3], wz[3];
     axis_weights<SCHEME>(px * Nf, N, i, wx[0], wx[1], wx[2]);
@@ -223,7 +218,7 @@ constexpr int BI_THREADS = 128;
 
 template <int SCHEME>
 __global__ void __launch_bounds__(BI_THREADS) interp_kick4_binned_kernel(
-    const float4 *__restrict__ force4, const float *__restrict__ bpos, const int *__restrict__ bsrc,
+    const float4 *__restrict__ force4, const float4 *__restrict__ brec,
     const int *__restrict__ offsets, float *__restrict__ vel, float *__restrict__ accel, int N, int NB,
     int x0, int xoff, int nxa, float half_dt, float *__restrict__ maxout) {
   __shared__ float4 tile[BT * BT * BT];  // 16,000 B
@@ -245,8 +240,9 @@ __global__ void __launch_bounds__(BI_THREADS) interp_kick4_binned_kernel(
   const float mh = -half_dt;
   float ma = 0.0f, mv = 0.0f;
   for (int n = beg + threadIdx.x; n < end; n += BI_THREADS) {
-    const float px = __ldg(&bpos[3 * (size_t)n]), py = __ldg(&bpos[3 * (size_t)n + 1]), pz = __ldg(&bpos[3 * (size_t)n + 2]);
-    const int row = __ldg(&bsrc[n]);
+    const float4 rec = __ldg(&brec[n]);
+    const float px = rec.x, py = rec.y, pz = rec.z;
+    const int row = __float_as_int(rec.w);
     int i, j, k;
     float wx[3], wy[3], wz[3];
     axis_weights<SCHEME>(px * Nf, N, i, wx[0], wx[1], wx[2]);
@@ -303,7 +299,7 @@ constexpr int BP_THREADS = 256;  // gradient + interpolation kernel
 template <int SCHEME, int ORDER, int TP1 = BT, int TP0 = BT * BT>
 __global__ void __launch_bounds__(BP_THREADS) interp_kick_phi_binned_kernel(
     const float *__restrict__ phi, const float *__restrict__ u, float f, int fr_n,
-    const float *__restrict__ bpos, const int *__restrict__ bsrc, const int *__restrict__ offsets,
+    const float4 *__restrict__ brec, const int *__restrict__ offsets,
     float *__restrict__ vel, float *__restrict__ accel, int N, int NB, int x0, int xoff, int nxa, float half_dt,
     float *__restrict__ maxout) {
   constexpr int H = Reach<ORDER>::H;
@@ -381,8 +377,9 @@ __global__ void __launch_bounds__(BP_THREADS) interp_kick_phi_binned_kernel(
   const float mh = -half_dt;
   float ma = 0.0f, mv = 0.0f;
   for (int n = beg + threadIdx.x; n < end; n += BP_THREADS) {
-    const float px = __ldg(&bpos[3 * (size_t)n]), py = __ldg(&bpos[3 * (size_t)n + 1]), pz = __ldg(&bpos[3 * (size_t)n + 2]);
-    const int row = __ldg(&bsrc[n]);
+    const float4 rec = __ldg(&brec[n]);
+    const float px = rec.x, py = rec.y, pz = rec.z;
+    const int row = __float_as_int(rec.w);
     int i, j, k;
     float wx[3], wy[3], wz[3];
     axis_weights<SCHEME>(px * Nf, N, i, wx[0], wx[1], wx[2]);
@@ -440,7 +437,7 @@ static bool slab_ok(int N, int x0, int nxl) {
 size_t psc_bin_workspace_bytes_slab(int64_t np, int N, int nxl) {
   if (np < 0 || !slab_ok(N, 0, nxl)) return 0;
   const int64_t nbins = (int64_t)(nxl / BB) * (N / BB) * (N / BB);
-  return 2 * a256(sizeof(int) * (nbins + 1)) + a256(sizeof(int) * (size_t)np) + a256(sizeof(float) * 3 * (size_t)np) +
+  return 2 * a256(sizeof(int) * (nbins + 1)) + a256(sizeof(float4) * (size_t)np) +
          a256(scan_tmp_bytes(nbins + 1)) + 256;
 }
 size_t psc_bin_workspace_bytes(int64_t np, int N) { return psc_bin_workspace_bytes_slab(np, N, N); }
@@ -469,8 +466,7 @@ int psc_bin_particles_slab(const float *pos, int64_t np, int N, int x0, int nxl,
     return PSC_ERR_CUDA;
   }
   if (np > 0) {
-    bin_scatter_kernel<<<grid_for(np, 256, 8), 256, 0, st>>>(pos, np, N, L.NB, x0, L.NBX, L.counts, L.offsets, L.pos,
-                                                             L.src);
+    bin_scatter_kernel<<<grid_for(np, 256, 8), 256, 0, st>>>(pos, np, N, L.NB, x0, L.NBX, L.counts, L.offsets, L.rec);
     count_launch();
   }
   PSC_CHECK_LAUNCH();
@@ -496,11 +492,11 @@ static int deposit_binned_impl(const void *scratch, size_t scratch_bytes, int64_
   if (np > 0) {
     const int grid = (int)L.nbins;
     if (scheme == PSC_TSC)
-      deposit_binned_kernel<PSC_TSC><<<grid, BD_WARPS * 32, 0, st>>>(L.pos, L.offsets, N, L.NB, x0, ghost, nxa, rho);
+      deposit_binned_kernel<PSC_TSC><<<grid, BD_WARPS * 32, 0, st>>>(L.rec, L.offsets, N, L.NB, x0, ghost, nxa, rho);
     else if (scheme == PSC_CIC)
-      deposit_binned_kernel<PSC_CIC><<<grid, BD_WARPS * 32, 0, st>>>(L.pos, L.offsets, N, L.NB, x0, ghost, nxa, rho);
+      deposit_binned_kernel<PSC_CIC><<<grid, BD_WARPS * 32, 0, st>>>(L.rec, L.offsets, N, L.NB, x0, ghost, nxa, rho);
     else
-      deposit_binned_kernel<PSC_NGP><<<grid, BD_WARPS * 32, 0, st>>>(L.pos, L.offsets, N, L.NB, x0, ghost, nxa, rho);
+      deposit_binned_kernel<PSC_NGP><<<grid, BD_WARPS * 32, 0, st>>>(L.rec, L.offsets, N, L.NB, x0, ghost, nxa, rho);
     count_launch();
     PSC_CHECK_LAUNCH();
   }
@@ -544,9 +540,9 @@ int psc_interp_kick4_binned(const float *force4, const void *scratch, size_t scr
   const float4 *f4 = reinterpret_cast<const float4 *>(force4);
   const int grid = (int)L.nbins;
   if (scheme == PSC_TSC)
-    interp_kick4_binned_kernel<PSC_TSC><<<grid, BI_THREADS, 0, st>>>(f4, L.pos, L.src, L.offsets, vel, acc, N, L.NB, 0, 0, N, half_dt, maxout);
+    interp_kick4_binned_kernel<PSC_TSC><<<grid, BI_THREADS, 0, st>>>(f4, L.rec, L.offsets, vel, acc, N, L.NB, 0, 0, N, half_dt, maxout);
   else
-    interp_kick4_binned_kernel<PSC_CIC><<<grid, BI_THREADS, 0, st>>>(f4, L.pos, L.src, L.offsets, vel, acc, N, L.NB, 0, 0, N, half_dt, maxout);
+    interp_kick4_binned_kernel<PSC_CIC><<<grid, BI_THREADS, 0, st>>>(f4, L.rec, L.offsets, vel, acc, N, L.NB, 0, 0, N, half_dt, maxout);
   count_launch();
   PSC_CHECK_LAUNCH();
   return PSC_OK;
@@ -568,7 +564,7 @@ static int interp_kick_phi_impl(const float *phi, const float *u, float f, int f
   const int grid = (int)L.nbins;
   const int nxa = nxl + 2 * ghost;
 #define PSC_IKP(S, O)                                                                                            \
-  interp_kick_phi_binned_kernel<S, O><<<grid, BP_THREADS, 0, st>>>(phi, u, f, fr_n, L.pos, L.src, L.offsets, vel, acc, \
+  interp_kick_phi_binned_kernel<S, O><<<grid, BP_THREADS, 0, st>>>(phi, u, f, fr_n, L.rec, L.offsets, vel, acc, \
                                                                    N, L.NB, x0, ghost, nxa, half_dt, maxout)
 #define PSC_IKP_O(S)               \
   if (order == 2) PSC_IKP(S, 2);    \
