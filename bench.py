@@ -37,6 +37,8 @@ N_REORDER = 50
 # (SURVEY 8d): the figure `roofline.achieved` is computed from.
 ALGO_BYTES = {
     "psc_kick_drift_wrap": 60.0,   # read x,v,a (36) + write x,v (24)
+    "psc_kick_drift_wrap_count": 60.0,   # same pass + the bin counts of the new positions
+    "psc_bin_particles_counted": 0.0,
     "psc_deposit": 16.0,           # read x (12) + write rho (4); rescale + RHS affine fused (0)
     "psc_fft_r2c": 8.0,            # read 4 + write 4 (half-spectrum ~ 4 B per real cell)
     "psc_green": 8.0,
@@ -365,7 +367,7 @@ def run_gpu_arm(args):
     for k, d in kern.items():
         if ALGO_BYTES.get(k, 0) > 0:
             # particle kernels see N^3 / world particles per rank, grid kernels the full (replicated) mesh
-            units = N ** 3 / world if k in ("psc_kick_drift_wrap", "psc_interp_kick4", "psc_interp_kick4_binned") else N ** 3
+            units = N ** 3 / world if k in ("psc_kick_drift_wrap", "psc_kick_drift_wrap_count", "psc_interp_kick4", "psc_interp_kick4_binned") else N ** 3
             if k == "psc_interp_kick_phi_binned":
                 units = N ** 3 * (60.0 / world + 16.0) / 76.0
             if k in ("psc_deposit", "psc_deposit_binned"):

@@ -103,6 +103,15 @@ int psc_deposit_binned(const void *scratch, size_t scratch_bytes, int64_t np, in
 int psc_interp_kick4_binned(const float *force4, const void *scratch, size_t scratch_bytes, float *vel, float *acc,
                             int64_t np, int N, int scheme, float half_dt, float *maxout, void *stream);
 
+/* psc_kick_drift_wrap with the bin count of the NEW positions folded in (the binning's first pass then costs no
+ * extra read of the positions): counts go to the bin scratch of np_total particles (zeroed first when zero_counts;
+ * pass 0 for the later chunks of a chunked upload).  psc_bin_particles_counted finishes the binning (scan +
+ * scatter) from those counts. */
+int psc_kick_drift_wrap_count(float *pos, float *vel, const float *acc, int64_t np, float half_dt, double dt,
+                              int dt_is_f64, int N, int64_t np_total, void *scratch, size_t scratch_bytes,
+                              int zero_counts, void *stream);
+int psc_bin_particles_counted(const float *pos, int64_t np, int N, void *scratch, size_t scratch_bytes, void *stream);
+
 /* mesh.derivative / derivative_fR (mesh.py:639-2174) fused into the binned interpolation + kick: every bin's CTA
  * derives its force tile from the potential phi (and, for f(R), the scalaron u: phi + f * u^(fr_n+1)) in shared
  * memory, so neither the gradient kernel nor the force grid exist in the step.  fr_n = 0: plain. */

@@ -90,6 +90,79 @@ __global__ void __launch_bounds__(256) bin_count_kernel(const float *__restrict_
   }
 }
 
+// pass 1 fused into the first half of the leapfrog step (integration.py:250-258): v -= half_dt a; x += dt v; wrap(x);
+// counts[bin(x)] += 1.  Four particles (three float4 per array) per thread; the common case "all four in one bin" costs
+// one warp-aggregated atomic.  Saves the separate read of the positions that bin_count_kernel does.
+template <bool F64>
+__global__ void __launch_bounds__(256) kick_drift_wrap_count_kernel(float *__restrict__ pos, float *__restrict__ vel,
+                                                                    const float *__restrict__ acc, int64_t np,
+                                                                    float half_dt, double dt, int N, int NB,
+                                                                    int *__restrict__ counts) {
+  const float dtf = (float)dt, mh = -half_dt, Nf = (float)N;
+  const int lane = threadIdx.x & 31;
+  const int64_t nq = np >> 2;
+  float4 *p4 = reinterpret_cast<float4 *>(pos);
+  float4 *v4 = reinterpret_cast<float4 *>(vel);
+  const float4 *a4 = reinterpret_cast<const float4 *>(acc);
+  const int64_t wstride = (((int64_t)gridDim.x * blockDim.x) >> 5) * 32;
+  for (int64_t base = (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 32; base < nq; base += wstride) {
+    const int64_t q = base + lane;
+    const bool valid = q < nq;
+    float f[12];
+    int b[4] = {-1 - lane, -1 - lane, -1 - lane, -1 - lane};
+    if (valid) {
+      float v[12], a[12];
+#pragma unroll
+      for (int c = 0; c < 3; c++) {
+        const float4 P = p4[3 * q + c], V = v4[3 * q + c], A = __ldg(&a4[3 * q + c]);
+        f[4 * c] = P.x; f[4 * c + 1] = P.y; f[4 * c + 2] = P.z; f[4 * c + 3] = P.w;
+        v[4 * c] = V.x; v[4 * c + 1] = V.y; v[4 * c + 2] = V.z; v[4 * c + 3] = V.w;
+        a[4 * c] = A.x; a[4 * c + 1] = A.y; a[4 * c + 2] = A.z; a[4 * c + 3] = A.w;
+      }
+#pragma unroll
+      for (int c = 0; c < 12; c++) {
+        v[c] += mh * a[c];
+        f[c] = F64 ? (float)((double)f[c] + dt * (double)v[c]) : f[c] + dtf * v[c];
+        f[c] = wrap01(f[c]);
+      }
+#pragma unroll
+      for (int c = 0; c < 3; c++) {
+        p4[3 * q + c] = make_float4(f[4 * c], f[4 * c + 1], f[4 * c + 2], f[4 * c + 3]);
+        v4[3 * q + c] = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+      }
+#pragma unroll
+      for (int r = 0; r < 4; r++) b[r] = bin_of(f[3 * r], f[3 * r + 1], f[3 * r + 2], Nf, NB, 0, NB);
+    }
+    const bool same = b[0] == b[1] && b[1] == b[2] && b[2] == b[3];
+    if (__all_sync(0xffffffffu, same)) {
+      const unsigned peers = __match_any_sync(0xffffffffu, b[0]);
+      if (valid && (__ffs(peers) - 1) == lane) atomicAdd(&counts[b[0]], 4 * __popc(peers));
+    } else {
+#pragma unroll
+      for (int r = 0; r < 4; r++) {
+        const unsigned peers = __match_any_sync(0xffffffffu, b[r]);
+        if (valid && (__ffs(peers) - 1) == lane) atomicAdd(&counts[b[r]], __popc(peers));
+      }
+    }
+  }
+  // the last np % 4 particles
+  if (blockIdx.x == 0 && threadIdx.x < (np & 3)) {
+    const int64_t n = (nq << 2) + threadIdx.x;
+    float x[3];
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+      float v = vel[3 * n + c] + mh * acc[3 * n + c];
+      float p = pos[3 * n + c];
+      p = F64 ? (float)((double)p + dt * (double)v) : p + dtf * v;
+      p = wrap01(p);
+      vel[3 * n + c] = v;
+      pos[3 * n + c] = p;
+      x[c] = p;
+    }
+    atomicAdd(&counts[bin_of(x[0], x[1], x[2], Nf, NB, 0, NB)], 1);
+  }
+}
+
 // pass 2: slot = offsets[bin] + (claimed range in the bin); counts[] is consumed (counted down to zero)
 __global__ void __launch_bounds__(256) bin_scatter_kernel(const float *__restrict__ pos, int64_t np, int N, int NB,
                                                           int x0, int NBX, int *__restrict__ counts, const int *__restrict__ offsets,
@@ -474,6 +547,56 @@ int psc_bin_particles_slab(const float *pos, int64_t np, int N, int x0, int nxl,
 }
 int psc_bin_particles(const float *pos, int64_t np, int N, void *scratch, size_t scratch_bytes, void *stream) {
   return psc_bin_particles_slab(pos, np, N, 0, N, scratch, scratch_bytes, stream);
+}
+
+int psc_kick_drift_wrap_count(float *pos, float *vel, const float *acc, int64_t np, float half_dt, double dt,
+                              int dt_is_f64, int N, int64_t np_total, void *scratch, size_t scratch_bytes,
+                              int zero_counts, void *stream) {
+  PSC_CHECK_ARG(np >= 0 && np <= np_total && np_total < ((int64_t)1 << 31), "np out of range");
+  PSC_CHECK_ARG(slab_ok(N, 0, N), "N must be a multiple of 8");
+  PSC_CHECK_ARG(scratch && ((uintptr_t)scratch & 255) == 0, "scratch must be 256-byte aligned");
+  BinLayout L;
+  if (!bin_layout(scratch, scratch_bytes, np_total, N, 0, N, L)) {
+    set_error("psc_kick_drift_wrap_count: scratch too small");
+    return PSC_ERR_WORKSPACE;
+  }
+  cudaStream_t st = as_stream(stream);
+  if (zero_counts) PSC_CUDA(cudaMemsetAsync(L.counts, 0, sizeof(int) * (L.nbins + 1), st));
+  if (np == 0) return PSC_OK;
+  PSC_CHECK_ARG(pos && vel && acc, "null pointer");
+  PSC_CHECK_ARG((((uintptr_t)pos | (uintptr_t)vel | (uintptr_t)acc) & 15) == 0, "pointers must be 16-byte aligned");
+  const int g = grid_for((np + 3) / 4, 256, 8);
+  if (dt_is_f64)
+    kick_drift_wrap_count_kernel<true><<<g, 256, 0, st>>>(pos, vel, acc, np, half_dt, dt, N, L.NB, L.counts);
+  else
+    kick_drift_wrap_count_kernel<false><<<g, 256, 0, st>>>(pos, vel, acc, np, half_dt, dt, N, L.NB, L.counts);
+  count_launch();
+  PSC_CHECK_LAUNCH();
+  return PSC_OK;
+}
+
+int psc_bin_particles_counted(const float *pos, int64_t np, int N, void *scratch, size_t scratch_bytes, void *stream) {
+  PSC_CHECK_ARG(np >= 0 && np < ((int64_t)1 << 31), "np out of range");
+  PSC_CHECK_ARG(slab_ok(N, 0, N), "N must be a multiple of 8");
+  PSC_CHECK_ARG(scratch && (pos || np == 0), "null pointer");
+  BinLayout L;
+  if (!bin_layout(scratch, scratch_bytes, np, N, 0, N, L)) {
+    set_error("psc_bin_particles_counted: scratch too small");
+    return PSC_ERR_WORKSPACE;
+  }
+  cudaStream_t st = as_stream(stream);
+  cudaError_t e = cub::DeviceScan::ExclusiveSum(L.cub_tmp, L.cub_bytes, L.counts, L.offsets, (int)(L.nbins + 1), st);
+  count_launch(2);
+  if (e != cudaSuccess) {
+    set_error("psc_bin_particles_counted: cub scan failed: %s", cudaGetErrorString(e));
+    return PSC_ERR_CUDA;
+  }
+  if (np > 0) {
+    bin_scatter_kernel<<<grid_for(np, 256, 8), 256, 0, st>>>(pos, np, N, L.NB, 0, L.NBX, L.counts, L.offsets, L.rec);
+    count_launch();
+  }
+  PSC_CHECK_LAUNCH();
+  return PSC_OK;
 }
 
 // ghost = 0: periodic N^3 grid (x0 = 0, nxl = N); ghost = 1: rho has nxl + 2 planes, plane 0 / nxl + 1 collect the

@@ -71,6 +71,14 @@ __device__ __forceinline__ void atomic_max_nonneg(float *addr, float v) {
   atomicMax(reinterpret_cast<unsigned int *>(addr), __float_as_uint(v));
 }
 
+// utils.periodic_wrap (utils.py:1131-1149): tiny negatives snap to 0 (t + 1 would round to 1.0), else shift by one box
+__device__ __forceinline__ float wrap01(float t) {
+  const double eps = -2.98023223876953125e-08 * (1.0 + 1e-6);  // -(2^-25) * (1 + 1e-6)
+  if (t < 0.0f) return ((double)t > eps) ? 0.0f : t + 1.0f;
+  if (t >= 1.0f) return t - 1.0f;
+  return t;
+}
+
 // TSC cell + the three 1-D weights of one axis (mesh.py:2502-2522): xp = x*N (float32)
 __device__ __forceinline__ void tsc_axis(float xp, int &c, float &wm, float &w0, float &wp) {
   c = (int)xp;  // trunc == floor for xp >= 0 (reference: np.int16(xp))

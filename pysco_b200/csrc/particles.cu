@@ -54,13 +54,6 @@ __global__ void __launch_bounds__(256) gather3_kernel(const int64_t *__restrict_
 }
 
 // ---------------------------------------------------------------------------- vector ops
-__device__ __forceinline__ float wrap01(float t) {
-  // utils.py:1131-1149: tiny negatives snap to 0 (t + 1 would round to 1.0), else shift by one box
-  const double eps = -2.98023223876953125e-08 * (1.0 + 1e-6);  // -(2^-25) * (1 + 1e-6)
-  if (t < 0.0f) return ((double)t > eps) ? 0.0f : t + 1.0f;
-  if (t >= 1.0f) return t - 1.0f;
-  return t;
-}
 
 template <bool F64>
 __global__ void __launch_bounds__(256) axpy_kernel(float *__restrict__ y, const float *__restrict__ x,

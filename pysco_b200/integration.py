@@ -12,7 +12,7 @@ import weakref
 import numpy as np
 import torch
 
-from . import _lib, distributed, solver, utils
+from . import _lib, distributed, mesh, solver, utils
 
 # maxima produced by the fused interpolation kernel, valid for exactly the (acceleration, velocity)
 # tensors returned by the last leapfrog step
@@ -72,6 +72,15 @@ def _from_device(c, position, velocity, pos, vel, acc, pot, add):
     return pos, vel, acc, pot, add
 
 
+def _binned_for(pos, param):
+    """Bin scratch for the step if the binned particle<->mesh kernels will be used (solver._pm_device)."""
+    N = 2 ** param["ncoarse"]
+    n = pos.shape[0]
+    if mesh.can_bin(N, n) and pos.data_ptr() % 16 == 0:
+        return mesh.alloc_binned(n, N)
+    return None
+
+
 _copy_streams = {}
 
 
@@ -120,6 +129,7 @@ def _leapfrog_pinned(position, velocity, acceleration, potential, additional_fie
         add = additional_field.to(dev, non_blocking=True)
     # rows per chunk: a multiple of 4 keeps every chunk 16-byte aligned
     step = max(4, ((n + nchunk - 1) // nchunk + 3) // 4 * 4)
+    counted = _binned_for(pos, param)
     for a in range(0, n, step):
         b = min(n, a + step)
         with torch.cuda.stream(s_in):
@@ -129,8 +139,12 @@ def _leapfrog_pinned(position, velocity, acceleration, potential, additional_fie
             landed = torch.cuda.Event()
             landed.record(s_in)
         cur.wait_event(landed)
-        _lib.check(lib.psc_kick_drift_wrap(_lib.ptr(pos[a:b]), _lib.ptr(vel[a:b]), _lib.ptr(acc[a:b]), b - a,
-                                           float(half_dt), float(dt), dt_is_f64, _lib.stream()))
+        if counted is not None:
+            mesh.kick_drift_wrap_count(pos[a:b], vel[a:b], acc[a:b], half_dt, dt, dt_is_f64, counted,
+                                       zero_counts=(a == 0))
+        else:
+            _lib.check(lib.psc_kick_drift_wrap(_lib.ptr(pos[a:b]), _lib.ptr(vel[a:b]), _lib.ptr(acc[a:b]), b - a,
+                                               float(half_dt), float(dt), dt_is_f64, _lib.stream()))
         drifted = torch.cuda.Event()
         drifted.record(cur)
         s_out.wait_event(drifted)
@@ -139,7 +153,7 @@ def _leapfrog_pinned(position, velocity, acceleration, potential, additional_fie
     _advance_clock(dt, tables, param)
     cur.wait_stream(s_in)
     del acc
-    acc, pot, add, maxima = solver._pm_device(pos, param, pot, add, tables, kick=(vel, half_dt))
+    acc, pot, add, maxima = solver._pm_device(pos, param, pot, add, tables, kick=(vel, half_dt), counted=counted)
     distributed.allreduce_max_(maxima)
     acc_h = torch.empty((n, 3), dtype=torch.float32, pin_memory=True)
     pot_h = torch.empty(pot.shape, dtype=torch.float32, pin_memory=True) if len(pot) else pot
@@ -172,10 +186,14 @@ def leapfrog(position, velocity, acceleration, potential, additional_field, dt, 
     pos, vel, acc, pot, add = _to_device(c, position, velocity, acceleration, potential, additional_field)
     half_dt = np.float32(0.5 * dt)
     dt_is_f64 = 0 if isinstance(dt, np.float32) else 1
-    _lib.check(_lib.load().psc_kick_drift_wrap(_lib.ptr(pos), _lib.ptr(vel), _lib.ptr(acc), pos.shape[0],
-                                               float(half_dt), float(dt), dt_is_f64, _lib.stream()))
+    counted = _binned_for(pos, param)
+    if counted is not None:   # first pass of the binning folded into the kick-drift-wrap
+        mesh.kick_drift_wrap_count(pos, vel, acc, half_dt, dt, dt_is_f64, counted)
+    else:
+        _lib.check(_lib.load().psc_kick_drift_wrap(_lib.ptr(pos), _lib.ptr(vel), _lib.ptr(acc), pos.shape[0],
+                                                   float(half_dt), float(dt), dt_is_f64, _lib.stream()))
     _advance_clock(dt, tables, param)
-    acc, pot, add, maxima = solver._pm_device(pos, param, pot, add, tables, kick=(vel, half_dt))
+    acc, pot, add, maxima = solver._pm_device(pos, param, pot, add, tables, kick=(vel, half_dt), counted=counted)
     distributed.allreduce_max_(maxima)
     mx = maxima.cpu().numpy()  # one 8-byte read: max|a|, max|v| for the next integrate()
     _maxima_cache.update(acc=weakref.ref(acc), vel=weakref.ref(vel), max=mx)

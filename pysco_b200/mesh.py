@@ -18,6 +18,28 @@ def can_bin(N, np_):
     return N >= 8 and N % 8 == 0 and 0 < np_ < 2 ** 31
 
 
+def alloc_binned(np_, ncells_1d):
+    """Scratch of a binning whose counts are produced elsewhere (psc_kick_drift_wrap_count)."""
+    N = int(ncells_1d)
+    nbytes = int(_lib.load().psc_bin_workspace_bytes(int(np_), N))
+    return Binned(_lib.empty((nbytes,), torch.uint8), int(np_), N)
+
+
+def kick_drift_wrap_count(pos, vel, acc, half_dt, dt, dt_is_f64, binned, zero_counts=True):
+    """integration.py:250-258 on (a chunk of) the particles + bin counts of the new positions into `binned`."""
+    _lib.check(_lib.load().psc_kick_drift_wrap_count(
+        _lib.ptr(pos), _lib.ptr(vel), _lib.ptr(acc), pos.shape[0], float(half_dt), float(dt), int(dt_is_f64),
+        binned.N, binned.np, _lib.ptr(binned.scratch), binned.scratch.numel(), int(zero_counts), _lib.stream()))
+
+
+def finish_binning(position, binned):
+    """scan + scatter from counts that are already in `binned`"""
+    _lib.check(_lib.load().psc_bin_particles_counted(_lib.ptr(position), position.shape[0], binned.N,
+                                                     _lib.ptr(binned.scratch), binned.scratch.numel(),
+                                                     _lib.stream()))
+    return binned
+
+
 def bin_particles(position, ncells_1d):
     """Bin a device position array; returns a Binned handle for deposit_rhs / interp_kick."""
     pos = _lib.Ctx().dev(position)

@@ -163,7 +163,7 @@ def get_additional_field(additional_field, density, param, tables):
     raise NotImplementedError(f"{param['theory']=}, should be 'newton', 'fr', 'parametrized' or 'mond'")
 
 
-def _pm_device(position, param, potential, additional_field, tables, kick=None):
+def _pm_device(position, param, potential, additional_field, tables, kick=None, counted=None):
     """pm() on device tensors.  kick = (velocity, half_dt) fuses the second leapfrog half-kick and the
     max reductions into the interpolation; returns (acc, potential, additional_field, maxima|None)."""
     ncells_1d = 2 ** (param["ncoarse"])
@@ -199,7 +199,11 @@ def _pm_device(position, param, potential, additional_field, tables, kick=None):
 
     conversion = np.float32(ncells_1d ** 3 / param["npart"]) if ncells_1d ** 3 != param["npart"] else np.float32(1)
     # one shadow binning of the particles per step, shared by the deposit and the interpolation
-    binned = mesh.bin_particles(position, ncells_1d) if mesh.can_bin(ncells_1d, position.shape[0]) else None
+    # (`counted`: a Binned whose counts were already produced by the fused kick-drift-wrap of integration.leapfrog)
+    if counted is not None:
+        binned = mesh.finish_binning(position, counted)
+    else:
+        binned = mesh.bin_particles(position, ncells_1d) if mesh.can_bin(ncells_1d, position.shape[0]) else None
     pk_from_density = param["save_pk"] and "multigrid" == LINEAR_NEWTON_SOLVER
     fuse_rhs = THEORY in ("newton", "parametrized") and not pk_from_density
     if distributed.is_active():
