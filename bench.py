@@ -494,6 +494,7 @@ def run_slab_arm(args):
 
     sampler = ClockSampler(local_rank)
     _lib.enable_timing(True)
+    S.phase_marks = []
     launches0 = _lib.launch_count()
     barrier()
     if rank == 0:
@@ -511,6 +512,13 @@ def run_slab_arm(args):
     launches = _lib.launch_count() - launches0
     records = _lib.timing_records()
     _lib.enable_timing(False)
+    marks, S.phase_marks = S.phase_marks, None
+    phase_samples = {}
+    for (n0, e0_), (n1, e1_) in zip(marks[:-1], marks[1:]):
+        if n1 != "start":   # device time between consecutive phase boundaries (kernels + collectives + bubbles)
+            phase_samples.setdefault(n1, []).append(e0_.elapsed_time(e1_))
+    phases = {k: {"mean": float(np.mean(v)), "median": float(np.median(v)), "max": float(np.max(v))}
+              for k, v in phase_samples.items()}
     t_ms_total = ev0.elapsed_time(ev1) + (args.steps / N_REORDER - n_reorders) * t_reorder_ms
     tt = torch.tensor([t_ms_total, float(S.np), float(migrated)], device="cuda", dtype=torch.float64)
     mx = tt.clone()
@@ -599,6 +607,7 @@ def run_slab_arm(args):
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
             "clocks": clocks, "kernels": kern,
             "kernel_ms_per_step": kernel_ms, "comm_and_host_ms_per_step": ms_per_step - kernel_ms,
+            "phases_ms_per_step_rank0": phases,
             "reorder": {"ms": t_reorder_ms, "in_timed_steps": n_reorders, "amortised_over": N_REORDER},
             "multi_gpu": {"decomposition": f"x-slabs of {S.nxl} planes per GPU",
                           "collectives_per_step": "migration counts + records all-to-all, 2 ghost-plane exchanges "

@@ -157,6 +157,16 @@ int psc_kick_drift_wrap_slab(float *pos, float *vel, const float *acc, int64_t n
 int psc_slab_pack_rows(const float *pos, const float *vel, const int64_t *ids, const int64_t *rows, int64_t nrows,
                        int N, int nxl, int P, int me, const int64_t *offsets, int64_t *cursor, float *sendbuf,
                        int64_t *holes, void *stream);
+/* Single-round neighbour migration: leavers towards the left / right slab are packed into fixed-capacity buffers
+ * sendL / sendR [(cap + 1) records]; record 0 is a header holding the true count (int64), records 1.. the leavers,
+ * holesL / holesR [cap] their rows.  rows / counts / list_capacity = the candidate list of
+ * psc_kick_drift_wrap_slab (rows may be NULL: all np particles are scanned; an incomplete list is detected on the
+ * device and also falls back to the scan).  status (device int64[3]) = leavers to the left, to the right (either may
+ * exceed cap: the excess is not packed and the exchange must be redone with a larger cap), and leavers to a
+ * non-neighbour (error).  P == 2: both neighbours are the same rank and every leaver counts as "left". */
+int psc_slab_pack_fixed(const float *pos, const float *vel, const int64_t *ids, int64_t np, const int64_t *rows,
+                        const int64_t *counts, int64_t list_capacity, int N, int nxl, int P, int me, int64_t cap,
+                        float *sendL, float *sendR, int64_t *holesL, int64_t *holesR, int64_t *status, void *stream);
 int psc_slab_count(const float *pos, int64_t np, int N, int nxl, int P, int me, int64_t *counts, void *stream);
 int psc_slab_pack_leavers(const float *pos, const float *vel, const int64_t *ids, int64_t np, int N, int nxl, int P,
                           int me, const int64_t *offsets, int64_t *cursor, float *sendbuf, int64_t *holes,

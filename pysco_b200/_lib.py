@@ -45,6 +45,7 @@ SIGNATURES = {
                                         _vp],
     "psc_kick_drift_wrap_slab": [_vp, _vp, _vp, _i64, _f, _d, _i, _i, _i, _i, _i, _vp, _vp, _i64, _vp],
     "psc_slab_pack_rows": [_vp, _vp, _vp, _vp, _i64, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp],
+    "psc_slab_pack_fixed": [_vp, _vp, _vp, _i64, _vp, _vp, _i64, _i, _i, _i, _i, _i64, _vp, _vp, _vp, _vp, _vp, _vp],
     "psc_slab_count": [_vp, _i64, _i, _i, _i, _i, _vp, _vp],
     "psc_slab_pack_leavers": [_vp, _vp, _vp, _i64, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp],
     "psc_slab_unpack_rows": [_vp, _vp, _i64, _vp, _vp, _vp, _vp],
@@ -131,7 +132,7 @@ _TIMED = ("psc_morton_keys", "psc_argsort_keys", "psc_gather3", "psc_axpy", "psc
           "psc_residual_sumsq", "psc_diff_sumsq", "psc_initialise_potential", "psc_gauss_seidel",
           "psc_restriction", "psc_prolongation", "psc_mond_rhs",
           "psc_bin_particles_slab", "psc_deposit_binned_slab", "psc_interp_kick_phi_binned_slab", "psc_slab_count",
-          "psc_slab_pack_leavers", "psc_kick_drift_wrap_slab", "psc_slab_pack_rows", "psc_slab_unpack_rows", "psc_slab_move_rows", "psc_slab_fft_r2c_planes",
+          "psc_slab_pack_leavers", "psc_kick_drift_wrap_slab", "psc_slab_pack_rows", "psc_slab_pack_fixed", "psc_slab_unpack_rows", "psc_slab_move_rows", "psc_slab_fft_r2c_planes",
           "psc_slab_fft_c2r_planes", "psc_slab_fft_x", "psc_slab_yblocks", "psc_green_slab")
 
 

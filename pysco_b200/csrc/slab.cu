@@ -89,6 +89,52 @@ __global__ void __launch_bounds__(256) slab_pack_rows_kernel(const float *__rest
   }
 }
 
+// Fixed-capacity packing for the single-round neighbour migration: leavers towards the left / right slab go to
+// sendL / sendR (capacity `cap` records after a one-record header), their rows to holesL / holesR.  Everything is
+// decided on the device -- the candidate list written by psc_kick_drift_wrap_slab is used if it is complete
+// (counts[P] <= list_capacity), otherwise all np particles are scanned -- so the host needs no count before the
+// exchange.  status[0] / [1] = leavers towards left / right (may exceed cap: those beyond cap are NOT packed),
+// status[2] = leavers whose owner is not a neighbour (an error: Courant condition violated).
+__global__ void __launch_bounds__(256) slab_pack_fixed_kernel(const float *__restrict__ pos, const float *__restrict__ vel,
+                                                              const int64_t *__restrict__ ids, int64_t np,
+                                                              const int64_t *__restrict__ rows,
+                                                              const int64_t *__restrict__ counts, int64_t list_capacity,
+                                                              int N, int nxl, int P, int me, int left, int right,
+                                                              int64_t cap, float *__restrict__ sendL,
+                                                              float *__restrict__ sendR, int64_t *__restrict__ holesL,
+                                                              int64_t *__restrict__ holesR,
+                                                              unsigned long long *__restrict__ status) {
+  const float Nf = (float)N;
+  const int64_t nlist = counts[P];
+  const bool use_list = rows != nullptr && nlist <= list_capacity;
+  const int64_t total = use_list ? nlist : np;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t n = use_list ? rows[t] : t;
+    const float x = pos[3 * n];
+    const int d = owner_of(x, Nf, nxl, P);
+    if (d == me) continue;
+    const bool to_left = d == left;
+    if (!to_left && d != right) { atomicAdd(&status[2], 1ull); continue; }
+    const int64_t slot = (int64_t)atomicAdd(&status[to_left ? 0 : 1], 1ull);
+    if (slot >= cap) continue;
+    float4 *rec = reinterpret_cast<float4 *>((to_left ? sendL : sendR) + REC * (slot + 1));
+    const int64_t id = ids[n];
+    rec[0] = make_float4(x, pos[3 * n + 1], pos[3 * n + 2], vel[3 * n]);
+    rec[1] = make_float4(vel[3 * n + 1], vel[3 * n + 2], __int_as_float((int)(id & 0xffffffffll)),
+                         __int_as_float((int)(id >> 32)));
+    (to_left ? holesL : holesR)[slot] = n;
+  }
+}
+
+// header record of both send buffers = the true leaver counts (int64 in the first two floats)
+__global__ void slab_pack_header_kernel(const unsigned long long *__restrict__ status, float *__restrict__ sendL,
+                                        float *__restrict__ sendR) {
+  if (threadIdx.x == 0) {
+    reinterpret_cast<unsigned long long *>(sendL)[0] = status[0];
+    reinterpret_cast<unsigned long long *>(sendR)[0] = status[1];
+  }
+}
+
 __global__ void __launch_bounds__(256) slab_unpack_kernel(const float *__restrict__ recvbuf,
                                                           const int64_t *__restrict__ rows, int64_t n,
                                                           float *__restrict__ pos, float *__restrict__ vel,
@@ -216,6 +262,32 @@ int psc_slab_pack_rows(const float *pos, const float *vel, const int64_t *ids, c
     count_launch();
     PSC_CHECK_LAUNCH();
   }
+  return PSC_OK;
+}
+
+int psc_slab_pack_fixed(const float *pos, const float *vel, const int64_t *ids, int64_t np, const int64_t *rows,
+                        const int64_t *counts, int64_t list_capacity, int N, int nxl, int P, int me, int64_t cap,
+                        float *sendL, float *sendR, int64_t *holesL, int64_t *holesR, int64_t *status, void *stream) {
+  PSC_CHECK_ARG(np >= 0 && N >= 1 && nxl >= 1 && P >= 2 && nxl * P == N && me >= 0 && me < P && cap >= 0,
+                "bad slab geometry");
+  PSC_CHECK_ARG(counts && sendL && sendR && holesL && holesR && status && (np == 0 || (pos && vel && ids)),
+                "null pointer");
+  PSC_CHECK_ARG((((uintptr_t)sendL | (uintptr_t)sendR) & 15) == 0, "send buffers must be 16-byte aligned");
+  cudaStream_t st = as_stream(stream);
+  PSC_CUDA(cudaMemsetAsync(status, 0, sizeof(int64_t) * 3, st));
+  const int left = (me + P - 1) % P, right = (me + 1) % P;
+  unsigned long long *stt = reinterpret_cast<unsigned long long *>(status);
+  if (np > 0) {
+    // grid-stride loop: the same grid serves the short candidate list and the (rare) full scan
+    slab_pack_fixed_kernel<<<grid_for(np, 256, 8), 256, 0, st>>>(
+        pos, vel, ids, np, rows, counts, list_capacity, N, nxl, P, me, left, right, cap, sendL, sendR, holesL, holesR,
+        stt);
+    count_launch();
+    PSC_CHECK_LAUNCH();
+  }
+  slab_pack_header_kernel<<<1, 32, 0, st>>>(stt, sendL, sendR);
+  count_launch();
+  PSC_CHECK_LAUNCH();
   return PSC_OK;
 }
 

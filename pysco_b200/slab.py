@@ -252,6 +252,7 @@ class CudaOps:
         self._work = None
         self._scratch = None
         self._leavers = None
+        self._mig = None
 
     # -- particles
     def kick_drift_wrap(self, pos, vel, acc, half_dt, dt, dt_is_f64):
@@ -280,6 +281,29 @@ class CudaOps:
                                                rows.shape[0], self.N, self.nxl, self.P, self.rank, _lib.ptr(offsets),
                                                _lib.ptr(cursor), _lib.ptr(sendbuf), _lib.ptr(holes), _lib.stream()))
         return sendbuf, holes
+
+    def pack_fixed(self, pos, vel, ids, detected, cap):
+        """Leavers towards the left / right neighbour into fixed-capacity buffers (header record + cap records);
+        returns (sendL, sendR, holesL, holesR, status[3]) -- all on the device, no host synchronisation."""
+        n = pos.shape[0]
+        if self._mig is None or self._mig[0].shape[0] != cap + 1:
+            self._mig = (torch.zeros((cap + 1, REC), dtype=torch.float32, device=self.dev),
+                         torch.zeros((cap + 1, REC), dtype=torch.float32, device=self.dev),
+                         torch.empty((cap,), dtype=torch.int64, device=self.dev),
+                         torch.empty((cap,), dtype=torch.int64, device=self.dev))
+        sendL, sendR, holesL, holesR = self._mig
+        status = torch.empty((3,), dtype=torch.int64, device=self.dev)
+        if detected is not None:
+            counts, rows = detected
+            rows_ptr, cap_rows = _lib.ptr(rows), rows.numel()
+        else:
+            counts = torch.zeros((self.P + 1,), dtype=torch.int64, device=self.dev)
+            rows_ptr, cap_rows = None, 0
+        _lib.check(self.lib.psc_slab_pack_fixed(_lib.ptr(pos), _lib.ptr(vel), _lib.ptr(ids), n, rows_ptr,
+                                                _lib.ptr(counts), cap_rows, self.N, self.nxl, self.P, self.rank, cap,
+                                                _lib.ptr(sendL), _lib.ptr(sendR), _lib.ptr(holesL), _lib.ptr(holesR),
+                                                _lib.ptr(status), _lib.stream()))
+        return sendL, sendR, holesL, holesR, status
 
     def count_owners(self, pos):
         counts = torch.empty((self.P,), dtype=torch.int64, device=self.dev)
@@ -415,6 +439,34 @@ class Slab:
         self.max_acc = self.max_vel = None
         self.potential = None  # owned planes [nxl, N, N] of the last solve (a view into the ghosted array)
         self.migrated_last = (0, 0)
+        self._warm_host_ops()
+        self._mig_cap = None      # records per direction of the fixed-capacity migration buffers (same on all ranks)
+        self._mig_want = 0        # largest message of the last migration; all-reduced in pm() to resize _mig_cap
+        self.phase_marks = None   # bench.py: list of (phase name, CUDA event) recorded at phase boundaries
+
+    def _warm_host_ops(self):
+        """The migration bookkeeping uses a handful of torch index ops on small tensors; CUDA loads each kernel's
+        module lazily on first use (tens of ms), so run every one of them once here rather than inside a step."""
+        dev = self._device()
+        if dev.type != "cuda":
+            return
+        holes = torch.arange(8, dtype=torch.int64, device=dev)
+        low = holes[holes < 4]
+        tail = torch.ones((4,), dtype=torch.bool, device=dev)
+        tail[holes[holes >= 4] - 4] = False
+        src = torch.nonzero(tail).flatten() + 4
+        torch.cat([low, src, torch.arange(8, 12, dtype=torch.int64, device=dev)]).cpu()
+        rec = torch.zeros((4, REC), dtype=torch.float32, device=dev)
+        torch.cat([rec[1:3], rec[0:1]]).contiguous()
+        torch.cat([holes[:3], rec[0, :2].contiguous().view(torch.int64)]).cpu()
+        m = torch.zeros((2,), dtype=torch.float32, device=dev)
+        torch.cat([m, torch.tensor([1.0], dtype=torch.float32, device=dev)]).cpu()
+
+    def _mark(self, name):
+        if self.phase_marks is not None:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            self.phase_marks.append((name, ev))
 
     # -- particle storage
     @property
@@ -549,6 +601,92 @@ class Slab:
                 ops.move_rows(src.contiguous(), dst, self.pos, self.vel, self.ids)
         self.np = n_new
 
+    def migrate_neighbours(self, detected=None):
+        """migrate() for the step after a leapfrog drift, in ONE exchange with each neighbouring slab and one host
+        synchronisation: the Courant condition (integration.py:324-326) keeps every particle within one cell of
+        where it was, so leavers only go to the adjacent slabs.  Both directions use fixed-capacity buffers whose
+        first record carries the true count; a count above the capacity (known to both ends of that message)
+        makes that pair repeat the message with a larger buffer."""
+        ops, comm, me, P = self.ops, self.comm, self.rank, self.P
+        if P == 1:
+            self.migrated_last = (0, 0)
+            return
+        n = self.np
+        dev = self._device()
+        if self._mig_cap is None:
+            self._mig_cap = 2 * self.N * self.N + 4096   # the same on every rank: two planes' worth of particles
+        cap = self._mig_cap
+        sendL, sendR, holesL, holesR, status = ops.pack_fixed(self.pos[:n], self.vel[:n], self.ids[:n], detected, cap)
+        if P == 2:   # one peer: everything travels "left"; nothing is sent or expected on the right
+            gotL, gotR = comm.neighbor_exchange(sendL, sendR[:0], 0, cap + 1)
+        else:
+            gotL, gotR = comm.neighbor_exchange(sendL, sendR, cap + 1, cap + 1)
+        hdr = [status]
+        hdr.append(gotL[0, :2].contiguous().view(torch.int64) if gotL.shape[0] else status[:1] * 0)
+        hdr.append(gotR[0, :2].contiguous().view(torch.int64) if gotR.shape[0] else status[:1] * 0)
+        outL, outR, bad, inL, inR = (int(v) for v in torch.cat(hdr).cpu().tolist())   # the step's one sync
+        if bad:
+            raise RuntimeError("a particle crossed more than one slab in a single step: the Courant condition "
+                               "is violated (Courant_factor > slab thickness in cells?)")
+        # the capacity has to stay identical on all ranks: the wish travels with the step's all-reduce(max) (pm())
+        self._mig_want = max(outL, outR, inL, inR)
+        if self._mig_want > cap:
+            # rare: the pairs concerned repeat their messages with exact sizes (both ends know them)
+            return self._migrate_redo(detected, outL, outR, inL, inR)
+        holes = torch.cat([holesL[:outL], holesR[:outR]])
+        recvbuf = torch.cat([gotL[1:1 + inL], gotR[1:1 + inR]])
+        self._apply_migration(n, holes, recvbuf, outL + outR, inL + inR)
+
+    def _migrate_redo(self, detected, outL, outR, inL, inR):
+        """Overflow path of migrate_neighbours: exact-size messages (both ends of every message know its size)."""
+        ops, comm, me, P = self.ops, self.comm, self.rank, self.P
+        n = self.np
+        dev = self._device()
+        left, right = (me - 1) % P, (me + 1) % P
+        send_counts = [0] * P
+        send_counts[left] += outL
+        send_counts[right] += outR
+        nout = outL + outR
+        if nout:
+            offsets = torch.tensor(np.concatenate([[0], np.cumsum(send_counts)[:-1]]).astype(np.int64), device=dev)
+            sendbuf, holes = ops.pack_leavers(self.pos[:n], self.vel[:n], self.ids[:n], offsets, nout)
+        else:
+            sendbuf = torch.empty((0, REC), dtype=torch.float32, device=dev)
+            holes = torch.empty((0,), dtype=torch.int64, device=dev)
+        first, second = (left, right) if left < right else (right, left)
+        a, b = sendbuf[:send_counts[first]], sendbuf[send_counts[first]:]
+        to_l, to_r = (a, b) if first == left else (b, a)
+        if left == right:
+            to_l, to_r = sendbuf, sendbuf[:0]
+        got_l, got_r = comm.neighbor_exchange(to_l, to_r, inL, inR)
+        recvbuf = torch.cat([got_l, got_r])
+        self._apply_migration(n, holes, recvbuf, nout, inL + inR)
+
+    def _apply_migration(self, n, holes, recvbuf, nout, nin):
+        """Fill the holes left by the leavers with the arrivals (and with tail particles if more left than came)."""
+        ops = self.ops
+        dev = self._device()
+        self.migrated_last = (nout, nin)
+        if nout == 0 and nin == 0:
+            return
+        n_new = n - nout + nin
+        self._ensure_capacity(n_new)
+        if nin >= nout:
+            rows = torch.cat([holes, torch.arange(n, n_new, dtype=torch.int64, device=dev)])
+            ops.unpack_rows(recvbuf.contiguous(), rows, self.pos, self.vel, self.ids)
+        else:
+            low = holes[holes < n_new]           # holes that stay inside the shrunken array
+            ops.unpack_rows(recvbuf.contiguous(), low[:nin].contiguous(), self.pos, self.vel, self.ids)
+            dst = low[nin:].contiguous()
+            if dst.numel():
+                # stayers living in the tail [n_new, n) move into the remaining holes
+                tail = torch.ones((n - n_new,), dtype=torch.bool, device=dev)
+                tail[holes[holes >= n_new] - n_new] = False
+                src = torch.nonzero(tail).flatten() + n_new
+                assert src.numel() == dst.numel(), (src.numel(), dst.numel())
+                ops.move_rows(src.contiguous(), dst, self.pos, self.vel, self.ids)
+        self.np = n_new
+
     # -- Poisson solve on the slab
     def fft_poisson(self, rhs_planes, out_planes, param):
         """solver.fft (solver.py:452-523) with the transposed slab FFT.  rhs_planes [nxl,N,N] is consumed;
@@ -600,8 +738,10 @@ class Slab:
         else:
             param["parametrized_mu_z"] = np.float32(1)
         n = self.np
+        self._mark("migrate")
         binned = ops.bin(self.pos[:n])
         rho = ops.deposit(binned, scheme)                      # [nxl + 2, N, N] raw sums
+        self._mark("bin+deposit")
         from_left, from_right = comm.exchange_planes(rho[0:1], rho[nxl + 1:nxl + 2])
         rho[1] += from_left[0]         # the left neighbour's plane nxl + 1 is my first owned plane
         rho[nxl] += from_right[0]      # the right neighbour's plane 0 is my last owned plane
@@ -611,25 +751,33 @@ class Slab:
             ops.affine(rhs, conversion, 0.0)
         f1 = np.float32(1.5 * param["aexp"] * param["Om_m"] * param["parametrized_mu_z"])
         ops.affine(rhs, f1, -f1)
+        self._mark("density ghosts+rhs")
         G = 1 + _REACH[order]
         if nxl < G:
             raise ValueError(f"slab of {nxl} planes is thinner than the {G} ghost planes the stencils need")
         phi_g = torch.empty((nxl + 2 * G, N, N), dtype=torch.float32, device=rho.device)
         self.fft_poisson(rhs, phi_g[G:G + nxl], param)
         del rho, rhs
+        self._mark("fft solve (2 transposes)")
         from_left, from_right = comm.exchange_planes(phi_g[G:2 * G], phi_g[nxl:nxl + G])
         phi_g[:G] = from_left          # the left neighbour's last G owned planes
         phi_g[nxl + G:] = from_right   # the right neighbour's first G owned planes
         half_dt = 0.0 if kick is None else kick
+        self._mark("potential ghosts")
         mx = ops.interp_kick_phi(phi_g, G, order, binned, self.vel[:n] if kick is not None else None,
                                  self.acc[:n], scheme, half_dt)
         self.potential = phi_g[G:G + nxl]
         if kick is None:
             mx[1] = ops.max_abs(self.vel[:n])[0]
+        self._mark("gradient+interp+kick")
+        mx = torch.cat([mx, torch.tensor([float(self._mig_want)], dtype=torch.float32, device=mx.device)])
         comm.allreduce_max_(mx)
         m = mx.cpu().numpy()
+        self._mark("allreduce max")
         self.max_acc, self.max_vel = np.float32(m[0]), np.float32(m[1])
-        return mx
+        if self._mig_cap is not None and m[2] > self._mig_cap:
+            self._mig_cap = 2 * int(m[2]) + 4096      # identical on every rank: m[2] is the all-reduced maximum
+        return mx[:2]
 
     # -- integration.integrate / leapfrog on the slab
     def leapfrog(self, dt, tables, param):
@@ -638,6 +786,7 @@ class Slab:
         n = self.np
         half_dt = np.float32(0.5 * dt)
         dt_is_f64 = 0 if isinstance(dt, np.float32) else 1
+        self._mark("start")
         detected = None
         if self.P > 1:
             detected = self.ops.kick_drift_wrap_detect(self.pos[:n], self.vel[:n], self.acc[:n], half_dt, dt,
@@ -649,7 +798,8 @@ class Slab:
         param["aexp"] = np.exp(tables[0](param["t"]))
         logging.info(f"{param['t']=} {param['aexp']=}")
         utils.set_units(param)
-        self.migrate(detected, neighbours_only=True)
+        self._mark("kick+drift+wrap")
+        self.migrate_neighbours(detected)
         self.pm(param, kick=half_dt)
 
     def integrate(self, tables, param, t_snap_next=np.float32(0)):

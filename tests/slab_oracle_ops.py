@@ -57,6 +57,28 @@ class OracleOps:
         rec[:, 6:8] = _np(ids)[r].astype(np.int64).view(np.float32).reshape(-1, 2)
         return torch.from_numpy(rec), torch.from_numpy(r.astype(np.int64))
 
+    def pack_fixed(self, pos, vel, ids, detected, cap):
+        own = self._owner(pos)
+        left, right = (self.rank - 1) % self.P, (self.rank + 1) % self.P
+        status = np.zeros(3, np.int64)
+        send = [np.zeros((cap + 1, REC), np.float32), np.zeros((cap + 1, REC), np.float32)]
+        holes = [np.zeros(cap, np.int64), np.zeros(cap, np.int64)]
+        for side, dest in ((0, left), (1, right)):
+            if side == 1 and right == left:
+                break
+            rows = np.nonzero(own == dest)[0] if dest != self.rank else np.zeros(0, np.int64)
+            status[side] = rows.size
+            rows = rows[:cap]
+            send[side][1:1 + rows.size, 0:3] = _np(pos)[rows]
+            send[side][1:1 + rows.size, 3:6] = _np(vel)[rows]
+            send[side][1:1 + rows.size, 6:8] = _np(ids)[rows].astype(np.int64).view(np.float32).reshape(-1, 2)
+            holes[side][:rows.size] = rows
+        status[2] = int(((own != self.rank) & (own != left) & (own != right)).sum())
+        for side in (0, 1):
+            send[side][0, 0:2] = np.array([status[side]], np.int64).view(np.float32)
+        return (torch.from_numpy(send[0]), torch.from_numpy(send[1]), torch.from_numpy(holes[0]),
+                torch.from_numpy(holes[1]), torch.from_numpy(status))
+
     def _owner(self, pos):
         i = (_np(pos)[:, 0] * np.float32(self.N)).astype(np.int64)
         return np.clip(i // self.nxl, 0, self.P - 1)

@@ -59,6 +59,8 @@ def _run_rank(N, comm, out, reorder_at=None):
                     torch.from_numpy(ids[mine].copy()))
     own = (s.position[:, 0].numpy() * np.float32(N)).astype(np.int64) // (N // P)
     assert (own == r).all()
+    if P == 4:
+        s._mig_cap = 8     # far too small: the first steps must take the overflow (repeat) path
     s.pm(param)
     moved = 0
     for step in range(NSTEPS):
