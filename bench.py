@@ -517,8 +517,8 @@ def run_slab_arm(args):
     for (n0, e0_), (n1, e1_) in zip(marks[:-1], marks[1:]):
         if n1 != "start":   # device time between consecutive phase boundaries (kernels + collectives + bubbles)
             phase_samples.setdefault(n1, []).append(e0_.elapsed_time(e1_))
-    phases = {k: {"mean": float(np.mean(v)), "median": float(np.median(v)), "max": float(np.max(v))}
-              for k, v in phase_samples.items()}
+    phases = {k: {"mean": float(np.mean(v)), "median": float(np.median(v)), "max": float(np.max(v)),
+                  "argmax_step": int(np.argmax(v))} for k, v in phase_samples.items()}
     t_ms_total = ev0.elapsed_time(ev1) + (args.steps / N_REORDER - n_reorders) * t_reorder_ms
     tt = torch.tensor([t_ms_total, float(S.np), float(migrated)], device="cuda", dtype=torch.float64)
     mx = tt.clone()
@@ -610,9 +610,11 @@ def run_slab_arm(args):
             "phases_ms_per_step_rank0": phases,
             "reorder": {"ms": t_reorder_ms, "in_timed_steps": n_reorders, "amortised_over": N_REORDER},
             "multi_gpu": {"decomposition": f"x-slabs of {S.nxl} planes per GPU",
-                          "collectives_per_step": "migration counts + records all-to-all, 2 ghost-plane exchanges "
-                                                  "(density add, potential copy), 2 all-to-all transposes of the "
-                                                  "half-spectrum, all-reduce(max) of 2 floats (NCCL)",
+                          "fft_transposes": "one kernel each, remote stores over NVLink peer memory + inter-GPU barrier"
+                          if S._peer else "NCCL all-to-all",
+                          "collectives_per_step": "1 neighbour exchange of migrants, 2 ghost-plane exchanges (density "
+                                                  "add, potential copy), 2 transposes of the half-spectrum, "
+                                                  "all-reduce(max) of 3 floats",
                           "particles_migrated_per_step": tt[2].item() / args.steps},
         }
         emit(line)

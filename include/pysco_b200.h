@@ -189,6 +189,13 @@ int psc_slab_fft_r2c_planes(void *plan, const float *planes, float *spec2d, void
 int psc_slab_fft_c2r_planes(void *plan, float *spec2d, float *planes, void *stream);
 int psc_slab_fft_x(void *plan, float *spec_t, int inverse, void *stream);
 int psc_slab_yblocks(const float *in, float *out, int N, int nxl, int nyl, int to_blocks, void *stream);
+/* The same transposes as ONE kernel over NVLink peer memory (no pack pass, no NCCL all-to-all): peer_ptrs_dev is a
+ * DEVICE array of P pointers, entry d = rank d's receive buffer mapped into this process (symmetric memory).
+ * forward != 0: in = [nxl][N][N/2+1] -> the destinations' [N][nyl][N/2+1] buffers; forward == 0: in =
+ * [N][nyl][N/2+1] -> the destinations' [nxl][N][N/2+1] buffers.  The caller orders the kernel against the peers'
+ * use of the buffers with inter-GPU barriers (pysco_b200/slab.py). */
+int psc_slab_transpose_put(const float *in, const void *peer_ptrs_dev, int N, int nxl, int nyl, int P, int me,
+                           int forward, void *stream);
 /* psc_green on a y-block of the transposed spectrum [N (kx)][nyl (ky = y0 + .)][N/2+1] */
 int psc_green_slab(float *spec_t, int N, int nyl, int y0, int kind, int p, float scale, void *stream);
 

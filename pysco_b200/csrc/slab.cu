@@ -181,6 +181,37 @@ __global__ void __launch_bounds__(256) yblock_kernel(const float2 *__restrict__ 
   }
 }
 
+// Transposes of the slab FFT as ONE kernel over NVLink peer memory: every rank stores the rows of its spectrum
+// straight into the receive buffers of their destination ranks (peers[d] = rank d's symmetric buffer, mapped into
+// this process), already in the layout the next transform wants.  No pack pass, no staging buffer, no NCCL
+// all-to-all; the self block is an ordinary local copy running at HBM speed alongside the remote stores.
+//   FWD: in [nxl][N][nz] (2-D spectra of my planes) -> peer d = y / nyl gets row (me nxl + x, y - d nyl) of its
+//        [N][nyl][nz] buffer;
+//   !FWD: in [N][nyl][nz] -> peer d = x / nxl gets row (x - d nxl, me nyl + yl) of its [nxl][N][nz] buffer.
+template <bool FWD>
+__global__ void __launch_bounds__(256) slab_put_kernel(const float2 *__restrict__ in, float2 *const *__restrict__ peers,
+                                                       int N, int nxl, int nyl, int nz, int me) {
+  const int64_t nrows = FWD ? (int64_t)nxl * N : (int64_t)N * nyl;
+  const int rows_per_cta = blockDim.x >> 5;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  for (int64_t r = (int64_t)blockIdx.x * rows_per_cta + wid; r < nrows; r += (int64_t)gridDim.x * rows_per_cta) {
+    int d;
+    int64_t drow;
+    if (FWD) {
+      const int y = (int)(r % N), x = (int)(r / N);
+      d = y / nyl;
+      drow = ((int64_t)me * nxl + x) * nyl + (y - d * nyl);
+    } else {
+      const int yl = (int)(r % nyl), x = (int)(r / nyl);
+      d = x / nxl;
+      drow = (int64_t)(x - d * nxl) * N + (int64_t)me * nyl + yl;
+    }
+    const float2 *s = in + r * nz;
+    float2 *t = peers[d] + drow * nz;
+    for (int k = lane; k < nz; k += 32) t[k] = s[k];
+  }
+}
+
 struct SlabFftPlan {
   int N, nxl, nyl;
   cufftHandle r2c, c2r, c2c;
@@ -389,6 +420,23 @@ int psc_slab_fft_x(void *plan, float *spec_t, int inverse, void *stream) {
   cufftComplex *p = reinterpret_cast<cufftComplex *>(spec_t);
   PSC_CUFFT2(cufftExecC2C(pl->c2c, p, p, inverse ? CUFFT_INVERSE : CUFFT_FORWARD));
   count_launch(1);
+  return PSC_OK;
+}
+
+int psc_slab_transpose_put(const float *in, const void *peer_ptrs_dev, int N, int nxl, int nyl, int P, int me,
+                           int forward, void *stream) {
+  PSC_CHECK_ARG(in && peer_ptrs_dev, "null pointer");
+  PSC_CHECK_ARG(N >= 2 && nxl >= 1 && nyl >= 1 && P >= 1 && nxl * P == N && nyl * P == N && me >= 0 && me < P,
+                "bad slab geometry");
+  const int nz = N / 2 + 1;
+  const int64_t nrows = forward ? (int64_t)nxl * N : (int64_t)N * nyl;
+  const int grid = grid_for(nrows * 32, 256, 8);
+  const float2 *i2 = reinterpret_cast<const float2 *>(in);
+  float2 *const *peers = reinterpret_cast<float2 *const *>(peer_ptrs_dev);
+  if (forward) slab_put_kernel<true><<<grid, 256, 0, as_stream(stream)>>>(i2, peers, N, nxl, nyl, nz, me);
+  else slab_put_kernel<false><<<grid, 256, 0, as_stream(stream)>>>(i2, peers, N, nxl, nyl, nz, me);
+  count_launch();
+  PSC_CHECK_LAUNCH();
   return PSC_OK;
 }
 

@@ -24,6 +24,7 @@ product default is CudaOps and nothing here falls back to it silently.
 """
 import ctypes as C
 import logging
+import os
 import threading
 
 import numpy as np
@@ -133,6 +134,30 @@ class TorchComm:
         from_right = torch.empty((n_from_right,) + shape, dtype=to_left.dtype, device=to_left.device)
         self._p2p(to_left, to_right, from_left, from_right)
         return from_left, from_right
+
+    def symmetric_buffers(self, numel, count):
+        """`count` float32 buffers of `numel` elements that every rank can address directly over NVLink
+        (torch symmetric memory: CUDA VMM allocations exchanged at a rendezvous).  Returns [(tensor, handle)] --
+        handle.buffer_ptrs_dev is the device array of the P peer pointers, handle.barrier() an inter-GPU barrier on
+        the current stream -- or None when peer memory is unavailable (the caller then uses the NCCL all-to-all).
+        Collective: every rank must call it."""
+        if dist.get_backend(self.group) != "nccl" or os.environ.get("PSC_NO_PEER_MEMORY"):
+            return None
+        out = []
+        ok = 1.0
+        try:
+            import torch.distributed._symmetric_memory as symm_mem
+            dev = torch.device("cuda", torch.cuda.current_device())
+            for _ in range(count):
+                t = symm_mem.empty(int(numel), dtype=torch.float32, device=dev)
+                h = symm_mem.rendezvous(t, self.group if self.group is not None else dist.group.WORLD)
+                out.append((t, h))
+        except Exception as e:  # noqa: BLE001
+            logging.warning(f"peer memory unavailable ({type(e).__name__}: {e}); using NCCL all-to-all transposes")
+            ok = 0.0
+        flag = torch.tensor([ok], dtype=torch.float32, device="cuda")
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
+        return out if flag.item() > 0 else None
 
     def allreduce_max_(self, t):
         dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
@@ -402,6 +427,10 @@ class CudaOps:
         _lib.check(self.lib.psc_slab_yblocks(_lib.ptr(src), _lib.ptr(dst), self.N, self.nxl, self.nyl,
                                              int(to_blocks), _lib.stream()))
 
+    def transpose_put(self, src, peer_ptrs_dev, forward):
+        _lib.check(self.lib.psc_slab_transpose_put(_lib.ptr(src), int(peer_ptrs_dev), self.N, self.nxl, self.nyl,
+                                                   self.P, self.rank, int(forward), _lib.stream()))
+
     def fft_x(self, spec_t, inverse):
         _lib.check(self.lib.psc_slab_fft_x(self._fft_plan(), _lib.ptr(spec_t), int(inverse), _lib.stream()))
 
@@ -440,6 +469,7 @@ class Slab:
         self.potential = None  # owned planes [nxl, N, N] of the last solve (a view into the ghosted array)
         self.migrated_last = (0, 0)
         self._warm_host_ops()
+        self._peer = None         # symmetric (peer-addressable) spectrum buffers, resolved at the first solve
         self._mig_cap = None      # records per direction of the fixed-capacity migration buffers (same on all ranks)
         self._mig_want = 0        # largest message of the last migration; all-reduced in pm() to resize _mig_cap
         self.phase_marks = None   # bench.py: list of (phase name, CUDA event) recorded at phase boundaries
@@ -687,6 +717,16 @@ class Slab:
                 ops.move_rows(src.contiguous(), dst, self.pos, self.vel, self.ids)
         self.np = n_new
 
+    def _peer_buffers(self):
+        """Two symmetric spectrum buffers (receive sides of the two transposes), or None."""
+        if self._peer is None:
+            fn = getattr(self.comm, "symmetric_buffers", None)
+            bufs = None
+            if fn is not None and isinstance(self.ops, CudaOps) and self.P > 1:
+                bufs = fn(self.nxl * self.N * (self.N // 2 + 1) * 2, 2)
+            self._peer = bufs if bufs else False
+        return self._peer or None
+
     # -- Poisson solve on the slab
     def fft_poisson(self, rhs_planes, out_planes, param):
         """solver.fft (solver.py:452-523) with the transposed slab FFT.  rhs_planes [nxl,N,N] is consumed;
@@ -701,6 +741,22 @@ class Slab:
         else:
             raise NotImplementedError(f"slab path: linear_newton_solver={param['linear_newton_solver']!r}, "
                                       "should be 'fft' or 'fft_7pt'")
+        peer = self._peer_buffers()
+        if peer is not None:
+            # transposes as one kernel each over NVLink peer memory (csrc/slab.cu: slab_put_kernel)
+            (A, hA), (B, hB) = peer
+            a = ops.spectrum_buffer()
+            ops.fft2d_r2c(rhs_planes, a)                        # [nxl][N][nz]
+            ops.transpose_put(a, hA.buffer_ptrs_dev, True)      # -> every rank's A = [N][nyl][nz]
+            del a
+            hA.barrier(channel=0)
+            ops.fft_x(A, False)
+            ops.green(A, kind, pp, 1.0 / float(self.N) ** 3)
+            ops.fft_x(A, True)
+            ops.transpose_put(A, hB.buffer_ptrs_dev, False)     # -> every rank's B = [nxl][N][nz]
+            hB.barrier(channel=0)
+            ops.fft2d_c2r(B, out_planes)
+            return
         a = ops.spectrum_buffer()
         b = ops.spectrum_buffer()
         ops.fft2d_r2c(rhs_planes, a)            # [nxl][N][nz]
