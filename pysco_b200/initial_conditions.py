@@ -1,0 +1,409 @@
+"""Mirror of pysco/initial_conditions.py: LPT initial conditions (1LPT / 2LPT / 3LPT) on the device.
+
+SURVEY 8(f) rank 1 -- the row after the hot path: it is what `main.run` needs to start from the shipped
+`examples/param.ini` (`initial_conditions = 2LPT`).  One-off setup, not part of the per-step path, so it is built
+from device-resident torch tensors and cuFFT through `torch.fft` (no hand-written kernels): the white noise is drawn
+on the host with the SAME NumPy generator calls, in the same order, as the reference (initial_conditions.py:615-616,
+636-655), everything after it -- transfer multiply, inverse Laplacian, spectral gradients / Hessians, the 2LPT and
+3LPT sources, displacements -- runs on the GPU in complex64 / float32 like the reference.
+
+    generate                      initial_conditions.py:25-213
+    generate_density_fourier      :401-445        get_transfer_grid :530-576
+    white_noise_fourier[_fixed]   :579-722
+    compute_2ndorder_rhs          :976-1039       compute_3{a,b,c_Ax,c_Ay,c_Az}_{rhs,displacement} :1042-1632
+    initialise_1LPT_{center,edge} :1681-1799      add_nLPT :1802-1855     pad / trim :1858-1927
+    fourier.gradient / hessian / sum_of_hessian / diff_of_hessian / gradient_inverse_laplacian (fourier.py:606-960)
+"""
+import logging
+import math
+
+import numpy as np
+import torch
+
+from . import _lib, iostream, utils
+
+_PC = 3.0856775814913673e16  # astropy.constants.pc (m)
+
+
+# ------------------------------------------------------------------------------------------ white noise (host)
+def _hermitian_fill(upper, middle, N):
+    """The full [N,N,N] array the reference's sequential loops leave behind (initial_conditions.py:620-635):
+    density[i,j,k] = upper[i,j,k] and density[-i,-j,-k] = conj(upper[i,j,k]) for i in 0..middle, later writes
+    winning.  Only the half k <= middle is used downstream; it is returned as [N, N, middle + 1]."""
+    nz = middle + 1
+    out = np.empty((N, N, nz), dtype=np.complex64)
+    # planes 0 < i < middle: written once as "upper"; planes N - i: conj(upper[i, -j, -k])
+    out[1:middle] = upper[1:middle, :, :nz]
+    neg = (-np.arange(N)) % N
+    for i in range(1, middle):
+        out[N - i] = np.conj(upper[i][neg][:, neg][:, :nz])
+    # self-conjugate planes i = 0 and i = middle: entry e = (j, k) and its partner p = (-j, -k) are both written at
+    # iteration e and at iteration p; the later iteration (lexicographic j, k) wins and leaves upper at its own
+    # index, conj(upper) at the partner (for e == p the conjugate is written last)
+    jj, kk = np.meshgrid(np.arange(N), np.arange(N), indexing="ij")
+    order_e = jj * N + kk
+    order_p = neg[jj] * N + neg[kk]
+    for i0 in (0, middle):
+        u = upper[i0]
+        conj_partner = np.conj(u[neg][:, neg])
+        plane = np.where(order_e > order_p, u, conj_partner)
+        out[i0] = plane[:, :nz]
+    return out
+
+
+def white_noise_fourier(N, rng):
+    """initial_conditions.py:585-655 (Rayleigh amplitudes, uniform phases); half-spectrum [N, N, N/2+1]"""
+    middle = N // 2
+    twopi = np.float32(2 * math.pi)
+    one = np.float32(1)
+    amp = rng.random((middle + 1, N, N), dtype=np.float32)
+    pha = rng.random((middle + 1, N, N), dtype=np.float32)
+    phase = twopi * pha
+    amplitude = np.sqrt(-np.log(one - amp))
+    upper = (amplitude * np.cos(phase) + 1j * (amplitude * np.sin(phase))).astype(np.complex64)
+    del amp, pha, phase, amplitude
+    d = _hermitian_fill(upper, middle, N)
+    d[0, 0, 0] = 0
+    for idx in ((0, 0, middle), (0, middle, 0), (0, middle, middle), (middle, 0, 0), (middle, 0, middle),
+                (middle, middle, 0), (middle, middle, middle)):
+        v = np.float32(math.sqrt(-math.log(one - rng.random(dtype=np.float32))))
+        if idx[2] <= middle:
+            d[idx] = v
+    return d
+
+
+def white_noise_fourier_fixed(N, rng, is_paired):
+    """initial_conditions.py:664-722 (unit amplitudes; paired: phases shifted by pi)"""
+    middle = N // 2
+    twopi = np.float32(2 * np.pi)
+    shift = np.float32(math.pi) if is_paired else np.float32(0)
+    pha = rng.random((middle + 1, N, N), dtype=np.float32)
+    phase = twopi * pha + shift
+    upper = (np.cos(phase) + 1j * np.sin(phase)).astype(np.complex64)
+    d = _hermitian_fill(upper, middle, N)
+    d[0, 0, 0] = 0
+    for idx in ((0, 0, middle), (0, middle, 0), (0, middle, middle), (middle, 0, 0), (middle, 0, middle),
+                (middle, middle, 0), (middle, middle, middle)):
+        d[idx] = 1
+    return d
+
+
+def get_transfer_grid(param):
+    """initial_conditions.py:531-576: sqrt(P(k)) N^3 / L^1.5 interpolated on the grid (float64), half grid only"""
+    k, Pk = np.loadtxt(param["power_spectrum_file"]).T
+    N = int(round(param["npart"] ** (1.0 / 3)))
+    if param["npart"] != N ** 3:
+        raise ValueError(f"{math.cbrt(param['npart'])=}, should be integer")
+    kf = 2 * np.pi / param["boxlen"]
+    k_dimensionless = k / kf
+    sqrtPk = (np.sqrt(Pk / param["boxlen"] ** 3) * N ** 3).astype(np.float32)
+    k_1d = np.fft.fftfreq(N, 1 / N)
+    kz = k_1d[: N // 2 + 1]      # the reference builds the full grid; only k <= N/2 is read afterwards
+    k_grid = np.sqrt(kz[np.newaxis, np.newaxis, :] ** 2 + k_1d[:, np.newaxis, np.newaxis] ** 2
+                     + k_1d[np.newaxis, :, np.newaxis] ** 2)
+    return np.interp(k_grid, k_dimensionless, sqrtPk)
+
+
+def generate_density_fourier(param):
+    """initial_conditions.py:402-445 -> device complex64 [N, N, N/2+1]"""
+    transfer = get_transfer_grid(param)
+    N = transfer.shape[0]
+    seed = param["seed"]
+    rng = np.random.default_rng() if seed < 0 else np.random.default_rng(seed)
+    if param["fixed_ICS"]:
+        d = white_noise_fourier_fixed(N, rng, param["paired_ICS"])
+    else:
+        d = white_noise_fourier(N, rng)
+    d = (d * transfer).astype(np.complex64)   # complex64 *= float64, rounded once like the reference
+    return torch.from_numpy(np.ascontiguousarray(d)).to(_lib.device())
+
+
+# ------------------------------------------------------------------------------------------ spectral operators
+def _kvec(N, dev):
+    """signed integer wave numbers with index >= N/2 -> index - N (fourier.py:754-766), as float32 [N], [N/2+1]"""
+    i = torch.arange(N, device=dev)
+    kfull = torch.where(i >= N // 2, i - N, i).to(torch.float32)
+    kz = torch.arange(N // 2 + 1, device=dev, dtype=torch.float32)
+    return kfull, kz
+
+
+def _k_of(axis, N, dev):
+    kfull, kz = _kvec(N, dev)
+    if axis == 0:
+        return kfull[:, None, None]
+    if axis == 1:
+        return kfull[None, :, None]
+    return kz[None, None, :]
+
+
+def inverse_laplacian(x):
+    """fourier.inverse_laplacian (fourier.py:460-491) on a half-spectrum, in place"""
+    N = x.shape[0]
+    kfull, kz = _kvec(N, x.device)
+    k2 = kfull[:, None, None] ** 2 + kfull[None, :, None] ** 2 + kz[None, None, :] ** 2
+    invpi2 = np.float32(-0.25 / np.pi ** 2)
+    k2[0, 0, 0] = 1.0
+    x *= (invpi2 / k2)
+    x[0, 0, 0] = 0
+    return x
+
+
+def gradient(x):
+    """fourier.gradient (fourier.py:730-770): i 2 pi k_j x -> [N, N, N/2+1, 3]"""
+    N = x.shape[0]
+    tmp = x * torch.complex(torch.zeros((), device=x.device), torch.tensor(np.float32(2 * np.pi), device=x.device))
+    return torch.stack([tmp * _k_of(a, N, x.device) for a in range(3)], dim=-1)
+
+
+def hessian(x, ij):
+    """fourier.hessian (fourier.py:784-832): -k_n k_m 4 pi^2 x"""
+    N = x.shape[0]
+    fourpi2 = np.float32(4 * np.pi ** 2)
+    return x * (-(_k_of(ij[0], N, x.device) * _k_of(ij[1], N, x.device)) * fourpi2)
+
+
+def sum_of_hessian(x, ij1, ij2, sign=1.0):
+    """fourier.sum_of_hessian / diff_of_hessian (fourier.py:842-960): -(k k +- k k) 4 pi^2 x"""
+    N = x.shape[0]
+    fourpi2 = np.float32(4 * np.pi ** 2)
+    dev = x.device
+    kk = _k_of(ij1[0], N, dev) * _k_of(ij1[1], N, dev) + sign * (_k_of(ij2[0], N, dev) * _k_of(ij2[1], N, dev))
+    return x * (-kk * fourpi2)
+
+
+def diff_of_hessian(x, ij1, ij2):
+    return sum_of_hessian(x, ij1, ij2, sign=-1.0)
+
+
+def gradient_inverse_laplacian(x):
+    """fourier.gradient_inverse_laplacian (fourier.py:606-653): -i k_j / (2 pi k^2) x, DC = 0"""
+    N = x.shape[0]
+    dev = x.device
+    kfull, kz = _kvec(N, dev)
+    k2 = kfull[:, None, None] ** 2 + kfull[None, :, None] ** 2 + kz[None, None, :] ** 2
+    k2[0, 0, 0] = 1.0
+    invtwopi = np.float32(0.5 / np.pi)
+    tmp = x * torch.complex(torch.zeros((), device=dev), -(invtwopi / k2))
+    out = torch.stack([tmp * _k_of(a, N, dev) for a in range(3)], dim=-1)
+    out[0, 0, 0, :] = 0
+    return out
+
+
+def ifft_3D_real(x):
+    N = x.shape[0]
+    return torch.fft.irfftn(x, s=(N, N, N), dim=(0, 1, 2))
+
+
+def fft_3D_real(x):
+    return torch.fft.rfftn(x, dim=(0, 1, 2))
+
+
+def ifft_3D_real_grad(x):
+    N = x.shape[0]
+    return torch.fft.irfftn(x, s=(N, N, N), dim=(0, 1, 2)).contiguous()
+
+
+def pad(x):
+    """initial_conditions.py:1859-1893 (Orszag 3/2 rule)"""
+    N = x.shape[0]
+    Ne, m = 3 * N // 2, N // 2
+    out = torch.zeros((Ne, Ne, Ne // 2 + 1), dtype=x.dtype, device=x.device)
+    out[:m, :m, :m] = x[:m, :m, :m]
+    out[-m + 1:, :m, :m] = x[-m + 1:, :m, :m]
+    out[:m, -m + 1:, :m] = x[:m, -m + 1:, :m]
+    out[-m + 1:, -m + 1:, :m] = x[-m + 1:, -m + 1:, :m]
+    return out
+
+
+def trim(x):
+    """initial_conditions.py:1897-1927"""
+    Ne = x.shape[0]
+    N = 2 * Ne // 3
+    m = N // 2
+    out = torch.zeros((N, N, m + 1), dtype=x.dtype, device=x.device)
+    out[:m, :m, :m] = x[:m, :m, :m]
+    out[-m + 1:, :m, :m] = x[-m + 1:, :m, :m]
+    out[:m, -m + 1:, :m] = x[:m, -m + 1:, :m]
+    out[-m + 1:, -m + 1:, :m] = x[-m + 1:, -m + 1:, :m]
+    return out
+
+
+def _real(x, ij):
+    return ifft_3D_real(hessian(x, ij))
+
+
+def _dealias_in(param, *fields):
+    return [pad(f) for f in fields] if param["dealiased_ICS"] else list(fields)
+
+
+def _dealias_out(param, phi, power):
+    if param["dealiased_ICS"]:
+        phi = ifft_3D_real(trim(fft_3D_real(phi)))
+        phi = phi * np.float32(1.5 ** power)
+    return phi
+
+
+# ------------------------------------------------------------------------------------------ LPT sources
+def compute_2ndorder_rhs(phi1, param):
+    """initial_conditions.py:976-1039"""
+    (p1,) = _dealias_in(param, phi1)
+    phi2 = _real(p1, (0, 0)) * ifft_3D_real(sum_of_hessian(p1, (1, 1), (2, 2)))
+    phi2 += _real(p1, (1, 1)) * _real(p1, (2, 2))
+    for ij in ((0, 1), (0, 2), (1, 2)):
+        t = _real(p1, ij)
+        phi2 -= t * t
+    return _dealias_out(param, phi2, 3)
+
+
+def compute_3a_rhs(phi1, param):
+    """initial_conditions.py:1042-1121"""
+    (p1,) = _dealias_in(param, phi1)
+    h = {ij: _real(p1, ij) for ij in ((0, 0), (1, 1), (2, 2), (0, 1), (0, 2), (1, 2))}
+    phi = h[0, 0] * h[1, 1] * h[2, 2]
+    phi += np.float32(2) * h[0, 1] * h[0, 2] * h[1, 2]
+    phi -= h[1, 2] * h[1, 2] * h[0, 0]
+    phi -= h[0, 2] * h[0, 2] * h[1, 1]
+    phi -= h[0, 1] * h[0, 1] * h[2, 2]
+    return _dealias_out(param, phi, 6)
+
+
+def compute_3b_rhs(phi1, phi2, param):
+    """initial_conditions.py:1162-1246"""
+    p1, p2 = _dealias_in(param, phi1, phi2)
+    half = np.float32(0.5)
+    phi = _real(p1, (0, 0)) * (half * ifft_3D_real(sum_of_hessian(p2, (1, 1), (2, 2))))
+    phi += half * _real(p1, (1, 1)) * ifft_3D_real(sum_of_hessian(p2, (0, 0), (2, 2)))
+    phi += half * _real(p1, (2, 2)) * ifft_3D_real(sum_of_hessian(p2, (0, 0), (1, 1)))
+    for ij in ((0, 1), (0, 2), (1, 2)):
+        phi -= _real(p1, ij) * _real(p2, ij)
+    return _dealias_out(param, phi, 3)
+
+
+def _compute_3c_rhs(phi1, phi2, param, a, b, c, d1, d2):
+    """Common form of compute_3c_A{x,y,z}_rhs (initial_conditions.py:1290-1591):
+    H1[a] H2[b] - H2[a] H1[b] + H1[c] (H2[d1] - H2[d2]) - H2[c] (H1[d1] - H1[d2])"""
+    p1, p2 = _dealias_in(param, phi1, phi2)
+    phi = _real(p1, a) * _real(p2, b)
+    phi -= _real(p2, a) * _real(p1, b)
+    phi += _real(p1, c) * ifft_3D_real(diff_of_hessian(p2, d1, d2))
+    phi -= _real(p2, c) * ifft_3D_real(diff_of_hessian(p1, d1, d2))
+    return _dealias_out(param, phi, 3)
+
+
+def compute_3c_Ax_rhs(phi1, phi2, param):
+    return _compute_3c_rhs(phi1, phi2, param, (0, 2), (0, 1), (1, 2), (1, 1), (2, 2))
+
+
+def compute_3c_Ay_rhs(phi1, phi2, param):
+    return _compute_3c_rhs(phi1, phi2, param, (0, 1), (1, 2), (0, 2), (2, 2), (0, 0))
+
+
+def compute_3c_Az_rhs(phi1, phi2, param):
+    return _compute_3c_rhs(phi1, phi2, param, (1, 2), (0, 2), (0, 1), (0, 0), (1, 1))
+
+
+def _displacement(rhs):
+    """fft -> gradient_inverse_laplacian -> inverse fft (initial_conditions.py:1124-1160 and siblings)"""
+    return ifft_3D_real_grad(gradient_inverse_laplacian(fft_3D_real(rhs)))
+
+
+# ------------------------------------------------------------------------------------------ particles
+def initialise_1LPT(psi, dplus_1, fH, param):
+    """initial_conditions.py:1635-1799: lattice (cell centres or edges) minus D1 psi; velocity -D1 f H psi"""
+    POSITION = param["position_ICS"].casefold()
+    if POSITION not in ("center", "edge"):
+        raise NotImplementedError(f"{POSITION=}, should be 'center' or 'edge'")
+    N = psi.shape[0]
+    h = np.float32(1.0 / N)
+    half_h = np.float32(0.5 / N) if POSITION == "center" else np.float32(0)
+    ax = half_h + torch.arange(N, device=psi.device, dtype=torch.float32) * h
+    grid = torch.stack(torch.meshgrid(ax, ax, ax, indexing="ij"), dim=-1)
+    dfH = np.float32(dplus_1 * fH)
+    position = grid + np.float32(dplus_1) * (-psi)
+    velocity = dfH * (-psi)
+    return position, velocity
+
+
+def add_nLPT(position, velocity, psi, dplus_n, fH_n):
+    """initial_conditions.py:1809-1855"""
+    position += np.float32(dplus_n) * psi
+    velocity += np.float32(dplus_n * fH_n) * psi
+
+
+def finalise_initial_conditions(position, velocity, param, do_reorder):
+    """initial_conditions.py:216-280: wrap (+ reorder) and write snapshot 0"""
+    if "base" not in param:
+        raise ValueError(f"{param.index=}, should contain 'base'")
+    utils.periodic_wrap(position)
+    if do_reorder:
+        position, velocity = utils.reorder_particles(position, velocity)
+    fmt = param["output_snapshot_format"].casefold()
+    if fmt == "parquet":
+        snap_name = f"{param['base']}/output_00000/particles_{param['extra']}.parquet"
+        iostream.write_snapshot_particles_parquet(snap_name, position, velocity)
+        param.to_csv(f"{param['base']}/output_00000/param_{param['extra']}.txt", sep="=", header=False)
+    elif fmt == "hdf5":
+        raise NotImplementedError("output_snapshot_format = HDF5 needs h5py (absent in this image); use parquet")
+    else:
+        raise NotImplementedError(f"{param['output_snapshot_format']=}, should be 'parquet' or 'hdf5'")
+    logging.warning(f"Write initial snapshot...{snap_name=}")
+    return position, velocity
+
+
+def generate(param, tables, write_snapshot=True):
+    """initial_conditions.py:25-213 for initial_conditions in {1LPT, 2LPT, 3LPT}.  Returns device tensors
+    (position, velocity) [Npart, 3] in the reference's lattice (lexicographic) order."""
+    IC = param["initial_conditions"]
+    if not (isinstance(IC, str) and "lpt" in IC.casefold()):
+        raise ValueError(f"{IC=}, should be 1LPT, 2LPT or 3LPT")
+    order = IC.casefold()
+    if order not in ("1lpt", "2lpt", "3lpt"):
+        raise ValueError(f"INITIAL_CONDITIONS={IC!r}, should be 1LPT, 2LPT or 3LPT")
+    a_start = 1.0 / (1 + param["z_start"])
+    lna_start = np.log(a_start)
+    logging.warning(f"{param['z_start']=}")
+    Hz = tables[2](lna_start)
+    mpc_to_km = 1e3 * _PC
+    Hz = Hz * param["unit_t"] / mpc_to_km  # km/s/Mpc to BU
+
+    phi1 = inverse_laplacian(generate_density_fourier(param))
+    psi1 = ifft_3D_real_grad(gradient(phi1))
+    logging.warning("Compute 1LPT contribution")
+    dplus_1_z0 = tables[3](0)
+    dplus_1 = np.float32(tables[3](lna_start) / dplus_1_z0)
+    fH_1 = np.float32(tables[4](lna_start) * Hz)
+    position, velocity = initialise_1LPT(psi1, dplus_1, fH_1, param)
+    del psi1
+
+    def done():
+        pos = position.reshape(param["npart"], 3).contiguous()
+        vel = velocity.reshape(param["npart"], 3).contiguous()
+        if write_snapshot:
+            finalise_initial_conditions(pos, vel, param, do_reorder=False)
+        else:
+            utils.periodic_wrap(pos)
+        return pos, vel
+
+    if order == "1lpt":
+        return done()
+    logging.warning("Compute 2LPT contribution")
+    phi2 = inverse_laplacian(fft_3D_real(compute_2ndorder_rhs(phi1, param)))
+    psi2 = ifft_3D_real_grad(gradient(phi2))
+    dplus_2 = np.float32(tables[5](lna_start) / dplus_1_z0 ** 2)
+    fH_2 = np.float32(tables[6](lna_start) * Hz)
+    add_nLPT(position, velocity, psi2, dplus_2, fH_2)
+    del psi2
+    if order == "2lpt":
+        return done()
+    dplus_3a = -np.float32(tables[7](lna_start) / dplus_1_z0 ** 3)
+    fH_3a = np.float32(tables[8](lna_start) * Hz)
+    dplus_3b = -np.float32(tables[9](lna_start) / dplus_1_z0 ** 3)
+    fH_3b = np.float32(tables[10](lna_start) * Hz)
+    dplus_3c = -np.float32(tables[11](lna_start) / dplus_1_z0 ** 3)
+    fH_3c = np.float32(tables[12](lna_start) * Hz)
+    logging.warning("Compute 3LPT contributions")
+    add_nLPT(position, velocity, _displacement(compute_3a_rhs(phi1, param)), dplus_3a, fH_3a)
+    add_nLPT(position, velocity, _displacement(compute_3b_rhs(phi1, phi2, param)), dplus_3b, fH_3b)
+    for rhs in (compute_3c_Ax_rhs, compute_3c_Ay_rhs, compute_3c_Az_rhs):
+        add_nLPT(position, velocity, _displacement(rhs(phi1, phi2, param)), dplus_3c, fH_3c)
+    return done()

@@ -72,12 +72,24 @@ def write_snapshot_particles(position, velocity, param) -> None:
     logging.warning(f"Snapshot written at ...{filename=} {param['aexp']=}")
 
 
+def write_snapshot_particles_parquet(filename: str, position, velocity) -> None:
+    """iostream.py:185-214"""
+    import pyarrow as pa
+    import pyarrow.parquet as pq
+    position, velocity = _host(position), _host(velocity)
+    os.makedirs(os.path.dirname(filename), exist_ok=True)
+    pq.write_table(pa.table({"x": position[:, 0], "y": position[:, 1], "z": position[:, 2],
+                             "vx": velocity[:, 0], "vy": velocity[:, 1], "vz": velocity[:, 2]}), filename)
+
+
 def read_snapshot_particles_parquet(filename: str):
     """iostream.py:111-133"""
     import pyarrow.parquet as pq
-    position = np.ascontiguousarray(np.array(pq.read_table(filename, columns=["x", "y", "z"])).T)
-    velocity = np.ascontiguousarray(np.array(pq.read_table(filename, columns=["vx", "vy", "vz"])).T)
-    return position, velocity
+    def cols(names):
+        t = pq.read_table(filename, columns=names)
+        return np.ascontiguousarray(np.stack([np.asarray(t.column(n)) for n in names], axis=1))   # [Npart, 3]
+
+    return cols(["x", "y", "z"]), cols(["vx", "vy", "vz"])
 
 
 def parse_z_out(param):

@@ -2,10 +2,10 @@
 PM step, and the ``-c param.ini`` command line (main.py:159-169).
 
 Scope: the per-step path (integration.integrate -> solver.pm, Morton reorder every
-n_reorder steps, snapshots) runs on the GPU.  Initial conditions are one-off setup and out of scope
-this round: ``run`` takes them from ``initial_state=(position, velocity)``, from a
-snapshot number (``initial_conditions = <int>``, parquet) or from an ``.npz`` file holding
-``position``/``velocity``; LPT generation raises NotImplementedError.
+n_reorder steps, snapshots) runs on the GPU.  Initial conditions: 1LPT / 2LPT / 3LPT generation on the
+device (pysco_b200/initial_conditions.py), ``initial_state=(position, velocity)``, a snapshot number
+(``initial_conditions = <int>``, parquet) or an ``.npz`` file holding ``position``/``velocity``; the
+RayGal ``.h5`` and Gadget readers (h5py / readgadget are not in this image) raise NotImplementedError.
 """
 import logging
 import os
@@ -18,10 +18,13 @@ import torch
 from . import _lib, cosmotable, integration, iostream, solver, utils
 
 
-def _initial_state(param, initial_state):
+def _initial_state(param, initial_state, tables):
     if initial_state is not None:
         return initial_state
     ic = param["initial_conditions"]
+    if isinstance(ic, str) and ic.casefold() in ("1lpt", "2lpt", "3lpt"):
+        from . import initial_conditions
+        return initial_conditions.generate(param, tables)
     if isinstance(ic, (int, np.integer)):
         # restart from snapshot i (initial_conditions.py:79-107), parquet flavour
         d = f"{param['base']}/output_{int(ic):05d}"
@@ -35,8 +38,9 @@ def _initial_state(param, initial_state):
         z = np.load(ic)
         return z["position"].astype(np.float32), z["velocity"].astype(np.float32)
     raise NotImplementedError(
-        f"initial_conditions={ic!r}: LPT initial-condition generation is outside the B200 hot path "
-        "(SURVEY 8f); pass initial_state=(position, velocity), a snapshot number or an .npz file")
+        f"initial_conditions={ic!r}: should be 1LPT, 2LPT, 3LPT, a snapshot number or an .npz file "
+        "(the reference's RayGal .h5 and Gadget readers need h5py / readgadget, absent here); "
+        "or pass initial_state=(position, velocity)")
 
 
 def run(param, initial_state=None):
@@ -83,14 +87,17 @@ def run(param, initial_state=None):
     utils.set_units(param)
     if "nsteps" not in param.index:
         param["nsteps"] = 0
-    position, velocity = _initial_state(param, initial_state)
+    position, velocity = _initial_state(param, initial_state, tables)
     utils.set_units(param)
     param["t"] = tables[1](np.log(param["aexp"]))
     logging.warning(f"{param['aexp']=} {param['t']=}")
 
     dev = _lib.device()
-    position = torch.as_tensor(np.ascontiguousarray(position), dtype=torch.float32).to(dev).contiguous()
-    velocity = torch.as_tensor(np.ascontiguousarray(velocity), dtype=torch.float32).to(dev).contiguous()
+    if not isinstance(position, torch.Tensor):
+        position = torch.as_tensor(np.ascontiguousarray(position), dtype=torch.float32)
+        velocity = torch.as_tensor(np.ascontiguousarray(velocity), dtype=torch.float32)
+    position = position.to(dev, torch.float32).contiguous()
+    velocity = velocity.to(dev, torch.float32).contiguous()
     acceleration, potential, additional_field = solver.pm(position, param)
     aexp_out = 1.0 / (np.array(z_out) + 1)
     aexp_out.sort()

@@ -185,3 +185,43 @@ def run_param(base, solver_name, ncoarse=5):
         "linear_newton_solver": solver_name, "gradient_stencil_order": 5, "Npre": 2, "Npost": 1, "epsrel": 1e-2,
         "verbose": 0,
     }
+
+
+# ---------------------------------------------------------------------------------------- initial conditions
+def ic_pk_table():
+    """A smooth LCDM-like P(k) table (k in h/Mpc, P in (Mpc/h)^3) written to a temporary file by the IC tests and by
+    make_golden.py, so that neither needs the reference's data files at run time."""
+    k = np.logspace(-4, 2, 400)
+    q = k / 0.2
+    T = np.log(1 + 2.34 * q) / (2.34 * q) * (1 + 3.89 * q + (16.1 * q) ** 2 + (5.46 * q) ** 3 + (6.71 * q) ** 4) ** -0.25
+    return k, 2.0e4 * k ** 0.96 * T ** 2
+
+
+def ic_pk_file(base):
+    import os
+    os.makedirs(base, exist_ok=True)
+    path = os.path.join(base, "pk_test.dat")
+    k, P = ic_pk_table()
+    np.savetxt(path, np.c_[k, P])
+    return path
+
+
+def ic_param(base, **over):
+    p = {
+        "initial_conditions": "2LPT", "z_start": 49.0, "theory": "newton", "H0": 72.0, "Om_m": 0.25733,
+        "T_cmb": 2.726, "N_eff": 3.044, "w0": -1.0, "wa": 0.0, "base": base, "extra": "test",
+        "power_spectrum_file": ic_pk_file(base), "boxlen": 100, "npart": 16 ** 3, "seed": 42,
+        "fixed_ICS": False, "paired_ICS": False, "dealiased_ICS": False, "position_ICS": "center",
+        "output_snapshot_format": "parquet", "nthreads": 1, "parametrized_mu0": 0.0, "verbose": 0,
+    }
+    p.update(over)
+    return p
+
+
+IC_CASES = {
+    "lpt1_edge": dict(initial_conditions="1LPT", position_ICS="edge"),
+    "lpt2": dict(initial_conditions="2LPT"),
+    "lpt3": dict(initial_conditions="3LPT", seed=7),
+    "lpt2_fixed_paired": dict(initial_conditions="2LPT", fixed_ICS=True, paired_ICS=True, seed=3),
+    "lpt3_dealiased": dict(initial_conditions="3LPT", dealiased_ICS=True, seed=11),
+}

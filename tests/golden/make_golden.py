@@ -328,6 +328,37 @@ def g_run():
 
 GROUPS["run"] = g_run
 
+def g_ics():
+    """Initial conditions of the reference (initial_conditions.generate, nthreads = 1) at 16^3 for every LPT
+    order / option, plus the table look-ups it used so that the build can be fed exactly the same growth factors."""
+    import pandas as pd
+    import cosmotable
+    import initial_conditions as ic
+    out = {}
+    base = "/tmp/pysco_golden_ics"
+    os.makedirs(base + "/output_00000", exist_ok=True)
+    for name, over in cases.IC_CASES.items():
+        param = pd.Series(cases.ic_param(base, **over))
+        param["aexp"] = 1.0 / (1 + param["z_start"])
+        utils.set_units(param)
+        tables = cosmotable.generate(param)
+        lna = np.log(1.0 / (1 + param["z_start"]))
+        out[f"{name}_tables"] = np.array([float(tables[2](lna))] + [float(tables[3](0))]
+                                         + [float(tables[i](lna)) for i in range(3, 13)])
+        out[f"{name}_unit_t"] = np.array([param["unit_t"]])
+        pos, vel = ic.generate(param, tables)
+        out[f"{name}_pos"], out[f"{name}_vel"] = pos.astype(np.float32), vel.astype(np.float32)
+    # host-side pieces, small enough for the CPU tier: white noise (half-spectrum part) and the density spectrum
+    for N, seed in ((8, 5), (12, 6)):
+        out[f"wn_N{N}"] = ic.white_noise_fourier(N, np.random.default_rng(seed))[:, :, :N // 2 + 1]
+        out[f"wnfixed_N{N}"] = ic.white_noise_fourier_fixed(N, np.random.default_rng(seed), True)[:, :, :N // 2 + 1]
+    param = pd.Series(cases.ic_param(base, npart=8 ** 3, seed=9))
+    out["density_fourier_N8"] = ic.generate_density_fourier(param)[:, :, :5]
+    save("ics", **out)
+
+
+GROUPS["ics"] = g_ics
+
 if __name__ == "__main__":
     todo = sys.argv[1:] or list(GROUPS)
     for g in todo:
