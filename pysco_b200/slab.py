@@ -909,3 +909,75 @@ class Slab:
         got = got[order]
         assert torch.equal(got[:, 9].long(), torch.arange(npart_total)), "particle ids lost or duplicated"
         return got[:, 0:3].float(), got[:, 3:6].float(), got[:, 6:9].float()
+
+
+# ------------------------------------------------------------------------------------------ main.run on slabs
+def run(param, comm=None, initial_state=None):
+    """`main.run` (main.py:30-156) on x-slabs: one call per rank (torchrun; or one thread per virtual rank with a
+    ThreadComm).  Every rank derives the same background tables; the initial particles come from `initial_state`
+    (global arrays, identical on every rank) or are generated identically on every rank (initial_conditions.generate:
+    meshes that fit one GPU) -- each rank adopts a strided share and the first migration routes the particles to their
+    slabs.  Snapshots are gathered to rank 0 in the reference's particle order.  Newtonian / parametrized gravity,
+    FFT solvers, leapfrog (what Slab.pm supports).  Returns (position, velocity) of the final state on rank 0
+    (CPU tensors, reference order), None elsewhere."""
+    import pandas as pd
+    from . import cosmotable, iostream, utils
+    from . import main as _main
+    comm = comm if comm is not None else default_comm()
+    if isinstance(param, dict):
+        param = pd.Series(param)
+    elif not isinstance(param, pd.Series):
+        raise ValueError(f"{type(param)=}, should be a dictionnary or a Pandas Series")
+    if param["verbose"] not in (0, 1, 2):
+        raise ValueError(f"{param['verbose']=}, should be 0, 1 or 2")
+    root = comm.rank == 0
+    param["write_snapshot"] = False
+    param["extra"] = f"{param['theory'].casefold()}_{param['linear_newton_solver']}_ncoarse{param['ncoarse']}"
+    if param["save_power_spectrum"].casefold() != "no":
+        raise NotImplementedError("slab path: save_power_spectrum must be 'no' (P(k) on slabs is not built)")
+    z_out = iostream.parse_z_out(param)
+    if root:
+        for i in range(len(z_out) + 1):
+            os.makedirs(f"{param['base']}/output_{i:05d}", exist_ok=True)
+    if not root:
+        param = param.copy()
+        param["base"] = ""          # only rank 0 writes tables and snapshots
+    tables = cosmotable.generate(param)
+    param["aexp"] = 1.0 / (1 + param["z_start"])
+    utils.set_units(param)
+    if "nsteps" not in param.index:
+        param["nsteps"] = 0
+    if initial_state is None:
+        from . import initial_conditions
+        position, velocity = initial_conditions.generate(param, tables, write_snapshot=root)
+    else:
+        position, velocity = initial_state
+    utils.set_units(param)
+    param["t"] = tables[1](np.log(param["aexp"]))
+    S = Slab(2 ** param["ncoarse"], comm=comm)
+    dev = S._device()
+    position = torch.as_tensor(position, dtype=torch.float32).to(dev)
+    velocity = torch.as_tensor(velocity, dtype=torch.float32).to(dev)
+    npart = position.shape[0]
+    ids = torch.arange(npart, dtype=torch.int64, device=dev)
+    mine = slice(comm.rank, None, comm.size)
+    S.set_particles(position[mine].contiguous(), velocity[mine].contiguous(), ids[mine].contiguous())
+    del position, velocity, ids
+    S.pm(param)
+    aexp_out = np.sort(1.0 / (np.array(z_out) + 1))
+    t_out = tables[1](np.log(aexp_out))
+    param["i_snap"] = 1 if "i_snap" not in param.index else param["i_snap"] + 1
+    while param["aexp"] < aexp_out[-1]:
+        param["nsteps"] += 1
+        S.integrate(tables, param, t_out[param["i_snap"] - 1])
+        if (param["nsteps"] % param["n_reorder"]) == 0:
+            S.reorder()
+        if param["write_snapshot"]:
+            state = S.gather_to_root(npart)
+            if root:
+                iostream.write_snapshot_particles(state[0], state[1], param)
+            param["i_snap"] += 1
+        logging.warning(f"{param['nsteps']=} {param['aexp']=} z = {1.0 / param['aexp'] - 1}")
+    state = S.gather_to_root(npart)
+    S.ops.close()
+    return (state[0], state[1]) if root else None

@@ -133,3 +133,32 @@ def test_pinned_host_pipeline_matches_device_path(solver_name):
         b = b.cpu()
         err = ((a - b).abs().max() / b.abs().max()).item()
         assert err < 1e-5, (name, err)
+
+
+def test_slab_whole_run_matches_reference_snapshot(tmp_path):
+    """BASELINE config 1 shape at 32^3, z = 49 -> 0, through slab.run on 2 virtual ranks: the final state, put back
+    in the reference's particle order, against the unmodified reference's final snapshot (tests/golden/run.npz).
+    The slab path restores the reference's particle order through the particle ids, so the comparison is row by
+    row."""
+    import cases
+    from pysco_b200 import slab
+    g = np.load(os.path.join(ROOT, "tests", "golden", "run.npz"))
+    base = str(tmp_path) + "/"
+    out = {}
+
+    def work(c, o):
+        param = cases.run_param(base, "fft")
+        param["save_power_spectrum"] = "no"
+        res = slab.run(param, comm=c, initial_state=(g["ic_pos"].copy(), g["ic_vel"].copy()))
+        if c.rank == 0:
+            o["pos"], o["vel"] = res[0].numpy(), res[1].numpy()
+
+    out = _threads(2, work)
+    # fewer than n_reorder = 50 steps: the reference never reorders, its final rows are the initial (lattice = id) rows
+    assert int(g["fft_nsteps"][0]) < 50
+    d = np.abs(out["pos"] - g["fft_pos"])
+    d = np.minimum(d, 1 - d)
+    assert d.max() < 1e-5, d.max()
+    assert np.abs(out["vel"] - g["fft_vel"]).max() < 1e-4 * np.abs(g["fft_vel"]).max() + 1e-7
+    snaps = __import__("glob").glob(os.path.join(base, "output_0000[1-6]", "particles_*.parquet"))
+    assert len(snaps) == 6
