@@ -196,7 +196,9 @@ int psc_slab_yblocks(const float *in, float *out, int N, int nxl, int nyl, int t
  * use of the buffers with inter-GPU barriers (pysco_b200/slab.py). */
 int psc_slab_transpose_put(const float *in, const void *peer_ptrs_dev, int N, int nxl, int nyl, int P, int me,
                            int forward, void *stream);
-/* psc_green on a y-block of the transposed spectrum [N (kx)][nyl (ky = y0 + .)][N/2+1] */
+/* psc_green / psc_pk on a y-block of the transposed spectrum [N (kx)][nyl (ky = y0 + .)][N/2+1]; the P(k) bins of the
+ * ranks are summed by the host (all-reduce) */
+int psc_pk_slab(float *spec_t, int N, int nyl, int y0, int p, double *bins, void *stream);
 int psc_green_slab(float *spec_t, int N, int nyl, int y0, int kind, int p, float scale, void *stream);
 
 /* ---------------------------------------------------------------- grid algebra ------------- */

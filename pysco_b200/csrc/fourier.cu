@@ -149,23 +149,25 @@ __global__ void __launch_bounds__(256) grad_green_kernel(const float2 *__restric
 
 // P(k): nearest-integer |k| bins, each stored half-spectrum mode counted once (no Hermitian weight).
 // Per-CTA shared-memory bins (double), flushed with native global double atomics.
-__global__ void __launch_bounds__(256) pk_kernel(float2 *__restrict__ spec, int N, int p,
+// The spectrum is [N (kx)][nyl (ky = y0 ..)][N/2+1] (nyl = N, y0 = 0: a whole grid; else a y-block of the transposed
+// slab layout).
+__global__ void __launch_bounds__(256) pk_kernel(float2 *__restrict__ spec, int N, int nyl, int y0, int p,
                                                  double *__restrict__ bins) {
   extern __shared__ double sb[];  // [3][N]
   for (int t = threadIdx.x; t < 3 * N; t += blockDim.x) sb[t] = 0.0;
   __syncthreads();
   const int nz = N / 2 + 1;
-  const int64_t total = (int64_t)N * N * nz;
+  const int64_t total = (int64_t)N * nyl * nz;
   const float h = 1.0f / (float)N;
   for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total;
        t += (int64_t)gridDim.x * blockDim.x) {
-    if (t == 0) {
-      spec[0] = make_float2(0.f, 0.f);  // side effect of the reference kept (fourier.py:61)
-      continue;
-    }
     int k = (int)(t % nz);
     int64_t r = t / nz;
-    int j = (int)(r % N), i = (int)(r / N);
+    int j = y0 + (int)(r % nyl), i = (int)(r / nyl);
+    if (i == 0 && j == 0 && k == 0) {
+      spec[t] = make_float2(0.f, 0.f);  // side effect of the reference kept (fourier.py:61)
+      continue;
+    }
     float kx = kfreq(i, N), ky = kfreq(j, N), kz = (float)k;
     float w = sinc_pi(kx * h) * sinc_pi(ky * h) * sinc_pi(kz * h);
     float iw = inv_pow_int(w, p);
@@ -298,16 +300,21 @@ int psc_grad_green(const float *spec, int N, int p, float scale, float *out3, vo
 }
 
 int psc_pk(float *spec, int N, int p, double *bins, void *stream) {
+  return psc_pk_slab(spec, N, N, 0, p, bins, stream);
+}
+
+int psc_pk_slab(float *spec, int N, int nyl, int y0, int p, double *bins, void *stream) {
   PSC_CHECK_ARG(spec && bins, "null pointer");
   PSC_CHECK_ARG(N >= 2 && N <= 2048, "N out of range");
+  PSC_CHECK_ARG(nyl >= 1 && y0 >= 0 && y0 + nyl <= N, "bad y block");
   PSC_CHECK_ARG(p >= 0 && p <= 8, "MAS index out of range");
   cudaStream_t st = as_stream(stream);
   PSC_CUDA(cudaMemsetAsync(bins, 0, sizeof(double) * 3 * N, st));
-  int64_t total = (int64_t)N * N * (N / 2 + 1);
+  int64_t total = (int64_t)N * nyl * (N / 2 + 1);
   size_t smem = sizeof(double) * 3 * N;
   if (smem > 48 * 1024)
     PSC_CUDA(cudaFuncSetAttribute(pk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  pk_kernel<<<grid_for(total, 256, 2), 256, smem, st>>>(reinterpret_cast<float2 *>(spec), N, p, bins);
+  pk_kernel<<<grid_for(total, 256, 2), 256, smem, st>>>(reinterpret_cast<float2 *>(spec), N, nyl, y0, p, bins);
   count_launch();
   PSC_CHECK_LAUNCH();
   return PSC_OK;

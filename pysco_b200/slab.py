@@ -434,6 +434,13 @@ class CudaOps:
     def fft_x(self, spec_t, inverse):
         _lib.check(self.lib.psc_slab_fft_x(self._fft_plan(), _lib.ptr(spec_t), int(inverse), _lib.stream()))
 
+    def pk_bins(self, spec_t, p):
+        """this rank's share of the P(k) bins [3][N] (sum |k|, sum |delta_k W^-p|^2, mode count), float64"""
+        bins = torch.empty((3, self.N), dtype=torch.float64, device=self.dev)
+        _lib.check(self.lib.psc_pk_slab(_lib.ptr(spec_t), self.N, self.nyl, self.y0, int(p), _lib.ptr(bins),
+                                        _lib.stream()))
+        return bins
+
     def green(self, spec_t, kind, p, scale):
         _lib.check(self.lib.psc_green_slab(_lib.ptr(spec_t), self.N, self.nyl, self.y0, kind, p, float(scale),
                                            _lib.stream()))
@@ -751,6 +758,8 @@ class Slab:
             del a
             hA.barrier(channel=0)
             ops.fft_x(A, False)
+            if param.get("save_pk", False):
+                self._write_pk(A, param)
             ops.green(A, kind, pp, 1.0 / float(self.N) ** 3)
             ops.fft_x(A, True)
             ops.transpose_put(A, hB.buffer_ptrs_dev, False)     # -> every rank's B = [nxl][N][nz]
@@ -763,11 +772,32 @@ class Slab:
         ops.yblocks(a, b, True)                 # [P][nxl][nyl][nz]
         comm.all_to_all_equal(b.view(self.P, -1), a.view(self.P, -1))   # [N][nyl][nz]
         ops.fft_x(a, False)
+        if param.get("save_pk", False):
+            self._write_pk(a, param)
         ops.green(a, kind, pp, 1.0 / float(self.N) ** 3)
         ops.fft_x(a, True)
         comm.all_to_all_equal(a.view(self.P, -1), b.view(self.P, -1))   # [P(y block)][nxl][nyl][nz]
         ops.yblocks(b, a, False)                # [nxl][N][nz]
         ops.fft2d_c2r(a, out_planes)
+
+    def _write_pk(self, spec_t, param):
+        """fourier.fourier_grid_to_Pk (fourier.py:22-100) + the scaling of solver.fft (solver.py:500-506) on the
+        transposed spectrum: per-rank bins, summed over ranks, written by rank 0."""
+        from . import iostream
+        bins = self.comm.allreduce_sum_(self.ops.pk_bins(spec_t, param["MAS_index"]))
+        if self.rank != 0:
+            return
+        b = bins.cpu().numpy()
+        N = self.N
+        kmax = int(2 * (N // 2) / 3)
+        nm = b[2, 1:kmax]
+        with np.errstate(invalid="ignore", divide="ignore"):
+            k = (b[0, 1:kmax] / nm).astype(np.float32)
+            pk = (b[1, 1:kmax] / nm).astype(np.float32)
+        pk *= (param["boxlen"] / N ** 2) ** 3
+        pk /= (1.5 * param["aexp"] * param["Om_m"]) ** 2 * param["parametrized_mu_z"] ** 2
+        k *= 2 * np.pi / param["boxlen"]
+        iostream.write_power_spectrum_to_ascii_file(k, pk, nm.astype(np.float32), param)
 
     # -- solver.pm on the slab
     def pm(self, param, kick=None):
@@ -793,6 +823,10 @@ class Slab:
             param["parametrized_mu_z"] = np.float32(1 + param["parametrized_mu0"] * olz / param["Om_lambda"])
         else:
             param["parametrized_mu_z"] = np.float32(1)
+        sps = str(param.get("save_power_spectrum", "no")).casefold()
+        if sps not in ("yes", "z_out", "no"):
+            raise NotImplementedError(f"SAVE_POWER_SPECTRUM={sps!r}, should be 'yes', 'z_out' or 'no'")
+        param["save_pk"] = sps == "yes" or (sps == "z_out" and bool(param["write_snapshot"]))
         n = self.np
         self._mark("migrate")
         binned = ops.bin(self.pos[:n])
@@ -933,10 +967,9 @@ def run(param, comm=None, initial_state=None):
     root = comm.rank == 0
     param["write_snapshot"] = False
     param["extra"] = f"{param['theory'].casefold()}_{param['linear_newton_solver']}_ncoarse{param['ncoarse']}"
-    if param["save_power_spectrum"].casefold() != "no":
-        raise NotImplementedError("slab path: save_power_spectrum must be 'no' (P(k) on slabs is not built)")
     z_out = iostream.parse_z_out(param)
     if root:
+        os.makedirs(f"{param['base']}/power", exist_ok=True)
         for i in range(len(z_out) + 1):
             os.makedirs(f"{param['base']}/output_{i:05d}", exist_ok=True)
     if not root:

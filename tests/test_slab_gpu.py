@@ -147,8 +147,7 @@ def test_slab_whole_run_matches_reference_snapshot(tmp_path):
     out = {}
 
     def work(c, o):
-        param = cases.run_param(base, "fft")
-        param["save_power_spectrum"] = "no"
+        param = cases.run_param(base, "fft")     # save_power_spectrum = z_out: P(k) at every snapshot
         res = slab.run(param, comm=c, initial_state=(g["ic_pos"].copy(), g["ic_vel"].copy()))
         if c.rank == 0:
             o["pos"], o["vel"] = res[0].numpy(), res[1].numpy()
@@ -160,5 +159,12 @@ def test_slab_whole_run_matches_reference_snapshot(tmp_path):
     d = np.minimum(d, 1 - d)
     assert d.max() < 1e-5, d.max()
     assert np.abs(out["vel"] - g["fft_vel"]).max() < 1e-4 * np.abs(g["fft_vel"]).max() + 1e-7
-    snaps = __import__("glob").glob(os.path.join(base, "output_0000[1-6]", "particles_*.parquet"))
+    glob = __import__("glob")
+    snaps = glob.glob(os.path.join(base, "output_0000[1-6]", "particles_*.parquet"))
     assert len(snaps) == 6
+    # the last P(k) file against the reference's (north-star bar 1e-4), summed over the two slabs' bins
+    pks = sorted(glob.glob(os.path.join(base, "power", "*.dat")))
+    mine, ref = np.loadtxt(pks[-1]), g["fft_pk_last"]
+    assert np.array_equal(mine[:, 2], ref[:, 2])
+    np.testing.assert_allclose(mine[:, 0], ref[:, 0], rtol=1e-6)
+    np.testing.assert_allclose(mine[:, 1], ref[:, 1], rtol=1e-4)
