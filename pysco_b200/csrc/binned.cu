@@ -237,12 +237,26 @@ __global__ void __launch_bounds__(BD_WARPS * 32) deposit_binned_kernel(const flo
     const unsigned peers = __match_any_sync(0xffffffffu, cellkey);
     const bool is_leader = valid && (__ffs(peers) - 1) == lane;
     unsigned rest = is_leader ? (peers & ~(1u << lane)) : 0u;
+    // (the peer's nine 1-D weights are shuffled and its 27 products re-formed here: 9 SHFL instead of 27 -- the
+    // shuffles share the saturated shared-memory pipe with the phases below, the multiplies are free)
     while (__any_sync(0xffffffffu, rest != 0u)) {
       const int src = rest ? (__ffs(rest) - 1) : lane;
+      float qx[3], qy[3], qz[3];
 #pragma unroll
-      for (int q = 0; q < 27; q++) {
-        const float v = __shfl_sync(0xffffffffu, wgt[q], src);
-        if (rest) wgt[q] += v;
+      for (int a = 0; a < 3; a++) {
+        qx[a] = __shfl_sync(0xffffffffu, wx[a], src);
+        qy[a] = __shfl_sync(0xffffffffu, wy[a], src);
+        qz[a] = __shfl_sync(0xffffffffu, wz[a], src);
+      }
+      if (rest) {
+#pragma unroll
+        for (int a = 0; a < 3; a++)
+#pragma unroll
+          for (int e = 0; e < 3; e++) {
+            const float qxy = qx[a] * qy[e];
+#pragma unroll
+            for (int g = 0; g < 3; g++) wgt[(a * 3 + e) * 3 + g] += qxy * qz[g];
+          }
       }
       rest &= rest - 1;
     }
