@@ -83,19 +83,22 @@ __global__ void __launch_bounds__(256) green_kernel(float2 *__restrict__ spec, i
   const float h = 1.0f / (float)N;
   // -1/(4 pi^2) for the continuous Green's functions, -(h^2/4) for the 7-point one
   const float c = (KIND == PSC_GREEN_7PT ? -(0.25f * h * h) : -0.0253302959105844f) * scale;
-  for (int64_t r0 = (int64_t)blockIdx.x * 4; r0 < nrows; r0 += (int64_t)gridDim.x * 4) {
+  // row indices fit 32 bits (N * nyl <= 4096^2): 64-bit divisions here made the kernel instruction-bound
+  const unsigned nrows32 = (unsigned)nrows, unyl = (unsigned)nyl;
+  for (unsigned r0 = blockIdx.x * 4u; r0 < nrows32; r0 += gridDim.x * 4u) {
     float kxy[4], wxy[4];
     float2 *row[4];
     bool dc[4];
 #pragma unroll
     for (int u = 0; u < 4; u++) {
-      const int64_t r = min(r0 + u, nrows - 1);
-      const int j = y0 + (int)(r % nyl), i = (int)(r / nyl);
+      const unsigned r = min(r0 + u, nrows32 - 1u);
+      const unsigned qi = r / unyl;
+      const int j = y0 + (int)(r - qi * unyl), i = (int)qi;
       dc[u] = i == 0 && j == 0;
       const float2 tx = gtab[i], ty = gtab[j];
       kxy[u] = tx.x + ty.x;
       wxy[u] = tx.y * ty.y;
-      row[u] = spec + r * nz;
+      row[u] = spec + (size_t)r * nz;
     }
     for (int k = threadIdx.x; k < nh; k += blockDim.x) {
       const float2 tz = gtab[k];
@@ -108,10 +111,10 @@ __global__ void __launch_bounds__(256) green_kernel(float2 *__restrict__ spec, i
         if (dc[u] && k == 0) g = 0.0f;  // DC mode -> 0 (reference: x[0,0,0] = 0 after the division)
         v[u].x *= g;
         v[u].y *= g;
-        if (r0 + u < nrows) row[u][k] = v[u];
+        if (r0 + u < nrows32) row[u][k] = v[u];
       }
     }
-    if (threadIdx.x < 4 && r0 + threadIdx.x < nrows) {
+    if (threadIdx.x < 4 && r0 + threadIdx.x < nrows32) {
       const int u = threadIdx.x;
       const float2 tz = gtab[nh];
       const float g = c * (wxy[u] * tz.y) / (kxy[u] + tz.x);
