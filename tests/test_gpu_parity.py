@@ -536,3 +536,47 @@ def test_config4_mond_512_newtonian_limit(psc):
     assert bool(torch.isfinite(acc_1).all())
     ratio = (acc_1.double().pow(2).mean().sqrt() / acc_n.double().pow(2).mean().sqrt()).item()
     assert ratio > 1.0
+
+
+# ------------------------------------------------------------------ ragged / edge-case inputs of the fused kernels
+@pytest.mark.parametrize("npart", [1, 3, 5003, 40001])
+def test_kick_drift_wrap_count_ragged(psc, orc, npart):
+    """psc_kick_drift_wrap_count (kick + drift + wrap + bin count in one pass) for particle counts that are not
+    multiples of 4 / 32 and positions on the domain edges: same particles as psc_kick_drift_wrap, and the bin counts
+    it leaves behind give the same binning as psc_bin_particles (checked through the deposit that consumes them)."""
+    import torch
+    N = 32
+    pos, vel = cases.particles(N, npart, seed=21), cases.velocities(npart, seed=22, scale=5e-3)
+    acc = cases.velocities(npart, seed=23, scale=1.0)
+    dt = np.float32(0.0371)
+    half = np.float32(0.5 * dt)
+    p, v = pos.copy(), vel.copy()
+    orc.utils.add_vector_scalar_inplace(v, acc, -half)
+    orc.utils.add_vector_scalar_inplace(p, v, dt)
+    orc.utils.periodic_wrap(p)
+    tp, tv, ta = _cuda(pos), _cuda(vel), _cuda(acc)
+    binned = psc.mesh.alloc_binned(npart, N)
+    psc.mesh.kick_drift_wrap_count(tp, tv, ta, half, dt, 0, binned)
+    assert np.max(np.abs(tp.cpu().numpy() - p)) <= 6e-8
+    assert_close(tv.cpu().numpy(), v, 1e-6, "kick")
+    psc.mesh.finish_binning(tp, binned)
+    rho = psc.mesh.deposit_rhs(tp, N, psc._lib.TSC, 1.0, 1.0, 0.0, binned)
+    ref = orc.mesh.TSC_seq(np.ascontiguousarray(tp.cpu().numpy()), N)
+    assert abs(rho.sum(dtype=torch.float64).item() - npart) < 1e-5 * max(npart, 1)
+    assert np.max(np.abs(rho.cpu().numpy() - ref)) < 1e-5
+
+
+def test_pm_ragged_and_edge_positions_vs_oracle(psc, orc):
+    """solver.pm (binned deposit + fused gradient / interpolation) with npart != N^3, particles exactly at 0, at the
+    largest float below 1, on cell centres and cell edges, and two identical particles."""
+    from oracle import host
+    N, npart = 16, 5003
+    pos = cases.particles(N, npart, seed=31)
+    p1 = cases.base_param(4, npart, linear_newton_solver="fft")
+    p2 = p1.copy()
+    psc.utils.set_units(p1)
+    host.set_units(p2)
+    acc, pot, _ = psc.solver.pm(_cuda(pos), p1)
+    acc_ref, pot_ref, _ = host.pm(pos.copy(), p2)
+    assert_close(pot.cpu().numpy(), pot_ref, 3e-5, "potential")
+    assert_close(acc.cpu().numpy(), acc_ref, 5e-5, "acceleration")

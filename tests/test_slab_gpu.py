@@ -15,6 +15,7 @@ for p in (ROOT, os.path.join(ROOT, "tests"), os.path.join(ROOT, "tests", "golden
     if p not in sys.path:
         sys.path.insert(0, p)
 
+import cases  # noqa: E402
 import test_slab_cpu as cpu  # noqa: E402
 
 pytestmark = pytest.mark.gpu
@@ -168,3 +169,40 @@ def test_slab_whole_run_matches_reference_snapshot(tmp_path):
     assert np.array_equal(mine[:, 2], ref[:, 2])
     np.testing.assert_allclose(mine[:, 0], ref[:, 0], rtol=1e-6)
     np.testing.assert_allclose(mine[:, 1], ref[:, 1], rtol=1e-4)
+
+
+@pytest.mark.parametrize("P", [2, 4])
+def test_slab_pm_edge_positions_and_ragged_counts(P):
+    """Slab deposit / interpolation with particles exactly on slab boundaries (x = r/P), at 0 and just below 1, with
+    npart != N^3 and very uneven counts per slab: acceleration of every particle against the oracle's solver.pm."""
+    from oracle import host
+    from pysco_b200 import slab
+    N, npart = 32, 20011
+    pos = cases.particles(N, npart, seed=41)
+    k = npart // 2
+    pos[16:16 + P, 0] = (np.arange(P, dtype=np.float32) / P)                     # exactly on the slab boundaries
+    pos[32:k, 0] = pos[32:k, 0] * np.float32(0.5 / P)                            # half of the particles in slab 0
+    pos = np.ascontiguousarray(pos.astype(np.float32))
+    param_ref = cases.base_param(5, npart, linear_newton_solver="fft")
+    host.set_units(param_ref)
+    acc_ref, _, _ = host.pm(pos.copy(), param_ref)
+
+    def work(c, o):
+        param = cases.base_param(5, npart, linear_newton_solver="fft")
+        host.set_units(param)
+        s = slab.Slab(N, comm=c)
+        ids = torch.arange(npart, dtype=torch.int64, device="cuda")
+        mine = slice(c.rank, None, c.size)
+        s.set_particles(torch.from_numpy(pos).cuda()[mine].contiguous(), torch.zeros((npart, 3), device="cuda")[mine],
+                        ids[mine].contiguous())
+        s.pm(param)
+        res = s.gather_to_root(npart)
+        if c.rank == 0:
+            o["acc"] = res[2].numpy()
+            o["pos"] = res[0].numpy()
+        s.ops.close()
+
+    out = _threads(P, work)
+    assert np.array_equal(out["pos"], pos)
+    err = np.max(np.abs(out["acc"] - acc_ref)) / np.sqrt(np.mean(acc_ref.astype(np.float64) ** 2))
+    assert err < 5e-5, err
