@@ -30,6 +30,11 @@ constexpr int BD_P1 = 12;       // row pitch of the per-warp tile; 12 / 144 spre
 constexpr int BD_P0 = 144;
 constexpr int BD_TILE = BT * BD_P0;  // 1100 floats per warp
 
+// A bin is processed by one CTA up to BIN_PART particles; the rest of a heavier bin (a halo core can hold 10^6
+// particles of a 512^3 run at z = 0) is cut into parts of BIN_PART particles listed in BinLayout::heavy and processed
+// by a second, persistent launch -- otherwise one CTA would serialise the whole bin.
+constexpr int BIN_PART = 4096;
+
 struct BinLayout {
   int NB;            // bins along y and z (N / 8)
   int NBX;           // bins along x (owned planes / 8; == NB for the periodic single-domain case)
@@ -38,6 +43,9 @@ struct BinLayout {
   int *counts;       // [nbins + 1]
   int *offsets;      // [nbins + 1]  exclusive prefix sum, offsets[nbins] = np
   float4 *rec;       // [np] binned particles: (x, y, z, source row as int bits) -- one 16-byte access per particle
+  int *heavy_count;  // [1] number of entries of `heavy`
+  int2 *heavy;       // [heavy_cap] (bin, part >= 1): the parts beyond the first BIN_PART particles of a bin
+  int heavy_cap;
   void *cub_tmp;
   size_t cub_bytes;
 };
@@ -60,6 +68,9 @@ static bool bin_layout(void *scratch, size_t bytes, int64_t np, int N, int x0, i
   L.counts = reinterpret_cast<int *>(p + off); off += a256(sizeof(int) * (L.nbins + 1));
   L.offsets = reinterpret_cast<int *>(p + off); off += a256(sizeof(int) * (L.nbins + 1));
   L.rec = reinterpret_cast<float4 *>(p + off); off += a256(sizeof(float4) * (size_t)np);
+  L.heavy_count = reinterpret_cast<int *>(p + off); off += 256;
+  L.heavy_cap = (int)(np / BIN_PART) + 1;
+  L.heavy = reinterpret_cast<int2 *>(p + off); off += a256(sizeof(int2) * (size_t)L.heavy_cap);
   L.cub_tmp = p + off;
   L.cub_bytes = scan_tmp_bytes(L.nbins + 1);
   off += a256(L.cub_bytes);
@@ -163,6 +174,19 @@ __global__ void __launch_bounds__(256) kick_drift_wrap_count_kernel(float *__res
   }
 }
 
+// after the scan: list the extra parts of the bins that hold more than BIN_PART particles
+__global__ void __launch_bounds__(256) bin_heavy_list_kernel(const int *__restrict__ offsets, int nbins,
+                                                             int *__restrict__ heavy_count, int2 *__restrict__ heavy,
+                                                             int heavy_cap) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= nbins) return;
+  const int extra = (offsets[b + 1] - offsets[b] - 1) / BIN_PART;
+  if (extra <= 0) return;
+  const int base = atomicAdd(heavy_count, extra);
+  for (int e = 0; e < extra; e++)
+    if (base + e < heavy_cap) heavy[base + e] = make_int2(b, e + 1);
+}
+
 // pass 2: slot = offsets[bin] + (claimed range in the bin); counts[] is consumed (counted down to zero)
 __global__ void __launch_bounds__(256) bin_scatter_kernel(const float *__restrict__ pos, int64_t np, int N, int NB,
                                                           int x0, int NBX, int *__restrict__ counts, const int *__restrict__ offsets,
@@ -195,15 +219,11 @@ __global__ void __launch_bounds__(256) bin_scatter_kernel(const float *__restric
 }
 
 // ------------------------------------------------------------------------------------- deposit
+// particles [beg, end) of bin b; shared = other CTAs deposit into the same bin (its interior cells need atomics too)
 template <int SCHEME>
-__global__ void __launch_bounds__(BD_WARPS * 32) deposit_binned_kernel(const float4 *__restrict__ brec,
-                                                                       const int *__restrict__ offsets, int N, int NB,
-                                                                       int x0, int xoff, int nxa,
-                                                                       float *__restrict__ rho) {
-  __shared__ float tiles[BD_WARPS][BD_TILE];
-  const int b = blockIdx.x;
-  const int beg = offsets[b], end = offsets[b + 1];
-  if (beg == end) return;  // rho was zeroed by the caller
+__device__ __forceinline__ void deposit_bin_range(float (*tiles)[BD_TILE], const float4 *__restrict__ brec, int b,
+                                                  int beg, int end, bool shared, int N, int NB, int x0, int xoff,
+                                                  int nxa, float *__restrict__ rho) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int bk = b % NB, bj = (b / NB) % NB, bi = b / (NB * NB);
   const int oi = x0 + bi * BB - 1, oj = bj * BB - 1, ok = bk * BB - 1;  // global cell of tile cell (0,0,0)
@@ -237,6 +257,16 @@ __global__ void __launch_bounds__(BD_WARPS * 32) deposit_binned_kernel(const flo
     const unsigned peers = __match_any_sync(0xffffffffu, cellkey);
     const bool is_leader = valid && (__ffs(peers) - 1) == lane;
     unsigned rest = is_leader ? (peers & ~(1u << lane)) : 0u;
+    // Dense cells (halo cores): Morton order puts runs of particles of ONE cell into a chunk; a chunk whose 32 lanes
+    // all share a cell is summed by a 5-step butterfly instead of 31 merge rounds.
+    if (__all_sync(0xffffffffu, peers == 0xffffffffu)) {
+#pragma unroll
+      for (int q = 0; q < 27; q++) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) wgt[q] += __shfl_xor_sync(0xffffffffu, wgt[q], o);
+      }
+      rest = 0u;
+    }
     // (the peer's nine 1-D weights are shuffled and its 27 products re-formed here: 9 SHFL instead of 27 -- the
     // shuffles share the saturated shared-memory pipe with the phases below, the multiplies are free)
     while (__any_sync(0xffffffffu, rest != 0u)) {
@@ -293,10 +323,41 @@ __global__ void __launch_bounds__(BD_WARPS * 32) deposit_binned_kernel(const flo
       for (int w = 1; w < BD_WARPS; w++) v += tiles[w][s];
       const int gi = wrap(pl0 + a, nxa), gj = wrap(oj + e, N);
       float *dst = rho + ((size_t)gi * N + gj) * N + gk;
-      const bool mine = kin && a >= 2 && a <= BT - 3 && e >= 2 && e <= BT - 3;
+      const bool mine = !shared && kin && a >= 2 && a <= BT - 3 && e >= 2 && e <= BT - 3;
       if (mine) *dst = v;
       else if (v != 0.0f) atomicAdd(dst, v);
     }
+  }
+}
+
+template <int SCHEME>
+__global__ void __launch_bounds__(BD_WARPS * 32) deposit_binned_kernel(const float4 *__restrict__ brec,
+                                                                       const int *__restrict__ offsets, int N, int NB,
+                                                                       int x0, int xoff, int nxa,
+                                                                       float *__restrict__ rho) {
+  __shared__ float tiles[BD_WARPS][BD_TILE];
+  const int b = blockIdx.x;
+  const int beg = offsets[b], end = offsets[b + 1];
+  if (beg == end) return;  // rho was zeroed by the caller
+  deposit_bin_range<SCHEME>(tiles, brec, b, beg, min(end, beg + BIN_PART), end - beg > BIN_PART, N, NB, x0, xoff, nxa,
+                            rho);
+}
+
+// the parts beyond BIN_PART particles of the heavy bins (persistent CTAs over BinLayout::heavy)
+template <int SCHEME>
+__global__ void __launch_bounds__(BD_WARPS * 32) deposit_heavy_kernel(const float4 *__restrict__ brec,
+                                                                      const int *__restrict__ offsets,
+                                                                      const int *__restrict__ heavy_count,
+                                                                      const int2 *__restrict__ heavy, int heavy_cap,
+                                                                      int N, int NB, int x0, int xoff, int nxa,
+                                                                      float *__restrict__ rho) {
+  __shared__ float tiles[BD_WARPS][BD_TILE];
+  const int nitems = min(*heavy_count, heavy_cap);
+  for (int it = blockIdx.x; it < nitems; it += gridDim.x) {
+    const int2 w = heavy[it];
+    const int beg = offsets[w.x] + w.y * BIN_PART, end = min(offsets[w.x + 1], beg + BIN_PART);
+    deposit_bin_range<SCHEME>(tiles, brec, w.x, beg, end, true, N, NB, x0, xoff, nxa, rho);
+    __syncthreads();
   }
 }
 
@@ -307,12 +368,20 @@ template <int SCHEME>
 __global__ void __launch_bounds__(BI_THREADS) interp_kick4_binned_kernel(
     const float4 *__restrict__ force4, const float4 *__restrict__ brec,
     const int *__restrict__ offsets, float *__restrict__ vel, float *__restrict__ accel, int N, int NB,
-    int x0, int xoff, int nxa, float half_dt, float *__restrict__ maxout) {
+    int x0, int xoff, int nxa, float half_dt, float *__restrict__ maxout, int nbins,
+    const int *__restrict__ heavy_count, const int2 *__restrict__ heavy) {
   __shared__ float4 tile[BT * BT * BT];  // 16,000 B
   __shared__ float s_max[BI_THREADS / 32][2];
-  const int b = blockIdx.x;
-  const int beg = offsets[b], end = offsets[b + 1];
-  if (beg == end) return;
+  int b = blockIdx.x, part = 0;
+  if (b >= nbins) {
+    const int it = b - nbins;
+    if (it >= *heavy_count) return;
+    const int2 w = heavy[it];
+    b = w.x;
+    part = w.y;
+  }
+  const int beg = offsets[b] + part * BIN_PART, end = min(offsets[b + 1], beg + BIN_PART);
+  if (beg >= end) return;
   const int bk = b % NB, bj = (b / NB) % NB, bi = b / (NB * NB);
   const int oi = x0 + bi * BB - 1, oj = bj * BB - 1, ok = bk * BB - 1;
   const int pl0 = bi * BB - 1 + xoff;
@@ -388,16 +457,24 @@ __global__ void __launch_bounds__(BP_THREADS) interp_kick_phi_binned_kernel(
     const float *__restrict__ phi, const float *__restrict__ u, float f, int fr_n,
     const float4 *__restrict__ brec, const int *__restrict__ offsets,
     float *__restrict__ vel, float *__restrict__ accel, int N, int NB, int x0, int xoff, int nxa, float half_dt,
-    float *__restrict__ maxout) {
+    float *__restrict__ maxout, int nbins, const int *__restrict__ heavy_count, const int2 *__restrict__ heavy) {
   constexpr int H = Reach<ORDER>::H;
   constexpr int PT = BT + 2 * H;  // potential tile edge
   constexpr int PK = 16;          // k pitch of the potential tile: the aligned 16-float window
   __shared__ __align__(16) float ptile[PT * PT * PK];
   __shared__ float4 tile[BT * TP0];
   __shared__ float s_max[BP_THREADS / 32][2];
-  const int b = blockIdx.x;
-  const int beg = offsets[b], end = offsets[b + 1];
-  if (beg == end) return;
+  // CTAs [0, nbins): the first BIN_PART particles of bin blockIdx.x; CTAs beyond: one listed part of a heavy bin
+  int b = blockIdx.x, part = 0;
+  if (b >= nbins) {
+    const int it = b - nbins;
+    if (it >= *heavy_count) return;
+    const int2 w = heavy[it];
+    b = w.x;
+    part = w.y;
+  }
+  const int beg = offsets[b] + part * BIN_PART, end = min(offsets[b + 1], beg + BIN_PART);
+  if (beg >= end) return;
   const int bk = b % NB, bj = (b / NB) % NB, bi = b / (NB * NB);
   const int oi = x0 + bi * BB - 1, oj = bj * BB - 1, ok = bk * BB - 1;
   const int pl0 = bi * BB - 1 + xoff;
@@ -524,8 +601,8 @@ static bool slab_ok(int N, int x0, int nxl) {
 size_t psc_bin_workspace_bytes_slab(int64_t np, int N, int nxl) {
   if (np < 0 || !slab_ok(N, 0, nxl)) return 0;
   const int64_t nbins = (int64_t)(nxl / BB) * (N / BB) * (N / BB);
-  return 2 * a256(sizeof(int) * (nbins + 1)) + a256(sizeof(float4) * (size_t)np) +
-         a256(scan_tmp_bytes(nbins + 1)) + 256;
+  return 2 * a256(sizeof(int) * (nbins + 1)) + a256(sizeof(float4) * (size_t)np) + 256 +
+         a256(sizeof(int2) * (size_t)(np / BIN_PART + 1)) + a256(scan_tmp_bytes(nbins + 1)) + 256;
 }
 size_t psc_bin_workspace_bytes(int64_t np, int N) { return psc_bin_workspace_bytes_slab(np, N, N); }
 
@@ -552,6 +629,10 @@ int psc_bin_particles_slab(const float *pos, int64_t np, int N, int x0, int nxl,
     set_error("psc_bin_particles: cub scan failed: %s", cudaGetErrorString(e));
     return PSC_ERR_CUDA;
   }
+  PSC_CUDA(cudaMemsetAsync(L.heavy_count, 0, sizeof(int), st));
+  bin_heavy_list_kernel<<<(int)((L.nbins + 255) / 256), 256, 0, st>>>(L.offsets, (int)L.nbins, L.heavy_count, L.heavy,
+                                                                     L.heavy_cap);
+  count_launch();
   if (np > 0) {
     bin_scatter_kernel<<<grid_for(np, 256, 8), 256, 0, st>>>(pos, np, N, L.NB, x0, L.NBX, L.counts, L.offsets, L.rec);
     count_launch();
@@ -605,6 +686,10 @@ int psc_bin_particles_counted(const float *pos, int64_t np, int N, void *scratch
     set_error("psc_bin_particles_counted: cub scan failed: %s", cudaGetErrorString(e));
     return PSC_ERR_CUDA;
   }
+  PSC_CUDA(cudaMemsetAsync(L.heavy_count, 0, sizeof(int), st));
+  bin_heavy_list_kernel<<<(int)((L.nbins + 255) / 256), 256, 0, st>>>(L.offsets, (int)L.nbins, L.heavy_count, L.heavy,
+                                                                     L.heavy_cap);
+  count_launch();
   if (np > 0) {
     bin_scatter_kernel<<<grid_for(np, 256, 8), 256, 0, st>>>(pos, np, N, L.NB, 0, L.NBX, L.counts, L.offsets, L.rec);
     count_launch();
@@ -628,13 +713,16 @@ static int deposit_binned_impl(const void *scratch, size_t scratch_bytes, int64_
   PSC_CUDA(cudaMemsetAsync(rho, 0, sizeof(float) * n3, st));
   if (np > 0) {
     const int grid = (int)L.nbins;
-    if (scheme == PSC_TSC)
-      deposit_binned_kernel<PSC_TSC><<<grid, BD_WARPS * 32, 0, st>>>(L.rec, L.offsets, N, L.NB, x0, ghost, nxa, rho);
-    else if (scheme == PSC_CIC)
-      deposit_binned_kernel<PSC_CIC><<<grid, BD_WARPS * 32, 0, st>>>(L.rec, L.offsets, N, L.NB, x0, ghost, nxa, rho);
-    else
-      deposit_binned_kernel<PSC_NGP><<<grid, BD_WARPS * 32, 0, st>>>(L.rec, L.offsets, N, L.NB, x0, ghost, nxa, rho);
-    count_launch();
+    const int hgrid = kNumSMs * 4;   // persistent CTAs over the heavy-bin parts (exit at once when there are none)
+#define PSC_DEP(S)                                                                                                 \
+  deposit_binned_kernel<S><<<grid, BD_WARPS * 32, 0, st>>>(L.rec, L.offsets, N, L.NB, x0, ghost, nxa, rho);        \
+  deposit_heavy_kernel<S><<<hgrid, BD_WARPS * 32, 0, st>>>(L.rec, L.offsets, L.heavy_count, L.heavy, L.heavy_cap, N, \
+                                                          L.NB, x0, ghost, nxa, rho)
+    if (scheme == PSC_TSC) { PSC_DEP(PSC_TSC); }
+    else if (scheme == PSC_CIC) { PSC_DEP(PSC_CIC); }
+    else { PSC_DEP(PSC_NGP); }
+#undef PSC_DEP
+    count_launch(2);
     PSC_CHECK_LAUNCH();
   }
   if (scale != 1.0f || f1 != 1.0f || f2 != 0.0f) {
@@ -675,11 +763,11 @@ int psc_interp_kick4_binned(const float *force4, const void *scratch, size_t scr
   }
   cudaStream_t st = as_stream(stream);
   const float4 *f4 = reinterpret_cast<const float4 *>(force4);
-  const int grid = (int)L.nbins;
+  const int grid = (int)L.nbins + L.heavy_cap;
   if (scheme == PSC_TSC)
-    interp_kick4_binned_kernel<PSC_TSC><<<grid, BI_THREADS, 0, st>>>(f4, L.rec, L.offsets, vel, acc, N, L.NB, 0, 0, N, half_dt, maxout);
+    interp_kick4_binned_kernel<PSC_TSC><<<grid, BI_THREADS, 0, st>>>(f4, L.rec, L.offsets, vel, acc, N, L.NB, 0, 0, N, half_dt, maxout, (int)L.nbins, L.heavy_count, L.heavy);
   else
-    interp_kick4_binned_kernel<PSC_CIC><<<grid, BI_THREADS, 0, st>>>(f4, L.rec, L.offsets, vel, acc, N, L.NB, 0, 0, N, half_dt, maxout);
+    interp_kick4_binned_kernel<PSC_CIC><<<grid, BI_THREADS, 0, st>>>(f4, L.rec, L.offsets, vel, acc, N, L.NB, 0, 0, N, half_dt, maxout, (int)L.nbins, L.heavy_count, L.heavy);
   count_launch();
   PSC_CHECK_LAUNCH();
   return PSC_OK;
@@ -698,11 +786,12 @@ static int interp_kick_phi_impl(const float *phi, const float *u, float f, int f
     return PSC_ERR_WORKSPACE;
   }
   cudaStream_t st = as_stream(stream);
-  const int grid = (int)L.nbins;
+  const int grid = (int)L.nbins + L.heavy_cap;   // the CTAs of unused heavy-part slots exit at once
   const int nxa = nxl + 2 * ghost;
 #define PSC_IKP(S, O)                                                                                            \
   interp_kick_phi_binned_kernel<S, O><<<grid, BP_THREADS, 0, st>>>(phi, u, f, fr_n, L.rec, L.offsets, vel, acc, \
-                                                                   N, L.NB, x0, ghost, nxa, half_dt, maxout)
+                                                                   N, L.NB, x0, ghost, nxa, half_dt, maxout,    \
+                                                                   (int)L.nbins, L.heavy_count, L.heavy)
 #define PSC_IKP_O(S)               \
   if (order == 2) PSC_IKP(S, 2);    \
   else if (order == 3) PSC_IKP(S, 3); \

@@ -580,3 +580,27 @@ def test_pm_ragged_and_edge_positions_vs_oracle(psc, orc):
     acc_ref, pot_ref, _ = host.pm(pos.copy(), p2)
     assert_close(pot.cpu().numpy(), pot_ref, 3e-5, "potential")
     assert_close(acc.cpu().numpy(), acc_ref, 5e-5, "acceleration")
+
+
+def test_interp_heavy_bins_vs_oracle(psc, orc):
+    """A bin holding far more than BIN_PART = 4096 particles (a 200 000-particle blob two cells wide): the gradient +
+    interpolation kernel splits such bins into parts handled by several CTAs; every particle must still get the
+    oracle's acceleration and kick.  (The deposit of the same set is covered by test_deposit_clustered_and_ragged,
+    against a float64 sum: with 10^4 particles per cell the reference's own float32 running sum is the less accurate
+    side, so a whole-pm comparison would test the oracle's rounding, not the kernel.)"""
+    N = 64
+    rng = np.random.default_rng(17)
+    blob = (0.37 + 0.01 * rng.standard_normal((200000, 3))).astype(np.float32)
+    pos = np.ascontiguousarray(np.concatenate([blob % 1.0, cases.particles(N, 62144, seed=18)]).astype(np.float32))
+    pos[pos >= 1.0] = 0.0
+    vel = cases.velocities(pos.shape[0], seed=19, scale=2e-3)
+    phi = cases.scalar_grid(N, seed=20, smooth=True)
+    a_ref = orc.mesh.invTSC_vec(orc.mesh.derivative(phi, 5), pos)
+    v_ref = vel.copy()
+    orc.utils.add_vector_scalar_inplace(v_ref, a_ref, -np.float32(0.0123))
+    tp, tv = _cuda(pos), _cuda(vel)
+    binned = psc.mesh.bin_particles(tp, N)
+    acc, mx = psc.mesh.interp_kick_phi(_cuda(phi), None, 0.0, 0, 5, tp, tv, psc._lib.TSC, np.float32(0.0123), binned)
+    assert_close(acc.cpu().numpy(), a_ref, 2e-5, "acceleration")
+    assert_close(tv.cpu().numpy(), v_ref, 2e-5, "kicked velocity")
+    np.testing.assert_allclose(mx.cpu().numpy()[0], np.abs(a_ref).max(), rtol=1e-5)

@@ -38,6 +38,15 @@ p = pos_mor + torch.randn(pos_mor.shape, generator=g, device="cuda") * (1.0 / N)
 p = p - torch.floor(p)
 p[p >= 1.0] = 0.0
 cases = {"morton": pos_mor, "morton+drift1.0": p.contiguous()}
+# clustered: half of the particles in 4096 Gaussian blobs of sigma = 0.7 cell (bins with ~10^4 particles)
+n = pos_mor.shape[0]
+centres = torch.rand((4096, 3), generator=g, device="cuda")
+which = torch.randint(0, 4096, (n // 2,), generator=g, device="cuda")
+pc = torch.cat([pos_mor[: n - n // 2], centres[which] + torch.randn((n // 2, 3), generator=g, device="cuda") * (0.7 / N)])
+pc = pc - torch.floor(pc)
+pc[pc >= 1.0] = 0.0
+cases["clustered (Morton)"] = utils.reorder_particles(pc.contiguous())
+del pc, which
 phi = torch.randn((N, N, N), device="cuda")
 for name, p in cases.items():
     t_bin = timeit(lambda: mesh.bin_particles(p, N))
