@@ -371,7 +371,7 @@ __global__ void __launch_bounds__(BI_THREADS) interp_kick4_binned_kernel(
     int x0, int xoff, int nxa, float half_dt, float *__restrict__ maxout, int nbins,
     const int *__restrict__ heavy_count, const int2 *__restrict__ heavy) {
   __shared__ float4 tile[BT * BT * BT];  // 16,000 B
-  __shared__ float s_max[BI_THREADS / 32][2];
+  __shared__ unsigned s_max[BI_THREADS / 32][2];
   int b = blockIdx.x, part = 0;
   if (b >= nbins) {
     const int it = b - nbins;
@@ -394,7 +394,7 @@ __global__ void __launch_bounds__(BI_THREADS) interp_kick4_binned_kernel(
   __syncthreads();
   const float Nf = (float)N;
   const float mh = -half_dt;
-  float ma = 0.0f, mv = 0.0f;
+  unsigned ma = 0u, mv = 0u;   // maxima of |.| as bit patterns: orders like the floats and lets a NaN win
   for (int n = beg + threadIdx.x; n < end; n += BI_THREADS) {
     const float4 rec = __ldg(&brec[n]);
     const float px = rec.x, py = rec.y, pz = rec.z;
@@ -420,23 +420,23 @@ __global__ void __launch_bounds__(BI_THREADS) interp_kick4_binned_kernel(
       }
     float *ap = accel + 3 * (size_t)row;
     ap[0] = ax; ap[1] = ay; ap[2] = az;
-    ma = fmaxf(ma, fmaxf(fabsf(ax), fmaxf(fabsf(ay), fabsf(az))));
+    ma = max(ma, max(__float_as_uint(fabsf(ax)), max(__float_as_uint(fabsf(ay)), __float_as_uint(fabsf(az)))));
     if (vel) {
       float *vp = vel + 3 * (size_t)row;
       const float v0 = vp[0] + mh * ax, v1 = vp[1] + mh * ay, v2 = vp[2] + mh * az;
       vp[0] = v0; vp[1] = v1; vp[2] = v2;
-      mv = fmaxf(mv, fmaxf(fabsf(v0), fmaxf(fabsf(v1), fabsf(v2))));
+      mv = max(mv, max(__float_as_uint(fabsf(v0)), max(__float_as_uint(fabsf(v1)), __float_as_uint(fabsf(v2)))));
     }
   }
-  ma = warp_max(ma);
-  mv = warp_max(mv);
+  ma = __reduce_max_sync(0xffffffffu, ma);
+  mv = __reduce_max_sync(0xffffffffu, mv);
   if ((threadIdx.x & 31) == 0) { s_max[threadIdx.x >> 5][0] = ma; s_max[threadIdx.x >> 5][1] = mv; }
   __syncthreads();
   if (threadIdx.x == 0) {
 #pragma unroll
-    for (int w = 1; w < BI_THREADS / 32; w++) { ma = fmaxf(ma, s_max[w][0]); mv = fmaxf(mv, s_max[w][1]); }
-    atomic_max_nonneg(&maxout[0], ma);
-    atomic_max_nonneg(&maxout[1], mv);
+    for (int w = 1; w < BI_THREADS / 32; w++) { ma = max(ma, s_max[w][0]); mv = max(mv, s_max[w][1]); }
+    atomicMax(reinterpret_cast<unsigned *>(&maxout[0]), ma);
+    atomicMax(reinterpret_cast<unsigned *>(&maxout[1]), mv);
   }
 }
 
@@ -463,7 +463,7 @@ __global__ void __launch_bounds__(BP_THREADS) interp_kick_phi_binned_kernel(
   constexpr int PK = 16;          // k pitch of the potential tile: the aligned 16-float window
   __shared__ __align__(16) float ptile[PT * PT * PK];
   __shared__ float4 tile[BT * TP0];
-  __shared__ float s_max[BP_THREADS / 32][2];
+  __shared__ unsigned s_max[BP_THREADS / 32][2];
   // CTAs [0, nbins): the first BIN_PART particles of bin blockIdx.x; CTAs beyond: one listed part of a heavy bin
   int b = blockIdx.x, part = 0;
   if (b >= nbins) {
@@ -539,7 +539,7 @@ __global__ void __launch_bounds__(BP_THREADS) interp_kick_phi_binned_kernel(
   __syncthreads();
   const float Nf = (float)N;
   const float mh = -half_dt;
-  float ma = 0.0f, mv = 0.0f;
+  unsigned ma = 0u, mv = 0u;   // maxima of |.| as bit patterns: orders like the floats and lets a NaN win
   for (int n = beg + threadIdx.x; n < end; n += BP_THREADS) {
     const float4 rec = __ldg(&brec[n]);
     const float px = rec.x, py = rec.y, pz = rec.z;
@@ -565,23 +565,23 @@ __global__ void __launch_bounds__(BP_THREADS) interp_kick_phi_binned_kernel(
       }
     float *ap = accel + 3 * (size_t)row;
     ap[0] = ax; ap[1] = ay; ap[2] = az;
-    ma = fmaxf(ma, fmaxf(fabsf(ax), fmaxf(fabsf(ay), fabsf(az))));
+    ma = max(ma, max(__float_as_uint(fabsf(ax)), max(__float_as_uint(fabsf(ay)), __float_as_uint(fabsf(az)))));
     if (vel) {
       float *vp = vel + 3 * (size_t)row;
       const float v0 = vp[0] + mh * ax, v1 = vp[1] + mh * ay, v2 = vp[2] + mh * az;
       vp[0] = v0; vp[1] = v1; vp[2] = v2;
-      mv = fmaxf(mv, fmaxf(fabsf(v0), fmaxf(fabsf(v1), fabsf(v2))));
+      mv = max(mv, max(__float_as_uint(fabsf(v0)), max(__float_as_uint(fabsf(v1)), __float_as_uint(fabsf(v2)))));
     }
   }
-  ma = warp_max(ma);
-  mv = warp_max(mv);
+  ma = __reduce_max_sync(0xffffffffu, ma);
+  mv = __reduce_max_sync(0xffffffffu, mv);
   if ((threadIdx.x & 31) == 0) { s_max[threadIdx.x >> 5][0] = ma; s_max[threadIdx.x >> 5][1] = mv; }
   __syncthreads();
   if (threadIdx.x == 0) {
 #pragma unroll
-    for (int w = 1; w < BP_THREADS / 32; w++) { ma = fmaxf(ma, s_max[w][0]); mv = fmaxf(mv, s_max[w][1]); }
-    atomic_max_nonneg(&maxout[0], ma);
-    atomic_max_nonneg(&maxout[1], mv);
+    for (int w = 1; w < BP_THREADS / 32; w++) { ma = max(ma, s_max[w][0]); mv = max(mv, s_max[w][1]); }
+    atomicMax(reinterpret_cast<unsigned *>(&maxout[0]), ma);
+    atomicMax(reinterpret_cast<unsigned *>(&maxout[1]), mv);
   }
 }
 

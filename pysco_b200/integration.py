@@ -30,17 +30,26 @@ def _cached_max(x, which):
     return m
 
 
+def _finite(m, what):
+    """The fused interpolation kernel lets a NaN win its max reduction: a non-finite force (e.g. the f(R) cubic root
+    without a real branch, cubic.py:196-197, where the reference stops with a math domain error) must stop the run
+    instead of silently turning every position into NaN."""
+    if not np.isfinite(m):
+        raise ValueError(f"math domain error: max|{what}| is {m} (non-finite {what} after the force computation)")
+    return m
+
+
 def dt_CFL_maxacc(acceleration, param):
     """integration.py:267-295 (free fall)"""
     dx = np.float32(0.5 ** param["ncoarse"])
-    max_acc = _cached_max(acceleration, "acc")
+    max_acc = _finite(_cached_max(acceleration, "acc"), "acceleration")
     return np.float32(param["Courant_factor"]) * np.sqrt(dx / max_acc)
 
 
 def dt_CFL_maxvel(velocity, param):
     """integration.py:298-326"""
     dx = np.float32(0.5 ** param["ncoarse"])
-    max_vel = _cached_max(velocity, "vel")
+    max_vel = _finite(_cached_max(velocity, "vel"), "velocity")
     return np.float32(param["Courant_factor"]) * dx / max_vel
 
 

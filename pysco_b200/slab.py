@@ -898,6 +898,9 @@ class Slab:
             raise RuntimeError("call pm() once before integrate() (the time step needs max|a|, max|v|)")
         if param["integrator"].casefold() != "leapfrog":
             raise NotImplementedError("slab path: integrator must be 'leapfrog'")
+        if not (np.isfinite(self.max_acc) and np.isfinite(self.max_vel)):
+            raise ValueError(f"math domain error: max|a| = {self.max_acc}, max|v| = {self.max_vel} (non-finite "
+                             "particles after the force computation)")
         dx = np.float32(0.5 ** param["ncoarse"])
         cf = np.float32(param["Courant_factor"])
         dt1 = cf * np.sqrt(dx / self.max_acc)

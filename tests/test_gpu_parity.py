@@ -604,3 +604,23 @@ def test_interp_heavy_bins_vs_oracle(psc, orc):
     assert_close(acc.cpu().numpy(), a_ref, 2e-5, "acceleration")
     assert_close(tv.cpu().numpy(), v_ref, 2e-5, "kicked velocity")
     np.testing.assert_allclose(mx.cpu().numpy()[0], np.abs(a_ref).max(), rtol=1e-5)
+
+
+def test_nonfinite_force_stops_the_run(psc):
+    """A NaN reaching the force must surface as an error at the next integrate() (the max reduction of the fused
+    interpolation kernel lets NaN win), not as silently corrupted particles."""
+    import torch
+    N = 16
+    tables = cases.toy_tables()
+    pos = _cuda(cases.lattice_particles(N, 0.3, seed=90))
+    vel = _cuda(cases.velocities(N ** 3, seed=91, scale=1e-3))
+    param = cases.base_param(4, N ** 3, linear_newton_solver="fft")
+    psc.utils.set_units(param)
+    acc, phi, add = psc.solver.pm(pos, param)
+    vel[7, 1] = float("nan")            # one bad particle: its NaN position poisons the density, hence every force
+    param["nsteps"] += 1
+    state = psc.integration.integrate(pos, vel, acc, phi, add, tables, param, 1e30)
+    assert not bool(torch.isfinite(state[2]).all())
+    param["nsteps"] += 1
+    with pytest.raises(ValueError, match="math domain error"):
+        psc.integration.integrate(*state, tables, param, 1e30)
