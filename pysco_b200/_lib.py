@@ -116,7 +116,7 @@ class _Timed:
         self.fn, self.name = fn, name
 
     def __call__(self, *args):
-        if _timing is None:
+        if _timing is None or torch.cuda.is_current_stream_capturing():
             return self.fn(*args)
         e0 = torch.cuda.Event(enable_timing=True)
         e1 = torch.cuda.Event(enable_timing=True)

@@ -56,6 +56,33 @@ def _cycle(kind, x, b, param, nlevel):
     laplacian.smoothing(x, b, param["Npost"])
 
 
+# A V-cycle at 256^3 is ~45 kernels, most of them on coarse levels where a launch costs more than the kernel: the
+# whole cycle is captured once per (grid size, smoothing counts) into a CUDA graph working on persistent buffers and
+# replayed by linear() -- one launch per cycle instead of one per kernel.
+_vcycle_graphs = {}
+
+
+def _graphs_enabled():
+    import os
+    return not os.environ.get("PSC_NO_GRAPHS")
+
+
+def _vcycle_graph(N, param):
+    key = (torch.cuda.current_device(), int(N), int(param["Npre"]), int(param["Npost"]), int(param["ncoarse"]))
+    if key not in _vcycle_graphs:
+        gx, gb = _lib.zeros((N, N, N)), _lib.zeros((N, N, N))
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):            # warm-up outside the capture (allocator, lazy module loading)
+            _cycle("V", gx, gb, param, 0)
+        torch.cuda.current_stream().wait_stream(side)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            _cycle("V", gx, gb, param, 0)
+        _vcycle_graphs[key] = (graph, gx, gb)
+    return _vcycle_graphs[key]
+
+
 def _run_cycle(kind, x, b, param, nlevel):
     c = _lib.Ctx()
     tx, tb = c.dev(x, inplace=True), c.dev(b)
@@ -93,13 +120,27 @@ def linear(x, b, param):
     tolerance = param["tolerance_mond"] if mond_pass else param["tolerance"]
     logging.info("Start linear Multigrid")
     residual_err = 1e30
+    N = tx.shape[0]
+    graph = None
+    if _graphs_enabled() and N >= 32 and not torch.cuda.is_current_stream_capturing():
+        graph, gx, gb = _vcycle_graph(N, param)
+        gx.copy_(tx)
+        gb.copy_(tb)
+        wx, wb = gx, gb
+    else:
+        wx, wb = tx, tb
     while residual_err > tolerance:
-        _cycle("V", tx, tb, param, 0)
-        residual_error_tmp = laplacian.residual_error(tx, tb)
+        if graph is not None:
+            graph.replay()
+        else:
+            _cycle("V", wx, wb, param, 0)
+        residual_error_tmp = laplacian.residual_error(wx, wb)
         logging.info(f"{residual_error_tmp=} {tolerance=}")
         if residual_error_tmp < tolerance or residual_err / residual_error_tmp < 2:
             break
         residual_err = residual_error_tmp
+    if graph is not None:
+        tx.copy_(gx)
     c.finish()
     return x if c.np_mode else tx
 
