@@ -261,6 +261,9 @@ int psc_initialise_potential(const float *b, float q, int N, int kind, float *ou
  * (cubic.py:269-627), quartic.gauss_seidel[_with_rhs] (quartic.py:270-628).  rhs may be NULL. */
 int psc_gauss_seidel(float *x, const float *b, float q, const float *rhs, int N, int kind,
                      float f_relax, void *stream);
+/* While set (non-NULL) the f(R) kernels above read q from this device float instead of their by-value argument, so
+ * that a CUDA graph captured over a FAS cycle follows q from step to step; NULL restores the by-value behaviour. */
+int psc_mg_set_q_device(const float *q_dev);
 /* mesh.restriction / minus_restriction (mesh.py:14-108): coarse = sign/8 * sum of 8 children */
 int psc_restriction(const float *x, int N, float sign, float *coarse, void *stream);
 /* mesh.prolongation / add_prolongation (mesh.py:180-453): fine (2Nc) (+)= P(coarse Nc) */

@@ -61,6 +61,7 @@ SIGNATURES = {
     "psc_slab_yblocks": [_vp, _vp, _i, _i, _i, _i, _vp],
     "psc_pk_slab": [_vp, _i, _i, _i, _i, _vp, _vp],
     "psc_green_slab": [_vp, _i, _i, _i, _i, _i, _f, _vp],
+    "psc_mg_set_q_device": [_vp],
     "psc_linear_operator": [_vp, _f, _f, _vp, _i64, _vp],
     "psc_lincomb": [_vp, _f, _vp, _f, _i64, _vp],
     "psc_gradient": [_vp, _vp, _f, _i, _i, _i, _i, _vp, _i, _vp],

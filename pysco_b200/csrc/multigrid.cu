@@ -199,8 +199,10 @@ __device__ __forceinline__ float solve_quartic(float pf, float qf) {
 }
 
 template <int KIND>
-__global__ void __launch_bounds__(256) init_potential_kernel(const float *__restrict__ b, float q, int N,
+__global__ void __launch_bounds__(256) init_potential_kernel(const float *__restrict__ b, float q_val,
+                                                             const float *__restrict__ q_dev, int N,
                                                              float *__restrict__ out, int64_t n) {
+  const float q = q_dev ? *q_dev : q_val;  // device-resident q: lets a captured CUDA graph follow q from step to step
   for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n;
        t += (int64_t)gridDim.x * blockDim.x) {
     if (KIND == PSC_OP_LAPLACIAN) {
@@ -234,9 +236,11 @@ __global__ void __launch_bounds__(256) init_potential_kernel(const float *__rest
 // colour = 0: even ("black").  Thread per updated cell: threadIdx.x walks k in steps of 2.
 template <int KIND>
 __global__ void __launch_bounds__(TKX *TJ) gs_colour_kernel(float *__restrict__ x,
-                                                            const float *__restrict__ b, float q,
+                                                            const float *__restrict__ b, float q_val,
+                                                            const float *__restrict__ q_dev,
                                                             const float *__restrict__ rhs, int N,
                                                             float f_relax, int colour) {
+  const float q = q_dev ? *q_dev : q_val;
   const int kh = blockIdx.x * TKX + threadIdx.x;
   const int j = blockIdx.y * TJ + threadIdx.y;
   const int i = blockIdx.z;
@@ -346,10 +350,12 @@ enum { MT_OPERATOR = 0, MT_RESIDUAL = 1, MT_SUMSQ = 2 };
 
 template <int KIND, int MODE>
 __global__ void __launch_bounds__(MT_K *MT_J) stencil_march_kernel(const float *__restrict__ x,
-                                                                   const float *__restrict__ b, float q,
+                                                                   const float *__restrict__ b, float q_val,
+                                                                   const float *__restrict__ q_dev,
                                                                    const float *__restrict__ rhs, int N,
                                                                    float *__restrict__ out,
                                                                    double *__restrict__ sumsq) {
+  const float q = q_dev ? *q_dev : q_val;
   __shared__ float tile[2][MT_J + 2][MT_K + 2];
   const int tx = threadIdx.x, ty = threadIdx.y;
   const int k = blockIdx.x * MT_K + tx, j = blockIdx.y * MT_J + ty;
@@ -444,13 +450,23 @@ using namespace psc;
 #define PSC_CHECK_KIND(kind) \
   PSC_CHECK_ARG((kind) >= PSC_OP_LAPLACIAN && (kind) <= PSC_OP_QUARTIC, "unknown operator kind")
 
+static const float *g_q_dev = nullptr;
+
 extern "C" {
+
+/* While set (non-NULL), every f(R) kernel (kinds CUBIC / QUARTIC) reads its q from this device float instead of the
+ * by-value argument: a CUDA graph captured with it set keeps working when q changes from step to step (the host
+ * rewrites the 4 bytes before each replay).  NULL restores the by-value behaviour. */
+int psc_mg_set_q_device(const float *q_dev) {
+  g_q_dev = q_dev;
+  return PSC_OK;
+}
 
 int psc_operator(const float *x, const float *b, float q, int N, int kind, float *out, void *stream) {
   PSC_CHECK_GRID(N);
   PSC_CHECK_KIND(kind);
   PSC_CHECK_ARG(x && out && (b || kind == PSC_OP_LAPLACIAN), "null pointer");
-#define CALL(K) stencil_march_kernel<K, MT_OPERATOR><<<march_grid(N), march_block(), 0, as_stream(stream)>>>(x, b, q, nullptr, N, out, nullptr)
+#define CALL(K) stencil_march_kernel<K, MT_OPERATOR><<<march_grid(N), march_block(), 0, as_stream(stream)>>>(x, b, q, g_q_dev, nullptr, N, out, nullptr)
   PSC_KIND_SWITCH(kind, CALL)
 #undef CALL
   count_launch();
@@ -463,7 +479,7 @@ int psc_residual(const float *x, const float *b, float q, const float *rhs, int 
   PSC_CHECK_GRID(N);
   PSC_CHECK_KIND(kind);
   PSC_CHECK_ARG(x && b && out && (rhs || kind == PSC_OP_LAPLACIAN), "null pointer");
-#define CALL(K) stencil_march_kernel<K, MT_RESIDUAL><<<march_grid(N), march_block(), 0, as_stream(stream)>>>(x, b, q, rhs, N, out, nullptr)
+#define CALL(K) stencil_march_kernel<K, MT_RESIDUAL><<<march_grid(N), march_block(), 0, as_stream(stream)>>>(x, b, q, g_q_dev, rhs, N, out, nullptr)
   PSC_KIND_SWITCH(kind, CALL)
 #undef CALL
   count_launch();
@@ -485,7 +501,7 @@ int psc_residual_sumsq(const float *x, const float *b, float q, int N, int kind,
   PSC_CHECK_GRID(N);
   PSC_CHECK_KIND(kind);
   PSC_CHECK_ARG(x && b && sumsq_out, "null pointer");
-#define CALL(K) stencil_march_kernel<K, MT_SUMSQ><<<march_grid(N), march_block(), 0, as_stream(stream)>>>(x, b, q, nullptr, N, nullptr, sumsq_out)
+#define CALL(K) stencil_march_kernel<K, MT_SUMSQ><<<march_grid(N), march_block(), 0, as_stream(stream)>>>(x, b, q, g_q_dev, nullptr, N, nullptr, sumsq_out)
   PSC_KIND_SWITCH(kind, CALL)
 #undef CALL
   count_launch();
@@ -508,7 +524,7 @@ int psc_initialise_potential(const float *b, float q, int N, int kind, float *ou
   PSC_CHECK_KIND(kind);
   PSC_CHECK_ARG(b && out, "null pointer");
   int64_t n = (int64_t)N * N * N;
-#define CALL(K) init_potential_kernel<K><<<grid_for(n, 256), 256, 0, as_stream(stream)>>>(b, q, N, out, n)
+#define CALL(K) init_potential_kernel<K><<<grid_for(n, 256), 256, 0, as_stream(stream)>>>(b, q, g_q_dev, N, out, n)
   PSC_KIND_SWITCH(kind, CALL)
 #undef CALL
   count_launch();
@@ -523,7 +539,7 @@ int psc_gauss_seidel(float *x, const float *b, float q, const float *rhs, int N,
   PSC_CHECK_ARG(x && b, "null pointer");
   dim3 grid((N / 2 + TKX - 1) / TKX, (N + TJ - 1) / TJ, N);
   for (int colour = 1; colour >= 0; colour--) {
-#define CALL(K) gs_colour_kernel<K><<<grid, cell_block(), 0, as_stream(stream)>>>(x, b, q, rhs, N, f_relax, colour)
+#define CALL(K) gs_colour_kernel<K><<<grid, cell_block(), 0, as_stream(stream)>>>(x, b, q, g_q_dev, rhs, N, f_relax, colour)
     PSC_KIND_SWITCH(kind, CALL)
 #undef CALL
     count_launch();

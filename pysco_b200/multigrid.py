@@ -211,6 +211,36 @@ def _cycle_FAS(kind, x, b, param, nlevel, rhs):
     smoothing(x, b, param["Npost"], param, rhs)
 
 
+_fas_graphs = {}
+
+
+def _fas_graph(N, param):
+    """CUDA graph of one FAS V-cycle on persistent buffers.  q (param["fR_q"]) changes every step, so the f(R) kernels
+    read it from a device scalar while the graph is captured (psc_mg_set_q_device) and the host rewrites that scalar
+    before each replay."""
+    key = (torch.cuda.current_device(), int(N), int(param["Npre"]), int(param["Npost"]), int(param["ncoarse"]),
+           int(param["fR_n"]))
+    if key not in _fas_graphs:
+        lib = _lib.load()
+        gx, gb, gq = _lib.zeros((N, N, N)), _lib.zeros((N, N, N)), _lib.zeros((1,))
+        gx.fill_(1.0)
+        gq.fill_(float(param["fR_q"]))
+        _lib.check(lib.psc_mg_set_q_device(_lib.ptr(gq)))
+        try:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                _cycle_FAS("V", gx, gb, param, 0, _EMPTY)
+            torch.cuda.current_stream().wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                _cycle_FAS("V", gx, gb, param, 0, _EMPTY)
+        finally:
+            _lib.check(lib.psc_mg_set_q_device(None))
+        _fas_graphs[key] = (graph, gx, gb, gq)
+    return _fas_graphs[key]
+
+
 def _run_cycle_FAS(kind, x, b, param, nlevel, rhs):
     c = _lib.Ctx()
     tx, tb = c.dev(x, inplace=True), c.dev(b)
@@ -241,12 +271,27 @@ def FAS(x, b, param):
     tolerance = param["tolerance_FAS"]
     logging.info("Start Full-Approximation Storage Multigrid")
     residual_err = 1e30
+    N = tx.shape[0]
+    graph = None
+    if _graphs_enabled() and N >= 32 and not torch.cuda.is_current_stream_capturing():
+        graph, gx, gb, gq = _fas_graph(N, param)
+        gq.fill_(float(np.float32(param["fR_q"])))
+        gx.copy_(tx)
+        gb.copy_(tb)
+        wx, wb = gx, gb
+    else:
+        wx, wb = tx, tb
     while residual_err > tolerance:
-        _cycle_FAS("V", tx, tb, param, 0, _EMPTY)
-        residual_error_tmp = residual_error(tx, tb, param)
+        if graph is not None:
+            graph.replay()
+        else:
+            _cycle_FAS("V", wx, wb, param, 0, _EMPTY)
+        residual_error_tmp = residual_error(wx, wb, param)
         logging.info(f"{residual_error_tmp=} {tolerance=}")
         if residual_error_tmp < tolerance or residual_err / residual_error_tmp < 2:
             break
         residual_err = residual_error_tmp
+    if graph is not None:
+        tx.copy_(gx)
     c.finish()
     return x if c.np_mode else tx

@@ -24,13 +24,20 @@ if cfg == 2:
 elif cfg == 3:
     param["theory"], param["fR_logfR0"], param["fR_n"] = "fr", 5, 1
     param["linear_newton_solver"] = "multigrid"
+    param["aexp"] = param["aexp_old"] = 0.05
 else:
     param["theory"], param["mond_function"], param["mond_g0"] = "mond", "simple", 1.2
     param["mond_scale_factor_exponent"], param["mond_alpha"] = 0, 1
     param["linear_newton_solver"] = "fft_7pt"
 param["t"] = float(tables[1](np.log(param["aexp"])))
 utils.set_units(param)
-pos, vel, _ = bench.slab_ics(N, 0, N)
+pos, vel, _ = bench.slab_ics(N, 0, N, vel_rms=1e-3 if cfg != 3 else 1e-5)
+if cfg == 3:
+    # nearly linear density field: with the 0.3-cell jitter of the PM bench the reference's cubic root formula has no
+    # real branch after a few steps (cubic.py:196-197) and the run stops with a math domain error, as in the reference
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    import cases
+    pos = torch.from_numpy(cases.lattice_particles(N, 0.02, seed=5)).cuda()
 pos, vel = utils.reorder_particles(pos, vel)
 state = [pos, vel] + list(solver.pm(pos, param, tables=tables))
 for _ in range(3):
