@@ -78,6 +78,9 @@ class TorchComm:
         self.group = group
         self.rank = dist.get_rank(group)
         self.size = dist.get_world_size(group)
+        self._mbox = None          # (buffer, handle, floats per slot) | False when peer memory is unavailable
+        self._mbox_set = 0
+        self._use_mailbox = not os.environ.get("PSC_NO_PEER_MAILBOX")
 
     def exchange_counts(self, counts):
         dev = "cuda" if dist.get_backend(self.group) == "nccl" else "cpu"
@@ -95,7 +98,46 @@ class TorchComm:
         dist.all_to_all_single(out, send, group=self.group)
         return out
 
+    # -- neighbour messages through peer memory: every rank owns a "mailbox" in symmetric memory with two slots (from
+    # the left / from the right neighbour) in two alternating sets; a sender copies its message straight into the
+    # neighbour's slot over NVLink (a plain device-to-device copy into the mapped peer buffer), an inter-GPU barrier
+    # on the stream publishes it.  The alternating sets make one barrier per exchange enough: a slot is rewritten two
+    # exchanges later, after a barrier that its owner only reaches once it has consumed the previous content.
+    def _mailbox(self, numel):
+        """symmetric mailbox with room for `numel` float32 per slot, or None (NCCL p2p is used then); collective"""
+        if self._mbox is False:
+            return None
+        if self._mbox is None or self._mbox[2] < numel:
+            cap = int(numel * 1.25) + 1024
+            bufs = self.symmetric_buffers(4 * cap, 1)
+            if not bufs:
+                self._mbox = False
+                return None
+            self._mbox = (bufs[0][0], bufs[0][1], cap)
+            self._mbox_set = 0
+        return self._mbox
+
     def _p2p(self, to_left, to_right, from_left, from_right):
+        P, r = self.size, self.rank
+        left, right = (r - 1) % P, (r + 1) % P
+        n = max(to_left.numel(), to_right.numel(), from_left.numel(), from_right.numel())
+        mb = self._mailbox(n) if (to_left.is_cuda and to_left.dtype == torch.float32 and self._use_mailbox) else None
+        if mb is None:
+            return self._p2p_nccl(to_left, to_right, from_left, from_right)
+        buf, hdl, cap = mb
+        base = self._mbox_set * 2 * cap          # slot 0: from the left neighbour, slot 1: from the right neighbour
+        self._mbox_set ^= 1
+        if to_left.numel():      # I am my left neighbour's RIGHT neighbour
+            hdl.get_buffer(left, (to_left.numel(),), torch.float32, base + cap).copy_(to_left.reshape(-1))
+        if to_right.numel():
+            hdl.get_buffer(right, (to_right.numel(),), torch.float32, base).copy_(to_right.reshape(-1))
+        hdl.barrier(channel=0)
+        if from_left.numel():
+            from_left.reshape(-1).copy_(buf[base:base + from_left.numel()])
+        if from_right.numel():
+            from_right.reshape(-1).copy_(buf[base + cap:base + cap + from_right.numel()])
+
+    def _p2p_nccl(self, to_left, to_right, from_left, from_right):
         """One batch of point-to-point messages with the two neighbours (4 NCCL p2p ops instead of the P (P - 1)
         of an all-to-all).  Message order per peer is what pairs sends with receives when P == 2 (the peer is both
         neighbours): sends go out as [to_left, to_right], receives are posted as [from_right, from_left]."""
@@ -865,8 +907,10 @@ class Slab:
         m = mx.cpu().numpy()
         self._mark("allreduce max")
         self.max_acc, self.max_vel = np.float32(m[0]), np.float32(m[1])
-        if self._mig_cap is not None and m[2] > self._mig_cap:
-            self._mig_cap = 2 * int(m[2]) + 4096      # identical on every rank: m[2] is the all-reduced maximum
+        if self._mig_cap is not None and (m[2] > self._mig_cap or 8 * m[2] + 4096 < self._mig_cap):
+            # grow after an overflow, shrink when the buffers are far larger than the traffic (they are exchanged in
+            # full every step); identical on every rank: m[2] is the all-reduced maximum
+            self._mig_cap = 2 * int(m[2]) + 4096
         return mx[:2]
 
     # -- integration.integrate / leapfrog on the slab
