@@ -320,6 +320,7 @@ class CudaOps:
         self._scratch = None
         self._leavers = None
         self._mig = None
+        self._sortws = None
 
     # -- particles
     def kick_drift_wrap(self, pos, vel, acc, half_dt, dt, dt_is_f64):
@@ -402,15 +403,27 @@ class CudaOps:
         return out
 
     def morton_order(self, pos):
-        """permutation that sorts the local particles by Morton key (morton.py:42-137, utils.py:1019-1075)"""
-        from . import utils
+        """permutation that sorts the local particles by Morton key (morton.py:42-137, utils.py:1019-1075).  The keys,
+        the permutation and the sort scratch live in one persistent (grow-only) workspace: a reorder allocates
+        nothing, so it cannot push the caching allocator into cudaMalloc / cudaFree storms in the step after it."""
         n = pos.shape[0]
-        keys = torch.empty((n,), dtype=torch.int64, device=self.dev)
+        nbytes = int(self.lib.psc_argsort_workspace_bytes(n))
+        need = 16 * n + nbytes + 512
+        if self._sortws is None or self._sortws.numel() < need:
+            self._sortws = None
+            self._sortws = torch.empty((int(need * 1.1) + 1024,), dtype=torch.uint8, device=self.dev)
+        ws = self._sortws
+        keys = ws[:8 * n].view(torch.int64)
+        idx = ws[8 * n:16 * n].view(torch.int64)
+        off = (16 * n + 255) // 256 * 256
+        scratch = ws[off:]
         _lib.check(self.lib.psc_morton_keys(_lib.ptr(pos), n, _lib.ptr(keys), _lib.stream()))
-        return utils.argsort_keys(keys)
+        _lib.check(self.lib.psc_argsort_keys(_lib.ptr(keys), n, _lib.ptr(idx), _lib.ptr(scratch), scratch.numel(),
+                                             _lib.stream()))
+        return idx
 
-    def gather_rows(self, idx, a):
-        out = torch.empty_like(a)
+    def gather_rows(self, idx, a, out=None):
+        out = torch.empty_like(a) if out is None else out
         _lib.check(self.lib.psc_gather3(_lib.ptr(idx), _lib.ptr(a), _lib.ptr(out), a.shape[0], _lib.stream()))
         return out
 
@@ -518,6 +531,7 @@ class Slab:
         self.potential = None  # owned planes [nxl, N, N] of the last solve (a view into the ghosted array)
         self.migrated_last = (0, 0)
         self._warm_host_ops()
+        self._spare3 = self._spare1 = None   # spare particle buffers the reorder gathers into (then swapped in)
         self._peer = None         # symmetric (peer-addressable) spectrum buffers, resolved at the first solve
         self._mig_cap = None      # records per direction of the fixed-capacity migration buffers (same on all ranks)
         self._mig_want = 0        # largest message of the last migration; all-reduced in pm() to resize _mig_cap
@@ -967,10 +981,18 @@ class Slab:
         if n == 0:
             return
         idx = self.ops.morton_order(self.pos[:n])
+        # gather into a persistent spare buffer and swap it in: no allocation, no copy back
+        cap = self.pos.shape[0]
+        if self._spare3 is None or self._spare3.shape[0] != cap:
+            self._spare3 = torch.empty((cap, 3), dtype=torch.float32, device=self._device())
+            self._spare1 = torch.empty((cap,), dtype=torch.int64, device=self._device())
         for name in ("pos", "vel", "acc"):
             a = getattr(self, name)
-            a[:n] = self.ops.gather_rows(idx, a[:n].contiguous())
-        self.ids[:n] = self.ids[:n][idx]
+            self.ops.gather_rows(idx, a[:n], self._spare3[:n])
+            setattr(self, name, self._spare3)
+            self._spare3 = a
+        torch.index_select(self.ids[:n], 0, idx, out=self._spare1[:n])
+        self.ids, self._spare1 = self._spare1, self.ids
 
     # -- gathering results in the reference's order (tests / snapshots)
     def gather_to_root(self, npart_total):

@@ -116,8 +116,12 @@ class OracleOps:
         keys = oracle.morton.positions_to_keys(np.ascontiguousarray(_np(pos)))
         return torch.from_numpy(np.argsort(keys, kind="stable").astype(np.int64))
 
-    def gather_rows(self, idx, a):
-        return a[idx]
+    def gather_rows(self, idx, a, out=None):
+        r = a[idx]
+        if out is None:
+            return r
+        out.copy_(r)
+        return out
 
     # -- particles <-> mesh (oracle on the full periodic grid, cut to the slab + ghosts)
     def bin(self, pos):
