@@ -104,7 +104,14 @@ def get_transfer_grid(param):
     return np.interp(k_grid, k_dimensionless, sqrtPk)
 
 
-def generate_density_fourier(param):
+def _periodic_wrap(x):
+    """utils.periodic_wrap (utils.py:1120-1149) with torch ops (device-agnostic; the step's CUDA kernel does the same)"""
+    eps = -2.98023223876953125e-08 * (1.0 + 1e-6)
+    neg = torch.where(x.double() > eps, torch.zeros_like(x), x + 1.0)
+    return torch.where(x < 0, neg, torch.where(x >= 1.0, x - 1.0, x))
+
+
+def generate_density_fourier(param, device=None):
     """initial_conditions.py:402-445 -> device complex64 [N, N, N/2+1]"""
     transfer = get_transfer_grid(param)
     N = transfer.shape[0]
@@ -115,7 +122,7 @@ def generate_density_fourier(param):
     else:
         d = white_noise_fourier(N, rng)
     d = (d * transfer).astype(np.complex64)   # complex64 *= float64, rounded once like the reference
-    return torch.from_numpy(np.ascontiguousarray(d)).to(_lib.device())
+    return torch.from_numpy(np.ascontiguousarray(d)).to(_lib.device() if device is None else device)
 
 
 # ------------------------------------------------------------------------------------------ spectral operators
@@ -334,7 +341,7 @@ def finalise_initial_conditions(position, velocity, param, do_reorder):
     """initial_conditions.py:216-280: wrap (+ reorder) and write snapshot 0"""
     if "base" not in param:
         raise ValueError(f"{param.index=}, should contain 'base'")
-    utils.periodic_wrap(position)
+    position.copy_(_periodic_wrap(position))
     if do_reorder:
         position, velocity = utils.reorder_particles(position, velocity)
     fmt = param["output_snapshot_format"].casefold()
@@ -350,9 +357,11 @@ def finalise_initial_conditions(position, velocity, param, do_reorder):
     return position, velocity
 
 
-def generate(param, tables, write_snapshot=True):
+def generate(param, tables, write_snapshot=True, device=None):
     """initial_conditions.py:25-213 for initial_conditions in {1LPT, 2LPT, 3LPT}.  Returns device tensors
-    (position, velocity) [Npart, 3] in the reference's lattice (lexicographic) order."""
+    (position, velocity) [Npart, 3] in the reference's lattice (lexicographic) order.  `device` (default: the current
+    CUDA device) exists for the CPU test tier: this row is built from torch ops only, so the same code is checked
+    against the reference's output without a GPU too."""
     IC = param["initial_conditions"]
     if not (isinstance(IC, str) and "lpt" in IC.casefold()):
         raise ValueError(f"{IC=}, should be 1LPT, 2LPT or 3LPT")
@@ -366,7 +375,7 @@ def generate(param, tables, write_snapshot=True):
     mpc_to_km = 1e3 * _PC
     Hz = Hz * param["unit_t"] / mpc_to_km  # km/s/Mpc to BU
 
-    phi1 = inverse_laplacian(generate_density_fourier(param))
+    phi1 = inverse_laplacian(generate_density_fourier(param, device))
     psi1 = ifft_3D_real_grad(gradient(phi1))
     logging.warning("Compute 1LPT contribution")
     dplus_1_z0 = tables[3](0)
@@ -381,7 +390,7 @@ def generate(param, tables, write_snapshot=True):
         if write_snapshot:
             finalise_initial_conditions(pos, vel, param, do_reorder=False)
         else:
-            utils.periodic_wrap(pos)
+            pos = _periodic_wrap(pos)
         return pos, vel
 
     if order == "1lpt":

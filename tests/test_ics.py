@@ -37,9 +37,7 @@ def test_density_fourier_host_part_matches_reference(tmp_path):
     assert np.max(np.abs(d - ref)) < 2e-6 * np.max(np.abs(ref))
 
 
-@pytest.mark.gpu
-@pytest.mark.parametrize("name", list(cases.IC_CASES))
-def test_generate_matches_reference(name, tmp_path):
+def _generate_and_check(name, tmp_path, device):
     import pandas as pd
     from pysco_b200 import initial_conditions as ic, utils
     param = pd.Series(cases.ic_param(str(tmp_path), **cases.IC_CASES[name]))
@@ -50,7 +48,7 @@ def test_generate_matches_reference(name, tmp_path):
     tables = [None, None, lambda x: t[0], lambda x: t[1] if x == 0 else t[2]] + \
              [(lambda v: (lambda x: v))(v) for v in t[3:]]
     os.makedirs(os.path.join(str(tmp_path), "output_00000"), exist_ok=True)
-    pos, vel = ic.generate(param, tables)
+    pos, vel = ic.generate(param, tables, device=device)
     pos, vel = pos.cpu().numpy(), vel.cpu().numpy()
     rpos, rvel = G[f"{name}_pos"], G[f"{name}_vel"]
     d = np.abs(pos - rpos)
@@ -58,3 +56,15 @@ def test_generate_matches_reference(name, tmp_path):
     assert d.max() < 2e-6, d.max()                                   # box units (cell = 1/16)
     assert np.max(np.abs(vel - rvel)) < 2e-5 * np.sqrt(np.mean(rvel.astype(np.float64) ** 2)) + 1e-9
     assert os.path.exists(os.path.join(str(tmp_path), "output_00000", "particles_test.parquet"))
+
+
+@pytest.mark.parametrize("name", list(cases.IC_CASES))
+def test_generate_matches_reference_cpu(name, tmp_path):
+    """the LPT chain is torch ops only: the same code on CPU tensors against the reference's particles"""
+    _generate_and_check(name, tmp_path, "cpu")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", list(cases.IC_CASES))
+def test_generate_matches_reference(name, tmp_path):
+    _generate_and_check(name, tmp_path, None)
