@@ -262,7 +262,7 @@ def workload_config(ncoarse):
     N = 2 ** ncoarse
     return {"workload": f"Newtonian FFT-PM leapfrog step, {N}^3 particles on {N}^3 mesh, TSC, compensated Green, "
                         f"5-pt gradient, n_reorder={N_REORDER} (BASELINE configs[0] shape at the metric's {N}^3 size)",
-            "ncells_1d": N, "npart": N ** 3, "ics": "lattice + N(0, 0.3 cell) displacement, seed 42, Morton-ordered; velocities: 8 long-wavelength plane waves per component, rms 1e-3 (coherent flows)",
+            "ncells_1d": N, "npart": N ** 3, "ics": "lattice + N(0, 0.3 cell) displacement, seed 42 (generated per x-slab), Morton-ordered; velocities: 8 long-wavelength plane waves per component, rms 1e-3 (coherent flows)",
             "l2_policy": "inputs larger than L2 (particle arrays 3 x %.1f GB, grids %.2f GB vs 126 MB L2)" % (
                 12 * N ** 3 / 1e9, 4 * N ** 3 / 1e9)}
 
@@ -597,9 +597,7 @@ def run_slab_arm(args):
             cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
                    "sample": f"{Nc}^3 particles / {Nc}^3 mesh full leapfrog step of the same workload shape "
                              f"(1 warm-up + 1 timed, {ms:.0f} ms); numpy-pocketfft FFT"}
-        cfg = workload_config(nc)
-        cfg["ics"] = ("lattice + N(0, 0.3 cell) displacement, generated per slab, Morton-ordered per slab; velocities: "
-                      "8 long-wavelength plane waves per component, rms 1e-3 (coherent flows)")
+        cfg = workload_config(nc)   # identical to the reference arm's config (same N^3 problem on every GPU count)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
