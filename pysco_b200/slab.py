@@ -1015,14 +1015,14 @@ class Slab:
 
 
 # ------------------------------------------------------------------------------------------ main.run on slabs
-def run(param, comm=None, initial_state=None):
+def run(param, comm=None, initial_state=None, ops_factory=None):
     """`main.run` (main.py:30-156) on x-slabs: one call per rank (torchrun; or one thread per virtual rank with a
     ThreadComm).  Every rank derives the same background tables; the initial particles come from `initial_state`
     (global arrays, identical on every rank) or are generated identically on every rank (initial_conditions.generate:
     meshes that fit one GPU) -- each rank adopts a strided share and the first migration routes the particles to their
     slabs.  Snapshots are gathered to rank 0 in the reference's particle order.  Newtonian / parametrized gravity,
     FFT solvers, leapfrog (what Slab.pm supports).  Returns (position, velocity) of the final state on rank 0
-    (CPU tensors, reference order), None elsewhere."""
+    (CPU tensors, reference order), None elsewhere.  ops_factory(N, P, rank) replaces the CUDA kernels (tests only)."""
     import pandas as pd
     from . import cosmotable, iostream, utils
     from . import main as _main
@@ -1056,7 +1056,8 @@ def run(param, comm=None, initial_state=None):
         position, velocity = initial_state
     utils.set_units(param)
     param["t"] = tables[1](np.log(param["aexp"]))
-    S = Slab(2 ** param["ncoarse"], comm=comm)
+    N = 2 ** param["ncoarse"]
+    S = Slab(N, comm=comm, ops=None if ops_factory is None else ops_factory(N, comm.size, comm.rank))
     dev = S._device()
     position = torch.as_tensor(position, dtype=torch.float32).to(dev)
     velocity = torch.as_tensor(velocity, dtype=torch.float32).to(dev)

@@ -164,3 +164,39 @@ def test_slab_gloo_world2_vs_oracle():
         mp.spawn(_gloo_worker, args=(2, port, out), nprocs=2, join=True)
         out = dict(out)
     _check(out, ref, ref_t, 2)
+
+
+def test_slab_run_loop_threads_vs_reference_snapshot(tmp_path):
+    """slab.run (main.run on slabs: snapshot schedule, per-slab reorder, gather in reference order, P(k) skipped) on 2
+    virtual ranks with the oracle standing in for the kernels, z = 49 -> 0 at 32^3, against the final snapshot of the
+    unmodified reference (tests/golden/run.npz)."""
+    import glob
+    from pysco_b200 import slab
+    from slab_oracle_ops import OracleOps
+    g = np.load(os.path.join(ROOT, "tests", "golden", "run.npz"))
+    base = str(tmp_path) + "/"
+    out, errs = {}, []
+    comms = slab.ThreadComm.world(2)
+
+    def work(c):
+        try:
+            param = cases.run_param(base, "fft")
+            param["save_power_spectrum"] = "no"
+            res = slab.run(param, comm=c, initial_state=(g["ic_pos"].copy(), g["ic_vel"].copy()),
+                           ops_factory=OracleOps)
+            if c.rank == 0:
+                out["pos"], out["vel"] = res[0].numpy(), res[1].numpy()
+        except BaseException as e:  # noqa: BLE001
+            errs.append(e)
+            c.w.barrier.abort()
+
+    ts = [threading.Thread(target=work, args=(c,)) for c in comms]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    if errs:
+        raise errs[0]
+    d = np.abs(out["pos"] - g["fft_pos"])
+    d = np.minimum(d, 1 - d)
+    assert d.max() < 1e-5, d.max()
+    assert np.abs(out["vel"] - g["fft_vel"]).max() < 1e-4 * np.abs(g["fft_vel"]).max() + 1e-7
+    assert len(glob.glob(os.path.join(base, "output_0000[1-6]", "particles_*.parquet"))) == 6
