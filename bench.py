@@ -64,8 +64,9 @@ ALGO_BYTES = {
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the ncu --set full capture of this same workload
-# (512^3, one GPU): profiles/r01_final_deposit_interp_ncu.txt
-NCU_TRAFFIC_512 = {"psc_interp_kick_phi_binned": 4.900609e9 + 3.384357e9, "psc_deposit_binned": 2.150668e9 + 0.517231e9}
+# (512^3, one GPU): profiles/r01_final_kernels_ncu.txt
+NCU_TRAFFIC_512 = {"psc_interp_kick_phi_binned": 4.900826e9 + 3.384417e9, "psc_deposit_binned": 2.688113e9 + 0.523306e9,
+                   "psc_kick_drift_wrap_count": 4.835572e9 + 3.177392e9}
 
 # whole Newtonian FFT step: kick/drift/wrap 60 + deposit 16 + FFT 8 + Green 8 + inverse FFT 8 + gradient 16 +
 # interpolation/kick 60 = 176 B per particle-update
@@ -380,7 +381,7 @@ def run_gpu_arm(args):
     roofline = {"bound": "hbm", "kernel": dom, "achieved": kern[dom]["achieved_gbs"], "peak": peak,
                 "unit": "GB/s", "frac": kern[dom]["achieved_gbs"] / peak,
                 "traffic": NCU_TRAFFIC_512.get(dom) if (N == 512 and world == 1) else None,
-                "traffic_source": "profiles/r01_final_deposit_interp_ncu.txt (ncu --set full, bytes per launch)",
+                "traffic_source": "profiles/r01_final_kernels_ncu.txt (ncu --set full, bytes per launch)",
                 "peak_source": peak_src, "algo_bytes_per_launch": kern[dom]["algo_bytes"],
                 "ms_per_launch": kern[dom]["ms_per_call"],
                 "whole_step": {"algo_bytes": step_algo_bytes,
