@@ -50,6 +50,7 @@ ALGO_BYTES = {
     "psc_deposit_binned": 16.0,
     "psc_bin_particles": 0.0,      # pure overhead of the order-independent scheme (not in the 176 B budget)
     # x-slab path (every kernel works on N^3 / P particles or cells)
+    "psc_kick_drift_wrap_slab": 60.0,      # kick + drift + wrap + leaver detection
     "psc_bin_particles_slab": 0.0,
     "psc_deposit_binned_slab": 16.0,
     "psc_linear_operator": 8.0,            # RHS affine map (fused into the deposit on the single-domain path)
