@@ -200,3 +200,51 @@ def test_slab_run_loop_threads_vs_reference_snapshot(tmp_path):
     assert d.max() < 1e-5, d.max()
     assert np.abs(out["vel"] - g["fft_vel"]).max() < 1e-4 * np.abs(g["fft_vel"]).max() + 1e-7
     assert len(glob.glob(os.path.join(base, "output_0000[1-6]", "particles_*.parquet"))) == 6
+
+
+def _gloo3_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    for p in (ROOT, os.path.join(ROOT, "tests"), os.path.join(ROOT, "tests", "golden")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    import torch.distributed as dist
+    from pysco_b200 import distributed, slab
+    distributed.init_from_env("gloo")
+    comm = slab.default_comm()
+    left, right = (rank - 1) % world, (rank + 1) % world
+    ok = True
+    # ghost planes: from_left is the left neighbour's to_right, from_right the right neighbour's to_left
+    fl, fr = comm.exchange_planes(torch.full((2, 3), 10.0 * rank + 1), torch.full((2, 3), 10.0 * rank + 2))
+    ok &= bool((fl == 10.0 * left + 2).all() and (fr == 10.0 * right + 1).all())
+    # variable-size neighbour messages (migration records): sizes differ per rank and direction
+    n_l, n_r = rank + 1, 2 * rank + 1
+    from_l, from_r = comm.neighbor_counts(n_l, n_r)
+    ok &= from_l == 2 * left + 1 and from_r == right + 1
+    got_l, got_r = comm.neighbor_exchange(torch.full((n_l, 8), float(rank)), torch.full((n_r, 8), float(rank) + 0.5),
+                                          from_l, from_r)
+    ok &= got_l.shape == (from_l, 8) and got_r.shape == (from_r, 8)
+    ok &= bool((got_l == left + 0.5).all() and (got_r == float(right)).all())
+    # equal-split all-to-all (the NCCL fallback of the FFT transposes): block s of rank r goes to rank s
+    send = torch.arange(world * 4, dtype=torch.float32).view(world, 4) + 100.0 * rank
+    recv = torch.empty_like(send)
+    comm.all_to_all_equal(send, recv)
+    want = torch.stack([torch.arange(4, dtype=torch.float32) + 4 * rank + 100.0 * s for s in range(world)])
+    ok &= bool(torch.equal(recv, want))
+    t = torch.tensor([float(rank), 5.0 - rank])
+    comm.allreduce_max_(t)
+    ok &= t.tolist() == [float(world - 1), 5.0]
+    out[rank] = bool(ok)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_torchcomm_semantics_gloo_world3():
+    """TorchComm with three ranks (left and right neighbours are different processes): the point-to-point pairing of
+    ghost planes and migration messages, the equal all-to-all and the reductions."""
+    import torch.multiprocessing as mp
+    port = _free_port()
+    with mp.Manager() as mgr:
+        out = mgr.dict()
+        mp.spawn(_gloo3_worker, args=(3, port, out), nprocs=3, join=True)
+        assert dict(out) == {0: True, 1: True, 2: True}
