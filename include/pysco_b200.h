@@ -271,6 +271,25 @@ int psc_prolongation(float *fine, const float *coarse, int Nc, int add, void *st
 /* mond.rhs_simple/n/beta/gamma/delta (mond.py:171-932) */
 int psc_mond_rhs(const float *phi, float *out, int N, float g0, int fn, float alpha, void *stream);
 
+/* ---- multigrid on an x-slab (ghost-plane stencils).  A slab level holds nxl owned planes of n x n cells;
+ * "xg" arrays are [nxl + 2][n][n] with one ghost plane on each side along x (the host fills them from the neighbours,
+ * pysco_b200/slab.py), "b" / outputs hold the owned planes only; y and z are periodic.  Same arithmetic as the
+ * single-domain entries above. */
+/* one colour of laplacian.gauss_seidel (laplacian.py:844-1022): colour 1 = cells with odd x0 + il + j + k (the
+ * reference's first half-sweep), colour 0 = even; x0 = global index of the first owned plane.  The ghost planes must
+ * be refreshed between the two colours. */
+int psc_box_gauss_seidel_colour(float *xg, const float *b, int nxl, int n, int x0, int colour, float f_relax,
+                                void *stream);
+/* laplacian.operator (laplacian.py:12-54): out[nxl][n][n] = L xg */
+int psc_box_operator(const float *xg, int nxl, int n, float *out, void *stream);
+/* laplacian.restrict_residual (laplacian.py:125-226): coarse[nxl/2][n/2][n/2] = R(b - L xg); nxl even */
+int psc_box_restrict_residual(const float *xg, const float *b, int nxl, int n, float *coarse, void *stream);
+/* mesh.restriction / minus_restriction (mesh.py:14-108) of owned planes: coarse[nxl/2][n/2][n/2]; nxl even */
+int psc_box_restriction(const float *fine, int nxl, int n, float sign, float *coarse, void *stream);
+/* mesh.add_prolongation (mesh.py:334-453): fine_g[2 nxlc + 2][2 nc][2 nc] += P(coarse_g[nxlc + 2][nc][nc]); the coarse
+ * ghost planes must be current, the fine ghost planes are not touched */
+int psc_box_add_prolongation(float *fine_g, const float *coarse_g, int nxlc, int nc, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

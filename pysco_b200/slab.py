@@ -11,6 +11,9 @@ The reference is single-process (README.md:49); this module is the multi-GPU for
                                ghost planes SENT to the neighbours and ADDED there
   FFT Poisson solve            2-D R2C per plane -> y-block all-to-all -> 1-D C2C along x -> Green ->
                                inverse 1-D -> all-to-all -> 2-D C2R      (psc_slab_fft_*, psc_green_slab)
+  multigrid Poisson solve      (linear_newton_solver = multigrid) V-cycles on ghosted slabs: ghost planes refreshed
+                               before every half-sweep / residual / prolongation, coarse levels thinner than two
+                               planes per rank gathered and solved redundantly (slab_multigrid.py, psc_box_*)
   gradient + interpolation     potential with G = 1 + stencil-reach ghost planes COPIED from the neighbours
                                (psc_interp_kick_phi_binned_slab: gradient, TSC gather, half-kick, max|a|, max|v|)
   time step                    all-reduce(max) of two floats
@@ -500,6 +503,47 @@ class CudaOps:
         _lib.check(self.lib.psc_green_slab(_lib.ptr(spec_t), self.N, self.nyl, self.y0, kind, p, float(scale),
                                            _lib.stream()))
 
+    # -- multigrid on the slab (csrc/slab_mg.cu; host sequencing in slab_multigrid.py)
+    def mg_gs_colour(self, xg, b, nxl, n, x0, colour, f_relax):
+        _lib.check(self.lib.psc_box_gauss_seidel_colour(_lib.ptr(xg), _lib.ptr(b), nxl, n, x0, colour,
+                                                        float(f_relax), _lib.stream()))
+
+    def mg_operator(self, xg, nxl, n):
+        out = torch.empty((nxl, n, n), dtype=torch.float32, device=self.dev)
+        _lib.check(self.lib.psc_box_operator(_lib.ptr(xg), nxl, n, _lib.ptr(out), _lib.stream()))
+        return out
+
+    def mg_restrict_residual(self, xg, b, nxl, n):
+        out = torch.empty((nxl // 2, n // 2, n // 2), dtype=torch.float32, device=self.dev)
+        _lib.check(self.lib.psc_box_restrict_residual(_lib.ptr(xg), _lib.ptr(b), nxl, n, _lib.ptr(out),
+                                                      _lib.stream()))
+        return out
+
+    def mg_restriction(self, fine, nxl, n, sign, out=None):
+        if out is None:
+            out = torch.empty((nxl // 2, n // 2, n // 2), dtype=torch.float32, device=self.dev)
+        _lib.check(self.lib.psc_box_restriction(_lib.ptr(fine), nxl, n, float(sign), _lib.ptr(out), _lib.stream()))
+        return out
+
+    def mg_add_prolongation(self, fine_g, coarse_g, nxlc, nc):
+        _lib.check(self.lib.psc_box_add_prolongation(_lib.ptr(fine_g), _lib.ptr(coarse_g), nxlc, nc, _lib.stream()))
+
+    def mg_diff_sumsq(self, a, fa, b):
+        out = torch.zeros((1,), dtype=torch.float64, device=self.dev)
+        _lib.check(self.lib.psc_diff_sumsq(_lib.ptr(a), float(fa), _lib.ptr(b), a.numel(), _lib.ptr(out),
+                                           _lib.stream()))
+        return out
+
+    def mg_cube_solve(self, res_cube, param, nlevel, coarsest):
+        """a gathered coarse level, solved on every rank by the single-domain kernels (multigrid.py:474-517)"""
+        from . import laplacian, multigrid
+        x = laplacian.initialise_potential(res_cube)
+        if coarsest:
+            laplacian.smoothing(x, res_cube, param["Npre"])
+        else:
+            multigrid._cycle("V", x, res_cube, param, nlevel + 1)
+        return x
+
     def close(self):
         if self._plan is not None:
             self.lib.psc_slab_fft_plan_destroy(self._plan)
@@ -532,6 +576,7 @@ class Slab:
         self.migrated_last = (0, 0)
         self._warm_host_ops()
         self._spare3 = self._spare1 = None   # spare particle buffers the reorder gathers into (then swapped in)
+        self._mg = None           # SlabMultigrid (slab_multigrid.py), built at the first multigrid solve
         self._peer = None         # symmetric (peer-addressable) spectrum buffers, resolved at the first solve
         self._mig_cap = None      # records per direction of the fixed-capacity migration buffers (same on all ranks)
         self._mig_want = 0        # largest message of the last migration; all-reduced in pm() to resize _mig_cap
@@ -836,7 +881,7 @@ class Slab:
         ops.yblocks(b, a, False)                # [nxl][N][nz]
         ops.fft2d_c2r(a, out_planes)
 
-    def _write_pk(self, spec_t, param):
+    def _write_pk(self, spec_t, param, from_density=False):
         """fourier.fourier_grid_to_Pk (fourier.py:22-100) + the scaling of solver.fft (solver.py:500-506) on the
         transposed spectrum: per-rank bins, summed over ranks, written by rank 0."""
         from . import iostream
@@ -851,15 +896,51 @@ class Slab:
             k = (b[0, 1:kmax] / nm).astype(np.float32)
             pk = (b[1, 1:kmax] / nm).astype(np.float32)
         pk *= (param["boxlen"] / N ** 2) ** 3
-        pk /= (1.5 * param["aexp"] * param["Om_m"]) ** 2 * param["parametrized_mu_z"] ** 2
+        if not from_density:
+            pk /= (1.5 * param["aexp"] * param["Om_m"]) ** 2 * param["parametrized_mu_z"] ** 2
         k *= 2 * np.pi / param["boxlen"]
         iostream.write_power_spectrum_to_ascii_file(k, pk, nm.astype(np.float32), param)
 
+    def _pk_from_density(self, density_planes, param):
+        """P(k) of the density when the solver is not spectral (solver.py:130-138): forward transposed FFT only, through
+        the all-to-all form of the transpose (output steps only)."""
+        ops = self.ops
+        a = ops.spectrum_buffer()
+        b = ops.spectrum_buffer()
+        ops.fft2d_r2c(density_planes, a)
+        ops.yblocks(a, b, True)
+        self.comm.all_to_all_equal(b.view(self.P, -1), a.view(self.P, -1))
+        ops.fft_x(a, False)
+        self._write_pk(a, param, from_density=True)
+
+    def multigrid_poisson(self, rhs_planes, phi_g, G, param, tables):
+        """solver.initialise_potential + multigrid.linear (solver.py:218-282, multigrid.py:23-83) on the slab.  The
+        solve runs in place inside phi_g (planes G - 1 .. G + nxl are the multigrid's ghosted array); the previous
+        potential, rescaled by a D1(a), is the first guess from the second call on."""
+        from .slab_multigrid import SlabMultigrid
+        if self._mg is None:
+            self._mg = SlabMultigrid(self.comm, self.ops, self.N)
+        nxl = self.nxl
+        xg = phi_g[G - 1:G + nxl + 1]
+        own = xg[1:nxl + 1]
+        if self.potential is None:
+            logging.info("Assign potential from density field")
+            own.copy_(rhs_planes)
+            self.ops.affine(own, SlabMultigrid.first_guess_factor(self.N), 0.0)
+        else:
+            logging.info("Rescale potential from previous step for Newtonian potential")
+            scaling = (param["aexp"] * tables[3](np.log(param["aexp"]))
+                       / (param["aexp_old"] * tables[3](np.log(param["aexp_old"]))))
+            own.copy_(self.potential)
+            self.ops.affine(own, np.float32(scaling), 0.0)
+        self._mg.linear(xg, rhs_planes, param)
+
     # -- solver.pm on the slab
-    def pm(self, param, kick=None):
-        """solver.pm (solver.py:30-215), Newtonian / parametrized, FFT solvers.  Fills self.acc[:np]; with
-        kick = half_dt also applies the second half-kick to the velocities.  Returns the device tensor
-        [max|a|, max|v|] already reduced over ranks."""
+    def pm(self, param, kick=None, tables=None):
+        """solver.pm (solver.py:30-215), Newtonian / parametrized; linear_newton_solver = fft, fft_7pt or multigrid.
+        Fills self.acc[:np]; with kick = half_dt also applies the second half-kick to the velocities.  ``tables`` (the
+        cosmology interpolators) are only needed by the multigrid warm start (solver.py:274-281).  Returns the device
+        tensor [max|a|, max|v|] already reduced over ranks."""
         ops, comm, N, nxl = self.ops, self.comm, self.N, self.nxl
         theory = param["theory"].casefold()
         if theory not in ("newton", "parametrized"):
@@ -895,6 +976,9 @@ class Slab:
         conversion = np.float32(N ** 3 / param["npart"]) if N ** 3 != param["npart"] else np.float32(1)
         if conversion != 1:
             ops.affine(rhs, conversion, 0.0)
+        use_multigrid = param["linear_newton_solver"].casefold() == "multigrid"
+        if use_multigrid and param["save_pk"]:
+            self._pk_from_density(rhs, param)      # solver.py:130-138: P(k) of the density, not of the RHS
         f1 = np.float32(1.5 * param["aexp"] * param["Om_m"] * param["parametrized_mu_z"])
         ops.affine(rhs, f1, -f1)
         self._mark("density ghosts+rhs")
@@ -902,9 +986,13 @@ class Slab:
         if nxl < G:
             raise ValueError(f"slab of {nxl} planes is thinner than the {G} ghost planes the stencils need")
         phi_g = torch.empty((nxl + 2 * G, N, N), dtype=torch.float32, device=rho.device)
-        self.fft_poisson(rhs, phi_g[G:G + nxl], param)
+        param["compute_additional_field"] = False    # solver.py:121 (Newtonian: no additional field)
+        if use_multigrid:
+            self.multigrid_poisson(rhs, phi_g, G, param, tables)
+        else:
+            self.fft_poisson(rhs, phi_g[G:G + nxl], param)
         del rho, rhs
-        self._mark("fft solve (2 transposes)")
+        self._mark("multigrid solve" if use_multigrid else "fft solve (2 transposes)")
         from_left, from_right = comm.exchange_planes(phi_g[G:2 * G], phi_g[nxl:nxl + G])
         phi_g[:G] = from_left          # the left neighbour's last G owned planes
         phi_g[nxl + G:] = from_right   # the right neighbour's first G owned planes
@@ -948,7 +1036,7 @@ class Slab:
         utils.set_units(param)
         self._mark("kick+drift+wrap")
         self.migrate_neighbours(detected)
-        self.pm(param, kick=half_dt)
+        self.pm(param, kick=half_dt, tables=tables)
 
     def integrate(self, tables, param, t_snap_next=np.float32(0)):
         """integration.integrate (integration.py:17-118), leapfrog only"""

@@ -1,0 +1,132 @@
+"""multigrid.linear (multigrid.py:23-83) on x-slabs: the host sequencing of the V-cycle over the ghost-plane kernels of
+csrc/slab_mg.cu, as SURVEY 8(e) lays it out.
+
+* Every level keeps the decomposition of the fine grid: rank r owns planes [r n/P, (r+1) n/P) of the n^3 level.
+  Potential-like arrays carry one ghost plane on each side along x; ``exchange_planes`` refreshes them before every
+  half-sweep of the red-black smoother (the two colours of a sweep read each other across the slab boundary), before a
+  residual and before a prolongation.
+* Restriction and prolongation are local: the two children planes of a coarse plane live on the same rank.
+* Once a coarse level would have fewer than two planes per rank it is gathered on every rank and solved redundantly
+  with the single-domain kernels (csrc/multigrid.cu), which costs one all-gather of at most (2P)^3 cells.
+* Norms (residual, truncation error) are local double sums, all-reduced.
+
+The cycle is the reference's: Npre smoothing sweeps, R(b - Lx), first guess -h^2/6 b, recursion (or Npre sweeps on the
+coarsest 4^3 level), x += P(correction), Npost sweeps; stopping rule and truncation-error refresh as multigrid.py:62-80.
+"""
+import logging
+
+import numpy as np
+import torch
+
+F_RELAX = np.float32(1.25)   # laplacian.py:1053
+
+
+class SlabMultigrid:
+    def __init__(self, comm, ops, ncells_1d):
+        self.comm, self.ops, self.N = comm, ops, int(ncells_1d)
+        self.P, self.rank = comm.size, comm.rank
+        nxl = self.N // self.P
+        if self.N % self.P or nxl < 2 or (nxl & (nxl - 1)):
+            raise ValueError(f"slab multigrid needs a power-of-two number of planes per rank (>= 2), got "
+                             f"{self.N} / {self.P}")
+        self.nxl = nxl
+
+    # -- ghosts
+    def exchange(self, xg, nxl):
+        """ghost plane 0 <- the left neighbour's last owned plane, ghost plane nxl + 1 <- the right neighbour's first"""
+        from_left, from_right = self.comm.exchange_planes(xg[1:2], xg[nxl:nxl + 1])
+        xg[0].copy_(from_left[0])
+        xg[nxl + 1].copy_(from_right[0])
+
+    # -- laplacian.smoothing (laplacian.py:1026-1055): red (odd i+j+k) then black, ghosts refreshed before each
+    def smoothing(self, xg, b, n, nxl, sweeps):
+        x0 = self.rank * nxl
+        for _ in range(int(sweeps)):
+            for colour in (1, 0):
+                self.exchange(xg, nxl)
+                self.ops.mg_gs_colour(xg, b, nxl, n, x0, colour, F_RELAX)
+
+    def _norm(self, sumsq):
+        self.comm.allreduce_sum_(sumsq)
+        return np.float32(np.sqrt(sumsq.item()))
+
+    def residual_error(self, xg, b, n, nxl):
+        """laplacian.residual_error (laplacian.py:327-381)"""
+        self.exchange(xg, nxl)
+        Lx = self.ops.mg_operator(xg, nxl, n)
+        return self._norm(self.ops.mg_diff_sumsq(b, 1.0, Lx))
+
+    def truncation_error(self, xg, n, nxl):
+        """laplacian.truncation_error (laplacian.py:502-533): || R(L x) - L(R x) ||"""
+        ops = self.ops
+        nc, nxlc = n // 2, nxl // 2
+        self.exchange(xg, nxl)
+        RLx = ops.mg_restriction(ops.mg_operator(xg, nxl, n), nxl, n, 1.0)
+        Rxg = torch.empty((nxlc + 2, nc, nc), dtype=torch.float32, device=xg.device)
+        ops.mg_restriction(xg[1:nxl + 1], nxl, n, 1.0, out=Rxg[1:nxlc + 1])
+        self.exchange(Rxg, nxlc)
+        LRx = ops.mg_operator(Rxg, nxlc, nc)
+        return self._norm(ops.mg_diff_sumsq(RLx, 1.0, LRx))
+
+    @staticmethod
+    def first_guess_factor(n):
+        """laplacian.initialise_potential (laplacian.py:765-796): x = -h^2/6 b, the factor rounded like the kernel's"""
+        h = float(np.float32(1.0) / np.float32(n))
+        return np.float32(-h * h / 6.0)
+
+    def _gather_level(self, planes, nc):
+        """all ranks' owned planes of a coarse level -> the full [nc, nc, nc] cube on every rank"""
+        P = self.P
+        send = planes.reshape(1, -1).expand(P, -1).contiguous()
+        out = torch.empty_like(send)
+        self.comm.all_to_all_equal(send, out)
+        return out.view(nc, nc, nc)
+
+    # -- multigrid.V_cycle (multigrid.py:474-517)
+    def v_cycle(self, xg, b, n, nxl, param, nlevel=0):
+        ops = self.ops
+        nc, nxlc = n // 2, nxl // 2
+        self.smoothing(xg, b, n, nxl, param["Npre"])
+        self.exchange(xg, nxl)
+        res_c = ops.mg_restrict_residual(xg, b, nxl, n)              # [nxlc, nc, nc]
+        coarsest = nlevel >= (param["ncoarse"] - 3)
+        if nxlc >= 2:
+            cg = torch.empty((nxlc + 2, nc, nc), dtype=torch.float32, device=xg.device)
+            cg[1:nxlc + 1].copy_(res_c)
+            ops.affine(cg[1:nxlc + 1], self.first_guess_factor(nc), 0.0)
+            if coarsest:
+                self.smoothing(cg, res_c, nc, nxlc, param["Npre"])
+            else:
+                self.v_cycle(cg, res_c, nc, nxlc, param, nlevel + 1)
+            self.exchange(cg, nxlc)
+        else:
+            # one coarse plane per rank: gather the level and solve it on every rank with the single-domain kernels
+            cube = self._gather_level(res_c, nc)
+            corr = ops.mg_cube_solve(cube, param, nlevel, coarsest)
+            c0 = self.rank * nxlc
+            idx = torch.tensor([(c0 - 1 + p) % nc for p in range(nxlc + 2)], dtype=torch.int64, device=corr.device)
+            cg = corr.index_select(0, idx)
+        ops.mg_add_prolongation(xg, cg, nxlc, nc)
+        self.smoothing(xg, b, n, nxl, param["Npost"])
+
+    # -- multigrid.linear (multigrid.py:23-83)
+    def linear(self, xg, b, param):
+        """xg [nxl + 2, N, N]: first guess in the owned planes, solution on return (ghost planes are scratch);
+        b [nxl, N, N]."""
+        if param.get("compute_additional_field", False) and "fr" == param["theory"].casefold():
+            raise ValueError("Linear should not be used for scalaron field")
+        n, nxl = self.N, self.nxl
+        if ("tolerance" not in param) or (param["nsteps"] % 3) == 0:
+            logging.info("Compute Truncation error")
+            param["tolerance"] = param["epsrel"] * self.truncation_error(xg, n, nxl)
+        tolerance = param["tolerance"]
+        logging.info("Start linear Multigrid (slab)")
+        residual_err = 1e30
+        while residual_err > tolerance:
+            self.v_cycle(xg, b, n, nxl, param, 0)
+            residual_error_tmp = self.residual_error(xg, b, n, nxl)
+            logging.info(f"{residual_error_tmp=} {tolerance=}")
+            if residual_error_tmp < tolerance or residual_err / residual_error_tmp < 2:
+                break
+            residual_err = residual_error_tmp
+        return xg

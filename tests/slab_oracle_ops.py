@@ -12,6 +12,36 @@ from oracle import api as oapi
 
 REC = 8
 
+_HX = None
+
+
+def _harness():
+    """tests/slab_mg_harness.cpp (the per-cell bodies of csrc/slab_mg.cu run on the host), built on first use"""
+    global _HX
+    if _HX is None:
+        import ctypes as C
+        import os
+        import subprocess
+        here = os.path.dirname(os.path.abspath(__file__))
+        src = os.path.join(here, "slab_mg_harness.cpp")
+        hdr = os.path.join(here, "..", "pysco_b200", "csrc", "slab_mg_cells.cuh")
+        out = os.path.join(here, "_build", "libslab_mg_harness.so")
+        os.makedirs(os.path.dirname(out), exist_ok=True)
+        if not os.path.exists(out) or os.path.getmtime(out) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
+            tmp = f"{out}.{os.getpid()}.tmp"
+            subprocess.check_call(["g++", "-O2", "-x", "c++", "-shared", "-fPIC", "-ffp-contract=off", "-o", tmp, src])
+            os.replace(tmp, out)
+        _HX = C.CDLL(out)
+        for f in ("hx_gs_colour", "hx_operator", "hx_restrict_residual", "hx_restriction", "hx_add_prolongation"):
+            getattr(_HX, f).restype = None
+    return _HX
+
+
+def _fp(t):
+    import ctypes as C
+    assert t.dtype == torch.float32 and t.is_contiguous()
+    return C.c_void_p(t.data_ptr())
+
 
 def _np(t):
     return t.detach().cpu().numpy()
@@ -200,6 +230,46 @@ class OracleOps:
             oapi.fourier.inverse_laplacian_7pt(ones)
         s = self._c(spec_t, (self.N, self.nyl, self.N // 2 + 1))
         s *= ones[:, self.y0:self.y0 + self.nyl, :] * np.float32(scale)
+
+    # -- multigrid on the slab: the per-cell code of csrc/slab_mg.cu through the host harness; gathered coarse levels
+    #    through the oracle's single-domain V-cycle
+    def mg_gs_colour(self, xg, b, nxl, n, x0, colour, f_relax):
+        import ctypes as C
+        _harness().hx_gs_colour(_fp(xg), _fp(b), nxl, n, x0, colour, C.c_float(float(f_relax)))
+
+    def mg_operator(self, xg, nxl, n):
+        out = torch.empty((nxl, n, n), dtype=torch.float32)
+        _harness().hx_operator(_fp(xg), nxl, n, _fp(out))
+        return out
+
+    def mg_restrict_residual(self, xg, b, nxl, n):
+        out = torch.empty((nxl // 2, n // 2, n // 2), dtype=torch.float32)
+        _harness().hx_restrict_residual(_fp(xg), _fp(b), nxl, n, _fp(out))
+        return out
+
+    def mg_restriction(self, fine, nxl, n, sign, out=None):
+        import ctypes as C
+        if out is None:
+            out = torch.empty((nxl // 2, n // 2, n // 2), dtype=torch.float32)
+        _harness().hx_restriction(_fp(fine), nxl, n, C.c_float(float(sign)), _fp(out))
+        return out
+
+    def mg_add_prolongation(self, fine_g, coarse_g, nxlc, nc):
+        _harness().hx_add_prolongation(_fp(fine_g), _fp(coarse_g), nxlc, nc)
+
+    def mg_diff_sumsq(self, a, fa, b):
+        d = np.float32(fa) * _np(a).astype(np.float32) - _np(b)
+        return torch.tensor([float(np.sum(d.astype(np.float64) ** 2))], dtype=torch.float64)
+
+    def mg_cube_solve(self, res_cube, param, nlevel, coarsest):
+        from oracle import host
+        res = np.ascontiguousarray(_np(res_cube))
+        x = oracle.laplacian.initialise_potential(res)
+        if coarsest:
+            oracle.laplacian.smoothing(x, res, param["Npre"])
+        else:
+            host._cycle("V", x, res, param, nlevel + 1)
+        return torch.from_numpy(x)
 
     def close(self):
         pass

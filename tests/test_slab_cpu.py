@@ -24,21 +24,21 @@ from oracle import host  # noqa: E402
 NSTEPS = 3
 
 
-def _setup(N):
+def _setup(N, solver="fft"):
     tables = cases.toy_tables()
     pos = cases.lattice_particles(N, 0.4, seed=11)
     vel = cases.velocities(N ** 3, seed=12, scale=0.3)  # large enough that particles cross slab boundaries
-    param = cases.base_param(int(np.log2(N)), N ** 3, linear_newton_solver="fft")
+    param = cases.base_param(int(np.log2(N)), N ** 3, linear_newton_solver=solver)
     param["aexp"] = 0.2
     param["t"] = float(tables[1](np.log(param["aexp"])))
     host.set_units(param)
     return tables, pos, vel, param
 
 
-def _reference(N):
-    tables, pos, vel, param = _setup(N)
+def _reference(N, solver="fft"):
+    tables, pos, vel, param = _setup(N, solver)
     pos, vel = pos.copy(), vel.copy()
-    acc, phi, add = host.pm(pos, param)
+    acc, phi, add = host.pm(pos, param, tables=tables)
     state = [pos, vel, acc, phi, add]
     for _ in range(NSTEPS):
         param["nsteps"] += 1
@@ -46,10 +46,10 @@ def _reference(N):
     return state, float(param["t"])
 
 
-def _run_rank(N, comm, out, reorder_at=None):
+def _run_rank(N, comm, out, reorder_at=None, solver="fft"):
     from pysco_b200 import slab
     from slab_oracle_ops import OracleOps
-    tables, pos, vel, param = _setup(N)
+    tables, pos, vel, param = _setup(N, solver)
     P, r = comm.size, comm.rank
     # every rank adopts an arbitrary 1/P of the particles: set_particles must route them to their owners
     ids = np.arange(N ** 3, dtype=np.int64)
@@ -61,7 +61,7 @@ def _run_rank(N, comm, out, reorder_at=None):
     assert (own == r).all()
     if P == 4:
         s._mig_cap = 8     # far too small: the first steps must take the overflow (repeat) path
-    s.pm(param)
+    s.pm(param, tables=tables)
     moved = 0
     for step in range(NSTEPS):
         param["nsteps"] += 1
@@ -100,17 +100,20 @@ def _check(out, ref, ref_t, P):
     assert rel(phi, rphi) < 2e-4
 
 
-@pytest.mark.parametrize("P", [1, 2, 4])
-def test_slab_threads_vs_oracle(P):
+@pytest.mark.parametrize("P,solver,N", [(1, "fft", 32), (2, "fft", 32), (4, "fft", 32), (1, "multigrid", 32),
+                                        (2, "multigrid", 32), (4, "multigrid", 32), (8, "multigrid", 64)])
+def test_slab_threads_vs_oracle(P, solver, N):
+    """multigrid: P = 1, 2 keep every level distributed (two planes per rank on the coarsest 4^3 grid at P = 2);
+    P = 4 gathers the 4^3 level and smooths it redundantly; P = 8 at 64^3 gathers the 8^3 level and runs the rest of
+    the V-cycle on it."""
     from pysco_b200 import slab
-    N = 32
-    ref, ref_t = _reference(N)
+    ref, ref_t = _reference(N, solver)
     comms = slab.ThreadComm.world(P) if P > 1 else [slab.SelfComm()]
     out, errs = {}, []
 
     def work(c):
         try:
-            _run_rank(N, c, out, reorder_at=1)
+            _run_rank(N, c, out, reorder_at=1, solver=solver)
         except BaseException as e:  # noqa: BLE001
             errs.append(e)
             if P > 1:
@@ -130,7 +133,7 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _gloo_worker(rank, world, port, out):
+def _gloo_worker(rank, world, port, out, solver="fft"):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
                       LOCAL_RANK=str(rank))
     for p in (ROOT, os.path.join(ROOT, "tests"), os.path.join(ROOT, "tests", "golden")):
@@ -148,20 +151,21 @@ def _gloo_worker(rank, world, port, out):
     left, right = (rank - 1) % world, (rank + 1) % world
     assert fl[0, 0].item() == 10 * left + 2 and fr[0, 0].item() == 10 * right + 1
     local = {}
-    _run_rank(32, comm, local)
+    _run_rank(32, comm, local, solver=solver)
     if rank == 0:
         out.update(local)
     dist.barrier()
     dist.destroy_process_group()
 
 
-def test_slab_gloo_world2_vs_oracle():
+@pytest.mark.parametrize("solver", ["fft", "multigrid"])
+def test_slab_gloo_world2_vs_oracle(solver):
     import torch.multiprocessing as mp
-    ref, ref_t = _reference(32)
+    ref, ref_t = _reference(32, solver)
     port = _free_port()
     with mp.Manager() as mgr:
         out = mgr.dict()
-        mp.spawn(_gloo_worker, args=(2, port, out), nprocs=2, join=True)
+        mp.spawn(_gloo_worker, args=(2, port, out, solver), nprocs=2, join=True)
         out = dict(out)
     _check(out, ref, ref_t, 2)
 
@@ -173,7 +177,9 @@ def test_slab_run_loop_threads_vs_reference_snapshot(tmp_path):
     import glob
     from pysco_b200 import slab
     from slab_oracle_ops import OracleOps
-    g = np.load(os.path.join(ROOT, "tests", "golden", "run.npz"))
+    with np.load(os.path.join(ROOT, "tests", "golden", "run.npz")) as z:
+        # materialised here: NpzFile reads lazily through one zip handle, which the rank threads must not share
+        g = {k: z[k] for k in ("ic_pos", "ic_vel", "fft_pos", "fft_vel")}
     base = str(tmp_path) + "/"
     out, errs = {}, []
     comms = slab.ThreadComm.world(2)
