@@ -220,6 +220,26 @@ class OracleOps:
         s = self._c(spec_t, (self.N, self.nyl, self.N // 2 + 1))
         s[:] = np.fft.ifft(s, axis=0) * self.N if inverse else np.fft.fft(s, axis=0)
 
+    def pk_bins(self, spec_t, p):
+        """fourier.fourier_grid_to_Pk (fourier.py:22-100) on this rank's y-block of the transposed spectrum: per-bin
+        sums of |k|, |delta_k W^-p|^2 and mode counts, [3][N] float64 (what psc_pk_slab returns)"""
+        N, nz = self.N, self.N // 2 + 1
+        s = self._c(spec_t, (N, self.nyl, nz))
+        fold = lambda i: np.where(i >= N // 2, i - N, i).astype(np.float32)   # noqa: E731
+        kx = fold(np.arange(N))[:, None, None]
+        ky = fold(np.arange(self.y0, self.y0 + self.nyl))[None, :, None]
+        kz = np.arange(nz, dtype=np.float32)[None, None, :]
+        w = (np.sinc(kx / np.float32(N)) * np.sinc(ky / np.float32(N)) * np.sinc(kz / np.float32(N))).astype(np.float64)
+        d2 = (np.abs(s.astype(np.complex128)) ** 2) * w ** (-2.0 * p)
+        knorm = np.sqrt(kx * kx + ky * ky + kz * kz).astype(np.float32)
+        ki = (knorm + np.float32(0.5)).astype(np.int64)
+        keep = np.ones(ki.shape, bool)
+        if self.y0 == 0:
+            keep[0, 0, 0] = False    # the DC mode is skipped
+        bins = np.stack([np.bincount(ki[keep], weights=a[keep].astype(np.float64), minlength=N)[:N]
+                         for a in (knorm, d2, np.ones_like(d2))])
+        return torch.from_numpy(bins)
+
     def green(self, spec_t, kind, p, scale):
         ones = np.ones((self.N, self.N, self.N // 2 + 1), dtype=np.complex64)
         if kind == 0:

@@ -170,24 +170,25 @@ def test_slab_gloo_world2_vs_oracle(solver):
     _check(out, ref, ref_t, 2)
 
 
-def test_slab_run_loop_threads_vs_reference_snapshot(tmp_path):
-    """slab.run (main.run on slabs: snapshot schedule, per-slab reorder, gather in reference order, P(k) skipped) on 2
+@pytest.mark.parametrize("solver", ["fft", "multigrid"])
+def test_slab_run_loop_threads_vs_reference_snapshot(tmp_path, solver):
+    """slab.run (main.run on slabs: snapshot schedule, per-slab reorder, gather in reference order, P(k) files) on 2
     virtual ranks with the oracle standing in for the kernels, z = 49 -> 0 at 32^3, against the final snapshot of the
-    unmodified reference (tests/golden/run.npz)."""
+    unmodified reference (tests/golden/run.npz), for the FFT and the multigrid solver (warm starts, truncation error
+    refreshed every third step, the reference's stopping rule)."""
     import glob
     from pysco_b200 import slab
     from slab_oracle_ops import OracleOps
     with np.load(os.path.join(ROOT, "tests", "golden", "run.npz")) as z:
         # materialised here: NpzFile reads lazily through one zip handle, which the rank threads must not share
-        g = {k: z[k] for k in ("ic_pos", "ic_vel", "fft_pos", "fft_vel")}
+        g = {k: z[k] for k in ("ic_pos", "ic_vel", f"{solver}_pos", f"{solver}_vel", f"{solver}_pk_last")}
     base = str(tmp_path) + "/"
     out, errs = {}, []
     comms = slab.ThreadComm.world(2)
 
     def work(c):
         try:
-            param = cases.run_param(base, "fft")
-            param["save_power_spectrum"] = "no"
+            param = cases.run_param(base, solver)     # save_power_spectrum = z_out: P(k) at every snapshot
             res = slab.run(param, comm=c, initial_state=(g["ic_pos"].copy(), g["ic_vel"].copy()),
                            ops_factory=OracleOps)
             if c.rank == 0:
@@ -201,11 +202,17 @@ def test_slab_run_loop_threads_vs_reference_snapshot(tmp_path):
     [t.join() for t in ts]
     if errs:
         raise errs[0]
-    d = np.abs(out["pos"] - g["fft_pos"])
+    d = np.abs(out["pos"] - g[f"{solver}_pos"])
     d = np.minimum(d, 1 - d)
     assert d.max() < 1e-5, d.max()
-    assert np.abs(out["vel"] - g["fft_vel"]).max() < 1e-4 * np.abs(g["fft_vel"]).max() + 1e-7
+    assert np.abs(out["vel"] - g[f"{solver}_vel"]).max() < 1e-4 * np.abs(g[f"{solver}_vel"]).max() + 1e-7
     assert len(glob.glob(os.path.join(base, "output_0000[1-6]", "particles_*.parquet"))) == 6
+    # the last P(k) file (fft: spectrum of the RHS inside the solve; multigrid: forward transform of the density)
+    pks = sorted(glob.glob(os.path.join(base, "power", "*.dat")))
+    mine, ref = np.loadtxt(pks[-1]), g[f"{solver}_pk_last"]
+    assert np.array_equal(mine[:, 2], ref[:, 2])
+    np.testing.assert_allclose(mine[:, 0], ref[:, 0], rtol=1e-6)
+    np.testing.assert_allclose(mine[:, 1], ref[:, 1], rtol=1e-4)
 
 
 def _gloo3_worker(rank, world, port, out):

@@ -171,7 +171,8 @@ def test_pinned_host_pipeline_matches_device_path(solver_name):
         assert err < 1e-5, (name, err)
 
 
-def test_slab_whole_run_matches_reference_snapshot(tmp_path):
+@pytest.mark.parametrize("solver", ["fft", "multigrid"])
+def test_slab_whole_run_matches_reference_snapshot(tmp_path, solver):
     """BASELINE config 1 shape at 32^3, z = 49 -> 0, through slab.run on 2 virtual ranks: the final state, put back
     in the reference's particle order, against the unmodified reference's final snapshot (tests/golden/run.npz).
     The slab path restores the reference's particle order through the particle ids, so the comparison is row by
@@ -180,29 +181,30 @@ def test_slab_whole_run_matches_reference_snapshot(tmp_path):
     from pysco_b200 import slab
     with np.load(os.path.join(ROOT, "tests", "golden", "run.npz")) as z:
         # materialised here: NpzFile reads lazily through one zip handle, which the rank threads must not share
-        g = {k: z[k] for k in ("ic_pos", "ic_vel", "fft_pos", "fft_vel", "fft_nsteps", "fft_pk_last")}
+        g = {k: z[k] for k in ("ic_pos", "ic_vel", f"{solver}_pos", f"{solver}_vel", f"{solver}_nsteps",
+                               f"{solver}_pk_last")}
     base = str(tmp_path) + "/"
     out = {}
 
     def work(c, o):
-        param = cases.run_param(base, "fft")     # save_power_spectrum = z_out: P(k) at every snapshot
+        param = cases.run_param(base, solver)    # save_power_spectrum = z_out: P(k) at every snapshot
         res = slab.run(param, comm=c, initial_state=(g["ic_pos"].copy(), g["ic_vel"].copy()))
         if c.rank == 0:
             o["pos"], o["vel"] = res[0].numpy(), res[1].numpy()
 
     out = _threads(2, work)
     # fewer than n_reorder = 50 steps: the reference never reorders, its final rows are the initial (lattice = id) rows
-    assert int(g["fft_nsteps"][0]) < 50
-    d = np.abs(out["pos"] - g["fft_pos"])
+    assert int(g[f"{solver}_nsteps"][0]) < 50
+    d = np.abs(out["pos"] - g[f"{solver}_pos"])
     d = np.minimum(d, 1 - d)
     assert d.max() < 1e-5, d.max()
-    assert np.abs(out["vel"] - g["fft_vel"]).max() < 1e-4 * np.abs(g["fft_vel"]).max() + 1e-7
+    assert np.abs(out["vel"] - g[f"{solver}_vel"]).max() < 1e-4 * np.abs(g[f"{solver}_vel"]).max() + 1e-7
     glob = __import__("glob")
     snaps = glob.glob(os.path.join(base, "output_0000[1-6]", "particles_*.parquet"))
     assert len(snaps) == 6
     # the last P(k) file against the reference's (north-star bar 1e-4), summed over the two slabs' bins
     pks = sorted(glob.glob(os.path.join(base, "power", "*.dat")))
-    mine, ref = np.loadtxt(pks[-1]), g["fft_pk_last"]
+    mine, ref = np.loadtxt(pks[-1]), g[f"{solver}_pk_last"]
     assert np.array_equal(mine[:, 2], ref[:, 2])
     np.testing.assert_allclose(mine[:, 0], ref[:, 0], rtol=1e-6)
     np.testing.assert_allclose(mine[:, 1], ref[:, 1], rtol=1e-4)
