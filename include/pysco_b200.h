@@ -289,6 +289,9 @@ int psc_box_restriction(const float *fine, int nxl, int n, float sign, float *co
 /* mesh.add_prolongation (mesh.py:334-453): fine_g[2 nxlc + 2][2 nc][2 nc] += P(coarse_g[nxlc + 2][nc][nc]); the coarse
  * ghost planes must be current, the fine ghost planes are not touched */
 int psc_box_add_prolongation(float *fine_g, const float *coarse_g, int nxlc, int nc, void *stream);
+/* mond.rhs_simple/n/beta/gamma/delta (mond.py:171-932) on the slab: phig[nxl + 2][n][n] is the Newtonian potential with
+ * its ghost planes, out[nxl][n][n] the QUMOND source */
+int psc_box_mond_rhs(const float *phig, float *out, int nxl, int n, float g0, int fn, float alpha, void *stream);
 
 #ifdef __cplusplus
 }

@@ -66,6 +66,17 @@ __global__ void __launch_bounds__(BX_K *BX_J) box_add_prolongation_kernel(float 
   box::prolong_add_cell(fine_g, coarse_g, ci, cj, ck, nc);
 }
 
+template <int FN>
+__global__ void __launch_bounds__(BX_K *BX_J) box_mond_rhs_kernel(const float *__restrict__ phig,
+                                                                  float *__restrict__ out, int nxl, int n, float g0,
+                                                                  float alpha) {
+  const int k = blockIdx.x * BX_K + threadIdx.x;
+  const int j = blockIdx.y * BX_J + threadIdx.y;
+  const int il = blockIdx.z;
+  if (k >= n || j >= n || il >= nxl) return;
+  out[((size_t)il * n + j) * n + k] = box::mond_rhs_cell<FN>(phig, il, j, k, n, g0, alpha);
+}
+
 static inline dim3 box_grid(int nk, int nj, int planes) {
   return dim3((nk + BX_K - 1) / BX_K, (nj + BX_J - 1) / BX_J, planes);
 }
@@ -129,6 +140,25 @@ int psc_box_add_prolongation(float *fine_g, const float *coarse_g, int nxlc, int
   PSC_CHECK_ARG(fine_g && coarse_g, "null pointer");
   box_add_prolongation_kernel<<<box_grid(nc, nc, nxlc), box_block(), 0, as_stream(stream)>>>(fine_g, coarse_g, nxlc,
                                                                                             nc);
+  count_launch();
+  PSC_CHECK_LAUNCH();
+  return PSC_OK;
+}
+
+int psc_box_mond_rhs(const float *phig, float *out, int nxl, int n, float g0, int fn, float alpha, void *stream) {
+  PSC_CHECK_BOX(nxl, n);
+  PSC_CHECK_ARG(phig && out && phig != out, "null or aliased pointer");
+  PSC_CHECK_ARG(fn >= PSC_MOND_SIMPLE && fn <= PSC_MOND_DELTA, "unknown MOND interpolating function");
+  cudaStream_t st = as_stream(stream);
+#define CALL(F) box_mond_rhs_kernel<F><<<box_grid(n, n, nxl), box_block(), 0, st>>>(phig, out, nxl, n, g0, alpha)
+  switch (fn) {
+    case PSC_MOND_SIMPLE: CALL(PSC_MOND_SIMPLE); break;
+    case PSC_MOND_N: CALL(PSC_MOND_N); break;
+    case PSC_MOND_BETA: CALL(PSC_MOND_BETA); break;
+    case PSC_MOND_GAMMA: CALL(PSC_MOND_GAMMA); break;
+    default: CALL(PSC_MOND_DELTA); break;
+  }
+#undef CALL
   count_launch();
   PSC_CHECK_LAUNCH();
   return PSC_OK;

@@ -6,12 +6,15 @@
 // y and z stay periodic inside the box.  The arithmetic (association order included) is the one of the single-domain
 // kernels in multigrid.cu, so a one-rank slab reproduces them bit for bit:
 //   laplacian.py: operator :12, restrict_residual :125, gauss_seidel :844;  mesh.py: restriction :14,
-//   add_prolongation :334.
+//   add_prolongation :334;  mond.py: rhs_simple/n/beta/gamma/delta :171-932.
 //
 // The bodies are plain functions of (il, j, k) so that the CPU tier can run the very same code through a host
 // harness (tests/slab_mg_harness.cpp) -- the __global__ wrappers in slab_mg.cu only map threads to cells.
 #pragma once
+#include <math.h>
 #include <stddef.h>
+
+#include "../../include/pysco_b200.h"
 
 #ifdef __CUDACC__
 #define PSC_CELL __device__ __forceinline__
@@ -19,6 +22,7 @@
 #else
 #define PSC_CELL static inline
 #define PSC_UNROLL
+static inline float rsqrtf(float x) { return 1.0f / sqrtf(x); }
 #endif
 
 namespace psc {
@@ -120,6 +124,72 @@ PSC_CELL void prolong_add_cell(float *fine_g, const float *coarse_g, int ci, int
                         f2 * (v[A][E][1] + v[1][E][G] + v[A][1][G]) + f3 * v[A][E][G];
         fine_g[(size_t)(2 * ci + a + 1) * n2 + (size_t)(2 * cj + e) * n + 2 * ck + g] += r;
       }
+}
+
+// ----------------------------------------------------------------------------------- MOND
+// interpolating functions nu(y) (mond.py:16-162), as in multigrid.cu mond_nu()
+template <int FN>
+PSC_CELL float mond_nu(float y, float alpha) {
+  if (FN == PSC_MOND_SIMPLE) return 0.5f + sqrtf(0.25f + 1.0f / y);
+  if (FN == PSC_MOND_N) {
+    int n = (int)alpha;
+    return powf(0.5f + sqrtf(0.25f + powf(y, (float)(-n))), 1.0f / (float)n);
+  }
+  if (FN == PSC_MOND_BETA) {
+    float e = expf(-y);
+    float nu = alpha * e;
+    float om = 1.0f - e;
+    if (om > 0.0f) nu += rsqrtf(om);
+    return nu;
+  }
+  if (FN == PSC_MOND_GAMMA) {
+    float e = expf(-powf(y, 0.5f * alpha));
+    return powf(1.0f - e, -1.0f / alpha) + (1.0f - 1.0f / alpha) * e;
+  }
+  return powf(1.0f - expf(-powf(y, 0.5f * alpha)), -1.0f / alpha);
+}
+
+// QUMOND source div(nu(|grad phi_N| / g0) grad phi_N) at owned cell (il, j, k) (mond.py:171-932): phig is the
+// Newtonian potential with one ghost plane per side; the six half-cell points A (-h/2) and B (+h/2) of each axis
+template <int FN>
+PSC_CELL float mond_rhs_cell(const float *phig, int il, int j, int k, int n, float g0, float alpha) {
+  const size_t n2 = (size_t)n * n;
+  const float inv_g0 = 1.0f / g0;
+  const float invh = (float)n, inv4h = 0.25f * (float)n;
+  const size_t ri[3] = {(size_t)il * n2, (size_t)(il + 1) * n2, (size_t)(il + 2) * n2};
+  const size_t rj[3] = {(size_t)pwrap(j - 1, n) * n, (size_t)j * n, (size_t)pwrap(j + 1, n) * n};
+  const int rk[3] = {pwrap(k - 1, n), k, pwrap(k + 1, n)};
+#define PSC_P(a, e, g) phig[ri[(a) + 1] + rj[(e) + 1] + rk[(g) + 1]]
+  float p0 = PSC_P(0, 0, 0);
+  float Axx = invh * (p0 - PSC_P(-1, 0, 0));
+  float Axy = inv4h * (PSC_P(0, 1, 0) - PSC_P(0, -1, 0) + PSC_P(-1, 1, 0) - PSC_P(-1, -1, 0));
+  float Axz = inv4h * (PSC_P(0, 0, 1) - PSC_P(0, 0, -1) + PSC_P(-1, 0, 1) - PSC_P(-1, 0, -1));
+  float fAx = sqrtf(Axx * Axx + Axy * Axy + Axz * Axz);
+  float Bxx = invh * (-p0 + PSC_P(1, 0, 0));
+  float Bxy = inv4h * (PSC_P(1, 1, 0) - PSC_P(1, -1, 0) + PSC_P(0, 1, 0) - PSC_P(0, -1, 0));
+  float Bxz = inv4h * (PSC_P(1, 0, 1) - PSC_P(1, 0, -1) + PSC_P(0, 0, 1) - PSC_P(0, 0, -1));
+  float fBx = sqrtf(Bxx * Bxx + Bxy * Bxy + Bxz * Bxz);
+  float Ayy = invh * (p0 - PSC_P(0, -1, 0));
+  float Ayx = inv4h * (PSC_P(1, 0, 0) - PSC_P(-1, 0, 0) + PSC_P(1, -1, 0) - PSC_P(-1, -1, 0));
+  float Ayz = inv4h * (PSC_P(0, 0, 1) - PSC_P(0, 0, -1) + PSC_P(0, -1, 1) - PSC_P(0, -1, -1));
+  float fAy = sqrtf(Ayx * Ayx + Ayy * Ayy + Ayz * Ayz);
+  float Byy = invh * (-p0 + PSC_P(0, 1, 0));
+  float Byx = inv4h * (PSC_P(1, 1, 0) - PSC_P(-1, 1, 0) + PSC_P(1, 0, 0) - PSC_P(-1, 0, 0));
+  float Byz = inv4h * (PSC_P(0, 1, 1) - PSC_P(0, 1, -1) + PSC_P(0, 0, 1) - PSC_P(0, 0, -1));
+  float fBy = sqrtf(Byx * Byx + Byy * Byy + Byz * Byz);
+  float Azz = invh * (p0 - PSC_P(0, 0, -1));
+  float Azx = inv4h * (PSC_P(1, 0, 0) - PSC_P(-1, 0, 0) + PSC_P(1, 0, -1) - PSC_P(-1, 0, -1));
+  float Azy = inv4h * (PSC_P(0, 1, 0) - PSC_P(0, -1, 0) + PSC_P(0, 1, -1) - PSC_P(0, -1, -1));
+  float fAz = sqrtf(Azx * Azx + Azy * Azy + Azz * Azz);
+  float Bzz = invh * (-p0 + PSC_P(0, 0, 1));
+  float Bzx = inv4h * (PSC_P(1, 0, 1) - PSC_P(-1, 0, 1) + PSC_P(1, 0, 0) - PSC_P(-1, 0, 0));
+  float Bzy = inv4h * (PSC_P(0, 1, 1) - PSC_P(0, -1, 1) + PSC_P(0, 1, 0) - PSC_P(0, -1, 0));
+  float fBz = sqrtf(Bzx * Bzx + Bzy * Bzy + Bzz * Bzz);
+#undef PSC_P
+  float r = mond_nu<FN>(fBx * inv_g0, alpha) * Bxx - mond_nu<FN>(fAx * inv_g0, alpha) * Axx +
+            mond_nu<FN>(fBy * inv_g0, alpha) * Byy - mond_nu<FN>(fAy * inv_g0, alpha) * Ayy +
+            mond_nu<FN>(fBz * inv_g0, alpha) * Bzz - mond_nu<FN>(fAz * inv_g0, alpha) * Azz;
+  return invh * r;
 }
 
 }  // namespace box

@@ -534,6 +534,10 @@ class CudaOps:
                                            _lib.stream()))
         return out
 
+    def mond_rhs(self, phig, out, nxl, n, g0, fn, alpha):
+        _lib.check(self.lib.psc_box_mond_rhs(_lib.ptr(phig), _lib.ptr(out), nxl, n, float(np.float32(g0)), int(fn),
+                                             float(alpha), _lib.stream()))
+
     def mg_cube_solve(self, res_cube, param, nlevel, coarsest):
         """a gathered coarse level, solved on every rank by the single-domain kernels (multigrid.py:474-517)"""
         from . import laplacian, multigrid
@@ -573,6 +577,7 @@ class Slab:
         self.pos = self.vel = self.acc = self.ids = None
         self.max_acc = self.max_vel = None
         self.potential = None  # owned planes [nxl, N, N] of the last solve (a view into the ghosted array)
+        self.additional_field = None   # MOND: owned planes of the Newtonian potential of the last step
         self.migrated_last = (0, 0)
         self._warm_host_ops()
         self._spare3 = self._spare1 = None   # spare particle buffers the reorder gathers into (then swapped in)
@@ -913,38 +918,51 @@ class Slab:
         ops.fft_x(a, False)
         self._write_pk(a, param, from_density=True)
 
-    def multigrid_poisson(self, rhs_planes, phi_g, G, param, tables):
+    def _poisson(self, rhs_planes, out_g, G, param, tables, previous):
+        """one linear Poisson solve into the owned planes out_g[G : G + nxl] of a ghosted array"""
+        if param["linear_newton_solver"].casefold() == "multigrid":
+            self.multigrid_poisson(rhs_planes, out_g, G, param, tables, previous)
+        else:
+            self.fft_poisson(rhs_planes, out_g[G:G + self.nxl], param)
+
+    def multigrid_poisson(self, rhs_planes, phi_g, G, param, tables, previous):
         """solver.initialise_potential + multigrid.linear (solver.py:218-282, multigrid.py:23-83) on the slab.  The
-        solve runs in place inside phi_g (planes G - 1 .. G + nxl are the multigrid's ghosted array); the previous
-        potential, rescaled by a D1(a), is the first guess from the second call on."""
+        solve runs in place inside phi_g (planes G - 1 .. G + nxl are the multigrid's ghosted array).  ``previous``
+        (the same field at the last step, owned planes) is the first guess from the second call on -- rescaled by
+        a D1(a) for the potential, as it is for an additional field."""
         from .slab_multigrid import SlabMultigrid
         if self._mg is None:
             self._mg = SlabMultigrid(self.comm, self.ops, self.N)
         nxl = self.nxl
         xg = phi_g[G - 1:G + nxl + 1]
         own = xg[1:nxl + 1]
-        if self.potential is None:
+        if previous is None:
             logging.info("Assign potential from density field")
             own.copy_(rhs_planes)
             self.ops.affine(own, SlabMultigrid.first_guess_factor(self.N), 0.0)
         else:
             logging.info("Rescale potential from previous step for Newtonian potential")
-            scaling = (param["aexp"] * tables[3](np.log(param["aexp"]))
-                       / (param["aexp_old"] * tables[3](np.log(param["aexp_old"]))))
-            own.copy_(self.potential)
-            self.ops.affine(own, np.float32(scaling), 0.0)
+            own.copy_(previous)
+            if not param["compute_additional_field"]:
+                scaling = (param["aexp"] * tables[3](np.log(param["aexp"]))
+                           / (param["aexp_old"] * tables[3](np.log(param["aexp_old"]))))
+                self.ops.affine(own, np.float32(scaling), 0.0)
         self._mg.linear(xg, rhs_planes, param)
 
     # -- solver.pm on the slab
     def pm(self, param, kick=None, tables=None):
-        """solver.pm (solver.py:30-215), Newtonian / parametrized; linear_newton_solver = fft, fft_7pt or multigrid.
-        Fills self.acc[:np]; with kick = half_dt also applies the second half-kick to the velocities.  ``tables`` (the
-        cosmology interpolators) are only needed by the multigrid warm start (solver.py:274-281).  Returns the device
-        tensor [max|a|, max|v|] already reduced over ranks."""
+        """solver.pm (solver.py:30-215): theory newton / parametrized (linear_newton_solver = fft, fft_7pt or multigrid)
+        and mond (QUMOND: fft_7pt or multigrid, two solves around the nu-weighted source).  Fills self.acc[:np]; with
+        kick = half_dt also applies the second half-kick to the velocities.  ``tables`` (the cosmology interpolators)
+        are only needed by the multigrid warm start (solver.py:274-281).  Returns the device tensor [max|a|, max|v|]
+        already reduced over ranks."""
         ops, comm, N, nxl = self.ops, self.comm, self.N, self.nxl
         theory = param["theory"].casefold()
-        if theory not in ("newton", "parametrized"):
-            raise NotImplementedError(f"slab path: theory={param['theory']!r} (newton / parametrized only)")
+        if theory not in ("newton", "parametrized", "mond"):
+            raise NotImplementedError(f"slab path: theory={param['theory']!r} (newton / parametrized / mond only)")
+        solver_name = param["linear_newton_solver"].casefold()
+        if theory == "mond" and solver_name not in ("multigrid", "fft_7pt"):
+            raise NotImplementedError(f"{param['linear_newton_solver']=}, should be 'multigrid' or 'fft_7pt'")
         ms = param["mass_scheme"].casefold()
         if ms not in _SCHEMES:
             raise NotImplementedError(f"{param['mass_scheme']=}, should be 'CIC' or 'TSC'")
@@ -976,7 +994,7 @@ class Slab:
         conversion = np.float32(N ** 3 / param["npart"]) if N ** 3 != param["npart"] else np.float32(1)
         if conversion != 1:
             ops.affine(rhs, conversion, 0.0)
-        use_multigrid = param["linear_newton_solver"].casefold() == "multigrid"
+        use_multigrid = solver_name == "multigrid"
         if use_multigrid and param["save_pk"]:
             self._pk_from_density(rhs, param)      # solver.py:130-138: P(k) of the density, not of the RHS
         f1 = np.float32(1.5 * param["aexp"] * param["Om_m"] * param["parametrized_mu_z"])
@@ -986,11 +1004,29 @@ class Slab:
         if nxl < G:
             raise ValueError(f"slab of {nxl} planes is thinner than the {G} ghost planes the stencils need")
         phi_g = torch.empty((nxl + 2 * G, N, N), dtype=torch.float32, device=rho.device)
-        param["compute_additional_field"] = False    # solver.py:121 (Newtonian: no additional field)
-        if use_multigrid:
-            self.multigrid_poisson(rhs, phi_g, G, param, tables)
+        if theory == "mond":
+            # QUMOND (solver.py:104-127, 365-378, 404-431): Newtonian potential phi_N (the "additional field") ->
+            # source div(nu(|grad phi_N| / g0) grad phi_N), written over the density buffer -> second solve
+            param["compute_additional_field"] = True
+            phiN_g = torch.empty((nxl + 2, N, N), dtype=torch.float32, device=rho.device)
+            self._poisson(rhs, phiN_g, 1, param, tables, self.additional_field)
+            param["compute_additional_field"] = False
+            from_left, from_right = comm.exchange_planes(phiN_g[1:2], phiN_g[nxl:nxl + 1])
+            phiN_g[0] = from_left[0]
+            phiN_g[nxl + 1] = from_right[0]
+            g0 = (param["mond_g0"] * 1e-3 * 1e-10 * param["unit_t"] ** 2 / param["unit_l"]
+                  * param["aexp"] ** (1 + param["mond_scale_factor_exponent"]))
+            fn = param["mond_function"].casefold()
+            if fn not in _lib.MOND_FN:
+                raise NotImplementedError(f"MOND_FUNCTION={fn!r}, should be 'simple', 'n', 'beta', 'gamma' or 'delta'")
+            ops.mond_rhs(phiN_g, rhs, nxl, N, g0, _lib.MOND_FN[fn], 1.0 if fn == "simple" else param["mond_alpha"])
+            self.additional_field = phiN_g[1:nxl + 1]
+            save_pk, param["save_pk"] = param["save_pk"], False     # no P(k) of the MOND source (solver.py:476-478)
+            self._poisson(rhs, phi_g, G, param, tables, self.potential)
+            param["save_pk"] = save_pk
         else:
-            self.fft_poisson(rhs, phi_g[G:G + nxl], param)
+            param["compute_additional_field"] = False    # solver.py:121 (no additional field)
+            self._poisson(rhs, phi_g, G, param, tables, self.potential)
         del rho, rhs
         self._mark("multigrid solve" if use_multigrid else "fft solve (2 transposes)")
         from_left, from_right = comm.exchange_planes(phi_g[G:2 * G], phi_g[nxl:nxl + G])

@@ -116,10 +116,12 @@ class SlabMultigrid:
         if param.get("compute_additional_field", False) and "fr" == param["theory"].casefold():
             raise ValueError("Linear should not be used for scalaron field")
         n, nxl = self.N, self.nxl
+        # the second solve of QUMOND keeps its own tolerance (multigrid.py:58-72)
+        mond_pass = (not param.get("compute_additional_field", False)) and "mond" == param["theory"].casefold()
         if ("tolerance" not in param) or (param["nsteps"] % 3) == 0:
             logging.info("Compute Truncation error")
-            param["tolerance"] = param["epsrel"] * self.truncation_error(xg, n, nxl)
-        tolerance = param["tolerance"]
+            param["tolerance_mond" if mond_pass else "tolerance"] = param["epsrel"] * self.truncation_error(xg, n, nxl)
+        tolerance = param["tolerance_mond"] if mond_pass else param["tolerance"]
         logging.info("Start linear Multigrid (slab)")
         residual_err = 1e30
         while residual_err > tolerance:

@@ -45,4 +45,20 @@ void hx_add_prolongation(float *fine_g, const float *coarse_g, int nxlc, int nc)
       for (int ck = 0; ck < nc; ck++) prolong_add_cell(fine_g, coarse_g, ci, cj, ck, nc);
 }
 
+void hx_mond_rhs(const float *phig, float *out, int nxl, int n, float g0, int fn, float alpha) {
+  for (int il = 0; il < nxl; il++)
+    for (int j = 0; j < n; j++)
+      for (int k = 0; k < n; k++) {
+        float r;
+        switch (fn) {
+          case PSC_MOND_SIMPLE: r = mond_rhs_cell<PSC_MOND_SIMPLE>(phig, il, j, k, n, g0, alpha); break;
+          case PSC_MOND_N: r = mond_rhs_cell<PSC_MOND_N>(phig, il, j, k, n, g0, alpha); break;
+          case PSC_MOND_BETA: r = mond_rhs_cell<PSC_MOND_BETA>(phig, il, j, k, n, g0, alpha); break;
+          case PSC_MOND_GAMMA: r = mond_rhs_cell<PSC_MOND_GAMMA>(phig, il, j, k, n, g0, alpha); break;
+          default: r = mond_rhs_cell<PSC_MOND_DELTA>(phig, il, j, k, n, g0, alpha); break;
+        }
+        out[((size_t)il * n + j) * n + k] = r;
+      }
+}
+
 }  // extern "C"

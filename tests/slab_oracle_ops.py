@@ -32,7 +32,8 @@ def _harness():
             subprocess.check_call(["g++", "-O2", "-x", "c++", "-shared", "-fPIC", "-ffp-contract=off", "-o", tmp, src])
             os.replace(tmp, out)
         _HX = C.CDLL(out)
-        for f in ("hx_gs_colour", "hx_operator", "hx_restrict_residual", "hx_restriction", "hx_add_prolongation"):
+        for f in ("hx_gs_colour", "hx_operator", "hx_restrict_residual", "hx_restriction", "hx_add_prolongation",
+                  "hx_mond_rhs"):
             getattr(_HX, f).restype = None
     return _HX
 
@@ -280,6 +281,11 @@ class OracleOps:
     def mg_diff_sumsq(self, a, fa, b):
         d = np.float32(fa) * _np(a).astype(np.float32) - _np(b)
         return torch.tensor([float(np.sum(d.astype(np.float64) ** 2))], dtype=torch.float64)
+
+    def mond_rhs(self, phig, out, nxl, n, g0, fn, alpha):
+        import ctypes as C
+        _harness().hx_mond_rhs(_fp(phig), _fp(out), nxl, n, C.c_float(float(np.float32(g0))), int(fn),
+                               C.c_float(float(alpha)))
 
     def mg_cube_solve(self, res_cube, param, nlevel, coarsest):
         from oracle import host

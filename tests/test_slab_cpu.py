@@ -24,19 +24,19 @@ from oracle import host  # noqa: E402
 NSTEPS = 3
 
 
-def _setup(N, solver="fft"):
+def _setup(N, solver="fft", **overrides):
     tables = cases.toy_tables()
     pos = cases.lattice_particles(N, 0.4, seed=11)
     vel = cases.velocities(N ** 3, seed=12, scale=0.3)  # large enough that particles cross slab boundaries
-    param = cases.base_param(int(np.log2(N)), N ** 3, linear_newton_solver=solver)
+    param = cases.base_param(int(np.log2(N)), N ** 3, linear_newton_solver=solver, **overrides)
     param["aexp"] = 0.2
     param["t"] = float(tables[1](np.log(param["aexp"])))
     host.set_units(param)
     return tables, pos, vel, param
 
 
-def _reference(N, solver="fft"):
-    tables, pos, vel, param = _setup(N, solver)
+def _reference(N, solver="fft", **overrides):
+    tables, pos, vel, param = _setup(N, solver, **overrides)
     pos, vel = pos.copy(), vel.copy()
     acc, phi, add = host.pm(pos, param, tables=tables)
     state = [pos, vel, acc, phi, add]
@@ -46,10 +46,10 @@ def _reference(N, solver="fft"):
     return state, float(param["t"])
 
 
-def _run_rank(N, comm, out, reorder_at=None, solver="fft"):
+def _run_rank(N, comm, out, reorder_at=None, solver="fft", **overrides):
     from pysco_b200 import slab
     from slab_oracle_ops import OracleOps
-    tables, pos, vel, param = _setup(N, solver)
+    tables, pos, vel, param = _setup(N, solver, **overrides)
     P, r = comm.size, comm.rank
     # every rank adopts an arbitrary 1/P of the particles: set_particles must route them to their owners
     ids = np.arange(N ** 3, dtype=np.int64)
@@ -124,6 +124,45 @@ def test_slab_threads_vs_oracle(P, solver, N):
     [t.join() for t in ts]
     if errs:
         raise errs[0]
+    _check(out, ref, ref_t, P)
+
+
+MOND_CASES = [(1, "fft_7pt", dict(theory="mond")),
+              (2, "fft_7pt", dict(theory="mond")),
+              (4, "fft_7pt", dict(theory="mond", mond_function="beta", mond_alpha=1.5)),
+              (2, "multigrid", dict(theory="mond", mond_function="n", mond_alpha=2)),
+              (4, "multigrid", dict(theory="mond", mond_function="gamma", mond_alpha=1.5, mass_scheme="CIC"))]
+
+
+def _run_threads(P, N, solver, overrides, runner=None):
+    from pysco_b200 import slab
+    comms = slab.ThreadComm.world(P) if P > 1 else [slab.SelfComm()]
+    out, errs = {}, []
+
+    def work(c):
+        try:
+            (runner or _run_rank)(N, c, out, reorder_at=1, solver=solver, **overrides)
+        except BaseException as e:  # noqa: BLE001
+            errs.append(e)
+            if P > 1:
+                c.w.barrier.abort()
+
+    ts = [threading.Thread(target=work, args=(c,)) for c in comms]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    if errs:
+        raise errs[0]
+    return out
+
+
+@pytest.mark.parametrize("P,solver,overrides", MOND_CASES)
+def test_slab_mond_threads_vs_oracle(P, solver, overrides):
+    """theory = mond on slabs (QUMOND: Newtonian solve -> psc_box_mond_rhs on the ghosted Newtonian potential ->
+    second solve, with the two warm starts and the two tolerances of the multigrid variant): three steps against the
+    oracle's single-process step."""
+    N = 32
+    ref, ref_t = _reference(N, solver, **overrides)
+    out = _run_threads(P, N, solver, overrides)
     _check(out, ref, ref_t, P)
 
 

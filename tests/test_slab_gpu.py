@@ -21,9 +21,9 @@ import test_slab_cpu as cpu  # noqa: E402
 pytestmark = pytest.mark.gpu
 
 
-def _run_rank_cuda(N, comm, out, order, reorder_at=None, solver="fft"):
+def _run_rank_cuda(N, comm, out, order, reorder_at=None, solver="fft", **overrides):
     from pysco_b200 import slab
-    tables, pos, vel, param = cpu._setup(N, solver)
+    tables, pos, vel, param = cpu._setup(N, solver, **overrides)
     param["gradient_stencil_order"] = order
     P, r = comm.size, comm.rank
     ids = np.arange(N ** 3, dtype=np.int64)

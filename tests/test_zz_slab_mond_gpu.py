@@ -1,0 +1,30 @@
+"""GPU parity of theory = mond on x-slabs (QUMOND: psc_box_mond_rhs between two slab solves) against the oracle's
+single-process step, on P = 1, 2, 4 virtual ranks sharing cuda:0.
+
+The host sequencing and the per-cell kernel code are covered on the CPU tier (tests/test_slab_cpu.py,
+tests/test_slab_mg_cells_cpu.py); the GPU budget of round 1 ran out before this file could be run on a B200, hence the
+non-strict xfail marker (an XPASS in the log is the first GPU confirmation; remove the marker then).  The file sorts
+last so that it cannot disturb the validated suites."""
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "tests"), os.path.join(ROOT, "tests", "golden")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import test_slab_cpu as cpu  # noqa: E402
+import test_slab_gpu as gpu  # noqa: E402
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.xfail(strict=False, reason="first run on a B200 happens after round 1 (GPU budget exhausted)")]
+
+
+@pytest.mark.parametrize("P,solver,overrides", cpu.MOND_CASES)
+def test_slab_cuda_mond_vs_oracle(P, solver, overrides):
+    N = 32
+    ref, ref_t = cpu._reference(N, solver, **overrides)
+    out = gpu._threads(P, lambda c, o: gpu._run_rank_cuda(N, c, o, 5, reorder_at=1, solver=solver, **overrides))
+    cpu._check(out, ref, ref_t, P)
