@@ -289,6 +289,13 @@ int psc_box_restriction(const float *fine, int nxl, int n, float sign, float *co
 /* mesh.add_prolongation (mesh.py:334-453): fine_g[2 nxlc + 2][2 nc][2 nc] += P(coarse_g[nxlc + 2][nc][nc]); the coarse
  * ghost planes must be current, the fine ghost planes are not touched */
 int psc_box_add_prolongation(float *fine_g, const float *coarse_g, int nxlc, int nc, void *stream);
+/* f(R) scalaron on the slab, kind = PSC_OP_CUBIC (fR_n = 1) or PSC_OP_QUARTIC (fR_n = 2): one colour of
+ * cubic/quartic.gauss_seidel[_with_rhs] (cubic.py:269-627, quartic.py:270-628; rhs may be NULL), cubic/quartic.operator
+ * (cubic.py:23-81) and cubic/quartic.initialise_potential (cubic.py:217-259, quartic.py:214-260; b, out = owned planes) */
+int psc_box_gauss_seidel_colour_fr(float *xg, const float *b, const float *rhs, float q, int nxl, int n, int x0,
+                                   int colour, float f_relax, int kind, void *stream);
+int psc_box_operator_fr(const float *xg, const float *b, float q, int nxl, int n, int kind, float *out, void *stream);
+int psc_box_initialise_potential_fr(const float *b, float q, int nxl, int n, int kind, float *out, void *stream);
 /* mond.rhs_simple/n/beta/gamma/delta (mond.py:171-932) on the slab: phig[nxl + 2][n][n] is the Newtonian potential with
  * its ghost planes, out[nxl][n][n] the QUMOND source */
 int psc_box_mond_rhs(const float *phig, float *out, int nxl, int n, float g0, int fn, float alpha, void *stream);

@@ -91,6 +91,9 @@ SIGNATURES = {
     "psc_box_restriction": [_vp, _i, _i, _f, _vp, _vp],
     "psc_box_add_prolongation": [_vp, _vp, _i, _i, _vp],
     "psc_box_mond_rhs": [_vp, _vp, _i, _i, _f, _i, _f, _vp],
+    "psc_box_gauss_seidel_colour_fr": [_vp, _vp, _vp, _f, _i, _i, _i, _i, _f, _i, _vp],
+    "psc_box_operator_fr": [_vp, _vp, _f, _i, _i, _i, _vp, _vp],
+    "psc_box_initialise_potential_fr": [_vp, _f, _i, _i, _i, _vp, _vp],
 }
 _RESTYPES = {"psc_last_error": C.c_char_p, "psc_launch_count": _i64, "psc_argsort_workspace_bytes": _sz,
              "psc_bin_workspace_bytes": _sz, "psc_bin_workspace_bytes_slab": _sz,

@@ -66,6 +66,39 @@ __global__ void __launch_bounds__(BX_K *BX_J) box_add_prolongation_kernel(float 
   box::prolong_add_cell(fine_g, coarse_g, ci, cj, ck, nc);
 }
 
+// f(R): KIND = PSC_OP_CUBIC (n = 1) or PSC_OP_QUARTIC (n = 2); rhs (FAS coarse levels) may be NULL
+template <int KIND>
+__global__ void __launch_bounds__(BX_K *BX_J) box_gs_colour_fr_kernel(float *__restrict__ xg,
+                                                                      const float *__restrict__ b,
+                                                                      const float *__restrict__ rhs, float q,
+                                                                      int nxl, int n, int x0, int colour,
+                                                                      float f_relax) {
+  const int kh = blockIdx.x * BX_K + threadIdx.x;
+  const int j = blockIdx.y * BX_J + threadIdx.y;
+  const int il = blockIdx.z;
+  const int k = 2 * kh + ((x0 + il + j + colour) & 1);
+  if (k >= n || j >= n || il >= nxl) return;
+  box::gs_fr_cell<KIND>(xg, b, rhs, q, il, j, k, n, f_relax);
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(BX_K *BX_J) box_operator_fr_kernel(const float *__restrict__ xg,
+                                                                     const float *__restrict__ b, float q, int nxl,
+                                                                     int n, float *__restrict__ out) {
+  const int k = blockIdx.x * BX_K + threadIdx.x;
+  const int j = blockIdx.y * BX_J + threadIdx.y;
+  const int il = blockIdx.z;
+  if (k >= n || j >= n || il >= nxl) return;
+  out[((size_t)il * n + j) * n + k] = box::operator_fr_cell<KIND>(xg, b, q, il, j, k, n);
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(256) box_init_fr_kernel(const float *__restrict__ b, float q, int n, int64_t count,
+                                                          float *__restrict__ out) {
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < count; t += (int64_t)gridDim.x * blockDim.x)
+    out[t] = box::init_fr_cell<KIND>(b[t], q, n);
+}
+
 template <int FN>
 __global__ void __launch_bounds__(BX_K *BX_J) box_mond_rhs_kernel(const float *__restrict__ phig,
                                                                   float *__restrict__ out, int nxl, int n, float g0,
@@ -140,6 +173,56 @@ int psc_box_add_prolongation(float *fine_g, const float *coarse_g, int nxlc, int
   PSC_CHECK_ARG(fine_g && coarse_g, "null pointer");
   box_add_prolongation_kernel<<<box_grid(nc, nc, nxlc), box_block(), 0, as_stream(stream)>>>(fine_g, coarse_g, nxlc,
                                                                                             nc);
+  count_launch();
+  PSC_CHECK_LAUNCH();
+  return PSC_OK;
+}
+
+#define PSC_CHECK_FR_KIND(kind) \
+  PSC_CHECK_ARG((kind) == PSC_OP_CUBIC || (kind) == PSC_OP_QUARTIC, "kind must be PSC_OP_CUBIC or PSC_OP_QUARTIC")
+
+int psc_box_gauss_seidel_colour_fr(float *xg, const float *b, const float *rhs, float q, int nxl, int n, int x0,
+                                   int colour, float f_relax, int kind, void *stream) {
+  PSC_CHECK_BOX(nxl, n);
+  PSC_CHECK_FR_KIND(kind);
+  PSC_CHECK_ARG(xg && b, "null pointer");
+  PSC_CHECK_ARG(x0 >= 0 && (colour == 0 || colour == 1), "x0 must be >= 0 and colour 0 or 1");
+  if (kind == PSC_OP_CUBIC)
+    box_gs_colour_fr_kernel<PSC_OP_CUBIC><<<box_grid(n / 2, n, nxl), box_block(), 0, as_stream(stream)>>>(
+        xg, b, rhs, q, nxl, n, x0, colour, f_relax);
+  else
+    box_gs_colour_fr_kernel<PSC_OP_QUARTIC><<<box_grid(n / 2, n, nxl), box_block(), 0, as_stream(stream)>>>(
+        xg, b, rhs, q, nxl, n, x0, colour, f_relax);
+  count_launch();
+  PSC_CHECK_LAUNCH();
+  return PSC_OK;
+}
+
+int psc_box_operator_fr(const float *xg, const float *b, float q, int nxl, int n, int kind, float *out,
+                        void *stream) {
+  PSC_CHECK_BOX(nxl, n);
+  PSC_CHECK_FR_KIND(kind);
+  PSC_CHECK_ARG(xg && b && out, "null pointer");
+  if (kind == PSC_OP_CUBIC)
+    box_operator_fr_kernel<PSC_OP_CUBIC><<<box_grid(n, n, nxl), box_block(), 0, as_stream(stream)>>>(xg, b, q, nxl,
+                                                                                                    n, out);
+  else
+    box_operator_fr_kernel<PSC_OP_QUARTIC><<<box_grid(n, n, nxl), box_block(), 0, as_stream(stream)>>>(xg, b, q, nxl,
+                                                                                                      n, out);
+  count_launch();
+  PSC_CHECK_LAUNCH();
+  return PSC_OK;
+}
+
+int psc_box_initialise_potential_fr(const float *b, float q, int nxl, int n, int kind, float *out, void *stream) {
+  PSC_CHECK_BOX(nxl, n);
+  PSC_CHECK_FR_KIND(kind);
+  PSC_CHECK_ARG(b && out, "null pointer");
+  const int64_t count = (int64_t)nxl * n * n;
+  if (kind == PSC_OP_CUBIC)
+    box_init_fr_kernel<PSC_OP_CUBIC><<<grid_for(count, 256), 256, 0, as_stream(stream)>>>(b, q, n, count, out);
+  else
+    box_init_fr_kernel<PSC_OP_QUARTIC><<<grid_for(count, 256), 256, 0, as_stream(stream)>>>(b, q, n, count, out);
   count_launch();
   PSC_CHECK_LAUNCH();
   return PSC_OK;

@@ -6,7 +6,8 @@
 // y and z stay periodic inside the box.  The arithmetic (association order included) is the one of the single-domain
 // kernels in multigrid.cu, so a one-rank slab reproduces them bit for bit:
 //   laplacian.py: operator :12, restrict_residual :125, gauss_seidel :844;  mesh.py: restriction :14,
-//   add_prolongation :334;  mond.py: rhs_simple/n/beta/gamma/delta :171-932.
+//   add_prolongation :334;  cubic.py / quartic.py: operator, gauss_seidel[_with_rhs], initialise_potential;
+//   mond.py: rhs_simple/n/beta/gamma/delta :171-932.
 //
 // The bodies are plain functions of (il, j, k) so that the CPU tier can run the very same code through a host
 // harness (tests/slab_mg_harness.cpp) -- the __global__ wrappers in slab_mg.cu only map threads to cells.
@@ -124,6 +125,127 @@ PSC_CELL void prolong_add_cell(float *fine_g, const float *coarse_g, int ci, int
                         f2 * (v[A][E][1] + v[1][E][G] + v[A][1][G]) + f3 * v[A][E][G];
         fine_g[(size_t)(2 * ci + a + 1) * n2 + (size_t)(2 * cj + e) * n + 2 * ck + g] += r;
       }
+}
+
+// ----------------------------------------------------------------------------------- f(R) scalaron (FAS)
+// closed-form roots in float64, float32 in / out -- as multigrid.cu solve_cubic / solve_quartic
+PSC_CELL float solve_cubic(float pf, float d1f) {
+  // cubic.py:162-207
+  const double inv3 = 1.0 / 3;
+  double d1 = (double)d1f, p = (double)pf;
+  double d = d1 * d1 + 108.0 * (p * p * p);
+  if (d > 0.0) {
+    d = d1 + sqrt(d);
+    if (d == 0.0) return (float)(-inv3 * pow(d1, inv3));
+    double C = pow(0.5 * d, inv3);
+    return (float)(-inv3 * (C - 3.0 * p / C));
+  } else if (d < 0.0) {
+    double d0 = -3.0 * p;
+    double s0 = sqrt(d0);
+    d = d1 / (2.0 * (d0 * s0));
+    if (fabs(d) < 1.0) {
+      double theta = acos(d);
+      return (float)(-2.0 * inv3 * s0 * cos(inv3 * (theta + 2.0 * 3.14159265358979323846)));
+    }
+    return (float)(-inv3 * pow(d1, inv3));
+  }
+  return (float)(-inv3 * pow(d1, inv3));
+}
+PSC_CELL float solve_quartic(float pf, float qf) {
+  // quartic.py:157-204
+  double pp = (double)pf, qq = (double)qf;
+  if (pp == 0.0) return (float)pow(-qq, 0.25);
+  const double inv3 = 1.0 / 3.0;
+  double d0 = 12.0 * qq;
+  double d1 = 27.0 * (pp * pp);
+  double r = d0 / d1;
+  double sqrt_term = 1.0 - 4.0 * d0 * (r * r);
+  if (sqrt_term < 0.0) return (float)pow(-qq, 0.25);
+  double Q = pow(0.5 * d1 * (1.0 + sqrt(sqrt_term)), inv3);
+  double Qd = Q + d0 / Q;
+  if (Qd > 0.0) {
+    double S = 0.5 * sqrt(Qd * inv3);
+    if (pp > 0.0) return (float)(-S + 0.5 * sqrt(-4.0 * (S * S) + pp / S));
+    return (float)(S + 0.5 * sqrt(-4.0 * (S * S) - pp / S));
+  }
+  return (float)pow(-qq, 0.25);
+}
+
+// KIND = PSC_OP_CUBIC: squares of the neighbours, PSC_OP_QUARTIC: cubes
+template <int KIND>
+PSC_CELL float npow(float v) {
+  return KIND == PSC_OP_CUBIC ? v * v : v * v * v;
+}
+template <int KIND>
+PSC_CELL float nb6_pow(const float *xg, int il, int j, int k, int n) {
+  const size_t n2 = (size_t)n * n;
+  const size_t ri = (size_t)(il + 1) * n2, rj = (size_t)j * n;
+  float a = xg[ri - n2 + rj + k];
+  float b = xg[ri + (size_t)pwrap(j - 1, n) * n + k];
+  float c = xg[ri + rj + pwrap(k - 1, n)];
+  float d = xg[ri + rj + pwrap(k + 1, n)];
+  float e = xg[ri + (size_t)pwrap(j + 1, n) * n + k];
+  float f = xg[ri + n2 + rj + k];
+  return npow<KIND>(a) + npow<KIND>(b) + npow<KIND>(c) + npow<KIND>(d) + npow<KIND>(e) + npow<KIND>(f);
+}
+
+// one nonlinear SOR update (cubic.py:269-627, quartic.py:270-628); rhs may be NULL (finest level)
+template <int KIND>
+PSC_CELL void gs_fr_cell(float *xg, const float *b, const float *rhs, float q, int il, int j, int k, int n,
+                         float f_relax) {
+  const size_t n2 = (size_t)n * n;
+  const size_t tx = (size_t)(il + 1) * n2 + (size_t)j * n + k;
+  const size_t tb = (size_t)il * n2 + (size_t)j * n + k;
+  const float h2 = 1.0f / ((float)n * (float)n);
+  const float invsix = 1.0f / 6.0f;
+  float xt = xg[tx];
+  float s = nb6_pow<KIND>(xg, il, j, k, n);
+  float p = h2 * b[tb] - invsix * s;
+  float target;
+  if (KIND == PSC_OP_CUBIC) {
+    float d1 = 27.0f * h2 * q;
+    if (rhs) d1 -= 27.0f * rhs[tb];
+    target = solve_cubic(p, d1);
+  } else {
+    float qq = q * h2;
+    if (rhs) qq -= rhs[tb];
+    target = solve_quartic(p, qq);
+  }
+  xg[tx] = xt + f_relax * (target - xt);
+}
+
+// L(u) = u^3 + p u + q h^2 (cubic.py:23-81) or u^4 + p u + q h^2 (quartic.py), p = h^2 b - sum6(u^2 | u^3) / 6
+template <int KIND>
+PSC_CELL float operator_fr_cell(const float *xg, const float *b, float q, int il, int j, int k, int n) {
+  const size_t n2 = (size_t)n * n;
+  const float h2 = 1.0f / ((float)n * (float)n), invsix = 1.0f / 6.0f;
+  const float cur = xg[(size_t)(il + 1) * n2 + (size_t)j * n + k];
+  const float s6 = nb6_pow<KIND>(xg, il, j, k, n);
+  const float p = h2 * b[(size_t)il * n2 + (size_t)j * n + k] - invsix * s6;
+  const float lead = KIND == PSC_OP_CUBIC ? cur * cur * cur : (cur * cur) * (cur * cur);
+  return lead + p * cur + q * h2;
+}
+
+// first guess from the density term alone (cubic.py:217-259, quartic.py:214-260)
+template <int KIND>
+PSC_CELL float init_fr_cell(float bt, float q, int n) {
+  if (KIND == PSC_OP_CUBIC) {
+    const float h2 = 1.0f / ((float)n * (float)n);
+    const float threeh2 = 3.0f * h2;
+    const double d1 = 27.0 * (double)h2 * (double)q;
+    float d0 = -threeh2 * bt;
+    double d03 = (double)d0 * (double)d0 * (double)d0;
+    double C = cbrt(0.5 * (d1 + sqrt(d1 * d1 - 4.0 * d03)));
+    return (float)(-(1.0 / 3) * (C + (double)d0 / C));
+  }
+  const double h2 = 1.0 / ((double)n * (double)n);
+  const double inv3 = 1.0 / 3;
+  const double d0 = 12.0 * h2 * (double)q;
+  double p = h2 * (double)bt;
+  double d1 = 27.0 * (p * p);
+  double Q = pow(0.5 * (d1 + sqrt(d1 * d1 - 4.0 * (d0 * d0 * d0))), inv3);
+  double S = 0.5 * sqrt((Q + d0 / Q) * inv3);
+  return (float)(-S + 0.5 * sqrt(-4.0 * (S * S) + p / S));
 }
 
 // ----------------------------------------------------------------------------------- MOND

@@ -451,10 +451,11 @@ class CudaOps:
         _lib.check(self.lib.psc_linear_operator(_lib.ptr(x), float(f1), float(f2), _lib.ptr(x), x.numel(),
                                                 _lib.stream()))
 
-    def interp_kick_phi(self, phi_g, ghost, order, binned, vel, acc, scheme, half_dt):
+    def interp_kick_phi(self, phi_g, ghost, order, binned, vel, acc, scheme, half_dt, u_g=None, f=0.0, fr_n=0):
+        """u_g, f, fr_n: the f(R) fifth force, gradient of phi + f u^(fr_n + 1) (mesh.py:860-2069)"""
         mx = torch.zeros((2,), dtype=torch.float32, device=self.dev)
         _lib.check(self.lib.psc_interp_kick_phi_binned_slab(
-            _lib.ptr(phi_g), None, 0.0, 0, order, self.x0, self.nxl, ghost, _lib.ptr(self._scratch),
+            _lib.ptr(phi_g), _lib.ptr(u_g), float(f), int(fr_n), order, self.x0, self.nxl, ghost, _lib.ptr(self._scratch),
             self._scratch.numel(), _lib.ptr(vel), _lib.ptr(acc), binned, self.N, scheme, float(half_dt), _lib.ptr(mx),
             _lib.stream()))
         return mx
@@ -534,6 +535,42 @@ class CudaOps:
                                            _lib.stream()))
         return out
 
+    def mg_gs_colour_fr(self, xg, b, rhs, q, nxl, n, x0, colour, f_relax, kind):
+        _lib.check(self.lib.psc_box_gauss_seidel_colour_fr(_lib.ptr(xg), _lib.ptr(b), _lib.ptr(rhs), float(q), nxl, n,
+                                                           x0, colour, float(f_relax), kind, _lib.stream()))
+
+    def mg_operator_fr(self, xg, b, q, nxl, n, kind):
+        out = torch.empty((nxl, n, n), dtype=torch.float32, device=self.dev)
+        _lib.check(self.lib.psc_box_operator_fr(_lib.ptr(xg), _lib.ptr(b), float(q), nxl, n, kind, _lib.ptr(out),
+                                                _lib.stream()))
+        return out
+
+    def mg_init_fr(self, b, q, nxl, n, kind, out):
+        _lib.check(self.lib.psc_box_initialise_potential_fr(_lib.ptr(b), float(q), nxl, n, kind, _lib.ptr(out),
+                                                            _lib.stream()))
+
+    def lincomb(self, x, f1, y, f2):
+        """utils.linear_operator_vectors_inplace (utils.py:721-755): x = f1 x + f2 y"""
+        _lib.check(self.lib.psc_lincomb(_lib.ptr(x), float(f1), _lib.ptr(y), float(f2), x.numel(), _lib.stream()))
+
+    def axpy(self, y, x, a):
+        """utils.add_vector_scalar_inplace (utils.py:264-297) with a float32 scalar: y += a x"""
+        _lib.check(self.lib.psc_axpy(_lib.ptr(y), _lib.ptr(x), float(a), 0, y.numel(), _lib.stream()))
+
+    def mg_cube_solve_fas(self, x_c, b_c, res_c, param, nlevel, coarsest):
+        """a gathered coarse FAS problem, solved on every rank by the single-domain kernels (multigrid.py:540-570):
+        returns the correction x_corr - x_c"""
+        from . import multigrid, utils
+        L_c = multigrid.operator(x_c, param, b_c)
+        utils.linear_operator_vectors_inplace(res_c, np.float32(4), L_c, np.float32(1))
+        corr = x_c.clone()
+        if coarsest:
+            multigrid.smoothing(corr, b_c, param["Npre"], param, res_c)
+        else:
+            multigrid._cycle_FAS("V", corr, b_c, param, nlevel + 1, res_c)
+        utils.add_vector_scalar_inplace(corr, x_c, np.float32(-1))
+        return corr
+
     def mond_rhs(self, phig, out, nxl, n, g0, fn, alpha):
         _lib.check(self.lib.psc_box_mond_rhs(_lib.ptr(phig), _lib.ptr(out), nxl, n, float(np.float32(g0)), int(fn),
                                              float(alpha), _lib.stream()))
@@ -577,7 +614,7 @@ class Slab:
         self.pos = self.vel = self.acc = self.ids = None
         self.max_acc = self.max_vel = None
         self.potential = None  # owned planes [nxl, N, N] of the last solve (a view into the ghosted array)
-        self.additional_field = None   # MOND: owned planes of the Newtonian potential of the last step
+        self.additional_field = None   # owned planes of the last step's Newtonian potential (MOND) / scalaron (f(R))
         self.migrated_last = (0, 0)
         self._warm_host_ops()
         self._spare3 = self._spare1 = None   # spare particle buffers the reorder gathers into (then swapped in)
@@ -918,6 +955,48 @@ class Slab:
         ops.fft_x(a, False)
         self._write_pk(a, param, from_density=True)
 
+    @staticmethod
+    def _fr_force_factor(param):
+        """(0.5 c^2 (-f_R(a)), fR_n): the fifth force is -grad(phi + f u^(n+1)) (solver.py:166-179)"""
+        from .solver import _fr_background
+        _, fR_a, c2 = _fr_background(param)
+        return np.float32(0.5 * (-fR_a) * c2), int(param["fR_n"])
+
+    def _scalaron(self, density_planes, G, param):
+        """solver.get_additional_field for f(R) (solver.py:326-359): density term, q, first guess (the previous scalaron,
+        or cubic / quartic.initialise_potential), multigrid.FAS on the slab.  Returns the scalaron with G ghost planes
+        per side, filled (the force stencil needs them)."""
+        from .slab_multigrid import SlabMultigrid
+        from .solver import _fr_background
+        if self._mg is None:
+            self._mg = SlabMultigrid(self.comm, self.ops, self.N)
+        ops, N, nxl = self.ops, self.N, self.nxl
+        kind = SlabMultigrid.fr_kind(param)
+        Rbar, fR_a, c2 = _fr_background(param)
+        a = param["aexp"]
+        f1 = np.float32(a * param["Om_m"] / (c2 * 6)) / (-fR_a)
+        f2 = np.float32(Rbar / 3 * a ** 4 - param["Om_m"] * a) / (6 * c2) / (-fR_a)
+        dens_term = density_planes.clone()
+        ops.affine(dens_term, f1, f2)
+        q = np.float32(-a ** 4 * Rbar / (18 * c2)) / (-fR_a)
+        param["fR_q"] = q
+        param["compute_additional_field"] = True
+        u_g = torch.empty((nxl + 2 * G, N, N), dtype=torch.float32, device=density_planes.device)
+        xg = u_g[G - 1:G + nxl + 1]
+        own = u_g[G:G + nxl]
+        if self.additional_field is None:
+            ops.mg_init_fr(dens_term, np.float32(q), nxl, N, kind, own)
+        else:
+            own.copy_(self.additional_field)
+        self._mg.fas(xg, dens_term, param)
+        param["compute_additional_field"] = False
+        self.additional_field = own
+        from_left, from_right = self.comm.exchange_planes(u_g[G:2 * G], u_g[nxl:nxl + G])
+        u_g[:G] = from_left
+        u_g[nxl + G:] = from_right
+        self._mark("scalaron FAS")
+        return u_g
+
     def _poisson(self, rhs_planes, out_g, G, param, tables, previous):
         """one linear Poisson solve into the owned planes out_g[G : G + nxl] of a ghosted array"""
         if param["linear_newton_solver"].casefold() == "multigrid":
@@ -951,15 +1030,16 @@ class Slab:
 
     # -- solver.pm on the slab
     def pm(self, param, kick=None, tables=None):
-        """solver.pm (solver.py:30-215): theory newton / parametrized (linear_newton_solver = fft, fft_7pt or multigrid)
-        and mond (QUMOND: fft_7pt or multigrid, two solves around the nu-weighted source).  Fills self.acc[:np]; with
+        """solver.pm (solver.py:30-215): theory newton / parametrized (linear_newton_solver = fft, fft_7pt or multigrid),
+        mond (QUMOND: fft_7pt or multigrid, two solves around the nu-weighted source) and fr (scalaron by FAS multigrid,
+        then the Newtonian solve; the fifth force enters through the gradient).  Fills self.acc[:np]; with
         kick = half_dt also applies the second half-kick to the velocities.  ``tables`` (the cosmology interpolators)
         are only needed by the multigrid warm start (solver.py:274-281).  Returns the device tensor [max|a|, max|v|]
         already reduced over ranks."""
         ops, comm, N, nxl = self.ops, self.comm, self.N, self.nxl
         theory = param["theory"].casefold()
-        if theory not in ("newton", "parametrized", "mond"):
-            raise NotImplementedError(f"slab path: theory={param['theory']!r} (newton / parametrized / mond only)")
+        if theory not in ("newton", "parametrized", "mond", "fr"):
+            raise NotImplementedError(f"{param['theory']=}, should be 'newton', 'fr', 'parametrized' or 'mond'")
         solver_name = param["linear_newton_solver"].casefold()
         if theory == "mond" and solver_name not in ("multigrid", "fft_7pt"):
             raise NotImplementedError(f"{param['linear_newton_solver']=}, should be 'multigrid' or 'fft_7pt'")
@@ -997,12 +1077,15 @@ class Slab:
         use_multigrid = solver_name == "multigrid"
         if use_multigrid and param["save_pk"]:
             self._pk_from_density(rhs, param)      # solver.py:130-138: P(k) of the density, not of the RHS
-        f1 = np.float32(1.5 * param["aexp"] * param["Om_m"] * param["parametrized_mu_z"])
-        ops.affine(rhs, f1, -f1)
-        self._mark("density ghosts+rhs")
         G = 1 + _REACH[order]
         if nxl < G:
             raise ValueError(f"slab of {nxl} planes is thinner than the {G} ghost planes the stencils need")
+        u_g, half_c2, fr_n = None, 0.0, 0
+        if theory == "fr":
+            u_g, half_c2, fr_n = self._scalaron(rhs, G, param), *self._fr_force_factor(param)
+        f1 = np.float32(1.5 * param["aexp"] * param["Om_m"] * param["parametrized_mu_z"])
+        ops.affine(rhs, f1, -f1)
+        self._mark("density ghosts+rhs")
         phi_g = torch.empty((nxl + 2 * G, N, N), dtype=torch.float32, device=rho.device)
         if theory == "mond":
             # QUMOND (solver.py:104-127, 365-378, 404-431): Newtonian potential phi_N (the "additional field") ->
@@ -1034,8 +1117,12 @@ class Slab:
         phi_g[nxl + G:] = from_right   # the right neighbour's first G owned planes
         half_dt = 0.0 if kick is None else kick
         self._mark("potential ghosts")
-        mx = ops.interp_kick_phi(phi_g, G, order, binned, self.vel[:n] if kick is not None else None,
-                                 self.acc[:n], scheme, half_dt)
+        if u_g is not None:
+            mx = ops.interp_kick_phi(phi_g, G, order, binned, self.vel[:n] if kick is not None else None,
+                                     self.acc[:n], scheme, half_dt, u_g, half_c2, fr_n)
+        else:
+            mx = ops.interp_kick_phi(phi_g, G, order, binned, self.vel[:n] if kick is not None else None,
+                                     self.acc[:n], scheme, half_dt)
         self.potential = phi_g[G:G + nxl]
         if kick is None:
             mx[1] = ops.max_abs(self.vel[:n])[0]

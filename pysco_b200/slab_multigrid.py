@@ -12,13 +12,19 @@ csrc/slab_mg.cu, as SURVEY 8(e) lays it out.
 
 The cycle is the reference's: Npre smoothing sweeps, R(b - Lx), first guess -h^2/6 b, recursion (or Npre sweeps on the
 coarsest 4^3 level), x += P(correction), Npost sweeps; stopping rule and truncation-error refresh as multigrid.py:62-80.
+
+The f(R) scalaron uses the same decomposition for the full-approximation-storage cycle (multigrid.FAS,
+multigrid.py:88-140, 521-579): nonlinear red-black sweeps (cubic / quartic closed-form roots), coarse problem
+L(x_c) = 4 R(residual) + L(R x), correction x_c - R x prolongated back.
 """
 import logging
 
 import numpy as np
 import torch
 
-F_RELAX = np.float32(1.25)   # laplacian.py:1053
+from . import _lib
+
+F_RELAX = np.float32(1.25)   # laplacian.py:1053, cubic.py:1094, 1133
 
 
 class SlabMultigrid:
@@ -127,6 +133,105 @@ class SlabMultigrid:
         while residual_err > tolerance:
             self.v_cycle(xg, b, n, nxl, param, 0)
             residual_error_tmp = self.residual_error(xg, b, n, nxl)
+            logging.info(f"{residual_error_tmp=} {tolerance=}")
+            if residual_error_tmp < tolerance or residual_err / residual_error_tmp < 2:
+                break
+            residual_err = residual_error_tmp
+        return xg
+
+    # ------------------------------------------------------------------------------------ f(R): FAS
+    @staticmethod
+    def fr_kind(param):
+        n = param["fR_n"]
+        if n == 1:
+            return _lib.OP_CUBIC
+        if n == 2:
+            return _lib.OP_QUARTIC
+        raise NotImplementedError(f"Only f(R) with n = 1 and 2, currently {param['fR_n']=}")
+
+    def smoothing_fr(self, xg, b, rhs, q, kind, n, nxl, sweeps):
+        """cubic / quartic.smoothing[_with_rhs] (cubic.py:1064-1140); rhs = None on the finest level"""
+        x0 = self.rank * nxl
+        for _ in range(int(sweeps)):
+            for colour in (1, 0):
+                self.exchange(xg, nxl)
+                self.ops.mg_gs_colour_fr(xg, b, rhs, q, nxl, n, x0, colour, F_RELAX, kind)
+
+    def residual_error_fr(self, xg, b, q, kind, n, nxl):
+        """cubic / quartic.residual_error (cubic.py:844-901): sqrt(sum L(x)^2)"""
+        self.exchange(xg, nxl)
+        Lx = self.ops.mg_operator_fr(xg, b, q, nxl, n, kind)
+        return self._norm(self.ops.mg_diff_sumsq(Lx, 2.0, Lx))     # (2 L - L)^2 = L^2, exactly
+
+    def truncation_error_fr(self, xg, b, q, kind, n, nxl):
+        """cubic / quartic.truncation_error (cubic.py:1021-1061): || 4 R(L x) - L(R x; R b) ||"""
+        ops = self.ops
+        nc, nxlc = n // 2, nxl // 2
+        self.exchange(xg, nxl)
+        RLx = ops.mg_restriction(ops.mg_operator_fr(xg, b, q, nxl, n, kind), nxl, n, 1.0)
+        Rxg = torch.empty((nxlc + 2, nc, nc), dtype=torch.float32, device=xg.device)
+        ops.mg_restriction(xg[1:nxl + 1], nxl, n, 1.0, out=Rxg[1:nxlc + 1])
+        self.exchange(Rxg, nxlc)
+        LRx = ops.mg_operator_fr(Rxg, ops.mg_restriction(b, nxl, n, 1.0), q, nxlc, nc, kind)
+        return self._norm(ops.mg_diff_sumsq(RLx, 4.0, LRx))
+
+    # -- multigrid.V_cycle_FAS (multigrid.py:521-579)
+    def v_cycle_fas(self, xg, b, n, nxl, param, nlevel, rhs, q, kind):
+        ops = self.ops
+        nc, nxlc = n // 2, nxl // 2
+        self.smoothing_fr(xg, b, rhs, q, kind, n, nxl, param["Npre"])
+        b_c = ops.mg_restriction(b, nxl, n, 1.0)
+        self.exchange(xg, nxl)
+        Lx = ops.mg_operator_fr(xg, b, q, nxl, n, kind)
+        if rhs is None:
+            res_c = ops.mg_restriction(Lx, nxl, n, -1.0)            # minus_restriction(L x)
+        else:
+            ops.lincomb(Lx, -1.0, rhs, 1.0)                         # rhs - L x
+            res_c = ops.mg_restriction(Lx, nxl, n, 1.0)
+        del Lx
+        coarsest = nlevel >= (param["ncoarse"] - 3)
+        if nxlc >= 2:
+            cg = torch.empty((nxlc + 2, nc, nc), dtype=torch.float32, device=xg.device)
+            own = cg[1:nxlc + 1]
+            ops.mg_restriction(xg[1:nxl + 1], nxl, n, 1.0, out=own)  # x_c = R x, the first guess of the coarse problem
+            x_c = own.clone()
+            self.exchange(cg, nxlc)
+            L_c = ops.mg_operator_fr(cg, b_c, q, nxlc, nc, kind)
+            ops.lincomb(res_c, 4.0, L_c, 1.0)                       # coarse right-hand side 4 R(res) + L(R x)
+            del L_c
+            if coarsest:
+                self.smoothing_fr(cg, b_c, res_c, q, kind, nc, nxlc, param["Npre"])
+            else:
+                self.v_cycle_fas(cg, b_c, nc, nxlc, param, nlevel + 1, res_c, q, kind)
+            ops.axpy(own, x_c, -1.0)                                # correction = x_c - R x
+            self.exchange(cg, nxlc)
+        else:
+            # one coarse plane per rank: the coarse problem is gathered and solved on every rank
+            x_c = ops.mg_restriction(xg[1:nxl + 1], nxl, n, 1.0)
+            corr = ops.mg_cube_solve_fas(self._gather_level(x_c, nc), self._gather_level(b_c, nc),
+                                         self._gather_level(res_c, nc), param, nlevel, coarsest)
+            c0 = self.rank * nxlc
+            idx = torch.tensor([(c0 - 1 + p) % nc for p in range(nxlc + 2)], dtype=torch.int64, device=corr.device)
+            cg = corr.index_select(0, idx)
+        ops.mg_add_prolongation(xg, cg, nxlc, nc)
+        self.smoothing_fr(xg, b, rhs, q, kind, n, nxl, param["Npost"])
+
+    # -- multigrid.FAS (multigrid.py:88-140)
+    def fas(self, xg, b, param):
+        """xg [nxl + 2, N, N]: first guess of the scalaron in the owned planes, solution on return; b [nxl, N, N] the
+        density term; q = param["fR_q"]."""
+        n, nxl = self.N, self.nxl
+        kind = self.fr_kind(param)
+        q = np.float32(param["fR_q"])
+        if ("tolerance_FAS" not in param) or (param["nsteps"] % 3) == 0:
+            logging.info("Compute FAS Truncation error")
+            param["tolerance_FAS"] = param["epsrel"] * self.truncation_error_fr(xg, b, q, kind, n, nxl)
+        tolerance = param["tolerance_FAS"]
+        logging.info("Start Full-Approximation Storage Multigrid (slab)")
+        residual_err = 1e30
+        while residual_err > tolerance:
+            self.v_cycle_fas(xg, b, n, nxl, param, 0, None, q, kind)
+            residual_error_tmp = self.residual_error_fr(xg, b, q, kind, n, nxl)
             logging.info(f"{residual_error_tmp=} {tolerance=}")
             if residual_error_tmp < tolerance or residual_err / residual_error_tmp < 2:
                 break

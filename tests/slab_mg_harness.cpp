@@ -45,6 +45,31 @@ void hx_add_prolongation(float *fine_g, const float *coarse_g, int nxlc, int nc)
       for (int ck = 0; ck < nc; ck++) prolong_add_cell(fine_g, coarse_g, ci, cj, ck, nc);
 }
 
+void hx_gs_colour_fr(float *xg, const float *b, const float *rhs, float q, int nxl, int n, int x0, int colour,
+                     float f_relax, int kind) {
+  for (int il = 0; il < nxl; il++)
+    for (int j = 0; j < n; j++)
+      for (int kh = 0; kh < n / 2; kh++) {
+        const int k = 2 * kh + ((x0 + il + j + colour) & 1);
+        if (kind == PSC_OP_CUBIC) gs_fr_cell<PSC_OP_CUBIC>(xg, b, rhs, q, il, j, k, n, f_relax);
+        else gs_fr_cell<PSC_OP_QUARTIC>(xg, b, rhs, q, il, j, k, n, f_relax);
+      }
+}
+
+void hx_operator_fr(const float *xg, const float *b, float q, int nxl, int n, int kind, float *out) {
+  for (int il = 0; il < nxl; il++)
+    for (int j = 0; j < n; j++)
+      for (int k = 0; k < n; k++)
+        out[((size_t)il * n + j) * n + k] = kind == PSC_OP_CUBIC ? operator_fr_cell<PSC_OP_CUBIC>(xg, b, q, il, j, k, n)
+                                                                 : operator_fr_cell<PSC_OP_QUARTIC>(xg, b, q, il, j, k, n);
+}
+
+void hx_init_fr(const float *b, float q, int nxl, int n, int kind, float *out) {
+  const size_t count = (size_t)nxl * n * n;
+  for (size_t t = 0; t < count; t++)
+    out[t] = kind == PSC_OP_CUBIC ? init_fr_cell<PSC_OP_CUBIC>(b[t], q, n) : init_fr_cell<PSC_OP_QUARTIC>(b[t], q, n);
+}
+
 void hx_mond_rhs(const float *phig, float *out, int nxl, int n, float g0, int fn, float alpha) {
   for (int il = 0; il < nxl; il++)
     for (int j = 0; j < n; j++)

@@ -33,7 +33,7 @@ def _harness():
             os.replace(tmp, out)
         _HX = C.CDLL(out)
         for f in ("hx_gs_colour", "hx_operator", "hx_restrict_residual", "hx_restriction", "hx_add_prolongation",
-                  "hx_mond_rhs"):
+                  "hx_mond_rhs", "hx_gs_colour_fr", "hx_operator_fr", "hx_init_fr"):
             getattr(_HX, f).restype = None
     return _HX
 
@@ -179,10 +179,15 @@ class OracleOps:
         a = _np(x)
         oracle.utils.linear_operator_inplace(a.reshape(-1), np.float32(f1), np.float32(f2))
 
-    def interp_kick_phi(self, phi_g, ghost, order, binned, vel, acc, scheme, half_dt):
+    def interp_kick_phi(self, phi_g, ghost, order, binned, vel, acc, scheme, half_dt, u_g=None, f=0.0, fr_n=0):
         full = np.zeros((self.N,) * 3, np.float32)
         full[self._planes(ghost)] = _np(phi_g)
-        force = oracle.mesh.derivative(full, order)
+        if u_g is not None:
+            full_u = np.zeros((self.N,) * 3, np.float32)
+            full_u[self._planes(ghost)] = _np(u_g)
+            force = oracle.mesh.derivative_fR(full, full_u, np.float32(f), fr_n, order)
+        else:
+            force = oracle.mesh.derivative(full, order)
         fn = {1: oracle.mesh.invCIC_vec, 2: oracle.mesh.invTSC_vec}[scheme]
         a = fn(force, self._binned) if binned else np.zeros((0, 3), np.float32)
         _np(acc)[:] = a
@@ -281,6 +286,42 @@ class OracleOps:
     def mg_diff_sumsq(self, a, fa, b):
         d = np.float32(fa) * _np(a).astype(np.float32) - _np(b)
         return torch.tensor([float(np.sum(d.astype(np.float64) ** 2))], dtype=torch.float64)
+
+    def mg_gs_colour_fr(self, xg, b, rhs, q, nxl, n, x0, colour, f_relax, kind):
+        import ctypes as C
+        _harness().hx_gs_colour_fr(_fp(xg), _fp(b), _fp(rhs) if rhs is not None else None, C.c_float(float(q)), nxl, n,
+                                   x0, colour, C.c_float(float(f_relax)), kind)
+
+    def mg_operator_fr(self, xg, b, q, nxl, n, kind):
+        import ctypes as C
+        out = torch.empty((nxl, n, n), dtype=torch.float32)
+        _harness().hx_operator_fr(_fp(xg), _fp(b), C.c_float(float(q)), nxl, n, kind, _fp(out))
+        return out
+
+    def mg_init_fr(self, b, q, nxl, n, kind, out):
+        import ctypes as C
+        _harness().hx_init_fr(_fp(b), C.c_float(float(q)), nxl, n, kind, _fp(out))
+
+    def lincomb(self, x, f1, y, f2):
+        oracle.utils.linear_operator_vectors_inplace(_np(x).reshape(-1), np.float32(f1), _np(y).reshape(-1),
+                                                     np.float32(f2))
+
+    def axpy(self, y, x, a):
+        oracle.utils.add_vector_scalar_inplace(_np(y).reshape(-1, 1), _np(x).reshape(-1, 1), np.float32(a))
+
+    def mg_cube_solve_fas(self, x_c, b_c, res_c, param, nlevel, coarsest):
+        from oracle import host
+        x_c, b_c, res_c = (np.ascontiguousarray(_np(t)) for t in (x_c, b_c, res_c))
+        q = np.float32(param["fR_q"])
+        L_c = host._fr_mod(param).operator(x_c, b_c, q)
+        oracle.utils.linear_operator_vectors_inplace(res_c, np.float32(4), L_c, np.float32(1))
+        corr = x_c.copy()
+        if coarsest:
+            host._fas_smooth(corr, b_c, param["Npre"], param, res_c)
+        else:
+            host._cycle_FAS("V", corr, b_c, param, nlevel + 1, res_c)
+        oracle.utils.add_vector_scalar_inplace(corr, x_c, np.float32(-1))
+        return torch.from_numpy(corr)
 
     def mond_rhs(self, phig, out, nxl, n, g0, fn, alpha):
         import ctypes as C

@@ -28,8 +28,9 @@ def _setup(N, solver="fft", **overrides):
     tables = cases.toy_tables()
     pos = cases.lattice_particles(N, 0.4, seed=11)
     vel = cases.velocities(N ** 3, seed=12, scale=0.3)  # large enough that particles cross slab boundaries
+    aexp = overrides.pop("aexp", 0.2) if overrides else 0.2
     param = cases.base_param(int(np.log2(N)), N ** 3, linear_newton_solver=solver, **overrides)
-    param["aexp"] = 0.2
+    param["aexp"] = param["aexp_old"] = aexp
     param["t"] = float(tables[1](np.log(param["aexp"])))
     host.set_units(param)
     return tables, pos, vel, param
@@ -77,8 +78,13 @@ def _run_rank(N, comm, out, reorder_at=None, solver="fft", **overrides):
     counts = [0] * P
     counts[0] = phi_planes.shape[0]
     phi = comm.all_to_all_v(phi_planes.reshape(phi_planes.shape[0], -1), counts, comm.exchange_counts(counts))
+    add = None
+    if s.additional_field is not None:      # MOND: the Newtonian potential, f(R): the scalaron
+        ap = s.additional_field.clone()
+        add = comm.all_to_all_v(ap.reshape(ap.shape[0], -1), counts, comm.exchange_counts(counts))
     if r == 0:
         out["state"] = [t.numpy() for t in res] + [phi.numpy().reshape(N, N, N)]
+        out["additional_field"] = None if add is None else add.numpy().reshape(N, N, N)
         out["t"] = float(param["t"])
         out["moved"] = float(tot[0])
 
@@ -98,6 +104,8 @@ def _check(out, ref, ref_t, P):
     assert rel(vel, rvel) < 5e-5
     assert rel(acc, racc) < 2e-4
     assert rel(phi, rphi) < 2e-4
+    if out.get("additional_field") is not None:
+        assert len(ref[4]) and rel(out["additional_field"], np.asarray(ref[4]).reshape(phi.shape)) < 2e-4
 
 
 @pytest.mark.parametrize("P,solver,N", [(1, "fft", 32), (2, "fft", 32), (4, "fft", 32), (1, "multigrid", 32),
@@ -161,9 +169,37 @@ def test_slab_mond_threads_vs_oracle(P, solver, overrides):
     second solve, with the two warm starts and the two tolerances of the multigrid variant): three steps against the
     oracle's single-process step."""
     N = 32
-    ref, ref_t = _reference(N, solver, **overrides)
-    out = _run_threads(P, N, solver, overrides)
+    ref, ref_t = _reference(N, solver, **dict(overrides))
+    out = _run_threads(P, N, solver, dict(overrides))
     _check(out, ref, ref_t, P)
+
+
+# f(R) in the screened (early) regime, where the reference's cubic root stays on its defined branches (DESIGN 2)
+FR_CASES = [(1, "multigrid", dict(theory="fr", fR_n=1, aexp=0.05)),
+            (2, "fft", dict(theory="fr", fR_n=1, aexp=0.05)),
+            (4, "multigrid", dict(theory="fr", fR_n=1, aexp=0.05)),
+            (2, "fft", dict(theory="fr", fR_n=2, fR_logfR0=6, aexp=0.05)),
+            (4, "fft_7pt", dict(theory="fr", fR_n=2, fR_logfR0=6, aexp=0.05, mass_scheme="CIC"))]
+
+
+@pytest.mark.parametrize("P,solver,overrides", FR_CASES)
+def test_slab_fr_threads_vs_oracle(P, solver, overrides):
+    """theory = fr on slabs: scalaron by the FAS cycle on ghosted slabs (nonlinear red-black sweeps, coarse problem
+    4 R(res) + L(R x), gathered 4^3 level at P = 4), warm start from the previous scalaron, then the Newtonian solve and
+    the fifth force through the gradient of phi + f u^(n+1) -- three steps against the oracle's single-process step."""
+    N = 32
+    ref, ref_t = _reference(N, solver, **dict(overrides))
+    out = _run_threads(P, N, solver, dict(overrides))
+    _check(out, ref, ref_t, P)
+
+
+def test_slab_fr_8_ranks_gathered_fas_levels():
+    """8 ranks at 64^3: the 8^3 FAS level is gathered (x_c, b_c and the residual) and the rest of the FAS V-cycle runs
+    redundantly on every rank."""
+    over = dict(theory="fr", fR_n=1, aexp=0.05)
+    ref, ref_t = _reference(64, "fft", **dict(over))
+    out = _run_threads(8, 64, "fft", dict(over))
+    _check(out, ref, ref_t, 8)
 
 
 def _free_port():

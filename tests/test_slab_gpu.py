@@ -47,7 +47,12 @@ def _run_rank_cuda(N, comm, out, order, reorder_at=None, solver="fft", **overrid
     counts = [0] * P
     counts[0] = phi_planes.shape[0]
     phi = comm.all_to_all_v(phi_planes.reshape(phi_planes.shape[0], -1), counts, comm.exchange_counts(counts))
+    add = None
+    if s.additional_field is not None:      # MOND: the Newtonian potential, f(R): the scalaron
+        ap = s.additional_field.clone()
+        add = comm.all_to_all_v(ap.reshape(ap.shape[0], -1), counts, comm.exchange_counts(counts))
     if r == 0:
+        out["additional_field"] = None if add is None else add.cpu().numpy().reshape(N, N, N)
         out["state"] = [t.numpy() for t in res] + [phi.cpu().numpy().reshape(N, N, N)]
         out["t"] = float(param["t"])
         out["moved"] = float(tot[0])

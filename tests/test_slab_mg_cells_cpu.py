@@ -102,3 +102,43 @@ def test_mond_rhs_in_guard_bands(fields, fn, alpha):
     scale = np.sqrt(np.mean(want.astype(np.float64) ** 2))
     assert np.abs(out.numpy() - want).max() < 2e-5 * scale
     assert bands_intact(pbuf, pg.numel()) and bands_intact(obuf, out.numel())
+
+
+@pytest.mark.parametrize("kind,mod", [(1, "cubic"), (2, "quartic")])
+def test_scalaron_cells_in_guard_bands(fields, kind, mod):
+    """cubic / quartic operator, first guess and one red-black sweep (with and without the FAS right-hand side)"""
+    x, b = fields
+    m = getattr(oracle, mod)
+    q = np.float32(-0.8)
+    u = (1.0 + 0.2 * x).astype(np.float32)           # positive scalaron, O(1)
+    dens = (0.5 * b).astype(np.float32)
+    rhs = (1e-4 * b[::-1]).astype(np.float32).copy()
+    ops = OracleOps(N, 1, 0)
+    ug, ubuf = guarded(ghosted(u))
+    dg, dbuf = guarded(dens)
+    rg, rbuf = guarded(rhs)
+    L = ops.mg_operator_fr(ug, dg, q, N, N, kind)
+    want = m.operator(u, dens, q)
+    assert np.abs(L.numpy() - want).max() < 2e-5 * np.sqrt(np.mean(want.astype(np.float64) ** 2))
+    first, fbuf = guarded(np.zeros_like(u))
+    pos_dens = (np.abs(dens) + 0.1).astype(np.float32)   # the first guess is defined for the physical sign only
+    pg, pbuf = guarded(pos_dens)
+    ops.mg_init_fr(pg, q, N, N, kind, first)
+    want = m.initialise_potential(pos_dens, q)
+    assert np.isfinite(want).all() and np.allclose(first.numpy(), want, rtol=2e-6, atol=0)
+    for with_rhs in (False, True):
+        ug, ubuf = guarded(ghosted(u))
+        for colour in (1, 0):
+            ug[0].copy_(ug[N])
+            ug[N + 1].copy_(ug[1])
+            ops.mg_gs_colour_fr(ug, dg, rg if with_rhs else None, q, N, N, 0, colour, np.float32(1.25), kind)
+        want = u.copy()
+        if with_rhs:
+            m.gauss_seidel_with_rhs(want, dens, q, rhs, np.float32(1.25))
+        else:
+            m.gauss_seidel(want, dens, q, np.float32(1.25))
+        assert np.isfinite(want).all()
+        assert np.abs(ug[1:N + 1].numpy() - want).max() < 5e-6 * np.abs(want).max()
+        assert bands_intact(ubuf, ug.numel())
+    for buf, size in ((dbuf, dg.numel()), (rbuf, rg.numel()), (fbuf, first.numel()), (pbuf, pg.numel())):
+        assert bands_intact(buf, size)

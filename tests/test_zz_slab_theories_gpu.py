@@ -1,5 +1,6 @@
-"""GPU parity of theory = mond on x-slabs (QUMOND: psc_box_mond_rhs between two slab solves) against the oracle's
-single-process step, on P = 1, 2, 4 virtual ranks sharing cuda:0.
+"""GPU parity of theory = mond (QUMOND: psc_box_mond_rhs between two slab solves) and theory = fr (scalaron by the FAS
+cycle on ghosted slabs, psc_box_*_fr; fifth force through the slab interpolation kernel) on x-slabs against the
+oracle's single-process step, on P = 1, 2, 4 virtual ranks sharing cuda:0.
 
 The host sequencing and the per-cell kernel code are covered on the CPU tier (tests/test_slab_cpu.py,
 tests/test_slab_mg_cells_cpu.py); the GPU budget of round 1 ran out before this file could be run on a B200, hence the
@@ -22,9 +23,21 @@ pytestmark = [pytest.mark.gpu,
               pytest.mark.xfail(strict=False, reason="first run on a B200 happens after round 1 (GPU budget exhausted)")]
 
 
+def _case(P, solver, overrides, N=32):
+    ref, ref_t = cpu._reference(N, solver, **dict(overrides))
+    out = gpu._threads(P, lambda c, o: gpu._run_rank_cuda(N, c, o, 5, reorder_at=1, solver=solver, **dict(overrides)))
+    cpu._check(out, ref, ref_t, P)
+
+
 @pytest.mark.parametrize("P,solver,overrides", cpu.MOND_CASES)
 def test_slab_cuda_mond_vs_oracle(P, solver, overrides):
-    N = 32
-    ref, ref_t = cpu._reference(N, solver, **overrides)
-    out = gpu._threads(P, lambda c, o: gpu._run_rank_cuda(N, c, o, 5, reorder_at=1, solver=solver, **overrides))
-    cpu._check(out, ref, ref_t, P)
+    _case(P, solver, overrides)
+
+
+@pytest.mark.parametrize("P,solver,overrides", cpu.FR_CASES)
+def test_slab_cuda_fr_vs_oracle(P, solver, overrides):
+    _case(P, solver, overrides)
+
+
+def test_slab_cuda_fr_8_ranks_gathered_fas_levels():
+    _case(8, "fft", dict(theory="fr", fR_n=1, aexp=0.05), N=64)
