@@ -1231,8 +1231,8 @@ def run(param, comm=None, initial_state=None, ops_factory=None):
     ThreadComm).  Every rank derives the same background tables; the initial particles come from `initial_state`
     (global arrays, identical on every rank) or are generated identically on every rank (initial_conditions.generate:
     meshes that fit one GPU) -- each rank adopts a strided share and the first migration routes the particles to their
-    slabs.  Snapshots are gathered to rank 0 in the reference's particle order.  Newtonian / parametrized gravity,
-    FFT solvers, leapfrog (what Slab.pm supports).  Returns (position, velocity) of the final state on rank 0
+    slabs.  Snapshots are gathered to rank 0 in the reference's particle order.  Theories and solvers: what Slab.pm
+    supports (newton / parametrized / mond / fr; fft, fft_7pt, multigrid), leapfrog.  Returns (position, velocity) of the final state on rank 0
     (CPU tensors, reference order), None elsewhere.  ops_factory(N, P, rank) replaces the CUDA kernels (tests only)."""
     import pandas as pd
     from . import cosmotable, iostream, utils
@@ -1246,7 +1246,17 @@ def run(param, comm=None, initial_state=None, ops_factory=None):
         raise ValueError(f"{param['verbose']=}, should be 0, 1 or 2")
     root = comm.rank == 0
     param["write_snapshot"] = False
-    param["extra"] = f"{param['theory'].casefold()}_{param['linear_newton_solver']}_ncoarse{param['ncoarse']}"
+    extra = param["theory"].casefold()       # the reference's file-name tag (main.py:82-93)
+    if extra == "fr":
+        extra += f"{param['fR_logfR0']}_n{param['fR_n']}"
+    elif extra == "mond":
+        mond_function = param["mond_function"].casefold()
+        extra += f"_g0_{param['mond_g0']}_exponent_{param['mond_scale_factor_exponent']}_{mond_function}"
+        if "simple" != mond_function:
+            extra += f"_{param['mond_alpha']}"
+    elif extra == "parametrized":
+        extra += f"_mu0_{param['parametrized_mu0']}"
+    param["extra"] = f"{extra}_{param['linear_newton_solver']}_ncoarse{param['ncoarse']}"
     z_out = iostream.parse_z_out(param)
     if root:
         os.makedirs(f"{param['base']}/power", exist_ok=True)
@@ -1277,7 +1287,7 @@ def run(param, comm=None, initial_state=None, ops_factory=None):
     mine = slice(comm.rank, None, comm.size)
     S.set_particles(position[mine].contiguous(), velocity[mine].contiguous(), ids[mine].contiguous())
     del position, velocity, ids
-    S.pm(param)
+    S.pm(param, tables=tables)
     aexp_out = np.sort(1.0 / (np.array(z_out) + 1))
     t_out = tables[1](np.log(aexp_out))
     param["i_snap"] = 1 if "i_snap" not in param.index else param["i_snap"] + 1
