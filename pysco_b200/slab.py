@@ -1023,6 +1023,9 @@ class Slab:
             logging.info("Rescale potential from previous step for Newtonian potential")
             own.copy_(previous)
             if not param["compute_additional_field"]:
+                if tables is None:
+                    raise ValueError("Slab.pm(param, tables=...) is needed from the second multigrid solve on: the "
+                                     "previous potential is rescaled with the growth table (solver.py:274-281)")
                 scaling = (param["aexp"] * tables[3](np.log(param["aexp"]))
                            / (param["aexp_old"] * tables[3](np.log(param["aexp_old"]))))
                 self.ops.affine(own, np.float32(scaling), 0.0)
