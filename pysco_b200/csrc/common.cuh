@@ -11,8 +11,12 @@ namespace psc {
 void set_error(const char *fmt, ...);
 void count_launch(int n = 1);
 
-// B200: 148 SMs.  Streaming kernels are launched as grid-stride loops over a multiple of the SM count.
-constexpr int kNumSMs = 148;
+// Streaming kernels are launched as grid-stride loops over a multiple of the SM count of the current device
+// (num_sms(): cudaDevAttrMultiProcessorCount, cached; 148 on a B200).
+constexpr int kNumSMsB200 = 148;
+int num_sms();
+int deposit_mode();   // PSC_DEPOSIT_MODE / psc_set_kernel_modes: kernel variants for A/B measurements
+int interp_mode();    // PSC_INTERP_MODE
 
 #define PSC_CHECK_ARG(cond, msg)                                  \
   do {                                                            \
@@ -45,7 +49,7 @@ static inline cudaStream_t as_stream(void *s) { return reinterpret_cast<cudaStre
 // grid size for a grid-stride loop over n items with `block` threads, capped at `waves` CTAs per SM
 static inline int grid_for(int64_t n, int block, int ctas_per_sm = 8) {
   int64_t need = (n + block - 1) / block;
-  int64_t cap = (int64_t)kNumSMs * ctas_per_sm;
+  int64_t cap = (int64_t)num_sms() * ctas_per_sm;
   if (need < 1) need = 1;
   return (int)(need < cap ? need : cap);
 }
@@ -96,6 +100,25 @@ __device__ __forceinline__ void cic_axis(float xp, int N, int &c, int &c2, float
   w2 = fabsf(d);
   w = 1.0f - w2;
   c2 = wrap(c + s, N);
+}
+
+// the three 1-D weights of one axis for cells c - 1, c, c + 1 (CIC as a 3-point stencil with one zero weight,
+// mesh.py:2318-2345: the second cell is c + sign(d); NGP: the cell itself)
+template <int SCHEME>
+__device__ __forceinline__ void axis_weights(float xp, int N, int &c, float &wm, float &w0, float &wp) {
+  if (SCHEME == PSC_TSC) {
+    tsc_axis(xp, c, wm, w0, wp);
+  } else if (SCHEME == PSC_CIC) {
+    c = (int)xp;
+    float d = xp - 0.5f - (float)c;
+    float ad = fabsf(d);
+    w0 = 1.0f - ad;
+    wm = d < 0.0f ? ad : 0.0f;
+    wp = d > 0.0f ? ad : 0.0f;
+  } else {
+    c = (int)xp;
+    wm = 0.0f; w0 = 1.0f; wp = 0.0f;
+  }
 }
 
 }  // namespace psc

@@ -1,8 +1,9 @@
 // deposit.cu -- mass assignment (mesh.NGP / CIC / TSC, mesh.py:2240-2595) fused with solver.pm's
 // density rescale and rhs_poisson's affine map (solver.py:114-116, 444-449).
 //
-// Path A (any particle order): one thread per particle, RED.ADD.F32 to the global grid.
-// Path B (spatially sorted particles, see deposit_tiled.cu): per-CTA shared-memory tile accumulation.
+// One thread per particle, RED.ADD.F32 to the global grid: correct for any N and any particle order.  This is the
+// path of meshes the cell-sorted kernels of binned.cu do not take (N < 8 or N % 8 != 0; mesh.can_bin) -- every
+// BASELINE configuration goes through psc_deposit_binned.
 #include "common.cuh"
 
 namespace psc {
@@ -77,10 +78,6 @@ __global__ void __launch_bounds__(256) rho_affine_kernel(float *__restrict__ rho
   }
 }
 
-// implemented in deposit_tiled.cu; returns 1 if it handled the deposit, 0 to fall back, <0 on error
-int deposit_tiled(const float *pos, int64_t np, int N, int scheme, float scale, float f1, float f2,
-                  float *rho, cudaStream_t st);
-
 }  // namespace psc
 
 using namespace psc;
@@ -93,10 +90,6 @@ extern "C" int psc_deposit(const float *pos, int64_t np, int N, int scheme, floa
   PSC_CHECK_ARG(rho && (pos || np == 0), "null pointer");
   cudaStream_t st = as_stream(stream);
   const int64_t n3 = (int64_t)N * N * N;
-
-  int handled = deposit_tiled(pos, np, N, scheme, scale, f1, f2, rho, st);
-  if (handled < 0) return handled;
-  if (handled) return PSC_OK;
 
   PSC_CUDA(cudaMemsetAsync(rho, 0, sizeof(float) * n3, st));
   if (np > 0) {

@@ -278,7 +278,7 @@ int psc_green_slab(float *spec_t, int N, int nyl, int y0, int kind, int p, float
   PSC_CHECK_ARG(kind >= PSC_GREEN_PLAIN && kind <= PSC_GREEN_7PT, "unknown Green's function");
   PSC_CHECK_ARG(p >= 0 && p <= 8, "MAS index out of range");
   int64_t nrows = (int64_t)N * nyl;
-  int g = (int)((nrows + 3) / 4 < (int64_t)kNumSMs * 8 ? (nrows + 3) / 4 : (int64_t)kNumSMs * 8);
+  int g = (int)((nrows + 3) / 4 < (int64_t)num_sms() * 8 ? (nrows + 3) / 4 : (int64_t)num_sms() * 8);
   float2 *s = reinterpret_cast<float2 *>(spec_t);
   cudaStream_t st = as_stream(stream);
   const size_t smem = sizeof(float2) * N;

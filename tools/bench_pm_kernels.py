@@ -1,10 +1,12 @@
 #!/usr/bin/env python
-"""Timing of the binned particle<->mesh kernels alone (bin, deposit, gradient+interpolation+kick) on one GPU, for a
-freshly Morton-sorted order and for an order that has drifted by one cell rms.
+"""Timing of the cell-sorted particle<->mesh kernels alone (sort, deposit, gradient+interpolation+kick) on one GPU,
+for a freshly Morton-sorted order, an order that has drifted by one cell rms, and a clustered set; both deposit paths
+(lanes own cells / lanes own particles) and both gradient stages (row-wise / cell-wise) through psc_set_kernel_modes.
 usage: python tools/bench_pm_kernels.py [ncoarse=9]"""
 import os
 import sys
 
+import numpy as np
 import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -14,7 +16,7 @@ from pysco_b200 import _lib, mesh, utils  # noqa: E402
 
 nc = int(sys.argv[1]) if len(sys.argv) > 1 else 9
 N = 2 ** nc
-_lib.load()
+lib = _lib.load()
 
 
 def timeit(fn, reps=5):
@@ -33,11 +35,17 @@ def timeit(fn, reps=5):
 
 pos, vel, _ = bench.slab_ics(N, 0, N)
 pos_mor, vel = utils.reorder_particles(pos, vel)
+del pos
 g = torch.Generator(device="cuda").manual_seed(1)
 p = pos_mor + torch.randn(pos_mor.shape, generator=g, device="cuda") * (1.0 / N)
 p = p - torch.floor(p)
 p[p >= 1.0] = 0.0
 cases = {"morton": pos_mor, "morton+drift1.0": p.contiguous()}
+# Poisson: uniform random positions, Morton-ordered (an evolved but unclustered field)
+pr = torch.rand(pos_mor.shape, generator=g, device="cuda")
+pr[pr >= 1.0] = 0.0
+cases["poisson (Morton)"] = utils.reorder_particles(pr.contiguous())
+del pr
 # clustered: half of the particles in 4096 Gaussian blobs of sigma = 0.7 cell (bins with ~10^4 particles)
 n = pos_mor.shape[0]
 centres = torch.rand((4096, 3), generator=g, device="cuda")
@@ -48,11 +56,32 @@ pc[pc >= 1.0] = 0.0
 cases["clustered (Morton)"] = utils.reorder_particles(pc.contiguous())
 del pc, which
 phi = torch.randn((N, N, N), device="cuda")
+acc = torch.randn(pos_mor.shape, device="cuda") * 1e-3
 for name, p in cases.items():
     t_bin = timeit(lambda: mesh.bin_particles(p, N))
     bn = mesh.bin_particles(p, N)
-    t_dep = timeit(lambda: mesh.deposit_rhs(p, N, 2, 1.0, 1.0, 0.0, bn))
-    v2 = vel.clone()
-    t_int = timeit(lambda: mesh.interp_kick_phi(phi, None, 0.0, 0, 5, p, v2, 2, 0.0, bn))
-    print(f"N={N} {name:18s} bin {t_bin:6.3f} ms | deposit {t_dep:6.3f} ms | gradient+interp+kick {t_int:6.3f} ms",
-          flush=True)
+    out = [f"N={N} {name:18s} sort {t_bin:6.3f} ms"]
+    for dm in (0, 1):
+        lib.psc_set_kernel_modes(dm, -1)
+        t_dep = timeit(lambda: mesh.deposit_rhs(p, N, 2, 1.0, 1.0, 0.0, bn))
+        out.append(f"deposit[{'cells' if dm == 0 else 'particles'}] {t_dep:6.3f} ms")
+    lib.psc_set_kernel_modes(0, -1)
+    for im in (0, 1):
+        lib.psc_set_kernel_modes(-1, im)
+        v2 = vel.clone()
+        t_int = timeit(lambda: mesh.interp_kick_phi(phi, None, 0.0, 0, 5, p, v2, 2, 0.0, bn))
+        out.append(f"grad+interp+kick[{'rows' if im == 0 else 'cellwise'}] {t_int:6.3f} ms")
+    lib.psc_set_kernel_modes(-1, 0)
+    print(" | ".join(out), flush=True)
+# kick + drift + wrap + per-cell count, then scan + scatter (the two halves of the sort inside a step)
+p = pos_mor.clone()
+v = vel.clone()
+bn = mesh.alloc_binned(n, N)
+t_kdw = timeit(lambda: mesh.kick_drift_wrap_count(p, v, acc, np.float32(1e-3), np.float32(1e-2), 0, bn))
+mesh.kick_drift_wrap_count(p, v, acc, np.float32(1e-3), np.float32(1e-2), 0, bn)
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+mesh.finish_binning(p, bn)
+e1.record()
+torch.cuda.synchronize()
+print(f"N={N} kick+drift+wrap+count {t_kdw:6.3f} ms | scan+scatter {e0.elapsed_time(e1):6.3f} ms", flush=True)
