@@ -225,3 +225,18 @@ IC_CASES = {
     "lpt2_fixed_paired": dict(initial_conditions="2LPT", fixed_ICS=True, paired_ICS=True, seed=3),
     "lpt3_dealiased": dict(initial_conditions="3LPT", dealiased_ICS=True, seed=11),
 }
+
+
+# background tables (cosmotable.generate): LCDM of examples/param.ini, a w0-wa model, the parametrized theory
+COSMO_CASES = {
+    "lcdm": dict(),
+    "w0wa": dict(w0=-0.9, wa=0.1, Om_m=0.3),
+    "parametrized": dict(theory="parametrized", parametrized_mu0=0.1),
+}
+
+
+def cosmo_param(**over):
+    p = {"theory": "newton", "H0": 72.0, "Om_m": 0.25733, "T_cmb": 2.726, "N_eff": 3.044, "w0": -1.0, "wa": 0.0,
+         "parametrized_mu0": 0.0, "evolution_table": "no", "base": "", "extra": "test"}
+    p.update(over)
+    return p

@@ -359,6 +359,62 @@ def g_ics():
 
 GROUPS["ics"] = g_ics
 
+def g_euler():
+    """Three Euler steps through integration.integrate (integration.py:121-189), the last one clamped to a snapshot
+    time; FFT solver at 16^3."""
+    out = {}
+    N = 16
+    tables = cases.toy_tables()
+    pos = cases.lattice_particles(N, 0.3, seed=62)
+    vel = cases.velocities(N ** 3, seed=63, scale=2e-3)
+    param = cases.base_param(4, N ** 3, linear_newton_solver="fft", integrator="euler")
+    param["aexp"] = 0.2
+    param["t"] = float(tables[1](np.log(param["aexp"])))
+    utils.set_units(param)
+    acc, pot, add = solver.pm(pos, param)
+    t_snap = param["t"] + 1e9
+    dts = []
+    for step in range(3):
+        param["nsteps"] += 1
+        if step == 2:
+            t_snap = param["t"] + 0.4 * float(dts[-1])
+        t0 = param["t"]
+        pos, vel, acc, pot, add = integration.integrate(pos, vel, acc, pot, add, tables, param, t_snap)
+        dts.append(param["t"] - t0)
+    out["pos"], out["vel"], out["acc"], out["pot"] = pos, vel, acc, pot
+    out["dts"] = np.array(dts, dtype=np.float64)
+    out["write_snapshot"] = np.array([param["write_snapshot"]])
+    save("euler", **out)
+
+
+GROUPS["euler"] = g_euler
+
+
+def g_cosmotable():
+    """The reference's cosmotable.generate (cosmotable.py:18-110: supercomoving time, growth ODEs of 1-3LPT) evaluated
+    at 24 scale factors for LCDM (examples/param.ini), w0-wa and the parametrized theory.  astropy is absent from this
+    container: the Flatw0waCDM class the reference instantiates is the repo's restatement (tests/golden/_stubs), so
+    these vectors pin everything cosmotable.py computes ON TOP of E(a) -- not astropy's E(a) itself."""
+    import pandas as pd
+    import cosmotable
+    out = {}
+    a = np.geomspace(1.0 / 150, 1.0, 24)
+    out["aexp"] = a
+    for name, over in cases.COSMO_CASES.items():
+        param = pd.Series(cases.cosmo_param(**over))
+        param["base"] = "/tmp/pysco_golden_cosmo"
+        os.makedirs(param["base"], exist_ok=True)
+        tables = cosmotable.generate(param)
+        lna = np.log(a)
+        t = tables[1](lna)
+        out[f"{name}_tables"] = np.array([tables[0](t)] + [tb(lna) for tb in tables[1:]], dtype=np.float64)
+        out[f"{name}_Om_r_Om_lambda"] = np.array([param["Om_r"], param["Om_lambda"]], dtype=np.float64)
+    save("cosmotable", **out)
+
+
+GROUPS["cosmotable"] = g_cosmotable
+
+
 if __name__ == "__main__":
     todo = sys.argv[1:] or list(GROUPS)
     for g in todo:

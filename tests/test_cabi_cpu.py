@@ -103,3 +103,28 @@ def test_cosmotable_tables():
     assert 1.5 < d1 < 2.0                                        # LCDM growth between a = 0.5 and 1
     assert 0.4 < float(tabs[4](0.0)) < 0.6                       # f = dlnD/dlna ~ Om^0.55 ~ 0.47
     assert abs(param["Om_lambda"] + param["Om_m"] + param["Om_r"] - 1) < 1e-12
+
+
+def test_cosmotable_vs_reference_golden():
+    """pysco_b200.cosmotable.generate against the reference's cosmotable.generate (cosmotable.py:18-110) at 24 scale
+    factors: a(t), t(a), H(a), D1, f1, D2, f2, D3a .. f3c for LCDM, w0-wa and the parametrized theory
+    (tests/golden/cosmotable.npz, make_golden.py cosmotable).  Provenance: astropy is not installed where the vectors
+    were made, so the reference ran with the repo's Flatw0waCDM restatement as its astropy.cosmology class -- the
+    vectors pin the time integration and the growth ODEs, NOT astropy's E(a) (parity unpinned for that class)."""
+    import os
+    import sys
+    import pandas as pd
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    import cases
+    from pysco_b200 import cosmotable
+    g = np.load(os.path.join(ROOT, "tests", "golden", "cosmotable.npz"))
+    lna = np.log(g["aexp"])
+    for name, over in cases.COSMO_CASES.items():
+        param = pd.Series(cases.cosmo_param(**over))
+        tabs = cosmotable.generate(param)
+        ref = g[f"{name}_tables"]
+        t = tabs[1](lna)
+        mine = np.array([tabs[0](t)] + [tb(lna) for tb in tabs[1:]], dtype=np.float64)
+        assert mine.shape == ref.shape == (13, len(lna))
+        np.testing.assert_allclose(mine, ref, rtol=1e-9, atol=1e-12)
+        np.testing.assert_allclose([param["Om_r"], param["Om_lambda"]], g[f"{name}_Om_r_Om_lambda"], rtol=1e-12)

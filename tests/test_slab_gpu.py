@@ -176,9 +176,7 @@ def test_pinned_host_pipeline_matches_device_path(solver_name):
         assert err < 1e-5, (name, err)
 
 
-@pytest.mark.parametrize("solver", ["fft", pytest.param("multigrid", marks=pytest.mark.xfail(
-    strict=False, reason="added after the last B200 run of round 1 (the CPU twin in test_slab_cpu.py is green; the "
-                         "three-step multigrid cases above ran on the B200): remove the marker after its first XPASS"))])
+@pytest.mark.parametrize("solver", ["fft", "multigrid"])
 def test_slab_whole_run_matches_reference_snapshot(tmp_path, solver):
     """BASELINE config 1 shape at 32^3, z = 49 -> 0, through slab.run on 2 virtual ranks: the final state, put back
     in the reference's particle order, against the unmodified reference's final snapshot (tests/golden/run.npz).

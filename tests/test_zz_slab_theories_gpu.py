@@ -3,9 +3,7 @@ cycle on ghosted slabs, psc_box_*_fr; fifth force through the slab interpolation
 oracle's single-process step, on P = 1, 2, 4 virtual ranks sharing cuda:0.
 
 The host sequencing and the per-cell kernel code are covered on the CPU tier (tests/test_slab_cpu.py,
-tests/test_slab_mg_cells_cpu.py); the GPU budget of round 1 ran out before this file could be run on a B200, hence the
-non-strict xfail marker (an XPASS in the log is the first GPU confirmation; remove the marker then).  The file sorts
-last so that it cannot disturb the validated suites."""
+tests/test_slab_mg_cells_cpu.py); first B200 run: the driver's round-1 GPU tier (GPUTEST_r01.json, all cases passed)."""
 import os
 import sys
 
@@ -19,8 +17,7 @@ for p in (ROOT, os.path.join(ROOT, "tests"), os.path.join(ROOT, "tests", "golden
 import test_slab_cpu as cpu  # noqa: E402
 import test_slab_gpu as gpu  # noqa: E402
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.xfail(strict=False, reason="first run on a B200 happens after round 1 (GPU budget exhausted)")]
+pytestmark = pytest.mark.gpu
 
 
 def _case(P, solver, overrides, N=32):
