@@ -328,6 +328,44 @@ def g_run():
 
 GROUPS["run"] = g_run
 
+def g_run64():
+    """Whole run at 64^3 (FFT solver, z = 49 -> 0): the reference's ICs, the final P(k) file, and every 16th particle of
+    the final snapshot (the full snapshot would be another 6 MB)."""
+    import shutil
+    import pandas as pd
+    sys.path.insert(0, REF)
+    import pysco
+    import initial_conditions, cosmotable  # noqa: E401
+    import pyarrow.parquet as pq
+    out = {}
+    base = "/tmp/pysco_golden_run64/"
+    shutil.rmtree(base, ignore_errors=True)
+    param = cases.run_param(base, "fft", ncoarse=6)
+    p0 = pd.Series(dict(param))
+    p0["write_snapshot"] = False
+    p0["extra"] = "ics"
+    os.makedirs(base + "/output_00000", exist_ok=True)
+    p0["i_snap"] = 0
+    tables = cosmotable.generate(p0)
+    p0["aexp"] = 1.0 / (1 + p0["z_start"])
+    utils.set_units(p0)
+    p0["nsteps"] = 0
+    pos0, vel0 = initial_conditions.generate(p0, tables)
+    out["ic_pos"], out["ic_vel"] = pos0.copy(), vel0.copy()
+    pysco.run(dict(param))
+    snap = f"{base}/output_00006/particles_newton_fft_ncoarse6.parquet"
+    t = pq.read_table(snap)
+    out["fft_pos_16th"] = np.stack([np.asarray(t[c]) for c in ("x", "y", "z")], axis=1).astype(np.float32)[::16]
+    out["fft_vel_16th"] = np.stack([np.asarray(t[c]) for c in ("vx", "vy", "vz")], axis=1).astype(np.float32)[::16]
+    pks = sorted(f for f in os.listdir(f"{base}/power") if f.endswith(".dat"))
+    out["fft_pk_last"] = np.loadtxt(f"{base}/power/{pks[-1]}")
+    out["fft_nsteps"] = np.array([int(pks[-1].split("_")[-1].split(".")[0])])
+    save("run64", **out)
+
+
+GROUPS["run64"] = g_run64
+
+
 def g_ics():
     """Initial conditions of the reference (initial_conditions.generate, nthreads = 1) at 16^3 for every LPT
     order / option, plus the table look-ups it used so that the build can be fed exactly the same growth factors."""
