@@ -47,10 +47,6 @@ const char *psc_last_error(void);
 int psc_version(void);
 /* number of kernel launches issued by this library since load (bench.py's gpu_launches claim) */
 int64_t psc_launch_count(void);
-/* measurement only (tools/bench_pm_kernels.py): run-time choice between kernel variants of the particle <-> mesh
- * kernels, same results; an argument < 0 keeps the current value; the environment variables PSC_DEPOSIT_MODE /
- * PSC_INTERP_MODE give the initial values (0 = the default path). */
-int psc_set_kernel_modes(int deposit, int interp);
 
 /* ---------------------------------------------------------------- particles ---------------- */
 /* morton.positions_to_keys (morton.py:42-137): 21 bits per axis, key = X<<2 | Y<<1 | Z */

@@ -20,7 +20,6 @@ SIGNATURES = {
     "psc_last_error": [],
     "psc_version": [],
     "psc_launch_count": [],
-    "psc_set_kernel_modes": [_i, _i],
     "psc_morton_keys": [_vp, _i64, _vp, _vp],
     "psc_argsort_workspace_bytes": [_i64],
     "psc_argsort_keys": [_vp, _i64, _vp, _vp, _sz, _vp],

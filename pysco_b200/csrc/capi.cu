@@ -34,33 +34,10 @@ int num_sms() {
   return n;
 }
 
-// Kernel-variant switches for A/B measurements (tools/bench_pm_kernels.py); 0 = the default path.
-static int env_mode(const char *name) {
-  const char *v = getenv(name);
-  return v ? atoi(v) : 0;
-}
-static std::atomic<int> g_deposit_mode{-1}, g_interp_mode{-1};
-int deposit_mode() {
-  int m = g_deposit_mode.load(std::memory_order_relaxed);
-  if (m < 0) { m = env_mode("PSC_DEPOSIT_MODE"); g_deposit_mode.store(m, std::memory_order_relaxed); }
-  return m;
-}
-int interp_mode() {
-  int m = g_interp_mode.load(std::memory_order_relaxed);
-  if (m < 0) { m = env_mode("PSC_INTERP_MODE"); g_interp_mode.store(m, std::memory_order_relaxed); }
-  return m;
-}
-
 }  // namespace psc
 
 extern "C" {
 const char *psc_last_error(void) { return psc::g_err; }
 int psc_version(void) { return 100; }
 int64_t psc_launch_count(void) { return (int64_t)psc::g_launches.load(std::memory_order_relaxed); }
-/* measurement only: select a kernel variant at run time (what < 0 keeps the current value); returns 0 */
-int psc_set_kernel_modes(int deposit, int interp) {
-  if (deposit >= 0) psc::g_deposit_mode.store(deposit, std::memory_order_relaxed);
-  if (interp >= 0) psc::g_interp_mode.store(interp, std::memory_order_relaxed);
-  return 0;
-}
 }

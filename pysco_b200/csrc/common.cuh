@@ -15,8 +15,6 @@ void count_launch(int n = 1);
 // (num_sms(): cudaDevAttrMultiProcessorCount, cached; 148 on a B200).
 constexpr int kNumSMsB200 = 148;
 int num_sms();
-int deposit_mode();   // PSC_DEPOSIT_MODE / psc_set_kernel_modes: kernel variants for A/B measurements
-int interp_mode();    // PSC_INTERP_MODE
 
 #define PSC_CHECK_ARG(cond, msg)                                  \
   do {                                                            \

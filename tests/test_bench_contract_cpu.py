@@ -10,7 +10,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def test_reference_arm_prints_one_json_line():
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
-                          "--warmup", "1", "--cpu-ncoarse", "5"], capture_output=True, text=True, timeout=600)
+                          "--warmup", "1", "--ncoarse", "5", "--cpu-ncoarse", "5"], capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stderr[-2000:]
     lines = [ln for ln in out.stdout.splitlines() if ln.strip()]
     assert len(lines) == 1, lines
@@ -24,7 +24,38 @@ def test_reference_arm_prints_one_json_line():
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     sys.path.insert(0, ROOT)
     import bench
-    assert d["config"] == bench.workload_config(9)      # what the B200 arm reports for the default workload
+    assert d["config"] == bench.workload_config(5)      # the config names the size that actually ran
+    assert d["scaling"] == "strong"
+
+
+def test_reference_arm_names_the_sample_it_ran():
+    """a workload whose K + W steps do not fit the time budget is sampled at --cpu-ncoarse, and the line says so"""
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
+                          "--warmup", "1", "--ncoarse", "6", "--cpu-ncoarse", "5", "--cpu-budget-s", "0"],
+                         capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    d = json.loads(out.stdout.strip().splitlines()[-1])
+    assert d["config"]["ncells_1d"] == 32 and "32^3" in d["config"]["workload"]
+    assert "1/8 of the 64^3 workload" in d["cpu_baseline"]["sample"]
+
+
+def test_ics_are_the_same_in_both_arms():
+    """bench.lattice_ics: the NumPy (CPU arm) and the torch (GPU arms, any x-slab) flavours give the same particles"""
+    import numpy as np
+    import torch
+    sys.path.insert(0, ROOT)
+    import bench
+    N = 16
+    p0, v0, i0 = bench.lattice_ics(np, N, 0, N)
+    p1, v1, i1 = bench.lattice_ics(torch, N, 4, 8, device="cpu")
+    sl = slice(4 * N * N, 12 * N * N)
+    assert np.array_equal(i0[sl], i1.numpy())
+    assert np.abs(p0[sl] - p1.numpy()).max() < 2e-7 and np.abs(v0[sl] - v1.numpy()).max() < 1e-9
+    assert 0.0 <= p0.min() and p0.max() < 1.0
+    assert abs(v0.std() / 1e-3 - 1) < 0.02 and abs(v0.mean()) < 1e-4
+    d = (p0 * N - (np.stack(np.meshgrid(*[np.arange(N) + 0.5] * 3, indexing="ij"), -1).reshape(-1, 3)))
+    d = d - N * np.round(d / N)
+    assert abs(d.std() / 0.3 - 1) < 0.03
 
 
 def test_every_timed_kernel_has_an_algorithmic_byte_entry_or_is_overhead():

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
-"""Timing of the cell-sorted particle<->mesh kernels alone (sort, deposit, gradient+interpolation+kick) on one GPU,
-for a freshly Morton-sorted order, an order that has drifted by one cell rms, and a clustered set; both deposit paths
-(lanes own cells / lanes own particles) and both gradient stages (row-wise / cell-wise) through psc_set_kernel_modes.
+"""Timing of the binned particle<->mesh kernels alone (binning, deposit, gradient+interpolation+kick) on one GPU, for
+a freshly Morton-sorted order, an order that has drifted by one cell rms, a Poisson (uniform random) set and a
+clustered set; plus the two halves of the binning inside a step (count fused into kick+drift+wrap, scan + scatter).
 usage: python tools/bench_pm_kernels.py [ncoarse=9]"""
 import os
 import sys
@@ -16,7 +16,7 @@ from pysco_b200 import _lib, mesh, utils  # noqa: E402
 
 nc = int(sys.argv[1]) if len(sys.argv) > 1 else 9
 N = 2 ** nc
-lib = _lib.load()
+_lib.load()
 
 
 def timeit(fn, reps=5):
@@ -60,18 +60,12 @@ acc = torch.randn(pos_mor.shape, device="cuda") * 1e-3
 for name, p in cases.items():
     t_bin = timeit(lambda: mesh.bin_particles(p, N))
     bn = mesh.bin_particles(p, N)
-    out = [f"N={N} {name:18s} sort {t_bin:6.3f} ms"]
-    for dm in (0, 1):
-        lib.psc_set_kernel_modes(dm, -1)
-        t_dep = timeit(lambda: mesh.deposit_rhs(p, N, 2, 1.0, 1.0, 0.0, bn))
-        out.append(f"deposit[{'cells' if dm == 0 else 'particles'}] {t_dep:6.3f} ms")
-    lib.psc_set_kernel_modes(0, -1)
-    for im in (0, 1):
-        lib.psc_set_kernel_modes(-1, im)
-        v2 = vel.clone()
-        t_int = timeit(lambda: mesh.interp_kick_phi(phi, None, 0.0, 0, 5, p, v2, 2, 0.0, bn))
-        out.append(f"grad+interp+kick[{'rows' if im == 0 else 'cellwise'}] {t_int:6.3f} ms")
-    lib.psc_set_kernel_modes(-1, 0)
+    out = [f"N={N} {name:18s} bin {t_bin:6.3f} ms"]
+    t_dep = timeit(lambda: mesh.deposit_rhs(p, N, 2, 1.0, 1.0, 0.0, bn))
+    out.append(f"deposit {t_dep:6.3f} ms")
+    v2 = vel.clone()
+    t_int = timeit(lambda: mesh.interp_kick_phi(phi, None, 0.0, 0, 5, p, v2, 2, 0.0, bn))
+    out.append(f"grad+interp+kick {t_int:6.3f} ms")
     print(" | ".join(out), flush=True)
 # kick + drift + wrap + per-cell count, then scan + scatter (the two halves of the sort inside a step)
 p = pos_mor.clone()

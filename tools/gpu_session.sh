@@ -13,7 +13,7 @@ timeout 900 python bench.py --steps 50 --warmup 3 > $out/${tag}_bench512.json 2>
 echo "bench rc=$?" >> $out/${tag}_bench512.err
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $out/${tag}_launches.csv \
   python bench.py --steps 2 --warmup 1 --no-e2e --no-cpu-baseline > $out/${tag}_ncu_launch.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:'deposit_cells_kernel|interp_kick_phi_binned_kernel|kick_drift_wrap_count_kernel|bin_scatter_kernel' \
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:'deposit_binned_kernel|interp_kick_phi_binned_kernel|kick_drift_wrap_count_kernel|bin_scatter_kernel' \
   --launch-skip 7 --launch-count 4 -o $out/${tag}_particle_kernels -f python tools/prof_step.py 9 step > $out/${tag}_ncu_full.log 2>&1
 python tools/ncu_summary.py $out/${tag}_particle_kernels.ncu-rep > $out/${tag}_particle_kernels_ncu.txt 2>&1
 ls -la $out | tail -20
