@@ -15,13 +15,19 @@ import torch
 from . import _lib, distributed, mesh, solver, utils
 
 # maxima produced by the fused interpolation kernel, valid for exactly the (acceleration, velocity)
-# tensors returned by the last leapfrog step
+# tensors returned by the last leapfrog step AND only as long as nobody has written to them since (the tensor's
+# version counter is stored with the weak reference: an in-place change by the caller is a cache miss)
 _maxima_cache = {"acc": None, "vel": None, "max": None}
 
 
+def _remember_maxima(acc, vel, mx):
+    _maxima_cache.update(acc=(weakref.ref(acc), acc._version), vel=(weakref.ref(vel), vel._version), max=mx)
+
+
 def _cached_max(x, which):
-    ref = _maxima_cache[which]
-    if ref is not None and isinstance(x, torch.Tensor) and ref() is x and _maxima_cache["max"] is not None:
+    entry = _maxima_cache[which]
+    if entry is not None and isinstance(x, torch.Tensor) and entry[0]() is x and entry[1] == x._version \
+            and _maxima_cache["max"] is not None:
         return np.float32(_maxima_cache["max"][0 if which == "acc" else 1])
     m = utils.max_abs(x)
     if distributed.is_active():  # particle-parallel: the time step is global
@@ -100,6 +106,26 @@ def _streams():
     return _copy_streams[d]
 
 
+_pinned_pool = []
+
+
+def _pinned_empty(shape):
+    """Pinned host staging buffer for a result.  cudaHostAlloc of a 1.6 GB array costs more than the copy that fills
+    it, so buffers are pooled; one is handed out again only when the caller has dropped every reference to it (the
+    reference returns fresh arrays each step: a result the caller still holds is never overwritten)."""
+    import sys
+    shape = tuple(shape)
+    for t in _pinned_pool:
+        # references: the pool's list, the loop variable, getrefcount's argument
+        if tuple(t.shape) == shape and sys.getrefcount(t) <= 3:
+            return t
+    t = torch.empty(shape, dtype=torch.float32, pin_memory=True)
+    _pinned_pool.append(t)
+    if len(_pinned_pool) > 8:   # shapes no longer in use (another run in the same process)
+        _pinned_pool[:] = [u for u in _pinned_pool if sys.getrefcount(u) > 3 or tuple(u.shape) == shape][-8:]
+    return t
+
+
 def _is_pinned_host(*ts):
     return all(isinstance(t, torch.Tensor) and not t.is_cuda and t.is_pinned() and t.dtype == torch.float32
                and t.is_contiguous() for t in ts)
@@ -164,8 +190,8 @@ def _leapfrog_pinned(position, velocity, acceleration, potential, additional_fie
     del acc
     acc, pot, add, maxima = solver._pm_device(pos, param, pot, add, tables, kick=(vel, half_dt), counted=counted)
     distributed.allreduce_max_(maxima)
-    acc_h = torch.empty((n, 3), dtype=torch.float32, pin_memory=True)
-    pot_h = torch.empty(pot.shape, dtype=torch.float32, pin_memory=True) if len(pot) else pot
+    acc_h = _pinned_empty((n, 3))
+    pot_h = _pinned_empty(pot.shape) if len(pot) else pot
     add_h = add
     s_out.wait_stream(cur)
     for t in (acc, pot, add):
@@ -177,12 +203,12 @@ def _leapfrog_pinned(position, velocity, acceleration, potential, additional_fie
         if len(pot):
             pot_h.copy_(pot, non_blocking=True)
         if len(add):
-            add_h = torch.empty(add.shape, dtype=torch.float32, pin_memory=True)
+            add_h = _pinned_empty(add.shape)
             add_h.copy_(add, non_blocking=True)
     mx = maxima.cpu().numpy()
     s_out.synchronize()
     # the cached maxima belong to exactly these host tensors
-    _maxima_cache.update(acc=weakref.ref(acc_h), vel=weakref.ref(velocity), max=mx)
+    _remember_maxima(acc_h, velocity, mx)
     return position, velocity, acc_h, pot_h, add_h
 
 
@@ -205,7 +231,7 @@ def leapfrog(position, velocity, acceleration, potential, additional_field, dt, 
     acc, pot, add, maxima = solver._pm_device(pos, param, pot, add, tables, kick=(vel, half_dt), counted=counted)
     distributed.allreduce_max_(maxima)
     mx = maxima.cpu().numpy()  # one 8-byte read: max|a|, max|v| for the next integrate()
-    _maxima_cache.update(acc=weakref.ref(acc), vel=weakref.ref(vel), max=mx)
+    _remember_maxima(acc, vel, mx)
     return _from_device(c, position, velocity, pos, vel, acc, pot, add)
 
 

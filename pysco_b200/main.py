@@ -26,12 +26,23 @@ def _initial_state(param, initial_state, tables):
         from . import initial_conditions
         return initial_conditions.generate(param, tables)
     if isinstance(ic, (int, np.integer)):
-        # restart from snapshot i (initial_conditions.py:79-107), parquet flavour
+        # restart from snapshot i (initial_conditions.py:79-107): every parameter saved with the snapshot comes back
+        # (aexp, t, nsteps, i_snap, but also the multigrid tolerances `tolerance`, `tolerance_FAS`, so that a restarted
+        # multigrid / f(R) run refreshes them at the same step phase as the uninterrupted one).  The reference means to
+        # keep the caller's nthreads (its `is not` test on strings never fires, so it overwrites it as well); host
+        # threads do not exist on this path, the caller's value is kept.
+        fmt = str(param["output_snapshot_format"]).casefold()
+        if fmt == "hdf5":
+            raise NotImplementedError("restart from an HDF5 snapshot needs h5py, which this image does not have; "
+                                      "write snapshots with output_snapshot_format = parquet")
+        if fmt != "parquet":
+            raise ValueError(f"{param['output_snapshot_format']=}, should be 'parquet' or 'hdf5'")
         d = f"{param['base']}/output_{int(ic):05d}"
         pos, vel = iostream.read_snapshot_particles_parquet(f"{d}/particles_{param['extra']}.parquet")
-        saved = pd.read_csv(f"{d}/param_{param['extra']}_{int(ic):05d}.txt", sep="=", header=None, index_col=0)[1]
-        for key in ("aexp", "t", "nsteps", "i_snap"):
-            param[key] = type(param[key])(float(saved[key])) if key in param else float(saved[key])
+        saved = iostream.read_param_file(f"{d}/param_{param['extra']}_{int(ic):05d}.txt")
+        for key in saved.index:
+            if key.casefold() != "nthreads":
+                param[key] = saved[key]
         param["nsteps"], param["i_snap"] = int(param["nsteps"]), int(param["i_snap"])
         return pos.astype(np.float32), vel.astype(np.float32)
     if isinstance(ic, str) and ic.endswith(".npz"):

@@ -63,6 +63,8 @@ class SelfComm:
     def neighbor_exchange(self, to_left, to_right, n_from_left, n_from_right):
         return to_right, to_left
 
+    pair_exchange = neighbor_exchange
+
     def allreduce_max_(self, t):
         return t
 
@@ -180,6 +182,16 @@ class TorchComm:
         self._p2p(to_left, to_right, from_left, from_right)
         return from_left, from_right
 
+    def pair_exchange(self, to_left, to_right, n_from_left, n_from_right):
+        """neighbor_exchange restricted to point-to-point operations: a message whose size is 0 on both of its ends is
+        not posted at all, and nothing synchronises the group -- what the overflow path of the migration needs, where
+        only the pairs whose message did not fit take part."""
+        shape = tuple(to_left.shape[1:])
+        from_left = torch.empty((n_from_left,) + shape, dtype=to_left.dtype, device=to_left.device)
+        from_right = torch.empty((n_from_right,) + shape, dtype=to_left.dtype, device=to_left.device)
+        self._p2p_nccl(to_left, to_right, from_left, from_right)
+        return from_left, from_right
+
     def symmetric_buffers(self, numel, count):
         """`count` float32 buffers of `numel` elements that every rank can address directly over NVLink
         (torch symmetric memory: CUDA VMM allocations exchanged at a rendezvous).  Returns [(tensor, handle)] --
@@ -218,9 +230,12 @@ class TorchComm:
 
 class _ThreadWorld:
     def __init__(self, size):
+        import queue
         self.size = size
         self.barrier = threading.Barrier(size)
         self.slots = [None] * size
+        # point-to-point channels (src, dst, direction) for pair_exchange
+        self.pipes = {(a, b, d): queue.Queue() for a in range(size) for b in range(size) for d in "LR"}
 
 
 class ThreadComm:
@@ -284,6 +299,18 @@ class ThreadComm:
         out = self.exchange_planes(to_left, to_right)
         assert out[0].shape[0] == n_from_left and out[1].shape[0] == n_from_right
         return out
+
+    def pair_exchange(self, to_left, to_right, n_from_left, n_from_right):
+        """point-to-point only (no barrier): empty messages are not posted"""
+        left, right = (self.rank - 1) % self.size, (self.rank + 1) % self.size
+        if to_left.shape[0]:
+            self.w.pipes[(self.rank, left, "L")].put(to_left.clone())
+        if to_right.shape[0]:
+            self.w.pipes[(self.rank, right, "R")].put(to_right.clone())
+        from_left = self.w.pipes[(left, self.rank, "R")].get(timeout=120) if n_from_left else to_left[:0]
+        from_right = self.w.pipes[(right, self.rank, "L")].get(timeout=120) if n_from_right else to_right[:0]
+        assert from_left.shape[0] == n_from_left and from_right.shape[0] == n_from_right
+        return from_left, from_right
 
     def _allreduce(self, t, fn):
         alls = self._share(t.clone())
@@ -622,6 +649,7 @@ class Slab:
         self._peer = None         # symmetric (peer-addressable) spectrum buffers, resolved at the first solve
         self._mig_cap = None      # records per direction of the fixed-capacity migration buffers (same on all ranks)
         self._mig_want = 0        # largest message of the last migration; all-reduced in pm() to resize _mig_cap
+        self.redo_count = 0       # migrations of this rank that had to repeat a message (capacity overflow)
         self.phase_marks = None   # bench.py: list of (phase name, CUDA event) recorded at phase boundaries
 
     def _warm_host_ops(self):
@@ -756,7 +784,9 @@ class Slab:
             to_l, to_r = (a, b) if first == left else (b, a)
             if left == right:
                 to_l, to_r = sendbuf, sendbuf[:0]
-            got_l, got_r = comm.neighbor_exchange(to_l, to_r, from_l, from_r)
+            # message sizes differ from rank to rank here: point-to-point only (the peer-memory mailbox grows
+            # collectively, which ranks with different sizes would enter at different times -- ADVICE r1)
+            got_l, got_r = comm.pair_exchange(to_l, to_r, from_l, from_r)
             recvbuf = torch.cat([got_l, got_r]) if (from_l and from_r) else (got_l if from_l else got_r)
         else:
             # every rank enters the all-to-all, even with nothing to send or receive
@@ -811,15 +841,20 @@ class Slab:
         # the capacity has to stay identical on all ranks: the wish travels with the step's all-reduce(max) (pm())
         self._mig_want = max(outL, outR, inL, inR)
         if self._mig_want > cap:
-            # rare: the pairs concerned repeat their messages with exact sizes (both ends know them)
-            return self._migrate_redo(detected, outL, outR, inL, inR)
+            # rare: the messages that did not fit are repeated with their exact size.  BOTH ends of a message know its
+            # true count (the header), so the decision is taken per message and only the pairs concerned communicate,
+            # point to point -- a rank whose messages all fitted is not involved and goes on.
+            return self._migrate_redo(detected, cap, outL, outR, inL, inR, gotL, gotR)
         holes = torch.cat([holesL[:outL], holesR[:outR]])
         recvbuf = torch.cat([gotL[1:1 + inL], gotR[1:1 + inR]])
         self._apply_migration(n, holes, recvbuf, outL + outR, inL + inR)
 
-    def _migrate_redo(self, detected, outL, outR, inL, inR):
-        """Overflow path of migrate_neighbours: exact-size messages (both ends of every message know its size)."""
+    def _migrate_redo(self, detected, cap, outL, outR, inL, inR, gotL, gotR):
+        """Overflow path of migrate_neighbours.  All leavers are packed again with exact sizes (pack_leavers); a
+        direction whose count exceeded `cap` is sent again in full, point to point; a direction that fitted keeps
+        the records that already arrived and is NOT sent again."""
         ops, comm, me, P = self.ops, self.comm, self.rank, self.P
+        self.redo_count += 1
         n = self.np
         dev = self._device()
         left, right = (me - 1) % P, (me + 1) % P
@@ -838,9 +873,12 @@ class Slab:
         to_l, to_r = (a, b) if first == left else (b, a)
         if left == right:
             to_l, to_r = sendbuf, sendbuf[:0]
-        got_l, got_r = comm.neighbor_exchange(to_l, to_r, inL, inR)
-        recvbuf = torch.cat([got_l, got_r])
-        self._apply_migration(n, holes, recvbuf, nout, inL + inR)
+        again_l, again_r = to_l if to_l.shape[0] > cap else to_l[:0], to_r if to_r.shape[0] > cap else to_r[:0]
+        need_l, need_r = (inL if inL > cap else 0), (inR if inR > cap else 0)
+        red_l, red_r = comm.pair_exchange(again_l, again_r, need_l, need_r)
+        from_l = red_l if need_l else gotL[1:1 + inL]
+        from_r = red_r if need_r else gotR[1:1 + inR]
+        self._apply_migration(n, holes, torch.cat([from_l, from_r]), nout, inL + inR)
 
     def _apply_migration(self, n, holes, recvbuf, nout, nin):
         """Fill the holes left by the leavers with the arrivals (and with tail particles if more left than came)."""
@@ -1135,10 +1173,14 @@ class Slab:
         m = mx.cpu().numpy()
         self._mark("allreduce max")
         self.max_acc, self.max_vel = np.float32(m[0]), np.float32(m[1])
-        if self._mig_cap is not None and (m[2] > self._mig_cap or 8 * m[2] + 4096 < self._mig_cap):
-            # grow after an overflow, shrink when the buffers are far larger than the traffic (they are exchanged in
-            # full every step); identical on every rank: m[2] is the all-reduced maximum
-            self._mig_cap = 2 * int(m[2]) + 4096
+        if self._mig_cap is not None:
+            # grow at once after an overflow; shrink only when the buffers (exchanged in full every step) have been far
+            # larger than the traffic for a while: the yardstick is a slowly decaying maximum of the per-step traffic,
+            # so one quiet step (a short step clamped to a snapshot time) does not halve the capacity just before
+            # the next ordinary step needs it.  Identical on every rank: m[2] is the all-reduced maximum.
+            self._mig_peak = max(float(m[2]), 0.97 * getattr(self, "_mig_peak", 0.0))
+            if m[2] > self._mig_cap or 8 * self._mig_peak + 4096 < self._mig_cap:
+                self._mig_cap = 2 * int(self._mig_peak) + 4096
         return mx[:2]
 
     # -- integration.integrate / leapfrog on the slab

@@ -29,6 +29,11 @@ def _setup(N, solver="fft", **overrides):
     pos = cases.lattice_particles(N, 0.4, seed=11)
     vel = cases.velocities(N ** 3, seed=12, scale=0.3)  # large enough that particles cross slab boundaries
     aexp = overrides.pop("aexp", 0.2) if overrides else 0.2
+    if overrides and overrides.pop("boost_slab0_right", False):
+        # a stream of particles about to leave slab 0 (of 4) to the right: one neighbour pair migrates ~7x more
+        # particles than every other pair
+        m = (pos[:, 0] > 0.21) & (pos[:, 0] < 0.25)
+        vel[m, 0] = np.float32(0.9)
     param = cases.base_param(int(np.log2(N)), N ** 3, linear_newton_solver=solver, **overrides)
     param["aexp"] = param["aexp_old"] = aexp
     param["t"] = float(tables[1](np.log(param["aexp"])))
@@ -47,7 +52,7 @@ def _reference(N, solver="fft", **overrides):
     return state, float(param["t"])
 
 
-def _run_rank(N, comm, out, reorder_at=None, solver="fft", **overrides):
+def _run_rank(N, comm, out, reorder_at=None, solver="fft", mig_cap=None, **overrides):
     from pysco_b200 import slab
     from slab_oracle_ops import OracleOps
     tables, pos, vel, param = _setup(N, solver, **overrides)
@@ -62,6 +67,8 @@ def _run_rank(N, comm, out, reorder_at=None, solver="fft", **overrides):
     assert (own == r).all()
     if P == 4:
         s._mig_cap = 8     # far too small: the first steps must take the overflow (repeat) path
+    if mig_cap is not None:
+        s._mig_cap = mig_cap
     s.pm(param, tables=tables)
     moved = 0
     for step in range(NSTEPS):
@@ -82,6 +89,7 @@ def _run_rank(N, comm, out, reorder_at=None, solver="fft", **overrides):
     if s.additional_field is not None:      # MOND: the Newtonian potential, f(R): the scalaron
         ap = s.additional_field.clone()
         add = comm.all_to_all_v(ap.reshape(ap.shape[0], -1), counts, comm.exchange_counts(counts))
+    out.setdefault("redo", {})[r] = s.redo_count
     if r == 0:
         out["state"] = [t.numpy() for t in res] + [phi.numpy().reshape(N, N, N)]
         out["additional_field"] = None if add is None else add.numpy().reshape(N, N, N)
@@ -133,6 +141,19 @@ def test_slab_threads_vs_oracle(P, solver, N):
     if errs:
         raise errs[0]
     _check(out, ref, ref_t, P)
+
+
+def test_migration_overflow_of_one_pair_only():
+    """the overflow decision is per message.  Only the pair (0, 1) of four ranks migrates more particles
+    than the fixed-capacity buffers hold; ranks 0 and 1 repeat that one message point to point while ranks 2 and 3,
+    whose messages all fitted, must neither wait for them nor be disturbed -- and the result is the oracle's."""
+    N, P = 32, 4
+    ref, ref_t = _reference(N, "fft", boost_slab0_right=True)
+    out = _run_threads(P, N, "fft", dict(boost_slab0_right=True, mig_cap=300))
+    _check(out, ref, ref_t, P)
+    redo = out["redo"]
+    assert redo[0] > 0 and redo[1] > 0, redo          # the two ends of the overflowing message
+    assert redo[2] == 0 and redo[3] == 0, redo        # bystanders
 
 
 MOND_CASES = [(1, "fft_7pt", dict(theory="mond")),
