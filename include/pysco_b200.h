@@ -261,6 +261,15 @@ int psc_initialise_potential(const float *b, float q, int N, int kind, float *ou
  * (cubic.py:269-627), quartic.gauss_seidel[_with_rhs] (quartic.py:270-628).  rhs may be NULL. */
 int psc_gauss_seidel(float *x, const float *b, float q, const float *rhs, int N, int kind,
                      float f_relax, void *stream);
+/* The same sweep as ONE plane-marching kernel (csrc/gs_fused.cu): a CTA stages four planes of x in shared memory (TMA
+ * bulk copies when use_tma != 0, LDG/STS otherwise), updates the red cells of plane s + 1 and then the black cells of
+ * plane s, and writes the finished plane to x_out -- 13 B per cell instead of the 24 B of the two colour passes,
+ * bit-identical result.  OUT OF PLACE (x_out != x).  Needs N >= 128 and N % 64 == 0
+ * (psc_gauss_seidel_fused_supported). */
+int psc_gauss_seidel_fused_supported(int N);
+int psc_gauss_seidel_fused(const float *x, const float *b, float q, const float *rhs, int N, int kind, float f_relax,
+                           float *x_out, int use_tma, void *stream);
+const float *psc_mg_q_device_ptr(void);
 /* While set (non-NULL) the f(R) kernels above read q from this device float instead of their by-value argument, so
  * that a CUDA graph captured over a FAS cycle follows q from step to step; NULL restores the by-value behaviour. */
 int psc_mg_set_q_device(const float *q_dev);

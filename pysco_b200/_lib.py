@@ -82,6 +82,9 @@ SIGNATURES = {
     "psc_diff_sumsq": [_vp, _f, _vp, _i64, _vp, _vp],
     "psc_initialise_potential": [_vp, _f, _i, _i, _vp, _vp],
     "psc_gauss_seidel": [_vp, _vp, _f, _vp, _i, _i, _f, _vp],
+    "psc_gauss_seidel_fused_supported": [_i],
+    "psc_gauss_seidel_fused": [_vp, _vp, _f, _vp, _i, _i, _f, _vp, _i, _vp],
+    "psc_mg_q_device_ptr": [],
     "psc_restriction": [_vp, _i, _f, _vp, _vp],
     "psc_prolongation": [_vp, _vp, _i, _i, _vp],
     "psc_mond_rhs": [_vp, _vp, _i, _f, _i, _f, _vp],
@@ -95,7 +98,7 @@ SIGNATURES = {
     "psc_box_operator_fr": [_vp, _vp, _f, _i, _i, _i, _vp, _vp],
     "psc_box_initialise_potential_fr": [_vp, _f, _i, _i, _i, _vp, _vp],
 }
-_RESTYPES = {"psc_last_error": C.c_char_p, "psc_launch_count": _i64, "psc_argsort_workspace_bytes": _sz,
+_RESTYPES = {"psc_mg_q_device_ptr": C.c_void_p, "psc_last_error": C.c_char_p, "psc_launch_count": _i64, "psc_argsort_workspace_bytes": _sz,
              "psc_bin_workspace_bytes": _sz, "psc_bin_workspace_bytes_slab": _sz,
              "psc_slab_fft_workspace_bytes": _sz,
              "psc_fft_plan_workspace_bytes": _sz}
@@ -141,7 +144,7 @@ _TIMED = ("psc_morton_keys", "psc_argsort_keys", "psc_gather3", "psc_axpy", "psc
           "psc_kick_drift_wrap", "psc_kick_drift_wrap_count", "psc_bin_particles_counted", "psc_deposit", "psc_bin_particles", "psc_deposit_binned", "psc_interp_kick4_binned", "psc_interp_kick_phi_binned", "psc_interp", "psc_interp_kick", "psc_interp_kick4", "psc_linear_operator",
           "psc_lincomb", "psc_gradient", "psc_fft_r2c", "psc_fft_c2r", "psc_fft_c2r_vec3", "psc_green",
           "psc_grad_green", "psc_pk", "psc_operator", "psc_residual", "psc_restrict_residual",
-          "psc_residual_sumsq", "psc_diff_sumsq", "psc_initialise_potential", "psc_gauss_seidel",
+          "psc_residual_sumsq", "psc_diff_sumsq", "psc_initialise_potential", "psc_gauss_seidel", "psc_gauss_seidel_fused",
           "psc_restriction", "psc_prolongation", "psc_mond_rhs",
           "psc_bin_particles_slab", "psc_deposit_binned_slab", "psc_interp_kick_phi_binned_slab", "psc_slab_count",
           "psc_slab_pack_leavers", "psc_kick_drift_wrap_slab", "psc_slab_pack_rows", "psc_slab_pack_fixed", "psc_slab_unpack_rows", "psc_slab_move_rows", "psc_slab_fft_r2c_planes",

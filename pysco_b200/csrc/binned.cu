@@ -229,10 +229,15 @@ __global__ void __launch_bounds__(256) bin_scatter_kernel(const float *__restric
 
 // ------------------------------------------------------------------------------------- deposit
 // particles [beg, end) of bin b; shared = other CTAs deposit into the same bin (its interior cells need atomics too)
+// scale / f1: the density rescale and the slope of rhs_poisson's affine map (solver.py:114-116, 444-449) applied to the
+// bin's sums before they leave the CTA; the caller has initialised rho with the map's constant f2, so that
+// rho = f1 * (scale * sum) + f2 needs no further pass over the grid (a cell fed by several bins gets f2 once and the
+// bins' scaled sums through REDs).
 template <int SCHEME>
 __device__ __forceinline__ void deposit_bin_range(float (*tiles)[BD_TILE], const float4 *__restrict__ brec, int b,
                                                   int beg, int end, bool shared, int N, int NB, int x0, int xoff,
-                                                  int nxa, float *__restrict__ rho) {
+                                                  int nxa, float scale, float f1, float f2,
+                                                  float *__restrict__ rho) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int bk = b % NB, bj = (b / NB) % NB, bi = b / (NB * NB);
   const int oi = x0 + bi * BB - 1, oj = bj * BB - 1, ok = bk * BB - 1;  // global cell of tile cell (0,0,0)
@@ -330,10 +335,11 @@ __device__ __forceinline__ void deposit_bin_range(float (*tiles)[BD_TILE], const
       float v = tiles[0][s];
 #pragma unroll
       for (int w = 1; w < BD_WARPS; w++) v += tiles[w][s];
+      v = f1 * (scale * v);
       const int gi = wrap(pl0 + a, nxa), gj = wrap(oj + e, N);
       float *dst = rho + ((size_t)gi * N + gj) * N + gk;
       const bool mine = !shared && kin && a >= 2 && a <= BT - 3 && e >= 2 && e <= BT - 3;
-      if (mine) *dst = v;
+      if (mine) *dst = v + f2;
       else if (v != 0.0f) atomicAdd(dst, v);
     }
   }
@@ -342,14 +348,14 @@ __device__ __forceinline__ void deposit_bin_range(float (*tiles)[BD_TILE], const
 template <int SCHEME>
 __global__ void __launch_bounds__(BD_WARPS * 32) deposit_binned_kernel(const float4 *__restrict__ brec,
                                                                        const int *__restrict__ offsets, int N, int NB,
-                                                                       int x0, int xoff, int nxa,
-                                                                       float *__restrict__ rho) {
+                                                                       int x0, int xoff, int nxa, float scale, float f1,
+                                                                       float f2, float *__restrict__ rho) {
   __shared__ float tiles[BD_WARPS][BD_TILE];
   const int b = blockIdx.x;
   const int beg = offsets[b], end = offsets[b + 1];
-  if (beg == end) return;  // rho was zeroed by the caller
+  if (beg == end) return;  // rho was initialised (f2) by the caller
   deposit_bin_range<SCHEME>(tiles, brec, b, beg, min(end, beg + BIN_PART), end - beg > BIN_PART, N, NB, x0, xoff, nxa,
-                            rho);
+                            scale, f1, f2, rho);
 }
 
 // the parts beyond BIN_PART particles of the heavy bins (persistent CTAs over BinLayout::heavy)
@@ -359,13 +365,14 @@ __global__ void __launch_bounds__(BD_WARPS * 32) deposit_heavy_kernel(const floa
                                                                       const int *__restrict__ heavy_count,
                                                                       const int2 *__restrict__ heavy, int heavy_cap,
                                                                       int N, int NB, int x0, int xoff, int nxa,
+                                                                      float scale, float f1, float f2,
                                                                       float *__restrict__ rho) {
   __shared__ float tiles[BD_WARPS][BD_TILE];
   const int nitems = min(*heavy_count, heavy_cap);
   for (int it = blockIdx.x; it < nitems; it += gridDim.x) {
     const int2 w = heavy[it];
     const int beg = offsets[w.x] + w.y * BIN_PART, end = min(offsets[w.x + 1], beg + BIN_PART);
-    deposit_bin_range<SCHEME>(tiles, brec, w.x, beg, end, true, N, NB, x0, xoff, nxa, rho);
+    deposit_bin_range<SCHEME>(tiles, brec, w.x, beg, end, true, N, NB, x0, xoff, nxa, scale, f1, f2, rho);
     __syncthreads();
   }
 }
@@ -594,8 +601,13 @@ __global__ void __launch_bounds__(BP_THREADS) interp_kick_phi_binned_kernel(
   }
 }
 
-// rho = f1 * (scale * rho) + f2, defined in deposit.cu
-__global__ void rho_affine_kernel(float *rho, int64_t n, float scale, float f1, float f2, int do_scale);
+__global__ void __launch_bounds__(256) fill_kernel(float *__restrict__ x, int64_t n, float v) {
+  const int64_t n4 = n >> 2;
+  float4 *x4 = reinterpret_cast<float4 *>(x);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x)
+    x4[i] = make_float4(v, v, v, v);
+  if (blockIdx.x == 0 && threadIdx.x < (n & 3)) x[(n4 << 2) + threadIdx.x] = v;
+}
 
 }  // namespace psc
 
@@ -719,24 +731,26 @@ static int deposit_binned_impl(const void *scratch, size_t scratch_bytes, int64_
   cudaStream_t st = as_stream(stream);
   const int nxa = nxl + 2 * ghost;
   const int64_t n3 = (int64_t)nxa * N * N;
-  PSC_CUDA(cudaMemsetAsync(rho, 0, sizeof(float) * n3, st));
+  // rho starts as the constant of the affine map (0 for a raw deposit); the kernels add f1 * (scale * sums)
+  if (f2 == 0.0f) {
+    PSC_CUDA(cudaMemsetAsync(rho, 0, sizeof(float) * n3, st));
+  } else {
+    fill_kernel<<<grid_for((n3 + 3) / 4, 256), 256, 0, st>>>(rho, n3, f2);
+    count_launch();
+  }
   if (np > 0) {
     const int grid = (int)L.nbins;
     const int hgrid = num_sms() * 4;   // persistent CTAs over the heavy-bin parts (exit at once when there are none)
-#define PSC_DEP(S)                                                                                                 \
-  deposit_binned_kernel<S><<<grid, BD_WARPS * 32, 0, st>>>(L.rec, L.offsets, N, L.NB, x0, ghost, nxa, rho);        \
+#define PSC_DEP(S)                                                                                                   \
+  deposit_binned_kernel<S><<<grid, BD_WARPS * 32, 0, st>>>(L.rec, L.offsets, N, L.NB, x0, ghost, nxa, scale, f1, f2,  \
+                                                           rho);                                                     \
   deposit_heavy_kernel<S><<<hgrid, BD_WARPS * 32, 0, st>>>(L.rec, L.offsets, L.heavy_count, L.heavy, L.heavy_cap, N, \
-                                                          L.NB, x0, ghost, nxa, rho)
+                                                          L.NB, x0, ghost, nxa, scale, f1, f2, rho)
     if (scheme == PSC_TSC) { PSC_DEP(PSC_TSC); }
     else if (scheme == PSC_CIC) { PSC_DEP(PSC_CIC); }
     else { PSC_DEP(PSC_NGP); }
 #undef PSC_DEP
     count_launch(2);
-    PSC_CHECK_LAUNCH();
-  }
-  if (scale != 1.0f || f1 != 1.0f || f2 != 0.0f) {
-    rho_affine_kernel<<<grid_for((n3 + 3) / 4, 256), 256, 0, st>>>(rho, n3, scale, f1, f2, scale != 1.0f);
-    count_launch();
     PSC_CHECK_LAUNCH();
   }
   return PSC_OK;

@@ -461,6 +461,8 @@ int psc_mg_set_q_device(const float *q_dev) {
   g_q_dev = q_dev;
   return PSC_OK;
 }
+/* (library-internal) the pointer set above, for kernels in other translation units (gs_fused.cu) */
+const float *psc_mg_q_device_ptr(void) { return g_q_dev; }
 
 int psc_operator(const float *x, const float *b, float q, int N, int kind, float *out, void *stream) {
   PSC_CHECK_GRID(N);

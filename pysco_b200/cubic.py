@@ -40,16 +40,14 @@ def gauss_seidel_with_rhs(x, b, q, rhs, f_relax) -> None:
 def smoothing(x, b, q, n_smoothing) -> None:
     c = _lib.Ctx()
     tx, tb = c.dev(x, inplace=True), c.dev(b)
-    for _ in range(int(n_smoothing)):
-        laplacian.gauss_seidel(tx, tb, np.float32(1.25), K, q)
+    laplacian.sweeps(tx, tb, n_smoothing, K, q)
     c.finish()
 
 
 def smoothing_with_rhs(x, b, q, n_smoothing, rhs) -> None:
     c = _lib.Ctx()
     tx, tb, tr = c.dev(x, inplace=True), c.dev(b), c.dev(rhs)
-    for _ in range(int(n_smoothing)):
-        laplacian.gauss_seidel(tx, tb, np.float32(1.25), K, q, tr)
+    laplacian.sweeps(tx, tb, n_smoothing, K, q, tr)
     c.finish()
 
 

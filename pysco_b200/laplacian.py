@@ -81,11 +81,33 @@ def gauss_seidel(x, b, f_relax, _kind=K, q=0.0, rhs=None) -> None:
     c.finish()
 
 
+def fused_sweeps_enabled():
+    import os
+    return not os.environ.get("PSC_NO_FUSED_GS")
+
+
+def sweeps(tx, tb, n, _kind=K, q=0.0, tr=None, f_relax=np.float32(1.25)) -> None:
+    """n red-black SOR sweeps on device tensors, in place on tx.  Grids the fused kernel takes (N >= 128, N % 64 == 0)
+    run their sweeps in PAIRS through psc_gauss_seidel_fused (x -> scratch -> x: 13 B per cell and sweep); an odd
+    last sweep, and every sweep of a smaller grid, is the two-launch in-place psc_gauss_seidel (24 B per cell).
+    Same bits either way."""
+    lib = _lib.load()
+    N, n = tx.shape[0], int(n)
+    args = (float(np.float32(q)), _lib.ptr(tr), N, _kind, float(f_relax))
+    if n >= 2 and fused_sweeps_enabled() and lib.psc_gauss_seidel_fused_supported(N):
+        tmp = torch.empty_like(tx)
+        tma = 0 if __import__("os").environ.get("PSC_GS_NO_TMA") else 1
+        for _ in range(n // 2):
+            _lib.check(lib.psc_gauss_seidel_fused(_lib.ptr(tx), _lib.ptr(tb), *args, _lib.ptr(tmp), tma, _lib.stream()))
+            _lib.check(lib.psc_gauss_seidel_fused(_lib.ptr(tmp), _lib.ptr(tb), *args, _lib.ptr(tx), tma, _lib.stream()))
+        n -= 2 * (n // 2)
+    for _ in range(n):
+        _lib.check(lib.psc_gauss_seidel(_lib.ptr(tx), _lib.ptr(tb), *args, _lib.stream()))
+
+
 def smoothing(x, b, n_smoothing) -> None:
     """laplacian.py:1026-1055"""
-    f_relax = np.float32(1.25)
     c = _lib.Ctx()
     tx, tb = c.dev(x, inplace=True), c.dev(b)
-    for _ in range(int(n_smoothing)):
-        gauss_seidel(tx, tb, f_relax)
+    sweeps(tx, tb, n_smoothing)
     c.finish()
