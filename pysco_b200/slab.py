@@ -695,7 +695,7 @@ class Slab:
 
     def _ensure_capacity(self, n):
         cap = 0 if self.pos is None else self.pos.shape[0]
-        if n <= cap:
+        if n <= cap and self.pos is not None:
             return
         new_cap = int(n * self.capacity_factor) + 1024
 
@@ -1274,9 +1274,13 @@ class Slab:
 def run(param, comm=None, initial_state=None, ops_factory=None):
     """`main.run` (main.py:30-156) on x-slabs: one call per rank (torchrun; or one thread per virtual rank with a
     ThreadComm).  Every rank derives the same background tables; the initial particles come from `initial_state`
-    (global arrays, identical on every rank) or are generated identically on every rank (initial_conditions.generate:
-    meshes that fit one GPU) -- each rank adopts a strided share and the first migration routes the particles to their
-    slabs.  Snapshots are gathered to rank 0 in the reference's particle order.  Theories and solvers: what Slab.pm
+    (global arrays, identical on every rank), from a snapshot number (`initial_conditions = i`: restart, every rank
+    reads its own share of the files -- initial_conditions.py:79-107) or are generated identically on every rank
+    (initial_conditions.generate: meshes that fit one GPU) -- each rank adopts a share and the first migration routes
+    the particles to their slabs.  Snapshots: `slab_snapshots = gather` (default up to 256^3 particles) collects them
+    on rank 0 in the reference's particle order and file layout; `slab_snapshots = parts` (default above) lets every
+    rank write its own slab (iostream.write_snapshot_slab_part), so that no rank ever holds the global arrays.
+    Theories and solvers: what Slab.pm
     supports (newton / parametrized / mond / fr; fft, fft_7pt, multigrid), leapfrog.  Returns (position, velocity) of the final state on rank 0
     (CPU tensors, reference order), None elsewhere.  ops_factory(N, P, rank) replaces the CUDA kernels (tests only)."""
     import pandas as pd
@@ -1307,31 +1311,64 @@ def run(param, comm=None, initial_state=None, ops_factory=None):
         os.makedirs(f"{param['base']}/power", exist_ok=True)
         for i in range(len(z_out) + 1):
             os.makedirs(f"{param['base']}/output_{i:05d}", exist_ok=True)
+    base_dir = param["base"]
     if not root:
         param = param.copy()
-        param["base"] = ""          # only rank 0 writes tables and snapshots
+        param["base"] = ""          # only rank 0 writes tables, P(k) files and gathered snapshots
     tables = cosmotable.generate(param)
     param["aexp"] = 1.0 / (1 + param["z_start"])
     utils.set_units(param)
     if "nsteps" not in param.index:
         param["nsteps"] = 0
-    if initial_state is None:
-        from . import initial_conditions
-        position, velocity = initial_conditions.generate(param, tables, write_snapshot=root)
-    else:
-        position, velocity = initial_state
-    utils.set_units(param)
-    param["t"] = tables[1](np.log(param["aexp"]))
     N = 2 ** param["ncoarse"]
     S = Slab(N, comm=comm, ops=None if ops_factory is None else ops_factory(N, comm.size, comm.rank))
     dev = S._device()
-    position = torch.as_tensor(position, dtype=torch.float32).to(dev)
-    velocity = torch.as_tensor(velocity, dtype=torch.float32).to(dev)
-    npart = position.shape[0]
-    ids = torch.arange(npart, dtype=torch.int64, device=dev)
-    mine = slice(comm.rank, None, comm.size)
-    S.set_particles(position[mine].contiguous(), velocity[mine].contiguous(), ids[mine].contiguous())
-    del position, velocity, ids
+    ic = param["initial_conditions"] if "initial_conditions" in param.index else None
+    if initial_state is None and isinstance(ic, (int, np.integer)):
+        # restart: every saved parameter comes back (as main._initial_state), every rank reads its own share
+        base = param["base"] if root else base_dir
+        d = f"{base}/output_{int(ic):05d}"
+        saved = iostream.read_param_file(f"{d}/param_{param['extra']}_{int(ic):05d}.txt")
+        for key in saved.index:
+            if key.casefold() not in ("nthreads", "base"):
+                param[key] = saved[key]
+        param["nsteps"], param["i_snap"] = int(param["nsteps"]), int(param["i_snap"])
+        utils.set_units(param)
+        p_, v_, i_ = iostream.read_snapshot_slab_parts(f"{d}/particles_{param['extra']}.parquet", comm.rank, comm.size)
+        npart = int(param["npart"])
+        S.set_particles(torch.from_numpy(p_).to(dev), torch.from_numpy(v_).to(dev), torch.from_numpy(i_).to(dev))
+        del p_, v_, i_
+    else:
+        if initial_state is None:
+            from . import initial_conditions
+            position, velocity = initial_conditions.generate(param, tables, write_snapshot=root)
+        else:
+            position, velocity = initial_state
+        utils.set_units(param)
+        param["t"] = tables[1](np.log(param["aexp"]))
+        position = torch.as_tensor(position, dtype=torch.float32).to(dev)
+        velocity = torch.as_tensor(velocity, dtype=torch.float32).to(dev)
+        npart = position.shape[0]
+        ids = torch.arange(npart, dtype=torch.int64, device=dev)
+        mine = slice(comm.rank, None, comm.size)
+        S.set_particles(position[mine].contiguous(), velocity[mine].contiguous(), ids[mine].contiguous())
+        del position, velocity, ids
+    mode = str(param["slab_snapshots"]).casefold() if "slab_snapshots" in param.index else "auto"
+    if mode not in ("auto", "gather", "parts"):
+        raise NotImplementedError(f"{param['slab_snapshots']=}, should be 'gather', 'parts' or 'auto'")
+    parts_mode = mode == "parts" or (mode == "auto" and npart > 256 ** 3)
+
+    def snapshot():
+        if parts_mode:
+            p = param.copy()
+            p["base"] = base_dir
+            n = S.np
+            iostream.write_snapshot_slab_part(S.pos[:n], S.vel[:n], S.ids[:n], p, comm.rank, root)
+            comm.barrier()
+        else:
+            state = S.gather_to_root(npart)
+            if root:
+                iostream.write_snapshot_particles(state[0], state[1], param)
     S.pm(param, tables=tables)
     aexp_out = np.sort(1.0 / (np.array(z_out) + 1))
     t_out = tables[1](np.log(aexp_out))
@@ -1342,11 +1379,14 @@ def run(param, comm=None, initial_state=None, ops_factory=None):
         if (param["nsteps"] % param["n_reorder"]) == 0:
             S.reorder()
         if param["write_snapshot"]:
-            state = S.gather_to_root(npart)
-            if root:
-                iostream.write_snapshot_particles(state[0], state[1], param)
+            snapshot()
             param["i_snap"] += 1
         logging.warning(f"{param['nsteps']=} {param['aexp']=} z = {1.0 / param['aexp'] - 1}")
+    if parts_mode:       # the final state stays distributed: this rank's slab (position, velocity, ids)
+        n = S.np
+        out = (S.pos[:n].clone(), S.vel[:n].clone(), S.ids[:n].clone())
+        S.ops.close()
+        return out
     state = S.gather_to_root(npart)
     S.ops.close()
     return (state[0], state[1]) if root else None

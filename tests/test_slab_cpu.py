@@ -357,3 +357,68 @@ def test_torchcomm_semantics_gloo_world3():
         out = mgr.dict()
         mp.spawn(_gloo3_worker, args=(3, port, out), nprocs=3, join=True)
         assert dict(out) == {0: True, 1: True, 2: True}
+
+
+def _run_slab_threads(P, base, overrides, g):
+    """slab.run on P virtual ranks (oracle kernels); returns {rank: result}"""
+    from pysco_b200 import slab
+    from slab_oracle_ops import OracleOps
+    out, errs = {}, []
+    comms = slab.ThreadComm.world(P) if P > 1 else [slab.SelfComm()]
+
+    def work(c):
+        try:
+            param = cases.run_param(base, "fft")
+            param.update(overrides)
+            init = None if isinstance(param["initial_conditions"], int) else (g["ic_pos"].copy(), g["ic_vel"].copy())
+            out[c.rank] = slab.run(param, comm=c, initial_state=init, ops_factory=OracleOps)
+        except BaseException as e:  # noqa: BLE001
+            errs.append(e)
+            if P > 1:
+                c.w.barrier.abort()
+
+    ts = [threading.Thread(target=work, args=(c,)) for c in comms]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    if errs:
+        raise errs[0]
+    return out
+
+
+def test_slab_snapshots_in_parts_and_restart(tmp_path):
+    """SURVEY 8(f) rank 2 on slabs: every rank writes its own slab of a snapshot (no gather), the directory reads back
+    as one table with the reference's reader, the run restarts from those parts on a DIFFERENT number of ranks
+    (initial_conditions = snapshot number, initial_conditions.py:79-107) and ends where the uninterrupted run ends --
+    which is the reference's final snapshot (tests/golden/run.npz)."""
+    import glob
+    from pysco_b200 import iostream
+    with np.load(os.path.join(ROOT, "tests", "golden", "run.npz")) as z:
+        g = {k: z[k] for k in ("ic_pos", "ic_vel", "fft_pos", "fft_vel")}
+    base = str(tmp_path) + "/"
+    over = dict(slab_snapshots="parts", save_power_spectrum="no")
+    full = _run_slab_threads(2, base, over, g)
+
+    def assemble(res):
+        pos = torch.cat([r[0].cpu() for r in res.values()]).numpy()
+        vel = torch.cat([r[1].cpu() for r in res.values()]).numpy()
+        ids = torch.cat([r[2].cpu() for r in res.values()]).numpy()
+        assert np.array_equal(np.sort(ids), np.arange(len(ids)))
+        o = np.argsort(ids)
+        return pos[o], vel[o]
+
+    pos, vel = assemble(full)
+    d = np.abs(pos - g["fft_pos"])
+    assert np.minimum(d, 1 - d).max() < 1e-5
+    # on disk: one directory per snapshot, one part per rank, readable as one table by the reference's reader
+    snap = glob.glob(os.path.join(base, "output_00003", "particles_*.parquet"))
+    assert len(snap) == 1 and os.path.isdir(snap[0])
+    assert sorted(os.listdir(snap[0])) == ["part-00000.parquet", "part-00001.parquet"]
+    p3, v3 = iostream.read_snapshot_particles_parquet(snap[0])
+    assert p3.shape == (32 ** 3, 3) and v3.shape == (32 ** 3, 3)
+    # restart from snapshot 3 on ONE rank, then from the same snapshot on FOUR ranks
+    for P in (1, 4):
+        again = _run_slab_threads(P, base, dict(over, initial_conditions=3), g)
+        pos2, vel2 = assemble(again)
+        d = np.abs(pos2 - pos)
+        assert np.minimum(d, 1 - d).max() < 2e-6, f"restart on {P} rank(s)"
+        assert np.abs(vel2 - vel).max() < 2e-5 * np.abs(vel).max()
