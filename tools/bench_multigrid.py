@@ -51,7 +51,8 @@ def report(name, ms, bytes_per_cell):
     print(f"N={N} {name:34s} {ms:8.3f} ms  {gbs:7.0f} GB/s algorithmic ({bytes_per_cell} B/cell)  frac {gbs / peak:.3f}", flush=True)
 
 
-report("gauss_seidel (1 sweep, red+black)", timeit(lambda: laplacian.gauss_seidel(x, b, np.float32(1.25))), 12)
+report("gauss_seidel (1 sweep, two launches)", timeit(lambda: laplacian.gauss_seidel(x, b, np.float32(1.25))), 12)
+report("smoothing x2 (fused pair), per sweep", timeit(lambda: laplacian.smoothing(x, b, 2)) / 2, 12)
 report("restrict_residual", timeit(lambda: laplacian.restrict_residual(x, b)), 8.5)
 xc = mesh.restriction(x)
 report("add_prolongation", timeit(lambda: mesh.add_prolongation(x, xc)), 8.5)
@@ -59,7 +60,8 @@ report("residual_error", timeit(lambda: laplacian.residual_error(x, b)), 8)
 report("operator", timeit(lambda: laplacian.operator(x)), 8)
 u = torch.ones_like(b) + 0.05 * b
 bb = 2.0 * (1 + 0.1 * b)
-report("cubic gauss_seidel (1 sweep)", timeit(lambda: cubic.gauss_seidel(u, bb, np.float32(-2.0), np.float32(1.25))), 12)
+report("cubic gauss_seidel (two launches)", timeit(lambda: cubic.gauss_seidel(u, bb, np.float32(-2.0), np.float32(1.25))), 12)
+report("cubic smoothing x2 (fused), per sweep", timeit(lambda: cubic.smoothing(u, bb, np.float32(-2.0), 2)) / 2, 12)
 param = bench.make_param(nc, 1)
 param["linear_newton_solver"] = "multigrid"
 param["compute_additional_field"] = False
