@@ -41,8 +41,8 @@ N_REORDER = 50
 # (SURVEY 8d): the figure `roofline.achieved` is computed from.
 ALGO_BYTES = {
     "psc_kick_drift_wrap": 60.0,   # read x,v,a (36) + write x,v (24)
-    "psc_kick_drift_wrap_count": 60.0,   # same pass + the per-cell counts of the new positions
-    "psc_bin_particles_counted": 0.0,    # scan + scatter of the counting sort: overhead, not in the 176 B budget
+    "psc_kick_drift_wrap_count": 60.0,   # same pass + the per-bin counts of the new positions
+    "psc_bin_particles_counted": 0.0,    # scan + scatter of the per-step binning: overhead, not in the 176 B budget
     "psc_deposit": 16.0,           # read x (12) + write rho (4); rescale + RHS affine fused (0)
     "psc_fft_r2c": 8.0,            # read 4 + write 4 (half-spectrum ~ 4 B per real cell)
     "psc_green": 8.0,
@@ -814,6 +814,14 @@ def run_slab_arm(args):
     if world == 8 and nc < 11 and not args.no_config5:
         del S
         torch.cuda.empty_cache()
+        # 2048^3 on 8 GPUs peaks at ~150 GB per GPU (the Morton reorder's sort buffers on top of 1.07 G particles):
+        # attempted only when EVERY rank has the room, so that no rank can run out of memory inside a collective
+        free = torch.tensor([torch.cuda.mem_get_info()[0] / 2 ** 30], device="cuda", dtype=torch.float64)
+        dist.all_reduce(free, op=dist.ReduceOp.MIN)
+        if free.item() < args.config5_min_free_gib:
+            config5 = {"skipped": f"least free device memory over the ranks {free.item():.0f} GiB < "
+                                  f"{args.config5_min_free_gib:.0f} GiB needed for 2048^3 on 8 GPUs"}
+    if config5 is None and world == 8 and nc < 11 and not args.no_config5:
         try:
             S5, p5 = build(11)
             m5 = slab_measure(S5, p5, tables, args.config5_steps, 3, world, rank, local_rank)
@@ -887,6 +895,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--extra-steps", type=int, default=8)
     ap.add_argument("--config5-steps", type=int, default=6)
+    ap.add_argument("--config5-min-free-gib", type=float, default=160.0)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true")

@@ -103,14 +103,20 @@ int psc_deposit_binned(const void *scratch, size_t scratch_bytes, int64_t np, in
 int psc_interp_kick4_binned(const float *force4, const void *scratch, size_t scratch_bytes, float *vel, float *acc,
                             int64_t np, int N, int scheme, float half_dt, float *maxout, void *stream);
 
-/* psc_kick_drift_wrap with the bin count of the NEW positions folded in (the binning's first pass then costs no
- * extra read of the positions): counts go to the bin scratch of np_total particles (zeroed first when zero_counts;
- * pass 0 for the later chunks of a chunked upload).  psc_bin_particles_counted finishes the binning (scan +
- * scatter) from those counts. */
+/* psc_kick_drift_wrap with the binning of the NEW positions folded in, on the bin scratch of np_total particles.
+ * mode 0: per-bin COUNT (the binning's first pass then costs no extra read of the positions);
+ * psc_bin_particles_counted(mode 0) finishes with scan + scatter.
+ * mode 1: DIRECT scatter -- the scratch still holds the previous step's binning of (about) the same particles: every
+ * bin gets its previous fill + 1/8 + 32 records of room and each particle drops its (x, y, z, row) record straight
+ * into its bin, so there is no count pass and no second read of the positions; psc_bin_particles_counted(mode 1)
+ * finishes (heavy-bin list) and, when a bin ran out of room, redoes the exact binning on the device.
+ * zero_counts: 1 for the first (or only) chunk of a step, 0 for the later chunks of a chunked upload; row0: global row
+ * of pos[0]. */
 int psc_kick_drift_wrap_count(float *pos, float *vel, const float *acc, int64_t np, float half_dt, double dt,
                               int dt_is_f64, int N, int64_t np_total, void *scratch, size_t scratch_bytes,
-                              int zero_counts, void *stream);
-int psc_bin_particles_counted(const float *pos, int64_t np, int N, void *scratch, size_t scratch_bytes, void *stream);
+                              int zero_counts, int mode, int64_t row0, void *stream);
+int psc_bin_particles_counted(const float *pos, int64_t np, int N, void *scratch, size_t scratch_bytes, int mode,
+                              void *stream);
 
 /* mesh.derivative / derivative_fR (mesh.py:639-2174) fused into the binned interpolation + kick: every bin's CTA
  * derives its force tile from the potential phi (and, for f(R), the scalaron u: phi + f * u^(fr_n+1)) in shared

@@ -33,8 +33,8 @@ SIGNATURES = {
     "psc_interp_kick": [_vp, _vp, _vp, _vp, _i64, _i, _i, _f, _vp, _vp],
     "psc_bin_workspace_bytes": [_i64, _i],
     "psc_bin_particles": [_vp, _i64, _i, _vp, _sz, _vp],
-    "psc_kick_drift_wrap_count": [_vp, _vp, _vp, _i64, _f, _d, _i, _i, _i64, _vp, _sz, _i, _vp],
-    "psc_bin_particles_counted": [_vp, _i64, _i, _vp, _sz, _vp],
+    "psc_kick_drift_wrap_count": [_vp, _vp, _vp, _i64, _f, _d, _i, _i, _i64, _vp, _sz, _i, _i, _i64, _vp],
+    "psc_bin_particles_counted": [_vp, _i64, _i, _vp, _sz, _i, _vp],
     "psc_deposit_binned": [_vp, _sz, _i64, _i, _i, _f, _f, _f, _vp, _vp],
     "psc_interp_kick4_binned": [_vp, _vp, _sz, _vp, _vp, _i64, _i, _i, _f, _vp, _vp],
     "psc_interp_kick_phi_binned": [_vp, _vp, _f, _i, _i, _vp, _sz, _vp, _vp, _i64, _i, _i, _f, _vp, _vp],

@@ -48,9 +48,16 @@ struct BinLayout {
   int NBX;           // bins along x (owned planes / 8; == NB for the periodic single-domain case)
   int x0;            // first owned x cell (0 unless the mesh is slab-decomposed)
   int64_t nbins;     // NBX * NB^2
-  int *counts;       // [nbins + 1]
-  int *offsets;      // [nbins + 1]  exclusive prefix sum, offsets[nbins] = np
-  float4 *rec;       // [np] binned particles: (x, y, z, source row as int bits) -- one 16-byte access per particle
+  int64_t nrec;      // records `rec` can hold: np + np / 8 + 40 nbins (room for the slack of the direct scatter)
+  int *counts;       // [nbins + 1]  result of a count pass (input of the scan of the exact binning)
+  int *fill;         // [nbins + 1]  records written to each bin: the particles of bin b are rec[base[b] .. base[b] + fill[b])
+  int *base;         // [nbins + 1]  first record of each bin.  Exact binning: the exclusive scan of counts (no gaps).
+                     //              Direct scatter (psc_kick_drift_wrap_count, mode 1): the scan of capacities derived
+                     //              from the PREVIOUS step's fill, so every bin has some slack and the kick-drift-wrap
+                     //              pass can drop its records straight into place without a count pass.
+  int *tmp;          // [nbins + 1]  capacities / fall-back offsets
+  int *overflow;     // [1] set by the direct scatter when a bin ran out of slack: the exact binning is redone
+  float4 *rec;       // [nrec] binned particles: (x, y, z, source row as int bits) -- one 16-byte access per particle
   int *heavy_count;  // [1] number of entries of `heavy`
   int2 *heavy;       // [heavy_cap] (bin, part >= 1): the parts beyond the first BIN_PART particles of a bin
   int heavy_cap;
@@ -66,6 +73,8 @@ static size_t scan_tmp_bytes(int64_t n) {
   return b;
 }
 
+static int64_t rec_capacity(int64_t np, int64_t nbins) { return np + np / 8 + 40 * nbins + 64; }
+
 static bool bin_layout(void *scratch, size_t bytes, int64_t np, int N, int x0, int nxl, BinLayout &L) {
   L.NB = N / BB;
   L.NBX = nxl / BB;
@@ -73,10 +82,14 @@ static bool bin_layout(void *scratch, size_t bytes, int64_t np, int N, int x0, i
   L.nbins = (int64_t)L.NBX * L.NB * L.NB;
   char *p = reinterpret_cast<char *>(scratch);
   size_t off = 0;
+  L.nrec = rec_capacity(np, L.nbins);
   L.counts = reinterpret_cast<int *>(p + off); off += a256(sizeof(int) * (L.nbins + 1));
-  L.offsets = reinterpret_cast<int *>(p + off); off += a256(sizeof(int) * (L.nbins + 1));
-  L.rec = reinterpret_cast<float4 *>(p + off); off += a256(sizeof(float4) * (size_t)np);
-  L.heavy_count = reinterpret_cast<int *>(p + off); off += 256;
+  L.fill = reinterpret_cast<int *>(p + off); off += a256(sizeof(int) * (L.nbins + 1));
+  L.base = reinterpret_cast<int *>(p + off); off += a256(sizeof(int) * (L.nbins + 1));
+  L.tmp = reinterpret_cast<int *>(p + off); off += a256(sizeof(int) * (L.nbins + 1));
+  L.rec = reinterpret_cast<float4 *>(p + off); off += a256(sizeof(float4) * (size_t)L.nrec);
+  L.overflow = reinterpret_cast<int *>(p + off); off += 128;
+  L.heavy_count = reinterpret_cast<int *>(p + off); off += 128;
   L.heavy_cap = (int)(np / BIN_PART) + 1;
   L.heavy = reinterpret_cast<int2 *>(p + off); off += a256(sizeof(int2) * (size_t)L.heavy_cap);
   L.cub_tmp = p + off;
@@ -96,7 +109,9 @@ __device__ __forceinline__ int bin_of(float x, float y, float z, float Nf, int N
 
 // pass 1: counts[bin] += 1, one atomic per distinct bin per warp
 __global__ void __launch_bounds__(256) bin_count_kernel(const float *__restrict__ pos, int64_t np, int N, int NB,
-                                                        int x0, int NBX, int *__restrict__ counts) {
+                                                        int x0, int NBX, int *__restrict__ counts,
+                                                        const int *__restrict__ only_if) {
+  if (only_if && *only_if == 0) return;
   const float Nf = (float)N;
   const int lane = threadIdx.x & 31;
   const int64_t nwarp_iters = (np + 31) >> 5;
@@ -113,11 +128,18 @@ __global__ void __launch_bounds__(256) bin_count_kernel(const float *__restrict_
 // pass 1 fused into the first half of the leapfrog step (integration.py:250-258): v -= half_dt a; x += dt v; wrap(x);
 // counts[bin(x)] += 1.  Four particles (three float4 per array) per thread; the common case "all four in one bin" costs
 // one warp-aggregated atomic.  Saves the separate read of the positions that bin_count_kernel does.
-template <bool F64>
+// DIRECT: instead of counting, every particle claims the next free record of its bin (fill[] is the cursor, base[] the
+// first record of each bin, with slack from the previous step's fill) and its (x, y, z, row) record is written at once:
+// the binning costs no second pass over the positions.  A bin whose slack is exhausted sets *overflow (the caller
+// then redoes the exact binning); row0 = global row of pos[0] (chunked uploads).
+template <bool F64, bool DIRECT>
 __global__ void __launch_bounds__(256) kick_drift_wrap_count_kernel(float *__restrict__ pos, float *__restrict__ vel,
                                                                     const float *__restrict__ acc, int64_t np,
                                                                     float half_dt, double dt, int N, int NB,
-                                                                    int *__restrict__ counts) {
+                                                                    int *__restrict__ counts,
+                                                                    const int *__restrict__ bbase, int64_t nrec,
+                                                                    float4 *__restrict__ brec, int row0,
+                                                                    int *__restrict__ overflow) {
   const float dtf = (float)dt, mh = -half_dt, Nf = (float)N;
   const int lane = threadIdx.x & 31;
   const int64_t nq = np >> 2;
@@ -154,14 +176,52 @@ __global__ void __launch_bounds__(256) kick_drift_wrap_count_kernel(float *__res
       for (int r = 0; r < 4; r++) b[r] = bin_of(f[3 * r], f[3 * r + 1], f[3 * r + 2], Nf, NB, 0, NB);
     }
     const bool same = b[0] == b[1] && b[1] == b[2] && b[2] == b[3];
-    if (__all_sync(0xffffffffu, same)) {
-      const unsigned peers = __match_any_sync(0xffffffffu, b[0]);
-      if (valid && (__ffs(peers) - 1) == lane) atomicAdd(&counts[b[0]], 4 * __popc(peers));
-    } else {
+    if (!DIRECT) {
+      if (__all_sync(0xffffffffu, same)) {
+        const unsigned peers = __match_any_sync(0xffffffffu, b[0]);
+        if (valid && (__ffs(peers) - 1) == lane) atomicAdd(&counts[b[0]], 4 * __popc(peers));
+      } else {
 #pragma unroll
-      for (int r = 0; r < 4; r++) {
-        const unsigned peers = __match_any_sync(0xffffffffu, b[r]);
-        if (valid && (__ffs(peers) - 1) == lane) atomicAdd(&counts[b[r]], __popc(peers));
+        for (int r = 0; r < 4; r++) {
+          const unsigned peers = __match_any_sync(0xffffffffu, b[r]);
+          if (valid && (__ffs(peers) - 1) == lane) atomicAdd(&counts[b[r]], __popc(peers));
+        }
+      }
+    } else {
+      const int row = row0 + (int)(4 * q);
+      if (__all_sync(0xffffffffu, same)) {
+        // one atomic per distinct bin of the warp claims 4 records per lane of the group
+        const unsigned peers = __match_any_sync(0xffffffffu, b[0]);
+        const int leader = __ffs(peers) - 1;
+        int first = 0;
+        if (valid && leader == lane) first = atomicAdd(&counts[b[0]], 4 * __popc(peers));
+        first = __shfl_sync(0xffffffffu, first, leader);
+        if (valid) {
+          const int64_t slot = (int64_t)bbase[b[0]] + first + 4 * __popc(peers & ((1u << lane) - 1u));
+          if (slot + 4 <= (int64_t)bbase[b[0] + 1] && slot + 4 <= nrec) {
+#pragma unroll
+            for (int r = 0; r < 4; r++)
+              brec[slot + r] = make_float4(f[3 * r], f[3 * r + 1], f[3 * r + 2], __int_as_float(row + r));
+          } else {
+            *overflow = 1;
+          }
+        }
+      } else {
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+          const unsigned peers = __match_any_sync(0xffffffffu, b[r]);
+          const int leader = __ffs(peers) - 1;
+          int first = 0;
+          if (valid && leader == lane) first = atomicAdd(&counts[b[r]], __popc(peers));
+          first = __shfl_sync(0xffffffffu, first, leader);
+          if (valid) {
+            const int64_t slot = (int64_t)bbase[b[r]] + first + __popc(peers & ((1u << lane) - 1u));
+            if (slot < (int64_t)bbase[b[r] + 1] && slot < nrec)
+              brec[slot] = make_float4(f[3 * r], f[3 * r + 1], f[3 * r + 2], __int_as_float(row + r));
+            else
+              *overflow = 1;
+          }
+        }
       }
     }
   }
@@ -179,27 +239,57 @@ __global__ void __launch_bounds__(256) kick_drift_wrap_count_kernel(float *__res
       pos[3 * n + c] = p;
       x[c] = p;
     }
-    atomicAdd(&counts[bin_of(x[0], x[1], x[2], Nf, NB, 0, NB)], 1);
+    const int bb = bin_of(x[0], x[1], x[2], Nf, NB, 0, NB);
+    const int first = atomicAdd(&counts[bb], 1);
+    if (DIRECT) {
+      const int64_t slot = (int64_t)bbase[bb] + first;
+      if (slot < (int64_t)bbase[bb + 1] && slot < nrec)
+        brec[slot] = make_float4(x[0], x[1], x[2], __int_as_float(row0 + (int)n));
+      else
+        *overflow = 1;
+    }
   }
 }
 
+// capacities for the next direct scatter from this step's fill: fill + 1/8 + 32 records per bin (sum <= rec capacity)
+__global__ void __launch_bounds__(256) bin_caps_kernel(const int *__restrict__ fill, int nbins, int64_t np,
+                                                       int *__restrict__ caps) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b > nbins) return;
+  int f = 0;
+  if (b < nbins) f = (int)min((int64_t)max(fill[b], 0), np);
+  caps[b] = b < nbins ? f + (f >> 3) + 32 : 0;
+}
+
+// fall-back of the direct scatter: adopt the exact offsets and restart the cursors
+__global__ void __launch_bounds__(256) bin_adopt_kernel(const int *__restrict__ overflow, const int *__restrict__ exact,
+                                                        int nbins, int *__restrict__ base, int *__restrict__ fill) {
+  if (*overflow == 0) return;
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b > nbins) return;
+  base[b] = exact[b];
+  fill[b] = 0;
+}
+
 // after the scan: list the extra parts of the bins that hold more than BIN_PART particles
-__global__ void __launch_bounds__(256) bin_heavy_list_kernel(const int *__restrict__ offsets, int nbins,
+__global__ void __launch_bounds__(256) bin_heavy_list_kernel(const int *__restrict__ fill, int nbins,
                                                              int *__restrict__ heavy_count, int2 *__restrict__ heavy,
                                                              int heavy_cap) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= nbins) return;
-  const int extra = (offsets[b + 1] - offsets[b] - 1) / BIN_PART;
+  const int extra = (fill[b] - 1) / BIN_PART;
   if (extra <= 0) return;
   const int base = atomicAdd(heavy_count, extra);
   for (int e = 0; e < extra; e++)
     if (base + e < heavy_cap) heavy[base + e] = make_int2(b, e + 1);
 }
 
-// pass 2: slot = offsets[bin] + (claimed range in the bin); counts[] is consumed (counted down to zero)
+// pass 2: every particle claims the next record of its bin: slot = base[bin] + fill[bin]++ (fill ends as the count)
 __global__ void __launch_bounds__(256) bin_scatter_kernel(const float *__restrict__ pos, int64_t np, int N, int NB,
-                                                          int x0, int NBX, int *__restrict__ counts, const int *__restrict__ offsets,
-                                                          float4 *__restrict__ brec) {
+                                                          int x0, int NBX, int *__restrict__ fill,
+                                                          const int *__restrict__ base, float4 *__restrict__ brec,
+                                                          const int *__restrict__ only_if) {
+  if (only_if && *only_if == 0) return;
   const float Nf = (float)N;
   const int lane = threadIdx.x & 31;
   const int64_t nwarp_iters = (np + 31) >> 5;
@@ -214,14 +304,11 @@ __global__ void __launch_bounds__(256) bin_scatter_kernel(const float *__restric
     }
     const unsigned peers = __match_any_sync(0xffffffffu, b);
     const int leader = __ffs(peers) - 1;
-    int base = 0;
-    if (b >= 0 && leader == lane) {
-      const int cnt = __popc(peers);
-      base = atomicSub(&counts[b], cnt) - cnt;
-    }
-    base = __shfl_sync(0xffffffffu, base, leader);
+    int first = 0;
+    if (b >= 0 && leader == lane) first = atomicAdd(&fill[b], __popc(peers));
+    first = __shfl_sync(0xffffffffu, first, leader);
     if (b >= 0) {
-      const int slot = offsets[b] + base + __popc(peers & ((1u << lane) - 1u));
+      const int slot = base[b] + first + __popc(peers & ((1u << lane) - 1u));
       brec[slot] = make_float4(x, y, z, __int_as_float((int)n));
     }
   }
@@ -347,12 +434,13 @@ __device__ __forceinline__ void deposit_bin_range(float (*tiles)[BD_TILE], const
 
 template <int SCHEME>
 __global__ void __launch_bounds__(BD_WARPS * 32) deposit_binned_kernel(const float4 *__restrict__ brec,
-                                                                       const int *__restrict__ offsets, int N, int NB,
+                                                                       const int *__restrict__ base,
+                                                                       const int *__restrict__ fill, int N, int NB,
                                                                        int x0, int xoff, int nxa, float scale, float f1,
                                                                        float f2, float *__restrict__ rho) {
   __shared__ float tiles[BD_WARPS][BD_TILE];
   const int b = blockIdx.x;
-  const int beg = offsets[b], end = offsets[b + 1];
+  const int beg = base[b], end = beg + fill[b];
   if (beg == end) return;  // rho was initialised (f2) by the caller
   deposit_bin_range<SCHEME>(tiles, brec, b, beg, min(end, beg + BIN_PART), end - beg > BIN_PART, N, NB, x0, xoff, nxa,
                             scale, f1, f2, rho);
@@ -361,7 +449,8 @@ __global__ void __launch_bounds__(BD_WARPS * 32) deposit_binned_kernel(const flo
 // the parts beyond BIN_PART particles of the heavy bins (persistent CTAs over BinLayout::heavy)
 template <int SCHEME>
 __global__ void __launch_bounds__(BD_WARPS * 32) deposit_heavy_kernel(const float4 *__restrict__ brec,
-                                                                      const int *__restrict__ offsets,
+                                                                      const int *__restrict__ base,
+                                                                      const int *__restrict__ fill,
                                                                       const int *__restrict__ heavy_count,
                                                                       const int2 *__restrict__ heavy, int heavy_cap,
                                                                       int N, int NB, int x0, int xoff, int nxa,
@@ -371,7 +460,7 @@ __global__ void __launch_bounds__(BD_WARPS * 32) deposit_heavy_kernel(const floa
   const int nitems = min(*heavy_count, heavy_cap);
   for (int it = blockIdx.x; it < nitems; it += gridDim.x) {
     const int2 w = heavy[it];
-    const int beg = offsets[w.x] + w.y * BIN_PART, end = min(offsets[w.x + 1], beg + BIN_PART);
+    const int beg = base[w.x] + w.y * BIN_PART, end = min(base[w.x] + fill[w.x], beg + BIN_PART);
     deposit_bin_range<SCHEME>(tiles, brec, w.x, beg, end, true, N, NB, x0, xoff, nxa, scale, f1, f2, rho);
     __syncthreads();
   }
@@ -383,7 +472,8 @@ constexpr int BI_THREADS = 128;
 template <int SCHEME>
 __global__ void __launch_bounds__(BI_THREADS) interp_kick4_binned_kernel(
     const float4 *__restrict__ force4, const float4 *__restrict__ brec,
-    const int *__restrict__ offsets, float *__restrict__ vel, float *__restrict__ accel, int N, int NB,
+    const int *__restrict__ base, const int *__restrict__ fill, float *__restrict__ vel, float *__restrict__ accel,
+    int N, int NB,
     int x0, int xoff, int nxa, float half_dt, float *__restrict__ maxout, int nbins,
     const int *__restrict__ heavy_count, const int2 *__restrict__ heavy) {
   __shared__ float4 tile[BT * BT * BT];  // 16,000 B
@@ -396,7 +486,7 @@ __global__ void __launch_bounds__(BI_THREADS) interp_kick4_binned_kernel(
     b = w.x;
     part = w.y;
   }
-  const int beg = offsets[b] + part * BIN_PART, end = min(offsets[b + 1], beg + BIN_PART);
+  const int beg = base[b] + part * BIN_PART, end = min(base[b] + fill[b], beg + BIN_PART);
   if (beg >= end) return;
   const int bk = b % NB, bj = (b / NB) % NB, bi = b / (NB * NB);
   const int oi = x0 + bi * BB - 1, oj = bj * BB - 1, ok = bk * BB - 1;
@@ -471,7 +561,7 @@ constexpr int BP_THREADS = 256;  // gradient + interpolation kernel
 template <int SCHEME, int ORDER, int TP1 = BT, int TP0 = BT * BT>
 __global__ void __launch_bounds__(BP_THREADS) interp_kick_phi_binned_kernel(
     const float *__restrict__ phi, const float *__restrict__ u, float f, int fr_n,
-    const float4 *__restrict__ brec, const int *__restrict__ offsets,
+    const float4 *__restrict__ brec, const int *__restrict__ base, const int *__restrict__ fill,
     float *__restrict__ vel, float *__restrict__ accel, int N, int NB, int x0, int xoff, int nxa, float half_dt,
     float *__restrict__ maxout, int nbins, const int *__restrict__ heavy_count, const int2 *__restrict__ heavy) {
   constexpr int H = Reach<ORDER>::H;
@@ -489,7 +579,7 @@ __global__ void __launch_bounds__(BP_THREADS) interp_kick_phi_binned_kernel(
     b = w.x;
     part = w.y;
   }
-  const int beg = offsets[b] + part * BIN_PART, end = min(offsets[b + 1], beg + BIN_PART);
+  const int beg = base[b] + part * BIN_PART, end = min(base[b] + fill[b], beg + BIN_PART);
   if (beg >= end) return;
   const int bk = b % NB, bj = (b / NB) % NB, bi = b / (NB * NB);
   const int oi = x0 + bi * BB - 1, oj = bj * BB - 1, ok = bk * BB - 1;
@@ -622,10 +712,38 @@ static bool slab_ok(int N, int x0, int nxl) {
 size_t psc_bin_workspace_bytes_slab(int64_t np, int N, int nxl) {
   if (np < 0 || !slab_ok(N, 0, nxl)) return 0;
   const int64_t nbins = (int64_t)(nxl / BB) * (N / BB) * (N / BB);
-  return 2 * a256(sizeof(int) * (nbins + 1)) + a256(sizeof(float4) * (size_t)np) + 256 +
+  return 4 * a256(sizeof(int) * (nbins + 1)) + a256(sizeof(float4) * (size_t)rec_capacity(np, nbins)) + 256 +
          a256(sizeof(int2) * (size_t)(np / BIN_PART + 1)) + a256(scan_tmp_bytes(nbins + 1)) + 256;
 }
 size_t psc_bin_workspace_bytes(int64_t np, int N) { return psc_bin_workspace_bytes_slab(np, N, N); }
+
+static int scan_bins(const BinLayout &L, const int *in, int *out, cudaStream_t st) {
+  size_t bytes = L.cub_bytes;
+  cudaError_t e = cub::DeviceScan::ExclusiveSum(L.cub_tmp, bytes, in, out, (int)(L.nbins + 1), st);
+  count_launch(2);
+  if (e != cudaSuccess) {
+    set_error("psc_bin_particles: cub scan failed: %s", cudaGetErrorString(e));
+    return PSC_ERR_CUDA;
+  }
+  return PSC_OK;
+}
+
+// exact binning from the per-bin counts in L.counts: base = scan(counts), scatter with fill as the cursor, heavy list
+static int finish_exact(const float *pos, int64_t np, int N, int x0, const BinLayout &L, cudaStream_t st) {
+  int rc = scan_bins(L, L.counts, L.base, st);
+  if (rc != PSC_OK) return rc;
+  PSC_CUDA(cudaMemsetAsync(L.fill, 0, sizeof(int) * (L.nbins + 1), st));
+  if (np > 0) {
+    bin_scatter_kernel<<<grid_for(np, 256, 8), 256, 0, st>>>(pos, np, N, L.NB, x0, L.NBX, L.fill, L.base, L.rec, nullptr);
+    count_launch();
+  }
+  PSC_CUDA(cudaMemsetAsync(L.heavy_count, 0, sizeof(int), st));
+  bin_heavy_list_kernel<<<(int)((L.nbins + 255) / 256), 256, 0, st>>>(L.fill, (int)L.nbins, L.heavy_count, L.heavy,
+                                                                     L.heavy_cap);
+  count_launch();
+  PSC_CHECK_LAUNCH();
+  return PSC_OK;
+}
 
 int psc_bin_particles_slab(const float *pos, int64_t np, int N, int x0, int nxl, void *scratch, size_t scratch_bytes,
                            void *stream) {
@@ -641,34 +759,27 @@ int psc_bin_particles_slab(const float *pos, int64_t np, int N, int x0, int nxl,
   cudaStream_t st = as_stream(stream);
   PSC_CUDA(cudaMemsetAsync(L.counts, 0, sizeof(int) * (L.nbins + 1), st));
   if (np > 0) {
-    bin_count_kernel<<<grid_for(np, 256, 8), 256, 0, st>>>(pos, np, N, L.NB, x0, L.NBX, L.counts);
+    bin_count_kernel<<<grid_for(np, 256, 8), 256, 0, st>>>(pos, np, N, L.NB, x0, L.NBX, L.counts, nullptr);
     count_launch();
   }
-  cudaError_t e = cub::DeviceScan::ExclusiveSum(L.cub_tmp, L.cub_bytes, L.counts, L.offsets, (int)(L.nbins + 1), st);
-  count_launch(2);
-  if (e != cudaSuccess) {
-    set_error("psc_bin_particles: cub scan failed: %s", cudaGetErrorString(e));
-    return PSC_ERR_CUDA;
-  }
-  PSC_CUDA(cudaMemsetAsync(L.heavy_count, 0, sizeof(int), st));
-  bin_heavy_list_kernel<<<(int)((L.nbins + 255) / 256), 256, 0, st>>>(L.offsets, (int)L.nbins, L.heavy_count, L.heavy,
-                                                                     L.heavy_cap);
-  count_launch();
-  if (np > 0) {
-    bin_scatter_kernel<<<grid_for(np, 256, 8), 256, 0, st>>>(pos, np, N, L.NB, x0, L.NBX, L.counts, L.offsets, L.rec);
-    count_launch();
-  }
-  PSC_CHECK_LAUNCH();
-  return PSC_OK;
+  return finish_exact(pos, np, N, x0, L, st);
 }
 int psc_bin_particles(const float *pos, int64_t np, int N, void *scratch, size_t scratch_bytes, void *stream) {
   return psc_bin_particles_slab(pos, np, N, 0, N, scratch, scratch_bytes, stream);
 }
 
+/* mode 0: kick + drift + wrap + per-bin COUNT of the new positions (psc_bin_particles_counted(mode 0) then scans and
+ * scatters).  mode 1: DIRECT scatter -- `scratch` still holds the fill of the previous step's binning of (about) the
+ * same particles: the bins get that fill + 1/8 + 32 records of room and every particle drops its record straight into
+ * its bin (no count pass, no second read of the positions); psc_bin_particles_counted(mode 1) finishes, redoing the
+ * exact binning on the device when a bin ran out of room.  zero_counts = 0 for the later chunks of a chunked upload
+ * (row0 = global row of pos[0]). */
 int psc_kick_drift_wrap_count(float *pos, float *vel, const float *acc, int64_t np, float half_dt, double dt,
                               int dt_is_f64, int N, int64_t np_total, void *scratch, size_t scratch_bytes,
-                              int zero_counts, void *stream) {
+                              int zero_counts, int mode, int64_t row0, void *stream) {
   PSC_CHECK_ARG(np >= 0 && np <= np_total && np_total < ((int64_t)1 << 31), "np out of range");
+  PSC_CHECK_ARG(row0 >= 0 && row0 + np <= np_total, "row0 out of range");
+  PSC_CHECK_ARG(mode == 0 || mode == 1, "mode must be 0 (count) or 1 (direct scatter)");
   PSC_CHECK_ARG(slab_ok(N, 0, N), "N must be a multiple of 8");
   PSC_CHECK_ARG(scratch && ((uintptr_t)scratch & 255) == 0, "scratch must be 256-byte aligned");
   BinLayout L;
@@ -677,22 +788,43 @@ int psc_kick_drift_wrap_count(float *pos, float *vel, const float *acc, int64_t 
     return PSC_ERR_WORKSPACE;
   }
   cudaStream_t st = as_stream(stream);
-  if (zero_counts) PSC_CUDA(cudaMemsetAsync(L.counts, 0, sizeof(int) * (L.nbins + 1), st));
+  if (zero_counts) {
+    if (mode == 1) {
+      // room for every bin from the previous step's fill, then fresh cursors
+      bin_caps_kernel<<<(int)((L.nbins + 256) / 256), 256, 0, st>>>(L.fill, (int)L.nbins, np_total, L.tmp);
+      count_launch();
+      int rc = scan_bins(L, L.tmp, L.base, st);
+      if (rc != PSC_OK) return rc;
+      PSC_CUDA(cudaMemsetAsync(L.fill, 0, sizeof(int) * (L.nbins + 1), st));
+      PSC_CUDA(cudaMemsetAsync(L.overflow, 0, sizeof(int), st));
+    } else {
+      PSC_CUDA(cudaMemsetAsync(L.counts, 0, sizeof(int) * (L.nbins + 1), st));
+    }
+  }
   if (np == 0) return PSC_OK;
   PSC_CHECK_ARG(pos && vel && acc, "null pointer");
   PSC_CHECK_ARG((((uintptr_t)pos | (uintptr_t)vel | (uintptr_t)acc) & 15) == 0, "pointers must be 16-byte aligned");
   const int g = grid_for((np + 3) / 4, 256, 8);
-  if (dt_is_f64)
-    kick_drift_wrap_count_kernel<true><<<g, 256, 0, st>>>(pos, vel, acc, np, half_dt, dt, N, L.NB, L.counts);
-  else
-    kick_drift_wrap_count_kernel<false><<<g, 256, 0, st>>>(pos, vel, acc, np, half_dt, dt, N, L.NB, L.counts);
+#define PSC_KDW(F64, DIRECT, CNT)                                                                                 \
+  kick_drift_wrap_count_kernel<F64, DIRECT><<<g, 256, 0, st>>>(pos, vel, acc, np, half_dt, dt, N, L.NB, CNT, L.base, \
+                                                               L.nrec, L.rec, (int)row0, L.overflow)
+  if (mode == 1) {
+    if (dt_is_f64) PSC_KDW(true, true, L.fill);
+    else PSC_KDW(false, true, L.fill);
+  } else {
+    if (dt_is_f64) PSC_KDW(true, false, L.counts);
+    else PSC_KDW(false, false, L.counts);
+  }
+#undef PSC_KDW
   count_launch();
   PSC_CHECK_LAUNCH();
   return PSC_OK;
 }
 
-int psc_bin_particles_counted(const float *pos, int64_t np, int N, void *scratch, size_t scratch_bytes, void *stream) {
+int psc_bin_particles_counted(const float *pos, int64_t np, int N, void *scratch, size_t scratch_bytes, int mode,
+                              void *stream) {
   PSC_CHECK_ARG(np >= 0 && np < ((int64_t)1 << 31), "np out of range");
+  PSC_CHECK_ARG(mode == 0 || mode == 1, "mode must be 0 (count) or 1 (direct scatter)");
   PSC_CHECK_ARG(slab_ok(N, 0, N), "N must be a multiple of 8");
   PSC_CHECK_ARG(scratch && (pos || np == 0), "null pointer");
   BinLayout L;
@@ -701,20 +833,28 @@ int psc_bin_particles_counted(const float *pos, int64_t np, int N, void *scratch
     return PSC_ERR_WORKSPACE;
   }
   cudaStream_t st = as_stream(stream);
-  cudaError_t e = cub::DeviceScan::ExclusiveSum(L.cub_tmp, L.cub_bytes, L.counts, L.offsets, (int)(L.nbins + 1), st);
-  count_launch(2);
-  if (e != cudaSuccess) {
-    set_error("psc_bin_particles_counted: cub scan failed: %s", cudaGetErrorString(e));
-    return PSC_ERR_CUDA;
-  }
-  PSC_CUDA(cudaMemsetAsync(L.heavy_count, 0, sizeof(int), st));
-  bin_heavy_list_kernel<<<(int)((L.nbins + 255) / 256), 256, 0, st>>>(L.offsets, (int)L.nbins, L.heavy_count, L.heavy,
-                                                                     L.heavy_cap);
-  count_launch();
+  if (mode == 0) return finish_exact(pos, np, N, 0, L, st);
+  // direct scatter: the records are in place unless a bin overflowed; in that case (flag on the device, no host
+  // round trip) the same stream redoes the exact binning: count -> scan -> adopt offsets -> scatter.  Every kernel
+  // of the fall-back returns at once when the flag is clear; the 1 MB scan runs either way.
+  PSC_CUDA(cudaMemsetAsync(L.counts, 0, sizeof(int) * (L.nbins + 1), st));
   if (np > 0) {
-    bin_scatter_kernel<<<grid_for(np, 256, 8), 256, 0, st>>>(pos, np, N, L.NB, 0, L.NBX, L.counts, L.offsets, L.rec);
+    bin_count_kernel<<<grid_for(np, 256, 8), 256, 0, st>>>(pos, np, N, L.NB, 0, L.NBX, L.counts, L.overflow);
     count_launch();
   }
+  int rc = scan_bins(L, L.counts, L.tmp, st);
+  if (rc != PSC_OK) return rc;
+  bin_adopt_kernel<<<(int)((L.nbins + 256) / 256), 256, 0, st>>>(L.overflow, L.tmp, (int)L.nbins, L.base, L.fill);
+  count_launch();
+  if (np > 0) {
+    bin_scatter_kernel<<<grid_for(np, 256, 8), 256, 0, st>>>(pos, np, N, L.NB, 0, L.NBX, L.fill, L.base, L.rec,
+                                                             L.overflow);
+    count_launch();
+  }
+  PSC_CUDA(cudaMemsetAsync(L.heavy_count, 0, sizeof(int), st));
+  bin_heavy_list_kernel<<<(int)((L.nbins + 255) / 256), 256, 0, st>>>(L.fill, (int)L.nbins, L.heavy_count, L.heavy,
+                                                                     L.heavy_cap);
+  count_launch();
   PSC_CHECK_LAUNCH();
   return PSC_OK;
 }
@@ -742,9 +882,9 @@ static int deposit_binned_impl(const void *scratch, size_t scratch_bytes, int64_
     const int grid = (int)L.nbins;
     const int hgrid = num_sms() * 4;   // persistent CTAs over the heavy-bin parts (exit at once when there are none)
 #define PSC_DEP(S)                                                                                                   \
-  deposit_binned_kernel<S><<<grid, BD_WARPS * 32, 0, st>>>(L.rec, L.offsets, N, L.NB, x0, ghost, nxa, scale, f1, f2,  \
-                                                           rho);                                                     \
-  deposit_heavy_kernel<S><<<hgrid, BD_WARPS * 32, 0, st>>>(L.rec, L.offsets, L.heavy_count, L.heavy, L.heavy_cap, N, \
+  deposit_binned_kernel<S><<<grid, BD_WARPS * 32, 0, st>>>(L.rec, L.base, L.fill, N, L.NB, x0, ghost, nxa, scale, f1, \
+                                                           f2, rho);                                                 \
+  deposit_heavy_kernel<S><<<hgrid, BD_WARPS * 32, 0, st>>>(L.rec, L.base, L.fill, L.heavy_count, L.heavy, L.heavy_cap, N, \
                                                           L.NB, x0, ghost, nxa, scale, f1, f2, rho)
     if (scheme == PSC_TSC) { PSC_DEP(PSC_TSC); }
     else if (scheme == PSC_CIC) { PSC_DEP(PSC_CIC); }
@@ -788,9 +928,9 @@ int psc_interp_kick4_binned(const float *force4, const void *scratch, size_t scr
   const float4 *f4 = reinterpret_cast<const float4 *>(force4);
   const int grid = (int)L.nbins + L.heavy_cap;
   if (scheme == PSC_TSC)
-    interp_kick4_binned_kernel<PSC_TSC><<<grid, BI_THREADS, 0, st>>>(f4, L.rec, L.offsets, vel, acc, N, L.NB, 0, 0, N, half_dt, maxout, (int)L.nbins, L.heavy_count, L.heavy);
+    interp_kick4_binned_kernel<PSC_TSC><<<grid, BI_THREADS, 0, st>>>(f4, L.rec, L.base, L.fill, vel, acc, N, L.NB, 0, 0, N, half_dt, maxout, (int)L.nbins, L.heavy_count, L.heavy);
   else
-    interp_kick4_binned_kernel<PSC_CIC><<<grid, BI_THREADS, 0, st>>>(f4, L.rec, L.offsets, vel, acc, N, L.NB, 0, 0, N, half_dt, maxout, (int)L.nbins, L.heavy_count, L.heavy);
+    interp_kick4_binned_kernel<PSC_CIC><<<grid, BI_THREADS, 0, st>>>(f4, L.rec, L.base, L.fill, vel, acc, N, L.NB, 0, 0, N, half_dt, maxout, (int)L.nbins, L.heavy_count, L.heavy);
   count_launch();
   PSC_CHECK_LAUNCH();
   return PSC_OK;
@@ -812,7 +952,7 @@ static int interp_kick_phi_impl(const float *phi, const float *u, float f, int f
   const int grid = (int)L.nbins + L.heavy_cap;   // the CTAs of unused heavy-part slots exit at once
   const int nxa = nxl + 2 * ghost;
 #define PSC_IKP(S, O)                                                                                            \
-  interp_kick_phi_binned_kernel<S, O><<<grid, BP_THREADS, 0, st>>>(phi, u, f, fr_n, L.rec, L.offsets, vel, acc, \
+  interp_kick_phi_binned_kernel<S, O><<<grid, BP_THREADS, 0, st>>>(phi, u, f, fr_n, L.rec, L.base, L.fill, vel, acc, \
                                                                    N, L.NB, x0, ghost, nxa, half_dt, maxout,    \
                                                                    (int)L.nbins, L.heavy_count, L.heavy)
 #define PSC_IKP_O(S)               \

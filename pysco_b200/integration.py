@@ -92,7 +92,7 @@ def _binned_for(pos, param):
     N = 2 ** param["ncoarse"]
     n = pos.shape[0]
     if mesh.can_bin(N, n) and pos.data_ptr() % 16 == 0:
-        return mesh.alloc_binned(n, N)
+        return mesh.step_binned(n, N)
     return None
 
 
@@ -176,7 +176,7 @@ def _leapfrog_pinned(position, velocity, acceleration, potential, additional_fie
         cur.wait_event(landed)
         if counted is not None:
             mesh.kick_drift_wrap_count(pos[a:b], vel[a:b], acc[a:b], half_dt, dt, dt_is_f64, counted,
-                                       zero_counts=(a == 0))
+                                       zero_counts=(a == 0), row0=a)
         else:
             _lib.check(lib.psc_kick_drift_wrap(_lib.ptr(pos[a:b]), _lib.ptr(vel[a:b]), _lib.ptr(acc[a:b]), b - a,
                                                float(half_dt), float(dt), dt_is_f64, _lib.stream()))

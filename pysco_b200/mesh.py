@@ -7,11 +7,15 @@ from . import _lib
 
 
 class Binned:
-    """Per-step shadow binning of the particles into 8^3-cell bins (csrc/binned.cu): bin offsets, a binned
-    copy of the positions and the source row of every binned particle, in one device scratch buffer."""
+    """Per-step shadow binning of the particles into 8^3-cell bins (csrc/binned.cu): per-bin first record / fill, a
+    binned copy of the positions and the source row of every binned particle, in one device scratch buffer.
+    ready: the scratch holds the fill of a finished binning, which the next step's kick+drift+wrap can use to drop its
+    records straight into the bins (direct scatter, psc_kick_drift_wrap_count mode 1)."""
 
     def __init__(self, scratch, np_, N):
         self.scratch, self.np, self.N = scratch, np_, N
+        self.ready = False
+        self.mode = 0
 
 
 def can_bin(N, np_):
@@ -25,18 +29,42 @@ def alloc_binned(np_, ncells_1d):
     return Binned(_lib.empty((nbytes,), torch.uint8), int(np_), N)
 
 
-def kick_drift_wrap_count(pos, vel, acc, half_dt, dt, dt_is_f64, binned, zero_counts=True):
-    """integration.py:250-258 on (a chunk of) the particles + bin counts of the new positions into `binned`."""
+_step_binned = {}
+
+
+def step_binned(np_, ncells_1d):
+    """The persistent Binned of the time loop for (device, N, np): kept from step to step so that the fill of one
+    step's binning sizes the bins of the next step's direct scatter.  PSC_NO_DIRECT_SCATTER=1 restores the count ->
+    scan -> scatter binning of every step."""
+    import os
+    key = (torch.cuda.current_device(), int(ncells_1d), int(np_))
+    b = _step_binned.get(key)
+    if b is None:
+        _step_binned.clear()          # one time loop at a time: do not hold scratch of finished runs
+        b = _step_binned[key] = alloc_binned(np_, ncells_1d)
+    if os.environ.get("PSC_NO_DIRECT_SCATTER"):
+        b.ready = False
+    return b
+
+
+def kick_drift_wrap_count(pos, vel, acc, half_dt, dt, dt_is_f64, binned, zero_counts=True, row0=0):
+    """integration.py:250-258 on (a chunk of) the particles + binning of the new positions into `binned`: per-bin counts
+    (binned.ready False) or the records themselves (direct scatter, binned.ready True)."""
+    if zero_counts:
+        binned.mode = 1 if binned.ready else 0
     _lib.check(_lib.load().psc_kick_drift_wrap_count(
         _lib.ptr(pos), _lib.ptr(vel), _lib.ptr(acc), pos.shape[0], float(half_dt), float(dt), int(dt_is_f64),
-        binned.N, binned.np, _lib.ptr(binned.scratch), binned.scratch.numel(), int(zero_counts), _lib.stream()))
+        binned.N, binned.np, _lib.ptr(binned.scratch), binned.scratch.numel(), int(zero_counts), binned.mode, int(row0),
+        _lib.stream()))
 
 
 def finish_binning(position, binned):
-    """scan + scatter from counts that are already in `binned`"""
+    """the rest of the binning started by kick_drift_wrap_count: scan + scatter from the counts (mode 0), or the
+    heavy-bin list and the on-device overflow fall-back of the direct scatter (mode 1)"""
     _lib.check(_lib.load().psc_bin_particles_counted(_lib.ptr(position), position.shape[0], binned.N,
-                                                     _lib.ptr(binned.scratch), binned.scratch.numel(),
+                                                     _lib.ptr(binned.scratch), binned.scratch.numel(), binned.mode,
                                                      _lib.stream()))
+    binned.ready = True
     return binned
 
 

@@ -40,6 +40,36 @@ def _a256(x):
     return (x + 255) & ~255
 
 
+def _layout(bn, n, N):
+    """(fill, base, records) of a Binned scratch: counts | fill | base | tmp (nbins + 1 ints each, 256-byte aligned),
+    then the records (csrc/binned.cu: bin_layout)"""
+    nbins = (N // 8) ** 3
+    raw = bn.scratch.cpu().numpy()
+    o = _a256(4 * (nbins + 1))
+    fill = raw[o: o + 4 * (nbins + 1)].view(np.int32)
+    base = raw[2 * o: 2 * o + 4 * (nbins + 1)].view(np.int32)
+    nrec = n + n // 8 + 40 * nbins + 64
+    rec = raw[4 * o: 4 * o + 16 * nrec].view(np.float32).reshape(nrec, 4)
+    return fill, base, rec
+
+
+def _check_binning(bn, pos, N, exact):
+    """every bin's records are exactly the particles of that bin (positions bit-exact, rows a permutation)"""
+    n = len(pos)
+    nbins = (N // 8) ** 3
+    fill, base, rec = _layout(bn, n, N)
+    key = _bin_key(pos, N)
+    counts = np.bincount(key, minlength=nbins)
+    assert np.array_equal(fill[:nbins], counts)
+    assert np.all(np.diff(base.astype(np.int64)) >= counts if not exact else np.diff(base.astype(np.int64)) == counts)
+    assert base[0] == 0
+    sel = np.concatenate([np.arange(base[b], base[b] + fill[b]) for b in np.nonzero(counts)[0]]) if n else np.zeros(0, int)
+    rows = rec[sel, 3].copy().view(np.int32)
+    assert np.array_equal(np.sort(rows), np.arange(n))
+    assert np.array_equal(rec[sel, :3], pos[rows])
+    assert np.array_equal(key[rows], np.repeat(np.nonzero(counts)[0], counts[np.nonzero(counts)[0]]))
+
+
 def _bin_key(pos, N):
     """(bi * NB + bj) * NB + bk: the bin of binned.cu (bin_of)"""
     c = np.minimum((pos * np.float32(N)).astype(np.int64), N - 1)
@@ -60,30 +90,26 @@ def _mixed_particles(N, seed=3):
 
 @pytest.mark.parametrize("kind", ["lattice", "mixed"])
 def test_binning_invariants(psc, kind):
-    """offsets[] is the exclusive scan of the per-bin counts, the records are a permutation of the rows, every record
-    sits in the range of its own bin and carries the position of its source row (bit-exact)."""
+    """base[] is the exclusive scan of the per-bin counts, fill[] the counts, the records of a bin are exactly its
+    particles (a permutation of the rows, positions bit-exact)"""
     N = 64
     pos = cases.lattice_particles(N, 0.3, seed=5) if kind == "lattice" else _mixed_particles(N)
-    n = len(pos)
-    tp = _cuda(pos)
-    bn = psc.mesh.bin_particles(tp, N)
-    nbins = (N // 8) ** 3
-    raw = bn.scratch.cpu().numpy()
-    o = _a256(4 * (nbins + 1))
-    offsets = raw[o: o + 4 * (nbins + 1)].view(np.int32)
-    rec = raw[2 * o: 2 * o + 16 * n].view(np.float32).reshape(n, 4)
-    rows = rec[:, 3].copy().view(np.int32)
-    key = _bin_key(pos, N)
-    counts = np.bincount(key, minlength=nbins)
-    assert offsets[0] == 0 and offsets[nbins] == n
-    assert np.array_equal(np.diff(offsets.astype(np.int64)), counts)
-    assert np.array_equal(np.sort(rows), np.arange(n))
-    assert np.array_equal(rec[:, :3], pos[rows])
-    assert np.all(np.diff(key[rows]) >= 0)
+    bn = psc.mesh.bin_particles(_cuda(pos), N)
+    _check_binning(bn, pos, N, exact=True)
 
 
-def test_kick_drift_count_matches_separate_binning(psc, orc):
-    """the count pass folded into kick+drift+wrap produces the same binning as psc_bin_particles of the new positions"""
+def _kdw_reference(orc, pos, vel, acc, dt):
+    p, v = pos.copy(), vel.copy()
+    orc.utils.add_vector_scalar_inplace(v, acc, -np.float32(0.5 * dt))
+    orc.utils.add_vector_scalar_inplace(p, v, dt)
+    orc.utils.periodic_wrap(p)
+    return p, v
+
+
+def test_kick_drift_count_then_direct_scatter(psc, orc):
+    """step 1: the count pass folded into kick+drift+wrap (mode 0) gives the binning psc_bin_particles gives; step 2 on
+    the same scratch: direct scatter (mode 1) -- no count pass, the records land in bins sized from step 1's fill;
+    step 3: direct scatter in two chunks (row0), as the pinned-host pipeline calls it"""
     import torch
     N = 32
     n = 50003   # not a multiple of 4: the scalar tail of the fused kernel
@@ -92,23 +118,58 @@ def test_kick_drift_count_matches_separate_binning(psc, orc):
     tp, tv, ta = _cuda(pos), _cuda(vel), _cuda(acc)
     bn = psc.mesh.alloc_binned(n, N)
     dt = np.float32(0.21)
-    psc.mesh.kick_drift_wrap_count(tp, tv, ta, np.float32(0.5 * dt), dt, 0, bn)
+    for step in range(3):
+        assert bn.ready == (step > 0)
+        if step < 2:
+            psc.mesh.kick_drift_wrap_count(tp, tv, ta, np.float32(0.5 * dt), dt, 0, bn)
+        else:
+            h = 20000   # a multiple of 4 keeps the second chunk 16-byte aligned
+            psc.mesh.kick_drift_wrap_count(tp[:h], tv[:h], ta[:h], np.float32(0.5 * dt), dt, 0, bn, zero_counts=True)
+            psc.mesh.kick_drift_wrap_count(tp[h:], tv[h:], ta[h:], np.float32(0.5 * dt), dt, 0, bn, zero_counts=False,
+                                           row0=h)
+        assert bn.mode == (1 if step > 0 else 0)
+        psc.mesh.finish_binning(tp, bn)
+        pos, vel = _kdw_reference(orc, pos, vel, acc, dt)
+        got = tp.cpu().numpy()
+        assert np.max(np.abs(got - pos)) <= 1.2e-7 * (step + 1)     # one ulp below 1.0 per step (fused multiply-add)
+        pos, vel = got, tv.cpu().numpy()                            # follow the device's bits from here on
+        _check_binning(bn, pos, N, exact=(step == 0))
+        rho = psc.mesh.deposit_rhs(tp, N, psc._lib.TSC, 1.0, 1.0, 0.0, bn)
+        assert_close(rho.cpu().numpy(), orc.mesh.TSC_seq(pos, N), TOL, f"deposit, step {step}")
+    torch.cuda.synchronize()
+
+
+def test_direct_scatter_overflow_falls_back_to_exact_binning(psc, orc):
+    """the particles move far more than the slack of the bins allows (here: everything collapses into a corner
+    between two steps): the direct scatter overflows, the device redoes the exact binning, nothing is lost"""
+    N = 32
+    n = 40000
+    pos = cases.particles(N, n, seed=31)
+    vel = np.zeros((n, 3), dtype=np.float32)
+    acc = np.zeros((n, 3), dtype=np.float32)
+    tp, tv, ta = _cuda(pos), _cuda(vel), _cuda(acc)
+    bn = psc.mesh.alloc_binned(n, N)
+    psc.mesh.kick_drift_wrap_count(tp, tv, ta, np.float32(0), np.float32(0), 0, bn)
     psc.mesh.finish_binning(tp, bn)
-    p, v = pos.copy(), vel.copy()
-    orc.utils.add_vector_scalar_inplace(v, acc, -np.float32(0.5 * dt))
-    orc.utils.add_vector_scalar_inplace(p, v, dt)
-    orc.utils.periodic_wrap(p)
-    assert np.max(np.abs(tp.cpu().numpy() - p)) <= 1.2e-7      # one ulp below 1.0 (fused multiply-add in the drift)
-    ref = psc.mesh.bin_particles(tp, N)
+    _check_binning(bn, pos, N, exact=True)
+    tp.mul_(0.2)                                            # all particles into 1/125 of the box
+    pos2 = tp.cpu().numpy()
+    psc.mesh.kick_drift_wrap_count(tp, tv, ta, np.float32(0), np.float32(0), 0, bn)   # mode 1, must overflow
+    assert bn.mode == 1
+    psc.mesh.finish_binning(tp, bn)
     nbins = (N // 8) ** 3
     o = _a256(4 * (nbins + 1))
-    a = bn.scratch[o: o + 4 * (nbins + 1)].cpu().numpy().view(np.int32)
-    b = ref.scratch[o: o + 4 * (nbins + 1)].cpu().numpy().view(np.int32)
-    assert np.array_equal(a, b)
-    rho_a = psc.mesh.deposit_rhs(tp, N, psc._lib.TSC, 1.0, 1.0, 0.0, bn)
-    rho_b = psc.mesh.deposit_rhs(tp, N, psc._lib.TSC, 1.0, 1.0, 0.0, ref)
-    assert_close(rho_a.cpu().numpy(), rho_b.cpu().numpy(), 1e-6, "deposit from the fused count")
-    torch.cuda.synchronize()
+    flag_off = 4 * o + _a256(16 * (n + n // 8 + 40 * nbins + 64))
+    assert bn.scratch[flag_off: flag_off + 4].cpu().numpy().view(np.int32)[0] == 1, "the test must overflow"
+    _check_binning(bn, pos2, N, exact=True)
+    rho = psc.mesh.deposit_rhs(tp, N, psc._lib.TSC, 1.0, 1.0, 0.0, bn)
+    exact = orc.mesh.deposit_f64(pos2, N, 2)
+    assert_close(rho.cpu().numpy(), exact, max(TOL, 3 * rel_err(orc.mesh.TSC_seq(pos2, N), exact)), "deposit after overflow")
+    # and the next step is a direct scatter again, now with room for the collapsed distribution
+    psc.mesh.kick_drift_wrap_count(tp, tv, ta, np.float32(0), np.float32(0), 0, bn)
+    psc.mesh.finish_binning(tp, bn)
+    assert bn.scratch[flag_off: flag_off + 4].cpu().numpy().view(np.int32)[0] == 0
+    _check_binning(bn, pos2, N, exact=False)
 
 
 @pytest.mark.parametrize("scheme", ["TSC", "CIC", "NGP"])
@@ -161,9 +222,8 @@ def test_positions_on_the_box_edge_do_not_leave_the_grid(psc, orc):
     tp = _cuda(pos)
     bn = psc.mesh.bin_particles(tp, N)
     nbins = (N // 8) ** 3
-    o = _a256(4 * (nbins + 1))
-    offsets = bn.scratch[o: o + 4 * (nbins + 1)].cpu().numpy().view(np.int32)
-    assert offsets[nbins] == len(pos) and np.all(np.diff(offsets) >= 0)
+    fill, base, _ = _layout(bn, len(pos), N)
+    assert base[nbins] == len(pos) and np.all(np.diff(base) >= 0) and fill[:nbins].sum() == len(pos)
     rho = psc.mesh.deposit_rhs(tp, N, psc._lib.TSC, 1.0, 1.0, 0.0, bn)
     assert abs(float(rho.sum(dtype=__import__("torch").float64)) - len(pos)) < 1e-5 * len(pos)
 

@@ -67,15 +67,29 @@ for name, p in cases.items():
     t_int = timeit(lambda: mesh.interp_kick_phi(phi, None, 0.0, 0, 5, p, v2, 2, 0.0, bn))
     out.append(f"grad+interp+kick {t_int:6.3f} ms")
     print(" | ".join(out), flush=True)
-# kick + drift + wrap + per-cell count, then scan + scatter (the two halves of the sort inside a step)
+# kick + drift + wrap + binning inside a step: count -> scan -> scatter (mode 0) against the direct scatter (mode 1)
 p = pos_mor.clone()
 v = vel.clone()
+acc0 = torch.zeros_like(acc)
 bn = mesh.alloc_binned(n, N)
-t_kdw = timeit(lambda: mesh.kick_drift_wrap_count(p, v, acc, np.float32(1e-3), np.float32(1e-2), 0, bn))
-mesh.kick_drift_wrap_count(p, v, acc, np.float32(1e-3), np.float32(1e-2), 0, bn)
-e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-e0.record()
-mesh.finish_binning(p, bn)
-e1.record()
-torch.cuda.synchronize()
-print(f"N={N} kick+drift+wrap+count {t_kdw:6.3f} ms | scan+scatter {e0.elapsed_time(e1):6.3f} ms", flush=True)
+
+
+def pair(events):
+    e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    e[0].record()
+    mesh.kick_drift_wrap_count(p, v, acc0, np.float32(0), np.float32(1e-2), 0, bn)
+    e[1].record()
+    mesh.finish_binning(p, bn)
+    e[2].record()
+    torch.cuda.synchronize()
+    events.append((e[0].elapsed_time(e[1]), e[1].elapsed_time(e[2])))
+
+
+for mode in (0, 1):
+    ev = []
+    for _ in range(6):
+        bn.ready = bool(mode)
+        pair(ev)
+    k, f = min(x[0] for x in ev[1:]), min(x[1] for x in ev[1:])
+    print(f"N={N} mode {mode} ({'direct scatter' if mode else 'count -> scan -> scatter'}): kick+drift+wrap(+bin) {k:6.3f} ms"
+          f" | finish {f:6.3f} ms | sum {k + f:6.3f} ms", flush=True)
