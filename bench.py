@@ -53,6 +53,11 @@ ALGO_BYTES = {
     "psc_interp_kick_phi_binned": 76.0,   # gradient (16) + interpolation/kick (60) in one kernel
     "psc_deposit_binned": 16.0,
     "psc_bin_particles": 0.0,
+    # the bin-ordered time loop: kick + drift + wrap fused with the re-sort of the particle arrays (60 B algorithmic;
+    # the second read of x, v, a and the ids are the price of the order, not in the 176 B budget)
+    "psc_step_sort": 60.0,
+    "psc_deposit_sorted": 16.0,
+    "psc_interp_kick_phi_sorted": 76.0,
     # x-slab path (every kernel works on N^3 / P particles or cells)
     "psc_kick_drift_wrap_slab": 60.0,      # kick + drift + wrap + leaver detection
     "psc_bin_particles_slab": 0.0,

@@ -118,6 +118,25 @@ int psc_kick_drift_wrap_count(float *pos, float *vel, const float *acc, int64_t 
 int psc_bin_particles_counted(const float *pos, int64_t np, int N, void *scratch, size_t scratch_bytes, int mode,
                               void *stream);
 
+/* ---- the time loop on particle arrays kept in BIN order (no binned copy, no source-row indirection).
+ * psc_step_sort: integration.leapfrog's first half (integration.py:250-258: v -= half_dt a; x += dt v; periodic_wrap)
+ * fused with a counting sort of the particles into 8^3-cell bins: pass 1 counts the NEW positions (nothing written),
+ * scan, pass 2 redoes the arithmetic and writes x', v' and the particle's id (ids == NULL: the input row) to its row of
+ * the bin-ordered output arrays (out of place).  `scratch` (psc_sorted_workspace_bytes) then holds the bin table that
+ * psc_deposit_sorted (mesh.TSC/CIC/NGP + rescale + rhs_poisson's affine map, as psc_deposit_binned) and
+ * psc_interp_kick_phi_sorted (as psc_interp_kick_phi_binned; vel / acc rows are the rows of pos_sorted) consume.
+ * psc_scatter3_by_id: out[ids[n]] = in[n], the way back to the reference's particle order. */
+size_t psc_sorted_workspace_bytes(int64_t np, int N);
+int psc_step_sort(const float *pos, const float *vel, const float *acc, const int *ids, int64_t np, float half_dt,
+                  double dt, int dt_is_f64, int N, void *scratch, size_t scratch_bytes, float *pos_out, float *vel_out,
+                  int *ids_out, void *stream);
+int psc_deposit_sorted(const float *pos_sorted, const void *scratch, size_t scratch_bytes, int64_t np, int N, int scheme,
+                       float scale, float f1, float f2, float *rho, void *stream);
+int psc_interp_kick_phi_sorted(const float *phi, const float *u, float f, int fr_n, int order, const float *pos_sorted,
+                               const void *scratch, size_t scratch_bytes, float *vel_sorted, float *acc_sorted,
+                               int64_t np, int N, int scheme, float half_dt, float *maxout, void *stream);
+int psc_scatter3_by_id(const int *ids, const float *in, float *out, int64_t np, void *stream);
+
 /* mesh.derivative / derivative_fR (mesh.py:639-2174) fused into the binned interpolation + kick: every bin's CTA
  * derives its force tile from the potential phi (and, for f(R), the scalaron u: phi + f * u^(fr_n+1)) in shared
  * memory, so neither the gradient kernel nor the force grid exist in the step.  fr_n = 0: plain. */

@@ -38,6 +38,11 @@ SIGNATURES = {
     "psc_deposit_binned": [_vp, _sz, _i64, _i, _i, _f, _f, _f, _vp, _vp],
     "psc_interp_kick4_binned": [_vp, _vp, _sz, _vp, _vp, _i64, _i, _i, _f, _vp, _vp],
     "psc_interp_kick_phi_binned": [_vp, _vp, _f, _i, _i, _vp, _sz, _vp, _vp, _i64, _i, _i, _f, _vp, _vp],
+    "psc_sorted_workspace_bytes": [_i64, _i],
+    "psc_step_sort": [_vp, _vp, _vp, _vp, _i64, _f, _d, _i, _i, _vp, _sz, _vp, _vp, _vp, _vp],
+    "psc_deposit_sorted": [_vp, _vp, _sz, _i64, _i, _i, _f, _f, _f, _vp, _vp],
+    "psc_interp_kick_phi_sorted": [_vp, _vp, _f, _i, _i, _vp, _vp, _sz, _vp, _vp, _i64, _i, _i, _f, _vp, _vp],
+    "psc_scatter3_by_id": [_vp, _vp, _vp, _i64, _vp],
     "psc_bin_workspace_bytes_slab": [_i64, _i, _i],
     "psc_bin_particles_slab": [_vp, _i64, _i, _i, _i, _vp, _sz, _vp],
     "psc_deposit_binned_slab": [_vp, _sz, _i64, _i, _i, _i, _i, _vp, _vp],
@@ -99,7 +104,7 @@ SIGNATURES = {
     "psc_box_initialise_potential_fr": [_vp, _f, _i, _i, _i, _vp, _vp],
 }
 _RESTYPES = {"psc_mg_q_device_ptr": C.c_void_p, "psc_last_error": C.c_char_p, "psc_launch_count": _i64, "psc_argsort_workspace_bytes": _sz,
-             "psc_bin_workspace_bytes": _sz, "psc_bin_workspace_bytes_slab": _sz,
+             "psc_bin_workspace_bytes": _sz, "psc_bin_workspace_bytes_slab": _sz, "psc_sorted_workspace_bytes": _sz,
              "psc_slab_fft_workspace_bytes": _sz,
              "psc_fft_plan_workspace_bytes": _sz}
 
@@ -141,7 +146,7 @@ class _Timed:
 
 
 _TIMED = ("psc_morton_keys", "psc_argsort_keys", "psc_gather3", "psc_axpy", "psc_periodic_wrap", "psc_max_abs",
-          "psc_kick_drift_wrap", "psc_kick_drift_wrap_count", "psc_bin_particles_counted", "psc_deposit", "psc_bin_particles", "psc_deposit_binned", "psc_interp_kick4_binned", "psc_interp_kick_phi_binned", "psc_interp", "psc_interp_kick", "psc_interp_kick4", "psc_linear_operator",
+          "psc_kick_drift_wrap", "psc_kick_drift_wrap_count", "psc_bin_particles_counted", "psc_step_sort", "psc_deposit_sorted", "psc_interp_kick_phi_sorted", "psc_scatter3_by_id", "psc_deposit", "psc_bin_particles", "psc_deposit_binned", "psc_interp_kick4_binned", "psc_interp_kick_phi_binned", "psc_interp", "psc_interp_kick", "psc_interp_kick4", "psc_linear_operator",
           "psc_lincomb", "psc_gradient", "psc_fft_r2c", "psc_fft_c2r", "psc_fft_c2r_vec3", "psc_green",
           "psc_grad_green", "psc_pk", "psc_operator", "psc_residual", "psc_restrict_residual",
           "psc_residual_sumsq", "psc_diff_sumsq", "psc_initialise_potential", "psc_gauss_seidel", "psc_gauss_seidel_fused",

@@ -75,14 +75,15 @@ static size_t scan_tmp_bytes(int64_t n) {
 
 static int64_t rec_capacity(int64_t np, int64_t nbins) { return np + np / 8 + 40 * nbins + 64; }
 
-static bool bin_layout(void *scratch, size_t bytes, int64_t np, int N, int x0, int nxl, BinLayout &L) {
+static bool bin_layout(void *scratch, size_t bytes, int64_t np, int N, int x0, int nxl, BinLayout &L,
+                       bool with_rec = true) {
   L.NB = N / BB;
   L.NBX = nxl / BB;
   L.x0 = x0;
   L.nbins = (int64_t)L.NBX * L.NB * L.NB;
   char *p = reinterpret_cast<char *>(scratch);
   size_t off = 0;
-  L.nrec = rec_capacity(np, L.nbins);
+  L.nrec = with_rec ? rec_capacity(np, L.nbins) : 0;   // sorted particle arrays need no binned copy
   L.counts = reinterpret_cast<int *>(p + off); off += a256(sizeof(int) * (L.nbins + 1));
   L.fill = reinterpret_cast<int *>(p + off); off += a256(sizeof(int) * (L.nbins + 1));
   L.base = reinterpret_cast<int *>(p + off); off += a256(sizeof(int) * (L.nbins + 1));
@@ -314,14 +315,166 @@ __global__ void __launch_bounds__(256) bin_scatter_kernel(const float *__restric
   }
 }
 
+// ------------------------------------------------------------------- particle arrays kept in bin order
+// Round 2, after measuring what the shadow binning costs once the source order has decayed (per-particle random
+// velocities: the rows of a bin's particles are spread over the array, the interpolation's v / a accesses by source row
+// become one 32-byte sector per lane -- 5.0 -> 7.3 ms at 512^3): the time loop keeps position / velocity /
+// acceleration THEMSELVES in bin order and re-sorts them every step, fused with the first half of the leapfrog:
+//   pass 1 (PASS = 1)  read x, v, a; form the new position in registers; count it in its bin.  Nothing is written.
+//   scan               base[] = first row of every bin (tight: no gaps, the arrays stay [np, 3]).
+//   pass 2 (PASS = 2)  read x, v, a (+ id) again, redo the same arithmetic (bit-identical), claim the next row of the
+//                      bin and write x', v' (and the particle's id = its row in the reference's order) there.
+// 36 + 40 B read, 28 B written per particle, all streaming; the deposit then reads 12 B and the interpolation 24 + 24 B
+// per particle in bin order -- no binned copy, no source-row indirection anywhere.  The reference's particle order is
+// restored from the ids when somebody asks for it (utils.reference_order: snapshots, NumPy callers, reorder_particles).
+template <bool F64, int PASS>
+__global__ void __launch_bounds__(256) step_sort_kernel(const float *__restrict__ pos, const float *__restrict__ vel,
+                                                        const float *__restrict__ acc, const int *__restrict__ ids,
+                                                        int64_t np, float half_dt, double dt, int N, int NB,
+                                                        int *__restrict__ cnt, const int *__restrict__ bbase,
+                                                        float *__restrict__ pos_out, float *__restrict__ vel_out,
+                                                        int *__restrict__ ids_out) {
+  const float dtf = (float)dt, mh = -half_dt, Nf = (float)N;
+  const int lane = threadIdx.x & 31;
+  const int64_t nq = np >> 2;
+  const float4 *p4 = reinterpret_cast<const float4 *>(pos);
+  const float4 *v4 = reinterpret_cast<const float4 *>(vel);
+  const float4 *a4 = reinterpret_cast<const float4 *>(acc);
+  const int64_t wstride = (((int64_t)gridDim.x * blockDim.x) >> 5) * 32;
+  for (int64_t wb = (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 32; wb < nq; wb += wstride) {
+    const int64_t q = wb + lane;
+    const bool valid = q < nq;
+    float f[12], v[12];
+    int b[4] = {-1 - lane, -1 - lane, -1 - lane, -1 - lane};
+    int id[4] = {0, 0, 0, 0};
+    if (valid) {
+      float a[12];
+#pragma unroll
+      for (int c = 0; c < 3; c++) {
+        const float4 P = __ldg(&p4[3 * q + c]), V = __ldg(&v4[3 * q + c]), A = __ldg(&a4[3 * q + c]);
+        f[4 * c] = P.x; f[4 * c + 1] = P.y; f[4 * c + 2] = P.z; f[4 * c + 3] = P.w;
+        v[4 * c] = V.x; v[4 * c + 1] = V.y; v[4 * c + 2] = V.z; v[4 * c + 3] = V.w;
+        a[4 * c] = A.x; a[4 * c + 1] = A.y; a[4 * c + 2] = A.z; a[4 * c + 3] = A.w;
+      }
+#pragma unroll
+      for (int c = 0; c < 12; c++) {
+        v[c] += mh * a[c];
+        f[c] = F64 ? (float)((double)f[c] + dt * (double)v[c]) : f[c] + dtf * v[c];
+        f[c] = wrap01(f[c]);
+      }
+#pragma unroll
+      for (int r = 0; r < 4; r++) b[r] = bin_of(f[3 * r], f[3 * r + 1], f[3 * r + 2], Nf, NB, 0, NB);
+      if (PASS == 2) {
+        if (ids) {
+          const int4 I = __ldg(reinterpret_cast<const int4 *>(ids) + q);
+          id[0] = I.x; id[1] = I.y; id[2] = I.z; id[3] = I.w;
+        } else {
+#pragma unroll
+          for (int r = 0; r < 4; r++) id[r] = (int)(4 * q) + r;
+        }
+      }
+    }
+    const bool same = b[0] == b[1] && b[1] == b[2] && b[2] == b[3];
+    if (__all_sync(0xffffffffu, same)) {
+      // the common case in a bin-ordered array: one atomic per distinct bin of the warp
+      const unsigned peers = __match_any_sync(0xffffffffu, b[0]);
+      const int leader = __ffs(peers) - 1;
+      int first = 0;
+      if (valid && leader == lane) first = atomicAdd(&cnt[b[0]], 4 * __popc(peers));
+      if (PASS == 2) {
+        first = __shfl_sync(0xffffffffu, first, leader);
+        if (valid) {
+          const size_t slot = (size_t)bbase[b[0]] + first + 4 * __popc(peers & ((1u << lane) - 1u));
+          // four consecutive rows: 48 bytes each of position and velocity, 16-byte aligned (slot is a multiple of 4
+          // only by chance, so plain float stores)
+#pragma unroll
+          for (int c = 0; c < 12; c++) {
+            pos_out[3 * slot + c] = f[c];
+            vel_out[3 * slot + c] = v[c];
+          }
+#pragma unroll
+          for (int r = 0; r < 4; r++) ids_out[slot + r] = id[r];
+        }
+      }
+    } else {
+#pragma unroll
+      for (int r = 0; r < 4; r++) {
+        const unsigned peers = __match_any_sync(0xffffffffu, b[r]);
+        const int leader = __ffs(peers) - 1;
+        int first = 0;
+        if (valid && leader == lane) first = atomicAdd(&cnt[b[r]], __popc(peers));
+        if (PASS == 2) {
+          first = __shfl_sync(0xffffffffu, first, leader);
+          if (valid) {
+            const size_t slot = (size_t)bbase[b[r]] + first + __popc(peers & ((1u << lane) - 1u));
+#pragma unroll
+            for (int c = 0; c < 3; c++) {
+              pos_out[3 * slot + c] = f[3 * r + c];
+              vel_out[3 * slot + c] = v[3 * r + c];
+            }
+            ids_out[slot] = id[r];
+          }
+        }
+      }
+    }
+  }
+  // the last np % 4 particles
+  if (blockIdx.x == 0 && threadIdx.x < (np & 3)) {
+    const int64_t n = (nq << 2) + threadIdx.x;
+    float x[3], w[3];
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+      float vv = vel[3 * n + c] + mh * acc[3 * n + c];
+      float p = pos[3 * n + c];
+      p = F64 ? (float)((double)p + dt * (double)vv) : p + dtf * vv;
+      x[c] = wrap01(p);
+      w[c] = vv;
+    }
+    const int bb = bin_of(x[0], x[1], x[2], Nf, NB, 0, NB);
+    const int first = atomicAdd(&cnt[bb], 1);
+    if (PASS == 2) {
+      const size_t slot = (size_t)bbase[bb] + first;
+#pragma unroll
+      for (int c = 0; c < 3; c++) { pos_out[3 * slot + c] = x[c]; vel_out[3 * slot + c] = w[c]; }
+      ids_out[slot] = ids ? ids[n] : (int)n;
+    }
+  }
+}
+
+// out[ids[n]] = in[n] for three-column arrays: back to the reference's particle order
+__global__ void __launch_bounds__(256) scatter3_by_id_kernel(const int *__restrict__ ids, const float *__restrict__ in,
+                                                             float *__restrict__ out, int64_t np) {
+  for (int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; n < np; n += (int64_t)gridDim.x * blockDim.x) {
+    const size_t d = 3 * (size_t)ids[n];
+    out[d] = in[3 * n]; out[d + 1] = in[3 * n + 1]; out[d + 2] = in[3 * n + 2];
+  }
+}
+
 // ------------------------------------------------------------------------------------- deposit
 // particles [beg, end) of bin b; shared = other CTAs deposit into the same bin (its interior cells need atomics too)
+// Where a kernel finds particle n of a bin.  SHADOW (SORTED = false): `src` is the binned copy float4[.] = (x, y, z, source
+// row), the particle arrays themselves are in another order and results go to `row`.  SORTED = true: `src` is the
+// position array [np, 3] itself, stored in bin order (csrc/sorted.cu): the row IS n.
+template <bool SORTED>
+__device__ __forceinline__ void load_particle(const void *__restrict__ src, int n, float &px, float &py, float &pz,
+                                              int &row) {
+  if (SORTED) {
+    const float *p = reinterpret_cast<const float *>(src) + 3 * (size_t)n;
+    px = __ldg(p); py = __ldg(p + 1); pz = __ldg(p + 2);
+    row = n;
+  } else {
+    const float4 r = __ldg(reinterpret_cast<const float4 *>(src) + n);
+    px = r.x; py = r.y; pz = r.z;
+    row = __float_as_int(r.w);
+  }
+}
+
 // scale / f1: the density rescale and the slope of rhs_poisson's affine map (solver.py:114-116, 444-449) applied to the
 // bin's sums before they leave the CTA; the caller has initialised rho with the map's constant f2, so that
 // rho = f1 * (scale * sum) + f2 needs no further pass over the grid (a cell fed by several bins gets f2 once and the
 // bins' scaled sums through REDs).
-template <int SCHEME>
-__device__ __forceinline__ void deposit_bin_range(float (*tiles)[BD_TILE], const float4 *__restrict__ brec, int b,
+template <int SCHEME, bool SORTED>
+__device__ __forceinline__ void deposit_bin_range(float (*tiles)[BD_TILE], const void *__restrict__ brec, int b,
                                                   int beg, int end, bool shared, int N, int NB, int x0, int xoff,
                                                   int nxa, float scale, float f1, float f2,
                                                   float *__restrict__ rho) {
@@ -337,7 +490,8 @@ __device__ __forceinline__ void deposit_bin_range(float (*tiles)[BD_TILE], const
     const int n = c + lane;
     const bool valid = n < end;
     float px = 0.f, py = 0.f, pz = 0.f;
-    if (valid) { const float4 r = __ldg(&brec[n]); px = r.x; py = r.y; pz = r.z; }
+    int row_unused;
+    if (valid) load_particle<SORTED>(brec, n, px, py, pz, row_unused);
     int i, j, k;
     float wx[3], wy[3], wz[3];
     axis_weights<SCHEME>(px * Nf, N, i, wx[0], wx[1], wx[2]);
@@ -432,8 +586,8 @@ __device__ __forceinline__ void deposit_bin_range(float (*tiles)[BD_TILE], const
   }
 }
 
-template <int SCHEME>
-__global__ void __launch_bounds__(BD_WARPS * 32) deposit_binned_kernel(const float4 *__restrict__ brec,
+template <int SCHEME, bool SORTED>
+__global__ void __launch_bounds__(BD_WARPS * 32) deposit_binned_kernel(const void *__restrict__ brec,
                                                                        const int *__restrict__ base,
                                                                        const int *__restrict__ fill, int N, int NB,
                                                                        int x0, int xoff, int nxa, float scale, float f1,
@@ -442,13 +596,13 @@ __global__ void __launch_bounds__(BD_WARPS * 32) deposit_binned_kernel(const flo
   const int b = blockIdx.x;
   const int beg = base[b], end = beg + fill[b];
   if (beg == end) return;  // rho was initialised (f2) by the caller
-  deposit_bin_range<SCHEME>(tiles, brec, b, beg, min(end, beg + BIN_PART), end - beg > BIN_PART, N, NB, x0, xoff, nxa,
-                            scale, f1, f2, rho);
+  deposit_bin_range<SCHEME, SORTED>(tiles, brec, b, beg, min(end, beg + BIN_PART), end - beg > BIN_PART, N, NB, x0, xoff,
+                                    nxa, scale, f1, f2, rho);
 }
 
 // the parts beyond BIN_PART particles of the heavy bins (persistent CTAs over BinLayout::heavy)
-template <int SCHEME>
-__global__ void __launch_bounds__(BD_WARPS * 32) deposit_heavy_kernel(const float4 *__restrict__ brec,
+template <int SCHEME, bool SORTED>
+__global__ void __launch_bounds__(BD_WARPS * 32) deposit_heavy_kernel(const void *__restrict__ brec,
                                                                       const int *__restrict__ base,
                                                                       const int *__restrict__ fill,
                                                                       const int *__restrict__ heavy_count,
@@ -461,7 +615,7 @@ __global__ void __launch_bounds__(BD_WARPS * 32) deposit_heavy_kernel(const floa
   for (int it = blockIdx.x; it < nitems; it += gridDim.x) {
     const int2 w = heavy[it];
     const int beg = base[w.x] + w.y * BIN_PART, end = min(base[w.x] + fill[w.x], beg + BIN_PART);
-    deposit_bin_range<SCHEME>(tiles, brec, w.x, beg, end, true, N, NB, x0, xoff, nxa, scale, f1, f2, rho);
+    deposit_bin_range<SCHEME, SORTED>(tiles, brec, w.x, beg, end, true, N, NB, x0, xoff, nxa, scale, f1, f2, rho);
     __syncthreads();
   }
 }
@@ -558,10 +712,10 @@ constexpr int BP_THREADS = 256;  // gradient + interpolation kernel
 
 // TP1 / TP0: row / plane pitch of the float4 force tile.  Measured at 512^3 (Morton order): 10/100 4.41 ms, 11/110 4.62,
 // 12/120 4.59, 12/144 4.75, 14/140 4.70, 11/112 5.19, 10/104 5.39 -- the dense tile is the best of those.
-template <int SCHEME, int ORDER, int TP1 = BT, int TP0 = BT * BT>
+template <int SCHEME, int ORDER, bool SORTED, int TP1 = BT, int TP0 = BT * BT>
 __global__ void __launch_bounds__(BP_THREADS) interp_kick_phi_binned_kernel(
     const float *__restrict__ phi, const float *__restrict__ u, float f, int fr_n,
-    const float4 *__restrict__ brec, const int *__restrict__ base, const int *__restrict__ fill,
+    const void *__restrict__ brec, const int *__restrict__ base, const int *__restrict__ fill,
     float *__restrict__ vel, float *__restrict__ accel, int N, int NB, int x0, int xoff, int nxa, float half_dt,
     float *__restrict__ maxout, int nbins, const int *__restrict__ heavy_count, const int2 *__restrict__ heavy) {
   constexpr int H = Reach<ORDER>::H;
@@ -647,9 +801,9 @@ __global__ void __launch_bounds__(BP_THREADS) interp_kick_phi_binned_kernel(
   const float mh = -half_dt;
   unsigned ma = 0u, mv = 0u;   // maxima of |.| as bit patterns: orders like the floats and lets a NaN win
   for (int n = beg + threadIdx.x; n < end; n += BP_THREADS) {
-    const float4 rec = __ldg(&brec[n]);
-    const float px = rec.x, py = rec.y, pz = rec.z;
-    const int row = __float_as_int(rec.w);
+    float px, py, pz;
+    int row;
+    load_particle<SORTED>(brec, n, px, py, pz, row);
     int i, j, k;
     float wx[3], wy[3], wz[3];
     axis_weights<SCHEME>(px * Nf, N, i, wx[0], wx[1], wx[2]);
@@ -862,9 +1016,10 @@ int psc_bin_particles_counted(const float *pos, int64_t np, int N, void *scratch
 // ghost = 0: periodic N^3 grid (x0 = 0, nxl = N); ghost = 1: rho has nxl + 2 planes, plane 0 / nxl + 1 collect the
 // mass that belongs to the neighbouring slabs
 static int deposit_binned_impl(const void *scratch, size_t scratch_bytes, int64_t np, int N, int x0, int nxl,
-                               int ghost, int scheme, float scale, float f1, float f2, float *rho, void *stream) {
+                               int ghost, int scheme, float scale, float f1, float f2, float *rho, void *stream,
+                               const float *sorted_pos = nullptr) {
   BinLayout L;
-  if (!bin_layout(const_cast<void *>(scratch), scratch_bytes, np, N, x0, nxl, L)) {
+  if (!bin_layout(const_cast<void *>(scratch), scratch_bytes, np, N, x0, nxl, L, sorted_pos == nullptr)) {
     set_error("psc_deposit_binned: scratch too small");
     return PSC_ERR_WORKSPACE;
   }
@@ -882,10 +1037,21 @@ static int deposit_binned_impl(const void *scratch, size_t scratch_bytes, int64_
     const int grid = (int)L.nbins;
     const int hgrid = num_sms() * 4;   // persistent CTAs over the heavy-bin parts (exit at once when there are none)
 #define PSC_DEP(S)                                                                                                   \
-  deposit_binned_kernel<S><<<grid, BD_WARPS * 32, 0, st>>>(L.rec, L.base, L.fill, N, L.NB, x0, ghost, nxa, scale, f1, \
-                                                           f2, rho);                                                 \
-  deposit_heavy_kernel<S><<<hgrid, BD_WARPS * 32, 0, st>>>(L.rec, L.base, L.fill, L.heavy_count, L.heavy, L.heavy_cap, N, \
-                                                          L.NB, x0, ghost, nxa, scale, f1, f2, rho)
+  do {                                                                                                               \
+    if (sorted_pos) {                                                                                                \
+      deposit_binned_kernel<S, true><<<grid, BD_WARPS * 32, 0, st>>>(sorted_pos, L.base, L.fill, N, L.NB, x0, ghost,  \
+                                                                     nxa, scale, f1, f2, rho);                       \
+      deposit_heavy_kernel<S, true><<<hgrid, BD_WARPS * 32, 0, st>>>(sorted_pos, L.base, L.fill, L.heavy_count,       \
+                                                                    L.heavy, L.heavy_cap, N, L.NB, x0, ghost, nxa,   \
+                                                                    scale, f1, f2, rho);                             \
+    } else {                                                                                                         \
+      deposit_binned_kernel<S, false><<<grid, BD_WARPS * 32, 0, st>>>(L.rec, L.base, L.fill, N, L.NB, x0, ghost, nxa, \
+                                                                      scale, f1, f2, rho);                           \
+      deposit_heavy_kernel<S, false><<<hgrid, BD_WARPS * 32, 0, st>>>(L.rec, L.base, L.fill, L.heavy_count, L.heavy,  \
+                                                                     L.heavy_cap, N, L.NB, x0, ghost, nxa, scale,    \
+                                                                     f1, f2, rho);                                   \
+    }                                                                                                                \
+  } while (0)
     if (scheme == PSC_TSC) { PSC_DEP(PSC_TSC); }
     else if (scheme == PSC_CIC) { PSC_DEP(PSC_CIC); }
     else { PSC_DEP(PSC_NGP); }
@@ -940,21 +1106,31 @@ int psc_interp_kick4_binned(const float *force4, const void *scratch, size_t scr
 // start at plane G
 static int interp_kick_phi_impl(const float *phi, const float *u, float f, int fr_n, int order, int x0, int nxl,
                                 int ghost, const void *scratch, size_t scratch_bytes, float *vel, float *acc,
-                                int64_t np, int N, int scheme, float half_dt, float *maxout, void *stream) {
+                                int64_t np, int N, int scheme, float half_dt, float *maxout, void *stream,
+                                const float *sorted_pos = nullptr) {
   if (np == 0) return PSC_OK;
   PSC_CHECK_ARG((((uintptr_t)phi | (uintptr_t)u) & 15) == 0, "phi and u must be 16-byte aligned");
   BinLayout L;
-  if (!bin_layout(const_cast<void *>(scratch), scratch_bytes, np, N, x0, nxl, L)) {
+  if (!bin_layout(const_cast<void *>(scratch), scratch_bytes, np, N, x0, nxl, L, sorted_pos == nullptr)) {
     set_error("psc_interp_kick_phi_binned: scratch too small");
     return PSC_ERR_WORKSPACE;
   }
   cudaStream_t st = as_stream(stream);
   const int grid = (int)L.nbins + L.heavy_cap;   // the CTAs of unused heavy-part slots exit at once
   const int nxa = nxl + 2 * ghost;
-#define PSC_IKP(S, O)                                                                                            \
-  interp_kick_phi_binned_kernel<S, O><<<grid, BP_THREADS, 0, st>>>(phi, u, f, fr_n, L.rec, L.base, L.fill, vel, acc, \
-                                                                   N, L.NB, x0, ghost, nxa, half_dt, maxout,    \
-                                                                   (int)L.nbins, L.heavy_count, L.heavy)
+#define PSC_IKP(S, O)                                                                                               \
+  do {                                                                                                              \
+    if (sorted_pos)                                                                                                 \
+      interp_kick_phi_binned_kernel<S, O, true><<<grid, BP_THREADS, 0, st>>>(phi, u, f, fr_n, sorted_pos, L.base,   \
+                                                                             L.fill, vel, acc, N, L.NB, x0, ghost,  \
+                                                                             nxa, half_dt, maxout, (int)L.nbins,    \
+                                                                             L.heavy_count, L.heavy);               \
+    else                                                                                                            \
+      interp_kick_phi_binned_kernel<S, O, false><<<grid, BP_THREADS, 0, st>>>(phi, u, f, fr_n, L.rec, L.base,       \
+                                                                              L.fill, vel, acc, N, L.NB, x0, ghost, \
+                                                                              nxa, half_dt, maxout, (int)L.nbins,   \
+                                                                              L.heavy_count, L.heavy);              \
+  } while (0)
 #define PSC_IKP_O(S)               \
   if (order == 2) PSC_IKP(S, 2);    \
   else if (order == 3) PSC_IKP(S, 3); \
@@ -992,6 +1168,94 @@ int psc_interp_kick_phi_binned_slab(const float *phi_ghost, const float *u_ghost
   PSC_CHECK_ARG(phi_ghost && scratch && acc && maxout && (u_ghost || fr_n == 0), "null pointer");
   return interp_kick_phi_impl(phi_ghost, u_ghost, f, fr_n, order, x0, nxl, ghost, scratch, scratch_bytes, vel, acc, np,
                               N, scheme, half_dt, maxout, stream);
+}
+
+/* ----------------------------------------------------------- particle arrays in bin order (the time loop) */
+size_t psc_sorted_workspace_bytes(int64_t np, int N) {
+  if (np < 0 || !slab_ok(N, 0, N)) return 0;
+  const int64_t nbins = (int64_t)(N / BB) * (N / BB) * (N / BB);
+  return 4 * a256(sizeof(int) * (nbins + 1)) + 256 + a256(sizeof(int2) * (size_t)(np / BIN_PART + 1)) +
+         a256(scan_tmp_bytes(nbins + 1)) + 256;
+}
+
+int psc_step_sort(const float *pos, const float *vel, const float *acc, const int *ids, int64_t np, float half_dt,
+                  double dt, int dt_is_f64, int N, void *scratch, size_t scratch_bytes, float *pos_out, float *vel_out,
+                  int *ids_out, void *stream) {
+  PSC_CHECK_ARG(np >= 0 && np < ((int64_t)1 << 31), "np out of range");
+  PSC_CHECK_ARG(slab_ok(N, 0, N), "N must be a multiple of 8");
+  PSC_CHECK_ARG(scratch && ((uintptr_t)scratch & 255) == 0, "scratch must be 256-byte aligned");
+  BinLayout L;
+  if (!bin_layout(scratch, scratch_bytes, np, N, 0, N, L, false)) {
+    set_error("psc_step_sort: scratch too small");
+    return PSC_ERR_WORKSPACE;
+  }
+  cudaStream_t st = as_stream(stream);
+  PSC_CUDA(cudaMemsetAsync(L.counts, 0, sizeof(int) * (L.nbins + 1), st));
+  PSC_CUDA(cudaMemsetAsync(L.fill, 0, sizeof(int) * (L.nbins + 1), st));
+  PSC_CUDA(cudaMemsetAsync(L.heavy_count, 0, sizeof(int), st));
+  if (np > 0) {
+    PSC_CHECK_ARG(pos && vel && acc && pos_out && vel_out && ids_out, "null pointer");
+    PSC_CHECK_ARG(pos != pos_out && vel != vel_out && ids != ids_out, "the sort is out of place");
+    PSC_CHECK_ARG((((uintptr_t)pos | (uintptr_t)vel | (uintptr_t)acc | (uintptr_t)ids) & 15) == 0,
+                  "pointers must be 16-byte aligned");
+    const int g = grid_for((np + 3) / 4, 256, 8);
+    if (dt_is_f64)
+      step_sort_kernel<true, 1><<<g, 256, 0, st>>>(pos, vel, acc, ids, np, half_dt, dt, N, L.NB, L.counts, nullptr,
+                                                  nullptr, nullptr, nullptr);
+    else
+      step_sort_kernel<false, 1><<<g, 256, 0, st>>>(pos, vel, acc, ids, np, half_dt, dt, N, L.NB, L.counts, nullptr,
+                                                   nullptr, nullptr, nullptr);
+    count_launch();
+  }
+  int rc = scan_bins(L, L.counts, L.base, st);
+  if (rc != PSC_OK) return rc;
+  if (np > 0) {
+    const int g = grid_for((np + 3) / 4, 256, 8);
+    if (dt_is_f64)
+      step_sort_kernel<true, 2><<<g, 256, 0, st>>>(pos, vel, acc, ids, np, half_dt, dt, N, L.NB, L.fill, L.base,
+                                                  pos_out, vel_out, ids_out);
+    else
+      step_sort_kernel<false, 2><<<g, 256, 0, st>>>(pos, vel, acc, ids, np, half_dt, dt, N, L.NB, L.fill, L.base,
+                                                   pos_out, vel_out, ids_out);
+    count_launch();
+  }
+  bin_heavy_list_kernel<<<(int)((L.nbins + 255) / 256), 256, 0, st>>>(L.fill, (int)L.nbins, L.heavy_count, L.heavy,
+                                                                     L.heavy_cap);
+  count_launch();
+  PSC_CHECK_LAUNCH();
+  return PSC_OK;
+}
+
+int psc_deposit_sorted(const float *pos_sorted, const void *scratch, size_t scratch_bytes, int64_t np, int N, int scheme,
+                       float scale, float f1, float f2, float *rho, void *stream) {
+  PSC_CHECK_ARG(scheme == PSC_NGP || scheme == PSC_CIC || scheme == PSC_TSC, "unknown mass scheme");
+  PSC_CHECK_ARG(slab_ok(N, 0, N), "N must be a multiple of 8");
+  PSC_CHECK_ARG(scratch && rho && (pos_sorted || np == 0), "null pointer");
+  static const float dummy = 0.0f;
+  return deposit_binned_impl(scratch, scratch_bytes, np, N, 0, N, 0, scheme, scale, f1, f2, rho, stream,
+                             pos_sorted ? pos_sorted : &dummy);
+}
+
+int psc_interp_kick_phi_sorted(const float *phi, const float *u, float f, int fr_n, int order, const float *pos_sorted,
+                               const void *scratch, size_t scratch_bytes, float *vel_sorted, float *acc_sorted,
+                               int64_t np, int N, int scheme, float half_dt, float *maxout, void *stream) {
+  PSC_CHECK_ARG(scheme == PSC_CIC || scheme == PSC_TSC, "mass scheme must be CIC or TSC");
+  PSC_CHECK_ARG(order == 2 || order == 3 || order == 5 || order == 7, "gradient order must be 2, 3, 5 or 7");
+  PSC_CHECK_ARG(fr_n >= 0 && fr_n <= 2, "fR_n must be 1 or 2");
+  PSC_CHECK_ARG(N >= 2 * BB && (N % BB) == 0, "N must be a multiple of 8 and >= 16");
+  PSC_CHECK_ARG(phi && scratch && acc_sorted && maxout && (u || fr_n == 0) && (pos_sorted || np == 0), "null pointer");
+  return interp_kick_phi_impl(phi, u, f, fr_n, order, 0, N, 0, scratch, scratch_bytes, vel_sorted, acc_sorted, np, N,
+                              scheme, half_dt, maxout, stream, pos_sorted);
+}
+
+int psc_scatter3_by_id(const int *ids, const float *in, float *out, int64_t np, void *stream) {
+  PSC_CHECK_ARG(np >= 0, "np < 0");
+  if (np == 0) return PSC_OK;
+  PSC_CHECK_ARG(ids && in && out && in != out, "null or aliased pointer");
+  scatter3_by_id_kernel<<<grid_for(np, 256, 8), 256, 0, as_stream(stream)>>>(ids, in, out, np);
+  count_launch();
+  PSC_CHECK_LAUNCH();
+  return PSC_OK;
 }
 
 }  // extern "C"

@@ -221,6 +221,19 @@ def leapfrog(position, velocity, acceleration, potential, additional_field, dt, 
     pos, vel, acc, pot, add = _to_device(c, position, velocity, acceleration, potential, additional_field)
     half_dt = np.float32(0.5 * dt)
     dt_is_f64 = 0 if isinstance(dt, np.float32) else 1
+    N = 2 ** param["ncoarse"]
+    if _bin_ordered_loop(c, pos, vel, acc, param):
+        # Device-resident arrays: the step re-sorts them into bin order while it kicks and drifts (no binned copy, no
+        # source-row indirection in the deposit / interpolation).  The arrays returned are NEW tensors in bin order;
+        # utils.particle_ids / utils.reference_order give the reference's rows back.
+        sb = mesh.step_sorted(pos.shape[0], N)
+        pos, vel, ids = mesh.step_sort(pos, vel, acc, utils.particle_ids(pos), half_dt, dt, dt_is_f64, sb)
+        _advance_clock(dt, tables, param)
+        acc, pot, add, maxima = solver._pm_device(pos, param, pot, add, tables, kick=(vel, half_dt), counted=sb)
+        utils.set_particle_ids((pos, vel, acc), ids)
+        mx = maxima.cpu().numpy()
+        _remember_maxima(acc, vel, mx)
+        return pos, vel, acc, pot, add
     counted = _binned_for(pos, param)
     if counted is not None:   # first pass of the binning folded into the kick-drift-wrap
         mesh.kick_drift_wrap_count(pos, vel, acc, half_dt, dt, dt_is_f64, counted)
@@ -233,6 +246,22 @@ def leapfrog(position, velocity, acceleration, potential, additional_field, dt, 
     mx = maxima.cpu().numpy()  # one 8-byte read: max|a|, max|v| for the next integrate()
     _remember_maxima(acc, vel, mx)
     return _from_device(c, position, velocity, pos, vel, acc, pot, add)
+
+
+def _bin_ordered_loop(c, pos, vel, acc, param):
+    """The bin-ordered time loop applies to device tensors (a NumPy / host caller gets its arrays updated in place, row
+    for row, like the reference), meshes the binned kernels take, the fused gradient + interpolation (not full_fft) and
+    one process per problem.  param["particle_order"] = "reference" keeps the rows where they are (shadow binning)."""
+    if c.np_mode or distributed.is_active():
+        return False
+    if str(param["particle_order"] if "particle_order" in param.index else "bins").casefold() == "reference":
+        return False
+    N = 2 ** param["ncoarse"]
+    ok = all(isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()
+             and t.data_ptr() % 16 == 0 for t in (pos, vel, acc))
+    return (ok and mesh.can_bin(N, pos.shape[0]) and N >= 16
+            and param["linear_newton_solver"].casefold() != "full_fft"
+            and param["mass_scheme"].casefold() in ("cic", "tsc"))
 
 
 def euler(position, velocity, acceleration, potential, additional_field, dt, tables, param):

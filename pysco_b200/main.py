@@ -127,10 +127,11 @@ def run(param, initial_state=None):
             logging.info("Reordering particles")
             position, velocity, acceleration = utils.reorder_particles(position, velocity, acceleration)
         if param["write_snapshot"]:
-            iostream.write_snapshot_particles(position, velocity, param)
+            # the device-resident arrays are in bin order between reorders: snapshots keep the reference's rows
+            iostream.write_snapshot_particles(*utils.reference_order(position, velocity), param)
             param["i_snap"] += 1
         logging.warning(f"{param['nsteps']=} {param['aexp']=} z = {1.0 / param['aexp'] - 1}")
-    return position, velocity
+    return utils.reference_order(position, velocity)
 
 
 def main():

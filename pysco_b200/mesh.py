@@ -29,6 +29,40 @@ def alloc_binned(np_, ncells_1d):
     return Binned(_lib.empty((nbytes,), torch.uint8), int(np_), N)
 
 
+class SortedBins:
+    """Bin table of particle arrays that are themselves stored in bin order (psc_step_sort): first row / count of
+    every 8^3-cell bin and the list of bins split into parts; no binned copy of the positions."""
+
+    def __init__(self, scratch, np_, N):
+        self.scratch, self.np, self.N = scratch, np_, N
+
+
+_step_sorted = {}
+
+
+def step_sorted(np_, ncells_1d):
+    """persistent SortedBins scratch of the time loop for (device, N, np)"""
+    key = (torch.cuda.current_device(), int(ncells_1d), int(np_))
+    b = _step_sorted.get(key)
+    if b is None:
+        _step_sorted.clear()
+        nbytes = int(_lib.load().psc_sorted_workspace_bytes(int(np_), int(ncells_1d)))
+        b = _step_sorted[key] = SortedBins(_lib.empty((nbytes,), torch.uint8), int(np_), int(ncells_1d))
+    return b
+
+
+def step_sort(pos, vel, acc, ids, half_dt, dt, dt_is_f64, sb):
+    """integration.py:250-258 (first half-kick, drift, wrap) fused with the re-sort of the particle arrays into bin
+    order: returns NEW (position, velocity, ids) in bin order; `sb` then describes the bins of these arrays."""
+    n = pos.shape[0]
+    pos2, vel2 = torch.empty_like(pos), torch.empty_like(vel)
+    ids2 = _lib.empty((n,), torch.int32)
+    _lib.check(_lib.load().psc_step_sort(_lib.ptr(pos), _lib.ptr(vel), _lib.ptr(acc), _lib.ptr(ids), n, float(half_dt),
+                                         float(dt), int(dt_is_f64), sb.N, _lib.ptr(sb.scratch), sb.scratch.numel(),
+                                         _lib.ptr(pos2), _lib.ptr(vel2), _lib.ptr(ids2), _lib.stream()))
+    return pos2, vel2, ids2
+
+
 _step_binned = {}
 
 
@@ -87,7 +121,10 @@ def _deposit(position, ncells_1d, scheme, scale=1.0, f1=1.0, f2=0.0, binned=None
     lib = _lib.load()
     if binned is None and can_bin(N, pos.shape[0]):
         binned = bin_particles(pos, N)
-    if binned is not None:
+    if isinstance(binned, SortedBins):
+        _lib.check(lib.psc_deposit_sorted(_lib.ptr(pos), _lib.ptr(binned.scratch), binned.scratch.numel(), binned.np, N,
+                                          scheme, float(scale), float(f1), float(f2), _lib.ptr(rho), _lib.stream()))
+    elif binned is not None:
         _lib.check(lib.psc_deposit_binned(_lib.ptr(binned.scratch), binned.scratch.numel(), binned.np, N, scheme,
                                           float(scale), float(f1), float(f2), _lib.ptr(rho), _lib.stream()))
     else:
@@ -183,10 +220,16 @@ def interp_kick_phi(potential, u, f, fr_n, order, position, velocity, scheme, ha
     n = pos.shape[0]
     acc = _lib.empty((n, 3))
     mx = _lib.zeros((2,))
-    _lib.check(_lib.load().psc_interp_kick_phi_binned(
-        _lib.ptr(phi), _lib.ptr(tu), float(np.float32(f)), fr_n, order, _lib.ptr(binned.scratch),
-        binned.scratch.numel(), _lib.ptr(vel), _lib.ptr(acc), n, phi.shape[0], scheme, float(half_dt), _lib.ptr(mx),
-        _lib.stream()))
+    if isinstance(binned, SortedBins):
+        _lib.check(_lib.load().psc_interp_kick_phi_sorted(
+            _lib.ptr(phi), _lib.ptr(tu), float(np.float32(f)), fr_n, order, _lib.ptr(pos), _lib.ptr(binned.scratch),
+            binned.scratch.numel(), _lib.ptr(vel), _lib.ptr(acc), n, phi.shape[0], scheme, float(half_dt),
+            _lib.ptr(mx), _lib.stream()))
+    else:
+        _lib.check(_lib.load().psc_interp_kick_phi_binned(
+            _lib.ptr(phi), _lib.ptr(tu), float(np.float32(f)), fr_n, order, _lib.ptr(binned.scratch),
+            binned.scratch.numel(), _lib.ptr(vel), _lib.ptr(acc), n, phi.shape[0], scheme, float(half_dt), _lib.ptr(mx),
+            _lib.stream()))
     c.finish()
     return c.ret(acc), mx
 

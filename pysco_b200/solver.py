@@ -200,7 +200,9 @@ def _pm_device(position, param, potential, additional_field, tables, kick=None, 
     conversion = np.float32(ncells_1d ** 3 / param["npart"]) if ncells_1d ** 3 != param["npart"] else np.float32(1)
     # one shadow binning of the particles per step, shared by the deposit and the interpolation
     # (`counted`: a Binned whose counts were already produced by the fused kick-drift-wrap of integration.leapfrog)
-    if counted is not None:
+    if isinstance(counted, mesh.SortedBins):
+        binned = counted        # the particle arrays are in bin order already (integration.leapfrog: mesh.step_sort)
+    elif counted is not None:
         binned = mesh.finish_binning(position, counted)
     else:
         binned = mesh.bin_particles(position, ncells_1d) if mesh.can_bin(ncells_1d, position.shape[0]) else None

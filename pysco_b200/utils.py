@@ -105,6 +105,46 @@ def argsort_keys(keys):
     return idx
 
 
+# ------------------------------------------------------------------ particle order of the device-resident time loop
+# integration.leapfrog keeps device-resident particle arrays in BIN order and re-sorts them every step (csrc/binned.cu:
+# psc_step_sort); the particle in row n of such arrays is the one the reference has in row ids[n].  The ids travel in
+# this registry, keyed by the tensors leapfrog returned; anything that needs the reference's row order (snapshots,
+# row-wise comparisons) calls reference_order().  Arrays nobody registered are in the reference's order already.
+import weakref
+
+_order_ids = {}
+
+
+def set_particle_ids(tensors, ids) -> None:
+    dead = [k for k, (ref, _) in _order_ids.items() if ref() is None]
+    for k in dead:
+        del _order_ids[k]
+    for t in tensors:
+        if isinstance(t, torch.Tensor):
+            _order_ids[id(t)] = (weakref.ref(t), ids)
+
+
+def particle_ids(t):
+    """int32 device tensor: row n of `t` is the particle of the reference's row ids[n]; None = reference order"""
+    e = _order_ids.get(id(t)) if isinstance(t, torch.Tensor) else None
+    return e[1] if e is not None and e[0]() is t else None
+
+
+def reference_order(*arrays):
+    """The given [np, 3] arrays (position, velocity, acceleration of the device-resident time loop) in the reference's
+    particle order: out[ids[n]] = in[n].  Arrays that already are in that order come back unchanged."""
+    out = []
+    for a in arrays:
+        ids = particle_ids(a)
+        if ids is None:
+            out.append(a)
+            continue
+        b = torch.empty_like(a)
+        _lib.check(_lib.load().psc_scatter3_by_id(_lib.ptr(ids), _lib.ptr(a), _lib.ptr(b), a.shape[0], _lib.stream()))
+        out.append(b)
+    return out[0] if len(out) == 1 else tuple(out)
+
+
 def reorder_particles(position, velocity=None, acceleration=None):
     """utils.py:1019-1075: Morton keys -> (global, stable) argsort -> gathers; returns NEW arrays.
     Matches the reference's nthreads == 1 path (np.argsort); rows of equal key keep their order."""

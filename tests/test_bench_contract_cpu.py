@@ -61,7 +61,8 @@ def test_ics_are_the_same_in_both_arms():
 def test_every_timed_kernel_has_an_algorithmic_byte_entry_or_is_overhead():
     sys.path.insert(0, ROOT)
     import bench
-    step_kernels = ["psc_kick_drift_wrap_count", "psc_bin_particles_counted", "psc_deposit_binned", "psc_fft_r2c",
+    step_kernels = ["psc_step_sort", "psc_deposit_sorted", "psc_interp_kick_phi_sorted",
+                    "psc_kick_drift_wrap_count", "psc_bin_particles_counted", "psc_deposit_binned", "psc_fft_r2c",
                     "psc_green", "psc_fft_c2r", "psc_interp_kick_phi_binned", "psc_kick_drift_wrap_slab",
                     "psc_bin_particles_slab", "psc_deposit_binned_slab", "psc_interp_kick_phi_binned_slab",
                     "psc_slab_fft_r2c_planes", "psc_slab_fft_x", "psc_green_slab", "psc_slab_fft_c2r_planes"]
@@ -72,3 +73,5 @@ def test_every_timed_kernel_has_an_algorithmic_byte_entry_or_is_overhead():
     single = ["psc_kick_drift_wrap_count", "psc_deposit_binned", "psc_fft_r2c", "psc_green", "psc_fft_c2r",
               "psc_interp_kick_phi_binned"]
     assert sum(bench.ALGO_BYTES[k] for k in single) == 176.0
+    loop = ["psc_step_sort", "psc_deposit_sorted", "psc_fft_r2c", "psc_green", "psc_fft_c2r", "psc_interp_kick_phi_sorted"]
+    assert sum(bench.ALGO_BYTES[k] for k in loop) == 176.0

