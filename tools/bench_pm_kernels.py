@@ -67,6 +67,16 @@ for name, p in cases.items():
     t_int = timeit(lambda: mesh.interp_kick_phi(phi, None, 0.0, 0, 5, p, v2, 2, 0.0, bn))
     out.append(f"grad+interp+kick {t_int:6.3f} ms")
     print(" | ".join(out), flush=True)
+    # the same particle set with the arrays THEMSELVES in bin order (the time loop's layout)
+    z = torch.zeros_like(p)
+    sb = mesh.step_sorted(p.shape[0], N)
+    t_sort = timeit(lambda: mesh.step_sort(p, vel, z, None, np.float32(0), np.float32(0), 0, sb))
+    sp, sv, sid = mesh.step_sort(p, vel, z, None, np.float32(0), np.float32(0), 0, sb)
+    t_dep = timeit(lambda: mesh.deposit_rhs(sp, N, 2, 1.0, 1.0, 0.0, sb))
+    t_int = timeit(lambda: mesh.interp_kick_phi(phi, None, 0.0, 0, 5, sp, sv, 2, 0.0, sb))
+    print(f"N={N} {name:18s} [bin-ordered arrays] kick+drift+wrap+sort {t_sort:6.3f} ms | deposit {t_dep:6.3f} ms | "
+          f"grad+interp+kick {t_int:6.3f} ms", flush=True)
+    del sp, sv, sid, z
 # kick + drift + wrap + binning inside a step: count -> scan -> scatter (mode 0) against the direct scatter (mode 1)
 p = pos_mor.clone()
 v = vel.clone()

@@ -8,19 +8,19 @@ nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm --format=csv > $out/${tag}_s
 timeout 1500 python -m pytest tests -m gpu -q > $out/${tag}_pytest.log 2>&1
 echo "pytest rc=$?" >> $out/${tag}_pytest.log
 timeout 600 python tools/bench_pm_kernels.py 9 > $out/${tag}_pm_kernels.log 2>&1
+if [ -z "$SKIP_MG" ]; then
 timeout 600 python tools/bench_multigrid.py 9 > $out/${tag}_multigrid512.log 2>&1
 timeout 600 python tools/bench_multigrid.py 8 > $out/${tag}_multigrid256.log 2>&1
-PSC_GS_NO_TMA=1 timeout 600 python tools/bench_multigrid.py 9 > $out/${tag}_multigrid512_notma.log 2>&1
-PSC_NO_FUSED_GS=1 timeout 600 python tools/bench_multigrid.py 9 > $out/${tag}_multigrid512_twopass.log 2>&1
+fi
 timeout 1200 python bench.py --steps 20 --warmup 3 > $out/${tag}_bench512.json 2> $out/${tag}_bench512.err
 echo "bench rc=$?" >> $out/${tag}_bench512.err
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $out/${tag}_launches.csv \
   python bench.py --steps 2 --warmup 1 --no-e2e --no-cpu-baseline --no-extras > $out/${tag}_ncu_launch.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:'deposit_binned_kernel|interp_kick_phi_binned_kernel|kick_drift_wrap_count_kernel|bin_scatter_kernel' \
-  --launch-skip 7 --launch-count 4 -o $out/${tag}_particle_kernels -f python tools/prof_step.py 9 step > $out/${tag}_ncu_full.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:'deposit_binned_kernel|interp_kick_phi_binned_kernel|step_sort_kernel' \
+  --launch-skip 6 --launch-count 4 -o $out/${tag}_particle_kernels -f python tools/prof_step.py 9 step > $out/${tag}_ncu_full.log 2>&1
 python tools/ncu_summary.py $out/${tag}_particle_kernels.ncu-rep > $out/${tag}_particle_kernels_ncu.txt 2>&1
-bash tools/gpu_session2.sh $tag
+if [ -z "$SKIP_GRID_NCU" ]; then bash tools/gpu_session2.sh $tag; fi
 ls -la $out | tail -30
 tail -5 $out/${tag}_pytest.log
 cat $out/${tag}_pm_kernels.log
-tail -12 $out/${tag}_multigrid512.log
+tail -12 $out/${tag}_multigrid512.log 2>/dev/null

@@ -15,7 +15,7 @@ from pysco_b200 import _lib, integration, mesh, solver, utils  # noqa: E402
 nc = int(sys.argv[1]) if len(sys.argv) > 1 else 9
 what = sys.argv[2] if len(sys.argv) > 2 else "step"
 N = 2 ** nc
-pos, vel = bench.synthetic_ics_device(N)
+pos, vel, _ = bench.slab_ics(N, 0, N)
 pos, vel = utils.reorder_particles(pos, vel)
 if what == "deposit":
     for _ in range(3):
