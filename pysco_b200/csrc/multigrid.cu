@@ -11,6 +11,7 @@
 // (j, i) tiles; neighbour rows come through L1/L2 (each row is re-read by its 4 lateral neighbours
 // of the same CTA).  Reductions: warp shuffle -> one double atomic per CTA.
 #include "common.cuh"
+#include "fr_roots.cuh"
 
 namespace psc {
 
@@ -155,48 +156,7 @@ __global__ void __launch_bounds__(TKX *TJ) prolongation_kernel(float *__restrict
     }
 }
 
-// ------------------------------------------------------------------------- f(R) root solvers
-__device__ __forceinline__ float solve_cubic(float pf, float d1f) {
-  // cubic.py:162-207 (float64 inside, float32 in/out)
-  const double inv3 = 1.0 / 3;
-  double d1 = (double)d1f, p = (double)pf;
-  double d = d1 * d1 + 108.0 * (p * p * p);
-  if (d > 0.0) {
-    d = d1 + sqrt(d);
-    if (d == 0.0) return (float)(-inv3 * pow(d1, inv3));
-    double C = pow(0.5 * d, inv3);
-    return (float)(-inv3 * (C - 3.0 * p / C));
-  } else if (d < 0.0) {
-    double d0 = -3.0 * p;
-    double s0 = sqrt(d0);
-    d = d1 / (2.0 * (d0 * s0));
-    if (fabs(d) < 1.0) {
-      double theta = acos(d);
-      return (float)(-2.0 * inv3 * s0 * cos(inv3 * (theta + 2.0 * 3.14159265358979323846)));
-    }
-    return (float)(-inv3 * pow(d1, inv3));
-  }
-  return (float)(-inv3 * pow(d1, inv3));
-}
-__device__ __forceinline__ float solve_quartic(float pf, float qf) {
-  // quartic.py:157-204
-  double pp = (double)pf, qq = (double)qf;
-  if (pp == 0.0) return (float)pow(-qq, 0.25);
-  const double inv3 = 1.0 / 3.0;
-  double d0 = 12.0 * qq;
-  double d1 = 27.0 * (pp * pp);
-  double r = d0 / d1;
-  double sqrt_term = 1.0 - 4.0 * d0 * (r * r);
-  if (sqrt_term < 0.0) return (float)pow(-qq, 0.25);
-  double Q = pow(0.5 * d1 * (1.0 + sqrt(sqrt_term)), inv3);
-  double Qd = Q + d0 / Q;
-  if (Qd > 0.0) {
-    double S = 0.5 * sqrt(Qd * inv3);
-    if (pp > 0.0) return (float)(-S + 0.5 * sqrt(-4.0 * (S * S) + pp / S));
-    return (float)(S + 0.5 * sqrt(-4.0 * (S * S) - pp / S));
-  }
-  return (float)pow(-qq, 0.25);
-}
+// f(R) root solvers: fr_roots.cuh (float32 fast path + the reference's float64 statement)
 
 template <int KIND>
 __global__ void __launch_bounds__(256) init_potential_kernel(const float *__restrict__ b, float q_val,

@@ -16,6 +16,7 @@
 #include <stddef.h>
 
 #include "../../include/pysco_b200.h"
+#include "fr_roots.cuh"
 
 #ifdef __CUDACC__
 #define PSC_CELL __device__ __forceinline__
@@ -128,48 +129,7 @@ PSC_CELL void prolong_add_cell(float *fine_g, const float *coarse_g, int ci, int
 }
 
 // ----------------------------------------------------------------------------------- f(R) scalaron (FAS)
-// closed-form roots in float64, float32 in / out -- as multigrid.cu solve_cubic / solve_quartic
-PSC_CELL float solve_cubic(float pf, float d1f) {
-  // cubic.py:162-207
-  const double inv3 = 1.0 / 3;
-  double d1 = (double)d1f, p = (double)pf;
-  double d = d1 * d1 + 108.0 * (p * p * p);
-  if (d > 0.0) {
-    d = d1 + sqrt(d);
-    if (d == 0.0) return (float)(-inv3 * pow(d1, inv3));
-    double C = pow(0.5 * d, inv3);
-    return (float)(-inv3 * (C - 3.0 * p / C));
-  } else if (d < 0.0) {
-    double d0 = -3.0 * p;
-    double s0 = sqrt(d0);
-    d = d1 / (2.0 * (d0 * s0));
-    if (fabs(d) < 1.0) {
-      double theta = acos(d);
-      return (float)(-2.0 * inv3 * s0 * cos(inv3 * (theta + 2.0 * 3.14159265358979323846)));
-    }
-    return (float)(-inv3 * pow(d1, inv3));
-  }
-  return (float)(-inv3 * pow(d1, inv3));
-}
-PSC_CELL float solve_quartic(float pf, float qf) {
-  // quartic.py:157-204
-  double pp = (double)pf, qq = (double)qf;
-  if (pp == 0.0) return (float)pow(-qq, 0.25);
-  const double inv3 = 1.0 / 3.0;
-  double d0 = 12.0 * qq;
-  double d1 = 27.0 * (pp * pp);
-  double r = d0 / d1;
-  double sqrt_term = 1.0 - 4.0 * d0 * (r * r);
-  if (sqrt_term < 0.0) return (float)pow(-qq, 0.25);
-  double Q = pow(0.5 * d1 * (1.0 + sqrt(sqrt_term)), inv3);
-  double Qd = Q + d0 / Q;
-  if (Qd > 0.0) {
-    double S = 0.5 * sqrt(Qd * inv3);
-    if (pp > 0.0) return (float)(-S + 0.5 * sqrt(-4.0 * (S * S) + pp / S));
-    return (float)(S + 0.5 * sqrt(-4.0 * (S * S) - pp / S));
-  }
-  return (float)pow(-qq, 0.25);
-}
+// closed-form roots: fr_roots.cuh (psc::solve_cubic / psc::solve_quartic), shared with multigrid.cu
 
 // KIND = PSC_OP_CUBIC: squares of the neighbours, PSC_OP_QUARTIC: cubes
 template <int KIND>
