@@ -43,6 +43,11 @@ SIGNATURES = {
     "psc_deposit_sorted": [_vp, _vp, _sz, _i64, _i, _i, _f, _f, _f, _vp, _vp],
     "psc_interp_kick_phi_sorted": [_vp, _vp, _f, _i, _i, _vp, _vp, _sz, _vp, _vp, _i64, _i, _i, _f, _vp, _vp],
     "psc_scatter3_by_id": [_vp, _vp, _vp, _i64, _vp],
+    "psc_sorted_workspace_bytes_slab": [_i64, _i, _i],
+    "psc_sort_by_bin_slab": [_vp, _vp, _vp, _i64, _i, _i, _i, _vp, _sz, _vp, _vp, _vp, _vp],
+    "psc_deposit_sorted_slab": [_vp, _vp, _sz, _i64, _i, _i, _i, _i, _vp, _vp],
+    "psc_interp_kick_phi_sorted_slab": [_vp, _vp, _f, _i, _i, _i, _i, _i, _vp, _vp, _sz, _vp, _vp, _i64, _i, _i, _f, _vp,
+                                        _vp],
     "psc_bin_workspace_bytes_slab": [_i64, _i, _i],
     "psc_bin_particles_slab": [_vp, _i64, _i, _i, _i, _vp, _sz, _vp],
     "psc_deposit_binned_slab": [_vp, _sz, _i64, _i, _i, _i, _i, _vp, _vp],
@@ -104,7 +109,7 @@ SIGNATURES = {
     "psc_box_initialise_potential_fr": [_vp, _f, _i, _i, _i, _vp, _vp],
 }
 _RESTYPES = {"psc_mg_q_device_ptr": C.c_void_p, "psc_last_error": C.c_char_p, "psc_launch_count": _i64, "psc_argsort_workspace_bytes": _sz,
-             "psc_bin_workspace_bytes": _sz, "psc_bin_workspace_bytes_slab": _sz, "psc_sorted_workspace_bytes": _sz,
+             "psc_bin_workspace_bytes": _sz, "psc_bin_workspace_bytes_slab": _sz, "psc_sorted_workspace_bytes": _sz, "psc_sorted_workspace_bytes_slab": _sz,
              "psc_slab_fft_workspace_bytes": _sz,
              "psc_fft_plan_workspace_bytes": _sz}
 
@@ -151,7 +156,7 @@ _TIMED = ("psc_morton_keys", "psc_argsort_keys", "psc_gather3", "psc_axpy", "psc
           "psc_grad_green", "psc_pk", "psc_operator", "psc_residual", "psc_restrict_residual",
           "psc_residual_sumsq", "psc_diff_sumsq", "psc_initialise_potential", "psc_gauss_seidel", "psc_gauss_seidel_fused",
           "psc_restriction", "psc_prolongation", "psc_mond_rhs",
-          "psc_bin_particles_slab", "psc_deposit_binned_slab", "psc_interp_kick_phi_binned_slab", "psc_slab_count",
+          "psc_bin_particles_slab", "psc_deposit_binned_slab", "psc_interp_kick_phi_binned_slab", "psc_sort_by_bin_slab", "psc_deposit_sorted_slab", "psc_interp_kick_phi_sorted_slab", "psc_slab_count",
           "psc_slab_pack_leavers", "psc_kick_drift_wrap_slab", "psc_slab_pack_rows", "psc_slab_pack_fixed", "psc_slab_unpack_rows", "psc_slab_move_rows", "psc_slab_fft_r2c_planes",
           "psc_slab_fft_c2r_planes", "psc_slab_fft_x", "psc_slab_transpose_put", "psc_slab_yblocks", "psc_green_slab")
 

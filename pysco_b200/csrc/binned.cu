@@ -57,6 +57,12 @@ struct BinLayout {
                      //              pass can drop its records straight into place without a count pass.
   int *tmp;          // [nbins + 1]  capacities / fall-back offsets
   int *overflow;     // [1] set by the direct scatter when a bin ran out of slack: the exact binning is redone
+  // sorted layout only (with_rec = false): the particle arrays are sorted by a FINER key than the bin -- 64 micro-blocks
+  // of 2^3 cells per bin, in Morton order inside the bin -- so that consecutive particles of a bin sit in neighbouring
+  // cells whatever order they arrived in (the tiles' bank spreading is made for that); base / fill are then derived
+  int64_t nkeys;     // 64 nbins
+  int *fcount;       // [nkeys + 1] counts, then the cursors of the scatter
+  int *fstart;       // [nkeys + 1] first row of every micro-block
   float4 *rec;       // [nrec] binned particles: (x, y, z, source row as int bits) -- one 16-byte access per particle
   int *heavy_count;  // [1] number of entries of `heavy`
   int2 *heavy;       // [heavy_cap] (bin, part >= 1): the parts beyond the first BIN_PART particles of a bin
@@ -74,6 +80,7 @@ static size_t scan_tmp_bytes(int64_t n) {
 }
 
 static int64_t rec_capacity(int64_t np, int64_t nbins) { return np + np / 8 + 40 * nbins + 64; }
+constexpr int MB_PER_BIN = 64;   // micro-blocks (2^3 cells) per bin: the sort key of the sorted layout
 
 static bool bin_layout(void *scratch, size_t bytes, int64_t np, int N, int x0, int nxl, BinLayout &L,
                        bool with_rec = true) {
@@ -91,10 +98,13 @@ static bool bin_layout(void *scratch, size_t bytes, int64_t np, int N, int x0, i
   L.rec = reinterpret_cast<float4 *>(p + off); off += a256(sizeof(float4) * (size_t)L.nrec);
   L.overflow = reinterpret_cast<int *>(p + off); off += 128;
   L.heavy_count = reinterpret_cast<int *>(p + off); off += 128;
+  L.nkeys = with_rec ? 0 : L.nbins * MB_PER_BIN;
+  L.fcount = reinterpret_cast<int *>(p + off); off += with_rec ? 0 : a256(sizeof(int) * (L.nkeys + 1));
+  L.fstart = reinterpret_cast<int *>(p + off); off += with_rec ? 0 : a256(sizeof(int) * (L.nkeys + 1));
   L.heavy_cap = (int)(np / BIN_PART) + 1;
   L.heavy = reinterpret_cast<int2 *>(p + off); off += a256(sizeof(int2) * (size_t)L.heavy_cap);
   L.cub_tmp = p + off;
-  L.cub_bytes = scan_tmp_bytes(L.nbins + 1);
+  L.cub_bytes = scan_tmp_bytes((with_rec ? L.nbins : L.nkeys) + 1);
   off += a256(L.cub_bytes);
   return off <= bytes;
 }
@@ -106,6 +116,44 @@ __device__ __forceinline__ int bin_of(float x, float y, float z, float Nf, int N
   const int i = (int)(x * Nf) - x0, j = (int)(y * Nf), k = (int)(z * Nf);
   const int bi = min(max(i >> 3, 0), NBX - 1), bj = min(max(j >> 3, 0), NB - 1), bk = min(max(k >> 3, 0), NB - 1);
   return (bi * NB + bj) * NB + bk;
+}
+
+// Sort key of the bin-ordered particle arrays: 64 * bin + the Morton index (x most significant, as morton.py) of the
+// 2^3-cell micro-block inside the bin.
+__device__ __forceinline__ int fine_key(float x, float y, float z, float Nf, int N, int NB, int x0, int NBX) {
+  int i = (int)(x * Nf) - x0, j = (int)(y * Nf), k = (int)(z * Nf);
+  i = min(max(i, 0), BB * NBX - 1);
+  j = min(max(j, 0), N - 1);
+  k = min(max(k, 0), N - 1);
+  const int b = ((i >> 3) * NB + (j >> 3)) * NB + (k >> 3);
+  const int ii = (i >> 1) & 3, jj = (j >> 1) & 3, kk = (k >> 1) & 3;
+  const int mb = ((ii >> 1) << 5) | ((jj >> 1) << 4) | ((kk >> 1) << 3) | ((ii & 1) << 2) | ((jj & 1) << 1) | (kk & 1);
+  return b * MB_PER_BIN + mb;
+}
+
+__global__ void __launch_bounds__(256) fine_count_kernel(const float *__restrict__ pos, int64_t np, int N, int NB,
+                                                         int x0, int NBX, int *__restrict__ counts) {
+  const float Nf = (float)N;
+  const int lane = threadIdx.x & 31;
+  const int64_t nwarp_iters = (np + 31) >> 5;
+  const int64_t wstride = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < nwarp_iters; w += wstride) {
+    const int64_t n = w * 32 + lane;
+    int b = -1 - lane;
+    if (n < np) b = fine_key(__ldg(&pos[3 * n]), __ldg(&pos[3 * n + 1]), __ldg(&pos[3 * n + 2]), Nf, N, NB, x0, NBX);
+    const unsigned peers = __match_any_sync(0xffffffffu, b);
+    if (b >= 0 && (__ffs(peers) - 1) == lane) atomicAdd(&counts[b], __popc(peers));
+  }
+}
+
+// bin table of the sorted layout from the micro-block table: base[b] = fstart[64 b], fill[b] = rows of the bin
+__global__ void __launch_bounds__(256) bin_extract_kernel(const int *__restrict__ fstart, int nbins,
+                                                          int *__restrict__ base, int *__restrict__ fill) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b > nbins) return;
+  const int s = fstart[(size_t)b * MB_PER_BIN];
+  base[b] = s;
+  fill[b] = b < nbins ? fstart[(size_t)(b + 1) * MB_PER_BIN] - s : 0;
 }
 
 // pass 1: counts[bin] += 1, one atomic per distinct bin per warp
@@ -363,7 +411,7 @@ __global__ void __launch_bounds__(256) step_sort_kernel(const float *__restrict_
         f[c] = wrap01(f[c]);
       }
 #pragma unroll
-      for (int r = 0; r < 4; r++) b[r] = bin_of(f[3 * r], f[3 * r + 1], f[3 * r + 2], Nf, NB, 0, NB);
+      for (int r = 0; r < 4; r++) b[r] = fine_key(f[3 * r], f[3 * r + 1], f[3 * r + 2], Nf, N, NB, 0, NB);
       if (PASS == 2) {
         if (ids) {
           const int4 I = __ldg(reinterpret_cast<const int4 *>(ids) + q);
@@ -376,7 +424,7 @@ __global__ void __launch_bounds__(256) step_sort_kernel(const float *__restrict_
     }
     const bool same = b[0] == b[1] && b[1] == b[2] && b[2] == b[3];
     if (__all_sync(0xffffffffu, same)) {
-      // the common case in a bin-ordered array: one atomic per distinct bin of the warp
+      // four particles of one micro-block in every lane: one atomic per distinct key of the warp
       const unsigned peers = __match_any_sync(0xffffffffu, b[0]);
       const int leader = __ffs(peers) - 1;
       int first = 0;
@@ -430,13 +478,47 @@ __global__ void __launch_bounds__(256) step_sort_kernel(const float *__restrict_
       x[c] = wrap01(p);
       w[c] = vv;
     }
-    const int bb = bin_of(x[0], x[1], x[2], Nf, NB, 0, NB);
+    const int bb = fine_key(x[0], x[1], x[2], Nf, N, NB, 0, NB);
     const int first = atomicAdd(&cnt[bb], 1);
     if (PASS == 2) {
       const size_t slot = (size_t)bbase[bb] + first;
 #pragma unroll
       for (int c = 0; c < 3; c++) { pos_out[3 * slot + c] = x[c]; vel_out[3 * slot + c] = w[c]; }
       ids_out[slot] = ids ? ids[n] : (int)n;
+    }
+  }
+}
+
+// slab flavour of the sort (the kick + drift + wrap is a separate pass there: migration sits in between): pass 2 of a
+// counting sort of (position, velocity, 64-bit id) into bin order; pass 1 is bin_count_kernel
+__global__ void __launch_bounds__(256) sort_scatter_kernel(const float *__restrict__ pos, const float *__restrict__ vel,
+                                                           const int64_t *__restrict__ ids, int64_t np, int N, int NB,
+                                                           int x0, int NBX, int *__restrict__ fill,
+                                                           const int *__restrict__ bbase, float *__restrict__ pos_out,
+                                                           float *__restrict__ vel_out, int64_t *__restrict__ ids_out) {
+  const float Nf = (float)N;
+  const int lane = threadIdx.x & 31;
+  const int64_t nwarp_iters = (np + 31) >> 5;
+  const int64_t wstride = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < nwarp_iters; w += wstride) {
+    const int64_t n = w * 32 + lane;
+    float x = 0.f, y = 0.f, z = 0.f;
+    int b = -1 - lane;
+    if (n < np) {
+      x = __ldg(&pos[3 * n]); y = __ldg(&pos[3 * n + 1]); z = __ldg(&pos[3 * n + 2]);
+      b = fine_key(x, y, z, Nf, N, NB, x0, NBX);
+    }
+    const unsigned peers = __match_any_sync(0xffffffffu, b);
+    const int leader = __ffs(peers) - 1;
+    int first = 0;
+    if (b >= 0 && leader == lane) first = atomicAdd(&fill[b], __popc(peers));
+    first = __shfl_sync(0xffffffffu, first, leader);
+    if (b >= 0) {
+      const size_t slot = (size_t)bbase[b] + first + __popc(peers & ((1u << lane) - 1u));
+      pos_out[3 * slot] = x; pos_out[3 * slot + 1] = y; pos_out[3 * slot + 2] = z;
+      vel_out[3 * slot] = __ldg(&vel[3 * n]); vel_out[3 * slot + 1] = __ldg(&vel[3 * n + 1]);
+      vel_out[3 * slot + 2] = __ldg(&vel[3 * n + 2]);
+      ids_out[slot] = ids[n];
     }
   }
 }
@@ -1171,11 +1253,36 @@ int psc_interp_kick_phi_binned_slab(const float *phi_ghost, const float *u_ghost
 }
 
 /* ----------------------------------------------------------- particle arrays in bin order (the time loop) */
+static size_t sorted_bytes(int64_t np, int64_t nbins) {
+  const int64_t nkeys = nbins * MB_PER_BIN;
+  if (nkeys + 1 >= ((int64_t)1 << 31)) return 0;
+  return 4 * a256(sizeof(int) * (nbins + 1)) + 256 + 2 * a256(sizeof(int) * (size_t)(nkeys + 1)) +
+         a256(sizeof(int2) * (size_t)(np / BIN_PART + 1)) + a256(scan_tmp_bytes(nkeys + 1)) + 256;
+}
 size_t psc_sorted_workspace_bytes(int64_t np, int N) {
   if (np < 0 || !slab_ok(N, 0, N)) return 0;
-  const int64_t nbins = (int64_t)(N / BB) * (N / BB) * (N / BB);
-  return 4 * a256(sizeof(int) * (nbins + 1)) + 256 + a256(sizeof(int2) * (size_t)(np / BIN_PART + 1)) +
-         a256(scan_tmp_bytes(nbins + 1)) + 256;
+  return sorted_bytes(np, (int64_t)(N / BB) * (N / BB) * (N / BB));
+}
+
+// the tail of both sorts: micro-block table -> bin table -> list of the bins split into parts
+static int sorted_finish(const BinLayout &L, cudaStream_t st) {
+  bin_extract_kernel<<<(int)((L.nbins + 256) / 256), 256, 0, st>>>(L.fstart, (int)L.nbins, L.base, L.fill);
+  bin_heavy_list_kernel<<<(int)((L.nbins + 255) / 256), 256, 0, st>>>(L.fill, (int)L.nbins, L.heavy_count, L.heavy,
+                                                                     L.heavy_cap);
+  count_launch(2);
+  PSC_CHECK_LAUNCH();
+  return PSC_OK;
+}
+
+static int scan_keys(const BinLayout &L, cudaStream_t st) {
+  size_t bytes = L.cub_bytes;
+  cudaError_t e = cub::DeviceScan::ExclusiveSum(L.cub_tmp, bytes, L.fcount, L.fstart, (int)(L.nkeys + 1), st);
+  count_launch(2);
+  if (e != cudaSuccess) {
+    set_error("psc_step_sort: cub scan failed: %s", cudaGetErrorString(e));
+    return PSC_ERR_CUDA;
+  }
+  return PSC_OK;
 }
 
 int psc_step_sort(const float *pos, const float *vel, const float *acc, const int *ids, int64_t np, float half_dt,
@@ -1190,40 +1297,35 @@ int psc_step_sort(const float *pos, const float *vel, const float *acc, const in
     return PSC_ERR_WORKSPACE;
   }
   cudaStream_t st = as_stream(stream);
-  PSC_CUDA(cudaMemsetAsync(L.counts, 0, sizeof(int) * (L.nbins + 1), st));
-  PSC_CUDA(cudaMemsetAsync(L.fill, 0, sizeof(int) * (L.nbins + 1), st));
+  PSC_CUDA(cudaMemsetAsync(L.fcount, 0, sizeof(int) * (size_t)(L.nkeys + 1), st));
   PSC_CUDA(cudaMemsetAsync(L.heavy_count, 0, sizeof(int), st));
+  const int g = grid_for((np + 3) / 4, 256, 8);
   if (np > 0) {
     PSC_CHECK_ARG(pos && vel && acc && pos_out && vel_out && ids_out, "null pointer");
     PSC_CHECK_ARG(pos != pos_out && vel != vel_out && ids != ids_out, "the sort is out of place");
     PSC_CHECK_ARG((((uintptr_t)pos | (uintptr_t)vel | (uintptr_t)acc | (uintptr_t)ids) & 15) == 0,
                   "pointers must be 16-byte aligned");
-    const int g = grid_for((np + 3) / 4, 256, 8);
     if (dt_is_f64)
-      step_sort_kernel<true, 1><<<g, 256, 0, st>>>(pos, vel, acc, ids, np, half_dt, dt, N, L.NB, L.counts, nullptr,
+      step_sort_kernel<true, 1><<<g, 256, 0, st>>>(pos, vel, acc, ids, np, half_dt, dt, N, L.NB, L.fcount, nullptr,
                                                   nullptr, nullptr, nullptr);
     else
-      step_sort_kernel<false, 1><<<g, 256, 0, st>>>(pos, vel, acc, ids, np, half_dt, dt, N, L.NB, L.counts, nullptr,
+      step_sort_kernel<false, 1><<<g, 256, 0, st>>>(pos, vel, acc, ids, np, half_dt, dt, N, L.NB, L.fcount, nullptr,
                                                    nullptr, nullptr, nullptr);
     count_launch();
   }
-  int rc = scan_bins(L, L.counts, L.base, st);
+  int rc = scan_keys(L, st);
   if (rc != PSC_OK) return rc;
+  PSC_CUDA(cudaMemsetAsync(L.fcount, 0, sizeof(int) * (size_t)(L.nkeys + 1), st));   // now the cursors
   if (np > 0) {
-    const int g = grid_for((np + 3) / 4, 256, 8);
     if (dt_is_f64)
-      step_sort_kernel<true, 2><<<g, 256, 0, st>>>(pos, vel, acc, ids, np, half_dt, dt, N, L.NB, L.fill, L.base,
+      step_sort_kernel<true, 2><<<g, 256, 0, st>>>(pos, vel, acc, ids, np, half_dt, dt, N, L.NB, L.fcount, L.fstart,
                                                   pos_out, vel_out, ids_out);
     else
-      step_sort_kernel<false, 2><<<g, 256, 0, st>>>(pos, vel, acc, ids, np, half_dt, dt, N, L.NB, L.fill, L.base,
+      step_sort_kernel<false, 2><<<g, 256, 0, st>>>(pos, vel, acc, ids, np, half_dt, dt, N, L.NB, L.fcount, L.fstart,
                                                    pos_out, vel_out, ids_out);
     count_launch();
   }
-  bin_heavy_list_kernel<<<(int)((L.nbins + 255) / 256), 256, 0, st>>>(L.fill, (int)L.nbins, L.heavy_count, L.heavy,
-                                                                     L.heavy_cap);
-  count_launch();
-  PSC_CHECK_LAUNCH();
-  return PSC_OK;
+  return sorted_finish(L, st);
 }
 
 int psc_deposit_sorted(const float *pos_sorted, const void *scratch, size_t scratch_bytes, int64_t np, int N, int scheme,
@@ -1256,6 +1358,68 @@ int psc_scatter3_by_id(const int *ids, const float *in, float *out, int64_t np, 
   count_launch();
   PSC_CHECK_LAUNCH();
   return PSC_OK;
+}
+
+/* ---- the same on a slab: the particle arrays of the rank are sorted into bin order after the migration */
+size_t psc_sorted_workspace_bytes_slab(int64_t np, int N, int nxl) {
+  if (np < 0 || !slab_ok(N, 0, nxl)) return 0;
+  return sorted_bytes(np, (int64_t)(nxl / BB) * (N / BB) * (N / BB));
+}
+
+int psc_sort_by_bin_slab(const float *pos, const float *vel, const int64_t *ids, int64_t np, int N, int x0, int nxl,
+                         void *scratch, size_t scratch_bytes, float *pos_out, float *vel_out, int64_t *ids_out,
+                         void *stream) {
+  PSC_CHECK_ARG(np >= 0 && np < ((int64_t)1 << 31), "np out of range");
+  PSC_CHECK_ARG(slab_ok(N, x0, nxl), "N and the slab thickness must be multiples of 8");
+  PSC_CHECK_ARG(scratch && ((uintptr_t)scratch & 255) == 0, "scratch must be 256-byte aligned");
+  BinLayout L;
+  if (!bin_layout(scratch, scratch_bytes, np, N, x0, nxl, L, false)) {
+    set_error("psc_sort_by_bin_slab: scratch too small");
+    return PSC_ERR_WORKSPACE;
+  }
+  cudaStream_t st = as_stream(stream);
+  PSC_CUDA(cudaMemsetAsync(L.fcount, 0, sizeof(int) * (size_t)(L.nkeys + 1), st));
+  PSC_CUDA(cudaMemsetAsync(L.heavy_count, 0, sizeof(int), st));
+  if (np > 0) {
+    PSC_CHECK_ARG(pos && vel && ids && pos_out && vel_out && ids_out, "null pointer");
+    PSC_CHECK_ARG(pos != pos_out && vel != vel_out && ids != ids_out, "the sort is out of place");
+    fine_count_kernel<<<grid_for(np, 256, 8), 256, 0, st>>>(pos, np, N, L.NB, x0, L.NBX, L.fcount);
+    count_launch();
+  }
+  int rc = scan_keys(L, st);
+  if (rc != PSC_OK) return rc;
+  PSC_CUDA(cudaMemsetAsync(L.fcount, 0, sizeof(int) * (size_t)(L.nkeys + 1), st));
+  if (np > 0) {
+    sort_scatter_kernel<<<grid_for(np, 256, 8), 256, 0, st>>>(pos, vel, ids, np, N, L.NB, x0, L.NBX, L.fcount, L.fstart,
+                                                              pos_out, vel_out, ids_out);
+    count_launch();
+  }
+  return sorted_finish(L, st);
+}
+
+int psc_deposit_sorted_slab(const float *pos_sorted, const void *scratch, size_t scratch_bytes, int64_t np, int N, int x0,
+                            int nxl, int scheme, float *rho_ghost, void *stream) {
+  PSC_CHECK_ARG(scheme == PSC_NGP || scheme == PSC_CIC || scheme == PSC_TSC, "unknown mass scheme");
+  PSC_CHECK_ARG(slab_ok(N, x0, nxl), "N and the slab thickness must be multiples of 8");
+  PSC_CHECK_ARG(scratch && rho_ghost && (pos_sorted || np == 0), "null pointer");
+  static const float dummy = 0.0f;
+  return deposit_binned_impl(scratch, scratch_bytes, np, N, x0, nxl, 1, scheme, 1.0f, 1.0f, 0.0f, rho_ghost, stream,
+                             pos_sorted ? pos_sorted : &dummy);
+}
+
+int psc_interp_kick_phi_sorted_slab(const float *phi_ghost, const float *u_ghost, float f, int fr_n, int order, int x0,
+                                    int nxl, int ghost, const float *pos_sorted, const void *scratch,
+                                    size_t scratch_bytes, float *vel_sorted, float *acc_sorted, int64_t np, int N,
+                                    int scheme, float half_dt, float *maxout, void *stream) {
+  PSC_CHECK_ARG(scheme == PSC_CIC || scheme == PSC_TSC, "mass scheme must be CIC or TSC");
+  PSC_CHECK_ARG(order == 2 || order == 3 || order == 5 || order == 7, "gradient order must be 2, 3, 5 or 7");
+  PSC_CHECK_ARG(fr_n >= 0 && fr_n <= 2, "fR_n must be 1 or 2");
+  PSC_CHECK_ARG(slab_ok(N, x0, nxl) && N >= 2 * BB, "N and the slab thickness must be multiples of 8");
+  PSC_CHECK_ARG(ghost >= 1 + (order == 7 ? 3 : order == 5 ? 2 : 1), "not enough ghost planes for this stencil");
+  PSC_CHECK_ARG(phi_ghost && scratch && acc_sorted && maxout && (u_ghost || fr_n == 0) && (pos_sorted || np == 0),
+                "null pointer");
+  return interp_kick_phi_impl(phi_ghost, u_ghost, f, fr_n, order, x0, nxl, ghost, scratch, scratch_bytes, vel_sorted,
+                              acc_sorted, np, N, scheme, half_dt, maxout, stream, pos_sorted);
 }
 
 }  // extern "C"

@@ -348,6 +348,7 @@ class CudaOps:
         self._plan = None
         self._work = None
         self._scratch = None
+        self._sorted = None
         self._leavers = None
         self._mig = None
         self._sortws = None
@@ -467,6 +468,36 @@ class CudaOps:
         _lib.check(self.lib.psc_bin_particles_slab(_lib.ptr(pos), n, self.N, self.x0, self.nxl,
                                                    _lib.ptr(self._scratch), self._scratch.numel(), _lib.stream()))
         return n
+
+    # -- particles <-> mesh on particle arrays kept in bin order (no binned copy, no source-row indirection)
+    sorted_layout = True
+
+    def sort_by_bin(self, pos, vel, ids, pos_out, vel_out, ids_out):
+        """counting sort of the rank's (position, velocity, id) rows into bin order; leaves the bin table in the scratch"""
+        n = pos.shape[0]
+        nbytes = int(self.lib.psc_sorted_workspace_bytes_slab(n, self.N, self.nxl))
+        if self._sorted is None or self._sorted.numel() < nbytes:
+            self._sorted = None
+            self._sorted = torch.empty((int(nbytes * 1.1) + 256,), dtype=torch.uint8, device=self.dev)
+        _lib.check(self.lib.psc_sort_by_bin_slab(_lib.ptr(pos), _lib.ptr(vel), _lib.ptr(ids), n, self.N, self.x0, self.nxl,
+                                                 _lib.ptr(self._sorted), self._sorted.numel(), _lib.ptr(pos_out),
+                                                 _lib.ptr(vel_out), _lib.ptr(ids_out), _lib.stream()))
+        return n
+
+    def deposit_sorted(self, pos, scheme):
+        rho = torch.empty((self.nxl + 2, self.N, self.N), dtype=torch.float32, device=self.dev)
+        _lib.check(self.lib.psc_deposit_sorted_slab(_lib.ptr(pos), _lib.ptr(self._sorted), self._sorted.numel(),
+                                                    pos.shape[0], self.N, self.x0, self.nxl, scheme, _lib.ptr(rho),
+                                                    _lib.stream()))
+        return rho
+
+    def interp_kick_phi_sorted(self, phi_g, ghost, order, pos, vel, acc, scheme, half_dt, u_g=None, f=0.0, fr_n=0):
+        mx = torch.zeros((2,), dtype=torch.float32, device=self.dev)
+        _lib.check(self.lib.psc_interp_kick_phi_sorted_slab(
+            _lib.ptr(phi_g), _lib.ptr(u_g), float(f), int(fr_n), order, self.x0, self.nxl, ghost, _lib.ptr(pos),
+            _lib.ptr(self._sorted), self._sorted.numel(), _lib.ptr(vel), _lib.ptr(acc), pos.shape[0], self.N, scheme,
+            float(half_dt), _lib.ptr(mx), _lib.stream()))
+        return mx
 
     def deposit(self, binned, scheme):
         rho = torch.empty((self.nxl + 2, self.N, self.N), dtype=torch.float32, device=self.dev)
@@ -1105,8 +1136,17 @@ class Slab:
         param["save_pk"] = sps == "yes" or (sps == "z_out" and bool(param["write_snapshot"]))
         n = self.np
         self._mark("migrate")
-        binned = ops.bin(self.pos[:n])
-        rho = ops.deposit(binned, scheme)                      # [nxl + 2, N, N] raw sums
+        sorted_layout = bool(getattr(ops, "sorted_layout", False)) and not os.environ.get("PSC_SLAB_SHADOW_BINNING")
+        if sorted_layout:
+            # the rank's particle arrays are sorted into bin order (the acceleration buffer, dead until the
+            # interpolation rewrites it, and the reorder's spare take the sorted copies): deposit and interpolation
+            # then read position / velocity in place
+            self._sort_by_bin()
+            binned = n
+            rho = ops.deposit_sorted(self.pos[:n], scheme)
+        else:
+            binned = ops.bin(self.pos[:n])
+            rho = ops.deposit(binned, scheme)                      # [nxl + 2, N, N] raw sums
         self._mark("bin+deposit")
         from_left, from_right = comm.exchange_planes(rho[0:1], rho[nxl + 1:nxl + 2])
         rho[1] += from_left[0]         # the left neighbour's plane nxl + 1 is my first owned plane
@@ -1158,12 +1198,12 @@ class Slab:
         phi_g[nxl + G:] = from_right   # the right neighbour's first G owned planes
         half_dt = 0.0 if kick is None else kick
         self._mark("potential ghosts")
-        if u_g is not None:
-            mx = ops.interp_kick_phi(phi_g, G, order, binned, self.vel[:n] if kick is not None else None,
-                                     self.acc[:n], scheme, half_dt, u_g, half_c2, fr_n)
+        vel_k = self.vel[:n] if kick is not None else None
+        extra = (u_g, half_c2, fr_n) if u_g is not None else ()
+        if sorted_layout:
+            mx = ops.interp_kick_phi_sorted(phi_g, G, order, self.pos[:n], vel_k, self.acc[:n], scheme, half_dt, *extra)
         else:
-            mx = ops.interp_kick_phi(phi_g, G, order, binned, self.vel[:n] if kick is not None else None,
-                                     self.acc[:n], scheme, half_dt)
+            mx = ops.interp_kick_phi(phi_g, G, order, binned, vel_k, self.acc[:n], scheme, half_dt, *extra)
         self.potential = phi_g[G:G + nxl]
         if kick is None:
             mx[1] = ops.max_abs(self.vel[:n])[0]
@@ -1229,6 +1269,20 @@ class Slab:
             param["write_snapshot"] = False
         self.leapfrog(dt, tables, param)
         return dt
+
+    def _sort_by_bin(self):
+        """Sort the rank's particle rows (position, velocity, id) into bin order, out of place: positions go to the
+        reorder's spare buffer, velocities to the acceleration buffer (its content is dead here: the kick has used it
+        and the interpolation rewrites every row), ids to the spare id buffer; the buffers then swap roles."""
+        n = self.np
+        cap = self.pos.shape[0]
+        dev = self._device()
+        if self._spare3 is None or self._spare3.shape[0] != cap:
+            self._spare3 = torch.empty((cap, 3), dtype=torch.float32, device=dev)
+            self._spare1 = torch.empty((cap,), dtype=torch.int64, device=dev)
+        self.ops.sort_by_bin(self.pos[:n], self.vel[:n], self.ids[:n], self._spare3[:n], self.acc[:n], self._spare1[:n])
+        self.pos, self.vel, self.acc, self._spare3 = self._spare3, self.acc, self.vel, self.pos
+        self.ids, self._spare1 = self._spare1, self.ids
 
     def reorder(self):
         """utils.reorder_particles (utils.py:1019-1075) on the local particles (the Morton key's leading bits are

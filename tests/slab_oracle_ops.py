@@ -161,6 +161,34 @@ class OracleOps:
         assert (own == self.rank).all(), "binning particles that are not in the slab"
         return pos.shape[0]
 
+    # the bin-ordered layout: a stable sort by (bin, micro-block) key -- the CUDA sort is not stable inside a key,
+    # which no consumer depends on
+    sorted_layout = True
+
+    def sort_by_bin(self, pos, vel, ids, pos_out, vel_out, ids_out):
+        own = self._owner(pos)
+        assert (own == self.rank).all(), "sorting particles that are not in the slab"
+        N = self.N
+        c = np.minimum((_np(pos) * np.float32(N)).astype(np.int64), N - 1)
+        NB = N // 8
+        i = c[:, 0] - self.x0
+        b = ((i >> 3) * NB + (c[:, 1] >> 3)) * NB + (c[:, 2] >> 3)
+        ii, jj, kk = (i >> 1) & 3, (c[:, 1] >> 1) & 3, (c[:, 2] >> 1) & 3
+        mb = ((ii >> 1) << 5) | ((jj >> 1) << 4) | ((kk >> 1) << 3) | ((ii & 1) << 2) | ((jj & 1) << 1) | (kk & 1)
+        order = torch.from_numpy(np.argsort(b * 64 + mb, kind="stable"))
+        pos_out.copy_(pos[order])
+        vel_out.copy_(vel[order])
+        ids_out.copy_(ids[order])
+        return pos.shape[0]
+
+    def deposit_sorted(self, pos, scheme):
+        self._binned = np.ascontiguousarray(_np(pos))
+        return self.deposit(pos.shape[0], scheme)
+
+    def interp_kick_phi_sorted(self, phi_g, ghost, order, pos, vel, acc, scheme, half_dt, u_g=None, f=0.0, fr_n=0):
+        self._binned = np.ascontiguousarray(_np(pos))
+        return self.interp_kick_phi(phi_g, ghost, order, pos.shape[0], vel, acc, scheme, half_dt, u_g, f, fr_n)
+
     def _planes(self, ghost):
         return np.arange(self.x0 - ghost, self.x0 + self.nxl + ghost) % self.N
 
