@@ -231,36 +231,53 @@ def clustered_positions(pos, N, seed=7, nblobs=4096, sigma_cells=0.7):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md).  nvidia-smi needs a
+    fraction of a second to start, which is as long as the timed region of a short run: the sampler is started ahead
+    of it (before the untimed pre-roll steps, same kernels, same load) and every sample carries its arrival time, so
+    that only the samples taken between mark_begin() and mark_end() are reported."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index):
         self.gpu, self.rows, self.proc = gpu_index, [], None
+        self.t0 = self.t1 = None
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-i", str(self.gpu), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+                                          "-i", str(self.gpu), "-lms", "50"], stdout=subprocess.PIPE, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
             self.proc = None
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
+
+    def mark_begin(self):
+        self.t0 = time.time()
+
+    def mark_end(self):
+        self.t1 = time.time()
 
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        if self.t1 is not None and not any(self.t0 <= t <= self.t1 + 0.06 for t, _ in self.rows):
+            time.sleep(0.15)          # let a sample that was in flight arrive
         self.proc.terminate()
-        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        rows = [r for t, r in self.rows if len(r) >= 7]
+        inside = [r for t, r in self.rows if len(r) >= 7 and self.t0 is not None and self.t0 <= t <= self.t1 + 0.06]
+        window = "timed region"
+        if not inside:                # a timed region shorter than the sampling period: the samples next to it
+            inside, window = rows[-3:], "last samples before the end of the timed region (same load: pre-roll steps)"
+        sm = [float(r[0]) for r in inside if r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in inside if r[1].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i].lower() == "active"})
+        reasons = sorted({names[i] for r in inside for i in range(4) if r[3 + i].lower() == "active"})
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+                "reasons": reasons, "samples": len(sm), "window": window}
 
 
 def measured_peak_gbs():
@@ -505,14 +522,15 @@ def run_gpu_arm(args):
     # the timed window sits in the middle of the 50-step reorder cycle
     preroll = max(0, (N_REORDER - K) // 2) if K < N_REORDER else 0
     param["nsteps"] = 0
+    sampler = ClockSampler(torch.cuda.current_device())
+    sampler.start()
     for _ in range(preroll):
         step()
 
-    sampler = ClockSampler(torch.cuda.current_device())
     _lib.enable_timing(True)
     launches0 = _lib.launch_count()
     torch.cuda.synchronize()
-    sampler.start()
+    sampler.mark_begin()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     n_reorders = 0
@@ -520,6 +538,7 @@ def run_gpu_arm(args):
         n_reorders += bool(step())
     ev1.record()
     torch.cuda.synchronize()
+    sampler.mark_end()
     clocks = sampler.stop()
     launches = _lib.launch_count() - launches0
     records = _lib.timing_records()
@@ -679,16 +698,17 @@ def slab_measure(S, param, tables, K, warmup, world, rank, local_rank, with_phas
     t_reorder_ms = e0.elapsed_time(e1)
     preroll = max(0, (N_REORDER - K) // 2) if K < N_REORDER else 0
     param["nsteps"] = 0
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
     for _ in range(preroll):
         step()
 
-    sampler = ClockSampler(local_rank)
     _lib.enable_timing(True)
     S.phase_marks = [] if with_phases else None
     launches0 = _lib.launch_count()
     barrier()
-    if rank == 0:
-        sampler.start()
+    sampler.mark_begin()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     n_reorders = 0
@@ -698,6 +718,7 @@ def slab_measure(S, param, tables, K, warmup, world, rank, local_rank, with_phas
         migrated += S.migrated_last[0]
     ev1.record()
     barrier()
+    sampler.mark_end()
     clocks = sampler.stop() if rank == 0 else None
     launches = _lib.launch_count() - launches0
     records = _lib.timing_records()
