@@ -127,14 +127,20 @@ int psc_bin_particles_counted(const float *pos, int64_t np, int N, void *scratch
  * psc_interp_kick_phi_sorted (as psc_interp_kick_phi_binned; vel / acc rows are the rows of pos_sorted) consume.
  * psc_scatter3_by_id: out[ids[n]] = in[n], the way back to the reference's particle order. */
 size_t psc_sorted_workspace_bytes(int64_t np, int N);
+/* The scratch holds TWO bin tables.  src_table = -1: the input arrays are in no particular order (first step, after a
+ * Morton reorder): one global atomic per particle and pass, result in table 0.  src_table = 0 / 1: the input arrays
+ * are the bin-ordered output of a previous call, described by that table: one CTA per source bin counts and sorts its
+ * particles in shared memory by (destination bin, 2^3-cell micro-block in Morton order) and writes contiguous runs;
+ * result in table 1 - src_table.  `table` of the two consumers = the table the sort wrote. */
 int psc_step_sort(const float *pos, const float *vel, const float *acc, const int *ids, int64_t np, float half_dt,
-                  double dt, int dt_is_f64, int N, void *scratch, size_t scratch_bytes, float *pos_out, float *vel_out,
-                  int *ids_out, void *stream);
-int psc_deposit_sorted(const float *pos_sorted, const void *scratch, size_t scratch_bytes, int64_t np, int N, int scheme,
-                       float scale, float f1, float f2, float *rho, void *stream);
+                  double dt, int dt_is_f64, int N, int src_table, void *scratch, size_t scratch_bytes, float *pos_out,
+                  float *vel_out, int *ids_out, void *stream);
+int psc_deposit_sorted(const float *pos_sorted, const void *scratch, size_t scratch_bytes, int table, int64_t np, int N,
+                       int scheme, float scale, float f1, float f2, float *rho, void *stream);
 int psc_interp_kick_phi_sorted(const float *phi, const float *u, float f, int fr_n, int order, const float *pos_sorted,
-                               const void *scratch, size_t scratch_bytes, float *vel_sorted, float *acc_sorted,
-                               int64_t np, int N, int scheme, float half_dt, float *maxout, void *stream);
+                               const void *scratch, size_t scratch_bytes, int table, float *vel_sorted,
+                               float *acc_sorted, int64_t np, int N, int scheme, float half_dt, float *maxout,
+                               void *stream);
 int psc_scatter3_by_id(const int *ids, const float *in, float *out, int64_t np, void *stream);
 /* the bin-ordered layout on a slab: after the migration the rank's (position, velocity, 64-bit id) arrays are sorted
  * into bin order (out of place); the deposit / interpolation then read them in place, as the two entries above. */

@@ -14,6 +14,13 @@
 // The sweep is OUT OF PLACE: a neighbouring CTA needs the OLD values of this CTA's edge cells whenever it gets to them.
 // Arithmetic and association of the neighbour sum are those of gs_colour_kernel, so the result is bit-identical to the
 // two-launch sweep (tests/test_gs_fused_gpu.py).
+//
+// Measured at 512^3 (profiles/r02_multigrid_kernels.txt, r02_grid_kernels_ncu.txt): DRAM traffic 1.71 GB per sweep
+// against 3.14 GB for the two colour launches, 0.687 ms against 0.717 ms -- the kernel is bound by instruction issue and
+// barrier / copy latency (three barriers per plane, 47 % issue-active), not by HBM.  A second version (lanes of a warp on
+// two rows so that the stride-2 colour accesses hit distinct banks, fully unrolled task loops, five-plane ring with the
+// next plane's TMA in flight under the arithmetic on a second mbarrier) removed the 2-way bank conflicts but issued more
+// instructions and ran at 0.79 ms; this first version is the one kept.
 #include <cuda/barrier>
 #include <cuda/ptx>
 
@@ -94,26 +101,16 @@ __device__ __forceinline__ void gsf_stage_plane(const float *__restrict__ x, int
   }
 }
 
-constexpr int GF_RING = 5;   // planes s - 1 .. s + 2 in use, plane s + 3 in flight
-constexpr size_t GF_SMEM = sizeof(float) * GF_RING * GF_PLANE + 64;
-
-__device__ __forceinline__ int gsf_slot(int p) { return (p + 2 * GF_RING) % GF_RING; }
-
-// Thread mapping of both stages: a warp works on TWO adjacent rows, 16 lanes each, every lane one cell of its row's
-// colour (columns two apart).  The two rows have opposite colour offsets and the row pitch (72 floats) is a multiple
-// of 8 banks, so the half-warps read the even and the odd banks respectively: no conflicts, where a warp spread along
-// ONE row of stride-2 cells hits every bank twice (ncu: 1.97 wavefronts per LDS in the first version).
 template <int KIND, bool TMA>
 __global__ void __launch_bounds__(GF_THREADS) gs_fused_kernel(const float *__restrict__ x, const float *__restrict__ b,
                                                               float q_val, const float *__restrict__ q_dev,
                                                               const float *__restrict__ rhs, int N, float f_relax,
                                                               float *__restrict__ out) {
-  extern __shared__ __align__(128) unsigned char gsf_raw[];
-  float(*ring)[GF_PLANE] = reinterpret_cast<float(*)[GF_PLANE]>(gsf_raw);
-  gsf_barrier *bar = reinterpret_cast<gsf_barrier *>(gsf_raw + sizeof(float) * GF_RING * GF_PLANE);   // two barriers
+  __shared__ __align__(128) float ring[4][GF_PLANE];
+#pragma nv_diag_suppress static_var_with_dynamic_init
+  __shared__ gsf_barrier bar;
   const float q = q_dev ? *q_dev : q_val;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int half = lane >> 4, l16 = lane & 15;
+  const int tid = threadIdx.x;
   const int k0 = blockIdx.x * GF_TK, j0 = blockIdx.y * GF_TJ, i0 = blockIdx.z * GF_CHUNK;
   const int i1 = min(N, i0 + GF_CHUNK);
   const float h2 = 1.0f / ((float)N * (float)N);
@@ -121,18 +118,19 @@ __global__ void __launch_bounds__(GF_THREADS) gs_fused_kernel(const float *__res
   const size_t N2 = (size_t)N * N;
   if (TMA) {
     if (tid == 0) {
-      init(&bar[0], GF_THREADS);
-      init(&bar[1], GF_THREADS);
+      init(&bar, GF_THREADS);
       cuda::ptx::fence_proxy_async(cuda::ptx::space_shared);
     }
     __syncthreads();
   }
-  int batch = 0;   // loads are issued in batches; batch n completes on bar[n & 1] (TMA) -- one batch may be in flight
-                   // while the previous one is waited for
-  auto stage = [&](int p, int n) { gsf_stage_plane<TMA>(x, N, wrap(p, N), j0, k0, ring[gsf_slot(p)], &bar[n & 1]); };
-  auto landed = [&](int n) {
-    if (TMA) bar[n & 1].arrive_and_wait();
-    else __syncthreads();
+
+  // all threads: wait until the planes staged since the last call have landed
+  auto landed = [&]() {
+    if (TMA) {
+      bar.arrive_and_wait();
+    } else {
+      __syncthreads();
+    }
   };
   // before the async proxy overwrites a ring slot that this CTA has read / written through the generic proxy
   auto release_slot = [&]() {
@@ -142,62 +140,49 @@ __global__ void __launch_bounds__(GF_THREADS) gs_fused_kernel(const float *__res
 
   // red cells (odd i + j + k) of plane p on the tile + one ring; neighbours: old black cells
   auto red_stage = [&](int p) {
-    const float *lo = ring[gsf_slot(p - 1)], *hi = ring[gsf_slot(p + 1)];
-    float *mid = ring[gsf_slot(p)];
-    const size_t pbase = (size_t)wrap(p, N) * N2;
-#pragma unroll
-    for (int it = 0; it < 5; it++) {
-      const int t = warp + 8 * it;          // 34 (row pair, column group) tasks + 2 tasks for the last column
-      int r, m;
-      if (t < 34) { r = 1 + 2 * (t >> 1) + half; m = 16 * (t & 1) + l16; }
-      else { r = 1 + 32 * (t - 34) + lane; m = GF_TK / 2; }
-      if (t < 36 && r <= GF_TJ + 2) {
-        const int c = 3 + 2 * m + ((p + r) & 1);             // staged column (global k = k0 - 4 + c), odd parity
-        const int o = r * GF_RK + c;
-        const float s6 = ((((gsf_pw<KIND>(lo[o]) + gsf_pw<KIND>(mid[o - GF_RK])) + gsf_pw<KIND>(mid[o - 1])) +
-                           gsf_pw<KIND>(mid[o + 1])) + gsf_pw<KIND>(mid[o + GF_RK])) + gsf_pw<KIND>(hi[o]);
-        const size_t g = pbase + (size_t)wrap(j0 - 2 + r, N) * N + wrap(k0 - 4 + c, N);
-        mid[o] = gsf_update<KIND>(mid[o], s6, __ldg(&b[g]), q, has_rhs, has_rhs ? __ldg(&rhs[g]) : 0.0f, h2, f_relax);
-      }
+    const float *lo = ring[(p - 1) & 3], *hi = ring[(p + 1) & 3];
+    float *mid = ring[p & 3];
+    const int gp = wrap(p, N);
+    for (int idx = tid; idx < (GF_TJ + 2) * (GF_TK / 2 + 1); idx += GF_THREADS) {
+      const int rr = idx / (GF_TK / 2 + 1), m = idx - rr * (GF_TK / 2 + 1);
+      const int r = 1 + rr;                                  // staged row (global j = j0 - 2 + r)
+      const int c = 3 + 2 * m + ((p + r) & 1);               // staged column (global k = k0 - 4 + c), odd parity
+      const int o = r * GF_RK + c;
+      const float s6 = ((((gsf_pw<KIND>(lo[o]) + gsf_pw<KIND>(mid[o - GF_RK])) + gsf_pw<KIND>(mid[o - 1])) +
+                         gsf_pw<KIND>(mid[o + 1])) + gsf_pw<KIND>(mid[o + GF_RK])) + gsf_pw<KIND>(hi[o]);
+      const size_t t = (size_t)gp * N2 + (size_t)wrap(j0 - 2 + r, N) * N + wrap(k0 - 4 + c, N);
+      mid[o] = gsf_update<KIND>(mid[o], s6, __ldg(&b[t]), q, has_rhs, has_rhs ? __ldg(&rhs[t]) : 0.0f, h2, f_relax);
     }
   };
   // black cells (even parity) of plane p on the tile, from the updated red cells; writes the finished plane
   auto black_stage = [&](int p) {
-    const float *lo = ring[gsf_slot(p - 1)], *mid = ring[gsf_slot(p)], *hi = ring[gsf_slot(p + 1)];
-    const size_t pbase = (size_t)p * N2;
-#pragma unroll
-    for (int it = 0; it < 4; it++) {
-      const int t = warp + 8 * it;          // 32 (row pair, column group) tasks
-      const int rr = 2 * (t >> 1) + half, m = 16 * (t & 1) + l16;
+    const float *lo = ring[(p - 1) & 3], *mid = ring[p & 3], *hi = ring[(p + 1) & 3];
+    const size_t base = (size_t)p * N2;
+    for (int idx = tid; idx < GF_TJ * (GF_TK / 2); idx += GF_THREADS) {
+      const int rr = idx / (GF_TK / 2), m = idx - rr * (GF_TK / 2);
       const int r = 2 + rr;
       const int ob = (p + r) & 1;                            // which of the pair (4 + 2m, 5 + 2m) is black
       const int o = r * GF_RK + 4 + 2 * m + ob;
       const float s6 = ((((gsf_pw<KIND>(lo[o]) + gsf_pw<KIND>(mid[o - GF_RK])) + gsf_pw<KIND>(mid[o - 1])) +
                          gsf_pw<KIND>(mid[o + 1])) + gsf_pw<KIND>(mid[o + GF_RK])) + gsf_pw<KIND>(hi[o]);
-      const size_t g = pbase + (size_t)(j0 + rr) * N + (k0 + 2 * m);
-      const float nb = gsf_update<KIND>(mid[o], s6, __ldg(&b[g + ob]), q, has_rhs, has_rhs ? __ldg(&rhs[g + ob]) : 0.0f,
+      const size_t t = base + (size_t)(j0 + rr) * N + (k0 + 2 * m);
+      const float nb = gsf_update<KIND>(mid[o], s6, __ldg(&b[t + ob]), q, has_rhs, has_rhs ? __ldg(&rhs[t + ob]) : 0.0f,
                                         h2, f_relax);
       const float red = mid[o + 1 - 2 * ob];
-      *reinterpret_cast<float2 *>(out + g) = ob ? make_float2(red, nb) : make_float2(nb, red);
+      *reinterpret_cast<float2 *>(out + t) = ob ? make_float2(red, nb) : make_float2(nb, red);
     }
   };
 
-  // prologue: planes i0 - 2 .. i0 + 1 (batch 0), plane i0 + 2 in flight (batch 1) under the first two red stages
-  for (int p = i0 - 2; p <= i0 + 1; p++) stage(p, batch);
-  landed(batch++);
-  if (TMA) stage(i0 + 2, batch);
+  // prologue: planes i0 - 2 .. i0 + 1, red cells of planes i0 - 1 and i0
+  for (int p = i0 - 2; p <= i0 + 1; p++) gsf_stage_plane<TMA>(x, N, wrap(p, N), j0, k0, ring[p & 3], &bar);
+  landed();
   red_stage(i0 - 1);
   __syncthreads();
   red_stage(i0);
   for (int s = i0; s < i1; s++) {
-    release_slot();                                   // red(s) is visible; plane s - 2 is dead
-    if (TMA) {
-      if (s + 3 <= i1 + 1) stage(s + 3, batch + 1);   // into the slot of plane s - 2, under this step's arithmetic
-      landed(batch++);                                // plane s + 2
-    } else {
-      stage(s + 2, batch);
-      landed(batch++);
-    }
+    release_slot();                                   // plane s - 2 is dead: its slot takes plane s + 2
+    gsf_stage_plane<TMA>(x, N, wrap(s + 2, N), j0, k0, ring[(s + 2) & 3], &bar);
+    landed();
     red_stage(s + 1);
     __syncthreads();
     black_stage(s);
@@ -224,20 +209,10 @@ int psc_gauss_seidel_fused(const float *x, const float *b, float q, const float 
   dim3 grid(N / GF_TK, N / GF_TJ, (N + GF_CHUNK - 1) / GF_CHUNK);
   cudaStream_t st = as_stream(stream);
   const float *qd = psc_mg_q_device_ptr();
-  static bool configured = false;   // five planes of 10.1 KB: above the 48 KB a kernel gets without opting in
-  if (!configured) {
-#define GSF_ATTR(K, T) \
-  PSC_CUDA(cudaFuncSetAttribute(gs_fused_kernel<K, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GF_SMEM))
-    GSF_ATTR(PSC_OP_LAPLACIAN, true); GSF_ATTR(PSC_OP_LAPLACIAN, false);
-    GSF_ATTR(PSC_OP_CUBIC, true); GSF_ATTR(PSC_OP_CUBIC, false);
-    GSF_ATTR(PSC_OP_QUARTIC, true); GSF_ATTR(PSC_OP_QUARTIC, false);
-#undef GSF_ATTR
-    configured = true;
-  }
-#define GSF(K)                                                                                                      \
-  do {                                                                                                              \
-    if (use_tma) gs_fused_kernel<K, true><<<grid, GF_THREADS, GF_SMEM, st>>>(x, b, q, qd, rhs, N, f_relax, x_out);  \
-    else gs_fused_kernel<K, false><<<grid, GF_THREADS, GF_SMEM, st>>>(x, b, q, qd, rhs, N, f_relax, x_out);         \
+#define GSF(K)                                                                                       \
+  do {                                                                                               \
+    if (use_tma) gs_fused_kernel<K, true><<<grid, GF_THREADS, 0, st>>>(x, b, q, qd, rhs, N, f_relax, x_out); \
+    else gs_fused_kernel<K, false><<<grid, GF_THREADS, 0, st>>>(x, b, q, qd, rhs, N, f_relax, x_out);        \
   } while (0)
   if (kind == PSC_OP_LAPLACIAN) GSF(PSC_OP_LAPLACIAN);
   else if (kind == PSC_OP_CUBIC) GSF(PSC_OP_CUBIC);

@@ -14,6 +14,12 @@ class Binned:
 
     def __init__(self, scratch, np_, N):
         self.scratch, self.np, self.N = scratch, np_, N
+        # the scratch holds two tables: `table` describes the arrays the last step_sort returned (`owner`, a weak
+        # reference to its position tensor); the next sort reads that table and writes the other one
+        self.table, self.owner = 0, None
+
+    def describes(self, pos):
+        return self.owner is not None and self.owner() is pos
         self.ready = False
         self.mode = 0
 
@@ -35,6 +41,12 @@ class SortedBins:
 
     def __init__(self, scratch, np_, N):
         self.scratch, self.np, self.N = scratch, np_, N
+        # the scratch holds two tables: `table` describes the arrays the last step_sort returned (`owner`, a weak
+        # reference to its position tensor); the next sort reads that table and writes the other one
+        self.table, self.owner = 0, None
+
+    def describes(self, pos):
+        return self.owner is not None and self.owner() is pos
 
 
 _step_sorted = {}
@@ -53,13 +65,23 @@ def step_sorted(np_, ncells_1d):
 
 def step_sort(pos, vel, acc, ids, half_dt, dt, dt_is_f64, sb):
     """integration.py:250-258 (first half-kick, drift, wrap) fused with the re-sort of the particle arrays into bin
-    order: returns NEW (position, velocity, ids) in bin order; `sb` then describes the bins of these arrays."""
+    order: returns NEW (position, velocity, ids) in bin order; `sb` then describes the bins of these arrays.
+
+    When `pos` is the bin-ordered array the previous call returned (sb.describes(pos)), every CTA sorts the particles
+    of one source bin in shared memory (csrc/binned.cu step_sort_local_kernel); otherwise -- first step, arrays
+    reordered by the caller, PSC_NO_LOCAL_SORT=1 -- the sort goes through one global atomic per particle."""
+    import os
+    import weakref
     n = pos.shape[0]
     pos2, vel2 = torch.empty_like(pos), torch.empty_like(vel)
     ids2 = _lib.empty((n,), torch.int32)
+    src = sb.table if (sb.describes(pos) and not os.environ.get("PSC_NO_LOCAL_SORT")) else -1
     _lib.check(_lib.load().psc_step_sort(_lib.ptr(pos), _lib.ptr(vel), _lib.ptr(acc), _lib.ptr(ids), n, float(half_dt),
-                                         float(dt), int(dt_is_f64), sb.N, _lib.ptr(sb.scratch), sb.scratch.numel(),
-                                         _lib.ptr(pos2), _lib.ptr(vel2), _lib.ptr(ids2), _lib.stream()))
+                                         float(dt), int(dt_is_f64), sb.N, src, _lib.ptr(sb.scratch),
+                                         sb.scratch.numel(), _lib.ptr(pos2), _lib.ptr(vel2), _lib.ptr(ids2),
+                                         _lib.stream()))
+    sb.table = 0 if src < 0 else 1 - src
+    sb.owner = weakref.ref(pos2)
     return pos2, vel2, ids2
 
 
@@ -122,8 +144,9 @@ def _deposit(position, ncells_1d, scheme, scale=1.0, f1=1.0, f2=0.0, binned=None
     if binned is None and can_bin(N, pos.shape[0]):
         binned = bin_particles(pos, N)
     if isinstance(binned, SortedBins):
-        _lib.check(lib.psc_deposit_sorted(_lib.ptr(pos), _lib.ptr(binned.scratch), binned.scratch.numel(), binned.np, N,
-                                          scheme, float(scale), float(f1), float(f2), _lib.ptr(rho), _lib.stream()))
+        _lib.check(lib.psc_deposit_sorted(_lib.ptr(pos), _lib.ptr(binned.scratch), binned.scratch.numel(), binned.table,
+                                          binned.np, N, scheme, float(scale), float(f1), float(f2), _lib.ptr(rho),
+                                          _lib.stream()))
     elif binned is not None:
         _lib.check(lib.psc_deposit_binned(_lib.ptr(binned.scratch), binned.scratch.numel(), binned.np, N, scheme,
                                           float(scale), float(f1), float(f2), _lib.ptr(rho), _lib.stream()))
@@ -223,8 +246,8 @@ def interp_kick_phi(potential, u, f, fr_n, order, position, velocity, scheme, ha
     if isinstance(binned, SortedBins):
         _lib.check(_lib.load().psc_interp_kick_phi_sorted(
             _lib.ptr(phi), _lib.ptr(tu), float(np.float32(f)), fr_n, order, _lib.ptr(pos), _lib.ptr(binned.scratch),
-            binned.scratch.numel(), _lib.ptr(vel), _lib.ptr(acc), n, phi.shape[0], scheme, float(half_dt),
-            _lib.ptr(mx), _lib.stream()))
+            binned.scratch.numel(), binned.table, _lib.ptr(vel), _lib.ptr(acc), n, phi.shape[0], scheme,
+            float(half_dt), _lib.ptr(mx), _lib.stream()))
     else:
         _lib.check(_lib.load().psc_interp_kick_phi_binned(
             _lib.ptr(phi), _lib.ptr(tu), float(np.float32(f)), fr_n, order, _lib.ptr(binned.scratch),

@@ -4,6 +4,8 @@ clustered and mixed particle sets (bins of all fills, including bins split into 
 and the path of meshes that cannot be binned (N % 8 != 0).
 
 Tolerance: max|diff| <= 5e-6 rms(reference) for float32 fields; the binning (bin of every record, permutation) is exact."""
+import os
+
 import numpy as np
 import pytest
 
@@ -251,25 +253,35 @@ def test_small_mesh_path_without_binning(psc, orc):
 
 def test_step_sort_is_kick_drift_wrap_plus_a_permutation(psc, orc):
     """psc_step_sort (first half of the leapfrog fused with the re-sort into bin order): the output arrays hold exactly
-    the particles psc_kick_drift_wrap produces, in bin order, with ids = their input rows; a second call carries the
-    ids through; the float64 drift (snapshot-clamped dt) too"""
+    the particles psc_kick_drift_wrap produces, in bin order, with ids = their input rows; the following calls start
+    from bin-ordered arrays (one CTA per source bin, shared-memory sort, tables 0 -> 1 -> 0 ...) and carry the ids
+    through: float64 drift (snapshot-clamped dt), drifts that move many particles into neighbouring bins and a drift of
+    a third of the box (the slow path of the local sort); PSC_NO_LOCAL_SORT=1 keeps the global-atomic sort"""
     import torch
     N = 32
     n = 50003
     pos, vel = cases.particles(N, n, seed=21), cases.velocities(n, seed=22, scale=5e-3)
-    acc = cases.velocities(n, seed=23, scale=1.0)
+    acc = cases.velocities(n, seed=23, scale=2e-3)
     lib, L = psc._lib, psc._lib.load()
     tp, tv, ta = _cuda(pos), _cuda(vel), _cuda(acc)
-    ids = None
+    ids, prev_table = None, 0
     nbins = (N // 8) ** 3
-    for step, dt in enumerate((np.float32(0.021), 0.0193456789012)):
+    for step, dt in enumerate((np.float32(0.021), 0.0193456789012, np.float32(4.0), np.float32(70.0), 2.5,
+                               np.float32(0.3))):
         half = np.float32(0.5 * dt)
         f64 = 0 if isinstance(dt, np.float32) else 1
         rp, rv = tp.clone(), tv.clone()
         lib.check(L.psc_kick_drift_wrap(lib.ptr(rp), lib.ptr(rv), lib.ptr(ta), n, float(half), float(dt), f64, lib.stream()))
         sb = psc.mesh.step_sorted(n, N)
-        sp, sv, sid = psc.mesh.step_sort(tp, tv, ta, ids, half, dt, f64, sb)
+        if step == 5:
+            os.environ["PSC_NO_LOCAL_SORT"] = "1"
+        try:
+            sp, sv, sid = psc.mesh.step_sort(tp, tv, ta, ids, half, dt, f64, sb)
+        finally:
+            os.environ.pop("PSC_NO_LOCAL_SORT", None)
         torch.cuda.synchronize()
+        assert sb.table == (0 if step in (0, 5) else 1 - prev_table) and sb.describes(sp)
+        prev_table = sb.table
         h_id = sid.cpu().numpy()
         assert np.array_equal(np.sort(h_id), np.arange(n))
         src = h_id if ids is None else np.argsort(ids.cpu().numpy())[h_id]     # input row of every output row
@@ -279,8 +291,9 @@ def test_step_sort_is_kick_drift_wrap_plus_a_permutation(psc, orc):
         assert np.all(np.diff(key) >= 0)
         raw = sb.scratch.cpu().numpy()
         o = _a256(4 * (nbins + 1))
-        fill = raw[o: o + 4 * nbins].view(np.int32)
-        base = raw[2 * o: 2 * o + 4 * (nbins + 1)].view(np.int32)
+        of, ob = (o, 2 * o) if sb.table == 0 else (4 * o + 256, 5 * o + 256)     # csrc/binned.cu bin_layout
+        fill = raw[of: of + 4 * nbins].view(np.int32)
+        base = raw[ob: ob + 4 * (nbins + 1)].view(np.int32)
         counts = np.bincount(key, minlength=nbins)
         assert np.array_equal(fill, counts) and np.array_equal(np.diff(base), counts) and base[0] == 0
         # deposit / interpolation on the sorted arrays against the oracle
