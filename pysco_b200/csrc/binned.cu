@@ -26,6 +26,8 @@
 // and the gather of the interpolation only drops from 7.9 to 6.5 wavefronts per LDS.128 on cell-sorted records.
 // Whole step 17.5 ms against 13.7 ms.  Evidence: profiles/r02_cellsort_experiment/.
 #include <cub/device/device_scan.cuh>
+#include <cuda/barrier>
+#include <cuda/ptx>
 
 #include "common.cuh"
 
@@ -458,8 +460,16 @@ __global__ void __launch_bounds__(256) step_sort_kernel(const float *__restrict_
 // one-atomic-per-particle scatter) -- at none of the cost of a global sort on the finer key (measured: 6.5 ms, the
 // 67 MB of counters are atomic-latency bound).  A particle that jumped further (never under the Courant condition)
 // takes a slow path through global atomics.
-constexpr int SL_CHUNK = 512;                 // particles sorted per round of a CTA (two per thread)
+constexpr int SL_CHUNK = 640;                 // particles per round of a CTA: a whole bin at the mean density + 5 sigma
+constexpr int SL_R = 3;                       // = ceil(SL_CHUNK / 256) particles per thread
 constexpr int SL_KEYS = 27 * MB_PER_BIN;      // (destination bin, micro-block) keys of a round
+constexpr int SL_F3 = 3 * SL_CHUNK + 4;       // floats of one staged [n][3] array (+ 16-byte alignment slack)
+constexpr int SL_I = SL_CHUNK + 4;            // ints of the staged ids
+constexpr int SL_STAGE = 3 * SL_F3 + SL_I;    // one stage: position, velocity, acceleration, ids (25664 bytes)
+constexpr size_t SL_SMEM = 2 * SL_STAGE * sizeof(float);
+static_assert((SL_F3 * 4) % 16 == 0 && (SL_I * 4) % 16 == 0, "stage arrays must stay 16-byte aligned");
+
+using sl_barrier = cuda::barrier<cuda::thread_scope_block>;
 
 __device__ __forceinline__ int axis_delta(int nb, int src, int NB) {
   // 0 / 1 / 2 for destination bin src - 1 / src / src + 1 (periodic), -1 otherwise
@@ -470,43 +480,93 @@ __device__ __forceinline__ int axis_delta(int nb, int src, int NB) {
   return -1;
 }
 
-template <bool F64, int PASS>
+// One bulk copy (TMA, completion on the stage's mbarrier) of the 16-byte aligned superset of src[first, first + n);
+// what the aligned superset would read beyond the end of the array (< 16 bytes, last round of the last bin only) is
+// left out.  Called by one thread.
+template <class T>
+__device__ __forceinline__ void sl_fetch(T *dst, const T *src, int64_t first, int64_t n, int64_t total,
+                                         sl_barrier &bar) {
+  const int64_t a0 = first & ~(int64_t)3;
+  int64_t a1 = (first + n + 3) & ~(int64_t)3;
+  if (a1 > total) {
+    a1 = total & ~(int64_t)3;
+    for (int64_t t = a1 > a0 ? a1 : a0; t < total; t++) dst[t - a0] = src[t];
+  }
+  if (a1 > a0) cuda::memcpy_async(dst, src + a0, cuda::aligned_size_t<16>(sizeof(T) * (size_t)(a1 - a0)), bar);
+}
+
+// Pass 2 of the local sort (pass 1 = the count pass of step_sort_kernel).  Persistent CTAs, each walking over bins
+// blockIdx.x, blockIdx.x + gridDim.x, ...; the rows of the NEXT bin (position, velocity, acceleration, ids: four bulk
+// copies, 25 KB) are in flight on the other stage's mbarrier while the current bin is sorted, so the DRAM latency of a
+// bin is hidden behind the sort of the one before.  A stage that has been read into registers becomes the staging area
+// of the sorted output, which leaves the CTA as contiguous float runs (one run per destination bin).
+template <bool F64>
 __global__ void __launch_bounds__(256) step_sort_local_kernel(
     const float *__restrict__ pos, const float *__restrict__ vel, const float *__restrict__ acc,
-    const int *__restrict__ ids, const int *__restrict__ base_src, const int *__restrict__ fill_src, float half_dt,
-    double dt, int N, int NB, int *__restrict__ cnt, const int *__restrict__ base_dst, float *__restrict__ pos_out,
-    float *__restrict__ vel_out, int *__restrict__ ids_out) {
-  __shared__ int hist[PASS == 2 ? SL_KEYS : 32];
-  __shared__ float4 rec[PASS == 2 ? 2 * SL_CHUNK : 1];
+    const int *__restrict__ ids, int64_t np, const int *__restrict__ base_src, const int *__restrict__ fill_src,
+    float half_dt, double dt, int N, int NB, int nbins, int *__restrict__ cnt, const int *__restrict__ base_dst,
+    float *__restrict__ pos_out, float *__restrict__ vel_out, int *__restrict__ ids_out) {
+  extern __shared__ __align__(128) float sl_smem[];
+  __shared__ int hist[SL_KEYS];
   __shared__ int s_dst[27], s_wsum[8], s_near;
-  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int nb = fill_src[b];
-  if (nb == 0) return;
-  const int beg = base_src[b];
-  const int sbk = b % NB, sbj = (b / NB) % NB, sbi = b / (NB * NB);
+  __shared__ sl_barrier bar[2];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const float dtf = (float)dt, mh = -half_dt, Nf = (float)N;
-  if (PASS == 1) {
-    if (tid < 32) hist[tid] = 0;
-    __syncthreads();
+  if (tid == 0) {
+    init(&bar[0], 256);
+    init(&bar[1], 256);
+    cuda::ptx::fence_proxy_async(cuda::ptx::space_shared);
   }
-  for (int c0 = 0; c0 < nb; c0 += SL_CHUNK) {
-    float f[2][3], v[2][3];
-    int id[2], key[2], dbin[2], rank[2];
+  for (int t = tid; t < SL_KEYS; t += 256) hist[t] = 0;
+  // the rounds of this CTA: (bin, first particle of the round within the bin), empty bins skipped
+  int b = blockIdx.x, c0 = 0, nb = 0;
+  while (b < nbins && (nb = __ldg(&fill_src[b])) == 0) b += gridDim.x;
+  __syncthreads();
+  auto fetch = [&](int fb, int fc0, int fnb, int stage) {   // thread 0
+    float *S = sl_smem + stage * SL_STAGE;
+    const int64_t first = (int64_t)__ldg(&base_src[fb]) + fc0, n = min(fnb - fc0, SL_CHUNK);
+    sl_fetch(S, pos, 3 * first, 3 * n, 3 * np, bar[stage]);
+    sl_fetch(S + SL_F3, vel, 3 * first, 3 * n, 3 * np, bar[stage]);
+    sl_fetch(S + 2 * SL_F3, acc, 3 * first, 3 * n, 3 * np, bar[stage]);
+    if (ids) sl_fetch(reinterpret_cast<int *>(S + 3 * SL_F3), ids, first, n, np, bar[stage]);
+  };
+  if (b < nbins && tid == 0) fetch(b, 0, nb, 0);
+  for (int it = 0; b < nbins; it++) {
+    const int stage = it & 1;
+    // the round after this one
+    int b2 = b, c2 = c0 + SL_CHUNK, nb2 = nb;
+    if (c2 >= nb) {
+      c2 = 0;
+      b2 = b + gridDim.x;
+      while (b2 < nbins && (nb2 = __ldg(&fill_src[b2])) == 0) b2 += gridDim.x;
+    }
+    if (b2 < nbins && tid == 0) {
+      cuda::ptx::fence_proxy_async(cuda::ptx::space_shared);   // the other stage was last written as an output area
+      fetch(b2, c2, nb2, stage ^ 1);
+    }
+    bar[stage].arrive_and_wait();
+    float *S = sl_smem + stage * SL_STAGE;
+    const int64_t first = (int64_t)__ldg(&base_src[b]) + c0;
+    const int n = min(nb - c0, SL_CHUNK);
+    const int off3 = (int)((3 * first) & 3), off1 = (int)(first & 3);
+    const int sbk = b % NB, sbj = (b / NB) % NB, sbi = b / (NB * NB);
+    float f[SL_R][3], v[SL_R][3];
+    int id[SL_R], key[SL_R], dbin[SL_R], rank[SL_R];
 #pragma unroll
-    for (int r = 0; r < 2; r++) {
-      const int n = c0 + tid + 256 * r;
+    for (int r = 0; r < SL_R; r++) {
+      const int m = tid + 256 * r;
       key[r] = -2;   // no particle
-      if (n < nb) {
-        const size_t g = (size_t)beg + n;
+      if (m < n) {
 #pragma unroll
         for (int c = 0; c < 3; c++) {
-          const float vv = __ldg(&vel[3 * g + c]) + mh * __ldg(&acc[3 * g + c]);
-          float p = __ldg(&pos[3 * g + c]);
+          const int o = off3 + 3 * m + c;
+          const float vv = S[SL_F3 + o] + mh * S[2 * SL_F3 + o];
+          float p = S[o];
           p = F64 ? (float)((double)p + dt * (double)vv) : p + dtf * vv;
           f[r][c] = wrap01(p);
           v[r][c] = vv;
         }
-        if (PASS == 2) id[r] = ids ? __ldg(&ids[g]) : (int)g;
+        id[r] = ids ? reinterpret_cast<const int *>(S + 3 * SL_F3)[off1 + m] : (int)(first + m);
         const int i = min(max((int)(f[r][0] * Nf), 0), N - 1), j = min(max((int)(f[r][1] * Nf), 0), N - 1),
                   k = min(max((int)(f[r][2] * Nf), 0), N - 1);
         const int di = axis_delta(i >> 3, sbi, NB), dj = axis_delta(j >> 3, sbj, NB), dk = axis_delta(k >> 3, sbk, NB);
@@ -515,29 +575,13 @@ __global__ void __launch_bounds__(256) step_sort_local_kernel(
           const int ii = (i >> 1) & 3, jj = (j >> 1) & 3, kk = (k >> 1) & 3;
           const int mb = ((ii >> 1) << 5) | ((jj >> 1) << 4) | ((kk >> 1) << 3) | ((ii & 1) << 2) | ((jj & 1) << 1) | (kk & 1);
           key[r] = ((di * 3 + dj) * 3 + dk) * MB_PER_BIN + mb;
+          rank[r] = atomicAdd(&hist[key[r]], 1);
         } else {
-          key[r] = -1;   // further than a neighbouring bin: slow path
+          key[r] = -1;   // further than a neighbouring bin (never under the Courant condition): slow path
         }
       }
     }
-    if (PASS == 1) {
-#pragma unroll
-      for (int r = 0; r < 2; r++) {
-        // one shared-memory atomic per distinct destination of the warp (almost always the source bin itself)
-        const int d = key[r] >= 0 ? key[r] / MB_PER_BIN : -1 - lane;
-        const unsigned peers = __match_any_sync(0xffffffffu, d);
-        if (d >= 0 && (__ffs(peers) - 1) == lane) atomicAdd(&hist[d], __popc(peers));
-        if (key[r] == -1) atomicAdd(&cnt[dbin[r]], 1);
-      }
-      continue;
-    }
-    // ---- pass 2: counting sort of the round in shared memory
-    for (int t = tid; t < SL_KEYS; t += 256) hist[t] = 0;
-    __syncthreads();
-#pragma unroll
-    for (int r = 0; r < 2; r++)
-      if (key[r] >= 0) rank[r] = atomicAdd(&hist[key[r]], 1);
-    __syncthreads();
+    __syncthreads();   // counts complete; the stage has been read by everybody
     {
       // exclusive scan of hist[0 .. SL_KEYS) in place: 7 entries per thread
       int loc[7], sum = 0;
@@ -574,27 +618,32 @@ __global__ void __launch_bounds__(256) step_sort_local_kernel(
       }
     }
     __syncthreads();
+    float *opos = S, *ovel = S + SL_F3;
+    int *oid = reinterpret_cast<int *>(S + 2 * SL_F3);
+    unsigned char *od = reinterpret_cast<unsigned char *>(S + 3 * SL_F3);
     if (tid < 27) {
       // one contiguous block of destination rows per destination bin: s_dst[d] + (index in the sorted round) = row
-      const int first = hist[tid * MB_PER_BIN], next = tid < 26 ? hist[(tid + 1) * MB_PER_BIN] : s_near;
-      const int tot = next - first;
+      const int head = hist[tid * MB_PER_BIN], next = tid < 26 ? hist[(tid + 1) * MB_PER_BIN] : s_near;
+      const int tot = next - head;
       int row0 = 0;
       if (tot > 0) {
         const int di = tid / 9, dj = (tid / 3) % 3, dk = tid % 3;
         const int bi = (sbi + di - 1 + NB) % NB, bj = (sbj + dj - 1 + NB) % NB, bk = (sbk + dk - 1 + NB) % NB;
         const int db = (bi * NB + bj) * NB + bk;
-        row0 = base_dst[db] + atomicAdd(&cnt[db], tot) - first;
+        row0 = __ldg(&base_dst[db]) + atomicAdd(&cnt[db], tot) - head;
       }
       s_dst[tid] = row0;
     }
 #pragma unroll
-    for (int r = 0; r < 2; r++) {
+    for (int r = 0; r < SL_R; r++) {
       if (key[r] >= 0) {
         const int si = hist[key[r]] + rank[r];
-        rec[2 * si] = make_float4(f[r][0], f[r][1], f[r][2], v[r][0]);
-        rec[2 * si + 1] = make_float4(v[r][1], v[r][2], __int_as_float(id[r]), __int_as_float(key[r] / MB_PER_BIN));
+#pragma unroll
+        for (int c = 0; c < 3; c++) { opos[3 * si + c] = f[r][c]; ovel[3 * si + c] = v[r][c]; }
+        oid[si] = id[r];
+        od[si] = (unsigned char)(key[r] / MB_PER_BIN);
       } else if (key[r] == -1) {
-        const size_t slot = (size_t)base_dst[dbin[r]] + atomicAdd(&cnt[dbin[r]], 1);
+        const size_t slot = (size_t)__ldg(&base_dst[dbin[r]]) + atomicAdd(&cnt[dbin[r]], 1);
 #pragma unroll
         for (int c = 0; c < 3; c++) { pos_out[3 * slot + c] = f[r][c]; vel_out[3 * slot + c] = v[r][c]; }
         ids_out[slot] = id[r];
@@ -602,22 +651,15 @@ __global__ void __launch_bounds__(256) step_sort_local_kernel(
     }
     __syncthreads();
     const int nnear = s_near;
-    for (int t = tid; t < nnear; t += 256) {
-      const float4 A = rec[2 * t], B = rec[2 * t + 1];
-      const size_t slot = (size_t)(s_dst[__float_as_int(B.w)] + t);
-      pos_out[3 * slot] = A.x; pos_out[3 * slot + 1] = A.y; pos_out[3 * slot + 2] = A.z;
-      vel_out[3 * slot] = A.w; vel_out[3 * slot + 1] = B.x; vel_out[3 * slot + 2] = B.y;
-      ids_out[slot] = __float_as_int(B.z);
+    for (int t = tid; t < 3 * nnear; t += 256) {
+      const int64_t g = (int64_t)3 * s_dst[od[t / 3]] + t;    // consecutive t: consecutive floats of a run
+      pos_out[g] = opos[t];
+      vel_out[g] = ovel[t];
     }
-    __syncthreads();   // rec / hist / s_dst are reused by the next round
-  }
-  if (PASS == 1) {
-    __syncthreads();
-    if (tid < 27 && hist[tid] > 0) {
-      const int di = tid / 9, dj = (tid / 3) % 3, dk = tid % 3;
-      const int bi = (sbi + di - 1 + NB) % NB, bj = (sbj + dj - 1 + NB) % NB, bk = (sbk + dk - 1 + NB) % NB;
-      atomicAdd(&cnt[(bi * NB + bj) * NB + bk], hist[tid]);
-    }
+    for (int t = tid; t < nnear; t += 256) ids_out[s_dst[od[t]] + t] = oid[t];
+    for (int t = tid; t < SL_KEYS; t += 256) hist[t] = 0;
+    __syncthreads();   // output area, hist and s_dst are free again
+    b = b2; c0 = c2; nb = nb2;
   }
 }
 
@@ -1433,31 +1475,47 @@ int psc_step_sort(const float *pos, const float *vel, const float *acc, const in
     PSC_CHECK_ARG((((uintptr_t)pos | (uintptr_t)vel | (uintptr_t)acc | (uintptr_t)ids) & 15) == 0,
                   "pointers must be 16-byte aligned");
   }
-  const int g = grid_for((np + 3) / 4, 256, 8), gl = (int)L.nbins;
-#define PSC_SORT_PASS(P, CNT, BASE)                                                                                    \
-  do {                                                                                                                 \
-    if (src_table < 0) {                                                                                               \
-      if (dt_is_f64)                                                                                                   \
-        step_sort_kernel<true, P><<<g, 256, 0, st>>>(pos, vel, acc, ids, np, half_dt, dt, N, L.NB, CNT, BASE, pos_out, \
-                                                     vel_out, ids_out);                                                \
-      else                                                                                                             \
-        step_sort_kernel<false, P><<<g, 256, 0, st>>>(pos, vel, acc, ids, np, half_dt, dt, N, L.NB, CNT, BASE,         \
-                                                      pos_out, vel_out, ids_out);                                      \
-    } else {                                                                                                           \
-      if (dt_is_f64)                                                                                                   \
-        step_sort_local_kernel<true, P><<<gl, 256, 0, st>>>(pos, vel, acc, ids, base_src, fill_src, half_dt, dt, N,    \
-                                                            L.NB, CNT, BASE, pos_out, vel_out, ids_out);               \
-      else                                                                                                             \
-        step_sort_local_kernel<false, P><<<gl, 256, 0, st>>>(pos, vel, acc, ids, base_src, fill_src, half_dt, dt, N,   \
-                                                             L.NB, CNT, BASE, pos_out, vel_out, ids_out);              \
-    }                                                                                                                  \
-    count_launch();                                                                                                    \
-  } while (0)
-  if (np > 0) PSC_SORT_PASS(1, L.counts, nullptr);
+  const int g = grid_for((np + 3) / 4, 256, 8);
+  if (np > 0) {
+    // pass 1, either input order: destination-bin counts, one atomic per distinct bin of a warp
+    if (dt_is_f64)
+      step_sort_kernel<true, 1><<<g, 256, 0, st>>>(pos, vel, acc, ids, np, half_dt, dt, N, L.NB, L.counts, nullptr,
+                                                   pos_out, vel_out, ids_out);
+    else
+      step_sort_kernel<false, 1><<<g, 256, 0, st>>>(pos, vel, acc, ids, np, half_dt, dt, N, L.NB, L.counts, nullptr,
+                                                    pos_out, vel_out, ids_out);
+    count_launch();
+  }
   int rc = scan_bins(L, L.counts, L.base, st);
   if (rc != PSC_OK) return rc;
-  if (np > 0) PSC_SORT_PASS(2, L.fill, L.base);
-#undef PSC_SORT_PASS
+  if (np > 0 && src_table < 0) {
+    if (dt_is_f64)
+      step_sort_kernel<true, 2><<<g, 256, 0, st>>>(pos, vel, acc, ids, np, half_dt, dt, N, L.NB, L.fill, L.base,
+                                                   pos_out, vel_out, ids_out);
+    else
+      step_sort_kernel<false, 2><<<g, 256, 0, st>>>(pos, vel, acc, ids, np, half_dt, dt, N, L.NB, L.fill, L.base,
+                                                    pos_out, vel_out, ids_out);
+    count_launch();
+  } else if (np > 0) {
+    static bool attr_set = false;
+    if (!attr_set) {
+      PSC_CUDA(cudaFuncSetAttribute(step_sort_local_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)SL_SMEM));
+      PSC_CUDA(cudaFuncSetAttribute(step_sort_local_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)SL_SMEM));
+      attr_set = true;
+    }
+    const int gl = (int)std::min<int64_t>(L.nbins, (int64_t)num_sms() * 3);
+    if (dt_is_f64)
+      step_sort_local_kernel<true><<<gl, 256, SL_SMEM, st>>>(pos, vel, acc, ids, np, base_src, fill_src, half_dt, dt, N,
+                                                            L.NB, (int)L.nbins, L.fill, L.base, pos_out, vel_out,
+                                                            ids_out);
+    else
+      step_sort_local_kernel<false><<<gl, 256, SL_SMEM, st>>>(pos, vel, acc, ids, np, base_src, fill_src, half_dt, dt,
+                                                             N, L.NB, (int)L.nbins, L.fill, L.base, pos_out, vel_out,
+                                                             ids_out);
+    count_launch();
+  }
   bin_heavy_list_kernel<<<(int)((L.nbins + 255) / 256), 256, 0, st>>>(L.fill, (int)L.nbins, L.heavy_count, L.heavy,
                                                                      L.heavy_cap);
   count_launch();

@@ -14,12 +14,6 @@ class Binned:
 
     def __init__(self, scratch, np_, N):
         self.scratch, self.np, self.N = scratch, np_, N
-        # the scratch holds two tables: `table` describes the arrays the last step_sort returned (`owner`, a weak
-        # reference to its position tensor); the next sort reads that table and writes the other one
-        self.table, self.owner = 0, None
-
-    def describes(self, pos):
-        return self.owner is not None and self.owner() is pos
         self.ready = False
         self.mode = 0
 

@@ -261,12 +261,12 @@ def test_step_sort_is_kick_drift_wrap_plus_a_permutation(psc, orc):
     N = 32
     n = 50003
     pos, vel = cases.particles(N, n, seed=21), cases.velocities(n, seed=22, scale=5e-3)
-    acc = cases.velocities(n, seed=23, scale=2e-3)
+    acc = cases.velocities(n, seed=23, scale=1e-4)
     lib, L = psc._lib, psc._lib.load()
     tp, tv, ta = _cuda(pos), _cuda(vel), _cuda(acc)
     ids, prev_table = None, 0
     nbins = (N // 8) ** 3
-    for step, dt in enumerate((np.float32(0.021), 0.0193456789012, np.float32(4.0), np.float32(70.0), 2.5,
+    for step, dt in enumerate((np.float32(0.021), 0.0193456789012, np.float32(4.0), np.float32(30.0), 2.5,
                                np.float32(0.3))):
         half = np.float32(0.5 * dt)
         f64 = 0 if isinstance(dt, np.float32) else 1

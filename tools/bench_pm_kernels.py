@@ -87,7 +87,7 @@ for name, p in cases.items():
         torch.cuda.synchronize()
         ts.append(e0.elapsed_time(e1))
     t_dep = timeit(lambda: mesh.deposit_rhs(sp, N, 2, 1.0, 1.0, 0.0, sb))
-    t_int = timeit(lambda: mesh.interp_kick_phi(phi, None, 0.0, 0, 5, sp, sv.clone(), 2, 0.0, sb))
+    t_int = timeit(lambda: mesh.interp_kick_phi(phi, None, 0.0, 0, 5, sp, sv, 2, 0.0, sb))
     print(f"N={N} {name:18s} [bin-ordered arrays, local sort, 6th step] kick+drift+wrap+sort {min(ts[1:]):6.3f} ms | "
           f"deposit {t_dep:6.3f} ms | grad+interp+kick {t_int:6.3f} ms", flush=True)
     del sp, sv, sid, z
