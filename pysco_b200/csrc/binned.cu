@@ -462,7 +462,8 @@ __global__ void __launch_bounds__(256) step_sort_kernel(const float *__restrict_
 // takes a slow path through global atomics.
 constexpr int SL_CHUNK = 640;                 // particles per round of a CTA: a whole bin at the mean density + 5 sigma
 constexpr int SL_R = 3;                       // = ceil(SL_CHUNK / 256) particles per thread
-constexpr int SL_KEYS = 27 * MB_PER_BIN;      // (destination bin, micro-block) keys of a round
+constexpr int SL_KEYS = 96;                   // sort keys of a round: the 64 micro-blocks of the particles that stay in
+                                              // the bin, then the 26 neighbouring destination bins (+ 6 unused)
 constexpr int SL_F3 = 3 * SL_CHUNK + 4;       // floats of one staged [n][3] array (+ 16-byte alignment slack)
 constexpr int SL_I = SL_CHUNK + 4;            // ints of the staged ids
 constexpr int SL_STAGE = 3 * SL_F3 + SL_I;    // one stage: position, velocity, acceleration, ids (25664 bytes)
@@ -551,7 +552,7 @@ __global__ void __launch_bounds__(256) step_sort_local_kernel(
     const int off3 = (int)((3 * first) & 3), off1 = (int)(first & 3);
     const int sbk = b % NB, sbj = (b / NB) % NB, sbi = b / (NB * NB);
     float f[SL_R][3], v[SL_R][3];
-    int id[SL_R], key[SL_R], dbin[SL_R], rank[SL_R];
+    int id[SL_R], key[SL_R], dbin[SL_R], rank[SL_R], dst[SL_R];
 #pragma unroll
     for (int r = 0; r < SL_R; r++) {
       const int m = tid + 256 * r;
@@ -574,7 +575,8 @@ __global__ void __launch_bounds__(256) step_sort_local_kernel(
         if ((di | dj | dk) >= 0) {
           const int ii = (i >> 1) & 3, jj = (j >> 1) & 3, kk = (k >> 1) & 3;
           const int mb = ((ii >> 1) << 5) | ((jj >> 1) << 4) | ((kk >> 1) << 3) | ((ii & 1) << 2) | ((jj & 1) << 1) | (kk & 1);
-          key[r] = ((di * 3 + dj) * 3 + dk) * MB_PER_BIN + mb;
+          dst[r] = (di * 3 + dj) * 3 + dk;
+          key[r] = dst[r] == 13 ? mb : MB_PER_BIN + dst[r] - (dst[r] > 13);
           rank[r] = atomicAdd(&hist[key[r]], 1);
         } else {
           key[r] = -1;   // further than a neighbouring bin (never under the Courant condition): slow path
@@ -582,49 +584,32 @@ __global__ void __launch_bounds__(256) step_sort_local_kernel(
       }
     }
     __syncthreads();   // counts complete; the stage has been read by everybody
-    {
-      // exclusive scan of hist[0 .. SL_KEYS) in place: 7 entries per thread
-      int loc[7], sum = 0;
-#pragma unroll
-      for (int q = 0; q < 7; q++) {
-        const int idx = 7 * tid + q;
-        loc[q] = sum;
-        sum += idx < SL_KEYS ? hist[idx] : 0;
-      }
+    if (warp == 0) {
+      // exclusive scan of the SL_KEYS (= 96) counts: three per lane
+      const int h0 = hist[3 * lane], h1 = hist[3 * lane + 1], h2 = hist[3 * lane + 2];
+      const int sum = h0 + h1 + h2;
       int incl = sum;
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) {
         const int t = __shfl_up_sync(0xffffffffu, incl, o);
         if (lane >= o) incl += t;
       }
-      if (lane == 31) s_wsum[warp] = incl;
-      __syncthreads();
-      if (warp == 0) {
-        int w = lane < 8 ? s_wsum[lane] : 0, wi = w;
-#pragma unroll
-        for (int o = 1; o < 8; o <<= 1) {
-          const int t = __shfl_up_sync(0xffffffffu, wi, o);
-          if (lane >= o) wi += t;
-        }
-        if (lane < 8) s_wsum[lane] = wi - w;
-        if (lane == 7) s_near = wi;
-      }
-      __syncthreads();
-      const int off = s_wsum[warp] + incl - sum;
-#pragma unroll
-      for (int q = 0; q < 7; q++) {
-        const int idx = 7 * tid + q;
-        if (idx < SL_KEYS) hist[idx] = off + loc[q];
-      }
+      const int ex = incl - sum;
+      hist[3 * lane] = ex;
+      hist[3 * lane + 1] = ex + h0;
+      hist[3 * lane + 2] = ex + h0 + h1;
+      if (lane == 31) s_near = incl;
     }
     __syncthreads();
     float *opos = S, *ovel = S + SL_F3;
     int *oid = reinterpret_cast<int *>(S + 2 * SL_F3);
     unsigned char *od = reinterpret_cast<unsigned char *>(S + 3 * SL_F3);
     if (tid < 27) {
-      // one contiguous block of destination rows per destination bin: s_dst[d] + (index in the sorted round) = row
-      const int head = hist[tid * MB_PER_BIN], next = tid < 26 ? hist[(tid + 1) * MB_PER_BIN] : s_near;
-      const int tot = next - head;
+      // one contiguous block of destination rows per destination bin: s_dst[d] + (index in the sorted round) = row.
+      // The round trip of the global atomic runs under the staging of the sorted records below.
+      const int k0 = tid == 13 ? 0 : MB_PER_BIN + tid - (tid > 13);              // first key of destination tid
+      const int k1 = tid == 13 ? MB_PER_BIN : k0 + 1;
+      const int head = hist[k0], tot = (k1 < SL_KEYS - 6 ? hist[k1] : s_near) - head;
       int row0 = 0;
       if (tot > 0) {
         const int di = tid / 9, dj = (tid / 3) % 3, dk = tid % 3;
@@ -641,7 +626,7 @@ __global__ void __launch_bounds__(256) step_sort_local_kernel(
 #pragma unroll
         for (int c = 0; c < 3; c++) { opos[3 * si + c] = f[r][c]; ovel[3 * si + c] = v[r][c]; }
         oid[si] = id[r];
-        od[si] = (unsigned char)(key[r] / MB_PER_BIN);
+        od[si] = (unsigned char)dst[r];
       } else if (key[r] == -1) {
         const size_t slot = (size_t)__ldg(&base_dst[dbin[r]]) + atomicAdd(&cnt[dbin[r]], 1);
 #pragma unroll
@@ -1505,7 +1490,7 @@ int psc_step_sort(const float *pos, const float *vel, const float *acc, const in
                                     (int)SL_SMEM));
       attr_set = true;
     }
-    const int gl = (int)std::min<int64_t>(L.nbins, (int64_t)num_sms() * 3);
+    const int gl = (int)std::min<int64_t>(L.nbins, (int64_t)num_sms() * 4);
     if (dt_is_f64)
       step_sort_local_kernel<true><<<gl, 256, SL_SMEM, st>>>(pos, vel, acc, ids, np, base_src, fill_src, half_dt, dt, N,
                                                             L.NB, (int)L.nbins, L.fill, L.base, pos_out, vel_out,
