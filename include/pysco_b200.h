@@ -141,6 +141,12 @@ int psc_interp_kick_phi_sorted(const float *phi, const float *u, float f, int fr
                                const void *scratch, size_t scratch_bytes, int table, float *vel_sorted,
                                float *acc_sorted, int64_t np, int N, int scheme, float half_dt, float *maxout,
                                void *stream);
+/* utils.reorder_particles (utils.py:1019-1075) for bin-ordered arrays: no particle moves; ids_out[n] = rank of the
+ * particle in row n in Morton-key order, i.e. its row in the reference after the reorder.  Per-bin block radix sort in
+ * shared memory + a scan of the bin counts in Z order.  N: power of two.  *too_big (device int) = 1 when a bin holds
+ * more than 2048 particles (the caller then sorts globally: psc_morton_keys + psc_argsort_keys). */
+int psc_morton_ids_sorted(const float *pos_sorted, void *scratch, size_t scratch_bytes, int table, int64_t np, int N,
+                          int *ids_out, int *too_big, void *stream);
 int psc_scatter3_by_id(const int *ids, const float *in, float *out, int64_t np, void *stream);
 /* the bin-ordered layout on a slab: after the migration the rank's (position, velocity, 64-bit id) arrays are sorted
  * into bin order (out of place); the deposit / interpolation then read them in place, as the two entries above. */

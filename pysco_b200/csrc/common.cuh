@@ -102,6 +102,25 @@ __device__ __forceinline__ void cic_axis(float xp, int N, int &c, int &c2, float
 
 // the three 1-D weights of one axis for cells c - 1, c, c + 1 (CIC as a 3-point stencil with one zero weight,
 // mesh.py:2318-2345: the second cell is c + sign(d); NGP: the cell itself)
+// morton.py:42-77: 21-bit magic-mask spread and the key of a position
+__device__ __forceinline__ unsigned long long spread21(unsigned long long x) {
+  x &= 0x1FFFFFull;
+  x = (x | x << 32) & 0x1F00000000FFFFull;
+  x = (x | x << 16) & 0x1F0000FF0000FFull;
+  x = (x | x << 8) & 0x100F00F00F00F00Full;
+  x = (x | x << 4) & 0x10C30C30C30C30C3ull;
+  x = (x | x << 2) & 0x1249249249249249ull;
+  return x;
+}
+
+__device__ __forceinline__ unsigned long long morton_key(float x, float y, float z) {
+  // x * 2^21 is exact in float32; floor then & 0x1FFFFF (two's complement for negatives, as numpy int64 & does)
+  const long long xi = (long long)floorf(x * 2097152.0f), yi = (long long)floorf(y * 2097152.0f),
+                  zi = (long long)floorf(z * 2097152.0f);
+  return spread21((unsigned long long)xi) << 2 | spread21((unsigned long long)yi) << 1 |
+         spread21((unsigned long long)zi);
+}
+
 template <int SCHEME>
 __device__ __forceinline__ void axis_weights(float xp, int N, int &c, float &wm, float &w0, float &wp) {
   if (SCHEME == PSC_TSC) {

@@ -7,29 +7,13 @@
 namespace psc {
 
 // ---------------------------------------------------------------------------- Morton keys
-// morton.py:42-77: 21-bit magic-mask spread
-__device__ __forceinline__ unsigned long long spread21(unsigned long long x) {
-  x &= 0x1FFFFFull;
-  x = (x | x << 32) & 0x1F00000000FFFFull;
-  x = (x | x << 16) & 0x1F0000FF0000FFull;
-  x = (x | x << 8) & 0x100F00F00F00F00Full;
-  x = (x | x << 4) & 0x10C30C30C30C30C3ull;
-  x = (x | x << 2) & 0x1249249249249249ull;
-  return x;
-}
-
 __global__ void __launch_bounds__(256) morton_keys_kernel(const float *__restrict__ pos, int64_t np,
                                                           int64_t *__restrict__ keys) {
   for (int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; n < np;
        n += (int64_t)gridDim.x * blockDim.x) {
     // x * 2^21 is exact in float32; floor then & 0x1FFFFF (two's complement for negatives, as
     // numpy int64 & does)
-    long long xi = (long long)floorf(pos[3 * n + 0] * 2097152.0f);
-    long long yi = (long long)floorf(pos[3 * n + 1] * 2097152.0f);
-    long long zi = (long long)floorf(pos[3 * n + 2] * 2097152.0f);
-    unsigned long long k = spread21((unsigned long long)xi) << 2 |
-                           spread21((unsigned long long)yi) << 1 | spread21((unsigned long long)zi);
-    keys[n] = (int64_t)k;
+    keys[n] = (int64_t)morton_key(pos[3 * n + 0], pos[3 * n + 1], pos[3 * n + 2]);
   }
 }
 

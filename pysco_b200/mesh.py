@@ -57,6 +57,14 @@ def step_sorted(np_, ncells_1d):
     return b
 
 
+def sorted_bins_of(pos):
+    """the SortedBins whose current table describes the bin-ordered tensor `pos`, or None"""
+    for sb in _step_sorted.values():
+        if sb.describes(pos):
+            return sb
+    return None
+
+
 def step_sort(pos, vel, acc, ids, half_dt, dt, dt_is_f64, sb):
     """integration.py:250-258 (first half-kick, drift, wrap) fused with the re-sort of the particle arrays into bin
     order: returns NEW (position, velocity, ids) in bin order; `sb` then describes the bins of these arrays.

@@ -339,6 +339,17 @@ def test_bin_ordered_loop_matches_row_preserving_loop(psc):
                 assert np.all(np.diff(k) >= 0), "arrays of the bin-ordered loop are sorted by bin"
             elif mode == "reference":
                 assert psc.utils.particle_ids(p) is None
+            if step == 1:
+                # utils.py:1019-1075, as main.run does every n_reorder steps: physically Morton-sorted arrays for the
+                # row-preserving loops; the bin-ordered arrays only get new ids (the same tensors come back)
+                q = psc.utils.reorder_particles(p, v, a)
+                if mode == "bins":
+                    assert q[0] is p and q[1] is v and q[2] is a
+                    ids = psc.utils.particle_ids(p).cpu().numpy()
+                    assert np.array_equal(np.sort(ids), np.arange(N ** 3))
+                    keys = psc.morton.positions_to_keys(p).cpu().numpy()
+                    assert np.all(np.diff(keys[np.argsort(ids)]) >= 0), "ids = rank in Morton-key order"
+                p, v, a = q
         if mode != "numpy":
             p, v, a = psc.utils.reference_order(p, v, a)
             p, v, a = (t.cpu().numpy() for t in (p, v, a))
@@ -348,3 +359,38 @@ def test_bin_ordered_loop_matches_row_preserving_loop(psc):
         assert np.minimum(d, 1 - d).max() < 2e-7, other
         assert_close(out["bins"][1], out[other][1], 1e-5, f"velocity vs {other}")
         assert_close(out["bins"][2], out[other][2], 5e-5, f"acceleration vs {other}")
+
+
+def test_morton_relabel_of_bin_ordered_arrays(psc):
+    """utils.reorder_particles on the bin-ordered arrays of the time loop: ids = rank of the Morton key (per-bin sort in
+    shared memory: bins of <= 768 and of 769..2048 particles), against numpy's argsort of the same keys; a bin beyond
+    2048 particles falls back to the global sort (new arrays in Morton order, no ids)"""
+    import torch
+    N = 32
+    rng = np.random.default_rng(77)
+    base = cases.particles(N, 60000, seed=78)
+    mid = (rng.random((1500, 3), dtype=np.float32) * np.float32(8 / N) + np.float32(0.25)).astype(np.float32)
+    for extra in (mid, np.concatenate([mid, mid[:900] * np.float32(0.999)])):      # a bin of ~1600, then of ~2500
+        pos = np.ascontiguousarray(np.concatenate([base, extra]))
+        n = len(pos)
+        vel = cases.velocities(n, seed=79, scale=1e-3)
+        tp, tv, ta = _cuda(pos), _cuda(vel), _cuda(np.zeros_like(vel))
+        sb = psc.mesh.step_sorted(n, N)
+        sp, sv, sid = psc.mesh.step_sort(tp, tv, ta, None, np.float32(0), np.float32(0), 0, sb)
+        psc.utils.set_particle_ids((sp, sv), sid)
+        fill_max = np.bincount(_bin_key(sp.cpu().numpy(), N)).max()
+        q = psc.utils.reorder_particles(sp, sv)
+        keys = psc.morton.positions_to_keys(sp).cpu().numpy()
+        want = pos[np.argsort(psc.morton.positions_to_keys(tp).cpu().numpy(), kind="stable")]
+        if fill_max <= 2048:
+            assert 768 < fill_max and q[0] is sp
+            ids = psc.utils.particle_ids(sp).cpu().numpy()
+            assert np.array_equal(np.sort(ids), np.arange(n))
+            assert np.all(np.diff(keys[np.argsort(ids)]) >= 0)
+        else:
+            assert q[0] is not sp and psc.utils.particle_ids(q[0]) is None
+        got = psc.utils.reference_order(*q)[0].cpu().numpy()
+        assert np.array_equal(np.sort(keys), psc.morton.positions_to_keys(_cuda(got)).cpu().numpy())
+        # distinct keys: the Morton-sorted arrays are unique
+        if len(np.unique(keys)) == n:
+            assert np.array_equal(got, want)

@@ -14,7 +14,7 @@ timeout 600 python tools/bench_multigrid.py 8 > $out/${tag}_multigrid256.log 2>&
 fi
 timeout 1200 python bench.py --steps 20 --warmup 3 > $out/${tag}_bench512.json 2> $out/${tag}_bench512.err
 echo "bench rc=$?" >> $out/${tag}_bench512.err
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv --log-file $out/${tag}_launches.csv \
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off -c 600 --csv --log-file $out/${tag}_launches.csv \
   python bench.py --steps 2 --warmup 1 --no-e2e --no-cpu-baseline --no-extras > $out/${tag}_ncu_launch.log 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:'deposit_binned_kernel|interp_kick_phi_binned_kernel|step_sort' \
   --launch-skip 8 --launch-count 8 -o $out/${tag}_particle_kernels -f python tools/prof_step.py 9 step > $out/${tag}_ncu_full.log 2>&1
