@@ -668,13 +668,21 @@ def slab_short_run(N, nc, steps):
         param["nsteps"] += 1
         S.integrate(tables, param, 1e30)
 
+    from pysco_b200 import _lib
     for _ in range(3):
         step()
+    _lib.enable_timing(True)
     ms = time_steps(step, steps)
+    records = _lib.timing_records()
+    _lib.enable_timing(False)
+    peak, _ = measured_peak_gbs()
+    kern = kernel_table(records, steps, N, 1, peak)
     del S
     torch.cuda.empty_cache()
     return {"what": "pysco_b200.slab.Slab.integrate on one rank (P = 1 point of the slab scaling curve)",
-            "ncells_1d": N, "steps": steps, "ms_per_step": ms, "value": N ** 3 / (ms * 1e-3), "unit": UNIT}
+            "ncells_1d": N, "steps": steps, "ms_per_step": ms, "value": N ** 3 / (ms * 1e-3), "unit": UNIT,
+            "kernels": {k: {"ms_per_step": v["ms_per_step"], "calls_per_step": v["calls_per_step"]}
+                        for k, v in kern.items()}}
 
 
 # ------------------------------------------------------------------- B200 arm, x-slab decomposition

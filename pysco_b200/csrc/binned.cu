@@ -25,6 +25,9 @@
 // speed of the fullest of a warp's 32 cells (11 of 32 lanes busy on a jittered lattice: 3.5 ms, against 2.9 ms here),
 // and the gather of the interpolation only drops from 7.9 to 6.5 wavefronts per LDS.128 on cell-sorted records.
 // Whole step 17.5 ms against 13.7 ms.  Evidence: profiles/r02_cellsort_experiment/.
+#include <cstdlib>
+#include <cstring>
+
 #include <cub/block/block_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 #include <cuda/barrier>
@@ -72,6 +75,11 @@ struct BinLayout {
 };
 
 static size_t a256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+static bool env_is(const char *name, const char *value) {
+  const char *e = getenv(name);
+  return e && strcmp(e, value) == 0;
+}
 
 static size_t scan_tmp_bytes(int64_t n) {
   size_t b = 0;
@@ -463,8 +471,8 @@ __global__ void __launch_bounds__(256) step_sort_kernel(const float *__restrict_
 // takes a slow path through global atomics.
 constexpr int SL_CHUNK = 640;                 // particles per round of a CTA: a whole bin at the mean density + 5 sigma
 constexpr int SL_R = 3;                       // = ceil(SL_CHUNK / 256) particles per thread
-constexpr int SL_KEYS = 96;                   // sort keys of a round: the 64 micro-blocks of the particles that stay in
-                                              // the bin, then the 26 neighbouring destination bins (+ 6 unused)
+constexpr int SL_KEYS = 544;                  // sort keys of a round: the nself (64 micro-blocks, or 512 cells) keys of
+                                              // the particles that stay in the bin, then the 26 neighbouring bins
 constexpr int SL_F3 = 3 * SL_CHUNK + 4;       // floats of one staged [n][3] array (+ 16-byte alignment slack)
 constexpr int SL_I = SL_CHUNK + 4;            // ints of the staged ids
 constexpr int SL_STAGE = 3 * SL_F3 + SL_I;    // one stage: position, velocity, acceleration, ids (25664 bytes)
@@ -506,8 +514,9 @@ template <bool F64>
 __global__ void __launch_bounds__(256) step_sort_local_kernel(
     const float *__restrict__ pos, const float *__restrict__ vel, const float *__restrict__ acc,
     const int *__restrict__ ids, int64_t np, const int *__restrict__ base_src, const int *__restrict__ fill_src,
-    float half_dt, double dt, int N, int NB, int nbins, int *__restrict__ cnt, const int *__restrict__ base_dst,
-    float *__restrict__ pos_out, float *__restrict__ vel_out, int *__restrict__ ids_out) {
+    float half_dt, double dt, int N, int NB, int nbins, int nself, int *__restrict__ cnt,
+    const int *__restrict__ base_dst, float *__restrict__ pos_out, float *__restrict__ vel_out,
+    int *__restrict__ ids_out) {
   extern __shared__ __align__(128) float sl_smem[];
   __shared__ int hist[SL_KEYS];
   __shared__ int s_dst[27], s_wsum[8], s_near;
@@ -577,7 +586,8 @@ __global__ void __launch_bounds__(256) step_sort_local_kernel(
           const int ii = (i >> 1) & 3, jj = (j >> 1) & 3, kk = (k >> 1) & 3;
           const int mb = ((ii >> 1) << 5) | ((jj >> 1) << 4) | ((kk >> 1) << 3) | ((ii & 1) << 2) | ((jj & 1) << 1) | (kk & 1);
           dst[r] = (di * 3 + dj) * 3 + dk;
-          key[r] = dst[r] == 13 ? mb : MB_PER_BIN + dst[r] - (dst[r] > 13);
+          const int self = nself == MB_PER_BIN ? mb : ((i & 7) << 6) | ((j & 7) << 3) | (k & 7);
+          key[r] = dst[r] == 13 ? self : nself + dst[r] - (dst[r] > 13);
           rank[r] = atomicAdd(&hist[key[r]], 1);
         } else {
           key[r] = -1;   // further than a neighbouring bin (never under the Courant condition): slow path
@@ -586,19 +596,28 @@ __global__ void __launch_bounds__(256) step_sort_local_kernel(
     }
     __syncthreads();   // counts complete; the stage has been read by everybody
     if (warp == 0) {
-      // exclusive scan of the SL_KEYS (= 96) counts: three per lane
-      const int h0 = hist[3 * lane], h1 = hist[3 * lane + 1], h2 = hist[3 * lane + 2];
-      const int sum = h0 + h1 + h2;
+      // exclusive scan of the nself + 26 counts: a run of `per` consecutive keys per lane
+      const int nkeys = nself + 26, per = (nkeys + 31) >> 5;
+      int sum = 0;
+      for (int q = 0; q < per; q++) {
+        const int idx = lane * per + q;
+        sum += idx < nkeys ? hist[idx] : 0;
+      }
       int incl = sum;
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) {
         const int t = __shfl_up_sync(0xffffffffu, incl, o);
         if (lane >= o) incl += t;
       }
-      const int ex = incl - sum;
-      hist[3 * lane] = ex;
-      hist[3 * lane + 1] = ex + h0;
-      hist[3 * lane + 2] = ex + h0 + h1;
+      int run = incl - sum;
+      for (int q = 0; q < per; q++) {
+        const int idx = lane * per + q;
+        if (idx < nkeys) {
+          const int h = hist[idx];
+          hist[idx] = run;
+          run += h;
+        }
+      }
       if (lane == 31) s_near = incl;
     }
     __syncthreads();
@@ -608,9 +627,9 @@ __global__ void __launch_bounds__(256) step_sort_local_kernel(
     if (tid < 27) {
       // one contiguous block of destination rows per destination bin: s_dst[d] + (index in the sorted round) = row.
       // The round trip of the global atomic runs under the staging of the sorted records below.
-      const int k0 = tid == 13 ? 0 : MB_PER_BIN + tid - (tid > 13);              // first key of destination tid
-      const int k1 = tid == 13 ? MB_PER_BIN : k0 + 1;
-      const int head = hist[k0], tot = (k1 < SL_KEYS - 6 ? hist[k1] : s_near) - head;
+      const int k0 = tid == 13 ? 0 : nself + tid - (tid > 13);              // first key of destination tid
+      const int k1 = tid == 13 ? nself : k0 + 1;
+      const int head = hist[k0], tot = (k1 < nself + 26 ? hist[k1] : s_near) - head;
       int row0 = 0;
       if (tot > 0) {
         const int di = tid / 9, dj = (tid / 3) % 3, dk = tid % 3;
@@ -643,7 +662,7 @@ __global__ void __launch_bounds__(256) step_sort_local_kernel(
       vel_out[g] = ovel[t];
     }
     for (int t = tid; t < nnear; t += 256) ids_out[s_dst[od[t]] + t] = oid[t];
-    for (int t = tid; t < SL_KEYS; t += 256) hist[t] = 0;
+    for (int t = tid; t < nself + 26; t += 256) hist[t] = 0;
     __syncthreads();   // output area, hist and s_dst are free again
     b = b2; c0 = c2; nb = nb2;
   }
@@ -683,7 +702,7 @@ __global__ void __launch_bounds__(256) morton_rank_kernel(const float *__restric
                                                           const int *__restrict__ fill, const int *__restrict__ zscan,
                                                           int NB, int lo, int key_bits, int *__restrict__ ids_out,
                                                           int *__restrict__ too_big) {
-  using Sort = cub::BlockRadixSort<unsigned long long, 256, ITEMS, int>;
+  using Sort = cub::BlockRadixSort<unsigned long long, 256, ITEMS, int, 6>;
   __shared__ typename Sort::TempStorage tmp;
   const int b = blockIdx.x, n = fill[b];
   if (n <= lo) return;
@@ -1433,6 +1452,15 @@ static int interp_kick_phi_impl(const float *phi, const float *u, float f, int f
   cudaStream_t st = as_stream(stream);
   const int grid = (int)L.nbins + L.heavy_cap;   // the CTAs of unused heavy-part slots exit at once
   const int nxa = nxl + 2 * ghost;
+  static const bool wide_tile = env_is("PSC_INTERP_PITCH", "16");
+  if (wide_tile && sorted_pos && scheme == PSC_TSC && order == 5) {
+    interp_kick_phi_binned_kernel<PSC_TSC, 5, true, 16, 160><<<grid, BP_THREADS, 0, st>>>(
+        phi, u, f, fr_n, sorted_pos, L.base, L.fill, vel, acc, N, L.NB, x0, ghost, nxa, half_dt, maxout, (int)L.nbins,
+        L.heavy_count, L.heavy);
+    count_launch();
+    PSC_CHECK_LAUNCH();
+    return PSC_OK;
+  }
 #define PSC_IKP(S, O)                                                                                               \
   do {                                                                                                              \
     if (sorted_pos)                                                                                                 \
@@ -1554,14 +1582,15 @@ int psc_step_sort(const float *pos, const float *vel, const float *acc, const in
       attr_set = true;
     }
     const int gl = (int)std::min<int64_t>(L.nbins, (int64_t)num_sms() * 4);
+    static const int nself = env_is("PSC_SORT_KEY", "cell") ? 512 : MB_PER_BIN;
     if (dt_is_f64)
       step_sort_local_kernel<true><<<gl, 256, SL_SMEM, st>>>(pos, vel, acc, ids, np, base_src, fill_src, half_dt, dt, N,
-                                                            L.NB, (int)L.nbins, L.fill, L.base, pos_out, vel_out,
-                                                            ids_out);
+                                                            L.NB, (int)L.nbins, nself, L.fill, L.base, pos_out,
+                                                            vel_out, ids_out);
     else
       step_sort_local_kernel<false><<<gl, 256, SL_SMEM, st>>>(pos, vel, acc, ids, np, base_src, fill_src, half_dt, dt,
-                                                             N, L.NB, (int)L.nbins, L.fill, L.base, pos_out, vel_out,
-                                                             ids_out);
+                                                             N, L.NB, (int)L.nbins, nself, L.fill, L.base, pos_out,
+                                                             vel_out, ids_out);
     count_launch();
   }
   bin_heavy_list_kernel<<<(int)((L.nbins + 255) / 256), 256, 0, st>>>(L.fill, (int)L.nbins, L.heavy_count, L.heavy,
