@@ -471,8 +471,8 @@ __global__ void __launch_bounds__(256) step_sort_kernel(const float *__restrict_
 // takes a slow path through global atomics.
 constexpr int SL_CHUNK = 640;                 // particles per round of a CTA: a whole bin at the mean density + 5 sigma
 constexpr int SL_R = 3;                       // = ceil(SL_CHUNK / 256) particles per thread
-constexpr int SL_KEYS = 544;                  // sort keys of a round: the nself (64 micro-blocks, or 512 cells) keys of
-                                              // the particles that stay in the bin, then the 26 neighbouring bins
+// sort keys of a round: the nself (64 micro-blocks; 512 cells in an experiment) keys of the particles that stay in the
+// bin, then the 26 neighbouring bins
 constexpr int SL_F3 = 3 * SL_CHUNK + 4;       // floats of one staged [n][3] array (+ 16-byte alignment slack)
 constexpr int SL_I = SL_CHUNK + 4;            // ints of the staged ids
 constexpr int SL_STAGE = 3 * SL_F3 + SL_I;    // one stage: position, velocity, acceleration, ids (25664 bytes)
@@ -510,15 +510,15 @@ __device__ __forceinline__ void sl_fetch(T *dst, const T *src, int64_t first, in
 // copies, 25 KB) are in flight on the other stage's mbarrier while the current bin is sorted, so the DRAM latency of a
 // bin is hidden behind the sort of the one before.  A stage that has been read into registers becomes the staging area
 // of the sorted output, which leaves the CTA as contiguous float runs (one run per destination bin).
-template <bool F64>
+template <bool F64, int nself>
 __global__ void __launch_bounds__(256) step_sort_local_kernel(
     const float *__restrict__ pos, const float *__restrict__ vel, const float *__restrict__ acc,
     const int *__restrict__ ids, int64_t np, const int *__restrict__ base_src, const int *__restrict__ fill_src,
-    float half_dt, double dt, int N, int NB, int nbins, int nself, int *__restrict__ cnt,
-    const int *__restrict__ base_dst, float *__restrict__ pos_out, float *__restrict__ vel_out,
-    int *__restrict__ ids_out) {
+    float half_dt, double dt, int N, int NB, int nbins, int *__restrict__ cnt, const int *__restrict__ base_dst,
+    float *__restrict__ pos_out, float *__restrict__ vel_out, int *__restrict__ ids_out) {
   extern __shared__ __align__(128) float sl_smem[];
-  __shared__ int hist[SL_KEYS];
+  constexpr int nkeys = nself + 26, per = (nkeys + 31) / 32;
+  __shared__ int hist[32 * per];
   __shared__ int s_dst[27], s_wsum[8], s_near;
   __shared__ sl_barrier bar[2];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -528,7 +528,7 @@ __global__ void __launch_bounds__(256) step_sort_local_kernel(
     init(&bar[1], 256);
     cuda::ptx::fence_proxy_async(cuda::ptx::space_shared);
   }
-  for (int t = tid; t < SL_KEYS; t += 256) hist[t] = 0;
+  for (int t = tid; t < 32 * per; t += 256) hist[t] = 0;
   // the rounds of this CTA: (bin, first particle of the round within the bin), empty bins skipped
   int b = blockIdx.x, c0 = 0, nb = 0;
   while (b < nbins && (nb = __ldg(&fill_src[b])) == 0) b += gridDim.x;
@@ -597,11 +597,11 @@ __global__ void __launch_bounds__(256) step_sort_local_kernel(
     __syncthreads();   // counts complete; the stage has been read by everybody
     if (warp == 0) {
       // exclusive scan of the nself + 26 counts: a run of `per` consecutive keys per lane
-      const int nkeys = nself + 26, per = (nkeys + 31) >> 5;
-      int sum = 0;
+      int h[per], sum = 0;
+#pragma unroll
       for (int q = 0; q < per; q++) {
-        const int idx = lane * per + q;
-        sum += idx < nkeys ? hist[idx] : 0;
+        h[q] = hist[lane * per + q];     // the keys beyond nkeys are never counted: zero
+        sum += h[q];
       }
       int incl = sum;
 #pragma unroll
@@ -610,13 +610,10 @@ __global__ void __launch_bounds__(256) step_sort_local_kernel(
         if (lane >= o) incl += t;
       }
       int run = incl - sum;
+#pragma unroll
       for (int q = 0; q < per; q++) {
-        const int idx = lane * per + q;
-        if (idx < nkeys) {
-          const int h = hist[idx];
-          hist[idx] = run;
-          run += h;
-        }
+        hist[lane * per + q] = run;
+        run += h[q];
       }
       if (lane == 31) s_near = incl;
     }
@@ -662,7 +659,7 @@ __global__ void __launch_bounds__(256) step_sort_local_kernel(
       vel_out[g] = ovel[t];
     }
     for (int t = tid; t < nnear; t += 256) ids_out[s_dst[od[t]] + t] = oid[t];
-    for (int t = tid; t < nself + 26; t += 256) hist[t] = 0;
+    for (int t = tid; t < nkeys; t += 256) hist[t] = 0;
     __syncthreads();   // output area, hist and s_dst are free again
     b = b2; c0 = c2; nb = nb2;
   }
@@ -1034,7 +1031,11 @@ template <int ORDER> struct Reach { static constexpr int H = ORDER == 7 ? 3 : OR
 constexpr int BP_THREADS = 256;  // gradient + interpolation kernel
 
 // TP1 / TP0: row / plane pitch of the float4 force tile.  Measured at 512^3 (Morton order): 10/100 4.41 ms, 11/110 4.62,
-// 12/120 4.59, 12/144 4.75, 14/140 4.70, 11/112 5.19, 10/104 5.39 -- the dense tile is the best of those.
+// 12/120 4.59, 12/144 4.75, 14/140 4.70, 11/112 5.19, 10/104 5.39 -- the dense tile is the best of those.  Round 2,
+// bin-ordered arrays (profiles/r02_exp_inbin_order_x_pitch.txt): micro-block order 10/100 4.44 ms, 16/160 6.21 ms;
+// particles in row-major CELL order within the bin (PSC_SORT_KEY=cell), where any 8 consecutive cells of a 16/160 tile
+// fall into 8 different 16-byte bank groups: 10/100 4.33 ms, 16/160 4.26 ms -- removing the LDS.128 conflicts buys 4 %,
+// less than the finer sort key costs in the sort (+0.17 ms) and the deposit (+0.08 ms).
 template <int SCHEME, int ORDER, bool SORTED, int TP1 = BT, int TP0 = BT * BT>
 __global__ void __launch_bounds__(BP_THREADS) interp_kick_phi_binned_kernel(
     const float *__restrict__ phi, const float *__restrict__ u, float f, int fr_n,
@@ -1452,15 +1453,6 @@ static int interp_kick_phi_impl(const float *phi, const float *u, float f, int f
   cudaStream_t st = as_stream(stream);
   const int grid = (int)L.nbins + L.heavy_cap;   // the CTAs of unused heavy-part slots exit at once
   const int nxa = nxl + 2 * ghost;
-  static const bool wide_tile = env_is("PSC_INTERP_PITCH", "16");
-  if (wide_tile && sorted_pos && scheme == PSC_TSC && order == 5) {
-    interp_kick_phi_binned_kernel<PSC_TSC, 5, true, 16, 160><<<grid, BP_THREADS, 0, st>>>(
-        phi, u, f, fr_n, sorted_pos, L.base, L.fill, vel, acc, N, L.NB, x0, ghost, nxa, half_dt, maxout, (int)L.nbins,
-        L.heavy_count, L.heavy);
-    count_launch();
-    PSC_CHECK_LAUNCH();
-    return PSC_OK;
-  }
 #define PSC_IKP(S, O)                                                                                               \
   do {                                                                                                              \
     if (sorted_pos)                                                                                                 \
@@ -1573,24 +1565,28 @@ int psc_step_sort(const float *pos, const float *vel, const float *acc, const in
                                                     pos_out, vel_out, ids_out);
     count_launch();
   } else if (np > 0) {
-    static bool attr_set = false;
-    if (!attr_set) {
-      PSC_CUDA(cudaFuncSetAttribute(step_sort_local_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    (int)SL_SMEM));
-      PSC_CUDA(cudaFuncSetAttribute(step_sort_local_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    (int)SL_SMEM));
-      attr_set = true;
-    }
+    static const bool cell_key = env_is("PSC_SORT_KEY", "cell");   // experiment: row-major cells instead of micro-blocks
     const int gl = (int)std::min<int64_t>(L.nbins, (int64_t)num_sms() * 4);
-    static const int nself = env_is("PSC_SORT_KEY", "cell") ? 512 : MB_PER_BIN;
-    if (dt_is_f64)
-      step_sort_local_kernel<true><<<gl, 256, SL_SMEM, st>>>(pos, vel, acc, ids, np, base_src, fill_src, half_dt, dt, N,
-                                                            L.NB, (int)L.nbins, nself, L.fill, L.base, pos_out,
-                                                            vel_out, ids_out);
-    else
-      step_sort_local_kernel<false><<<gl, 256, SL_SMEM, st>>>(pos, vel, acc, ids, np, base_src, fill_src, half_dt, dt,
-                                                             N, L.NB, (int)L.nbins, nself, L.fill, L.base, pos_out,
-                                                             vel_out, ids_out);
+#define PSC_SORT_LOCAL(F64, NSELF)                                                                                    \
+  do {                                                                                                                \
+    static bool attr_set = false;                                                                                     \
+    if (!attr_set) {                                                                                                  \
+      PSC_CUDA(cudaFuncSetAttribute(step_sort_local_kernel<F64, NSELF>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
+                                    (int)SL_SMEM));                                                                   \
+      attr_set = true;                                                                                                \
+    }                                                                                                                 \
+    step_sort_local_kernel<F64, NSELF><<<gl, 256, SL_SMEM, st>>>(pos, vel, acc, ids, np, base_src, fill_src, half_dt, \
+                                                                 dt, N, L.NB, (int)L.nbins, L.fill, L.base, pos_out,  \
+                                                                 vel_out, ids_out);                                   \
+  } while (0)
+    if (cell_key) {
+      if (dt_is_f64) PSC_SORT_LOCAL(true, 512);
+      else PSC_SORT_LOCAL(false, 512);
+    } else {
+      if (dt_is_f64) PSC_SORT_LOCAL(true, MB_PER_BIN);
+      else PSC_SORT_LOCAL(false, MB_PER_BIN);
+    }
+#undef PSC_SORT_LOCAL
     count_launch();
   }
   bin_heavy_list_kernel<<<(int)((L.nbins + 255) / 256), 256, 0, st>>>(L.fill, (int)L.nbins, L.heavy_count, L.heavy,
