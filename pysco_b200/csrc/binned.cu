@@ -659,7 +659,7 @@ __global__ void __launch_bounds__(256) step_sort_local_kernel(
       vel_out[g] = ovel[t];
     }
     for (int t = tid; t < nnear; t += 256) ids_out[s_dst[od[t]] + t] = oid[t];
-    for (int t = tid; t < nkeys; t += 256) hist[t] = 0;
+    for (int t = tid; t < 32 * per; t += 256) hist[t] = 0;   // all of them: the scan wrote the unused tail too
     __syncthreads();   // output area, hist and s_dst are free again
     b = b2; c0 = c2; nb = nb2;
   }

@@ -251,15 +251,15 @@ def test_small_mesh_path_without_binning(psc, orc):
     assert_close(tv.cpu().numpy(), v_ref, TOL, "kick N=12")
 
 
-def test_step_sort_is_kick_drift_wrap_plus_a_permutation(psc, orc):
+@pytest.mark.parametrize("N,n", [(32, 50003), (128, 600011)])
+def test_step_sort_is_kick_drift_wrap_plus_a_permutation(psc, orc, N, n):
     """psc_step_sort (first half of the leapfrog fused with the re-sort into bin order): the output arrays hold exactly
     the particles psc_kick_drift_wrap produces, in bin order, with ids = their input rows; the following calls start
     from bin-ordered arrays (one CTA per source bin, shared-memory sort, tables 0 -> 1 -> 0 ...) and carry the ids
     through: float64 drift (snapshot-clamped dt), drifts that move many particles into neighbouring bins and a drift of
     a third of the box (the slow path of the local sort); PSC_NO_LOCAL_SORT=1 keeps the global-atomic sort"""
+    # N = 128: 4096 bins for 592 persistent CTAs, every CTA walks over several bins (the TMA pipeline of the local sort)
     import torch
-    N = 32
-    n = 50003
     pos, vel = cases.particles(N, n, seed=21), cases.velocities(n, seed=22, scale=5e-3)
     acc = cases.velocities(n, seed=23, scale=1e-4)
     lib, L = psc._lib, psc._lib.load()
@@ -312,18 +312,18 @@ def test_step_sort_is_kick_drift_wrap_plus_a_permutation(psc, orc):
         tp, tv, ids = sp, v0, sid
 
 
-def test_bin_ordered_loop_matches_row_preserving_loop(psc):
+@pytest.mark.parametrize("N", [32, 128])
+def test_bin_ordered_loop_matches_row_preserving_loop(psc, N):
     """integration.integrate on device tensors keeps the arrays in bin order (default) or leaves every particle in
     its row (param['particle_order'] = 'reference', the shadow binning): same physics -- after utils.reference_order
     the two agree to float32 summation order; NumPy callers always get their rows back"""
     import torch
-    N = 32
     tables = cases.toy_tables()
     pos = cases.lattice_particles(N, 0.3, seed=60)
     vel = cases.velocities(N ** 3, seed=61, scale=2e-3)
     out = {}
     for mode in ("bins", "reference", "numpy"):
-        param = cases.base_param(5, N ** 3, linear_newton_solver="fft")
+        param = cases.base_param(int(np.log2(N)), N ** 3, linear_newton_solver="fft")
         param["aexp"] = 0.2
         param["t"] = float(tables[1](np.log(param["aexp"])))
         param["particle_order"] = "reference" if mode == "reference" else "bins"

@@ -47,6 +47,7 @@ if rank == 0:
         param["nsteps"] += 1
         state = list(integration.integrate(*state, tables, param, 1e30))
     order = torch.argsort(ids)
+    state[:3] = utils.reference_order(*state[:3])      # the device-resident loop keeps its arrays in bin order
     ref = [state[0][order].cpu(), state[1][order].cpu(), state[2][order].cpu(), float(param["t"])]
     del state, pos, vel, acc, pot, add
     torch.cuda.empty_cache()
