@@ -149,17 +149,20 @@ int psc_morton_ids_sorted(const float *pos_sorted, void *scratch, size_t scratch
                           int *ids_out, int *too_big, void *stream);
 int psc_scatter3_by_id(const int *ids, const float *in, float *out, int64_t np, void *stream);
 /* the bin-ordered layout on a slab: after the migration the rank's (position, velocity, 64-bit id) arrays are sorted
- * into bin order (out of place); the deposit / interpolation then read them in place, as the two entries above. */
+ * into bin order (out of place); the deposit / interpolation then read them in place, as the two entries above.
+ * src_table / src_rows: -1 / 0 for arrays in no particular order (result: table 0); else the table that describes rows
+ * [0, src_rows) of the input as the previous sort left them -- kicked, drifted and migrated in place since (result:
+ * table 1 - src_table; per-source-bin sort in shared memory).  `table` of the consumers = the table the sort wrote. */
 size_t psc_sorted_workspace_bytes_slab(int64_t np, int N, int nxl);
 int psc_sort_by_bin_slab(const float *pos, const float *vel, const int64_t *ids, int64_t np, int N, int x0, int nxl,
-                         void *scratch, size_t scratch_bytes, float *pos_out, float *vel_out, int64_t *ids_out,
-                         void *stream);
-int psc_deposit_sorted_slab(const float *pos_sorted, const void *scratch, size_t scratch_bytes, int64_t np, int N, int x0,
-                            int nxl, int scheme, float *rho_ghost, void *stream);
+                         int src_table, int64_t src_rows, void *scratch, size_t scratch_bytes, float *pos_out,
+                         float *vel_out, int64_t *ids_out, void *stream);
+int psc_deposit_sorted_slab(const float *pos_sorted, const void *scratch, size_t scratch_bytes, int table, int64_t np,
+                            int N, int x0, int nxl, int scheme, float *rho_ghost, void *stream);
 int psc_interp_kick_phi_sorted_slab(const float *phi_ghost, const float *u_ghost, float f, int fr_n, int order, int x0,
                                     int nxl, int ghost, const float *pos_sorted, const void *scratch,
-                                    size_t scratch_bytes, float *vel_sorted, float *acc_sorted, int64_t np, int N,
-                                    int scheme, float half_dt, float *maxout, void *stream);
+                                    size_t scratch_bytes, int table, float *vel_sorted, float *acc_sorted, int64_t np,
+                                    int N, int scheme, float half_dt, float *maxout, void *stream);
 
 /* mesh.derivative / derivative_fR (mesh.py:639-2174) fused into the binned interpolation + kick: every bin's CTA
  * derives its force tile from the potential phi (and, for f(R), the scalaron u: phi + f * u^(fr_n+1)) in shared

@@ -45,10 +45,10 @@ SIGNATURES = {
     "psc_interp_kick_phi_sorted": [_vp, _vp, _f, _i, _i, _vp, _vp, _sz, _i, _vp, _vp, _i64, _i, _i, _f, _vp, _vp],
     "psc_scatter3_by_id": [_vp, _vp, _vp, _i64, _vp],
     "psc_sorted_workspace_bytes_slab": [_i64, _i, _i],
-    "psc_sort_by_bin_slab": [_vp, _vp, _vp, _i64, _i, _i, _i, _vp, _sz, _vp, _vp, _vp, _vp],
-    "psc_deposit_sorted_slab": [_vp, _vp, _sz, _i64, _i, _i, _i, _i, _vp, _vp],
-    "psc_interp_kick_phi_sorted_slab": [_vp, _vp, _f, _i, _i, _i, _i, _i, _vp, _vp, _sz, _vp, _vp, _i64, _i, _i, _f, _vp,
-                                        _vp],
+    "psc_sort_by_bin_slab": [_vp, _vp, _vp, _i64, _i, _i, _i, _i, _i64, _vp, _sz, _vp, _vp, _vp, _vp],
+    "psc_deposit_sorted_slab": [_vp, _vp, _sz, _i, _i64, _i, _i, _i, _i, _vp, _vp],
+    "psc_interp_kick_phi_sorted_slab": [_vp, _vp, _f, _i, _i, _i, _i, _i, _vp, _vp, _sz, _i, _vp, _vp, _i64, _i, _i, _f,
+                                        _vp, _vp],
     "psc_bin_workspace_bytes_slab": [_i64, _i, _i],
     "psc_bin_particles_slab": [_vp, _i64, _i, _i, _i, _vp, _sz, _vp],
     "psc_deposit_binned_slab": [_vp, _sz, _i64, _i, _i, _i, _i, _vp, _vp],

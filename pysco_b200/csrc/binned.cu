@@ -26,6 +26,7 @@
 // and the gather of the interpolation only drops from 7.9 to 6.5 wavefronts per LDS.128 on cell-sorted records.
 // Whole step 17.5 ms against 13.7 ms.  Evidence: profiles/r02_cellsort_experiment/.
 #include <cstdlib>
+#include <type_traits>
 #include <cstring>
 
 #include <cub/block/block_radix_sort.cuh>
@@ -496,10 +497,11 @@ __device__ __forceinline__ int axis_delta(int nb, int src, int NB) {
 template <class T>
 __device__ __forceinline__ void sl_fetch(T *dst, const T *src, int64_t first, int64_t n, int64_t total,
                                          sl_barrier &bar) {
-  const int64_t a0 = first & ~(int64_t)3;
-  int64_t a1 = (first + n + 3) & ~(int64_t)3;
+  constexpr int64_t q = 16 / sizeof(T);   // elements per 16 bytes
+  const int64_t a0 = first & ~(q - 1);
+  int64_t a1 = (first + n + q - 1) & ~(q - 1);
   if (a1 > total) {
-    a1 = total & ~(int64_t)3;
+    a1 = total & ~(q - 1);
     for (int64_t t = a1 > a0 ? a1 : a0; t < total; t++) dst[t - a0] = src[t];
   }
   if (a1 > a0) cuda::memcpy_async(dst, src + a0, cuda::aligned_size_t<16>(sizeof(T) * (size_t)(a1 - a0)), bar);
@@ -510,12 +512,20 @@ __device__ __forceinline__ void sl_fetch(T *dst, const T *src, int64_t first, in
 // copies, 25 KB) are in flight on the other stage's mbarrier while the current bin is sorted, so the DRAM latency of a
 // bin is hidden behind the sort of the one before.  A stage that has been read into registers becomes the staging area
 // of the sorted output, which leaves the CTA as contiguous float runs (one run per destination bin).
-template <bool F64, int nself>
+//
+// SLAB = true is the same sort for the particles of an x-slab (psc_sort_by_bin_slab): the kick + drift + wrap and the
+// migration have already been applied in place (so nothing is recomputed and the acceleration is not read), ids are
+// 64-bit, bins are those of the slab [x0, x0 + 8 NBX) (periodic in x only when the slab is the whole box), and only the
+// first `rows` rows are described by the source table (the migration may have shortened or extended the arrays; rows
+// that hold arrivals or moved tail particles are wherever the migration put them: they take the slow path).
+template <bool F64, int nself, bool SLAB>
 __global__ void __launch_bounds__(256) step_sort_local_kernel(
     const float *__restrict__ pos, const float *__restrict__ vel, const float *__restrict__ acc,
-    const int *__restrict__ ids, int64_t np, const int *__restrict__ base_src, const int *__restrict__ fill_src,
-    float half_dt, double dt, int N, int NB, int nbins, int *__restrict__ cnt, const int *__restrict__ base_dst,
-    float *__restrict__ pos_out, float *__restrict__ vel_out, int *__restrict__ ids_out) {
+    const typename std::conditional<SLAB, long long, int>::type *__restrict__ ids, int64_t np, int64_t rows,
+    const int *__restrict__ base_src, const int *__restrict__ fill_src, float half_dt, double dt, int N, int NB, int x0,
+    int NBX, int nbins, int *__restrict__ cnt, const int *__restrict__ base_dst, float *__restrict__ pos_out,
+    float *__restrict__ vel_out, typename std::conditional<SLAB, long long, int>::type *__restrict__ ids_out) {
+  using IdT = typename std::conditional<SLAB, long long, int>::type;
   extern __shared__ __align__(128) float sl_smem[];
   constexpr int nkeys = nself + 26, per = (nkeys + 31) / 32;
   __shared__ int hist[32 * per];
@@ -530,16 +540,26 @@ __global__ void __launch_bounds__(256) step_sort_local_kernel(
   }
   for (int t = tid; t < 32 * per; t += 256) hist[t] = 0;
   // the rounds of this CTA: (bin, first particle of the round within the bin), empty bins skipped
+  // particles of source bin sb that are still there: its rows below `rows`
+  auto live = [&](int sb) {
+    const int64_t left = rows - (int64_t)__ldg(&base_src[sb]);
+    return (int)max((int64_t)0, min((int64_t)__ldg(&fill_src[sb]), left));
+  };
+  const int NBXp = NBX == NB ? NB : 0x40000000;   // period of the bin index along x (none inside a slab)
   int b = blockIdx.x, c0 = 0, nb = 0;
-  while (b < nbins && (nb = __ldg(&fill_src[b])) == 0) b += gridDim.x;
+  while (b < nbins && (nb = live(b)) == 0) b += gridDim.x;
   __syncthreads();
   auto fetch = [&](int fb, int fc0, int fnb, int stage) {   // thread 0
     float *S = sl_smem + stage * SL_STAGE;
     const int64_t first = (int64_t)__ldg(&base_src[fb]) + fc0, n = min(fnb - fc0, SL_CHUNK);
     sl_fetch(S, pos, 3 * first, 3 * n, 3 * np, bar[stage]);
     sl_fetch(S + SL_F3, vel, 3 * first, 3 * n, 3 * np, bar[stage]);
-    sl_fetch(S + 2 * SL_F3, acc, 3 * first, 3 * n, 3 * np, bar[stage]);
-    if (ids) sl_fetch(reinterpret_cast<int *>(S + 3 * SL_F3), ids, first, n, np, bar[stage]);
+    if (SLAB) {   // 64-bit ids in the (unused) acceleration area
+      if (ids) sl_fetch(reinterpret_cast<IdT *>(S + 2 * SL_F3), ids, first, n, np, bar[stage]);
+    } else {
+      sl_fetch(S + 2 * SL_F3, acc, 3 * first, 3 * n, 3 * np, bar[stage]);
+      if (ids) sl_fetch(reinterpret_cast<IdT *>(S + 3 * SL_F3), ids, first, n, np, bar[stage]);
+    }
   };
   if (b < nbins && tid == 0) fetch(b, 0, nb, 0);
   for (int it = 0; b < nbins; it++) {
@@ -549,7 +569,7 @@ __global__ void __launch_bounds__(256) step_sort_local_kernel(
     if (c2 >= nb) {
       c2 = 0;
       b2 = b + gridDim.x;
-      while (b2 < nbins && (nb2 = __ldg(&fill_src[b2])) == 0) b2 += gridDim.x;
+      while (b2 < nbins && (nb2 = live(b2)) == 0) b2 += gridDim.x;
     }
     if (b2 < nbins && tid == 0) {
       cuda::ptx::fence_proxy_async(cuda::ptx::space_shared);   // the other stage was last written as an output area
@@ -559,10 +579,11 @@ __global__ void __launch_bounds__(256) step_sort_local_kernel(
     float *S = sl_smem + stage * SL_STAGE;
     const int64_t first = (int64_t)__ldg(&base_src[b]) + c0;
     const int n = min(nb - c0, SL_CHUNK);
-    const int off3 = (int)((3 * first) & 3), off1 = (int)(first & 3);
+    const int off3 = (int)((3 * first) & 3), off1 = (int)(first & (16 / sizeof(IdT) - 1));
     const int sbk = b % NB, sbj = (b / NB) % NB, sbi = b / (NB * NB);
     float f[SL_R][3], v[SL_R][3];
-    int id[SL_R], key[SL_R], dbin[SL_R], rank[SL_R], dst[SL_R];
+    IdT id[SL_R];
+    int key[SL_R], dbin[SL_R], rank[SL_R], dst[SL_R];
 #pragma unroll
     for (int r = 0; r < SL_R; r++) {
       const int m = tid + 256 * r;
@@ -571,16 +592,22 @@ __global__ void __launch_bounds__(256) step_sort_local_kernel(
 #pragma unroll
         for (int c = 0; c < 3; c++) {
           const int o = off3 + 3 * m + c;
-          const float vv = S[SL_F3 + o] + mh * S[2 * SL_F3 + o];
-          float p = S[o];
-          p = F64 ? (float)((double)p + dt * (double)vv) : p + dtf * vv;
-          f[r][c] = wrap01(p);
-          v[r][c] = vv;
+          if (SLAB) {
+            f[r][c] = S[o];
+            v[r][c] = S[SL_F3 + o];
+          } else {
+            const float vv = S[SL_F3 + o] + mh * S[2 * SL_F3 + o];
+            float p = S[o];
+            p = F64 ? (float)((double)p + dt * (double)vv) : p + dtf * vv;
+            f[r][c] = wrap01(p);
+            v[r][c] = vv;
+          }
         }
-        id[r] = ids ? reinterpret_cast<const int *>(S + 3 * SL_F3)[off1 + m] : (int)(first + m);
-        const int i = min(max((int)(f[r][0] * Nf), 0), N - 1), j = min(max((int)(f[r][1] * Nf), 0), N - 1),
+        id[r] = ids ? reinterpret_cast<const IdT *>(S + (SLAB ? 2 : 3) * SL_F3)[off1 + m] : (IdT)(first + m);
+        // the cell, clamped into the slab like bin_of does
+        const int i = min(max((int)(f[r][0] * Nf) - x0, 0), 8 * NBX - 1), j = min(max((int)(f[r][1] * Nf), 0), N - 1),
                   k = min(max((int)(f[r][2] * Nf), 0), N - 1);
-        const int di = axis_delta(i >> 3, sbi, NB), dj = axis_delta(j >> 3, sbj, NB), dk = axis_delta(k >> 3, sbk, NB);
+        const int di = axis_delta(i >> 3, sbi, NBXp), dj = axis_delta(j >> 3, sbj, NB), dk = axis_delta(k >> 3, sbk, NB);
         dbin[r] = ((i >> 3) * NB + (j >> 3)) * NB + (k >> 3);
         if ((di | dj | dk) >= 0) {
           const int ii = (i >> 1) & 3, jj = (j >> 1) & 3, kk = (k >> 1) & 3;
@@ -619,7 +646,7 @@ __global__ void __launch_bounds__(256) step_sort_local_kernel(
     }
     __syncthreads();
     float *opos = S, *ovel = S + SL_F3;
-    int *oid = reinterpret_cast<int *>(S + 2 * SL_F3);
+    IdT *oid = reinterpret_cast<IdT *>(S + 2 * SL_F3);
     unsigned char *od = reinterpret_cast<unsigned char *>(S + 3 * SL_F3);
     if (tid < 27) {
       // one contiguous block of destination rows per destination bin: s_dst[d] + (index in the sorted round) = row.
@@ -630,7 +657,7 @@ __global__ void __launch_bounds__(256) step_sort_local_kernel(
       int row0 = 0;
       if (tot > 0) {
         const int di = tid / 9, dj = (tid / 3) % 3, dk = tid % 3;
-        const int bi = (sbi + di - 1 + NB) % NB, bj = (sbj + dj - 1 + NB) % NB, bk = (sbk + dk - 1 + NB) % NB;
+        const int bi = (sbi + di - 1 + NBX) % NBX, bj = (sbj + dj - 1 + NB) % NB, bk = (sbk + dk - 1 + NB) % NB;
         const int db = (bi * NB + bj) * NB + bk;
         row0 = __ldg(&base_dst[db]) + atomicAdd(&cnt[db], tot) - head;
       }
@@ -699,7 +726,7 @@ __global__ void __launch_bounds__(256) morton_rank_kernel(const float *__restric
                                                           const int *__restrict__ fill, const int *__restrict__ zscan,
                                                           int NB, int lo, int key_bits, int *__restrict__ ids_out,
                                                           int *__restrict__ too_big) {
-  using Sort = cub::BlockRadixSort<unsigned long long, 256, ITEMS, int, 6>;
+  using Sort = cub::BlockRadixSort<unsigned long long, 256, ITEMS, int>;   // 4-bit digits: 8.3 ms at 512^3, 6-bit: 10.2
   __shared__ typename Sort::TempStorage tmp;
   const int b = blockIdx.x, n = fill[b];
   if (n <= lo) return;
@@ -1571,13 +1598,13 @@ int psc_step_sort(const float *pos, const float *vel, const float *acc, const in
   do {                                                                                                                \
     static bool attr_set = false;                                                                                     \
     if (!attr_set) {                                                                                                  \
-      PSC_CUDA(cudaFuncSetAttribute(step_sort_local_kernel<F64, NSELF>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
-                                    (int)SL_SMEM));                                                                   \
+      PSC_CUDA(cudaFuncSetAttribute(step_sort_local_kernel<F64, NSELF, false>,                                        \
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SL_SMEM));                      \
       attr_set = true;                                                                                                \
     }                                                                                                                 \
-    step_sort_local_kernel<F64, NSELF><<<gl, 256, SL_SMEM, st>>>(pos, vel, acc, ids, np, base_src, fill_src, half_dt, \
-                                                                 dt, N, L.NB, (int)L.nbins, L.fill, L.base, pos_out,  \
-                                                                 vel_out, ids_out);                                   \
+    step_sort_local_kernel<F64, NSELF, false><<<gl, 256, SL_SMEM, st>>>(                                              \
+        pos, vel, acc, ids, np, np, base_src, fill_src, half_dt, dt, N, L.NB, 0, L.NB, (int)L.nbins, L.fill, L.base,  \
+        pos_out, vel_out, ids_out);                                                                                   \
   } while (0)
     if (cell_key) {
       if (dt_is_f64) PSC_SORT_LOCAL(true, 512);
@@ -1675,21 +1702,31 @@ size_t psc_sorted_workspace_bytes_slab(int64_t np, int N, int nxl) {
   return sorted_bytes(np, (int64_t)(nxl / BB) * (N / BB) * (N / BB));
 }
 
+/* src_table = -1: the input arrays are in no particular order (after set_particles / the Morton reorder): one global
+ * atomic per particle, result in table 0.  src_table = 0 / 1: rows [0, src_rows) are the bin-ordered arrays that table
+ * describes, as the in-place kick + drift and the migration left them (arrivals in the holes of the leavers, tail rows
+ * moved down or new rows [src_rows, np) appended): one CTA per source bin sorts in shared memory
+ * (step_sort_local_kernel<.., SLAB>), the appended rows go through the per-particle path; result in table
+ * 1 - src_table. */
 int psc_sort_by_bin_slab(const float *pos, const float *vel, const int64_t *ids, int64_t np, int N, int x0, int nxl,
-                         void *scratch, size_t scratch_bytes, float *pos_out, float *vel_out, int64_t *ids_out,
-                         void *stream) {
+                         int src_table, int64_t src_rows, void *scratch, size_t scratch_bytes, float *pos_out,
+                         float *vel_out, int64_t *ids_out, void *stream) {
   PSC_CHECK_ARG(np >= 0 && np < ((int64_t)1 << 31), "np out of range");
   PSC_CHECK_ARG(slab_ok(N, x0, nxl), "N and the slab thickness must be multiples of 8");
+  PSC_CHECK_ARG(src_table >= -1 && src_table <= 1 && src_rows >= 0, "src_table must be -1, 0 or 1");
   PSC_CHECK_ARG(scratch && ((uintptr_t)scratch & 255) == 0, "scratch must be 256-byte aligned");
   BinLayout L;
   if (!bin_layout(scratch, scratch_bytes, np, N, x0, nxl, L, false)) {
     set_error("psc_sort_by_bin_slab: scratch too small");
     return PSC_ERR_WORKSPACE;
   }
+  const int *base_src = src_table == 1 ? L.base2 : L.base, *fill_src = src_table == 1 ? L.fill2 : L.fill;
+  use_table(L, src_table < 0 ? 0 : 1 - src_table);
   cudaStream_t st = as_stream(stream);
   PSC_CUDA(cudaMemsetAsync(L.counts, 0, sizeof(int) * (L.nbins + 1), st));
   PSC_CUDA(cudaMemsetAsync(L.fill, 0, sizeof(int) * (L.nbins + 1), st));
   PSC_CUDA(cudaMemsetAsync(L.heavy_count, 0, sizeof(int), st));
+  const bool local = src_table >= 0 && np > 0 && ((((uintptr_t)pos | (uintptr_t)vel | (uintptr_t)ids) & 15) == 0);
   if (np > 0) {
     PSC_CHECK_ARG(pos && vel && ids && pos_out && vel_out && ids_out, "null pointer");
     PSC_CHECK_ARG(pos != pos_out && vel != vel_out && ids != ids_out, "the sort is out of place");
@@ -1698,9 +1735,25 @@ int psc_sort_by_bin_slab(const float *pos, const float *vel, const int64_t *ids,
   }
   int rc = scan_bins(L, L.counts, L.base, st);
   if (rc != PSC_OK) return rc;
-  if (np > 0) {
-    sort_scatter_kernel<<<grid_for(np, 256, 8), 256, 0, st>>>(pos, vel, ids, np, N, L.NB, x0, L.NBX, L.fill, L.base,
-                                                              pos_out, vel_out, ids_out);
+  // rows the per-particle scatter takes: all of them, or the ones appended behind the rows the source table describes
+  const int64_t tail0 = local ? std::min(src_rows, np) : 0;
+  if (local) {
+    static bool attr_set = false;
+    if (!attr_set) {
+      PSC_CUDA(cudaFuncSetAttribute(step_sort_local_kernel<false, MB_PER_BIN, true>,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SL_SMEM));
+      attr_set = true;
+    }
+    const int gl = (int)std::min<int64_t>(L.nbins, (int64_t)num_sms() * 4);
+    step_sort_local_kernel<false, MB_PER_BIN, true><<<gl, 256, SL_SMEM, st>>>(
+        pos, vel, nullptr, reinterpret_cast<const long long *>(ids), np, tail0, base_src, fill_src, 0.0f, 0.0, N, L.NB, x0,
+        L.NBX, (int)L.nbins, L.fill, L.base, pos_out, vel_out, reinterpret_cast<long long *>(ids_out));
+    count_launch();
+  }
+  if (np > tail0) {
+    sort_scatter_kernel<<<grid_for(np - tail0, 256, 8), 256, 0, st>>>(pos + 3 * tail0, vel + 3 * tail0, ids + tail0,
+                                                                     np - tail0, N, L.NB, x0, L.NBX, L.fill, L.base,
+                                                                     pos_out, vel_out, ids_out);
     count_launch();
   }
   bin_heavy_list_kernel<<<(int)((L.nbins + 255) / 256), 256, 0, st>>>(L.fill, (int)L.nbins, L.heavy_count, L.heavy,
@@ -1710,20 +1763,21 @@ int psc_sort_by_bin_slab(const float *pos, const float *vel, const int64_t *ids,
   return PSC_OK;
 }
 
-int psc_deposit_sorted_slab(const float *pos_sorted, const void *scratch, size_t scratch_bytes, int64_t np, int N, int x0,
-                            int nxl, int scheme, float *rho_ghost, void *stream) {
+int psc_deposit_sorted_slab(const float *pos_sorted, const void *scratch, size_t scratch_bytes, int table, int64_t np,
+                            int N, int x0, int nxl, int scheme, float *rho_ghost, void *stream) {
   PSC_CHECK_ARG(scheme == PSC_NGP || scheme == PSC_CIC || scheme == PSC_TSC, "unknown mass scheme");
   PSC_CHECK_ARG(slab_ok(N, x0, nxl), "N and the slab thickness must be multiples of 8");
   PSC_CHECK_ARG(scratch && rho_ghost && (pos_sorted || np == 0), "null pointer");
+  PSC_CHECK_ARG(table == 0 || table == 1, "table must be 0 or 1");
   static const float dummy = 0.0f;
   return deposit_binned_impl(scratch, scratch_bytes, np, N, x0, nxl, 1, scheme, 1.0f, 1.0f, 0.0f, rho_ghost, stream,
-                             pos_sorted ? pos_sorted : &dummy);
+                             pos_sorted ? pos_sorted : &dummy, table);
 }
 
 int psc_interp_kick_phi_sorted_slab(const float *phi_ghost, const float *u_ghost, float f, int fr_n, int order, int x0,
                                     int nxl, int ghost, const float *pos_sorted, const void *scratch,
-                                    size_t scratch_bytes, float *vel_sorted, float *acc_sorted, int64_t np, int N,
-                                    int scheme, float half_dt, float *maxout, void *stream) {
+                                    size_t scratch_bytes, int table, float *vel_sorted, float *acc_sorted, int64_t np,
+                                    int N, int scheme, float half_dt, float *maxout, void *stream) {
   PSC_CHECK_ARG(scheme == PSC_CIC || scheme == PSC_TSC, "mass scheme must be CIC or TSC");
   PSC_CHECK_ARG(order == 2 || order == 3 || order == 5 || order == 7, "gradient order must be 2, 3, 5 or 7");
   PSC_CHECK_ARG(fr_n >= 0 && fr_n <= 2, "fR_n must be 1 or 2");
@@ -1731,8 +1785,9 @@ int psc_interp_kick_phi_sorted_slab(const float *phi_ghost, const float *u_ghost
   PSC_CHECK_ARG(ghost >= 1 + (order == 7 ? 3 : order == 5 ? 2 : 1), "not enough ghost planes for this stencil");
   PSC_CHECK_ARG(phi_ghost && scratch && acc_sorted && maxout && (u_ghost || fr_n == 0) && (pos_sorted || np == 0),
                 "null pointer");
+  PSC_CHECK_ARG(table == 0 || table == 1, "table must be 0 or 1");
   return interp_kick_phi_impl(phi_ghost, u_ghost, f, fr_n, order, x0, nxl, ghost, scratch, scratch_bytes, vel_sorted,
-                              acc_sorted, np, N, scheme, half_dt, maxout, stream, pos_sorted);
+                              acc_sorted, np, N, scheme, half_dt, maxout, stream, pos_sorted, table);
 }
 
 }  // extern "C"

@@ -349,6 +349,7 @@ class CudaOps:
         self._work = None
         self._scratch = None
         self._sorted = None
+        self._table = -1      # which of the scratch's two bin tables describes the sorted arrays (-1: none)
         self._leavers = None
         self._mig = None
         self._sortws = None
@@ -472,31 +473,39 @@ class CudaOps:
     # -- particles <-> mesh on particle arrays kept in bin order (no binned copy, no source-row indirection)
     sorted_layout = True
 
-    def sort_by_bin(self, pos, vel, ids, pos_out, vel_out, ids_out):
-        """counting sort of the rank's (position, velocity, id) rows into bin order; leaves the bin table in the scratch"""
+    def sort_by_bin(self, pos, vel, ids, pos_out, vel_out, ids_out, src_rows=None):
+        """Sort of the rank's (position, velocity, id) rows into bin order; leaves the bin table in the scratch.
+        src_rows: the input arrays are the output of the previous sort (its first src_rows rows), updated in place by the
+        kick + drift and the migration since -- then every CTA sorts one source bin in shared memory
+        (csrc/binned.cu step_sort_local_kernel); None: arrays in no particular order, one global atomic per particle."""
         n = pos.shape[0]
         nbytes = int(self.lib.psc_sorted_workspace_bytes_slab(n, self.N, self.nxl))
         if self._sorted is None or self._sorted.numel() < nbytes:
+            # a new scratch has no table: the bin tables live at offsets that depend on nothing but (N, nxl), but a
+            # fresh buffer is uninitialised
             self._sorted = None
             self._sorted = torch.empty((int(nbytes * 1.1) + 256,), dtype=torch.uint8, device=self.dev)
+            self._table = -1
+        src = self._table if (src_rows is not None and not os.environ.get("PSC_NO_LOCAL_SORT")) else -1
         _lib.check(self.lib.psc_sort_by_bin_slab(_lib.ptr(pos), _lib.ptr(vel), _lib.ptr(ids), n, self.N, self.x0, self.nxl,
-                                                 _lib.ptr(self._sorted), self._sorted.numel(), _lib.ptr(pos_out),
-                                                 _lib.ptr(vel_out), _lib.ptr(ids_out), _lib.stream()))
+                                                 src, int(src_rows or 0), _lib.ptr(self._sorted), self._sorted.numel(),
+                                                 _lib.ptr(pos_out), _lib.ptr(vel_out), _lib.ptr(ids_out), _lib.stream()))
+        self._table = 0 if src < 0 else 1 - src
         return n
 
     def deposit_sorted(self, pos, scheme):
         rho = torch.empty((self.nxl + 2, self.N, self.N), dtype=torch.float32, device=self.dev)
         _lib.check(self.lib.psc_deposit_sorted_slab(_lib.ptr(pos), _lib.ptr(self._sorted), self._sorted.numel(),
-                                                    pos.shape[0], self.N, self.x0, self.nxl, scheme, _lib.ptr(rho),
-                                                    _lib.stream()))
+                                                    self._table, pos.shape[0], self.N, self.x0, self.nxl, scheme,
+                                                    _lib.ptr(rho), _lib.stream()))
         return rho
 
     def interp_kick_phi_sorted(self, phi_g, ghost, order, pos, vel, acc, scheme, half_dt, u_g=None, f=0.0, fr_n=0):
         mx = torch.zeros((2,), dtype=torch.float32, device=self.dev)
         _lib.check(self.lib.psc_interp_kick_phi_sorted_slab(
             _lib.ptr(phi_g), _lib.ptr(u_g), float(f), int(fr_n), order, self.x0, self.nxl, ghost, _lib.ptr(pos),
-            _lib.ptr(self._sorted), self._sorted.numel(), _lib.ptr(vel), _lib.ptr(acc), pos.shape[0], self.N, scheme,
-            float(half_dt), _lib.ptr(mx), _lib.stream()))
+            _lib.ptr(self._sorted), self._sorted.numel(), self._table, _lib.ptr(vel), _lib.ptr(acc), pos.shape[0],
+            self.N, scheme, float(half_dt), _lib.ptr(mx), _lib.stream()))
         return mx
 
     def deposit(self, binned, scheme):
@@ -676,6 +685,7 @@ class Slab:
         self.migrated_last = (0, 0)
         self._warm_host_ops()
         self._spare3 = self._spare1 = None   # spare particle buffers the reorder gathers into (then swapped in)
+        self._sorted_rows = None             # rows [0, _sorted_rows) are the output of the last sort into bins
         self._mg = None           # SlabMultigrid (slab_multigrid.py), built at the first multigrid solve
         self._peer = None         # symmetric (peer-addressable) spectrum buffers, resolved at the first solve
         self._mig_cap = None      # records per direction of the fixed-capacity migration buffers (same on all ranks)
@@ -750,6 +760,7 @@ class Slab:
         tensors on this rank's device; ids are the global rows of the particles (kept through migrations so that
         results can be put back in the reference's order)."""
         n = position.shape[0]
+        self._sorted_rows = None
         self.np = 0
         self.pos = self.vel = self.acc = self.ids = None
         self._ensure_capacity(n)
@@ -1280,9 +1291,11 @@ class Slab:
         if self._spare3 is None or self._spare3.shape[0] != cap:
             self._spare3 = torch.empty((cap, 3), dtype=torch.float32, device=dev)
             self._spare1 = torch.empty((cap,), dtype=torch.int64, device=dev)
-        self.ops.sort_by_bin(self.pos[:n], self.vel[:n], self.ids[:n], self._spare3[:n], self.acc[:n], self._spare1[:n])
+        self.ops.sort_by_bin(self.pos[:n], self.vel[:n], self.ids[:n], self._spare3[:n], self.acc[:n], self._spare1[:n],
+                             src_rows=self._sorted_rows)
         self.pos, self.vel, self.acc, self._spare3 = self._spare3, self.acc, self.vel, self.pos
         self.ids, self._spare1 = self._spare1, self.ids
+        self._sorted_rows = n     # rows [0, n) are now in bin order (until something reorders them)
 
     def reorder(self):
         """utils.reorder_particles (utils.py:1019-1075) on the local particles (the Morton key's leading bits are
@@ -1290,6 +1303,7 @@ class Slab:
         n = self.np
         if n == 0:
             return
+        self._sorted_rows = None      # the rows are about to be permuted
         idx = self.ops.morton_order(self.pos[:n])
         # gather into a persistent spare buffer and swap it in: no allocation, no copy back
         cap = self.pos.shape[0]

@@ -165,7 +165,7 @@ class OracleOps:
     # which no consumer depends on
     sorted_layout = True
 
-    def sort_by_bin(self, pos, vel, ids, pos_out, vel_out, ids_out):
+    def sort_by_bin(self, pos, vel, ids, pos_out, vel_out, ids_out, src_rows=None):
         own = self._owner(pos)
         assert (own == self.rank).all(), "sorting particles that are not in the slab"
         N = self.N
