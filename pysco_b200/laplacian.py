@@ -87,14 +87,17 @@ def fused_sweeps_enabled():
 
 
 def sweeps(tx, tb, n, _kind=K, q=0.0, tr=None, f_relax=np.float32(1.25)) -> None:
-    """n red-black SOR sweeps on device tensors, in place on tx.  Grids the fused kernel takes (N >= 128, N % 64 == 0)
-    run their sweeps in PAIRS through psc_gauss_seidel_fused (x -> scratch -> x: 13 B per cell and sweep); an odd
-    last sweep, and every sweep of a smaller grid, is the two-launch in-place psc_gauss_seidel (24 B per cell).
-    Same bits either way."""
+    """n red-black SOR sweeps on device tensors, in place on tx.  Laplacian sweeps on grids of 512^3 and more run in
+    PAIRS through psc_gauss_seidel_fused (x -> scratch -> x: 13 B per cell and sweep); an odd last sweep, every sweep
+    of a smaller grid and the f(R) smoothers are the two-launch in-place psc_gauss_seidel (24 B per cell).  Same bits
+    either way."""
     lib = _lib.load()
     N, n = tx.shape[0], int(n)
     args = (float(np.float32(q)), _lib.ptr(tr), N, _kind, float(f_relax))
-    if n >= 2 and fused_sweeps_enabled() and lib.psc_gauss_seidel_fused_supported(N):
+    # measured (tools/bench_multigrid.py, profiles/r02_multigrid_{512,256}.txt): the fused sweep wins at 512^3 for the
+    # Laplacian (0.693 vs 0.722 ms) but loses at 256^3 (32 column CTAs for 148 SMs: 0.218 vs 0.103 ms) and for the
+    # f(R) smoothers, whose arithmetic hides the second pass over the data (1.51 vs 1.29 ms)
+    if n >= 2 and _kind == 0 and N >= 512 and fused_sweeps_enabled() and lib.psc_gauss_seidel_fused_supported(N):
         tmp = torch.empty_like(tx)
         tma = 0 if __import__("os").environ.get("PSC_GS_NO_TMA") else 1
         for _ in range(n // 2):

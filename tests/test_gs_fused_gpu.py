@@ -95,3 +95,18 @@ def test_smoothing_pairs_vs_oracle(psc):
         z = u.copy()
         oracle.cubic.smoothing_with_rhs(z, bb, q, n, rhs)
         assert_close(y, z, 1e-5, f"cubic smoothing_with_rhs x{n}")
+
+
+def test_smoothing_512_fused_pairs_equal_two_launch_sweeps(psc, monkeypatch):
+    """laplacian.sweeps at 512^3 (where the product uses the fused pairs) against the two-launch sweeps: same bits"""
+    import torch
+    N = 512
+    g = torch.Generator(device="cuda").manual_seed(5)
+    x = torch.randn((N, N, N), generator=g, device="cuda") * 1e-3
+    b = torch.randn((N, N, N), generator=g, device="cuda")
+    y = x.clone()
+    psc.laplacian.sweeps(y, b, 3)
+    monkeypatch.setenv("PSC_NO_FUSED_GS", "1")
+    z = x.clone()
+    psc.laplacian.sweeps(z, b, 3)
+    assert torch.equal(y, z)
