@@ -855,31 +855,7 @@ def run_slab_arm(args):
     peer = bool(S._peer)
     nxl = S.nxl
 
-    # ---- BASELINE config 5 (the north-star target): 2048^3 on 8 GPUs, a few steps, its own roofline
-    config5 = None
-    if world == 8 and nc < 11 and not args.no_config5:
-        del S
-        torch.cuda.empty_cache()
-        # 2048^3 on 8 GPUs peaks at ~150 GB per GPU (the Morton reorder's sort buffers on top of 1.07 G particles):
-        # attempted only when EVERY rank has the room, so that no rank can run out of memory inside a collective
-        free = torch.tensor([torch.cuda.mem_get_info()[0] / 2 ** 30], device="cuda", dtype=torch.float64)
-        dist.all_reduce(free, op=dist.ReduceOp.MIN)
-        if free.item() < args.config5_min_free_gib:
-            config5 = {"skipped": f"least free device memory over the ranks {free.item():.0f} GiB < "
-                                  f"{args.config5_min_free_gib:.0f} GiB needed for 2048^3 on 8 GPUs"}
-    if config5 is None and world == 8 and nc < 11 and not args.no_config5:
-        try:
-            S5, p5 = build(11)
-            m5 = slab_measure(S5, p5, tables, args.config5_steps, 3, world, rank, local_rank)
-            config5 = {"config": workload_config(11), "steps": args.config5_steps, "warmup": 3, "scaling": "strong",
-                       "target": "north_star: >= 0.60 of the aggregate HBM roofline",
-                       **{k: m5[k] for k in ("ms_per_step", "value", "roofline", "kernels", "kernel_ms_per_step",
-                                             "comm_and_host_ms_per_step", "phases_ms_per_step_rank0", "reorder")}}
-            del S5
-        except Exception as exc:
-            config5 = {"error": f"{type(exc).__name__}: {exc}"[:300]}
-        torch.cuda.empty_cache()
-
+    line = None
     if rank == 0:
         cfg = workload_config(nc)   # identical to the reference arm's config (same N^3 problem on every GPU count)
         cfg["timed_window"] = (f"steps {m['preroll'] + 1}..{m['preroll'] + K} of the {N_REORDER}-step reorder cycle"
@@ -900,8 +876,57 @@ def run_slab_arm(args):
                                                   "add, potential copy), 2 transposes of the half-spectrum, "
                                                   "max of 3 floats over the ranks",
                           "particles_migrated_per_step": m["particles_migrated_per_step"]},
-            "config5": config5,
+            "config5": None,
         }
+
+    # ---- BASELINE config 5 (the north-star target): 2048^3 on 8 GPUs, a few steps, its own roofline.  It runs AFTER
+    # the 512^3 measurement and must never cost that line: a watchdog prints the line without it and ends every rank if
+    # the big run does not come back (a rank that failed inside a collective leaves the others waiting).
+    config5 = None
+    if world == 8 and nc < 11 and not args.no_config5:
+        del S
+        torch.cuda.empty_cache()
+        # 2048^3 on 8 GPUs peaks at ~150 GB per GPU (the Morton reorder's sort buffers on top of 1.07 G particles):
+        # attempted only when EVERY rank has the room, so that no rank can run out of memory inside a collective
+        free = torch.tensor([torch.cuda.mem_get_info()[0] / 2 ** 30], device="cuda", dtype=torch.float64)
+        dist.all_reduce(free, op=dist.ReduceOp.MIN)
+        if free.item() < args.config5_min_free_gib:
+            config5 = {"skipped": f"least free device memory over the ranks {free.item():.0f} GiB < "
+                                  f"{args.config5_min_free_gib:.0f} GiB needed for 2048^3 on 8 GPUs"}
+    if config5 is None and world == 8 and nc < 11 and not args.no_config5:
+        import threading
+
+        def give_up():
+            if line is not None:
+                line["config5"] = {"error": f"2048^3 run did not finish within {args.config5_timeout_s:.0f} s"}
+                emit(line)
+                sys.stdout.flush()
+            os._exit(0)
+
+        watchdog = threading.Timer(args.config5_timeout_s, give_up)
+        watchdog.daemon = True
+        watchdog.start()
+        try:
+            S5, p5 = build(11)
+            m5 = slab_measure(S5, p5, tables, args.config5_steps, 3, world, rank, local_rank)
+            config5 = {"config": workload_config(11), "steps": args.config5_steps, "warmup": 3, "scaling": "strong",
+                       "target": "north_star: >= 0.60 of the aggregate HBM roofline",
+                       **{k: m5[k] for k in ("ms_per_step", "value", "roofline", "kernels", "kernel_ms_per_step",
+                                             "comm_and_host_ms_per_step", "phases_ms_per_step_rank0", "reorder")}}
+            del S5
+        except Exception as exc:
+            config5 = {"error": f"{type(exc).__name__}: {exc}"[:300]}
+            if line is not None:      # the other ranks may be waiting in a collective this rank has left
+                line["config5"] = config5
+                emit(line)
+                sys.stdout.flush()
+                os._exit(0)
+            os._exit(0)
+        watchdog.cancel()
+        torch.cuda.empty_cache()
+
+    if rank == 0:
+        line["config5"] = config5
         emit(line)
     if world > 1:
         dist.barrier()
@@ -942,6 +967,7 @@ def main():
     ap.add_argument("--extra-steps", type=int, default=8)
     ap.add_argument("--config5-steps", type=int, default=6)
     ap.add_argument("--config5-min-free-gib", type=float, default=160.0)
+    ap.add_argument("--config5-timeout-s", type=float, default=420.0)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true")
