@@ -542,6 +542,7 @@ __global__ void __launch_bounds__(256) step_sort_local_kernel(
   // the rounds of this CTA: (bin, first particle of the round within the bin), empty bins skipped
   // particles of source bin sb that are still there: its rows below `rows`
   auto live = [&](int sb) {
+    if (!SLAB) return __ldg(&fill_src[sb]);   // the single-domain arrays never change length
     const int64_t left = rows - (int64_t)__ldg(&base_src[sb]);
     return (int)max((int64_t)0, min((int64_t)__ldg(&fill_src[sb]), left));
   };
@@ -1055,7 +1056,8 @@ __global__ void __launch_bounds__(BI_THREADS) interp_kick4_binned_kernel(
 // the gradient kernel and the force grid (16 B/cell written + re-read) from the step.
 template <int ORDER> struct Reach { static constexpr int H = ORDER == 7 ? 3 : ORDER == 5 ? 2 : 1; };
 
-constexpr int BP_THREADS = 256;  // gradient + interpolation kernel
+constexpr int BP_THREADS = 256;  // gradient + interpolation kernel.  Resident CTAs per SM (register bound), 512^3, bin-ordered
+                                 // arrays: 5 (48 registers) 4.44 ms, 6 (40 registers) 4.31 ms, 7 (32 registers) 4.52 ms
 
 // TP1 / TP0: row / plane pitch of the float4 force tile.  Measured at 512^3 (Morton order): 10/100 4.41 ms, 11/110 4.62,
 // 12/120 4.59, 12/144 4.75, 14/140 4.70, 11/112 5.19, 10/104 5.39 -- the dense tile is the best of those.  Round 2,
@@ -1064,7 +1066,7 @@ constexpr int BP_THREADS = 256;  // gradient + interpolation kernel
 // fall into 8 different 16-byte bank groups: 10/100 4.33 ms, 16/160 4.26 ms -- removing the LDS.128 conflicts buys 4 %,
 // less than the finer sort key costs in the sort (+0.17 ms) and the deposit (+0.08 ms).
 template <int SCHEME, int ORDER, bool SORTED, int TP1 = BT, int TP0 = BT * BT>
-__global__ void __launch_bounds__(BP_THREADS) interp_kick_phi_binned_kernel(
+__global__ void __launch_bounds__(BP_THREADS, 6) interp_kick_phi_binned_kernel(
     const float *__restrict__ phi, const float *__restrict__ u, float f, int fr_n,
     const void *__restrict__ brec, const int *__restrict__ base, const int *__restrict__ fill,
     float *__restrict__ vel, float *__restrict__ accel, int N, int NB, int x0, int xoff, int nxa, float half_dt,

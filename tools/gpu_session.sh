@@ -19,6 +19,10 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --profile-
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:'deposit_binned_kernel|interp_kick_phi_binned_kernel|step_sort' \
   --launch-skip 8 --launch-count 8 -o $out/${tag}_particle_kernels -f python tools/prof_step.py 9 step > $out/${tag}_ncu_full.log 2>&1
 python tools/ncu_summary.py $out/${tag}_particle_kernels.ncu-rep > $out/${tag}_particle_kernels_ncu.txt 2>&1
+if [ -n "$REFARM" ]; then
+timeout 900 python bench.py --impl reference --steps 3 --warmup 1 > $out/${tag}_reference_arm.json 2> $out/${tag}_reference_arm.err
+echo "reference arm rc=$?" >> $out/${tag}_reference_arm.err
+fi
 if [ -n "$DIAG3" ]; then
 for v in "" "PSC_NO_FUSED_GS=1" "PSC_ORDER=reference"; do env $v timeout 300 python tools/diag_config3.py 8 14 >> $out/${tag}_diag3.log 2>&1; done
 fi
