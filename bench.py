@@ -47,6 +47,7 @@ ALGO_BYTES = {
     "psc_fft_r2c": 8.0,            # read 4 + write 4 (half-spectrum ~ 4 B per real cell)
     "psc_green": 8.0,
     "psc_fft_c2r": 8.0,
+    "psc_fft_poisson": 24.0,       # = r2c + Green + c2r in one call (the x passes and the Green multiply fused)
     "psc_gradient": 16.0,          # read phi (4) + write force (12)
     "psc_interp_kick4": 60.0,      # read x,v (24) + force once per cell (12) + write v,a (24)
     "psc_interp_kick4_binned": 60.0,

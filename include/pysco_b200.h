@@ -276,6 +276,12 @@ int psc_fft_r2c(void *plan, const float *in, float *spec_out, void *stream);
 int psc_fft_c2r(void *plan, float *spec_in, float *out, void *stream);
 /* fourier.ifft_3D_real_grad (fourier.py:372-410): three C2R transforms of an interleaved
  * [N,N,N/2+1,3] spectrum into an AoS [N,N,N,3] grid */
+/* solver.fft (solver.py:444-500) in one call: out = irfftn(G * rfftn(rhs)) with G = Green's function (kind) x
+ * W^-2p x scale.  cuFFT runs the batched 2-D (y, z) transforms of the x planes; the forward and backward transforms
+ * along x and the Green multiply are ONE kernel (shared-memory radix-8 FFT, 5 passes over the spectrum instead of 7).
+ * N = 64 or 512 (psc_fft_poisson_supported); spec = [N, N, N/2+1] complex64 scratch; out may alias rhs. */
+int psc_fft_poisson_supported(int N);
+int psc_fft_poisson(void *plan, const float *rhs, float *spec, float *out, int kind, int p, float scale, void *stream);
 int psc_fft_c2r_vec3(void *plan, float *spec3_in, float *out3, void *stream);
 /* fourier.inverse_laplacian / _compensated / _7pt (fourier.py:460-595), in place, DC zeroed;
  * every mode is additionally multiplied by `scale` */

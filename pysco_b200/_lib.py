@@ -82,6 +82,8 @@ SIGNATURES = {
     "psc_fft_plan_workspace_bytes": [_vp],
     "psc_fft_r2c": [_vp, _vp, _vp, _vp],
     "psc_fft_c2r": [_vp, _vp, _vp, _vp],
+    "psc_fft_poisson_supported": [_i],
+    "psc_fft_poisson": [_vp, _vp, _vp, _vp, _i, _i, _f, _vp],
     "psc_fft_c2r_vec3": [_vp, _vp, _vp, _vp],
     "psc_green": [_vp, _i, _i, _i, _f, _vp],
     "psc_grad_green": [_vp, _i, _i, _f, _vp, _vp],
@@ -153,7 +155,7 @@ class _Timed:
 
 _TIMED = ("psc_morton_keys", "psc_argsort_keys", "psc_gather3", "psc_axpy", "psc_periodic_wrap", "psc_max_abs",
           "psc_kick_drift_wrap", "psc_kick_drift_wrap_count", "psc_bin_particles_counted", "psc_step_sort", "psc_deposit_sorted", "psc_interp_kick_phi_sorted", "psc_scatter3_by_id", "psc_morton_ids_sorted", "psc_deposit", "psc_bin_particles", "psc_deposit_binned", "psc_interp_kick4_binned", "psc_interp_kick_phi_binned", "psc_interp", "psc_interp_kick", "psc_interp_kick4", "psc_linear_operator",
-          "psc_lincomb", "psc_gradient", "psc_fft_r2c", "psc_fft_c2r", "psc_fft_c2r_vec3", "psc_green",
+          "psc_lincomb", "psc_gradient", "psc_fft_r2c", "psc_fft_c2r", "psc_fft_c2r_vec3", "psc_fft_poisson", "psc_green",
           "psc_grad_green", "psc_pk", "psc_operator", "psc_residual", "psc_restrict_residual",
           "psc_residual_sumsq", "psc_diff_sumsq", "psc_initialise_potential", "psc_gauss_seidel", "psc_gauss_seidel_fused",
           "psc_restriction", "psc_prolongation", "psc_mond_rhs",

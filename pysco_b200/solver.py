@@ -99,12 +99,24 @@ def fft(rhs, param):
     trhs = c.dev(rhs)
     N = trhs.shape[0]
     MAS_index = param["MAS_index"]
-    spec = fourier.fft_3D_real(trhs, param["nthreads"])
     name = param["linear_newton_solver"].casefold()
     compute_MOND_potential = param["compute_additional_field"] is False and param["theory"] == "mond".casefold()
-    if "save_pk" in param and param["save_pk"] and not compute_MOND_potential:
-        _write_pk(spec, param, N, True)
+    want_pk = "save_pk" in param and param["save_pk"] and not compute_MOND_potential
     scale = 1.0 / float(N) ** 3
+    lib = _lib.load()
+    if (not want_pk and name in ("fft", "fft_7pt") and lib.psc_fft_poisson_supported(N)
+            and not __import__("os").environ.get("PSC_NO_FUSED_XFFT")):
+        # cuFFT does the (y, z) transforms of the x planes; the transforms along x and the Green's function are one
+        # kernel (csrc/fourier.cu xfft_green_kernel): 5 passes over the spectrum instead of 7
+        kind = _lib.GREEN_7PT if name == "fft_7pt" else (_lib.GREEN_PLAIN if MAS_index == 0 else _lib.GREEN_COMPENSATED)
+        spec = _lib.empty((N, N, N // 2 + 1), torch.complex64)
+        out = trhs if not c.np_mode else _lib.empty((N, N, N))
+        _lib.check(lib.psc_fft_poisson(_lib.fft_plan(N), _lib.ptr(trhs), _lib.ptr(spec), _lib.ptr(out), kind,
+                                       int(MAS_index), scale, _lib.stream()))
+        return c.ret(out)
+    spec = fourier.fft_3D_real(trhs, param["nthreads"])
+    if want_pk:
+        _write_pk(spec, param, N, True)
     if name == "fft":
         if MAS_index == 0:
             fourier.inverse_laplacian(spec, scale)

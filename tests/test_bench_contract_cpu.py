@@ -75,3 +75,5 @@ def test_every_timed_kernel_has_an_algorithmic_byte_entry_or_is_overhead():
     assert sum(bench.ALGO_BYTES[k] for k in single) == 176.0
     loop = ["psc_step_sort", "psc_deposit_sorted", "psc_fft_r2c", "psc_green", "psc_fft_c2r", "psc_interp_kick_phi_sorted"]
     assert sum(bench.ALGO_BYTES[k] for k in loop) == 176.0
+    fused = ["psc_step_sort", "psc_deposit_sorted", "psc_fft_poisson", "psc_interp_kick_phi_sorted"]
+    assert sum(bench.ALGO_BYTES[k] for k in fused) == 176.0

@@ -8,6 +8,8 @@ and checks size-independent properties at larger sizes (mass conservation, zero-
 
 Tolerances: Morton keys / orderings bit-exact; float32 fields max|diff| <= tol * rms(reference).
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -628,3 +630,37 @@ def test_nonfinite_force_stops_the_run(psc):
     param["nsteps"] += 1
     with pytest.raises(ValueError, match="math domain error"):
         psc.integration.integrate(*state, tables, param, 1e30)
+
+
+@pytest.mark.parametrize("N", [64, 512])
+@pytest.mark.parametrize("solver_name,mas", [("fft", 0), ("fft", 3), ("fft_7pt", 3)])
+def test_fft_poisson_fused_x_pass(psc, orc, N, solver_name, mas):
+    """solver.fft through psc_fft_poisson (cuFFT 2-D (y, z) transforms + ONE kernel for the forward transform along x,
+    the Green's function and the backward transform along x) against the three-call path (rfftn, Green, irfftn) and, at
+    64^3, against the oracle: two float32 FFTs of the same data, tolerance of the potential as in DESIGN section 2"""
+    import torch
+    L = psc._lib.load()
+    assert L.psc_fft_poisson_supported(N) and not L.psc_fft_poisson_supported(128)
+    rhs = cases.density_contrast_rhs(N, seed=77) if N == 64 else None
+    if rhs is None:
+        g = torch.Generator(device="cuda").manual_seed(9)
+        t = torch.randn((N, N, N), generator=g, device="cuda")
+        t -= t.mean()
+    else:
+        t = torch.from_numpy(rhs).cuda()
+    param = cases.base_param(int(np.log2(N)), N ** 3, linear_newton_solver=solver_name)
+    param["MAS_index"] = mas
+    param["compute_additional_field"] = False
+    param["save_pk"] = False
+    fused = psc.solver.fft(t.clone(), param)
+    os.environ["PSC_NO_FUSED_XFFT"] = "1"
+    try:
+        plain = psc.solver.fft(t.clone(), param)
+    finally:
+        del os.environ["PSC_NO_FUSED_XFFT"]
+    rms = float(plain.pow(2).mean().sqrt())
+    assert float((fused - plain).abs().max()) <= 2e-5 * rms, float((fused - plain).abs().max()) / rms
+    if rhs is not None:
+        from oracle import host
+        ref = host.fft(rhs.copy(), param)
+        assert_close(fused.cpu().numpy(), ref, 3e-5, "fused-x-pass FFT solve vs oracle")
