@@ -279,9 +279,12 @@ int psc_fft_c2r(void *plan, float *spec_in, float *out, void *stream);
 /* solver.fft (solver.py:444-500) in one call: out = irfftn(G * rfftn(rhs)) with G = Green's function (kind) x
  * W^-2p x scale.  cuFFT runs the batched 2-D (y, z) transforms of the x planes; the forward and backward transforms
  * along x and the Green multiply are ONE kernel (shared-memory radix-8 FFT, 5 passes over the spectrum instead of 7).
- * N = 64 or 512 (psc_fft_poisson_supported); spec = [N, N, N/2+1] complex64 scratch; out may alias rhs. */
+ * N = a power of two in [64, 2048] (psc_fft_poisson_supported); spec = [N, N, N/2+1] complex64 scratch; out may alias
+ * rhs.  psc_xfft_green_slab: the same kernel on the transposed spectrum [N (kx)][nyl (ky = y0 ..)][N/2+1] of the
+ * slab-decomposed solve, replacing psc_slab_fft_x (forward) + psc_green_slab + psc_slab_fft_x (backward). */
 int psc_fft_poisson_supported(int N);
 int psc_fft_poisson(void *plan, const float *rhs, float *spec, float *out, int kind, int p, float scale, void *stream);
+int psc_xfft_green_slab(float *spec_t, int N, int nyl, int y0, int kind, int p, float scale, void *stream);
 int psc_fft_c2r_vec3(void *plan, float *spec3_in, float *out3, void *stream);
 /* fourier.inverse_laplacian / _compensated / _7pt (fourier.py:460-595), in place, DC zeroed;
  * every mode is additionally multiplied by `scale` */

@@ -84,6 +84,7 @@ SIGNATURES = {
     "psc_fft_c2r": [_vp, _vp, _vp, _vp],
     "psc_fft_poisson_supported": [_i],
     "psc_fft_poisson": [_vp, _vp, _vp, _vp, _i, _i, _f, _vp],
+    "psc_xfft_green_slab": [_vp, _i, _i, _i, _i, _i, _f, _vp],
     "psc_fft_c2r_vec3": [_vp, _vp, _vp, _vp],
     "psc_green": [_vp, _i, _i, _i, _f, _vp],
     "psc_grad_green": [_vp, _i, _i, _f, _vp, _vp],
@@ -161,7 +162,7 @@ _TIMED = ("psc_morton_keys", "psc_argsort_keys", "psc_gather3", "psc_axpy", "psc
           "psc_restriction", "psc_prolongation", "psc_mond_rhs",
           "psc_bin_particles_slab", "psc_deposit_binned_slab", "psc_interp_kick_phi_binned_slab", "psc_sort_by_bin_slab", "psc_deposit_sorted_slab", "psc_interp_kick_phi_sorted_slab", "psc_slab_count",
           "psc_slab_pack_leavers", "psc_kick_drift_wrap_slab", "psc_slab_pack_rows", "psc_slab_pack_fixed", "psc_slab_unpack_rows", "psc_slab_move_rows", "psc_slab_fft_r2c_planes",
-          "psc_slab_fft_c2r_planes", "psc_slab_fft_x", "psc_slab_transpose_put", "psc_slab_yblocks", "psc_green_slab")
+          "psc_slab_fft_c2r_planes", "psc_slab_fft_x", "psc_slab_transpose_put", "psc_slab_yblocks", "psc_green_slab", "psc_xfft_green_slab")
 
 
 def load():

@@ -7,6 +7,9 @@
 #include <cufft.h>
 
 #include <cmath>
+#include <map>
+#include <mutex>
+#include <utility>
 #include <vector>
 
 #include "common.cuh"
@@ -203,15 +206,14 @@ __global__ void __launch_bounds__(256) pk_kernel(float2 *__restrict__ spec, int 
 // and does the rest -- forward transform along x, the Green / deconvolution / 1/N^3 multiply, backward transform along
 // x -- in ONE pass: 5 passes over the 0.54 GB spectrum at 512^3 instead of 7.
 //
-// A CTA owns the x columns of one ky and 16 consecutive kz (128 contiguous bytes per x): N x 16 complex values in shared
-// memory, column pitch N + 1 (the 16 lanes of a half warp work on 16 different columns: 16 different 8-byte bank pairs).
-// N = 8^S: S radix-8 stages, decimation in frequency on the way forward (natural order in, digit-reversed out),
+// A CTA owns the x columns of one ky and 16 consecutive kz (128 contiguous bytes per x; 8 for N = 2048): N x 16 complex
+// values in shared memory, column pitch N + 1 (the 16 lanes of a half warp work on 16 different columns: 16 different
+// 8-byte bank pairs).  N = 8^S x {8, 4, 2}: radix-8 stages and a last radix-8 / 4 / 2 stage on contiguous blocks,
+// decimation in frequency on the way forward (natural order in, digit-reversed out),
 // decimation in time on the way back (digit-reversed in, natural out), so no reordering is ever needed: the Green
 // multiply runs on the digit-reversed modes, in registers, between the last forward and the first backward butterfly
 // of a block of 8.  The first stage reads its 8 inputs straight from global memory and the last one stores straight
 // back (x = j + (N/8) m for 16 adjacent kz: 128-byte segments).
-constexpr int XF_TK = 16;   // kz per CTA
-
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
   return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
 }
@@ -219,130 +221,215 @@ __device__ __forceinline__ float2 cmulc(float2 a, float2 b) {   // a * conj(b)
   return make_float2(a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y);
 }
 
-// X_q = sum_m v_m exp(-+ 2 pi i q m / 8), natural order in and out; FWD: minus sign
+// X_q = sum_m v_m exp(-+ 2 pi i q m / R), natural order in and out; FWD: minus sign.  R = 8, 4, 2.
 template <bool FWD>
-__device__ __forceinline__ void dft8(float2 (&v)[8]) {
-  constexpr float R = 0.70710678118654752f;
-  auto add = [](float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); };
-  auto sub = [](float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); };
-  auto rot = [](float2 a) { return FWD ? make_float2(a.y, -a.x) : make_float2(-a.y, a.x); };   // * (-+ i)
-  const float2 a0 = add(v[0], v[4]), a4 = sub(v[0], v[4]);
-  const float2 a1 = add(v[1], v[5]), t5 = sub(v[1], v[5]);
-  const float2 a2 = add(v[2], v[6]), a6 = rot(sub(v[2], v[6]));
-  const float2 a3 = add(v[3], v[7]), t7 = sub(v[3], v[7]);
-  // W8^1 = (1 -+ i) / sqrt 2, W8^3 = (-1 -+ i) / sqrt 2
-  const float2 a5 = FWD ? make_float2(R * (t5.x + t5.y), R * (t5.y - t5.x)) : make_float2(R * (t5.x - t5.y), R * (t5.y + t5.x));
-  const float2 a7 = FWD ? make_float2(R * (t7.y - t7.x), -R * (t7.x + t7.y)) : make_float2(-R * (t7.x + t7.y), R * (t7.x - t7.y));
-  // even outputs from (a0..a3), odd outputs from (a4, a5, a6, a7)
-  const float2 b0 = add(a0, a2), b2 = sub(a0, a2), b1 = add(a1, a3), b3 = rot(sub(a1, a3));
-  const float2 c0 = add(a4, a6), c2 = sub(a4, a6), c1 = add(a5, a7), c3 = rot(sub(a5, a7));
-  v[0] = add(b0, b1); v[4] = sub(b0, b1); v[2] = add(b2, b3); v[6] = sub(b2, b3);
-  v[1] = add(c0, c1); v[5] = sub(c0, c1); v[3] = add(c2, c3); v[7] = sub(c2, c3);
+__device__ __forceinline__ float2 rot90(float2 a) {   // * (-+ i)
+  return FWD ? make_float2(a.y, -a.x) : make_float2(-a.y, a.x);
+}
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+
+template <bool FWD, int R>
+__device__ __forceinline__ void dft_small(float2 (&v)[8]) {
+  if (R == 2) {
+    const float2 a = cadd(v[0], v[1]), b = csub(v[0], v[1]);
+    v[0] = a; v[1] = b;
+  } else if (R == 4) {
+    const float2 b0 = cadd(v[0], v[2]), b2 = csub(v[0], v[2]), b1 = cadd(v[1], v[3]), b3 = rot90<FWD>(csub(v[1], v[3]));
+    v[0] = cadd(b0, b1); v[2] = csub(b0, b1); v[1] = cadd(b2, b3); v[3] = csub(b2, b3);
+  } else {
+    constexpr float Q = 0.70710678118654752f;
+    const float2 a0 = cadd(v[0], v[4]), a4 = csub(v[0], v[4]);
+    const float2 a1 = cadd(v[1], v[5]), t5 = csub(v[1], v[5]);
+    const float2 a2 = cadd(v[2], v[6]), a6 = rot90<FWD>(csub(v[2], v[6]));
+    const float2 a3 = cadd(v[3], v[7]), t7 = csub(v[3], v[7]);
+    // W8^1 = (1 -+ i) / sqrt 2, W8^3 = (-1 -+ i) / sqrt 2
+    const float2 a5 = FWD ? make_float2(Q * (t5.x + t5.y), Q * (t5.y - t5.x)) : make_float2(Q * (t5.x - t5.y), Q * (t5.y + t5.x));
+    const float2 a7 = FWD ? make_float2(Q * (t7.y - t7.x), -Q * (t7.x + t7.y)) : make_float2(-Q * (t7.x + t7.y), Q * (t7.x - t7.y));
+    // even outputs from (a0..a3), odd outputs from (a4, a5, a6, a7)
+    const float2 b0 = cadd(a0, a2), b2 = csub(a0, a2), b1 = cadd(a1, a3), b3 = rot90<FWD>(csub(a1, a3));
+    const float2 c0 = cadd(a4, a6), c2 = csub(a4, a6), c1 = cadd(a5, a7), c3 = rot90<FWD>(csub(a5, a7));
+    v[0] = cadd(b0, b1); v[4] = csub(b0, b1); v[2] = cadd(b2, b3); v[6] = csub(b2, b3);
+    v[1] = cadd(c0, c1); v[5] = csub(c0, c1); v[3] = cadd(c2, c3); v[7] = csub(c2, c3);
+  }
 }
 
+// N = 8^S x RM: S radix-8 stages and a last radix RM = 8, 4 or 2 on contiguous blocks
+template <int N> struct XfShape {
+  static constexpr int RM = (N == 64 || N == 512) ? 8 : (N == 256 || N == 2048) ? 4 : 2;
+  static constexpr int S = (N / RM == 8) ? 1 : (N / RM == 64) ? 2 : 3;
+  static constexpr int TK = N <= 1024 ? 16 : 8;     // kz per CTA (64 KB .. 131 KB of columns)
+  static_assert(N == 64 || N == 128 || N == 256 || N == 512 || N == 1024 || N == 2048, "unsupported N");
+};
+__host__ __device__ constexpr int xf_pow8(int e) { return e <= 0 ? 1 : 8 * xf_pow8(e - 1); }
+
+// radix-8 stage s of the forward / backward transform of the TK columns in shared memory: blocks of B = N / 8^(s-1),
+// sub-stride L = B / 8, twiddles W_B^(j q) = W_N^(8^(s-1) j q)
+template <int N, int TK, int PITCH, int s, bool FWD>
+__device__ __forceinline__ void xf_stage(float2 *col, const float2 *tw) {
+  constexpr int L = N / xf_pow8(s), B = 8 * L, M = xf_pow8(s - 1);
+  for (int u = threadIdx.x; u < N * TK / 8; u += 256) {
+    const int c = u % TK, t = u / TK, blk = t / L, j = t - blk * L;
+    float2 *a = col + c * PITCH + blk * B + j;
+    float2 v[8];
+    if (FWD) {
+#pragma unroll
+      for (int m = 0; m < 8; m++) v[m] = a[L * m];
+      dft_small<true, 8>(v);
+#pragma unroll
+      for (int q = 0; q < 8; q++) a[L * q] = q ? cmul(v[q], tw[M * j * q]) : v[q];
+    } else {
+#pragma unroll
+      for (int q = 0; q < 8; q++) v[q] = q ? cmulc(a[L * q], tw[M * j * q]) : a[0];
+      dft_small<false, 8>(v);
+#pragma unroll
+      for (int m = 0; m < 8; m++) a[L * m] = v[m];
+    }
+  }
+  __syncthreads();
+}
+
+// spec: element (x, row, kz) at x * xstride + row * nz + kz; row = 0 .. nrows-1 is ky = y0 + row.  Whole grid:
+// xstride = N * nz, nrows = N, y0 = 0; transposed slab layout [kx][nyl][nz]: xstride = nyl * nz, nrows = nyl.
 template <int KIND, int N>
 __global__ void __launch_bounds__(256) xfft_green_kernel(float2 *__restrict__ spec, const float2 *__restrict__ twiddle,
-                                                         int p, float scale) {
-  static_assert(N == 64 || N == 512, "N = 8^S");
-  constexpr int nz = N / 2 + 1, L1 = N / 8, PITCH = N + 1;
-  extern __shared__ float2 xs[];          // [XF_TK][PITCH] columns, then the twiddles [N], then the Green table [N]
-  float2 *col = xs, *tw = xs + XF_TK * PITCH, *gtab = tw + N;
-  const int ky = blockIdx.y, kz0 = blockIdx.x * XF_TK;
+                                                         size_t xstride, int y0, int p, float scale) {
+  constexpr int nz = N / 2 + 1, L1 = N / 8, PITCH = N + 1, RM = XfShape<N>::RM, S = XfShape<N>::S, TK = XfShape<N>::TK;
+  extern __shared__ float2 xs[];          // [TK][PITCH] columns, then the twiddles [N], then the Green table [N]
+  float2 *col = xs, *tw = xs + TK * PITCH, *gtab = tw + N;
+  const int ky = y0 + blockIdx.y, kz0 = blockIdx.x * TK;
   for (int n = threadIdx.x; n < N; n += 256) {
     tw[n] = twiddle[n];
     gtab[n] = green_axis_entry<KIND>(n, N, p);
   }
   const float h = 1.0f / (float)N;
   const float cst = (KIND == PSC_GREEN_7PT ? -(0.25f * h * h) : -0.0253302959105844f) * scale;
-  constexpr int NB8 = N * XF_TK / 8;      // butterflies per stage
-  float2 *g0 = spec + (size_t)ky * nz + kz0;          // + x * N * nz + c
-  constexpr size_t XS = (size_t)N * nz;   // stride of x in the spectrum
-  // ---- forward stage 1: x = j + L1 m from global memory, out at j + L1 q, times W_N^(j q)
+  float2 *g0 = spec + (size_t)blockIdx.y * nz + kz0;          // + x * xstride + c
   __syncthreads();
-  for (int u = threadIdx.x; u < NB8; u += 256) {
-    const int c = u % XF_TK, j = u / XF_TK;
+  // ---- forward stage 1: x = j + L1 m from global memory, out at j + L1 q, times W_N^(j q)
+  for (int u = threadIdx.x; u < N * TK / 8; u += 256) {
+    const int c = u % TK, j = u / TK;
     float2 v[8];
     if (kz0 + c < nz) {
 #pragma unroll
-      for (int m = 0; m < 8; m++) v[m] = g0[(size_t)(j + L1 * m) * XS + c];
+      for (int m = 0; m < 8; m++) v[m] = g0[(size_t)(j + L1 * m) * xstride + c];
     } else {
 #pragma unroll
       for (int m = 0; m < 8; m++) v[m] = make_float2(0.0f, 0.0f);
     }
-    dft8<true>(v);
+    dft_small<true, 8>(v);
 #pragma unroll
-    for (int q = 0; q < 8; q++) col[c * PITCH + j + L1 * q] = q ? cmul(v[q], tw[(j * q) & (N - 1)]) : v[q];
+    for (int q = 0; q < 8; q++) col[c * PITCH + j + L1 * q] = q ? cmul(v[q], tw[j * q]) : v[q];
   }
   __syncthreads();
-  if (N == 512) {
-    // ---- forward stage 2: blocks of 64, sub-stride 8, twiddle W_64^(j2 q) = W_512^(8 j2 q)
-    for (int u = threadIdx.x; u < NB8; u += 256) {
-      const int c = u % XF_TK, t = u / XF_TK, base = (t >> 3) * 64 + (t & 7), j2 = t & 7;
-      float2 *a = col + c * PITCH + base;
-      float2 v[8];
-#pragma unroll
-      for (int m = 0; m < 8; m++) v[m] = a[8 * m];
-      dft8<true>(v);
-#pragma unroll
-      for (int q = 0; q < 8; q++) a[8 * q] = q ? cmul(v[q], tw[8 * j2 * q]) : v[q];
-    }
-    __syncthreads();
-  }
-  // ---- last forward stage, Green's function, first backward stage: blocks of 8 in registers.  Position p of the
-  // digit-reversed spectrum holds kx = q1 + 8 q2 (+ 64 q3): the digits of p read backwards
-  for (int u = threadIdx.x; u < NB8; u += 256) {
-    const int c = u % XF_TK, blk = u / XF_TK;
-    float2 *a = col + c * PITCH + 8 * blk;
+  if constexpr (S >= 2) xf_stage<N, TK, PITCH, 2, true>(col, tw);
+  if constexpr (S >= 3) xf_stage<N, TK, PITCH, 3, true>(col, tw);
+  // ---- last forward stage, Green's function, first backward stage: blocks of RM in registers.  The block index read
+  // backwards in base 8 gives the low digits of kx, the position within the block the highest one.
+  for (int u = threadIdx.x; u < N * TK / RM; u += 256) {
+    const int c = u % TK, blk = u / TK;
+    float2 *a = col + c * PITCH + RM * blk;
     float2 v[8];
 #pragma unroll
-    for (int m = 0; m < 8; m++) v[m] = a[m];
-    dft8<true>(v);
-    const int klow = N == 512 ? (blk >> 3) + 8 * (blk & 7) : blk;        // q1 + 8 q2 | q1
+    for (int m = 0; m < RM; m++) v[m] = a[m];
+    dft_small<true, RM>(v);
+    const int klow = S == 1 ? blk : S == 2 ? (blk >> 3) + 8 * (blk & 7) : (blk >> 6) + 8 * ((blk >> 3) & 7) + 64 * (blk & 7);
     const int kz = min(kz0 + c, nz - 1);
     const float2 ty = gtab[ky], tz = gtab[kz];
     const float k2 = ty.x + tz.x, w = ty.y * tz.y;
 #pragma unroll
-    for (int q = 0; q < 8; q++) {
-      const int kx = klow + (N / 8) * q;
+    for (int q = 0; q < RM; q++) {
+      const int kx = klow + xf_pow8(S) * q;
       const float2 tx = gtab[kx];
       float g = cst * (w * tx.y) / (k2 + tx.x);
       if (kx == 0 && ky == 0 && kz == 0) g = 0.0f;    // DC mode -> 0 (reference: x[0,0,0] = 0 after the division)
       v[q].x *= g;
       v[q].y *= g;
     }
-    dft8<false>(v);
+    dft_small<false, RM>(v);
 #pragma unroll
-    for (int m = 0; m < 8; m++) a[m] = v[m];
+    for (int m = 0; m < RM; m++) a[m] = v[m];
   }
   __syncthreads();
-  if (N == 512) {
-    // ---- backward stage 2
-    for (int u = threadIdx.x; u < NB8; u += 256) {
-      const int c = u % XF_TK, t = u / XF_TK, base = (t >> 3) * 64 + (t & 7), j2 = t & 7;
-      float2 *a = col + c * PITCH + base;
-      float2 v[8];
-#pragma unroll
-      for (int q = 0; q < 8; q++) v[q] = q ? cmulc(a[8 * q], tw[8 * j2 * q]) : a[0];
-      dft8<false>(v);
-#pragma unroll
-      for (int m = 0; m < 8; m++) a[8 * m] = v[m];
-    }
-    __syncthreads();
-  }
+  if constexpr (S >= 3) xf_stage<N, TK, PITCH, 3, false>(col, tw);
+  if constexpr (S >= 2) xf_stage<N, TK, PITCH, 2, false>(col, tw);
   // ---- backward stage 1, straight to global memory
-  for (int u = threadIdx.x; u < NB8; u += 256) {
-    const int c = u % XF_TK, j = u / XF_TK;
+  for (int u = threadIdx.x; u < N * TK / 8; u += 256) {
+    const int c = u % TK, j = u / TK;
     if (kz0 + c >= nz) continue;
     float2 v[8];
 #pragma unroll
     for (int q = 0; q < 8; q++) {
       const float2 e = col[c * PITCH + j + L1 * q];
-      v[q] = q ? cmulc(e, tw[(j * q) & (N - 1)]) : e;
+      v[q] = q ? cmulc(e, tw[j * q]) : e;
     }
-    dft8<false>(v);
+    dft_small<false, 8>(v);
 #pragma unroll
-    for (int m = 0; m < 8; m++) g0[(size_t)(j + L1 * m) * XS + c] = v[m];
+    for (int m = 0; m < 8; m++) g0[(size_t)(j + L1 * m) * xstride + c] = v[m];
   }
+}
+
+// W_N^k = exp(-2 pi i k / N), k < N, built once per (device, N) from double precision
+static float2 *xf_twiddles(int N) {
+  static std::mutex mu;
+  static std::map<std::pair<int, int>, float2 *> cache;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  std::lock_guard<std::mutex> lock(mu);
+  auto it = cache.find({dev, N});
+  if (it != cache.end()) return it->second;
+  std::vector<float2> tw(N);
+  for (int k = 0; k < N; k++) {
+    const double a = -2.0 * 3.14159265358979323846 * (double)k / (double)N;
+    tw[k] = make_float2((float)cos(a), (float)sin(a));
+  }
+  float2 *d = nullptr;
+  if (cudaMalloc(&d, sizeof(float2) * N) != cudaSuccess) return nullptr;
+  if (cudaMemcpy(d, tw.data(), sizeof(float2) * N, cudaMemcpyHostToDevice) != cudaSuccess) return nullptr;
+  cache[{dev, N}] = d;
+  return d;
+}
+
+template <int KIND, int N>
+static int xfft_green_launch(float2 *spec, size_t xstride, int nrows, int y0, int p, float scale, cudaStream_t st) {
+  constexpr int TK = XfShape<N>::TK, nz = N / 2 + 1;
+  const size_t smem = sizeof(float2) * (TK * (N + 1) + 2 * N);
+  static bool attr = false;
+  if (!attr) {
+    PSC_CUDA(cudaFuncSetAttribute(xfft_green_kernel<KIND, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr = true;
+  }
+  float2 *tw = xf_twiddles(N);
+  if (!tw) {
+    set_error("xfft_green: could not allocate the twiddle table");
+    return PSC_ERR_CUDA;
+  }
+  const dim3 grid((nz + TK - 1) / TK, nrows);
+  xfft_green_kernel<KIND, N><<<grid, 256, smem, st>>>(spec, tw, xstride, y0, p, scale);
+  count_launch();
+  PSC_CHECK_LAUNCH();
+  return PSC_OK;
+}
+
+template <int KIND>
+static int xfft_green_n(float2 *spec, int N, size_t xstride, int nrows, int y0, int p, float scale, cudaStream_t st) {
+  switch (N) {
+    case 64: return xfft_green_launch<KIND, 64>(spec, xstride, nrows, y0, p, scale, st);
+    case 128: return xfft_green_launch<KIND, 128>(spec, xstride, nrows, y0, p, scale, st);
+    case 256: return xfft_green_launch<KIND, 256>(spec, xstride, nrows, y0, p, scale, st);
+    case 512: return xfft_green_launch<KIND, 512>(spec, xstride, nrows, y0, p, scale, st);
+    case 1024: return xfft_green_launch<KIND, 1024>(spec, xstride, nrows, y0, p, scale, st);
+    case 2048: return xfft_green_launch<KIND, 2048>(spec, xstride, nrows, y0, p, scale, st);
+  }
+  set_error("xfft_green: N must be a power of two in [64, 2048]");
+  return PSC_ERR_INVALID;
+}
+
+static int xfft_green(float2 *spec, int N, size_t xstride, int nrows, int y0, int kind, int p, float scale,
+                      cudaStream_t st) {
+  if (kind == PSC_GREEN_PLAIN) return xfft_green_n<PSC_GREEN_PLAIN>(spec, N, xstride, nrows, y0, p, scale, st);
+  if (kind == PSC_GREEN_COMPENSATED) return xfft_green_n<PSC_GREEN_COMPENSATED>(spec, N, xstride, nrows, y0, p, scale, st);
+  return xfft_green_n<PSC_GREEN_7PT>(spec, N, xstride, nrows, y0, p, scale, st);
 }
 
 }  // namespace psc
@@ -378,7 +465,6 @@ int psc_fft_plan_destroy(void *plan) {
   if (pl->has_yz) {
     cufftDestroy(pl->r2c_yz);
     cufftDestroy(pl->c2r_yz);
-    cudaFree(pl->twiddle);
   }
   delete pl;
   return PSC_OK;
@@ -406,16 +492,16 @@ int psc_fft_c2r(void *plan, float *spec_in, float *out, void *stream) {
   return PSC_OK;
 }
 
-int psc_fft_poisson_supported(int N) { return N == 64 || N == 512; }
+int psc_fft_poisson_supported(int N) { return N >= 64 && N <= 2048 && (N & (N - 1)) == 0; }
 
 /* solver.fft (solver.py:444-500) in one call: rhs -> rfftn -> Green's function x W^-2p x scale -> irfftn -> out.
  * cuFFT does the batched 2-D (y, z) transforms of the x planes; the transforms along x and the Green multiply are one
- * kernel (xfft_green_kernel).  spec: [N, N, N/2+1] complex64 scratch; out may alias rhs.  N = 64 or 512. */
+ * kernel (xfft_green_kernel).  spec: [N, N, N/2+1] complex64 scratch; out may alias rhs.  N: power of two, 64..2048. */
 int psc_fft_poisson(void *plan, const float *rhs, float *spec, float *out, int kind, int p, float scale, void *stream) {
   PSC_CHECK_ARG(plan && rhs && spec && out, "null pointer");
   FftPlan *pl = reinterpret_cast<FftPlan *>(plan);
   const int N = pl->N;
-  PSC_CHECK_ARG(psc_fft_poisson_supported(N), "psc_fft_poisson: N must be 64 or 512");
+  PSC_CHECK_ARG(psc_fft_poisson_supported(N), "psc_fft_poisson: N must be a power of two in [64, 2048]");
   PSC_CHECK_ARG(kind >= PSC_GREEN_PLAIN && kind <= PSC_GREEN_7PT, "unknown Green's function");
   PSC_CHECK_ARG(p >= 0 && p <= 8, "MAS index out of range");
   cudaStream_t st = as_stream(stream);
@@ -427,42 +513,28 @@ int psc_fft_poisson(void *plan, const float *rhs, float *spec, float *out, int k
     PSC_CUFFT(cufftMakePlanMany(pl->r2c_yz, 2, n, nullptr, 1, N * N, nullptr, 1, N * nz, CUFFT_R2C, N, &w));
     PSC_CUFFT(cufftCreate(&pl->c2r_yz));
     PSC_CUFFT(cufftMakePlanMany(pl->c2r_yz, 2, n, nullptr, 1, N * nz, nullptr, 1, N * N, CUFFT_C2R, N, &w));
-    std::vector<float2> tw(N);
-    for (int k = 0; k < N; k++) {
-      const double a = -2.0 * 3.14159265358979323846 * (double)k / (double)N;
-      tw[k] = make_float2((float)cos(a), (float)sin(a));
-    }
-    PSC_CUDA(cudaMalloc(&pl->twiddle, sizeof(float2) * N));
-    PSC_CUDA(cudaMemcpy(pl->twiddle, tw.data(), sizeof(float2) * N, cudaMemcpyHostToDevice));
     pl->has_yz = true;
   }
   PSC_CUFFT(cufftSetStream(pl->r2c_yz, st));
   PSC_CUFFT(cufftExecR2C(pl->r2c_yz, const_cast<float *>(rhs), reinterpret_cast<cufftComplex *>(spec)));
-  const dim3 grid((nz + XF_TK - 1) / XF_TK, N);
-#define PSC_XFFT(K, NN)                                                                                          \
-  do {                                                                                                            \
-    const size_t smem = sizeof(float2) * (XF_TK * (NN + 1) + 2 * NN);                                             \
-    static bool attr = false;                                                                                     \
-    if (!attr) {                                                                                                  \
-      PSC_CUDA(cudaFuncSetAttribute(xfft_green_kernel<K, NN>, cudaFuncAttributeMaxDynamicSharedMemorySize,        \
-                                    (int)smem));                                                                  \
-      attr = true;                                                                                                \
-    }                                                                                                             \
-    xfft_green_kernel<K, NN><<<grid, 256, smem, st>>>(reinterpret_cast<float2 *>(spec), pl->twiddle, p, scale);   \
-  } while (0)
-#define PSC_XFFT_N(K)          \
-  if (N == 512) PSC_XFFT(K, 512); \
-  else PSC_XFFT(K, 64);
-  if (kind == PSC_GREEN_PLAIN) { PSC_XFFT_N(PSC_GREEN_PLAIN) }
-  else if (kind == PSC_GREEN_COMPENSATED) { PSC_XFFT_N(PSC_GREEN_COMPENSATED) }
-  else { PSC_XFFT_N(PSC_GREEN_7PT) }
-#undef PSC_XFFT_N
-#undef PSC_XFFT
-  PSC_CHECK_LAUNCH();
+  int rc = xfft_green(reinterpret_cast<float2 *>(spec), N, (size_t)N * nz, N, 0, kind, p, scale, st);
+  if (rc != PSC_OK) return rc;
   PSC_CUFFT(cufftSetStream(pl->c2r_yz, st));
   PSC_CUFFT(cufftExecC2R(pl->c2r_yz, reinterpret_cast<cufftComplex *>(spec), out));
-  count_launch(5);
+  count_launch(4);
   return PSC_OK;
+}
+
+/* The x part of the slab-decomposed FFT solve (psc_slab_fft_x forward, psc_green_slab, psc_slab_fft_x backward) in one
+ * kernel, in place on the transposed spectrum [N (kx)][nyl (ky = y0 ..)][N/2+1]. */
+int psc_xfft_green_slab(float *spec_t, int N, int nyl, int y0, int kind, int p, float scale, void *stream) {
+  PSC_CHECK_ARG(spec_t, "null pointer");
+  PSC_CHECK_ARG(psc_fft_poisson_supported(N), "psc_xfft_green_slab: N must be a power of two in [64, 2048]");
+  PSC_CHECK_ARG(nyl >= 1 && y0 >= 0 && y0 + nyl <= N, "bad y block");
+  PSC_CHECK_ARG(kind >= PSC_GREEN_PLAIN && kind <= PSC_GREEN_7PT, "unknown Green's function");
+  PSC_CHECK_ARG(p >= 0 && p <= 8, "MAS index out of range");
+  return xfft_green(reinterpret_cast<float2 *>(spec_t), N, (size_t)nyl * (N / 2 + 1), nyl, y0, kind, p, scale,
+                    as_stream(stream));
 }
 
 int psc_fft_c2r_vec3(void *plan, float *spec3_in, float *out3, void *stream) {

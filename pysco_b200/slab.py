@@ -567,6 +567,16 @@ class CudaOps:
                                         _lib.stream()))
         return bins
 
+    def xfft_green(self, spec_t, kind, p, scale):
+        """forward FFT along x, Green's function, backward FFT along x of the transposed spectrum in ONE kernel
+        (csrc/fourier.cu xfft_green_kernel); False when N is not a power of two in [64, 2048] (the caller then runs the
+        three separate steps)"""
+        if not self.lib.psc_fft_poisson_supported(self.N) or os.environ.get("PSC_NO_FUSED_XFFT"):
+            return False
+        _lib.check(self.lib.psc_xfft_green_slab(_lib.ptr(spec_t), self.N, self.nyl, self.y0, kind, p, float(scale),
+                                                _lib.stream()))
+        return True
+
     def green(self, spec_t, kind, p, scale):
         _lib.check(self.lib.psc_green_slab(_lib.ptr(spec_t), self.N, self.nyl, self.y0, kind, p, float(scale),
                                            _lib.stream()))
@@ -980,11 +990,7 @@ class Slab:
             ops.transpose_put(a, hA.buffer_ptrs_dev, True)      # -> every rank's A = [N][nyl][nz]
             del a
             hA.barrier(channel=0)
-            ops.fft_x(A, False)
-            if param.get("save_pk", False):
-                self._write_pk(A, param)
-            ops.green(A, kind, pp, 1.0 / float(self.N) ** 3)
-            ops.fft_x(A, True)
+            self._x_solve(A, kind, pp, param)
             ops.transpose_put(A, hB.buffer_ptrs_dev, False)     # -> every rank's B = [nxl][N][nz]
             hB.barrier(channel=0)
             ops.fft2d_c2r(B, out_planes)
@@ -994,14 +1000,25 @@ class Slab:
         ops.fft2d_r2c(rhs_planes, a)            # [nxl][N][nz]
         ops.yblocks(a, b, True)                 # [P][nxl][nyl][nz]
         comm.all_to_all_equal(b.view(self.P, -1), a.view(self.P, -1))   # [N][nyl][nz]
-        ops.fft_x(a, False)
-        if param.get("save_pk", False):
-            self._write_pk(a, param)
-        ops.green(a, kind, pp, 1.0 / float(self.N) ** 3)
-        ops.fft_x(a, True)
+        self._x_solve(a, kind, pp, param)
         comm.all_to_all_equal(a.view(self.P, -1), b.view(self.P, -1))   # [P(y block)][nxl][nyl][nz]
         ops.yblocks(b, a, False)                # [nxl][N][nz]
         ops.fft2d_c2r(a, out_planes)
+
+    def _x_solve(self, spec_t, kind, pp, param):
+        """the x part of the solve on the transposed spectrum [N][nyl][nz]: forward FFT along x, (P(k)), Green's
+        function with the 1/N^3 of the inverse transform, backward FFT along x -- one kernel unless a P(k) is wanted"""
+        ops = self.ops
+        scale = 1.0 / float(self.N) ** 3
+        want_pk = bool(param.get("save_pk", False))
+        fused = getattr(ops, "xfft_green", None)
+        if not want_pk and fused is not None and fused(spec_t, kind, pp, scale):
+            return
+        ops.fft_x(spec_t, False)
+        if want_pk:
+            self._write_pk(spec_t, param)
+        ops.green(spec_t, kind, pp, scale)
+        ops.fft_x(spec_t, True)
 
     def _write_pk(self, spec_t, param, from_density=False):
         """fourier.fourier_grid_to_Pk (fourier.py:22-100) + the scaling of solver.fft (solver.py:500-506) on the

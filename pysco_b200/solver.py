@@ -107,7 +107,7 @@ def fft(rhs, param):
     if (not want_pk and name in ("fft", "fft_7pt") and lib.psc_fft_poisson_supported(N)
             and not __import__("os").environ.get("PSC_NO_FUSED_XFFT")):
         # cuFFT does the (y, z) transforms of the x planes; the transforms along x and the Green's function are one
-        # kernel (csrc/fourier.cu xfft_green_kernel): 5 passes over the spectrum instead of 7
+        # kernel (csrc/fourier.cu xfft_green_kernel): 5 passes over the spectrum instead of 7 (N = 2^k, 64..2048)
         kind = _lib.GREEN_7PT if name == "fft_7pt" else (_lib.GREEN_PLAIN if MAS_index == 0 else _lib.GREEN_COMPENSATED)
         spec = _lib.empty((N, N, N // 2 + 1), torch.complex64)
         out = trhs if not c.np_mode else _lib.empty((N, N, N))

@@ -632,16 +632,16 @@ def test_nonfinite_force_stops_the_run(psc):
         psc.integration.integrate(*state, tables, param, 1e30)
 
 
-@pytest.mark.parametrize("N", [64, 512])
+@pytest.mark.parametrize("N", [64, 128, 256, 512])
 @pytest.mark.parametrize("solver_name,mas", [("fft", 0), ("fft", 3), ("fft_7pt", 3)])
 def test_fft_poisson_fused_x_pass(psc, orc, N, solver_name, mas):
     """solver.fft through psc_fft_poisson (cuFFT 2-D (y, z) transforms + ONE kernel for the forward transform along x,
-    the Green's function and the backward transform along x) against the three-call path (rfftn, Green, irfftn) and, at
-    64^3, against the oracle: two float32 FFTs of the same data, tolerance of the potential as in DESIGN section 2"""
+    the Green's function and the backward transform along x; radix 8 x 8, 8 x 8 x 2, 8 x 8 x 4, 8 x 8 x 8) against the
+    three-call path (rfftn, Green, irfftn) and, at 64^3 / 128^3, against the oracle: two float32 FFTs of the same data, tolerance of the potential as in DESIGN section 2"""
     import torch
     L = psc._lib.load()
-    assert L.psc_fft_poisson_supported(N) and not L.psc_fft_poisson_supported(128)
-    rhs = cases.density_contrast_rhs(N, seed=77) if N == 64 else None
+    assert L.psc_fft_poisson_supported(N) and not L.psc_fft_poisson_supported(96) and not L.psc_fft_poisson_supported(32)
+    rhs = cases.density_contrast_rhs(N, seed=77) if N <= 128 else None
     if rhs is None:
         g = torch.Generator(device="cuda").manual_seed(9)
         t = torch.randn((N, N, N), generator=g, device="cuda")
@@ -664,3 +664,26 @@ def test_fft_poisson_fused_x_pass(psc, orc, N, solver_name, mas):
         from oracle import host
         ref = host.fft(rhs.copy(), param)
         assert_close(fused.cpu().numpy(), ref, 3e-5, "fused-x-pass FFT solve vs oracle")
+
+
+@pytest.mark.parametrize("N,nyl,y0", [(64, 8, 16), (512, 16, 32), (1024, 4, 8), (2048, 4, 2040)])
+@pytest.mark.parametrize("kind,p", [(1, 3), (2, 0)])
+def test_xfft_green_slab_vs_torch_fft(psc, N, nyl, y0, kind, p):
+    """psc_xfft_green_slab (the x part of the slab-decomposed solve in one kernel: radix-8 stages + a last radix 8 / 4 / 2
+    stage, up to N = 2048 with 8 kz per CTA) against torch.fft along x around psc_green_slab on the same transposed
+    block [N (kx)][nyl (ky = y0 ..)][N/2+1]"""
+    import torch
+    lib, L = psc._lib, psc._lib.load()
+    nz = N // 2 + 1
+    g = torch.Generator(device="cuda").manual_seed(N + nyl)
+    a = torch.view_as_complex(torch.randn((N, nyl, nz, 2), generator=g, device="cuda"))
+    scale = 1.0 / float(N) ** 3
+    ref = torch.fft.fft(a, dim=0).contiguous()
+    lib.check(L.psc_green_slab(lib.ptr(ref), N, nyl, y0, kind, p, scale, lib.stream()))
+    ref = torch.fft.ifft(ref, dim=0) * N
+    out = a.clone()
+    lib.check(L.psc_xfft_green_slab(lib.ptr(out), N, nyl, y0, kind, p, scale, lib.stream()))
+    torch.cuda.synchronize()
+    rms = float(ref.abs().pow(2).mean().sqrt())
+    err = float((out - ref).abs().max()) / rms
+    assert err < 2e-5, err
