@@ -258,7 +258,12 @@ __device__ __forceinline__ void dft_small(float2 (&v)[8]) {
 template <int N> struct XfShape {
   static constexpr int RM = (N == 64 || N == 512) ? 8 : (N == 256 || N == 2048) ? 4 : 2;
   static constexpr int S = (N / RM == 8) ? 1 : (N / RM == 64) ? 2 : 3;
-  static constexpr int TK = N <= 1024 ? 16 : 8;     // kz per CTA (64 KB .. 131 KB of columns)
+  // kz per CTA (64 KB .. 131 KB of columns).  Measured at 512^3: 16 kz x 256 threads x 3 CTAs 0.40 ms, 16 x 512 x 2
+  // 0.39 ms, 32 kz x 1024 threads x 1 CTA 0.46 ms; N = 2048 (8 kz): 256 threads 7.3 ms, 1024 threads 5.9 ms per 4.3 GB
+  static constexpr int TK = N <= 1024 ? 16 : 8;
+  // threads per CTA: the long transforms fit one or two CTAs per SM only, so the CTA itself must fill the SM
+  static constexpr int NT = N <= 256 ? 256 : N == 512 ? 512 : 1024;
+  static constexpr int MINB = N <= 256 ? 3 : N == 512 ? 2 : 1;   // resident CTAs per SM the register budget must allow
   static_assert(N == 64 || N == 128 || N == 256 || N == 512 || N == 1024 || N == 2048, "unsupported N");
 };
 __host__ __device__ constexpr int xf_pow8(int e) { return e <= 0 ? 1 : 8 * xf_pow8(e - 1); }
@@ -267,8 +272,8 @@ __host__ __device__ constexpr int xf_pow8(int e) { return e <= 0 ? 1 : 8 * xf_po
 // sub-stride L = B / 8, twiddles W_B^(j q) = W_N^(8^(s-1) j q)
 template <int N, int TK, int PITCH, int s, bool FWD>
 __device__ __forceinline__ void xf_stage(float2 *col, const float2 *tw) {
-  constexpr int L = N / xf_pow8(s), B = 8 * L, M = xf_pow8(s - 1);
-  for (int u = threadIdx.x; u < N * TK / 8; u += 256) {
+  constexpr int L = N / xf_pow8(s), B = 8 * L, M = xf_pow8(s - 1), NT = XfShape<N>::NT;
+  for (int u = threadIdx.x; u < N * TK / 8; u += NT) {
     const int c = u % TK, t = u / TK, blk = t / L, j = t - blk * L;
     float2 *a = col + c * PITCH + blk * B + j;
     float2 v[8];
@@ -292,13 +297,15 @@ __device__ __forceinline__ void xf_stage(float2 *col, const float2 *tw) {
 // spec: element (x, row, kz) at x * xstride + row * nz + kz; row = 0 .. nrows-1 is ky = y0 + row.  Whole grid:
 // xstride = N * nz, nrows = N, y0 = 0; transposed slab layout [kx][nyl][nz]: xstride = nyl * nz, nrows = nyl.
 template <int KIND, int N>
-__global__ void __launch_bounds__(256) xfft_green_kernel(float2 *__restrict__ spec, const float2 *__restrict__ twiddle,
-                                                         size_t xstride, int y0, int p, float scale) {
+__global__ void __launch_bounds__(XfShape<N>::NT, XfShape<N>::MINB) xfft_green_kernel(float2 *__restrict__ spec,
+                                                                    const float2 *__restrict__ twiddle, size_t xstride,
+                                                                    int y0, int p, float scale) {
   constexpr int nz = N / 2 + 1, L1 = N / 8, PITCH = N + 1, RM = XfShape<N>::RM, S = XfShape<N>::S, TK = XfShape<N>::TK;
+  constexpr int NT = XfShape<N>::NT;
   extern __shared__ float2 xs[];          // [TK][PITCH] columns, then the twiddles [N], then the Green table [N]
   float2 *col = xs, *tw = xs + TK * PITCH, *gtab = tw + N;
   const int ky = y0 + blockIdx.y, kz0 = blockIdx.x * TK;
-  for (int n = threadIdx.x; n < N; n += 256) {
+  for (int n = threadIdx.x; n < N; n += NT) {
     tw[n] = twiddle[n];
     gtab[n] = green_axis_entry<KIND>(n, N, p);
   }
@@ -307,7 +314,7 @@ __global__ void __launch_bounds__(256) xfft_green_kernel(float2 *__restrict__ sp
   float2 *g0 = spec + (size_t)blockIdx.y * nz + kz0;          // + x * xstride + c
   __syncthreads();
   // ---- forward stage 1: x = j + L1 m from global memory, out at j + L1 q, times W_N^(j q)
-  for (int u = threadIdx.x; u < N * TK / 8; u += 256) {
+  for (int u = threadIdx.x; u < N * TK / 8; u += NT) {
     const int c = u % TK, j = u / TK;
     float2 v[8];
     if (kz0 + c < nz) {
@@ -326,7 +333,7 @@ __global__ void __launch_bounds__(256) xfft_green_kernel(float2 *__restrict__ sp
   if constexpr (S >= 3) xf_stage<N, TK, PITCH, 3, true>(col, tw);
   // ---- last forward stage, Green's function, first backward stage: blocks of RM in registers.  The block index read
   // backwards in base 8 gives the low digits of kx, the position within the block the highest one.
-  for (int u = threadIdx.x; u < N * TK / RM; u += 256) {
+  for (int u = threadIdx.x; u < N * TK / RM; u += NT) {
     const int c = u % TK, blk = u / TK;
     float2 *a = col + c * PITCH + RM * blk;
     float2 v[8];
@@ -354,7 +361,7 @@ __global__ void __launch_bounds__(256) xfft_green_kernel(float2 *__restrict__ sp
   if constexpr (S >= 3) xf_stage<N, TK, PITCH, 3, false>(col, tw);
   if constexpr (S >= 2) xf_stage<N, TK, PITCH, 2, false>(col, tw);
   // ---- backward stage 1, straight to global memory
-  for (int u = threadIdx.x; u < N * TK / 8; u += 256) {
+  for (int u = threadIdx.x; u < N * TK / 8; u += NT) {
     const int c = u % TK, j = u / TK;
     if (kz0 + c >= nz) continue;
     float2 v[8];
@@ -405,7 +412,7 @@ static int xfft_green_launch(float2 *spec, size_t xstride, int nrows, int y0, in
     return PSC_ERR_CUDA;
   }
   const dim3 grid((nz + TK - 1) / TK, nrows);
-  xfft_green_kernel<KIND, N><<<grid, 256, smem, st>>>(spec, tw, xstride, y0, p, scale);
+  xfft_green_kernel<KIND, N><<<grid, XfShape<N>::NT, smem, st>>>(spec, tw, xstride, y0, p, scale);
   count_launch();
   PSC_CHECK_LAUNCH();
   return PSC_OK;
