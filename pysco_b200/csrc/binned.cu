@@ -483,12 +483,10 @@ static_assert((SL_F3 * 4) % 16 == 0 && (SL_I * 4) % 16 == 0, "stage arrays must 
 using sl_barrier = cuda::barrier<cuda::thread_scope_block>;
 
 __device__ __forceinline__ int axis_delta(int nb, int src, int NB) {
-  // 0 / 1 / 2 for destination bin src - 1 / src / src + 1 (periodic), -1 otherwise
-  const int d = nb - src;
-  if (d == 0) return 1;
-  if (d == 1 || d == 1 - NB) return 2;
-  if (d == -1 || d == NB - 1) return 0;
-  return -1;
+  // 0 / 1 / 2 for destination bin src - 1 / src / src + 1 (periodic with period NB), -1 otherwise
+  int d = nb - src;
+  d += d > 1 ? -NB : (d < -1 ? NB : 0);
+  return (unsigned)(d + 1) <= 2u ? d + 1 : -1;
 }
 
 // One bulk copy (TMA, completion on the stage's mbarrier) of the 16-byte aligned superset of src[first, first + n);
@@ -547,12 +545,22 @@ __global__ void __launch_bounds__(256) step_sort_local_kernel(
     return (int)max((int64_t)0, min((int64_t)__ldg(&fill_src[sb]), left));
   };
   const int NBXp = NBX == NB ? NB : 0x40000000;   // period of the bin index along x (none inside a slab)
-  int b = blockIdx.x, c0 = 0, nb = 0;
-  while (b < nbins && (nb = live(b)) == 0) b += gridDim.x;
-  __syncthreads();
-  auto fetch = [&](int fb, int fc0, int fnb, int stage) {   // thread 0
+  // The rounds of this CTA are described by thread 0, one round ahead (it needs them to issue the copies): the source
+  // bin, its particles of the round, their first row and the bin's coordinates.  Everybody else reads the descriptor
+  // from shared memory after the stage's mbarrier -- no per-thread divisions, no per-thread loads of the bin table.
+  struct Round { int b, n, sbi, sbj, sbk, c0, nb; long long first; };
+  __shared__ Round s_round[2];
+  auto describe = [&](int rb, int rc0, int rnb, Round &R) {   // thread 0; rb >= nbins: no such round
+    R.b = rb; R.c0 = rc0; R.nb = rnb;
+    if (rb < nbins) {
+      R.n = min(rnb - rc0, SL_CHUNK);
+      R.first = (long long)__ldg(&base_src[rb]) + rc0;
+      R.sbk = rb % NB; R.sbj = (rb / NB) % NB; R.sbi = rb / (NB * NB);
+    }
+  };
+  auto fetch = [&](const Round &R, int stage) {   // thread 0
     float *S = sl_smem + stage * SL_STAGE;
-    const int64_t first = (int64_t)__ldg(&base_src[fb]) + fc0, n = min(fnb - fc0, SL_CHUNK);
+    const int64_t first = R.first, n = R.n;
     sl_fetch(S, pos, 3 * first, 3 * n, 3 * np, bar[stage]);
     sl_fetch(S + SL_F3, vel, 3 * first, 3 * n, 3 * np, bar[stage]);
     if (SLAB) {   // 64-bit ids in the (unused) acceleration area
@@ -562,26 +570,37 @@ __global__ void __launch_bounds__(256) step_sort_local_kernel(
       if (ids) sl_fetch(reinterpret_cast<IdT *>(S + 3 * SL_F3), ids, first, n, np, bar[stage]);
     }
   };
-  if (b < nbins && tid == 0) fetch(b, 0, nb, 0);
-  for (int it = 0; b < nbins; it++) {
+  if (tid == 0) {
+    int b = blockIdx.x, nb = 0;
+    while (b < nbins && (nb = live(b)) == 0) b += gridDim.x;
+    describe(b, 0, nb, s_round[0]);
+    if (b < nbins) fetch(s_round[0], 0);
+  }
+  __syncthreads();
+  for (int it = 0;; it++) {
     const int stage = it & 1;
-    // the round after this one
-    int b2 = b, c2 = c0 + SL_CHUNK, nb2 = nb;
-    if (c2 >= nb) {
-      c2 = 0;
-      b2 = b + gridDim.x;
-      while (b2 < nbins && (nb2 = live(b2)) == 0) b2 += gridDim.x;
-    }
-    if (b2 < nbins && tid == 0) {
-      cuda::ptx::fence_proxy_async(cuda::ptx::space_shared);   // the other stage was last written as an output area
-      fetch(b2, c2, nb2, stage ^ 1);
+    if (s_round[stage].b >= nbins) break;
+    if (tid == 0) {
+      // the round after this one
+      const Round &R = s_round[stage];
+      int b2 = R.b, c2 = R.c0 + SL_CHUNK, nb2 = R.nb;
+      if (c2 >= nb2) {
+        c2 = 0;
+        b2 += gridDim.x;
+        while (b2 < nbins && (nb2 = live(b2)) == 0) b2 += gridDim.x;
+      }
+      describe(b2, c2, nb2, s_round[stage ^ 1]);
+      if (b2 < nbins) {
+        cuda::ptx::fence_proxy_async(cuda::ptx::space_shared);   // the other stage was last written as an output area
+        fetch(s_round[stage ^ 1], stage ^ 1);
+      }
     }
     bar[stage].arrive_and_wait();
     float *S = sl_smem + stage * SL_STAGE;
-    const int64_t first = (int64_t)__ldg(&base_src[b]) + c0;
-    const int n = min(nb - c0, SL_CHUNK);
+    const int64_t first = s_round[stage].first;
+    const int n = s_round[stage].n;
     const int off3 = (int)((3 * first) & 3), off1 = (int)(first & (16 / sizeof(IdT) - 1));
-    const int sbk = b % NB, sbj = (b / NB) % NB, sbi = b / (NB * NB);
+    const int sbk = s_round[stage].sbk, sbj = s_round[stage].sbj, sbi = s_round[stage].sbi;
     float f[SL_R][3], v[SL_R][3];
     IdT id[SL_R];
     int key[SL_R], dbin[SL_R], rank[SL_R], dst[SL_R];
@@ -680,16 +699,24 @@ __global__ void __launch_bounds__(256) step_sort_local_kernel(
       }
     }
     __syncthreads();
-    const int nnear = s_near;
-    for (int t = tid; t < 3 * nnear; t += 256) {
-      const int64_t g = (int64_t)3 * s_dst[od[t / 3]] + t;    // consecutive t: consecutive floats of a run
-      pos_out[g] = opos[t];
-      vel_out[g] = ovel[t];
+    const int nnear = s_near, nstay = hist[nself];     // the sorted round: nstay stayers, then the leavers by bin
+    {
+      const int64_t g0 = (int64_t)3 * s_dst[13];
+      for (int t = tid; t < 3 * nstay; t += 256) {           // the stayers: one contiguous run of floats
+        pos_out[g0 + t] = opos[t];
+        vel_out[g0 + t] = ovel[t];
+      }
+      for (int t = 3 * nstay + tid; t < 3 * nnear; t += 256) {
+        const int64_t g = (int64_t)3 * s_dst[od[t / 3]] + t;    // consecutive t: consecutive floats of a run
+        pos_out[g] = opos[t];
+        vel_out[g] = ovel[t];
+      }
+      IdT *io = ids_out + s_dst[13];
+      for (int t = tid; t < nstay; t += 256) io[t] = oid[t];
+      for (int t = nstay + tid; t < nnear; t += 256) ids_out[s_dst[od[t]] + t] = oid[t];
     }
-    for (int t = tid; t < nnear; t += 256) ids_out[s_dst[od[t]] + t] = oid[t];
     for (int t = tid; t < 32 * per; t += 256) hist[t] = 0;   // all of them: the scan wrote the unused tail too
     __syncthreads();   // output area, hist and s_dst are free again
-    b = b2; c0 = c2; nb = nb2;
   }
 }
 
