@@ -533,6 +533,11 @@ def run_gpu_arm(args):
     for _ in range(preroll):
         step()
 
+    from pysco_b200 import mesh as _mesh
+
+    def count_hits():   # steps whose sort used the bin counts predicted by the previous interpolation kernel
+        return sum(getattr(sb, "counts_skipped", 0) for sb in _mesh._step_sorted.values())
+    hits0 = count_hits()
     _lib.enable_timing(True)
     launches0 = _lib.launch_count()
     torch.cuda.synchronize()
@@ -642,6 +647,9 @@ def run_gpu_arm(args):
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
         "clocks": clocks, "kernels": kern,
         "ms_per_step_outside_calls": outside_ms,
+        "predicted_bin_counts_used": {"steps": int(count_hits() - hits0), "of": K,
+                                      "what": "steps whose sort skipped its count pass: the previous interpolation "
+                                              "kernel had counted the bins under the time step that was then taken"},
         "reorder": {"ms": t_reorder_ms, "in_timed_steps": n_reorders, "amortised_over": N_REORDER,
                     "calls_ms": reorder_calls},
         "extra": extra,

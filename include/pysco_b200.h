@@ -133,14 +133,19 @@ size_t psc_sorted_workspace_bytes(int64_t np, int N);
  * particles in shared memory by (destination bin, 2^3-cell micro-block in Morton order) and writes contiguous runs;
  * result in table 1 - src_table.  `table` of the two consumers = the table the sort wrote. */
 int psc_step_sort(const float *pos, const float *vel, const float *acc, const int *ids, int64_t np, float half_dt,
-                  double dt, int dt_is_f64, int N, int src_table, void *scratch, size_t scratch_bytes, float *pos_out,
-                  float *vel_out, int *ids_out, void *stream);
+                  double dt, int dt_is_f64, int N, int src_table, int counts_ready, void *scratch,
+                  size_t scratch_bytes, float *pos_out, float *vel_out, int *ids_out, void *stream);
 int psc_deposit_sorted(const float *pos_sorted, const void *scratch, size_t scratch_bytes, int table, int64_t np, int N,
                        int scheme, float scale, float f1, float f2, float *rho, void *stream);
+/* predict = 1: the kernel also applies the NEXT step's first half (next_half_dt, next_dt, next_dt_is_f64: the values
+ * the next psc_step_sort will be called with -- known in advance when the scale-factor criterion of
+ * integration.py:329-358 binds) to every particle in registers and counts its destination bin, into the scratch's count
+ * table; that psc_step_sort is then called with counts_ready = 1 and skips its count pass.  If the host ends up with
+ * another time step it passes counts_ready = 0 and the sort counts again. */
 int psc_interp_kick_phi_sorted(const float *phi, const float *u, float f, int fr_n, int order, const float *pos_sorted,
                                const void *scratch, size_t scratch_bytes, int table, float *vel_sorted,
                                float *acc_sorted, int64_t np, int N, int scheme, float half_dt, float *maxout,
-                               void *stream);
+                               int predict, float next_half_dt, double next_dt, int next_dt_is_f64, void *stream);
 /* utils.reorder_particles (utils.py:1019-1075) for bin-ordered arrays: no particle moves; ids_out[n] = rank of the
  * particle in row n in Morton-key order, i.e. its row in the reference after the reorder.  Per-bin block radix sort in
  * shared memory + a scan of the bin counts in Z order.  N: power of two.  *too_big (device int) = 1 when a bin holds

@@ -40,9 +40,10 @@ SIGNATURES = {
     "psc_interp_kick_phi_binned": [_vp, _vp, _f, _i, _i, _vp, _sz, _vp, _vp, _i64, _i, _i, _f, _vp, _vp],
     "psc_sorted_workspace_bytes": [_i64, _i],
     "psc_morton_ids_sorted": [_vp, _vp, _sz, _i, _i64, _i, _vp, _vp, _vp],
-    "psc_step_sort": [_vp, _vp, _vp, _vp, _i64, _f, _d, _i, _i, _i, _vp, _sz, _vp, _vp, _vp, _vp],
+    "psc_step_sort": [_vp, _vp, _vp, _vp, _i64, _f, _d, _i, _i, _i, _i, _vp, _sz, _vp, _vp, _vp, _vp],
     "psc_deposit_sorted": [_vp, _vp, _sz, _i, _i64, _i, _i, _f, _f, _f, _vp, _vp],
-    "psc_interp_kick_phi_sorted": [_vp, _vp, _f, _i, _i, _vp, _vp, _sz, _i, _vp, _vp, _i64, _i, _i, _f, _vp, _vp],
+    "psc_interp_kick_phi_sorted": [_vp, _vp, _f, _i, _i, _vp, _vp, _sz, _i, _vp, _vp, _i64, _i, _i, _f, _vp, _i, _f, _d,
+                                   _i, _vp],
     "psc_scatter3_by_id": [_vp, _vp, _vp, _i64, _vp],
     "psc_sorted_workspace_bytes_slab": [_i64, _i, _i],
     "psc_sort_by_bin_slab": [_vp, _vp, _vp, _i64, _i, _i, _i, _i, _i64, _vp, _sz, _vp, _vp, _vp, _vp],

@@ -182,9 +182,7 @@ __global__ void __launch_bounds__(256) kick_drift_wrap_count_kernel(float *__res
       }
 #pragma unroll
       for (int c = 0; c < 12; c++) {
-        v[c] += mh * a[c];
-        f[c] = F64 ? (float)((double)f[c] + dt * (double)v[c]) : f[c] + dtf * v[c];
-        f[c] = wrap01(f[c]);
+        kick_drift_wrap1<F64>(f[c], v[c], a[c], mh, dtf, dt);
       }
 #pragma unroll
       for (int c = 0; c < 3; c++) {
@@ -250,10 +248,8 @@ __global__ void __launch_bounds__(256) kick_drift_wrap_count_kernel(float *__res
     float x[3];
 #pragma unroll
     for (int c = 0; c < 3; c++) {
-      float v = vel[3 * n + c] + mh * acc[3 * n + c];
-      float p = pos[3 * n + c];
-      p = F64 ? (float)((double)p + dt * (double)v) : p + dtf * v;
-      p = wrap01(p);
+      float v = vel[3 * n + c], p = pos[3 * n + c];
+      kick_drift_wrap1<F64>(p, v, acc[3 * n + c], mh, dtf, dt);
       vel[3 * n + c] = v;
       pos[3 * n + c] = p;
       x[c] = p;
@@ -376,9 +372,7 @@ __global__ void __launch_bounds__(256) step_sort_kernel(const float *__restrict_
       }
 #pragma unroll
       for (int c = 0; c < 12; c++) {
-        v[c] += mh * a[c];
-        f[c] = F64 ? (float)((double)f[c] + dt * (double)v[c]) : f[c] + dtf * v[c];
-        f[c] = wrap01(f[c]);
+        kick_drift_wrap1<F64>(f[c], v[c], a[c], mh, dtf, dt);
       }
 #pragma unroll
       for (int r = 0; r < 4; r++) b[r] = bin_of(f[3 * r], f[3 * r + 1], f[3 * r + 2], Nf, NB, 0, NB);
@@ -442,10 +436,9 @@ __global__ void __launch_bounds__(256) step_sort_kernel(const float *__restrict_
     float x[3], w[3];
 #pragma unroll
     for (int c = 0; c < 3; c++) {
-      float vv = vel[3 * n + c] + mh * acc[3 * n + c];
-      float p = pos[3 * n + c];
-      p = F64 ? (float)((double)p + dt * (double)vv) : p + dtf * vv;
-      x[c] = wrap01(p);
+      float vv = vel[3 * n + c], p = pos[3 * n + c];
+      kick_drift_wrap1<F64>(p, vv, acc[3 * n + c], mh, dtf, dt);
+      x[c] = p;
       w[c] = vv;
     }
     const int bb = bin_of(x[0], x[1], x[2], Nf, NB, 0, NB);
@@ -616,10 +609,9 @@ __global__ void __launch_bounds__(256) step_sort_local_kernel(
             f[r][c] = S[o];
             v[r][c] = S[SL_F3 + o];
           } else {
-            const float vv = S[SL_F3 + o] + mh * S[2 * SL_F3 + o];
-            float p = S[o];
-            p = F64 ? (float)((double)p + dt * (double)vv) : p + dtf * vv;
-            f[r][c] = wrap01(p);
+            float vv = S[SL_F3 + o], p = S[o];
+            kick_drift_wrap1<F64>(p, vv, S[2 * SL_F3 + o], mh, dtf, dt);
+            f[r][c] = p;
             v[r][c] = vv;
           }
         }
@@ -1083,6 +1075,19 @@ __global__ void __launch_bounds__(BI_THREADS) interp_kick4_binned_kernel(
 // the gradient kernel and the force grid (16 B/cell written + re-read) from the step.
 template <int ORDER> struct Reach { static constexpr int H = ORDER == 7 ? 3 : ORDER == 5 ? 2 : 1; };
 
+// Speculative bin count of the NEXT step's sort (psc_step_sort pass 1) inside the interpolation kernel: the particle's
+// position, its velocity after the second half-kick and its new acceleration are all in registers here, so with the
+// next time step in hand -- it is known in advance whenever the scale-factor criterion binds (integration.py:329-358
+// depends on a(t) only) -- the kernel applies the next kick + drift + wrap (same bits as every other kernel:
+// kick_drift_wrap1) and counts the destination bins.  The host uses the counts only if the time step it then computes
+// is the predicted one; otherwise the sort counts again.  counts == nullptr: off.
+struct BinPredict {
+  int *counts;
+  float mh, dtf;
+  double dt;
+  int f64;
+};
+
 constexpr int BP_THREADS = 256;  // gradient + interpolation kernel.  Resident CTAs per SM (register bound), 512^3, bin-ordered
                                  // arrays: 5 (48 registers) 4.44 ms, 6 (40 registers) 4.31 ms, 7 (32 registers) 4.52 ms
 
@@ -1097,7 +1102,8 @@ __global__ void __launch_bounds__(BP_THREADS, 6) interp_kick_phi_binned_kernel(
     const float *__restrict__ phi, const float *__restrict__ u, float f, int fr_n,
     const void *__restrict__ brec, const int *__restrict__ base, const int *__restrict__ fill,
     float *__restrict__ vel, float *__restrict__ accel, int N, int NB, int x0, int xoff, int nxa, float half_dt,
-    float *__restrict__ maxout, int nbins, const int *__restrict__ heavy_count, const int2 *__restrict__ heavy) {
+    float *__restrict__ maxout, int nbins, const int *__restrict__ heavy_count, const int2 *__restrict__ heavy,
+    BinPredict pred) {
   constexpr int H = Reach<ORDER>::H;
   constexpr int PT = BT + 2 * H;  // potential tile edge
   constexpr int PK = 16;          // k pitch of the potential tile: the aligned 16-float window
@@ -1180,37 +1186,58 @@ __global__ void __launch_bounds__(BP_THREADS, 6) interp_kick_phi_binned_kernel(
   const float Nf = (float)N;
   const float mh = -half_dt;
   unsigned ma = 0u, mv = 0u;   // maxima of |.| as bit patterns: orders like the floats and lets a NaN win
-  for (int n = beg + threadIdx.x; n < end; n += BP_THREADS) {
-    float px, py, pz;
-    int row;
-    load_particle<SORTED>(brec, n, px, py, pz, row);
-    int i, j, k;
-    float wx[3], wy[3], wz[3];
-    axis_weights<SCHEME>(px * Nf, N, i, wx[0], wx[1], wx[2]);
-    axis_weights<SCHEME>(py * Nf, N, j, wy[0], wy[1], wy[2]);
-    axis_weights<SCHEME>(pz * Nf, N, k, wz[0], wz[1], wz[2]);
-    const float4 *c0 = tile + (min(max(i - oi, 1), BB) - 1) * TP0 + (min(max(j - oj, 1), BB) - 1) * TP1 + (min(max(k - ok, 1), BB) - 1);
-    float ax = 0.0f, ay = 0.0f, az = 0.0f;
+  const int lane = threadIdx.x & 31;
+  for (int n0 = beg + (threadIdx.x & ~31); n0 < end; n0 += BP_THREADS) {   // warp-uniform trip count
+    const int n = n0 + lane;
+    int db = -1 - lane;      // destination bin of the particle in the next step (prediction), none
+    if (n < end) {
+      float px, py, pz;
+      int row;
+      load_particle<SORTED>(brec, n, px, py, pz, row);
+      int i, j, k;
+      float wx[3], wy[3], wz[3];
+      axis_weights<SCHEME>(px * Nf, N, i, wx[0], wx[1], wx[2]);
+      axis_weights<SCHEME>(py * Nf, N, j, wy[0], wy[1], wy[2]);
+      axis_weights<SCHEME>(pz * Nf, N, k, wz[0], wz[1], wz[2]);
+      const float4 *c0 = tile + (min(max(i - oi, 1), BB) - 1) * TP0 + (min(max(j - oj, 1), BB) - 1) * TP1 + (min(max(k - ok, 1), BB) - 1);
+      float ax = 0.0f, ay = 0.0f, az = 0.0f;
 #pragma unroll
-    for (int a = 0; a < 3; a++)
+      for (int a = 0; a < 3; a++)
 #pragma unroll
-      for (int e = 0; e < 3; e++) {
-        const float wxy = wx[a] * wy[e];
+        for (int e = 0; e < 3; e++) {
+          const float wxy = wx[a] * wy[e];
 #pragma unroll
-        for (int g = 0; g < 3; g++) {
-          const float w = wxy * wz[g];
-          const float4 ff = c0[a * TP0 + e * TP1 + g];
-          ax += w * ff.x; ay += w * ff.y; az += w * ff.z;
+          for (int g = 0; g < 3; g++) {
+            const float w = wxy * wz[g];
+            const float4 ff = c0[a * TP0 + e * TP1 + g];
+            ax += w * ff.x; ay += w * ff.y; az += w * ff.z;
+          }
+        }
+      float *ap = accel + 3 * (size_t)row;
+      ap[0] = ax; ap[1] = ay; ap[2] = az;
+      ma = max(ma, max(__float_as_uint(fabsf(ax)), max(__float_as_uint(fabsf(ay)), __float_as_uint(fabsf(az)))));
+      if (vel) {
+        float *vp = vel + 3 * (size_t)row;
+        float v0 = vp[0] + mh * ax, v1 = vp[1] + mh * ay, v2 = vp[2] + mh * az;
+        vp[0] = v0; vp[1] = v1; vp[2] = v2;
+        mv = max(mv, max(__float_as_uint(fabsf(v0)), max(__float_as_uint(fabsf(v1)), __float_as_uint(fabsf(v2)))));
+        if (SORTED && pred.counts) {
+          if (pred.f64) {
+            kick_drift_wrap1<true>(px, v0, ax, pred.mh, pred.dtf, pred.dt);
+            kick_drift_wrap1<true>(py, v1, ay, pred.mh, pred.dtf, pred.dt);
+            kick_drift_wrap1<true>(pz, v2, az, pred.mh, pred.dtf, pred.dt);
+          } else {
+            kick_drift_wrap1<false>(px, v0, ax, pred.mh, pred.dtf, pred.dt);
+            kick_drift_wrap1<false>(py, v1, ay, pred.mh, pred.dtf, pred.dt);
+            kick_drift_wrap1<false>(pz, v2, az, pred.mh, pred.dtf, pred.dt);
+          }
+          db = bin_of(px, py, pz, Nf, NB, 0, NB);
         }
       }
-    float *ap = accel + 3 * (size_t)row;
-    ap[0] = ax; ap[1] = ay; ap[2] = az;
-    ma = max(ma, max(__float_as_uint(fabsf(ax)), max(__float_as_uint(fabsf(ay)), __float_as_uint(fabsf(az)))));
-    if (vel) {
-      float *vp = vel + 3 * (size_t)row;
-      const float v0 = vp[0] + mh * ax, v1 = vp[1] + mh * ay, v2 = vp[2] + mh * az;
-      vp[0] = v0; vp[1] = v1; vp[2] = v2;
-      mv = max(mv, max(__float_as_uint(fabsf(v0)), max(__float_as_uint(fabsf(v1)), __float_as_uint(fabsf(v2)))));
+    }
+    if (SORTED && pred.counts) {
+      const unsigned peers = __match_any_sync(0xffffffffu, db);
+      if (db >= 0 && (__ffs(peers) - 1) == lane) atomicAdd(&pred.counts[db], __popc(peers));
     }
   }
   ma = __reduce_max_sync(0xffffffffu, ma);
@@ -1497,7 +1524,7 @@ int psc_interp_kick4_binned(const float *force4, const void *scratch, size_t scr
 static int interp_kick_phi_impl(const float *phi, const float *u, float f, int fr_n, int order, int x0, int nxl,
                                 int ghost, const void *scratch, size_t scratch_bytes, float *vel, float *acc,
                                 int64_t np, int N, int scheme, float half_dt, float *maxout, void *stream,
-                                const float *sorted_pos = nullptr, int table = 0) {
+                                const float *sorted_pos = nullptr, int table = 0, const BinPredict *predict = nullptr) {
   if (np == 0) return PSC_OK;
   PSC_CHECK_ARG((((uintptr_t)phi | (uintptr_t)u) & 15) == 0, "phi and u must be 16-byte aligned");
   BinLayout L;
@@ -1509,18 +1536,24 @@ static int interp_kick_phi_impl(const float *phi, const float *u, float f, int f
   cudaStream_t st = as_stream(stream);
   const int grid = (int)L.nbins + L.heavy_cap;   // the CTAs of unused heavy-part slots exit at once
   const int nxa = nxl + 2 * ghost;
+  BinPredict pr = {nullptr, 0.0f, 0.0f, 0.0, 0};
+  if (predict && sorted_pos && vel) {
+    pr = *predict;
+    pr.counts = L.counts;
+    PSC_CUDA(cudaMemsetAsync(L.counts, 0, sizeof(int) * (L.nbins + 1), st));
+  }
 #define PSC_IKP(S, O)                                                                                               \
   do {                                                                                                              \
     if (sorted_pos)                                                                                                 \
       interp_kick_phi_binned_kernel<S, O, true><<<grid, BP_THREADS, 0, st>>>(phi, u, f, fr_n, sorted_pos, L.base,   \
                                                                              L.fill, vel, acc, N, L.NB, x0, ghost,  \
                                                                              nxa, half_dt, maxout, (int)L.nbins,    \
-                                                                             L.heavy_count, L.heavy);               \
+                                                                             L.heavy_count, L.heavy, pr);           \
     else                                                                                                            \
       interp_kick_phi_binned_kernel<S, O, false><<<grid, BP_THREADS, 0, st>>>(phi, u, f, fr_n, L.rec, L.base,       \
                                                                               L.fill, vel, acc, N, L.NB, x0, ghost, \
                                                                               nxa, half_dt, maxout, (int)L.nbins,   \
-                                                                              L.heavy_count, L.heavy);              \
+                                                                              L.heavy_count, L.heavy, pr);          \
   } while (0)
 #define PSC_IKP_O(S)               \
   if (order == 2) PSC_IKP(S, 2);    \
@@ -1576,8 +1609,8 @@ size_t psc_sorted_workspace_bytes(int64_t np, int N) {
  * bin-ordered output of a previous call described by that table: one CTA per source bin sorts its particles in shared
  * memory (step_sort_local_kernel) and the result is table 1 - src_table. */
 int psc_step_sort(const float *pos, const float *vel, const float *acc, const int *ids, int64_t np, float half_dt,
-                  double dt, int dt_is_f64, int N, int src_table, void *scratch, size_t scratch_bytes, float *pos_out,
-                  float *vel_out, int *ids_out, void *stream) {
+                  double dt, int dt_is_f64, int N, int src_table, int counts_ready, void *scratch,
+                  size_t scratch_bytes, float *pos_out, float *vel_out, int *ids_out, void *stream) {
   PSC_CHECK_ARG(np >= 0 && np < ((int64_t)1 << 31), "np out of range");
   PSC_CHECK_ARG(slab_ok(N, 0, N), "N must be a multiple of 8");
   PSC_CHECK_ARG(src_table >= -1 && src_table <= 1, "src_table must be -1, 0 or 1");
@@ -1590,7 +1623,9 @@ int psc_step_sort(const float *pos, const float *vel, const float *acc, const in
   const int *base_src = src_table == 1 ? L.base2 : L.base, *fill_src = src_table == 1 ? L.fill2 : L.fill;
   use_table(L, src_table < 0 ? 0 : 1 - src_table);     // L.base / L.fill: the table being written
   cudaStream_t st = as_stream(stream);
-  PSC_CUDA(cudaMemsetAsync(L.counts, 0, sizeof(int) * (L.nbins + 1), st));
+  // counts_ready: the previous psc_interp_kick_phi_sorted(predict = 1) already counted the destination bins of exactly
+  // this (half_dt, dt, dt_is_f64) on exactly these arrays
+  if (!counts_ready) PSC_CUDA(cudaMemsetAsync(L.counts, 0, sizeof(int) * (L.nbins + 1), st));
   PSC_CUDA(cudaMemsetAsync(L.fill, 0, sizeof(int) * (L.nbins + 1), st));
   PSC_CUDA(cudaMemsetAsync(L.heavy_count, 0, sizeof(int), st));
   if (np > 0) {
@@ -1600,7 +1635,7 @@ int psc_step_sort(const float *pos, const float *vel, const float *acc, const in
                   "pointers must be 16-byte aligned");
   }
   const int g = grid_for((np + 3) / 4, 256, 8);
-  if (np > 0) {
+  if (np > 0 && !counts_ready) {
     // pass 1, either input order: destination-bin counts, one atomic per distinct bin of a warp
     if (dt_is_f64)
       step_sort_kernel<true, 1><<<g, 256, 0, st>>>(pos, vel, acc, ids, np, half_dt, dt, N, L.NB, L.counts, nullptr,
@@ -1666,15 +1701,16 @@ int psc_deposit_sorted(const float *pos_sorted, const void *scratch, size_t scra
 int psc_interp_kick_phi_sorted(const float *phi, const float *u, float f, int fr_n, int order, const float *pos_sorted,
                                const void *scratch, size_t scratch_bytes, int table, float *vel_sorted,
                                float *acc_sorted, int64_t np, int N, int scheme, float half_dt, float *maxout,
-                               void *stream) {
+                               int predict, float next_half_dt, double next_dt, int next_dt_is_f64, void *stream) {
   PSC_CHECK_ARG(table == 0 || table == 1, "table must be 0 or 1");
+  BinPredict pr = {nullptr, -next_half_dt, (float)next_dt, next_dt, next_dt_is_f64 != 0};
   PSC_CHECK_ARG(scheme == PSC_CIC || scheme == PSC_TSC, "mass scheme must be CIC or TSC");
   PSC_CHECK_ARG(order == 2 || order == 3 || order == 5 || order == 7, "gradient order must be 2, 3, 5 or 7");
   PSC_CHECK_ARG(fr_n >= 0 && fr_n <= 2, "fR_n must be 1 or 2");
   PSC_CHECK_ARG(N >= 2 * BB && (N % BB) == 0, "N must be a multiple of 8 and >= 16");
   PSC_CHECK_ARG(phi && scratch && acc_sorted && maxout && (u || fr_n == 0) && (pos_sorted || np == 0), "null pointer");
   return interp_kick_phi_impl(phi, u, f, fr_n, order, 0, N, 0, scratch, scratch_bytes, vel_sorted, acc_sorted, np, N,
-                              scheme, half_dt, maxout, stream, pos_sorted, table);
+                              scheme, half_dt, maxout, stream, pos_sorted, table, predict ? &pr : nullptr);
 }
 
 /* ids_out[n] = rank of particle n (row n of the bin-ordered pos_sorted) in Morton-key order: after the call

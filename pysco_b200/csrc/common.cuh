@@ -81,6 +81,17 @@ __device__ __forceinline__ float wrap01(float t) {
   return t;
 }
 
+// integration.py:250-258 for one component: v -= half_dt a (mh = -half_dt); x += dt v (in float32, or in float64 when the
+// time step was clamped to a snapshot time: F64); periodic wrap.  Explicit fused multiply-adds: every kernel that
+// applies -- or predicts -- this update must produce the SAME bits, because bins are counted by one kernel and filled
+// by another.
+template <bool F64>
+__device__ __forceinline__ void kick_drift_wrap1(float &x, float &v, float a, float mh, float dtf, double dt) {
+  v = __fmaf_rn(mh, a, v);
+  x = F64 ? (float)__fma_rn(dt, (double)v, (double)x) : __fmaf_rn(dtf, v, x);
+  x = wrap01(x);
+}
+
 // TSC cell + the three 1-D weights of one axis (mesh.py:2502-2522): xp = x*N (float32)
 __device__ __forceinline__ void tsc_axis(float xp, int &c, float &wm, float &w0, float &wp) {
   c = (int)xp;  // trunc == floor for xp >= 0 (reference: np.int16(xp))

@@ -115,10 +115,7 @@ __global__ void __launch_bounds__(256) kick_drift_wrap_kernel(float *__restrict_
   float4 *p4 = reinterpret_cast<float4 *>(pos);
   float4 *v4 = reinterpret_cast<float4 *>(vel);
   const float4 *a4 = reinterpret_cast<const float4 *>(acc);
-#define PSC_KDW(pc, vc, ac)                                       \
-  vc += mh * ac;                                                  \
-  pc = F64 ? (float)((double)pc + dt * (double)vc) : pc + dtf * vc; \
-  pc = wrap01(pc);
+#define PSC_KDW(pc, vc, ac) kick_drift_wrap1<F64>(pc, vc, ac, mh, dtf, dt);
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4;
        i += (int64_t)gridDim.x * blockDim.x) {
     float4 p = p4[i], v = v4[i], a = __ldg(&a4[i]);
@@ -151,10 +148,7 @@ __global__ void __launch_bounds__(256) kick_drift_wrap_slab_kernel(float *__rest
   float4 *p4 = reinterpret_cast<float4 *>(pos);
   float4 *v4 = reinterpret_cast<float4 *>(vel);
   const float4 *a4 = reinterpret_cast<const float4 *>(acc);
-#define PSC_KDW(pc, vc, ac)                                       \
-  vc += mh * ac;                                                  \
-  pc = F64 ? (float)((double)pc + dt * (double)vc) : pc + dtf * vc; \
-  pc = wrap01(pc);
+#define PSC_KDW(pc, vc, ac) kick_drift_wrap1<F64>(pc, vc, ac, mh, dtf, dt);
 #define PSC_LEAVER(pc, flat)                                                        \
   if ((flat) % 3 == 0) {                                                            \
     const int d = min(max((int)(pc * Nf) / nxl, 0), P - 1);                         \

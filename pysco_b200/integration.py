@@ -7,6 +7,7 @@ B200 fusions (same arithmetic): kick+drift+wrap is one kernel (60 B/particle); t
 and the max|a|, max|v| reductions of the NEXT step's dt are folded into the force interpolation.
 """
 import logging
+import os
 import weakref
 
 import numpy as np
@@ -229,6 +230,12 @@ def leapfrog(position, velocity, acceleration, potential, additional_field, dt, 
         sb = mesh.step_sorted(pos.shape[0], N)
         pos, vel, ids = mesh.step_sort(pos, vel, acc, utils.particle_ids(pos), half_dt, dt, dt_is_f64, sb)
         _advance_clock(dt, tables, param)
+        if not os.environ.get("PSC_NO_PREDICTED_COUNT"):
+            # The next time step is min(free fall, Courant, scale-factor variation) (integrate, above); the last of the
+            # three depends on a(t) only and is the one that binds through most of a cosmological run.  Let the
+            # interpolation kernel count the next sort's bins under that guess; step_sort checks the guess.
+            dt_guess = dt_weak_variation(tables[1], param)
+            sb.predict_next = (np.float32(0.5 * dt_guess), dt_guess, 0 if isinstance(dt_guess, np.float32) else 1)
         acc, pot, add, maxima = solver._pm_device(pos, param, pot, add, tables, kick=(vel, half_dt), counted=sb)
         utils.set_particle_ids((pos, vel, acc), ids)
         mx = maxima.cpu().numpy()

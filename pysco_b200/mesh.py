@@ -38,6 +38,10 @@ class SortedBins:
         # the scratch holds two tables: `table` describes the arrays the last step_sort returned (`owner`, a weak
         # reference to its position tensor); the next sort reads that table and writes the other one
         self.table, self.owner = 0, None
+        # speculative count pass (csrc/binned.cu BinPredict): predict_next = (half_dt, dt, dt_is_f64) asks the next
+        # interp_kick_phi to count the bins of the next step under that time step; predicted = what it counted for
+        self.predict_next = None
+        self.predicted = None
 
     def describes(self, pos):
         return self.owner is not None and self.owner() is pos
@@ -78,10 +82,15 @@ def step_sort(pos, vel, acc, ids, half_dt, dt, dt_is_f64, sb):
     pos2, vel2 = torch.empty_like(pos), torch.empty_like(vel)
     ids2 = _lib.empty((n,), torch.int32)
     src = sb.table if (sb.describes(pos) and not os.environ.get("PSC_NO_LOCAL_SORT")) else -1
+    # the count pass was done by the previous interpolation kernel if it predicted exactly this time step for exactly
+    # these arrays (same bits: float(half_dt), float(dt) and the float64 flag are what both calls hand to the library)
+    ready = int(src >= 0 and sb.predicted == (float(half_dt), float(dt), int(dt_is_f64)))
+    sb.predicted = None
     _lib.check(_lib.load().psc_step_sort(_lib.ptr(pos), _lib.ptr(vel), _lib.ptr(acc), _lib.ptr(ids), n, float(half_dt),
-                                         float(dt), int(dt_is_f64), sb.N, src, _lib.ptr(sb.scratch),
+                                         float(dt), int(dt_is_f64), sb.N, src, ready, _lib.ptr(sb.scratch),
                                          sb.scratch.numel(), _lib.ptr(pos2), _lib.ptr(vel2), _lib.ptr(ids2),
                                          _lib.stream()))
+    sb.counts_skipped = getattr(sb, "counts_skipped", 0) + ready
     sb.table = 0 if src < 0 else 1 - src
     sb.owner = weakref.ref(pos2)
     return pos2, vel2, ids2
@@ -246,10 +255,15 @@ def interp_kick_phi(potential, u, f, fr_n, order, position, velocity, scheme, ha
     acc = _lib.empty((n, 3))
     mx = _lib.zeros((2,))
     if isinstance(binned, SortedBins):
+        nxt, binned.predict_next, binned.predicted = binned.predict_next, None, None
+        predict = nxt is not None and vel is not None and binned.describes(pos)
+        h2, d2, f2 = nxt if predict else (0.0, 0.0, 0)
         _lib.check(_lib.load().psc_interp_kick_phi_sorted(
             _lib.ptr(phi), _lib.ptr(tu), float(np.float32(f)), fr_n, order, _lib.ptr(pos), _lib.ptr(binned.scratch),
             binned.scratch.numel(), binned.table, _lib.ptr(vel), _lib.ptr(acc), n, phi.shape[0], scheme,
-            float(half_dt), _lib.ptr(mx), _lib.stream()))
+            float(half_dt), _lib.ptr(mx), int(predict), float(h2), float(d2), int(f2), _lib.stream()))
+        if predict:
+            binned.predicted = (float(h2), float(d2), int(f2))
     else:
         _lib.check(_lib.load().psc_interp_kick_phi_binned(
             _lib.ptr(phi), _lib.ptr(tu), float(np.float32(f)), fr_n, order, _lib.ptr(binned.scratch),

@@ -163,6 +163,7 @@ def _morton_relabel(position, velocity, acceleration):
     flag = _lib.empty((1,), torch.int32)
     _lib.check(_lib.load().psc_morton_ids_sorted(_lib.ptr(position), _lib.ptr(sb.scratch), sb.scratch.numel(), sb.table,
                                                  n, sb.N, _lib.ptr(ids), _lib.ptr(flag), _lib.stream()))
+    sb.predicted = None       # the relabelling used the count table as scratch
     if int(flag.item()):      # a bin beyond the in-kernel sort's capacity (2048 particles): global sort
         return None
     group = [t for t in (position, velocity, acceleration) if t is not None]

@@ -395,3 +395,48 @@ def test_morton_relabel_of_bin_ordered_arrays(psc):
         # distinct keys: the Morton-sorted arrays are unique
         if len(np.unique(keys)) == n:
             assert np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("dt2", [np.float32(3.0), 2.7182818284])
+def test_predicted_bin_count_equals_the_count_pass(psc, orc, dt2):
+    """psc_interp_kick_phi_sorted(predict = 1) counts, in the interpolation kernel, the bins the NEXT psc_step_sort will
+    fill (speculative count pass): the count table must equal the bins of psc_kick_drift_wrap's new positions, and the
+    sort that skips its count pass must produce exactly what the counting sort does (float32 and float64 time steps)"""
+    import torch
+    N, n = 128, 500009
+    pos, vel = cases.particles(N, n, seed=41), cases.velocities(n, seed=42, scale=5e-3)
+    lib, L = psc._lib, psc._lib.load()
+    sb = psc.mesh.step_sorted(n, N)
+    zero = torch.zeros((n, 3), device="cuda")
+    sp, sv, sid = psc.mesh.step_sort(_cuda(pos), _cuda(vel), zero, None, np.float32(0), np.float32(0), 0, sb)
+    phi = _cuda(cases.scalar_grid(N, seed=43, smooth=True) * np.float32(2e-3))
+    half2 = np.float32(0.5 * dt2)
+    f64 = 0 if isinstance(dt2, np.float32) else 1
+    sb.predict_next = (half2, dt2, f64)
+    acc, _ = psc.mesh.interp_kick_phi(phi, None, 0.0, 0, 5, sp, sv, 2, np.float32(0.01), sb)
+    assert sb.predicted == (float(half2), float(dt2), f64)
+    # reference: the stand-alone kick + drift + wrap on copies
+    rp, rv = sp.clone(), sv.clone()
+    lib.check(L.psc_kick_drift_wrap(lib.ptr(rp), lib.ptr(rv), lib.ptr(acc), n, float(half2), float(dt2), f64, lib.stream()))
+    torch.cuda.synchronize()
+    nbins = (N // 8) ** 3
+    want = np.bincount(_bin_key(rp.cpu().numpy(), N), minlength=nbins)
+    got = sb.scratch.cpu().numpy()[: 4 * nbins].view(np.int32)          # the count table opens the scratch
+    assert np.array_equal(got, want)
+    assert np.any(want != np.bincount(_bin_key(sp.cpu().numpy(), N), minlength=nbins)), "particles must change bins"
+    skipped = getattr(sb, "counts_skipped", 0)
+    p2, v2, i2 = psc.mesh.step_sort(sp, sv, acc, sid, half2, dt2, f64, sb)
+    assert sb.counts_skipped == skipped + 1
+    torch.cuda.synchronize()
+    order = np.argsort(sid.cpu().numpy())[i2.cpu().numpy()]            # input row of every output row
+    assert np.array_equal(p2.cpu().numpy(), rp.cpu().numpy()[order])
+    assert np.array_equal(v2.cpu().numpy(), rv.cpu().numpy()[order])
+    key = _bin_key(p2.cpu().numpy(), N)
+    assert np.all(np.diff(key) >= 0)
+    # another time step than the predicted one: the sort counts for itself
+    sb.predict_next = (half2, dt2, f64)
+    acc2, _ = psc.mesh.interp_kick_phi(phi, None, 0.0, 0, 5, p2, v2, 2, np.float32(0.01), sb)
+    p3, v3, i3 = psc.mesh.step_sort(p2, v2, acc2, i2, np.float32(0.25), np.float32(0.5), 0, sb)
+    assert sb.counts_skipped == skipped + 1
+    assert np.all(np.diff(_bin_key(p3.cpu().numpy(), N)) >= 0)
+    assert np.array_equal(np.sort(i3.cpu().numpy()), np.arange(n))
