@@ -234,8 +234,14 @@ def leapfrog(position, velocity, acceleration, potential, additional_field, dt, 
             # The next time step is min(free fall, Courant, scale-factor variation) (integrate, above); the last of the
             # three depends on a(t) only and is the one that binds through most of a cosmological run.  Let the
             # interpolation kernel count the next sort's bins under that guess; step_sort checks the guess.
-            dt_guess = dt_weak_variation(tables[1], param)
-            sb.predict_next = (np.float32(0.5 * dt_guess), dt_guess, 0 if isinstance(dt_guess, np.float32) else 1)
+            # After three unused guesses in a row (another criterion sets the step) it pauses for eight steps.
+            if sb.miss_streak >= 3:
+                sb.miss_streak, sb.rest = 0, 8
+            if sb.rest > 0:
+                sb.rest -= 1
+            else:
+                dt_guess = dt_weak_variation(tables[1], param)
+                sb.predict_next = (np.float32(0.5 * dt_guess), dt_guess, 0 if isinstance(dt_guess, np.float32) else 1)
         acc, pot, add, maxima = solver._pm_device(pos, param, pot, add, tables, kick=(vel, half_dt), counted=sb)
         utils.set_particle_ids((pos, vel, acc), ids)
         mx = maxima.cpu().numpy()

@@ -42,6 +42,9 @@ class SortedBins:
         # interp_kick_phi to count the bins of the next step under that time step; predicted = what it counted for
         self.predict_next = None
         self.predicted = None
+        self.miss_streak = 0      # consecutive predictions the host did not use (another criterion set the step)
+        self.rest = 0             # steps left without prediction after a streak of misses
+        self.counts_skipped = 0   # sorts that used a prediction
 
     def describes(self, pos):
         return self.owner is not None and self.owner() is pos
@@ -85,12 +88,14 @@ def step_sort(pos, vel, acc, ids, half_dt, dt, dt_is_f64, sb):
     # the count pass was done by the previous interpolation kernel if it predicted exactly this time step for exactly
     # these arrays (same bits: float(half_dt), float(dt) and the float64 flag are what both calls hand to the library)
     ready = int(src >= 0 and sb.predicted == (float(half_dt), float(dt), int(dt_is_f64)))
+    if sb.predicted is not None:
+        sb.miss_streak = 0 if ready else sb.miss_streak + 1
     sb.predicted = None
     _lib.check(_lib.load().psc_step_sort(_lib.ptr(pos), _lib.ptr(vel), _lib.ptr(acc), _lib.ptr(ids), n, float(half_dt),
                                          float(dt), int(dt_is_f64), sb.N, src, ready, _lib.ptr(sb.scratch),
                                          sb.scratch.numel(), _lib.ptr(pos2), _lib.ptr(vel2), _lib.ptr(ids2),
                                          _lib.stream()))
-    sb.counts_skipped = getattr(sb, "counts_skipped", 0) + ready
+    sb.counts_skipped += ready
     sb.table = 0 if src < 0 else 1 - src
     sb.owner = weakref.ref(pos2)
     return pos2, vel2, ids2

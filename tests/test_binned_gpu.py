@@ -424,7 +424,7 @@ def test_predicted_bin_count_equals_the_count_pass(psc, orc, dt2):
     got = sb.scratch.cpu().numpy()[: 4 * nbins].view(np.int32)          # the count table opens the scratch
     assert np.array_equal(got, want)
     assert np.any(want != np.bincount(_bin_key(sp.cpu().numpy(), N), minlength=nbins)), "particles must change bins"
-    skipped = getattr(sb, "counts_skipped", 0)
+    skipped = sb.counts_skipped
     p2, v2, i2 = psc.mesh.step_sort(sp, sv, acc, sid, half2, dt2, f64, sb)
     assert sb.counts_skipped == skipped + 1
     torch.cuda.synchronize()
