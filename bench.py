@@ -551,6 +551,7 @@ def run_gpu_arm(args):
     ev1.record()
     torch.cuda.synchronize()
     torch.cuda.cudart().cudaProfilerStop()
+    hits = int(count_hits() - hits0)
     sampler.mark_end()
     clocks = sampler.stop()
     launches = _lib.launch_count() - launches0
@@ -647,7 +648,7 @@ def run_gpu_arm(args):
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
         "clocks": clocks, "kernels": kern,
         "ms_per_step_outside_calls": outside_ms,
-        "predicted_bin_counts_used": {"steps": int(count_hits() - hits0), "of": K,
+        "predicted_bin_counts_used": {"steps": hits, "of": K,
                                       "what": "steps whose sort skipped its count pass: the previous interpolation "
                                               "kernel had counted the bins under the time step that was then taken"},
         "reorder": {"ms": t_reorder_ms, "in_timed_steps": n_reorders, "amortised_over": N_REORDER,
