@@ -109,7 +109,9 @@ class TorchComm:
     # on the stream publishes it.  The alternating sets make one barrier per exchange enough: a slot is rewritten two
     # exchanges later, after a barrier that its owner only reaches once it has consumed the previous content.
     def _mailbox(self, numel):
-        """symmetric mailbox with room for `numel` float32 per slot, or None (NCCL p2p is used then); collective"""
+        """symmetric mailbox with room for `numel` float32 per slot, or None (NCCL p2p is used then).  Growing it is a
+        collective (symmetric-memory rendezvous), so only messages whose size is the same on every rank may come through
+        here: ghost planes and the fixed-capacity migration messages; rank-dependent sizes use pair_exchange."""
         if self._mbox is False:
             return None
         if self._mbox is None or self._mbox[2] < numel:

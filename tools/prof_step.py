@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Tiny driver for ncu captures: a few full PM steps (or only the deposit) at 2^nc cells per side.
-usage: python tools/prof_step.py [nc=9] [what=step|deposit|interp]"""
+usage: python tools/prof_step.py [nc=9] [what=step|step+reorder|deposit|interp]"""
 import os
 import sys
 
@@ -31,8 +31,10 @@ else:
     utils.set_units(param)
     state = list(solver.pm(pos, param))
     state = [pos, vel] + state
-    for _ in range(3):
+    for it in range(3):
         param["nsteps"] += 1
         state = list(integration.integrate(*state, tables, param, 1e30))
+        if it == 1 and what == "step+reorder":    # utils.reorder_particles on the bin-ordered arrays: the id relabel
+            state[:3] = utils.reorder_particles(*state[:3])
 torch.cuda.synchronize()
 print("done", what, N)
