@@ -64,6 +64,12 @@ def step_sorted(np_, ncells_1d):
     return b
 
 
+def _stamp(*tensors):
+    """identity and in-place version of device tensors (the library's own kernels write through raw pointers and do not
+    bump versions; anything the caller does through torch does)"""
+    return tuple((id(t), t._version) for t in tensors)
+
+
 def sorted_bins_of(pos):
     """the SortedBins whose current table describes the bin-ordered tensor `pos`, or None"""
     for sb in _step_sorted.values():
@@ -87,7 +93,7 @@ def step_sort(pos, vel, acc, ids, half_dt, dt, dt_is_f64, sb):
     src = sb.table if (sb.describes(pos) and not os.environ.get("PSC_NO_LOCAL_SORT")) else -1
     # the count pass was done by the previous interpolation kernel if it predicted exactly this time step for exactly
     # these arrays (same bits: float(half_dt), float(dt) and the float64 flag are what both calls hand to the library)
-    ready = int(src >= 0 and sb.predicted == (float(half_dt), float(dt), int(dt_is_f64)))
+    ready = int(src >= 0 and sb.predicted == (float(half_dt), float(dt), int(dt_is_f64), _stamp(pos, vel, acc)))
     if sb.predicted is not None:
         sb.miss_streak = 0 if ready else sb.miss_streak + 1
     sb.predicted = None
@@ -268,7 +274,9 @@ def interp_kick_phi(potential, u, f, fr_n, order, position, velocity, scheme, ha
             binned.scratch.numel(), binned.table, _lib.ptr(vel), _lib.ptr(acc), n, phi.shape[0], scheme,
             float(half_dt), _lib.ptr(mx), int(predict), float(h2), float(d2), int(f2), _lib.stream()))
         if predict:
-            binned.predicted = (float(h2), float(d2), int(f2))
+            # the guess holds for exactly these tensors in exactly this state: an in-place torch operation of the
+            # caller on any of them before the next step bumps its version and voids the prediction
+            binned.predicted = (float(h2), float(d2), int(f2), _stamp(pos, vel, acc))
     else:
         _lib.check(_lib.load().psc_interp_kick_phi_binned(
             _lib.ptr(phi), _lib.ptr(tu), float(np.float32(f)), fr_n, order, _lib.ptr(binned.scratch),

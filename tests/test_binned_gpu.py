@@ -414,7 +414,7 @@ def test_predicted_bin_count_equals_the_count_pass(psc, orc, dt2):
     f64 = 0 if isinstance(dt2, np.float32) else 1
     sb.predict_next = (half2, dt2, f64)
     acc, _ = psc.mesh.interp_kick_phi(phi, None, 0.0, 0, 5, sp, sv, 2, np.float32(0.01), sb)
-    assert sb.predicted == (float(half2), float(dt2), f64)
+    assert sb.predicted[:3] == (float(half2), float(dt2), f64)
     # reference: the stand-alone kick + drift + wrap on copies
     rp, rv = sp.clone(), sv.clone()
     lib.check(L.psc_kick_drift_wrap(lib.ptr(rp), lib.ptr(rv), lib.ptr(acc), n, float(half2), float(dt2), f64, lib.stream()))
@@ -438,5 +438,12 @@ def test_predicted_bin_count_equals_the_count_pass(psc, orc, dt2):
     acc2, _ = psc.mesh.interp_kick_phi(phi, None, 0.0, 0, 5, p2, v2, 2, np.float32(0.01), sb)
     p3, v3, i3 = psc.mesh.step_sort(p2, v2, acc2, i2, np.float32(0.25), np.float32(0.5), 0, sb)
     assert sb.counts_skipped == skipped + 1
+    # the predicted step, but the caller touched the velocities in between: the guess is void
+    sb.predict_next = (half2, dt2, f64)
+    acc3, _ = psc.mesh.interp_kick_phi(phi, None, 0.0, 0, 5, p3, v3, 2, np.float32(0.01), sb)
+    v3 += 1e-4
+    p4, v4, i4 = psc.mesh.step_sort(p3, v3, acc3, i3, half2, dt2, f64, sb)
+    assert sb.counts_skipped == skipped + 1
+    assert np.all(np.diff(_bin_key(p4.cpu().numpy(), N)) >= 0) and np.array_equal(np.sort(i4.cpu().numpy()), np.arange(n))
     assert np.all(np.diff(_bin_key(p3.cpu().numpy(), N)) >= 0)
     assert np.array_equal(np.sort(i3.cpu().numpy()), np.arange(n))
