@@ -861,10 +861,12 @@ __device__ __forceinline__ void deposit_bin_range(float (*tiles)[BD_TILE], const
     if (valid) load_particle<SORTED>(brec, n, px, py, pz, row_unused);
     int i, j, k;
     float wx[3], wy[3], wz[3];
-    axis_weights<SCHEME>(px * Nf, N, i, wx[0], wx[1], wx[2]);
-    axis_weights<SCHEME>(py * Nf, N, j, wy[0], wy[1], wy[2]);
-    axis_weights<SCHEME>(pz * Nf, N, k, wz[0], wz[1], wz[2]);
-    const int t0 = min(max(i - oi, 1), BB), t1 = min(max(j - oj, 1), BB), t2 = min(max(k - ok, 1), BB);  // in [1, 8] for every particle of this bin (clamped like bin_of)
+    axis_weights_bin<SCHEME>(px * Nf, N, i, wx[0], wx[1], wx[2]);
+    axis_weights_bin<SCHEME>(py * Nf, N, j, wy[0], wy[1], wy[2]);
+    axis_weights_bin<SCHEME>(pz * Nf, N, k, wz[0], wz[1], wz[2]);
+    // in [1, 8] for every particle of this bin (clamped like bin_of); the shifted CIC window reaches 9
+    constexpr int TMAX = SCHEME == PSC_CIC ? BB + 1 : BB;
+    const int t0 = min(max(i - oi, 1), TMAX), t1 = min(max(j - oj, 1), TMAX), t2 = min(max(k - ok, 1), TMAX);
     float wgt[27];
 #pragma unroll
     for (int a = 0; a < 3; a++)
@@ -920,7 +922,7 @@ __device__ __forceinline__ void deposit_bin_range(float (*tiles)[BD_TILE], const
       for (int e = 0; e < 3; e++)
 #pragma unroll
         for (int g = 0; g < 3; g++) {
-          if (SCHEME == PSC_NGP && !(a == 1 && e == 1 && g == 1)) continue;
+          if (!stencil_uses<SCHEME>(a, e, g)) continue;
           if (is_leader) {
             float *p = cell0 + a * BD_P0 + e * BD_P1 + g;
             *p += wgt[(a * 3 + e) * 3 + g];
@@ -1028,10 +1030,11 @@ __global__ void __launch_bounds__(BI_THREADS) interp_kick4_binned_kernel(
     const int row = __float_as_int(rec.w);
     int i, j, k;
     float wx[3], wy[3], wz[3];
-    axis_weights<SCHEME>(px * Nf, N, i, wx[0], wx[1], wx[2]);
-    axis_weights<SCHEME>(py * Nf, N, j, wy[0], wy[1], wy[2]);
-    axis_weights<SCHEME>(pz * Nf, N, k, wz[0], wz[1], wz[2]);
-    const float4 *c0 = tile + ((min(max(i - oi, 1), BB) - 1) * BT + (min(max(j - oj, 1), BB) - 1)) * BT + (min(max(k - ok, 1), BB) - 1);
+    axis_weights_bin<SCHEME>(px * Nf, N, i, wx[0], wx[1], wx[2]);
+    axis_weights_bin<SCHEME>(py * Nf, N, j, wy[0], wy[1], wy[2]);
+    axis_weights_bin<SCHEME>(pz * Nf, N, k, wz[0], wz[1], wz[2]);
+    constexpr int TMAX = SCHEME == PSC_CIC ? BB + 1 : BB;   // the shifted CIC window reaches tile index 9
+    const float4 *c0 = tile + ((min(max(i - oi, 1), TMAX) - 1) * BT + (min(max(j - oj, 1), TMAX) - 1)) * BT + (min(max(k - ok, 1), TMAX) - 1);
     float ax = 0.0f, ay = 0.0f, az = 0.0f;
 #pragma unroll
     for (int a = 0; a < 3; a++)
@@ -1040,6 +1043,7 @@ __global__ void __launch_bounds__(BI_THREADS) interp_kick4_binned_kernel(
         const float wxy = wx[a] * wy[e];
 #pragma unroll
         for (int g = 0; g < 3; g++) {
+          if (!stencil_uses<SCHEME == PSC_NGP ? PSC_TSC : SCHEME>(a, e, g)) continue;   // CIC: 8 of the 27 points
           const float w = wxy * wz[g];
           const float4 f = c0[(a * BT + e) * BT + g];
           ax += w * f.x; ay += w * f.y; az += w * f.z;
@@ -1196,10 +1200,11 @@ __global__ void __launch_bounds__(BP_THREADS, 6) interp_kick_phi_binned_kernel(
       load_particle<SORTED>(brec, n, px, py, pz, row);
       int i, j, k;
       float wx[3], wy[3], wz[3];
-      axis_weights<SCHEME>(px * Nf, N, i, wx[0], wx[1], wx[2]);
-      axis_weights<SCHEME>(py * Nf, N, j, wy[0], wy[1], wy[2]);
-      axis_weights<SCHEME>(pz * Nf, N, k, wz[0], wz[1], wz[2]);
-      const float4 *c0 = tile + (min(max(i - oi, 1), BB) - 1) * TP0 + (min(max(j - oj, 1), BB) - 1) * TP1 + (min(max(k - ok, 1), BB) - 1);
+      axis_weights_bin<SCHEME>(px * Nf, N, i, wx[0], wx[1], wx[2]);
+      axis_weights_bin<SCHEME>(py * Nf, N, j, wy[0], wy[1], wy[2]);
+      axis_weights_bin<SCHEME>(pz * Nf, N, k, wz[0], wz[1], wz[2]);
+      constexpr int TMAX = SCHEME == PSC_CIC ? BB + 1 : BB;   // the shifted CIC window reaches tile index 9
+      const float4 *c0 = tile + (min(max(i - oi, 1), TMAX) - 1) * TP0 + (min(max(j - oj, 1), TMAX) - 1) * TP1 + (min(max(k - ok, 1), TMAX) - 1);
       float ax = 0.0f, ay = 0.0f, az = 0.0f;
 #pragma unroll
       for (int a = 0; a < 3; a++)
@@ -1208,6 +1213,7 @@ __global__ void __launch_bounds__(BP_THREADS, 6) interp_kick_phi_binned_kernel(
           const float wxy = wx[a] * wy[e];
 #pragma unroll
           for (int g = 0; g < 3; g++) {
+            if (!stencil_uses<SCHEME == PSC_NGP ? PSC_TSC : SCHEME>(a, e, g)) continue;   // CIC: 8 of the 27 points
             const float w = wxy * wz[g];
             const float4 ff = c0[a * TP0 + e * TP1 + g];
             ax += w * ff.x; ay += w * ff.y; az += w * ff.z;

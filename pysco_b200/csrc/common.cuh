@@ -149,4 +149,29 @@ __device__ __forceinline__ void axis_weights(float xp, int N, int &c, float &wm,
   }
 }
 
+// The same for the bin kernels, with CIC as a genuine 2-point scheme: the window is shifted so that the two cells with
+// weight are always (c - 1, c) -- wp == 0 -- and the kernels skip every offset with a third index: 8 shared-memory
+// updates / gathers per particle instead of 27.  The values are those of axis_weights<PSC_CIC>, cell for cell; c may
+// be one past the particle's cell (a particle in the upper half of the last cell of a bin reaches tile index 9).
+template <int SCHEME>
+__device__ __forceinline__ void axis_weights_bin(float xp, int N, int &c, float &wm, float &w0, float &wp) {
+  if (SCHEME == PSC_CIC) {
+    const int cell = (int)xp;
+    const float d = xp - 0.5f - (float)cell;
+    const float ad = fabsf(d);
+    const bool up = d > 0.0f;            // weight on (cell, cell + 1), else on (cell - 1, cell); d == 0: all on cell
+    c = cell + (up ? 1 : 0);
+    wm = up ? 1.0f - ad : ad;
+    w0 = up ? ad : 1.0f - ad;
+    wp = 0.0f;
+  } else {
+    axis_weights<SCHEME>(xp, N, c, wm, w0, wp);
+  }
+}
+// offsets (a, e, g) in {0, 1, 2}^3 a scheme touches around (c - 1): TSC all, CIC the lower 2^3, NGP the centre
+template <int SCHEME>
+__device__ __forceinline__ constexpr bool stencil_uses(int a, int e, int g) {
+  return SCHEME == PSC_TSC ? true : SCHEME == PSC_CIC ? (a < 2 && e < 2 && g < 2) : (a == 1 && e == 1 && g == 1);
+}
+
 }  // namespace psc
