@@ -1238,7 +1238,10 @@ class Slab:
         if kick is None:
             mx[1] = ops.max_abs(self.vel[:n])[0]
         self._mark("gradient+interp+kick")
-        mx = torch.cat([mx, torch.tensor([float(self._mig_want)], dtype=torch.float32, device=mx.device)])
+        # (torch.full, not torch.tensor: a host list would be copied from pageable memory, which blocks the host until
+        # the stream has drained -- the all-reduce and the read below are then enqueued behind the interpolation
+        # kernel instead of after it)
+        mx = torch.cat([mx, torch.full((1,), float(self._mig_want), dtype=torch.float32, device=mx.device)])
         comm.allreduce_max_(mx)
         m = mx.cpu().numpy()
         self._mark("allreduce max")
