@@ -60,10 +60,21 @@ def dt_CFL_maxvel(velocity, param):
     return np.float32(param["Courant_factor"]) * dx / max_vel
 
 
+_dt3_memo = [None, None]
+
+
 def dt_weak_variation(func_t_a, param):
-    """integration.py:329-358"""
-    aexp_factor = 1.0 + 0.01 * param["max_aexp_stepping"]
-    return np.float32(func_t_a(np.log(aexp_factor * param["aexp"])) - func_t_a(np.log(param["aexp"])))
+    """integration.py:329-358.  The value depends on a(t) only; leapfrog asks for it right after it has advanced the
+    clock (the guess of the speculative bin count) and integrate() asks again at the start of the next step, on the
+    critical path between two steps: the second call is answered from a one-entry memo."""
+    aexp, stepping = param["aexp"], param["max_aexp_stepping"]
+    key = (id(func_t_a), float(aexp), float(stepping))
+    if _dt3_memo[0] == key:
+        return _dt3_memo[1]
+    aexp_factor = 1.0 + 0.01 * stepping
+    val = np.float32(func_t_a(np.log(aexp_factor * aexp)) - func_t_a(np.log(aexp)))
+    _dt3_memo[0], _dt3_memo[1] = key, val
+    return val
 
 
 def _advance_clock(dt, tables, param):
