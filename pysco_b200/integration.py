@@ -68,12 +68,16 @@ def dt_weak_variation(func_t_a, param):
     clock (the guess of the speculative bin count) and integrate() asks again at the start of the next step, on the
     critical path between two steps: the second call is answered from a one-entry memo."""
     aexp, stepping = param["aexp"], param["max_aexp_stepping"]
-    key = (id(func_t_a), float(aexp), float(stepping))
-    if _dt3_memo[0] == key:
+    key = (float(aexp), float(stepping))
+    owner = _dt3_memo[0]
+    if owner is not None and owner[0]() is func_t_a and owner[1] == key:
         return _dt3_memo[1]
     aexp_factor = 1.0 + 0.01 * stepping
     val = np.float32(func_t_a(np.log(aexp_factor * aexp)) - func_t_a(np.log(aexp)))
-    _dt3_memo[0], _dt3_memo[1] = key, val
+    try:
+        _dt3_memo[0], _dt3_memo[1] = (weakref.ref(func_t_a), key), val
+    except TypeError:      # a table object that cannot be weakly referenced: no memo
+        _dt3_memo[0] = None
     return val
 
 
