@@ -20,6 +20,7 @@ one rank, and BASELINE configs 2-4; `config5` (N = 8) = BASELINE config 5 (2048^
 STRONG scaling: the same N^3 problem on every GPU count.
 """
 import argparse
+import gc
 import json
 import os
 import subprocess
@@ -540,6 +541,7 @@ def run_gpu_arm(args):
     hits0 = count_hits()
     _lib.enable_timing(True)
     launches0 = _lib.launch_count()
+    gc.collect()
     torch.cuda.synchronize()
     torch.cuda.cudart().cudaProfilerStart()   # `ncu --profile-from-start off` lists the timed steps only
     sampler.mark_begin()
@@ -737,6 +739,7 @@ def slab_measure(S, param, tables, K, warmup, world, rank, local_rank, with_phas
     _lib.enable_timing(True)
     S.phase_marks = [] if with_phases else None
     launches0 = _lib.launch_count()
+    gc.collect()      # a full collection now, so that none is due inside the timed steps (one rank pausing stalls all)
     barrier()
     sampler.mark_begin()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
