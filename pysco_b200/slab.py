@@ -85,6 +85,7 @@ class TorchComm:
         self.size = dist.get_world_size(group)
         self._mbox = None          # (buffer, handle, floats per slot) | False when peer memory is unavailable
         self._mbox_set = 0
+        self._views = {}           # cached tensor views of the peers' mailbox slots
         self._use_mailbox = not os.environ.get("PSC_NO_PEER_MAILBOX")
 
     def exchange_counts(self, counts):
@@ -122,7 +123,18 @@ class TorchComm:
                 return None
             self._mbox = (bufs[0][0], bufs[0][1], cap)
             self._mbox_set = 0
+            self._views = {}
         return self._mbox
+
+    def _peer_view(self, hdl, peer, numel, offset):
+        """tensor view of a peer's mailbox slot (cached: creating one costs more host time than the copy it serves)"""
+        key = (peer, numel, offset)
+        v = self._views.get(key)
+        if v is None:
+            if len(self._views) > 64:
+                self._views.clear()
+            v = self._views[key] = hdl.get_buffer(peer, (numel,), torch.float32, offset)
+        return v
 
     def _p2p(self, to_left, to_right, from_left, from_right):
         P, r = self.size, self.rank
@@ -135,9 +147,9 @@ class TorchComm:
         base = self._mbox_set * 2 * cap          # slot 0: from the left neighbour, slot 1: from the right neighbour
         self._mbox_set ^= 1
         if to_left.numel():      # I am my left neighbour's RIGHT neighbour
-            hdl.get_buffer(left, (to_left.numel(),), torch.float32, base + cap).copy_(to_left.reshape(-1))
+            self._peer_view(hdl, left, to_left.numel(), base + cap).copy_(to_left.reshape(-1))
         if to_right.numel():
-            hdl.get_buffer(right, (to_right.numel(),), torch.float32, base).copy_(to_right.reshape(-1))
+            self._peer_view(hdl, right, to_right.numel(), base).copy_(to_right.reshape(-1))
         hdl.barrier(channel=0)
         if from_left.numel():
             from_left.reshape(-1).copy_(buf[base:base + from_left.numel()])
