@@ -23,6 +23,8 @@ import argparse
 import gc
 import json
 import os
+
+os.environ.setdefault("CUDA_MODULE_LOADING", "EAGER")   # no lazy kernel loads inside the timed steps
 import subprocess
 import sys
 import threading

@@ -5,6 +5,8 @@ import os
 import sys
 import time
 
+os.environ.setdefault("CUDA_MODULE_LOADING", os.environ.get("TRACE_LOADING", "EAGER"))
+
 import numpy as np
 import torch
 
