@@ -544,6 +544,7 @@ def run_gpu_arm(args):
     _lib.enable_timing(True)
     launches0 = _lib.launch_count()
     gc.collect()
+    gc.freeze()       # see slab_measure: no full pass of the cyclic collector over the import-time heap in a step
     torch.cuda.synchronize()
     torch.cuda.cudart().cudaProfilerStart()   # `ncu --profile-from-start off` lists the timed steps only
     sampler.mark_begin()
@@ -741,7 +742,12 @@ def slab_measure(S, param, tables, K, warmup, world, rank, local_rank, with_phas
     _lib.enable_timing(True)
     S.phase_marks = [] if with_phases else None
     launches0 = _lib.launch_count()
-    gc.collect()      # a full collection now, so that none is due inside the timed steps (one rank pausing stalls all)
+    # Python's cyclic collector runs a full (generation 2) pass about every 24 steps of this loop and takes ~3 ms on
+    # a heap with torch, pandas and scipy loaded -- and a rank that pauses stalls all the others at the next exchange
+    # (measured: one 7.6 ms step among 4.6 ms ones, tools/trace_slab_steps.py).  Collect now and freeze what exists,
+    # so that later passes only look at objects created since (microseconds); main.run / slab.run do the same.
+    gc.collect()
+    gc.freeze()
     barrier()
     sampler.mark_begin()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

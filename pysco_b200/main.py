@@ -118,6 +118,11 @@ def run(param, initial_state=None):
     else:
         param["i_snap"] += 1
 
+    # the time loop allocates a few thousand small Python objects per step: without this the cyclic collector makes a
+    # full pass over the whole import-time heap (torch, pandas, scipy: ~3 ms) every couple of dozen steps
+    import gc
+    gc.collect()
+    gc.freeze()
     while param["aexp"] < aexp_out[-1]:
         param["nsteps"] += 1
         position, velocity, acceleration, potential, additional_field = integration.integrate(

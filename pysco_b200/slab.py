@@ -1475,6 +1475,11 @@ def run(param, comm=None, initial_state=None, ops_factory=None):
     aexp_out = np.sort(1.0 / (np.array(z_out) + 1))
     t_out = tables[1](np.log(aexp_out))
     param["i_snap"] = 1 if "i_snap" not in param.index else param["i_snap"] + 1
+    # the time loop allocates a few thousand small Python objects per step: without this the cyclic collector makes a
+    # full pass over the whole import-time heap (torch, pandas, scipy: ~3 ms) every couple of dozen steps
+    import gc
+    gc.collect()
+    gc.freeze()
     while param["aexp"] < aexp_out[-1]:
         param["nsteps"] += 1
         S.integrate(tables, param, t_out[param["i_snap"] - 1])
