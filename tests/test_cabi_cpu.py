@@ -128,3 +128,32 @@ def test_cosmotable_vs_reference_golden():
         assert mine.shape == ref.shape == (13, len(lna))
         np.testing.assert_allclose(mine, ref, rtol=1e-9, atol=1e-12)
         np.testing.assert_allclose([param["Om_r"], param["Om_lambda"]], g[f"{name}_Om_r_Om_lambda"], rtol=1e-12)
+
+
+def test_dt_weak_variation_memo_follows_table_and_parameters():
+    """integration.dt_weak_variation answers the second of its two calls per step from a one-entry memo: the memo must
+    follow the table object, a(t) and max_aexp_stepping (integration.py:329-358 has no state)"""
+    import numpy as np
+    import pandas as pd
+    from scipy.interpolate import interp1d
+    from pysco_b200 import integration
+
+    def table(scale):
+        lna = np.linspace(-6.0, 0.5, 64)
+        return interp1d(lna, scale * np.exp(1.5 * lna), fill_value="extrapolate")
+
+    def direct(f, p):
+        fac = 1.0 + 0.01 * p["max_aexp_stepping"]
+        return np.float32(f(np.log(fac * p["aexp"])) - f(np.log(p["aexp"])))
+
+    p = pd.Series({"aexp": 0.1, "max_aexp_stepping": 10})
+    f1, f2 = table(1.0), table(2.0)
+    for f in (f1, f1, f2, f1):
+        assert integration.dt_weak_variation(f, p) == direct(f, p)
+    p["aexp"] = 0.2
+    assert integration.dt_weak_variation(f1, p) == direct(f1, p)
+    p["max_aexp_stepping"] = 5
+    assert integration.dt_weak_variation(f1, p) == direct(f1, p)
+    del f2
+    f3 = table(3.0)      # may reuse the identity of the deleted table
+    assert integration.dt_weak_variation(f3, p) == direct(f3, p)
