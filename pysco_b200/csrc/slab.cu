@@ -208,17 +208,7 @@ __global__ void __launch_bounds__(256) slab_put_kernel(const float2 *__restrict_
     }
     const float2 *s = in + r * nz;
     float2 *t = peers[d] + drow * nz;
-    // 16-byte remote stores (512 contiguous bytes per warp and iteration instead of 256): a row of nz = N/2 + 1
-    // complex values starts on an 8-byte boundary only, so the first element is peeled off where needed
-    const int k0 = (int)((reinterpret_cast<uintptr_t>(t) >> 3) & 1);
-    if (k0 && lane == 0) t[0] = s[0];
-    const int npair = (nz - k0) >> 1;
-    float4 *t4 = reinterpret_cast<float4 *>(t + k0);
-    for (int q = lane; q < npair; q += 32) {
-      const float2 a = s[k0 + 2 * q], b = s[k0 + 2 * q + 1];
-      t4[q] = make_float4(a.x, a.y, b.x, b.y);
-    }
-    if (((nz - k0) & 1) && lane == 0) t[nz - 1] = s[nz - 1];
+    for (int k = lane; k < nz; k += 32) t[k] = s[k];
   }
 }
 
