@@ -444,6 +444,13 @@ def test_predicted_bin_count_equals_the_count_pass(psc, orc, dt2):
     v3 += 1e-4
     p4, v4, i4 = psc.mesh.step_sort(p3, v3, acc3, i3, half2, dt2, f64, sb)
     assert sb.counts_skipped == skipped + 1
-    assert np.all(np.diff(_bin_key(p4.cpu().numpy(), N)) >= 0) and np.array_equal(np.sort(i4.cpu().numpy()), np.arange(n))
+    torch.cuda.synchronize()
+    k4, ids4 = _bin_key(p4.cpu().numpy(), N), i4.cpu().numpy()
+    rp4, rv4 = p3.clone(), v3.clone()
+    lib.check(L.psc_kick_drift_wrap(lib.ptr(rp4), lib.ptr(rv4), lib.ptr(acc3), n, float(half2), float(dt2), f64, lib.stream()))
+    want4 = np.bincount(_bin_key(rp4.cpu().numpy(), N), minlength=nbins)
+    diag = (f"rows out of order {int(np.sum(np.diff(k4) < 0))}, duplicate ids {n - len(np.unique(ids4))}, bins whose "
+            f"count differs from the reference {int(np.sum(np.bincount(k4, minlength=nbins) != want4))}")
+    assert np.all(np.diff(k4) >= 0) and np.array_equal(np.sort(ids4), np.arange(n)), diag
     assert np.all(np.diff(_bin_key(p3.cpu().numpy(), N)) >= 0)
     assert np.array_equal(np.sort(i3.cpu().numpy()), np.arange(n))
