@@ -657,6 +657,9 @@ __global__ void __launch_bounds__(256) step_sort_local_kernel(
       if (lane == 31) s_near = incl;
     }
     __syncthreads();
+    // the sorted round: nstay stayers, then the leavers by bin (read here: hist is cleared again by whoever finishes
+    // the write-out first)
+    const int nnear = s_near, nstay = hist[nself];
     float *opos = S, *ovel = S + SL_F3;
     IdT *oid = reinterpret_cast<IdT *>(S + 2 * SL_F3);
     unsigned char *od = reinterpret_cast<unsigned char *>(S + 3 * SL_F3);
@@ -691,7 +694,6 @@ __global__ void __launch_bounds__(256) step_sort_local_kernel(
       }
     }
     __syncthreads();
-    const int nnear = s_near, nstay = hist[nself];     // the sorted round: nstay stayers, then the leavers by bin
     {
       const int64_t g0 = (int64_t)3 * s_dst[13];
       for (int t = tid; t < 3 * nstay; t += 256) {           // the stayers: one contiguous run of floats
@@ -708,6 +710,9 @@ __global__ void __launch_bounds__(256) step_sort_local_kernel(
       for (int t = nstay + tid; t < nnear; t += 256) ids_out[s_dst[od[t]] + t] = oid[t];
     }
     for (int t = tid; t < 32 * per; t += 256) hist[t] = 0;   // all of them: the scan wrote the unused tail too
+    // this stage is the destination of the next bulk copy: every thread orders its own generic-proxy accesses to the
+    // output area before the async proxy (the documented pattern: fence in every thread, barrier, then the copy)
+    cuda::ptx::fence_proxy_async(cuda::ptx::space_shared);
     __syncthreads();   // output area, hist and s_dst are free again
   }
 }
