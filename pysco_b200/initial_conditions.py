@@ -16,6 +16,7 @@ on the host with the SAME NumPy generator calls, in the same order, as the refer
 """
 import logging
 import math
+import threading
 
 import numpy as np
 import torch
@@ -104,6 +105,106 @@ def get_transfer_grid(param):
     return np.interp(k_grid, k_dimensionless, sqrtPk)
 
 
+# ---- the same white noise, one y block of the transposed spectrum at a time (x-slab runs: SlabLayout)
+class _NoiseStream:
+    """Random access into the float32 draws of numpy.random.default_rng(seed): Generator.random(dtype=float32) takes
+    the 32-bit halves of PCG64's 64-bit outputs in order (low half first), so element e of a draw that started on a
+    64-bit boundary comes from output e // 2 -- PCG64.advance() jumps there in O(log) time.  Every rank reproduces
+    exactly the numbers the reference draws for its block without drawing the rest."""
+
+    def __init__(self, seed):
+        self.bg = np.random.PCG64(seed)
+        self.start = self.bg.state
+
+    def floats(self, first, count):
+        """elements [first, first + count) of the float32 stream (first even)"""
+        assert first % 2 == 0
+        self.bg.state = self.start
+        self.bg.advance(first // 2)
+        return np.random.Generator(self.bg).random(count, dtype=np.float32)
+
+
+def _rows_of_stream(stream, offset, i, rows, N):
+    """rows `rows` (ascending) of plane i of an [.., N, N] float32 draw that starts at element `offset`: [len, N]"""
+    out = np.empty((len(rows), N), dtype=np.float32)
+    a = 0
+    while a < len(rows):            # contiguous runs of rows: one jump each
+        b = a + 1
+        while b < len(rows) and rows[b] == rows[b - 1] + 1:
+            b += 1
+        out[a:b] = stream.floats(offset + (i * N + int(rows[a])) * N, (b - a) * N).reshape(b - a, N)
+        a = b
+    return out
+
+
+def white_noise_fourier_block(N, seed, y0, nyl, fixed=False, paired=False):
+    """The block [:, y0:y0+nyl, :] of white_noise_fourier(N, default_rng(seed)) (or of white_noise_fourier_fixed),
+    bit for bit, from 2 nyl / N of the random numbers: plane i needs the rows of the block and, for the conjugate
+    half (planes N - i and the self-conjugate planes 0, N/2), the rows -j of the block.  complex64 [N, nyl, N/2+1]"""
+    middle = N // 2
+    nz = middle + 1
+    stream = _NoiseStream(seed)
+    plane = (middle + 1) * N * N                       # elements of one (middle + 1, N, N) draw
+    twopi, one = np.float32(2 * math.pi), np.float32(1)
+    shift = np.float32(math.pi) if paired else np.float32(0)
+    J = np.arange(y0, y0 + nyl)
+    negJ = (-J) % N
+    rows = np.unique(np.concatenate([J, negJ]))        # ascending: what _rows_of_stream wants
+    at_J, at_negJ = np.searchsorted(rows, J), np.searchsorted(rows, negJ)
+    K = np.arange(nz)
+    negK = (-K) % N
+    later = (J[:, None] * N + K[None, :]) > (negJ[:, None] * N + negK[None, :])    # the write that wins (planes 0, N/2)
+    out = np.empty((N, nyl, nz), dtype=np.complex64)
+    for i in range(middle + 1):
+        if fixed:
+            phase = twopi * _rows_of_stream(stream, 0, i, rows, N) + shift
+            upper = (np.cos(phase) + 1j * np.sin(phase)).astype(np.complex64)
+        else:
+            amp = _rows_of_stream(stream, 0, i, rows, N)
+            phase = twopi * _rows_of_stream(stream, plane, i, rows, N)
+            amplitude = np.sqrt(-np.log(one - amp))
+            upper = (amplitude * np.cos(phase) + 1j * (amplitude * np.sin(phase))).astype(np.complex64)
+        own = upper[at_J][:, :nz]
+        partner = np.conj(upper[at_negJ][:, negK])
+        if i in (0, middle):
+            out[i] = np.where(later, own, partner)
+        else:
+            out[i] = own
+            out[N - i] = partner
+    # the eight real modes (initial_conditions.py:636-655): drawn after the two big draws, in this order
+    specials = ((0, 0, middle), (0, middle, 0), (0, middle, middle), (middle, 0, 0), (middle, 0, middle),
+                (middle, middle, 0), (middle, middle, middle))
+    if fixed:
+        values = [np.float32(1)] * 7
+    else:
+        stream.bg.state = stream.start
+        stream.bg.advance(plane)                       # two draws of `plane` floats = plane 64-bit outputs
+        g = np.random.Generator(stream.bg)
+        values = [np.float32(math.sqrt(-math.log(one - g.random(dtype=np.float32)))) for _ in specials]
+    for (i, j, k), v in zip(specials, values):
+        if y0 <= j < y0 + nyl:
+            out[i, j - y0, k] = v
+    if y0 == 0:
+        out[0, 0, 0] = 0
+    return out
+
+
+def get_transfer_grid_block(param, y0, nyl):
+    """get_transfer_grid for the block [:, y0:y0+nyl, :] (same float64 expressions element by element)"""
+    k, Pk = np.loadtxt(param["power_spectrum_file"]).T
+    N = int(round(param["npart"] ** (1.0 / 3)))
+    if param["npart"] != N ** 3:
+        raise ValueError(f"{math.cbrt(param['npart'])=}, should be integer")
+    kf = 2 * np.pi / param["boxlen"]
+    sqrtPk = (np.sqrt(Pk / param["boxlen"] ** 3) * N ** 3).astype(np.float32)
+    k_1d = np.fft.fftfreq(N, 1 / N)
+    kz = k_1d[: N // 2 + 1]
+    ky = k_1d[y0:y0 + nyl]
+    k_grid = np.sqrt(kz[np.newaxis, np.newaxis, :] ** 2 + k_1d[:, np.newaxis, np.newaxis] ** 2
+                     + ky[np.newaxis, :, np.newaxis] ** 2)
+    return np.interp(k_grid, k / kf, sqrtPk)
+
+
 def _periodic_wrap(x):
     """utils.periodic_wrap (utils.py:1120-1149) with torch ops (device-agnostic; the step's CUDA kernel does the same)"""
     eps = -2.98023223876953125e-08 * (1.0 + 1e-6)
@@ -113,6 +214,18 @@ def _periodic_wrap(x):
 
 def generate_density_fourier(param, device=None):
     """initial_conditions.py:402-445 -> device complex64 [N, N, N/2+1]"""
+    L = _layout()
+    if not L.whole:
+        # this rank's block [N, nyl, N/2+1] of the same spectrum (bit-identical to the slice of the full one)
+        seed = int(param["seed"])
+        if seed < 0:            # "random": every rank must still draw from the same stream
+            t = torch.tensor([float(np.random.default_rng().integers(0, 2 ** 24))],
+                             device=_lib.device() if device is None else device)
+            L.comm.allreduce_max_(t)
+            seed = int(t[0])
+        d = white_noise_fourier_block(L.N, seed, L.y0, L.nyl, bool(param["fixed_ICS"]), bool(param["paired_ICS"]))
+        d = (d * get_transfer_grid_block(param, L.y0, L.nyl)).astype(np.complex64)
+        return torch.from_numpy(np.ascontiguousarray(d)).to(_lib.device() if device is None else device)
     transfer = get_transfer_grid(param)
     N = transfer.shape[0]
     seed = param["seed"]
@@ -134,24 +247,103 @@ def _kvec(N, dev):
     return kfull, kz
 
 
+class _WholeLayout:
+    """One process holds the whole half-spectrum [N, N, N/2+1] and the whole real grid [N, N, N]."""
+    has_dc = True       # element [0, 0, 0] of a spectrum is the k = 0 mode
+    whole = True
+
+    def k_of(self, axis, N, dev):
+        kfull, kz = _kvec(N, dev)
+        if axis == 0:
+            return kfull[:, None, None]
+        if axis == 1:
+            return kfull[None, :, None]
+        return kz[None, None, :]
+
+    def fft(self, x):
+        return torch.fft.rfftn(x, dim=(0, 1, 2))
+
+    def ifft(self, x):
+        N = x.shape[0]
+        return torch.fft.irfftn(x, s=(N, N, N), dim=(0, 1, 2))
+
+
+class SlabLayout:
+    """The grids of an x-slab decomposition over the P ranks of `comm` (pysco_b200/slab.py): real fields are this
+    rank's planes [nxl, N, N] (x0 = rank nxl), spectra are TRANSPOSED blocks [N, nyl, N/2+1] -- all of kx, the y block
+    [y0, y0 + nyl) of ky, half of kz -- exactly the layout of Slab.fft_poisson.  The transforms are torch.fft along
+    (y, z) on the planes, one equal-size all-to-all, torch.fft along x (and back): one-off setup work, so library FFTs
+    and the comm's generic all-to-all rather than the peer-memory kernels of the time loop."""
+    whole = False
+
+    def __init__(self, comm, N):
+        self.comm, self.N, self.P, self.rank = comm, int(N), comm.size, comm.rank
+        if self.N % self.P:
+            raise ValueError(f"N = {N} planes cannot be split over {self.P} ranks")
+        self.nxl = self.nyl = self.N // self.P
+        self.x0 = self.y0 = self.rank * self.nxl
+        self.nz = self.N // 2 + 1
+        self.has_dc = self.rank == 0
+
+    def k_of(self, axis, N, dev):
+        kfull, kz = _kvec(N, dev)
+        if axis == 0:
+            return kfull[:, None, None]
+        if axis == 1:
+            return kfull[None, self.y0:self.y0 + self.nyl, None]
+        return kz[None, None, :]
+
+    def _all_to_all(self, send):
+        """send [P, ...] complex: block q goes to rank q; returns [P, ...] with block q received from rank q"""
+        a = torch.view_as_real(send.contiguous()).reshape(self.P, -1)
+        out = torch.empty_like(a)
+        self.comm.all_to_all_equal(a, out)
+        return torch.view_as_complex(out.reshape(tuple(send.shape) + (2,)))
+
+    def fft(self, x):
+        """real planes [nxl, N, N] -> transposed spectrum block [N, nyl, nz]"""
+        P, nxl, nyl, nz = self.P, self.nxl, self.nyl, self.nz
+        a = torch.fft.rfft2(x, dim=(1, 2))                                        # [nxl, N, nz]
+        a = a.reshape(nxl, P, nyl, nz).permute(1, 0, 2, 3)                        # [P (y block), nxl, nyl, nz]
+        b = self._all_to_all(a)                                                   # [P (x block), nxl, nyl, nz]
+        return torch.fft.fft(b.reshape(self.N, nyl, nz), dim=0)
+
+    def ifft(self, x):
+        """transposed spectrum block [N, nyl, nz] -> real planes [nxl, N, N]"""
+        P, nxl, nyl, nz, N = self.P, self.nxl, self.nyl, self.nz, self.N
+        a = torch.fft.ifft(x, dim=0).reshape(P, nxl, nyl, nz)                     # [P (x block), nxl, nyl, nz]
+        b = self._all_to_all(a)                                                   # [P (y block), nxl, nyl, nz]
+        b = b.permute(1, 0, 2, 3).reshape(nxl, N, nz)
+        return torch.fft.irfft2(b, s=(N, N), dim=(1, 2))
+
+
+_WHOLE = _WholeLayout()
+_tls = threading.local()     # the ranks of a ThreadComm are threads of one process: one layout per thread
+
+
+def _layout():
+    return getattr(_tls, "layout", _WHOLE)
+
+
 def _k_of(axis, N, dev):
-    kfull, kz = _kvec(N, dev)
-    if axis == 0:
-        return kfull[:, None, None]
-    if axis == 1:
-        return kfull[None, :, None]
-    return kz[None, None, :]
+    return _layout().k_of(axis, N, dev)
+
+
+def _k2(N, dev):
+    """kx^2 + ky^2 + kz^2 on the current layout, with the k = 0 mode (if this process holds it) set to 1"""
+    k2 = _k_of(0, N, dev) ** 2 + _k_of(1, N, dev) ** 2 + _k_of(2, N, dev) ** 2
+    if _layout().has_dc:
+        k2[0, 0, 0] = 1.0
+    return k2
 
 
 def inverse_laplacian(x):
     """fourier.inverse_laplacian (fourier.py:460-491) on a half-spectrum, in place"""
-    N = x.shape[0]
-    kfull, kz = _kvec(N, x.device)
-    k2 = kfull[:, None, None] ** 2 + kfull[None, :, None] ** 2 + kz[None, None, :] ** 2
+    k2 = _k2(x.shape[0], x.device)
     invpi2 = np.float32(-0.25 / np.pi ** 2)
-    k2[0, 0, 0] = 1.0
     x *= (invpi2 / k2)
-    x[0, 0, 0] = 0
+    if _layout().has_dc:
+        x[0, 0, 0] = 0
     return x
 
 
@@ -186,28 +378,30 @@ def gradient_inverse_laplacian(x):
     """fourier.gradient_inverse_laplacian (fourier.py:606-653): -i k_j / (2 pi k^2) x, DC = 0"""
     N = x.shape[0]
     dev = x.device
-    kfull, kz = _kvec(N, dev)
-    k2 = kfull[:, None, None] ** 2 + kfull[None, :, None] ** 2 + kz[None, None, :] ** 2
-    k2[0, 0, 0] = 1.0
+    k2 = _k2(N, dev)
     invtwopi = np.float32(0.5 / np.pi)
     tmp = x * torch.complex(torch.zeros((), device=dev), -(invtwopi / k2))
     out = torch.stack([tmp * _k_of(a, N, dev) for a in range(3)], dim=-1)
-    out[0, 0, 0, :] = 0
+    if _layout().has_dc:
+        out[0, 0, 0, :] = 0
     return out
 
 
 def ifft_3D_real(x):
-    N = x.shape[0]
-    return torch.fft.irfftn(x, s=(N, N, N), dim=(0, 1, 2))
+    return _layout().ifft(x)
 
 
 def fft_3D_real(x):
-    return torch.fft.rfftn(x, dim=(0, 1, 2))
+    return _layout().fft(x)
 
 
 def ifft_3D_real_grad(x):
-    N = x.shape[0]
-    return torch.fft.irfftn(x, s=(N, N, N), dim=(0, 1, 2)).contiguous()
+    """the three components of a spectral vector field [..., 3] -> real [..., 3]"""
+    L = _layout()
+    if L.whole:
+        N = x.shape[0]
+        return torch.fft.irfftn(x, s=(N, N, N), dim=(0, 1, 2)).contiguous()
+    return torch.stack([L.ifft(x[..., c]) for c in range(3)], dim=-1)
 
 
 def pad(x):
@@ -240,6 +434,8 @@ def _real(x, ij):
 
 
 def _dealias_in(param, *fields):
+    if param["dealiased_ICS"] and not _layout().whole:
+        raise NotImplementedError("dealiased_ICS on x-slabs (the 3/2-rule padding re-blocks the spectrum)")
     return [pad(f) for f in fields] if param["dealiased_ICS"] else list(fields)
 
 
@@ -320,11 +516,13 @@ def initialise_1LPT(psi, dplus_1, fH, param):
     POSITION = param["position_ICS"].casefold()
     if POSITION not in ("center", "edge"):
         raise NotImplementedError(f"{POSITION=}, should be 'center' or 'edge'")
-    N = psi.shape[0]
+    N = psi.shape[1]
     h = np.float32(1.0 / N)
     half_h = np.float32(0.5 / N) if POSITION == "center" else np.float32(0)
     ax = half_h + torch.arange(N, device=psi.device, dtype=torch.float32) * h
-    grid = torch.stack(torch.meshgrid(ax, ax, ax, indexing="ij"), dim=-1)
+    L = _layout()
+    axx = ax if L.whole else ax[L.x0:L.x0 + L.nxl]       # x-slab: the lattice planes this rank owns
+    grid = torch.stack(torch.meshgrid(axx, ax, ax, indexing="ij"), dim=-1)
     dfH = np.float32(dplus_1 * fH)
     position = grid + np.float32(dplus_1) * (-psi)
     velocity = dfH * (-psi)
@@ -385,8 +583,8 @@ def generate(param, tables, write_snapshot=True, device=None):
     del psi1
 
     def done():
-        pos = position.reshape(param["npart"], 3).contiguous()
-        vel = velocity.reshape(param["npart"], 3).contiguous()
+        pos = position.reshape(-1, 3).contiguous()
+        vel = velocity.reshape(-1, 3).contiguous()
         if write_snapshot:
             finalise_initial_conditions(pos, vel, param, do_reorder=False)
         else:
@@ -416,3 +614,25 @@ def generate(param, tables, write_snapshot=True, device=None):
     for rhs in (compute_3c_Ax_rhs, compute_3c_Ay_rhs, compute_3c_Az_rhs):
         add_nLPT(position, velocity, _displacement(rhs(phi1, phi2, param)), dplus_3c, fH_3c)
     return done()
+
+
+def generate_slab(param, tables, comm, device=None):
+    """generate() for an x-slab run (SURVEY 8f rank 1 at the sizes of BASELINE config 5): every rank produces only
+    the particles of its own lattice planes [x0, x0 + N/P) -- its y block of the white noise (bit-identical to the
+    reference's draw, white_noise_fourier_block), the LPT chain on transposed spectrum blocks / real planes with the
+    distributed transforms of SlabLayout -- so no rank ever holds a global array.  One call per rank of `comm`
+    (collective).  Returns (position [n, 3], velocity [n, 3], ids [n] int64): wrapped positions, ids = the particle's
+    row in the reference's lexicographic lattice order.  A displaced particle may lie outside the slab:
+    Slab.set_particles routes it to its owner.  dealiased_ICS raises (use the replicated path, slab_ics = replicated)."""
+    N = int(round(param["npart"] ** (1.0 / 3)))
+    if param["npart"] != N ** 3:
+        raise ValueError(f"{math.cbrt(param['npart'])=}, should be integer")
+    L = SlabLayout(comm, N)
+    _tls.layout = L
+    try:
+        pos, vel = generate(param, tables, write_snapshot=False, device=device)
+    finally:
+        del _tls.layout
+    n = pos.shape[0]
+    ids = torch.arange(n, dtype=torch.int64, device=pos.device) + L.x0 * N * N
+    return pos, vel, ids
