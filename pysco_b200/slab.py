@@ -1373,13 +1373,24 @@ class Slab:
 
 
 # ------------------------------------------------------------------------------------------ main.run on slabs
+def _ics_per_slab(param, comm):
+    """param['slab_ics']: 'slab' = every rank generates its own planes (initial_conditions.generate_slab), 'replicated'
+    = every rank generates the whole set and adopts a share (meshes that fit one GPU; the only path for
+    dealiased_ICS), 'auto' (default) = per slab on more than one rank unless dealiased"""
+    how = str(param["slab_ics"]).casefold() if "slab_ics" in param.index else "auto"
+    if how not in ("auto", "slab", "replicated"):
+        raise NotImplementedError(f"{param['slab_ics']=}, should be 'slab', 'replicated' or 'auto'")
+    return how == "slab" or (how == "auto" and comm.size > 1 and not bool(param["dealiased_ICS"]))
+
+
 def run(param, comm=None, initial_state=None, ops_factory=None):
     """`main.run` (main.py:30-156) on x-slabs: one call per rank (torchrun; or one thread per virtual rank with a
     ThreadComm).  Every rank derives the same background tables; the initial particles come from `initial_state`
     (global arrays, identical on every rank), from a snapshot number (`initial_conditions = i`: restart, every rank
-    reads its own share of the files -- initial_conditions.py:79-107) or are generated identically on every rank
-    (initial_conditions.generate: meshes that fit one GPU) -- each rank adopts a share and the first migration routes
-    the particles to their slabs.  Snapshots: `slab_snapshots = gather` (default up to 256^3 particles) collects them
+    reads its own share of the files -- initial_conditions.py:79-107) or are generated from the parameter file: per slab
+    (initial_conditions.generate_slab, every rank its own lattice planes: `slab_ics`, see _ics_per_slab) or identically
+    on every rank (initial_conditions.generate: meshes that fit one GPU) -- each rank adopts its particles or a share
+    and the first migration routes them to their slabs.  Snapshots: `slab_snapshots = gather` (default up to 256^3 particles) collects them
     on rank 0 in the reference's particle order and file layout; `slab_snapshots = parts` (default above) lets every
     rank write its own slab (iostream.write_snapshot_slab_part), so that no rank ever holds the global arrays.
     Theories and solvers: what Slab.pm
@@ -1426,6 +1437,7 @@ def run(param, comm=None, initial_state=None, ops_factory=None):
     S = Slab(N, comm=comm, ops=None if ops_factory is None else ops_factory(N, comm.size, comm.rank))
     dev = S._device()
     ic = param["initial_conditions"] if "initial_conditions" in param.index else None
+    ics_snapshot = False
     if initial_state is None and isinstance(ic, (int, np.integer)):
         # restart: every saved parameter comes back (as main._initial_state), every rank reads its own share
         base = param["base"] if root else base_dir
@@ -1440,10 +1452,21 @@ def run(param, comm=None, initial_state=None, ops_factory=None):
         npart = int(param["npart"])
         S.set_particles(torch.from_numpy(p_).to(dev), torch.from_numpy(v_).to(dev), torch.from_numpy(i_).to(dev))
         del p_, v_, i_
+    elif initial_state is None and _ics_per_slab(param, comm):
+        # every rank generates the particles of its own lattice planes (initial_conditions.generate_slab): no rank
+        # holds a global array, the white noise is the reference's, block by block
+        from . import initial_conditions
+        p_, v_, i_ = initial_conditions.generate_slab(param, tables, comm, device=dev)
+        utils.set_units(param)
+        param["t"] = tables[1](np.log(param["aexp"]))
+        npart = int(param["npart"])
+        S.set_particles(p_, v_, i_)
+        del p_, v_, i_
+        ics_snapshot = True
     else:
         if initial_state is None:
             from . import initial_conditions
-            position, velocity = initial_conditions.generate(param, tables, write_snapshot=root)
+            position, velocity = initial_conditions.generate(param, tables, write_snapshot=root, device=dev)
         else:
             position, velocity = initial_state
         utils.set_units(param)
@@ -1471,6 +1494,20 @@ def run(param, comm=None, initial_state=None, ops_factory=None):
             state = S.gather_to_root(npart)
             if root:
                 iostream.write_snapshot_particles(state[0], state[1], param)
+    if ics_snapshot:
+        # the initial snapshot (initial_conditions.py:216-280), which the replicated generator writes itself
+        if parts_mode:
+            p = param.copy()
+            p["base"], p["i_snap"] = base_dir, 0
+            iostream.write_snapshot_slab_part(S.pos[:S.np], S.vel[:S.np], S.ids[:S.np], p, comm.rank, False)
+            comm.barrier()
+        else:
+            state = S.gather_to_root(npart)
+            if root:
+                iostream.write_snapshot_particles_parquet(
+                    f"{param['base']}/output_00000/particles_{param['extra']}.parquet", state[0], state[1])
+        if root:
+            param.to_csv(f"{param['base']}/output_00000/param_{param['extra']}.txt", sep="=", header=False)
     S.pm(param, tables=tables)
     aexp_out = np.sort(1.0 / (np.array(z_out) + 1))
     t_out = tables[1](np.log(aexp_out))

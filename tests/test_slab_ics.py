@@ -137,3 +137,111 @@ def test_generate_slab_dealiased_raises(tmp_path):
     with pytest.raises(NotImplementedError):
         ic.generate_slab(param, _tables_of("lpt3_dealiased"), SelfComm(), device="cpu")
     assert ic._layout() is ic._WHOLE
+
+
+def _run_slab(base, how, P, **over):
+    from pysco_b200 import slab
+    from slab_oracle_ops import OracleOps
+    os.makedirs(base, exist_ok=True)
+    pk = cases.ic_pk_file(base)
+    out, errs = {}, []
+
+    def work(c):
+        try:
+            param = cases.run_param(base + "/", "fft", ncoarse=4)
+            param.update(power_spectrum_file=pk, z_out="[30, 0]", save_power_spectrum="no", slab_ics=how)
+            param.update(over)
+            res = slab.run(param, comm=c, ops_factory=OracleOps)
+            out[c.rank] = res
+        except BaseException as e:  # noqa: BLE001
+            errs.append(e)
+            c.w.barrier.abort()
+    ts = [threading.Thread(target=work, args=(c,)) for c in slab.ThreadComm.world(P)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    if errs:
+        raise errs[0]
+    return out
+
+
+def test_slab_run_generates_its_initial_conditions_per_slab(tmp_path):
+    """slab.run from a parameter file on 2 virtual ranks (oracle kernels): per-slab generation (the default on more
+    than one rank) against the replicated generator -- same initial snapshot, same final particles"""
+    import glob
+    import pyarrow.parquet as pq
+    a = _run_slab(str(tmp_path / "slab"), "auto", 2)
+    b = _run_slab(str(tmp_path / "repl"), "replicated", 2)
+    ics = []
+    for d in ("slab", "repl"):
+        f = glob.glob(str(tmp_path / d / "output_00000" / "particles_*.parquet"))
+        assert len(f) == 1 and glob.glob(str(tmp_path / d / "output_00000" / "param_*.txt"))
+        t = pq.read_table(f[0])
+        ics.append(np.stack([np.asarray(t.column(c)) for c in ("x", "y", "z", "vx", "vy", "vz")], axis=1))
+    dx = np.abs(ics[0][:, :3] - ics[1][:, :3])
+    assert np.minimum(dx, 1 - dx).max() < 2e-6
+    assert np.abs(ics[0][:, 3:] - ics[1][:, 3:]).max() < 2e-5 * np.abs(ics[1][:, 3:]).max()
+    pa, va = (t.numpy() for t in a[0])
+    pb, vb = (t.numpy() for t in b[0])
+    d = np.abs(pa - pb)
+    assert np.minimum(d, 1 - d).max() < 2e-5
+    assert np.abs(va - vb).max() < 1e-4 * np.abs(vb).max()
+    assert len(glob.glob(str(tmp_path / "slab" / "output_0000[12]" / "particles_*.parquet"))) == 2
+
+
+def test_slab_run_per_slab_ics_in_parts(tmp_path):
+    """slab_snapshots = parts: the initial snapshot is written slab by slab as well; together the parts hold every
+    lattice particle exactly once"""
+    import glob
+    from pysco_b200 import iostream
+    out = _run_slab(str(tmp_path / "parts"), "slab", 2, slab_snapshots="parts")
+    assert sorted(out) == [0, 1] and all(len(o) == 3 for o in out.values())
+    d = glob.glob(str(tmp_path / "parts" / "output_00000" / "particles_*.parquet"))
+    assert len(d) == 1 and len(glob.glob(d[0] + "/part-*.parquet")) == 2
+    ids = np.concatenate([iostream.read_snapshot_slab_parts(d[0], r, 2)[2] for r in range(2)])
+    assert np.array_equal(np.sort(ids), np.arange(16 ** 3))
+
+
+def test_slab_ics_switch_is_validated(tmp_path):
+    from pysco_b200 import slab
+    import pandas as pd
+    p = pd.Series({"slab_ics": "sometimes", "dealiased_ICS": False})
+    with pytest.raises(NotImplementedError):
+        slab._ics_per_slab(p, slab.SelfComm())
+    assert not slab._ics_per_slab(pd.Series({"dealiased_ICS": False}), slab.SelfComm())
+    comms = slab.ThreadComm.world(2)
+    assert slab._ics_per_slab(pd.Series({"dealiased_ICS": False}), comms[0])
+    assert not slab._ics_per_slab(pd.Series({"dealiased_ICS": True}), comms[0])
+
+
+def _gloo_ics_worker(rank, world, port, base, name, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    for p in (ROOT, os.path.join(ROOT, "tests"), os.path.join(ROOT, "tests", "golden")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    import pathlib
+    import torch.distributed as dist
+    from pysco_b200 import distributed, initial_conditions as ic, slab
+    distributed.init_from_env("gloo")
+    comm = slab.default_comm()
+    assert isinstance(comm, slab.TorchComm) and comm.size == world
+    sub = pathlib.Path(base) / f"rank{rank}"          # every process writes its own copy of the P(k) table
+    sub.mkdir(parents=True, exist_ok=True)
+    pos, vel, ids = ic.generate_slab(_param_of(name, sub), _tables_of(name), comm, device="cpu")
+    out[rank] = (pos.numpy(), vel.numpy(), ids.numpy())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_generate_slab_gloo_world2(tmp_path):
+    """the same over torch.distributed (gloo, two processes): the transposes go through all_to_all_single"""
+    import socket
+    import torch.multiprocessing as mp
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    with mp.Manager() as mgr:
+        out = mgr.dict()
+        mp.spawn(_gloo_ics_worker, args=(2, port, str(tmp_path), "lpt2", out), nprocs=2, join=True)
+        out = dict(out)
+    _check_against_reference("lpt2", [out[0], out[1]])
