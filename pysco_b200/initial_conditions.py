@@ -189,8 +189,8 @@ def white_noise_fourier_block(N, seed, y0, nyl, fixed=False, paired=False):
     return out
 
 
-def get_transfer_grid_block(param, y0, nyl):
-    """get_transfer_grid for the block [:, y0:y0+nyl, :] (same float64 expressions element by element)"""
+def get_transfer_grid_block(param, y0, nyl, x0=0, nx=None):
+    """get_transfer_grid for the block [x0:x0+nx, y0:y0+nyl, :] (same float64 expressions element by element)"""
     k, Pk = np.loadtxt(param["power_spectrum_file"]).T
     N = int(round(param["npart"] ** (1.0 / 3)))
     if param["npart"] != N ** 3:
@@ -200,7 +200,8 @@ def get_transfer_grid_block(param, y0, nyl):
     k_1d = np.fft.fftfreq(N, 1 / N)
     kz = k_1d[: N // 2 + 1]
     ky = k_1d[y0:y0 + nyl]
-    k_grid = np.sqrt(kz[np.newaxis, np.newaxis, :] ** 2 + k_1d[:, np.newaxis, np.newaxis] ** 2
+    kx = k_1d[x0:N if nx is None else x0 + nx]
+    k_grid = np.sqrt(kz[np.newaxis, np.newaxis, :] ** 2 + kx[:, np.newaxis, np.newaxis] ** 2
                      + ky[np.newaxis, :, np.newaxis] ** 2)
     return np.interp(k_grid, k / kf, sqrtPk)
 
@@ -224,7 +225,10 @@ def generate_density_fourier(param, device=None):
             L.comm.allreduce_max_(t)
             seed = int(t[0])
         d = white_noise_fourier_block(L.N, seed, L.y0, L.nyl, bool(param["fixed_ICS"]), bool(param["paired_ICS"]))
-        d = (d * get_transfer_grid_block(param, L.y0, L.nyl)).astype(np.complex64)
+        step = max(1, (1 << 22) // (L.nyl * L.nz))     # kx planes per chunk: float64 temporaries of ~32 MB
+        for a in range(0, L.N, step):
+            b = min(L.N, a + step)
+            d[a:b] = (d[a:b] * get_transfer_grid_block(param, L.y0, L.nyl, a, b - a)).astype(np.complex64)
         return torch.from_numpy(np.ascontiguousarray(d)).to(_lib.device() if device is None else device)
     transfer = get_transfer_grid(param)
     N = transfer.shape[0]

@@ -139,16 +139,18 @@ def test_generate_slab_dealiased_raises(tmp_path):
     assert ic._layout() is ic._WHOLE
 
 
-def _run_slab(base, how, P, **over):
+def _run_slab(base, how, P, cuda=False, ncoarse=4, **over):
     from pysco_b200 import slab
-    from slab_oracle_ops import OracleOps
+    OracleOps = None
+    if not cuda:
+        from slab_oracle_ops import OracleOps
     os.makedirs(base, exist_ok=True)
     pk = cases.ic_pk_file(base)
     out, errs = {}, []
 
     def work(c):
         try:
-            param = cases.run_param(base + "/", "fft", ncoarse=4)
+            param = cases.run_param(base + "/", "fft", ncoarse=ncoarse)
             param.update(power_spectrum_file=pk, z_out="[30, 0]", save_power_spectrum="no", slab_ics=how)
             param.update(over)
             res = slab.run(param, comm=c, ops_factory=OracleOps)
@@ -245,3 +247,41 @@ def test_generate_slab_gloo_world2(tmp_path):
         mp.spawn(_gloo_ics_worker, args=(2, port, str(tmp_path), "lpt2", out), nprocs=2, join=True)
         out = dict(out)
     _check_against_reference("lpt2", [out[0], out[1]])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["lpt2", "lpt3"])
+def test_generate_slab_matches_reference_gpu(name, tmp_path):
+    """the per-slab generator on CUDA tensors (cuFFT through torch.fft), 2 virtual ranks sharing cuda:0"""
+    from pysco_b200 import initial_conditions as ic
+    from pysco_b200.slab import ThreadComm
+    out, errs = {}, []
+    param0 = _param_of(name, tmp_path)
+
+    def rank(comm):
+        try:
+            pos, vel, ids = ic.generate_slab(param0.copy(), _tables_of(name), comm)
+            assert pos.is_cuda
+            out[comm.rank] = (pos.cpu().numpy(), vel.cpu().numpy(), ids.cpu().numpy())
+        except BaseException as e:  # noqa: BLE001
+            errs.append(e)
+            comm.w.barrier.abort()
+    ts = [threading.Thread(target=rank, args=(c,)) for c in ThreadComm.world(2)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    if errs:
+        raise errs[0]
+    _check_against_reference(name, [out[0], out[1]])
+
+
+@pytest.mark.gpu
+def test_slab_run_per_slab_ics_gpu(tmp_path):
+    """slab.run from a parameter file with the CUDA kernels on 2 virtual ranks at 32^3, z = 49 -> 0: initial
+    conditions generated per slab against the replicated generator"""
+    a = _run_slab(str(tmp_path / "slab"), "auto", 2, cuda=True, ncoarse=5)
+    b = _run_slab(str(tmp_path / "repl"), "replicated", 2, cuda=True, ncoarse=5)
+    pa, va = (t.numpy() for t in a[0])
+    pb, vb = (t.numpy() for t in b[0])
+    d = np.abs(pa - pb)
+    assert np.minimum(d, 1 - d).max() < 5e-5, np.minimum(d, 1 - d).max()
+    assert np.abs(va - vb).max() < 5e-4 * np.abs(vb).max()
