@@ -149,7 +149,16 @@ def main():
     param = iostream.read_param_file(args.config_file)
     print(param)
     t_start = perf_counter()
-    run(param)
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        # launched by torchrun, one process per GPU: the same run on x-slabs (pysco_b200/slab.py)
+        import torch.distributed as dist
+        from . import distributed, slab
+        distributed.init_from_env()
+        slab.run(param)
+        dist.barrier()
+        dist.destroy_process_group()
+    else:
+        run(param)
     print(f"Simulation run time: {perf_counter() - t_start} seconds.")
 
 

@@ -285,3 +285,25 @@ def test_slab_run_per_slab_ics_gpu(tmp_path):
     d = np.abs(pa - pb)
     assert np.minimum(d, 1 - d).max() < 5e-5, np.minimum(d, 1 - d).max()
     assert np.abs(va - vb).max() < 5e-4 * np.abs(vb).max()
+
+
+def test_command_line_runs_on_slabs_under_torchrun(tmp_path, monkeypatch):
+    """`torchrun -m pysco_b200.main -c param.ini`: with WORLD_SIZE > 1 the command line hands the run to slab.run"""
+    import torch.distributed as dist
+    from pysco_b200 import distributed, main, slab
+    cfg = tmp_path / "param.ini"
+    cfg.write_text("theory = newton\nnpart = 4096\nncoarse = 4\n")
+    called = {}
+    monkeypatch.setenv("WORLD_SIZE", "2")
+    monkeypatch.setattr(sys, "argv", ["pysco_b200", "-c", str(cfg)])
+    monkeypatch.setattr(distributed, "init_from_env", lambda backend=None: called.setdefault("init", True))
+    monkeypatch.setattr(slab, "run", lambda param, **kw: called.setdefault("param", param))
+    monkeypatch.setattr(main, "run", lambda param: called.setdefault("single", True))
+    monkeypatch.setattr(dist, "barrier", lambda *a, **k: None)
+    monkeypatch.setattr(dist, "destroy_process_group", lambda *a, **k: None)
+    main.main()
+    assert called.get("init") and "single" not in called and int(called["param"]["ncoarse"]) == 4
+    called.clear()
+    monkeypatch.setenv("WORLD_SIZE", "1")
+    main.main()
+    assert called == {"single": True}
