@@ -290,11 +290,13 @@ class SlabLayout:
         self.has_dc = self.rank == 0
 
     def k_of(self, axis, N, dev):
+        """N: the grid the spectrum belongs to (the particle grid or its 3/2 dealiasing grid)"""
         kfull, kz = _kvec(N, dev)
         if axis == 0:
             return kfull[:, None, None]
         if axis == 1:
-            return kfull[None, self.y0:self.y0 + self.nyl, None]
+            nyl = N // self.P
+            return kfull[None, self.rank * nyl:(self.rank + 1) * nyl, None]
         return kz[None, None, :]
 
     def _all_to_all(self, send):
@@ -305,20 +307,63 @@ class SlabLayout:
         return torch.view_as_complex(out.reshape(tuple(send.shape) + (2,)))
 
     def fft(self, x):
-        """real planes [nxl, N, N] -> transposed spectrum block [N, nyl, nz]"""
-        P, nxl, nyl, nz = self.P, self.nxl, self.nyl, self.nz
-        a = torch.fft.rfft2(x, dim=(1, 2))                                        # [nxl, N, nz]
+        """real planes [n/P, n, n] -> transposed spectrum block [n, n/P, n/2+1] (n: any grid divisible by P)"""
+        P, nxl, n = self.P, x.shape[0], x.shape[1]
+        nyl, nz = n // P, n // 2 + 1
+        a = torch.fft.rfft2(x, dim=(1, 2))                                        # [nxl, n, nz]
         a = a.reshape(nxl, P, nyl, nz).permute(1, 0, 2, 3)                        # [P (y block), nxl, nyl, nz]
         b = self._all_to_all(a)                                                   # [P (x block), nxl, nyl, nz]
-        return torch.fft.fft(b.reshape(self.N, nyl, nz), dim=0)
+        return torch.fft.fft(b.reshape(n, nyl, nz), dim=0)
 
     def ifft(self, x):
-        """transposed spectrum block [N, nyl, nz] -> real planes [nxl, N, N]"""
-        P, nxl, nyl, nz, N = self.P, self.nxl, self.nyl, self.nz, self.N
+        """transposed spectrum block [n, n/P, n/2+1] -> real planes [n/P, n, n]"""
+        P, n, nyl, nz = self.P, x.shape[0], x.shape[1], x.shape[2]
+        nxl = n // P
         a = torch.fft.ifft(x, dim=0).reshape(P, nxl, nyl, nz)                     # [P (x block), nxl, nyl, nz]
         b = self._all_to_all(a)                                                   # [P (y block), nxl, nyl, nz]
-        b = b.permute(1, 0, 2, 3).reshape(nxl, N, nz)
-        return torch.fft.irfft2(b, s=(N, N), dim=(1, 2))
+        b = b.permute(1, 0, 2, 3).reshape(nxl, n, nz)
+        return torch.fft.irfft2(b, s=(n, n), dim=(1, 2))
+
+    def regrid(self, x, n_to):
+        """pad (n_to = 3 n / 2) or trim (n_to = 2 n / 3) of a transposed spectrum block (initial_conditions.py:1858-1927,
+        the Orszag 3/2 rule): the modes |k| < m = min(n, n_to) / 2 of every axis keep their signed wave numbers on
+        the other grid, the rest is zero.  Along x and z that is local index arithmetic; the ky rows change owner
+        (the y blocks of the two grids differ): one all-to-all-v of rows.  The mapping of kept rows is monotonic, so
+        the rows a rank sends to each destination, and receives from each source, are contiguous and in order."""
+        P, r = self.P, self.rank
+        n, nyl = x.shape[0], x.shape[1]
+        if n_to % P or (n_to // P) * P != n_to:
+            raise ValueError(f"dealiasing grid {n_to} cannot be split over {P} ranks")
+        m = min(n, n_to) // 2
+        nyl_to, nz_to = n_to // P, n_to // 2 + 1
+        dev = x.device
+
+        def kept(lo, hi, size):
+            """indices in [lo, hi) of a `size` grid that hold a kept mode, and the same modes' indices on the other
+            grid (index < m: as is; index > size - m: from the end)"""
+            idx = torch.arange(lo, hi, device=dev)
+            keep = (idx < m) | (idx > size - m)
+            idx = idx[keep]
+            other = n_to if size == n else n
+            return idx, torch.where(idx < m, idx, idx + (other - size))
+        # x and z: local
+        xi, xo = kept(0, n, n)
+        rows_here, rows_there = kept(r * nyl, (r + 1) * nyl, n)                  # my ky rows that survive, their new index
+        part = torch.zeros((len(rows_here), n_to, nz_to), dtype=x.dtype, device=dev)
+        src = x[:, rows_here - r * nyl, :m].permute(1, 0, 2)                     # [rows, n, m]
+        part[:, xo, :m] = src[:, xi, :]
+        dest = torch.div(rows_there, nyl_to, rounding_mode="floor")
+        send_counts = [int((dest == q).sum()) for q in range(P)]
+        recv_counts = self.comm.exchange_counts(send_counts)
+        flat = torch.view_as_real(part.contiguous()).reshape(len(rows_here), -1)
+        got = self.comm.all_to_all_v(flat, send_counts, recv_counts)
+        got = torch.view_as_complex(got.reshape(-1, n_to, nz_to, 2).contiguous())
+        # the rows I now own, in the order they arrive (ascending on the new grid)
+        mine, _ = kept(r * nyl_to, (r + 1) * nyl_to, n_to)
+        assert got.shape[0] == len(mine), (got.shape, len(mine))
+        out = torch.zeros((n_to, nyl_to, nz_to), dtype=x.dtype, device=dev)
+        out[:, mine - r * nyl_to, :] = got.permute(1, 0, 2)
+        return out
 
 
 _WHOLE = _WholeLayout()
@@ -411,6 +456,8 @@ def ifft_3D_real_grad(x):
 def pad(x):
     """initial_conditions.py:1859-1893 (Orszag 3/2 rule)"""
     N = x.shape[0]
+    if not _layout().whole:
+        return _layout().regrid(x, 3 * N // 2)
     Ne, m = 3 * N // 2, N // 2
     out = torch.zeros((Ne, Ne, Ne // 2 + 1), dtype=x.dtype, device=x.device)
     out[:m, :m, :m] = x[:m, :m, :m]
@@ -424,6 +471,8 @@ def trim(x):
     """initial_conditions.py:1897-1927"""
     Ne = x.shape[0]
     N = 2 * Ne // 3
+    if not _layout().whole:
+        return _layout().regrid(x, N)
     m = N // 2
     out = torch.zeros((N, N, m + 1), dtype=x.dtype, device=x.device)
     out[:m, :m, :m] = x[:m, :m, :m]
@@ -438,8 +487,9 @@ def _real(x, ij):
 
 
 def _dealias_in(param, *fields):
-    if param["dealiased_ICS"] and not _layout().whole:
-        raise NotImplementedError("dealiased_ICS on x-slabs (the 3/2-rule padding re-blocks the spectrum)")
+    L = _layout()
+    if param["dealiased_ICS"] and not L.whole and (3 * L.N // 2) % L.P:
+        raise NotImplementedError(f"dealiased_ICS on x-slabs: the 3/2 grid {3 * L.N // 2} must split over {L.P} ranks")
     return [pad(f) for f in fields] if param["dealiased_ICS"] else list(fields)
 
 
@@ -627,7 +677,7 @@ def generate_slab(param, tables, comm, device=None):
     distributed transforms of SlabLayout -- so no rank ever holds a global array.  One call per rank of `comm`
     (collective).  Returns (position [n, 3], velocity [n, 3], ids [n] int64): wrapped positions, ids = the particle's
     row in the reference's lexicographic lattice order.  A displaced particle may lie outside the slab:
-    Slab.set_particles routes it to its owner.  dealiased_ICS raises (use the replicated path, slab_ics = replicated)."""
+    Slab.set_particles routes it to its owner.  dealiased_ICS: the 3/2 grid must split over the ranks too (SlabLayout.regrid)."""
     N = int(round(param["npart"] ** (1.0 / 3)))
     if param["npart"] != N ** 3:
         raise ValueError(f"{math.cbrt(param['npart'])=}, should be integer")

@@ -1375,12 +1375,19 @@ class Slab:
 # ------------------------------------------------------------------------------------------ main.run on slabs
 def _ics_per_slab(param, comm):
     """param['slab_ics']: 'slab' = every rank generates its own planes (initial_conditions.generate_slab), 'replicated'
-    = every rank generates the whole set and adopts a share (meshes that fit one GPU; the only path for
-    dealiased_ICS), 'auto' (default) = per slab on more than one rank unless dealiased"""
+    = every rank generates the whole set and adopts a share (meshes that fit one GPU), 'auto' (default) = per slab on
+    more than one rank (with dealiased_ICS only when the 3/2 dealiasing grid splits over the ranks as well)"""
     how = str(param["slab_ics"]).casefold() if "slab_ics" in param.index else "auto"
     if how not in ("auto", "slab", "replicated"):
         raise NotImplementedError(f"{param['slab_ics']=}, should be 'slab', 'replicated' or 'auto'")
-    return how == "slab" or (how == "auto" and comm.size > 1 and not bool(param["dealiased_ICS"]))
+    if how != "auto":
+        return how == "slab"
+    if comm.size == 1:
+        return False
+    if bool(param["dealiased_ICS"]):
+        n = int(round(float(param["npart"]) ** (1.0 / 3)))
+        return (3 * n // 2) % comm.size == 0
+    return True
 
 
 def run(param, comm=None, initial_state=None, ops_factory=None):

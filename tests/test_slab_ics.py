@@ -104,7 +104,7 @@ def _check_against_reference(name, parts):
 
 
 @pytest.mark.parametrize("P", [1, 2, 4])
-@pytest.mark.parametrize("name", ["lpt1_edge", "lpt2", "lpt3", "lpt2_fixed_paired"])
+@pytest.mark.parametrize("name", ["lpt1_edge", "lpt2", "lpt3", "lpt2_fixed_paired", "lpt3_dealiased"])
 def test_generate_slab_matches_reference(name, P, tmp_path):
     from pysco_b200 import initial_conditions as ic
     from pysco_b200.slab import ThreadComm
@@ -130,12 +130,57 @@ def test_generate_slab_matches_reference(name, P, tmp_path):
     assert ic._layout() is ic._WHOLE
 
 
-def test_generate_slab_dealiased_raises(tmp_path):
+@pytest.mark.parametrize("P", [1, 2, 4])
+def test_slab_pad_and_trim_match_the_whole_grid(P):
+    """the 3/2-rule regridding of transposed blocks (ky rows change owner) against initial_conditions.pad / trim"""
     from pysco_b200 import initial_conditions as ic
-    from pysco_b200.slab import SelfComm
+    from pysco_b200.slab import ThreadComm
+    N = 16
+    rng = np.random.default_rng(4)
+    x = torch.from_numpy((rng.standard_normal((N, N, N // 2 + 1)) + 1j * rng.standard_normal((N, N, N // 2 + 1)))
+                         .astype(np.complex64))
+    big = ic.pad(x)
+    Ne = big.shape[0]
+    y = torch.from_numpy((rng.standard_normal(tuple(big.shape)) + 1j * rng.standard_normal(tuple(big.shape)))
+                         .astype(np.complex64))
+    small = ic.trim(y)
+    out, errs = {}, []
+
+    def rank(comm):
+        try:
+            L = ic.SlabLayout(comm, N)
+            r, nyl, nye = comm.rank, N // P, Ne // P
+            out[r] = (L.regrid(x[:, r * nyl:(r + 1) * nyl].clone(), Ne), L.regrid(y[:, r * nye:(r + 1) * nye].clone(), N))
+        except BaseException as e:  # noqa: BLE001
+            errs.append(e)
+            comm.w.barrier.abort()
+    ts = [threading.Thread(target=rank, args=(c,)) for c in ThreadComm.world(P)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    if errs:
+        raise errs[0]
+    for r in range(P):
+        assert torch.equal(out[r][0], big[:, r * (Ne // P):(r + 1) * (Ne // P)])
+        assert torch.equal(out[r][1], small[:, r * (N // P):(r + 1) * (N // P)])
+
+
+def test_generate_slab_dealiased_needs_a_divisible_grid(tmp_path):
+    """3 N / 2 = 24 planes do not split over 16 ranks: NotImplementedError (slab_ics = replicated is the way then)"""
+    from pysco_b200 import initial_conditions as ic
+    from pysco_b200.slab import ThreadComm
     param = _param_of("lpt3_dealiased", tmp_path)
-    with pytest.raises(NotImplementedError):
-        ic.generate_slab(param, _tables_of("lpt3_dealiased"), SelfComm(), device="cpu")
+    errs = []
+
+    def rank(comm):
+        try:
+            ic.generate_slab(param.copy(), _tables_of("lpt3_dealiased"), comm, device="cpu")
+        except BaseException as e:  # noqa: BLE001
+            errs.append(e)
+            comm.w.barrier.abort()
+    ts = [threading.Thread(target=rank, args=(c,)) for c in ThreadComm.world(16)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    assert any(isinstance(e, NotImplementedError) for e in errs)
     assert ic._layout() is ic._WHOLE
 
 
@@ -212,7 +257,9 @@ def test_slab_ics_switch_is_validated(tmp_path):
     assert not slab._ics_per_slab(pd.Series({"dealiased_ICS": False}), slab.SelfComm())
     comms = slab.ThreadComm.world(2)
     assert slab._ics_per_slab(pd.Series({"dealiased_ICS": False}), comms[0])
-    assert not slab._ics_per_slab(pd.Series({"dealiased_ICS": True}), comms[0])
+    assert slab._ics_per_slab(pd.Series({"dealiased_ICS": True, "npart": 16 ** 3}), comms[0])
+    assert not slab._ics_per_slab(pd.Series({"dealiased_ICS": True, "npart": 16 ** 3}), slab.ThreadComm.world(16)[0])
+    assert not slab._ics_per_slab(pd.Series({"dealiased_ICS": True, "npart": 16 ** 3, "slab_ics": "replicated"}), comms[0])
 
 
 def _gloo_ics_worker(rank, world, port, base, name, out):
