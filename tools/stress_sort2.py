@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Stress of the sort after a speculative count that the caller voids (tests/test_binned_gpu.py::
+"""Stress of the sort after a speculative count that the caller voids (tests/test_zz_sort_gpu.py::
 test_predicted_bin_count_equals_the_count_pass, last part), repeated.  usage: stress_sort2.py [reps=40]"""
 import os
 import sys
