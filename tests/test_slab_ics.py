@@ -282,8 +282,10 @@ def _gloo_ics_worker(rank, world, port, base, name, out):
     dist.destroy_process_group()
 
 
-def test_generate_slab_gloo_world2(tmp_path):
-    """the same over torch.distributed (gloo, two processes): the transposes go through all_to_all_single"""
+@pytest.mark.parametrize("name", ["lpt2", "lpt3_dealiased"])
+def test_generate_slab_gloo_world2(name, tmp_path):
+    """the same over torch.distributed (gloo, two processes): the transposes go through all_to_all_single, the ky rows
+    of the dealiasing grid through all_to_all_single with split sizes"""
     import socket
     import torch.multiprocessing as mp
     with socket.socket() as s:
@@ -291,9 +293,9 @@ def test_generate_slab_gloo_world2(tmp_path):
         port = s.getsockname()[1]
     with mp.Manager() as mgr:
         out = mgr.dict()
-        mp.spawn(_gloo_ics_worker, args=(2, port, str(tmp_path), "lpt2", out), nprocs=2, join=True)
+        mp.spawn(_gloo_ics_worker, args=(2, port, str(tmp_path), name, out), nprocs=2, join=True)
         out = dict(out)
-    _check_against_reference("lpt2", [out[0], out[1]])
+    _check_against_reference(name, [out[0], out[1]])
 
 
 @pytest.mark.gpu
