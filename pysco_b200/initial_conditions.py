@@ -332,7 +332,7 @@ class SlabLayout:
         the rows a rank sends to each destination, and receives from each source, are contiguous and in order."""
         P, r = self.P, self.rank
         n, nyl = x.shape[0], x.shape[1]
-        if n_to % P or (n_to // P) * P != n_to:
+        if n_to % P:
             raise ValueError(f"dealiasing grid {n_to} cannot be split over {P} ranks")
         m = min(n, n_to) // 2
         nyl_to, nz_to = n_to // P, n_to // 2 + 1

@@ -18,7 +18,29 @@ for p in (ROOT, os.path.join(ROOT, "tests"), os.path.join(ROOT, "tests", "golden
         sys.path.insert(0, p)
 import cases  # noqa: E402
 
-G = np.load(os.path.join(ROOT, "tests", "golden", "ics.npz"))
+with np.load(os.path.join(ROOT, "tests", "golden", "ics.npz")) as _z:
+    G = {k: _z[k] for k in _z.files}     # materialised: NpzFile reads lazily through one zip handle, not thread-safe
+
+
+def _ranks(P, fn):
+    """fn(comm) on P virtual ranks (threads); the first real exception of a rank aborts the others' barriers and is
+    re-raised here (no rank is left waiting)"""
+    from pysco_b200.slab import ThreadComm
+    errs = []
+
+    def work(comm):
+        try:
+            fn(comm)
+        except threading.BrokenBarrierError:
+            pass
+        except BaseException as e:  # noqa: BLE001
+            errs.append(e)
+            comm.w.barrier.abort()
+    ts = [threading.Thread(target=work, args=(c,)) for c in ThreadComm.world(P)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    if errs:
+        raise errs[0]
 
 
 @pytest.mark.parametrize("N,seed", [(8, 5), (12, 6), (32, 1)])
@@ -64,9 +86,7 @@ def test_distributed_transforms_match_rfftn(P):
         mine = x[L.x0:L.x0 + L.nxl].clone()
         s = L.fft(mine)
         out[comm.rank] = (s, L.ifft(s.clone()), L.y0, L.nyl, L.x0, L.nxl)
-    ts = [threading.Thread(target=rank, args=(c,)) for c in ThreadComm.world(P)]
-    [t.start() for t in ts]
-    [t.join(60) for t in ts]
+    _ranks(P, rank)
     assert len(out) == P
     scale = float(spec.abs().max())
     for r, (s, back, y0, nyl, x0, nxl) in out.items():
@@ -108,23 +128,17 @@ def _check_against_reference(name, parts):
 def test_generate_slab_matches_reference(name, P, tmp_path):
     from pysco_b200 import initial_conditions as ic
     from pysco_b200.slab import ThreadComm
-    out, err = {}, []
+    out = {}
     param0 = _param_of(name, tmp_path)      # written once (the power-spectrum file), copied per rank
+    tables = _tables_of(name)
 
     def rank(comm):
-        try:
-            param = param0.copy()
-            pos, vel, ids = ic.generate_slab(param, _tables_of(name), comm, device="cpu")
-            n3 = 16 ** 3 // P
-            assert pos.shape == (n3, 3) and ids[0] == comm.rank * n3 and ids[-1] == (comm.rank + 1) * n3 - 1
-            out[comm.rank] = (pos.numpy(), vel.numpy(), ids.numpy())
-        except Exception as e:   # noqa: BLE001
-            err.append(e)
-            raise
-    ts = [threading.Thread(target=rank, args=(c,)) for c in ThreadComm.world(P)]
-    [t.start() for t in ts]
-    [t.join(120) for t in ts]
-    assert not err and len(out) == P, err
+        pos, vel, ids = ic.generate_slab(param0.copy(), tables, comm, device="cpu")
+        n3 = 16 ** 3 // P
+        assert pos.shape == (n3, 3) and ids[0] == comm.rank * n3 and ids[-1] == (comm.rank + 1) * n3 - 1
+        out[comm.rank] = (pos.numpy(), vel.numpy(), ids.numpy())
+    _ranks(P, rank)
+    assert len(out) == P
     _check_against_reference(name, [out[r] for r in range(P)])
     # the layout is per thread and gone afterwards: the single-domain generator is untouched
     assert ic._layout() is ic._WHOLE
@@ -144,21 +158,13 @@ def test_slab_pad_and_trim_match_the_whole_grid(P):
     y = torch.from_numpy((rng.standard_normal(tuple(big.shape)) + 1j * rng.standard_normal(tuple(big.shape)))
                          .astype(np.complex64))
     small = ic.trim(y)
-    out, errs = {}, []
+    out = {}
 
     def rank(comm):
-        try:
-            L = ic.SlabLayout(comm, N)
-            r, nyl, nye = comm.rank, N // P, Ne // P
-            out[r] = (L.regrid(x[:, r * nyl:(r + 1) * nyl].clone(), Ne), L.regrid(y[:, r * nye:(r + 1) * nye].clone(), N))
-        except BaseException as e:  # noqa: BLE001
-            errs.append(e)
-            comm.w.barrier.abort()
-    ts = [threading.Thread(target=rank, args=(c,)) for c in ThreadComm.world(P)]
-    [t.start() for t in ts]
-    [t.join() for t in ts]
-    if errs:
-        raise errs[0]
+        L = ic.SlabLayout(comm, N)
+        r, nyl, nye = comm.rank, N // P, Ne // P
+        out[r] = (L.regrid(x[:, r * nyl:(r + 1) * nyl].clone(), Ne), L.regrid(y[:, r * nye:(r + 1) * nye].clone(), N))
+    _ranks(P, rank)
     for r in range(P):
         assert torch.equal(out[r][0], big[:, r * (Ne // P):(r + 1) * (Ne // P)])
         assert torch.equal(out[r][1], small[:, r * (N // P):(r + 1) * (N // P)])
@@ -169,18 +175,16 @@ def test_generate_slab_dealiased_needs_a_divisible_grid(tmp_path):
     from pysco_b200 import initial_conditions as ic
     from pysco_b200.slab import ThreadComm
     param = _param_of("lpt3_dealiased", tmp_path)
-    errs = []
-
-    def rank(comm):
-        try:
-            ic.generate_slab(param.copy(), _tables_of("lpt3_dealiased"), comm, device="cpu")
-        except BaseException as e:  # noqa: BLE001
-            errs.append(e)
-            comm.w.barrier.abort()
-    ts = [threading.Thread(target=rank, args=(c,)) for c in ThreadComm.world(16)]
-    [t.start() for t in ts]
-    [t.join() for t in ts]
-    assert any(isinstance(e, NotImplementedError) for e in errs)
+    ic._tls.layout = ic.SlabLayout(ThreadComm.world(16)[3], 16)
+    try:
+        with pytest.raises(NotImplementedError):
+            ic._dealias_in(param, torch.zeros((16, 1, 9), dtype=torch.complex64))
+        ic._tls.layout = ic.SlabLayout(ThreadComm.world(8)[3], 16)       # 24 planes over 8 ranks: fine
+        param["dealiased_ICS"] = False
+        (x,) = ic._dealias_in(param, torch.zeros((16, 2, 9), dtype=torch.complex64))
+        assert x.shape == (16, 2, 9)
+    finally:
+        del ic._tls.layout
     assert ic._layout() is ic._WHOLE
 
 
@@ -304,22 +308,15 @@ def test_generate_slab_matches_reference_gpu(name, tmp_path):
     """the per-slab generator on CUDA tensors (cuFFT through torch.fft), 2 virtual ranks sharing cuda:0"""
     from pysco_b200 import initial_conditions as ic
     from pysco_b200.slab import ThreadComm
-    out, errs = {}, []
+    out = {}
     param0 = _param_of(name, tmp_path)
+    tables = _tables_of(name)
 
     def rank(comm):
-        try:
-            pos, vel, ids = ic.generate_slab(param0.copy(), _tables_of(name), comm)
-            assert pos.is_cuda
-            out[comm.rank] = (pos.cpu().numpy(), vel.cpu().numpy(), ids.cpu().numpy())
-        except BaseException as e:  # noqa: BLE001
-            errs.append(e)
-            comm.w.barrier.abort()
-    ts = [threading.Thread(target=rank, args=(c,)) for c in ThreadComm.world(2)]
-    [t.start() for t in ts]
-    [t.join() for t in ts]
-    if errs:
-        raise errs[0]
+        pos, vel, ids = ic.generate_slab(param0.copy(), tables, comm)
+        assert pos.is_cuda
+        out[comm.rank] = (pos.cpu().numpy(), vel.cpu().numpy(), ids.cpu().numpy())
+    _ranks(2, rank)
     _check_against_reference(name, [out[0], out[1]])
 
 
