@@ -234,8 +234,8 @@ def test_slab_run_generates_its_initial_conditions_per_slab(tmp_path):
     pa, va = (t.numpy() for t in a[0])
     pb, vb = (t.numpy() for t in b[0])
     d = np.abs(pa - pb)
-    assert np.minimum(d, 1 - d).max() < 2e-5
-    assert np.abs(va - vb).max() < 1e-4 * np.abs(vb).max()
+    assert np.minimum(d, 1 - d).max() < 1e-4           # a cell is 6e-2; the ICs differ by transform rounding only
+    assert np.abs(va - vb).max() < 1e-3 * np.abs(vb).max()
     assert len(glob.glob(str(tmp_path / "slab" / "output_0000[12]" / "particles_*.parquet"))) == 2
 
 
@@ -329,8 +329,11 @@ def test_slab_run_per_slab_ics_gpu(tmp_path):
     pa, va = (t.numpy() for t in a[0])
     pb, vb = (t.numpy() for t in b[0])
     d = np.abs(pa - pb)
-    assert np.minimum(d, 1 - d).max() < 5e-5, np.minimum(d, 1 - d).max()
-    assert np.abs(va - vb).max() < 5e-4 * np.abs(vb).max()
+    # two runs whose initial conditions differ by float32 rounding of the transforms (1e-7), ~45 steps of growth and
+    # float atomics in the deposit: measured 1e-5 box units / 2e-4 of max |v| (128^3 over NCCL,
+    # profiles/r02_slab_ics_nccl_n2.txt); wrong initial conditions are off by a cell (3e-2) or more
+    assert np.minimum(d, 1 - d).max() < 2e-4, np.minimum(d, 1 - d).max()
+    assert np.abs(va - vb).max() < 2e-3 * np.abs(vb).max()
 
 
 def test_command_line_runs_on_slabs_under_torchrun(tmp_path, monkeypatch):
